@@ -1,0 +1,223 @@
+/*
+ * xevd_b200.h -- C ABI of the B200-native XEVD picture-reconstruction path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no torch / C++ types.
+ * Everything below replaces, at frame granularity, what the reference reaches through its
+ * internal function tables after entropy decode has filled XEVD_CU_DATA:
+ *
+ *   reference seam (file:line)                                  -> entry point here
+ *   -----------------------------------------------------------------------------------------
+ *   xevd_platform_init / xevdm_platform_init table wiring        -> xb200_create / xb200_destroy
+ *     (src_base/xevd.c:2074-2149, src_main/xevdm.c:3388-3479)
+ *   PICBUF_ALLOCATOR.fn_alloc / fn_free (xevd_def.h:685-705,      -> xb200_pic_alloc / xb200_pic_free
+ *     installed src_base/xevd.c:335-342)                             xb200_pic_upload / xb200_pic_download
+ *   xevd_ctu_row_rec_mt -> xevd_recon_tree -> xevd_recon_unit     -> xb200_recon_frame[_dev]
+ *     (src_base/xevd.c:1470,1019,678; src_main/xevdm.c:2463,1854,1230):
+ *     cu_init + coef_rect_to_series + xevd_sub_block_itdq + xevd_mc /
+ *     xevd_ipred + xevd_recon_yuv + xevd_set_dec_info
+ *   ctx->fn_deblock = xevd_deblock / xevdm_deblock                -> xb200_deblock
+ *     (src_base/xevd.c:1116, src_main/xevdm.c:2048)
+ *   mctx->fn_alf = xevd_alf (src_main/xevdm.c:2105)               -> xb200_alf
+ *   ctx->fn_picbuf_expand = xevd_picbuf_expand                    -> xb200_pad
+ *     (src_base/xevd_util.c:1487)
+ *   leaf tables xevd_func_mc_l/c, fn_itxb, xevdm_fn_itx,          -> xb200_mc_blocks / xb200_itdq_blocks
+ *     xevd_func_itrans (per-block CPU callbacks; kept only as        (batched micro-benchmark entry points,
+ *     batched entry points)                       BASELINE.json config 5)
+ *
+ * All entry points return XEVD-style codes: >= 0 success, < 0 failure (inc/xevd.h:50-77).
+ * There is no CPU fallback: every call fails with XB200_ERR_NO_DEVICE when no CUDA device
+ * is usable.
+ */
+#ifndef XEVD_B200_H
+#define XEVD_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XB200_ABI_VERSION 1
+
+/* error codes: same numeric values as inc/xevd.h:50-73 where a counterpart exists */
+#define XB200_OK                     0
+#define XB200_ERR                   (-1)
+#define XB200_ERR_INVALID_ARGUMENT  (-101)
+#define XB200_ERR_OUT_OF_MEMORY     (-102)
+#define XB200_ERR_UNSUPPORTED       (-104)
+#define XB200_ERR_UNEXPECTED        (-105)
+#define XB200_ERR_NO_DEVICE         (-401)   /* no CUDA device / driver: there is no CPU path */
+#define XB200_ERR_CUDA              (-402)   /* a CUDA runtime call failed; see xb200_last_error */
+
+typedef int16_t xb200_pel;           /* pel == s16 always (src_base/xevd_port.h:51) */
+
+/* prediction modes of a CU work item (values follow xevd_def.h:287-290 for the first three) */
+#define XB200_MODE_INTRA   0
+#define XB200_MODE_INTER   1         /* MODE_INTER / MODE_SKIP / MODE_DIR once motion is resolved */
+#define XB200_MODE_IBC     4
+#define XB200_MODE_AFFINE  5
+
+/* XB200_CU.flags */
+#define XB200_CUF_LUMA     0x01      /* CU carries luma   (tree_cons != TREE_C) */
+#define XB200_CUF_CHROMA   0x02      /* CU carries chroma (tree_cons != TREE_L) */
+#define XB200_CUF_SKIP     0x04      /* MODE_SKIP: published to map_scu (MCU_SET_SF) */
+#define XB200_CUF_DMVR     0x08      /* DMVR enabled for this CU (Main) */
+#define XB200_CUF_ATS_INTRA 0x10     /* ats_intra_cu */
+#define XB200_CUF_AFF6     0x20      /* 6-parameter affine (vertex_num == 3) */
+
+/*
+ * One fully-resolved coding unit: what xevd_recon_unit holds in XEVD_CORE after cu_init and motion
+ * derivation (src_base/xevd.c:567-730), flattened.  32 bytes, little endian, no pointers.
+ * The producer is the host motion-derivation pass or a synthetic generator.
+ */
+typedef struct XB200_CU {
+    uint16_t x, y;            /* luma position of the CU's top-left sample                       */
+    uint8_t  log2w, log2h;    /* 2..7                                                            */
+    uint8_t  mode;            /* XB200_MODE_*                                                    */
+    uint8_t  flags;           /* XB200_CUF_*                                                     */
+    uint8_t  qp_y, qp_u, qp_v;/* XEVD_CU_DATA.qp_y/u/v: already include 6*(bit_depth-8)          */
+    uint8_t  qp_map;          /* core->qp as stored in map_scu (deblock QP)                      */
+    int8_t   refi[2];         /* inter: reference indices (list0, list1), < 0 = unused
+                                 intra: ipm[0] (luma mode), ipm[1] (chroma mode)                 */
+    uint16_t cbf;             /* nnz_sub: bits 0-3 luma 64x64 sub-blocks, 4-7 Cb, 8-11 Cr
+                                 (bit (j<<1)|i as xevd_eco.c:618-625); for CUs <= 64 only bit 0  */
+    int16_t  mv[2][2];        /* inter: final UNCLIPPED motion vectors [list][x,y], quarter-pel
+                                 intra / affine: mv[1] holds a uint32 index into the extension
+                                 array (XB200_CU_EXT), mv[0] is unused                           */
+    uint8_t  ats;             /* bits 0-1 ats_mode_h/v, bits 2-7 ats_inter_info                  */
+    uint8_t  avail;           /* avail_lr (bits 0-1) | up-left available (bit 2)                 */
+    uint16_t reserved;
+    uint32_t coef_off;        /* offset (in int16 units) of this CU's coefficients inside the
+                                 coefficient stream: [Y w*h][Cb w*h/4][Cr w*h/4], CU-raster;
+                                 planes whose cbf bits are all 0 are absent (no bytes)           */
+} XB200_CU;
+
+/* extension record, 32 bytes: meaning depends on XB200_CU.mode */
+typedef struct XB200_CU_EXT {
+    union {
+        struct {              /* XB200_MODE_INTRA: neighbour availability, one bit per SCU */
+            uint64_t up;      /* bit i: SCU i of the row above, i in [0, scuw+scuh)  (up then up-right)   */
+            uint64_t left;    /* bit i: SCU i of the column left, i in [0, scuh+scuw)                    */
+            uint64_t right;   /* Main/SUCO: column right                                                 */
+            uint64_t pad;
+        } intra;
+        struct {              /* XB200_MODE_AFFINE: control point MVs [list][vertex][x,y], 1/4 pel       */
+            int16_t cp[2][3][2];
+            int16_t pad[4];
+        } affine;
+    } u;
+} XB200_CU_EXT;
+
+/* sequence / picture level switches that change arithmetic */
+typedef struct XB200_PARAMS {
+    int32_t w, h;                 /* luma picture size in samples (ctx->w, ctx->h)                     */
+    int32_t bit_depth_luma;       /* 8..14                                                             */
+    int32_t bit_depth_chroma;
+    int32_t chroma_format_idc;    /* only 1 (4:2:0) is implemented; others -> XB200_ERR_UNSUPPORTED     */
+    int32_t log2_ctu;             /* ctx->log2_max_cuwh: 6 for Baseline, 5..7 Main                      */
+    int32_t tool_admvp;           /* 1/16-pel interpolation tables (xevdm_mc.c:121-175)                 */
+    int32_t tool_iqt;             /* IQT transform + dq table {..72} (xevdm_itdq.c:423-706)             */
+    int32_t tool_ats;
+    int32_t tool_addb;
+    int32_t tool_alf;
+    int32_t tool_htdf;
+    int32_t tool_dmvr;
+    int32_t tool_eipd;
+    int32_t tool_affine;
+    int32_t tool_ibc;
+    int32_t slice_qp;             /* sh.qp (HTDF, T11)                                                  */
+    int32_t qp_u_offset, qp_v_offset;        /* pic_qp_u/v_offset used by deblock chroma QP            */
+    int32_t deblock_alpha_offset, deblock_beta_offset;
+    int32_t poc;                  /* POC of the current picture                                         */
+    int32_t reserved[10];
+} XB200_PARAMS;
+
+typedef struct xb200_ctx xb200_ctx;   /* device context: stream, uploaded tables, scratch              */
+typedef struct xb200_pic xb200_pic;   /* device picture: 3 padded planes + per-SCU maps                 */
+
+/* geometry of a device picture; the padded layout follows xevd_imgb_create (xevd_util.c:153-230):
+ * pad 144 / 72 on every side, strides in pels                                                          */
+typedef struct XB200_PIC_INFO {
+    int32_t w_l, h_l, w_c, h_c;
+    int32_t s_l, s_c;             /* strides in pels                                                    */
+    int32_t pad_l, pad_c;
+    void   *dev_y, *dev_u, *dev_v;/* device addresses of sample (0,0) of each plane                     */
+    void   *dev_map_mv;           /* int16[w_scu*h_scu][2][2]                                           */
+    void   *dev_map_refi;         /* int8 [w_scu*h_scu][2]                                              */
+    void   *dev_map_scu;          /* uint32[w_scu*h_scu], bit layout xevd_def.h:372-437                 */
+    int32_t w_scu, h_scu;
+    int32_t poc;
+} XB200_PIC_INFO;
+
+/* ---- context ------------------------------------------------------------------------------------- */
+int  xb200_abi_version(void);
+int  xb200_device_count(void);                            /* < 0 on driver failure                       */
+xb200_ctx *xb200_create(int device, int *err);            /* NULL + *err on failure                      */
+void xb200_destroy(xb200_ctx *ctx);
+const char *xb200_last_error(xb200_ctx *ctx);             /* last CUDA error string (may be "")          */
+int  xb200_sync(xb200_ctx *ctx);                          /* wait for the context's stream               */
+void *xb200_stream(xb200_ctx *ctx);                       /* the cudaStream_t all launches go to         */
+int  xb200_set_stream(xb200_ctx *ctx, void *cuda_stream); /* use a caller-owned stream                   */
+long long xb200_launch_count(xb200_ctx *ctx);             /* kernels launched by this context so far     */
+
+/* ---- pictures (PICBUF_ALLOCATOR) ------------------------------------------------------------------ */
+xb200_pic *xb200_pic_alloc(xb200_ctx *ctx, int w, int h, int *err);
+void xb200_pic_free(xb200_ctx *ctx, xb200_pic *pic);
+int  xb200_pic_info(xb200_pic *pic, XB200_PIC_INFO *info);
+int  xb200_pic_set_poc(xb200_pic *pic, int poc);
+/* host planes are tightly described by (ptr, stride in pels) and hold w x h valid samples;
+ * upload copies them into the padded device planes (borders are NOT replicated: call xb200_pad) */
+int  xb200_pic_upload(xb200_ctx *ctx, xb200_pic *pic,
+                      const xb200_pel *y, int sy, const xb200_pel *u, int su, const xb200_pel *v, int sv);
+int  xb200_pic_download(xb200_ctx *ctx, xb200_pic *pic,
+                        xb200_pel *y, int sy, xb200_pel *u, int su, xb200_pel *v, int sv);
+/* full padded planes (incl. borders), for checking xb200_pad against xevd_picbuf_expand */
+int  xb200_pic_download_padded(xb200_ctx *ctx, xb200_pic *pic, xb200_pel *y, xb200_pel *u, xb200_pel *v);
+int  xb200_pic_download_maps(xb200_ctx *ctx, xb200_pic *pic, int16_t *map_mv, int8_t *map_refi, uint32_t *map_scu);
+
+/* ---- per-picture reconstruction (xevd_ctu_row_rec_mt) ---------------------------------------------- */
+/*
+ * Reconstruct every CU of one picture.  `cus` are in decoding order; `ctu_first[k]` is the index of the
+ * first CU of CTU k (raster CTU order), `ctu_first[n_ctu] == n_cu`.  `refs[l][i]` is the device picture
+ * ctx->refp[i][l].pic.  Host variant: all array arguments are HOST pointers; the call stages them
+ * through pinned memory and is asynchronous on the context stream.  _dev variant: device pointers.
+ */
+int  xb200_recon_frame(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
+                       xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
+                       const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                       const XB200_CU_EXT *ext, int n_ext,
+                       const int16_t *coef, size_t n_coef);
+int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
+                       xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
+                       const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
+                       const void *d_ext, int n_ext,
+                       const void *d_coef, size_t n_coef, int has_intra);
+
+/* ---- picture-wide in-loop filters ------------------------------------------------------------------ */
+/* edge flags, one byte per SCU */
+#define XB200_EDGE_LEFT   0x01    /* a CU/TU boundary runs along the left side of this SCU           */
+#define XB200_EDGE_TOP    0x02    /* ... along the top side                                          */
+int  xb200_deblock(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
+                   xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
+                   const uint8_t *edge_flags /* host, w_scu*h_scu */);
+int  xb200_deblock_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
+                   xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
+                   const void *d_edge_flags);
+int  xb200_pad(xb200_ctx *ctx, xb200_pic *pic);           /* xevd_picbuf_expand                        */
+
+/* ---- batched leaf kernels (micro-benchmarks, BASELINE.json config 5) ------------------------------ */
+/* n blocks of (1<<log2w) x (1<<log2h) coefficients, contiguous, in place semantics of
+ * xevd_itdq (xevd_itdq.c:494-542): dequant with `scale` then 2-D inverse DCT-2.  iqt selects the Main
+ * IQT variant.  d_in / d_out are device pointers.                                                      */
+int  xb200_itdq_blocks_dev(xb200_ctx *ctx, const void *d_in, void *d_out, int n, int log2w, int log2h,
+                           int qp, int bit_depth, int iqt);
+/* n luma (is_chroma=0) or chroma blocks of w x h: d_mv = int32[n][4] {gmv_x, gmv_y (1/16 or 1/32 pel,
+ * absolute, already clipped), ori_mv_x, ori_mv_y}; output blocks contiguous w*h each.                  */
+int  xb200_mc_blocks_dev(xb200_ctx *ctx, xb200_pic *ref, int plane, const void *d_mv, void *d_out, int n,
+                         int w, int h, int bit_depth, int main_tables);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEVD_B200_H */

@@ -1,0 +1,74 @@
+/*
+ * oracle/ -- CPU restatement of the XEVD reconstruction hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under xevd_b200/ may include, link or call this code; it
+ * exists so that tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg can check the CUDA
+ * path.  Parity status: PINNED -- every function here is compared against the unmodified reference
+ * compiled from /root/reference (oracle/_ref/libxevd_ref.so, built by oracle/Makefile) in
+ * tests/test_oracle_vs_ref.py, and against the golden vectors generated from that build
+ * (tests/golden/, script tests/golden/make_golden.py).  The reference ships no test vectors of its own
+ * (SURVEY 4, 8c).
+ *
+ * Each function cites the reference file:line whose arithmetic it restates.  The code is written
+ * from the arithmetic, in direct (matrix / loop) form; it is not a copy of the reference's
+ * butterflies or SIMD.
+ */
+#ifndef ORC_COMMON_H
+#define ORC_COMMON_H
+
+#include <stdint.h>
+#include <stddef.h>
+#include "../include/xevd_b200.h"
+
+typedef int16_t pel;
+
+/* a host picture in the reference's padded layout (xevd_util.c:153-230, 250-363) */
+typedef struct ORC_PIC {
+    pel *y, *u, *v;          /* sample (0,0) of each plane                                    */
+    int  s_l, s_c;           /* strides in pels                                               */
+    int  w_l, h_l, w_c, h_c;
+    int  pad_l, pad_c;
+    int  poc;
+    int16_t  *map_mv;        /* [h_scu*w_scu][2][2]                                           */
+    int8_t   *map_refi;      /* [h_scu*w_scu][2]                                              */
+    uint32_t *map_scu;       /* [h_scu*w_scu]                                                 */
+    int  w_scu, h_scu;
+} ORC_PIC;
+
+static inline int orc_clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int orc_min(int a, int b) { return a < b ? a : b; }
+static inline int orc_max(int a, int b) { return a > b ? a : b; }
+
+/* orc_tables.c */
+const int8_t  *orc_dct2_matrix(int log2n);          /* [n][n], row k = basis k (xevd_tbl_tm2..64)   */
+const int16_t *orc_mc_luma_taps(int main_tables);   /* [16][8]                                       */
+const int16_t *orc_mc_chroma_taps(int main_tables); /* [32][4]                                       */
+const int16_t *orc_ats_matrix(int dst7, int log2n); /* inverse ATS matrices, [n][n] (xevd_tbl_inv_tr*) */
+int orc_dq_scale(int qp, int iqt);
+
+/* orc_mc.c */
+void orc_mc_luma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x, int ori_mv_y,
+                 pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables);
+void orc_mc_chroma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x, int ori_mv_y,
+                   pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables);
+void orc_mv_clip(int x, int y, int pic_w, int pic_h, int w, int h, const int8_t refi[2],
+                 const int16_t mv[2][2], int16_t mv_t[2][2]);
+/* full inter prediction of one CU: pred[c] is w*h (luma) / (w/2)*(h/2) (chroma), CU raster */
+void orc_inter_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const int8_t refi[2],
+                    const int16_t mv[2][2], const ORC_PIC *const *refs_l0, const ORC_PIC *const *refs_l1,
+                    pel *pred_y, pel *pred_u, pel *pred_v);
+
+/* orc_itdq.c */
+void orc_dequant(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);
+void orc_inv_dct2(int16_t *coef, int log2w, int log2h, int bit_depth, int iqt);
+void orc_itdq_block(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);
+/* whole-CU residual (xevd_sub_block_itdq / xevdm_sub_block_itdq): coef[c] CU-raster, in place */
+void orc_itdq_cu(const XB200_PARAMS *prm, const XB200_CU *cu, int16_t *cy, int16_t *cu_, int16_t *cv);
+
+/* orc_recon.c */
+int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
+                    const ORC_PIC *const *refs_l0, int n_l0, const ORC_PIC *const *refs_l1, int n_l1,
+                    const XB200_CU *cus, int n_cu, const XB200_CU_EXT *ext, const int16_t *coef);
+void orc_pad(ORC_PIC *pic);
+
+#endif

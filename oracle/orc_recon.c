@@ -1,0 +1,98 @@
+/*
+ * Picture-level reconstruction driver and border padding.  TEST INFRASTRUCTURE ONLY (orc_common.h).
+ * Restates the per-CU sequence of xevd_recon_unit (src_base/xevd.c:678-756; Main
+ * src_main/xevdm.c:1230-1405) on fully-resolved CU work items: residual (itdq) -> prediction ->
+ * rec = clip(pred + resid) (src_base/xevd_recon.c:36-68) -> publish per-SCU maps
+ * (xevd_set_dec_info, src_base/xevd_util.c:1574-1650).
+ */
+#include <string.h>
+#include <stdlib.h>
+#include "orc_common.h"
+
+static void put_block(pel *rec, int s_rec, const pel *pred, const int16_t *res, int w, int h, int bd)
+{
+    const int maxv = (1 << bd) - 1;
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            /* t0 is an s16 in the reference (xevd_recon.c:40,60): the sum wraps to 16 bits first */
+            int16_t t = (int16_t)((res ? res[i * w + j] : 0) + pred[i * w + j]);
+            rec[i * s_rec + j] = (pel)orc_clip3(0, maxv, t);
+        }
+}
+
+static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu)
+{
+    const int x0 = cu->x >> 2, y0 = cu->y >> 2, nw = 1 << (cu->log2w - 2), nh = 1 << (cu->log2h - 2);
+    const int intra = cu->mode == XB200_MODE_INTRA;
+    for (int j = 0; j < nh; j++)
+        for (int i = 0; i < nw; i++) {
+            const int p = (y0 + j) * cur->w_scu + x0 + i;
+            /* MCU_SET_IF_SN_QP | CBFL | SF | COD (xevd_def.h:372-437); slice number 0 */
+            uint32_t m = ((uint32_t)(cu->qp_map & 0x7f) << 16) | ((uint32_t)intra << 15) | (1u << 31);
+            if (cu->cbf & 1) m |= 1u << 24;
+            if (cu->flags & XB200_CUF_SKIP) m |= 1u << 23;
+            cur->map_scu[p] = m;
+            for (int l = 0; l < 2; l++) {
+                cur->map_refi[p * 2 + l] = intra ? -1 : cu->refi[l];
+                cur->map_mv[(p * 2 + l) * 2 + 0] = intra ? 0 : cu->mv[l][0];
+                cur->map_mv[(p * 2 + l) * 2 + 1] = intra ? 0 : cu->mv[l][1];
+            }
+        }
+}
+
+int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
+                    const ORC_PIC *const *refs_l0, int n_l0, const ORC_PIC *const *refs_l1, int n_l1,
+                    const XB200_CU *cus, int n_cu, const XB200_CU_EXT *ext, const int16_t *coef)
+{
+    pel     *pred = (pel *)malloc(3 * 128 * 128 * sizeof(pel));
+    int16_t *res  = (int16_t *)malloc(3 * 128 * 128 * sizeof(int16_t));
+    (void)ext; (void)n_l0; (void)n_l1;
+    for (int n = 0; n < n_cu; n++) {
+        const XB200_CU *cu = &cus[n];
+        const int w = 1 << cu->log2w, h = 1 << cu->log2h, cw = w >> 1, ch = h >> 1;
+        pel *py = pred, *pu = pred + w * h, *pv = pu + cw * ch;
+        int16_t *ry = res, *ru = res + w * h, *rv = ru + cw * ch;
+        const int16_t *c = coef + cu->coef_off;
+        const int has_y = (cu->cbf & 0x00f) != 0, has_u = (cu->cbf & 0x0f0) != 0, has_v = (cu->cbf & 0xf00) != 0;
+
+        if (has_y) { memcpy(ry, c, sizeof(int16_t) * w * h); c += w * h; }
+        if (has_u) { memcpy(ru, c, sizeof(int16_t) * cw * ch); c += cw * ch; }
+        if (has_v) { memcpy(rv, c, sizeof(int16_t) * cw * ch); }
+        orc_itdq_cu(prm, cu, ry, ru, rv);
+
+        if (cu->mode == XB200_MODE_INTER) {
+            orc_inter_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, py, pu, pv);
+        } else {
+            free(pred); free(res);
+            return XB200_ERR_UNSUPPORTED;
+        }
+        put_block(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma);
+        /* the reference passes the LUMA bit depth to all three planes (xevd_recon.c:70-91) */
+        put_block(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma);
+        put_block(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma);
+        publish_maps(prm, cur, cu);
+    }
+    free(pred); free(res);
+    return XB200_OK;
+}
+
+/* xevd_picbuf_expand -> picbuf_expand (xevd_util.c:365-427): replicate the outermost samples into the
+ * pad_l / pad_c wide border, rows first then whole rows up and down */
+static void pad_plane(pel *a, int s, int w, int h, int pad)
+{
+    for (int y = 0; y < h; y++) {
+        pel *row = a + y * s;
+        for (int x = 1; x <= pad; x++) { row[-x] = row[0]; row[w - 1 + x] = row[w - 1]; }
+    }
+    for (int y = 1; y <= pad; y++) {
+        memcpy(a - y * s - pad, a - pad, sizeof(pel) * (w + 2 * pad));
+        memcpy(a + (h - 1 + y) * s - pad, a + (h - 1) * s - pad, sizeof(pel) * (w + 2 * pad));
+    }
+}
+
+void orc_pad(ORC_PIC *pic)
+{
+    pad_plane(pic->y, pic->s_l, pic->w_l, pic->h_l, pic->pad_l);
+    pad_plane(pic->u, pic->s_c, pic->w_c, pic->h_c, pic->pad_c);
+    pad_plane(pic->v, pic->s_c, pic->w_c, pic->h_c, pic->pad_c);
+}

@@ -1,0 +1,183 @@
+"""ctypes front-end of the CPU oracle (oracle/liboracle.so) and of the compiled reference
+(oracle/_ref/libxevd_ref.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs.
+The product package (xevd_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from xevd_b200.abi import CU_DTYPE, EXT_DTYPE, Params
+from xevd_b200.frame import CuList, HostPicture
+
+HERE = Path(__file__).resolve().parent
+ORACLE_SO = HERE / "liboracle.so"
+REF_SO = HERE / "_ref" / "libxevd_ref.so"
+
+
+class OrcPic(C.Structure):
+    """struct ORC_PIC (oracle/orc_common.h)"""
+
+    _fields_ = [
+        ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+        ("s_l", C.c_int), ("s_c", C.c_int),
+        ("w_l", C.c_int), ("h_l", C.c_int), ("w_c", C.c_int), ("h_c", C.c_int),
+        ("pad_l", C.c_int), ("pad_c", C.c_int), ("poc", C.c_int),
+        ("map_mv", C.c_void_p), ("map_refi", C.c_void_p), ("map_scu", C.c_void_p),
+        ("w_scu", C.c_int), ("h_scu", C.c_int),
+    ]
+
+
+def orc_pic(p: HostPicture) -> OrcPic:
+    o = OrcPic()
+    o.y, o.u, o.v = p.y.ctypes.data, p.u.ctypes.data, p.v.ctypes.data
+    o.s_l, o.s_c = p.s_l, p.s_c
+    o.w_l, o.h_l, o.w_c, o.h_c = p.w, p.h, p.w_c, p.h_c
+    o.pad_l, o.pad_c, o.poc = p.pad_l, p.pad_c, p.poc
+    o.map_mv, o.map_refi, o.map_scu = p.map_mv.ctypes.data, p.map_refi.ctypes.data, p.map_scu.ctypes.data
+    o.w_scu, o.h_scu = p.w_scu, p.h_scu
+    return o
+
+
+def build(force: bool = False) -> None:
+    """compile the C restatement (and the reference harness when /root/reference is present)"""
+    subprocess.run(["make", "-s", "-C", str(HERE), "-j8", "all"] + (["-B"] if force else []), check=True)
+
+
+def _ptr_array(pics):
+    keep = [orc_pic(p) for p in pics]
+    arr = (C.POINTER(OrcPic) * max(1, len(keep)))()
+    for i, k in enumerate(keep):
+        arr[i] = C.pointer(k)
+    return arr, keep
+
+
+class _Backend:
+    """common call surface of liboracle.so (prefix orc_) and libxevd_ref.so (prefix ref_)"""
+
+    def __init__(self, path: Path, prefix: str):
+        if not path.exists():
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(str(path))
+        self.prefix = prefix
+        L = self.lib
+        for name in ("mc_luma", "mc_chroma"):
+            f = getattr(L, prefix + name)
+            f.restype = None
+            f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        f = getattr(L, prefix + "itdq_block")
+        f.restype = None
+        f.argtypes = [C.c_void_p] + [C.c_int] * 5
+        f = getattr(L, prefix + "recon_frame")
+        f.restype = C.c_int
+        f.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        f = getattr(L, prefix + "pad")
+        f.restype = None
+        f.argtypes = [C.POINTER(OrcPic)]
+
+    # -- leaf kernels -----------------------------------------------------------------------
+    def mc(self, plane: np.ndarray, origin_xy, gmv, ori_mv, w, h, bit_depth, chroma=False, main_tables=False):
+        """plane: 2-D int16 array; origin_xy: array index of sample (0,0); gmv absolute (1/16 or 1/32 pel)"""
+        assert plane.dtype == np.int16 and plane.flags.c_contiguous
+        base = plane.ctypes.data + 2 * (origin_xy[1] * plane.shape[1] + origin_xy[0])
+        # the reference's SIMD kernels store whole vectors: narrow blocks overrun w*h (harmless inside the
+        # decoder, where pred[] is MAX_CU_DIM), so give the output slack
+        buf = np.zeros(h * w + 256, np.int16)
+        fn = getattr(self.lib, self.prefix + ("mc_chroma" if chroma else "mc_luma"))
+        fn(base, plane.shape[1], gmv[0], gmv[1], ori_mv[0], ori_mv[1], buf.ctypes.data, w, w, h, bit_depth, int(main_tables))
+        return buf[:h * w].reshape(h, w).copy()
+
+    def itdq_block(self, coef: np.ndarray, qp: int, bit_depth: int, iqt=False):
+        h, w = coef.shape
+        c = np.ascontiguousarray(coef, np.int16).copy()
+        getattr(self.lib, self.prefix + "itdq_block")(c.ctypes.data, int(np.log2(w)), int(np.log2(h)), qp, bit_depth, int(iqt))
+        return c
+
+    # -- picture level ------------------------------------------------------------------------
+    def recon_frame(self, prm: Params, cur: HostPicture, refs_l0, refs_l1, cl: CuList):
+        a0, k0 = _ptr_array(refs_l0)
+        a1, k1 = _ptr_array(refs_l1)
+        cur_o = orc_pic(cur)
+        cus = np.ascontiguousarray(cl.cus)
+        ext = np.ascontiguousarray(cl.ext)
+        coef = np.ascontiguousarray(cl.coef)
+        r = getattr(self.lib, self.prefix + "recon_frame")(
+            C.byref(prm), C.byref(cur_o), a0, len(refs_l0), a1, len(refs_l1),
+            cus.ctypes.data, len(cus), ext.ctypes.data, coef.ctypes.data)
+        if r < 0:
+            raise RuntimeError(f"{self.prefix}recon_frame failed: {r}")
+        return cur
+
+    def pad(self, pic: HostPicture):
+        o = orc_pic(pic)
+        getattr(self.lib, self.prefix + "pad")(C.byref(o))
+        return pic
+
+
+class Oracle(_Backend):
+    def __init__(self):
+        if not ORACLE_SO.exists():
+            build()
+        super().__init__(ORACLE_SO, "orc_")
+        L = self.lib
+        L.orc_dct2_matrix.restype = C.POINTER(C.c_int8)
+        L.orc_dct2_matrix.argtypes = [C.c_int]
+        L.orc_ats_matrix.restype = C.POINTER(C.c_int16)
+        L.orc_ats_matrix.argtypes = [C.c_int, C.c_int]
+        L.orc_mc_luma_taps.restype = C.POINTER(C.c_int16)
+        L.orc_mc_luma_taps.argtypes = [C.c_int]
+        L.orc_mc_chroma_taps.restype = C.POINTER(C.c_int16)
+        L.orc_mc_chroma_taps.argtypes = [C.c_int]
+
+    def dct2_matrix(self, log2n):
+        n = 1 << log2n
+        return np.ctypeslib.as_array(self.lib.orc_dct2_matrix(log2n), (n, n)).copy()
+
+    def ats_matrix(self, dst7, log2n):
+        n = 1 << log2n
+        return np.ctypeslib.as_array(self.lib.orc_ats_matrix(int(dst7), log2n), (n, n)).copy()
+
+    def mc_taps(self, main_tables):
+        return (np.ctypeslib.as_array(self.lib.orc_mc_luma_taps(int(main_tables)), (16, 8)).copy(),
+                np.ctypeslib.as_array(self.lib.orc_mc_chroma_taps(int(main_tables)), (32, 4)).copy())
+
+
+class Reference(_Backend):
+    """the unmodified reference library; impl 0 = plain C, 1 = SSE4.1, 2 = AVX2 (dispatched on x86)"""
+
+    def __init__(self, impl: int = 2):
+        super().__init__(REF_SO, "ref_")
+        self.lib.ref_set_impl.argtypes = [C.c_int]
+        self.lib.ref_set_impl(impl)
+        self.impl = impl
+
+    def set_impl(self, impl):
+        self.lib.ref_set_impl(impl)
+        self.impl = impl
+
+    def dct2_matrix(self, log2n):
+        n = 1 << log2n
+        out = np.zeros((n, n), np.int8)
+        assert self.lib.ref_get_dct2(log2n, C.c_void_p(out.ctypes.data)) == 0
+        return out
+
+    def ats_matrix(self, dst7, log2n):
+        n = 1 << log2n
+        out = np.zeros((n, n), np.int16)
+        assert self.lib.ref_get_inv_ats(int(dst7), log2n, C.c_void_p(out.ctypes.data)) == 0
+        return out
+
+    def mc_taps(self, main_tables):
+        l, c = np.zeros((16, 8), np.int16), np.zeros((32, 4), np.int16)
+        self.lib.ref_get_mc_taps(int(main_tables), C.c_void_p(l.ctypes.data), C.c_void_p(c.ctypes.data))
+        return l, c
+
+
+def have_reference() -> bool:
+    return REF_SO.exists()

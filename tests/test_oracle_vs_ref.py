@@ -1,0 +1,105 @@
+"""Pins the CPU oracle (oracle/orc_*.c) against the UNMODIFIED reference compiled from /root/reference
+(oracle/_ref/libxevd_ref.so): tables, leaf kernels and CU-level picture reconstruction.  C, SSE and AVX2
+variants of the reference are all exercised."""
+import numpy as np
+import pytest
+
+from xevd_b200 import synth
+from xevd_b200.frame import HostPicture
+
+
+def test_dct2_tables(oracle, reference):
+    for lg in range(1, 7):
+        assert np.array_equal(oracle.dct2_matrix(lg), reference.dct2_matrix(lg)), f"tm{1 << lg}"
+
+
+def test_ats_tables(oracle, reference):
+    for lg in range(2, 6):
+        for dst7 in (0, 1):
+            assert np.array_equal(oracle.ats_matrix(dst7, lg), reference.ats_matrix(dst7, lg))
+
+
+def test_mc_taps(oracle, reference):
+    for m in (0, 1):
+        lo, co = oracle.mc_taps(m)
+        lr, cr = reference.mc_taps(m)
+        assert np.array_equal(lo, lr) and np.array_equal(co, cr)
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("bit_depth", [8, 10])
+def test_mc_leaf(oracle, reference, impl, bit_depth):
+    reference.set_impl(impl)
+    rng = np.random.default_rng(100 + impl + bit_depth)
+    plane = rng.integers(0, 1 << bit_depth, (200, 232), dtype=np.int16)
+    org = (40, 36)
+    sizes = [4, 8, 16, 32, 64, 128]
+    for t in range(250):
+        main = bool(t & 1)
+        w, h = sizes[rng.integers(6)], sizes[rng.integers(6)]
+        w, h = min(w, 128), min(h, 96)
+        # luma: 1/16 pel; Baseline only has quarter-pel phases
+        step = 1 if main else 4
+        fx, fy = int(rng.integers(0, 16 // step)) * step, int(rng.integers(0, 16 // step)) * step
+        gx, gy = (int(rng.integers(-20, 40)) << 4) + fx, (int(rng.integers(-20, 40)) << 4) + fy
+        # the variant comes from the unclipped vector; make it sometimes disagree with the phase (T3)
+        ox, oy = (fx, fy) if rng.random() < 0.8 else (int(rng.integers(0, 16)), int(rng.integers(0, 16)))
+        a = oracle.mc(plane, org, (gx, gy), (ox, oy), w, h, bit_depth, False, main)
+        b = reference.mc(plane, org, (gx, gy), (ox, oy), w, h, bit_depth, False, main)
+        assert np.array_equal(a, b), (impl, "luma", w, h, gx, gy, ox, oy, main)
+        cw, ch = max(2, w // 2), max(2, h // 2)
+        cstep = 1 if main else 4
+        cfx, cfy = int(rng.integers(0, 32 // cstep)) * cstep, int(rng.integers(0, 32 // cstep)) * cstep
+        cgx, cgy = (int(rng.integers(-10, 30)) << 5) + cfx, (int(rng.integers(-10, 30)) << 5) + cfy
+        cox, coy = (cfx, cfy) if rng.random() < 0.8 else (int(rng.integers(0, 32)), int(rng.integers(0, 32)))
+        a = oracle.mc(plane, org, (cgx, cgy), (cox, coy), cw, ch, bit_depth, True, main)
+        b = reference.mc(plane, org, (cgx, cgy), (cox, coy), cw, ch, bit_depth, True, main)
+        assert np.array_equal(a, b), (impl, "chroma", cw, ch, cgx, cgy, cox, coy, main)
+    reference.set_impl(2)
+
+
+@pytest.mark.parametrize("impl", [0, 2])
+@pytest.mark.parametrize("iqt", [0, 1])
+def test_itdq_all_shapes(oracle, reference, impl, iqt):
+    reference.set_impl(impl)
+    rng = np.random.default_rng(7 + impl)
+    for bit_depth in (8, 10):
+        qp = 32 + 6 * (bit_depth - 8)
+        for lw in range(1, 7):
+            for lh in range(1, 7):
+                w, h = 1 << lw, 1 << lh
+                for rep in range(3):
+                    res = rng.laplace(0, 40.0 * (1 << (bit_depth - 8)), (h, w))
+                    lev = synth.quantised_dct(res, qp, bool(iqt))
+                    if rep == 2:      # sparse high-frequency content too
+                        lev[:] = 0
+                        # (IQT: stay inside the 32 lowest frequencies, see synth.quantised_dct)
+                        lim = 32 if iqt else 64
+                        lev[rng.integers(min(h, lim)), rng.integers(min(w, lim))] = rng.integers(-40, 40)
+                    a = oracle.itdq_block(lev, qp, bit_depth, iqt)
+                    b = reference.itdq_block(lev, qp, bit_depth, iqt)
+                    assert np.array_equal(a, b), (impl, iqt, bit_depth, lw, lh, rep)
+    reference.set_impl(2)
+
+
+@pytest.mark.parametrize("variant,bit_depth,iqt", [("A", 10, 0), ("B", 10, 0), ("B", 8, 0), ("B", 10, 1)])
+def test_recon_frame_inter(oracle, reference, variant, bit_depth, iqt):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bit_depth, variant=variant, seed=5, n_refs=2,
+                                     coded_frac=0.8, mv_range_px=200, iqt=bool(iqt))
+    cl.validate()
+    refs = synth.make_refs(w, h, bit_depth, 2, seed=9)
+    refs[1].poc = refs[0].poc if variant == "B" else refs[1].poc   # exercise the identical-motion shortcut
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), name
+
+
+def test_pad(oracle, reference):
+    rng = np.random.default_rng(3)
+    p = HostPicture.random(72, 40, 10, rng)
+    a = oracle.pad(p.copy())
+    b = reference.pad(p.copy())
+    assert np.array_equal(a.buf_y, b.buf_y) and np.array_equal(a.buf_u, b.buf_u) and np.array_equal(a.buf_v, b.buf_v)
+    assert np.array_equal(a.buf_y, p.copy().pad_borders().buf_y)
