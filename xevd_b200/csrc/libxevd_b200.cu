@@ -1,0 +1,379 @@
+// libxevd_b200.cu -- the C ABI (include/xevd_b200.h) over the sm_100a kernels.  Single translation unit.
+//
+// Host side of the boundary: device pictures (PICBUF_ALLOCATOR replacement), argument marshalling,
+// pinned staging for the host-pointer entry points, launches on one CUDA stream per context.
+// No CPU implementation of any kernel exists here: without a device every call fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "xb_common.cuh"
+#include "xb_itdq.cuh"
+#include "xb_recon.cuh"
+#include "xb_filters.cuh"
+#include "xb_micro.cuh"
+
+struct xb200_pic {
+    int w, h, w_c, h_c, s_l, s_c, pad_l, pad_c, w_scu, h_scu, poc;
+    size_t luma_elems, chroma_elems;
+    pel *buf;                    // one allocation: Y | U | V padded planes
+    pel *y, *u, *v;              // sample (0,0)
+    int16_t *map_mv;
+    int8_t *map_refi;
+    uint32_t *map_scu;
+};
+
+struct Staging {                 // one slot of the host->device staging ring
+    void *pinned = nullptr, *dev = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;  // recorded after the kernel that consumes the slot
+    bool busy = false;
+};
+
+struct xb200_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    long long launches;
+    char err[256];
+    Staging ring[3];
+    int ring_pos;
+    int sm_count;
+};
+
+#define CK(ctx, call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), "%s: %s", #call, cudaGetErrorString(e_)); \
+            return XB200_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+extern "C" {
+
+int xb200_abi_version(void) { return XB200_ABI_VERSION; }
+
+int xb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return XB200_ERR_NO_DEVICE;
+    return n;
+}
+
+xb200_ctx *xb200_create(int device, int *err)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        if (err) *err = XB200_ERR_NO_DEVICE;
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { if (err) *err = XB200_ERR_NO_DEVICE; return nullptr; }
+    xb200_ctx *c = new (std::nothrow) xb200_ctx();
+    if (!c) { if (err) *err = XB200_ERR_OUT_OF_MEMORY; return nullptr; }
+    c->device = device;
+    c->own_stream = true;
+    c->launches = 0;
+    c->err[0] = 0;
+    c->ring_pos = 0;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        if (err) *err = XB200_ERR_CUDA;
+        return nullptr;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB)
+    cudaFuncSetAttribute(xb::k_recon_inter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
+    cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
+    if (err) *err = XB200_OK;
+    return c;
+}
+
+void xb200_destroy(xb200_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &s : c->ring) {
+        if (s.pinned) cudaFreeHost(s.pinned);
+        if (s.dev) cudaFree(s.dev);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *xb200_last_error(xb200_ctx *c) { return c ? c->err : "no context"; }
+int xb200_sync(xb200_ctx *c)
+{
+    if (!c) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+void *xb200_stream(xb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int xb200_set_stream(xb200_ctx *c, void *s)
+{
+    if (!c) return XB200_ERR_INVALID_ARGUMENT;
+    if (c->own_stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)s;
+    return XB200_OK;
+}
+long long xb200_launch_count(xb200_ctx *c) { return c ? c->launches : 0; }
+
+// ---- pictures ---------------------------------------------------------------------------------------------------
+xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
+{
+    if (!c || w <= 0 || h <= 0 || (w & 7) || (h & 7)) { if (err) *err = XB200_ERR_INVALID_ARGUMENT; return nullptr; }
+    cudaSetDevice(c->device);
+    xb200_pic *p = new (std::nothrow) xb200_pic();
+    if (!p) { if (err) *err = XB200_ERR_OUT_OF_MEMORY; return nullptr; }
+    p->w = w; p->h = h; p->w_c = w >> 1; p->h_c = h >> 1;
+    p->pad_l = 144; p->pad_c = 72;                       // PIC_PAD_SIZE_L / _C (xevd_def.h:211-212)
+    p->s_l = w + 2 * p->pad_l; p->s_c = p->w_c + 2 * p->pad_c;
+    p->w_scu = (w + 3) >> 2; p->h_scu = (h + 3) >> 2;
+    p->poc = 0;
+    p->luma_elems = (size_t)p->s_l * (h + 2 * p->pad_l);
+    p->chroma_elems = (size_t)p->s_c * (p->h_c + 2 * p->pad_c);
+    const size_t nscu = (size_t)p->w_scu * p->h_scu;
+    const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
+    const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
+    const size_t total = pix_al + nscu * (8 + 4 + 2) + 256;
+    if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
+        delete p;
+        if (err) *err = XB200_ERR_OUT_OF_MEMORY;
+        return nullptr;
+    }
+    cudaMemsetAsync(p->buf, 0, total, c->stream);
+    p->y = p->buf + (size_t)p->pad_l * p->s_l + p->pad_l;
+    p->u = p->buf + p->luma_elems + (size_t)p->pad_c * p->s_c + p->pad_c;
+    p->v = p->buf + p->luma_elems + p->chroma_elems + (size_t)p->pad_c * p->s_c + p->pad_c;
+    unsigned char *m = (unsigned char *)p->buf + pix_al;
+    p->map_mv = (int16_t *)m;
+    p->map_scu = (uint32_t *)(m + nscu * 8);
+    p->map_refi = (int8_t *)(m + nscu * 12);
+    if (err) *err = XB200_OK;
+    return p;
+}
+
+void xb200_pic_free(xb200_ctx *c, xb200_pic *p)
+{
+    if (!p) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(p->buf);
+    delete p;
+}
+
+int xb200_pic_info(xb200_pic *p, XB200_PIC_INFO *i)
+{
+    if (!p || !i) return XB200_ERR_INVALID_ARGUMENT;
+    i->w_l = p->w; i->h_l = p->h; i->w_c = p->w_c; i->h_c = p->h_c;
+    i->s_l = p->s_l; i->s_c = p->s_c; i->pad_l = p->pad_l; i->pad_c = p->pad_c;
+    i->dev_y = p->y; i->dev_u = p->u; i->dev_v = p->v;
+    i->dev_map_mv = p->map_mv; i->dev_map_refi = p->map_refi; i->dev_map_scu = p->map_scu;
+    i->w_scu = p->w_scu; i->h_scu = p->h_scu; i->poc = p->poc;
+    return XB200_OK;
+}
+
+int xb200_pic_set_poc(xb200_pic *p, int poc) { if (!p) return XB200_ERR_INVALID_ARGUMENT; p->poc = poc; return XB200_OK; }
+
+int xb200_pic_upload(xb200_ctx *c, xb200_pic *p, const xb200_pel *y, int sy, const xb200_pel *u, int su, const xb200_pel *v, int sv)
+{
+    if (!c || !p || !y || !u || !v) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpy2DAsync(p->y, p->s_l * 2, y, sy * 2, p->w * 2, p->h, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpy2DAsync(p->u, p->s_c * 2, u, su * 2, p->w_c * 2, p->h_c, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpy2DAsync(p->v, p->s_c * 2, v, sv * 2, p->w_c * 2, p->h_c, cudaMemcpyHostToDevice, c->stream));
+    return XB200_OK;
+}
+
+int xb200_pic_download(xb200_ctx *c, xb200_pic *p, xb200_pel *y, int sy, xb200_pel *u, int su, xb200_pel *v, int sv)
+{
+    if (!c || !p || !y || !u || !v) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpy2DAsync(y, sy * 2, p->y, p->s_l * 2, p->w * 2, p->h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(u, su * 2, p->u, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(v, sv * 2, p->v, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToHost, c->stream));
+    return XB200_OK;
+}
+
+int xb200_pic_download_padded(xb200_ctx *c, xb200_pic *p, xb200_pel *y, xb200_pel *u, xb200_pel *v)
+{
+    if (!c || !p || !y || !u || !v) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpyAsync(y, p->buf, p->luma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(u, p->buf + p->luma_elems, p->chroma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(v, p->buf + p->luma_elems + p->chroma_elems, p->chroma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
+int xb200_pic_download_maps(xb200_ctx *c, xb200_pic *p, int16_t *map_mv, int8_t *map_refi, uint32_t *map_scu)
+{
+    if (!c || !p) return XB200_ERR_INVALID_ARGUMENT;
+    const size_t n = (size_t)p->w_scu * p->h_scu;
+    if (map_mv) CK(c, cudaMemcpyAsync(map_mv, p->map_mv, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (map_refi) CK(c, cudaMemcpyAsync(map_refi, p->map_refi, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (map_scu) CK(c, cudaMemcpyAsync(map_scu, p->map_scu, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
+// ---- reconstruction ------------------------------------------------------------------------------------------------
+static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                     XbFrameArgs &a)
+{
+    if (!c || !prm || !cur) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->chroma_format_idc != 1) return XB200_ERR_UNSUPPORTED;
+    if (prm->w != cur->w || prm->h != cur->h) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->log2_ctu < 5 || prm->log2_ctu > 7) return XB200_ERR_INVALID_ARGUMENT;
+    if (n0 < 0 || n1 < 0 || n0 > XB_MAX_REFS || n1 > XB_MAX_REFS) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->bit_depth_luma < 8 || prm->bit_depth_luma > 14) return XB200_ERR_UNSUPPORTED;
+    memset(&a, 0, sizeof(a));
+    a.cur.y = cur->y; a.cur.u = cur->u; a.cur.v = cur->v;
+    for (int l = 0; l < 2; l++) {
+        xb200_pic *const *lst = l ? l1 : l0;
+        const int n = l ? n1 : n0;
+        for (int i = 0; i < n; i++) {
+            if (!lst || !lst[i] || lst[i]->w != cur->w || lst[i]->h != cur->h) return XB200_ERR_INVALID_ARGUMENT;
+            a.ref_y[l][i] = lst[i]->y; a.ref_u[l][i] = lst[i]->u; a.ref_v[l][i] = lst[i]->v;
+            a.ref_poc[l][i] = lst[i]->poc;
+        }
+    }
+    a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
+    a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma;
+    a.log2_ctu = prm->log2_ctu;
+    a.w_ctu = (cur->w + (1 << a.log2_ctu) - 1) >> a.log2_ctu;
+    a.n_ctu = a.w_ctu * ((cur->h + (1 << a.log2_ctu) - 1) >> a.log2_ctu);
+    a.main_tables = prm->tool_admvp ? 1 : 0;
+    a.iqt = prm->tool_iqt ? 1 : 0;
+    a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu;
+    a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
+    return XB200_OK;
+}
+
+int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
+                          xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                          const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
+                          const void *d_ext, int n_ext, const void *d_coef, size_t n_coef, int has_intra)
+{
+    XbFrameArgs a;
+    int r = fill_args(c, prm, cur, l0, n0, l1, n1, a);
+    if (r < 0) return r;
+    (void)n_ext; (void)n_coef;
+    if (has_intra) return XB200_ERR_UNSUPPORTED;
+    if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
+    if (cur->poc != prm->poc) cur->poc = prm->poc;
+    a.cus = (const XB200_CU *)d_cus;
+    a.ctu_first = (const uint32_t *)d_ctu_first;
+    a.coef = (const int16_t *)d_coef;
+    a.ext = (const XB200_CU_EXT *)d_ext;
+    cudaSetDevice(c->device);
+    const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
+    if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
+    else       xb::k_recon_inter<false><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+// grab the next staging slot, make sure its previous consumer has finished, and size it
+static int stage_acquire(xb200_ctx *c, size_t bytes, Staging **out)
+{
+    Staging &s = c->ring[c->ring_pos];
+    c->ring_pos = (c->ring_pos + 1) % 3;
+    if (!s.done) CK(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (s.busy) { CK(c, cudaEventSynchronize(s.done)); s.busy = false; }
+    if (s.cap < bytes) {
+        if (s.pinned) cudaFreeHost(s.pinned);
+        if (s.dev) cudaFree(s.dev);
+        s.cap = bytes + bytes / 4 + 4096;
+        CK(c, cudaMallocHost(&s.pinned, s.cap));
+        CK(c, cudaMalloc(&s.dev, s.cap));
+    }
+    *out = &s;
+    return XB200_OK;
+}
+
+int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
+                      xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                      const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                      const XB200_CU_EXT *ext, int n_ext, const int16_t *coef, size_t n_coef)
+{
+    if (!c || !cus || !ctu_first || n_cu < 0 || n_ctu <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    // one staging blob: [cus][ctu_first][ext][coef], each 256-byte aligned
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t b_cu = al((size_t)n_cu * sizeof(XB200_CU)), b_first = al((size_t)(n_ctu + 1) * 4);
+    const size_t b_ext = al((size_t)(n_ext > 0 ? n_ext : 1) * sizeof(XB200_CU_EXT)), b_coef = al(n_coef * 2 + 2);
+    Staging *s;
+    int r = stage_acquire(c, b_cu + b_first + b_ext + b_coef, &s);
+    if (r < 0) return r;
+    unsigned char *hp = (unsigned char *)s->pinned, *dp = (unsigned char *)s->dev;
+    memcpy(hp, cus, (size_t)n_cu * sizeof(XB200_CU));
+    memcpy(hp + b_cu, ctu_first, (size_t)(n_ctu + 1) * 4);
+    if (ext && n_ext > 0) memcpy(hp + b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT));
+    if (coef && n_coef) memcpy(hp + b_cu + b_first + b_ext, coef, n_coef * 2);
+    int has_intra = 0;
+    for (int i = 0; i < n_cu; i++) has_intra |= (cus[i].mode == XB200_MODE_INTRA);
+    CK(c, cudaMemcpyAsync(dp, hp, b_cu + b_first + b_ext + b_coef, cudaMemcpyHostToDevice, c->stream));
+    r = xb200_recon_frame_dev(c, prm, cur, l0, n0, l1, n1, dp, n_cu, dp + b_cu, n_ctu, dp + b_cu + b_first, n_ext,
+                              dp + b_cu + b_first + b_ext, n_coef, has_intra);
+    CK(c, cudaEventRecord(s->done, c->stream));
+    s->busy = true;
+    return r;
+}
+
+// ---- in-loop filters / padding ----------------------------------------------------------------------------------------
+int xb200_pad(xb200_ctx *c, xb200_pic *p)
+{
+    if (!c || !p) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    xb::launch_pad(p->y, p->s_l, p->w, p->h, p->pad_l, p->u, p->v, p->s_c, p->w_c, p->h_c, p->pad_c, c->stream);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_deblock_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0,
+                      xb200_pic *const *l1, int n1, const void *d_edge_flags)
+{
+    (void)prm; (void)cur; (void)l0; (void)n0; (void)l1; (void)n1; (void)d_edge_flags;
+    if (!c) return XB200_ERR_INVALID_ARGUMENT;
+    return XB200_ERR_UNSUPPORTED;
+}
+
+int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0,
+                  xb200_pic *const *l1, int n1, const uint8_t *edge_flags)
+{
+    (void)prm; (void)cur; (void)l0; (void)n0; (void)l1; (void)n1; (void)edge_flags;
+    if (!c) return XB200_ERR_INVALID_ARGUMENT;
+    return XB200_ERR_UNSUPPORTED;
+}
+
+// ---- batched leaf kernels ---------------------------------------------------------------------------------------------
+int xb200_itdq_blocks_dev(xb200_ctx *c, const void *d_in, void *d_out, int n, int log2w, int log2h, int qp, int bit_depth, int iqt)
+{
+    if (!c || !d_in || !d_out || n <= 0 || log2w < 1 || log2w > 6 || log2h < 1 || log2h > 6) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    int r = xb::launch_itdq_blocks((const int16_t *)d_in, (int16_t *)d_out, n, log2w, log2h, qp, bit_depth, iqt, c->stream);
+    if (r < 0) return r;
+    c->launches += r;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_mc_blocks_dev(xb200_ctx *c, xb200_pic *ref, int plane, const void *d_mv, void *d_out, int n, int w, int h, int bit_depth, int main_tables)
+{
+    if (!c || !ref || !d_mv || !d_out || n <= 0 || plane < 0 || plane > 2) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    const pel *base = plane == 0 ? ref->y : (plane == 1 ? ref->u : ref->v);
+    int r = xb::launch_mc_blocks(base, plane == 0 ? ref->s_l : ref->s_c, plane != 0, (const int *)d_mv, (pel *)d_out, n, w, h, bit_depth,
+                                 main_tables, c->stream);
+    if (r < 0) return r;
+    c->launches += r;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+}  // extern "C"

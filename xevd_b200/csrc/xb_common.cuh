@@ -1,0 +1,68 @@
+// xb_common.cuh -- shared device-side declarations of the B200 reconstruction path.
+//
+// Layout in HBM: pictures are padded 16-bit planes exactly like the reference's
+// XEVD_PIC (pad 144 luma / 72 chroma, xevd_util.c:153-230); per-SCU maps follow XEVD_PIC.map_mv /
+// map_refi and ctx->map_scu.  CU work items, the coefficient stream and the per-CTU index are the
+// flat arrays of include/xevd_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/xevd_b200.h"
+
+#define XB_MAX_REFS 17          // XEVD_MAX_NUM_REF_PICS (21) is never reached per list; 17 = 16 + 1
+
+typedef int16_t pel;
+
+struct XbPlanes {
+    pel *y, *u, *v;             // sample (0,0)
+};
+
+// everything one picture-level kernel needs, passed by value (__grid_constant__)
+struct XbFrameArgs {
+    XbPlanes cur;
+    const pel *ref_y[2][XB_MAX_REFS];
+    const pel *ref_u[2][XB_MAX_REFS];
+    const pel *ref_v[2][XB_MAX_REFS];
+    int ref_poc[2][XB_MAX_REFS];
+    int s_l, s_c;               // strides in pels (same geometry for every picture of a sequence)
+    int w, h;                   // luma size
+    int bd_l, bd_c;
+    int log2_ctu, w_ctu, n_ctu;
+    int main_tables, iqt;
+    const XB200_CU *cus;
+    const uint32_t *ctu_first;
+    const int16_t *coef;
+    const XB200_CU_EXT *ext;
+    int16_t *map_mv;            // [scu][2][2]
+    int8_t *map_refi;           // [scu][2]
+    uint32_t *map_scu;
+    int w_scu, h_scu;
+};
+
+__device__ __forceinline__ int xb_clip3(int lo, int hi, int v) { return max(lo, min(hi, v)); }
+__device__ __forceinline__ int xb_clip16(int v) { return max(-32768, min(32767, v)); }
+
+// The library is a single translation unit (libxevd_b200.cu includes every .cuh), so __constant__
+// tables are plain definitions.
+// interpolation taps [main_tables][phase][tap]: src_base/xevd_mc.c:80-134, src_main/xevdm_mc.c:121-175
+__constant__ int16_t c_mc_l[2][16][8] = {
+    {{0, 0, 0, 64, 0, 0, 0, 0}, {0}, {0}, {0}, {0, 1, -5, 52, 20, -5, 1, 0}, {0}, {0}, {0},
+     {0, 2, -10, 40, 40, -10, 2, 0}, {0}, {0}, {0}, {0, 1, -5, 20, 52, -5, 1, 0}, {0}, {0}, {0}},
+    {{0, 0, 0, 64, 0, 0, 0, 0},        {0, 1, -3, 63, 4, -2, 1, 0},      {-1, 2, -5, 62, 8, -3, 1, 0},
+     {-1, 3, -8, 60, 13, -4, 1, 0},    {-1, 4, -10, 58, 17, -5, 1, 0},   {-1, 4, -11, 52, 26, -8, 3, -1},
+     {-1, 3, -9, 47, 31, -10, 4, -1},  {-1, 4, -11, 45, 34, -10, 4, -1}, {-1, 4, -11, 40, 40, -11, 4, -1},
+     {-1, 4, -10, 34, 45, -11, 4, -1}, {-1, 4, -10, 31, 47, -9, 3, -1},  {-1, 3, -8, 26, 52, -11, 4, -1},
+     {0, 1, -5, 17, 58, -10, 4, -1},   {0, 1, -4, 13, 60, -8, 3, -1},    {0, 1, -3, 8, 62, -5, 2, -1},
+     {0, 1, -2, 4, 63, -3, 1, 0}}};
+__constant__ int16_t c_mc_c[2][32][4] = {
+    {{0, 64, 0, 0},   {0}, {0}, {0}, {-2, 58, 10, -2}, {0}, {0}, {0}, {-4, 52, 20, -4}, {0}, {0}, {0},
+     {-6, 46, 30, -6}, {0}, {0}, {0}, {-8, 40, 40, -8}, {0}, {0}, {0}, {-6, 30, 46, -6}, {0}, {0}, {0},
+     {-4, 20, 52, -4}, {0}, {0}, {0}, {-2, 10, 58, -2}, {0}, {0}, {0}},
+    {{0, 64, 0, 0},    {-1, 63, 2, 0},   {-2, 62, 4, 0},   {-2, 60, 7, -1},  {-2, 58, 10, -2}, {-3, 57, 12, -2},
+     {-4, 56, 14, -2}, {-4, 55, 15, -2}, {-4, 54, 16, -2}, {-5, 53, 18, -2}, {-6, 52, 20, -2}, {-6, 49, 24, -3},
+     {-6, 46, 28, -4}, {-5, 44, 29, -4}, {-4, 42, 30, -4}, {-4, 39, 33, -4}, {-4, 36, 36, -4}, {-4, 33, 39, -4},
+     {-4, 30, 42, -4}, {-4, 29, 44, -5}, {-4, 28, 46, -6}, {-3, 24, 49, -6}, {-2, 20, 52, -6}, {-2, 18, 53, -5},
+     {-2, 16, 54, -4}, {-2, 15, 55, -4}, {-2, 14, 56, -4}, {-2, 12, 57, -3}, {-2, 10, 58, -2}, {-1, 7, 60, -2},
+     {0, 4, 62, -2},   {0, 2, 63, -1}}};
+// xevd_tbl_dq_scale_b / xevd_tbl_dq_scale (src_base/xevd_tbl.c:255-256), [iqt][qp % 6]
+__constant__ int c_dq_scale[2][6] = {{40, 45, 51, 57, 64, 71}, {40, 45, 51, 57, 64, 72}};

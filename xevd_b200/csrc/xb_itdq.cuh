@@ -1,0 +1,102 @@
+// xb_itdq.cuh -- inverse quantisation and inverse DCT-2 device code.
+//
+// Replaces xevd_dquant + xevd_itx_pb{2..64}b (src_base/xevd_itdq.c:48-517, dispatched AVX2 variant
+// src_base/avx/xevd_itdq_avx.c:2486) and the Main IQT xevdm_itx_pb{2..64} (src_main/xevdm_itdq.c:423-724).
+//
+// Each thread owns one line (a column in pass 1, a row in pass 2) of a transform block and evaluates
+// the N-point inverse DCT-2 in registers with the even/odd factorisation
+//      x[n], x[N-1-n] = E[n] +- O[n],  E = IDCT_{N/2}(even inputs),  O[n] = sum_{k odd} T[k][n] X[k]
+// with the kernel entries as compile-time literals.  All sums are plain 32-bit integers: this
+// reproduces the dispatched x86 path of the reference bit for bit (mod-2^32 accumulation in pass 2,
+// SURVEY T4) and the plain-C path whenever nothing overflows.
+#pragma once
+#include "xb_common.cuh"
+
+namespace xb {
+
+__device__ constexpr int8_t kTM64[64][64] = {
+#include "gen/dct2_tm64.inc"
+};
+
+// entry [k][n] of the N-point kernel (xevd_tbl_tmN), n < N
+template <int N> __device__ __forceinline__ constexpr int tm(int k, int n) { return kTM64[k * (64 / N)][n]; }
+
+template <int N> struct InvDct2 {
+    // out[n] = sum_k tm<N>(k, n) * in[k]
+    static __device__ __forceinline__ void run(const int (&in)[N], int (&out)[N])
+    {
+        int ev[N / 2], E[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) ev[k] = in[2 * k];
+        InvDct2<N / 2>::run(ev, E);
+#pragma unroll
+        for (int n = 0; n < N / 2; n++) {
+            int o = 0;
+#pragma unroll
+            for (int k = 1; k < N; k += 2) o += tm<N>(k, n) * in[k];
+            out[n] = E[n] + o;
+            out[N - 1 - n] = E[n] - o;
+        }
+    }
+};
+template <> struct InvDct2<2> {
+    static __device__ __forceinline__ void run(const int (&in)[2], int (&out)[2])
+    {
+        out[0] = 64 * (in[0] + in[1]);
+        out[1] = 64 * (in[0] - in[1]);
+    }
+};
+
+// xevd_itdq prologue (xevd_itdq.c:494-517): the dequantiser of one transform block
+struct Dequant {
+    long long mul;      // scale * (181 when log2w + log2h is odd)
+    long long off;
+    int shift;
+    __device__ __forceinline__ void init(int log2w, int log2h, int qp, int bit_depth, int iqt)
+    {
+        const int odd = (log2w + log2h) & 1;
+        shift = 20 - 14 - (15 - bit_depth - ((log2w + log2h) >> 1)) + (odd ? 8 : 0);
+        off = shift == 0 ? 0 : (1LL << (shift - 1));
+        mul = (long long)(c_dq_scale[iqt][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
+    }
+    __device__ __forceinline__ int apply(int c) const
+    {
+        if (c == 0) return 0;
+        long long v = (c * mul + off) >> shift;
+        return (int)max(-32768LL, min(32767LL, v));
+    }
+};
+
+// Pass 1 of one line: N dequantised inputs read with stride `sstride` from `src`, results to dst[n*dstride].
+//   Baseline: no shift, s32 results.  IQT: (sum + 64) >> 7 clipped to s16 (xevdm_itdq.c:35-39,714-716).
+template <int N, bool IQT, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void itx_line(LoadFn load, StoreFn store, int shift)
+{
+    int in[N], out[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) in[k] = load(k);
+    InvDct2<N>::run(in, out);
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        int v = out[n];
+        if (shift > 0) v = (v + (1 << (shift - 1))) >> shift;
+        if (IQT || shift > 0) v = xb_clip16(v);
+        store(n, v);
+    }
+}
+
+// dispatch on the line length (2..64)
+template <bool IQT, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void itx_line_dyn(int log2n, LoadFn load, StoreFn store, int shift)
+{
+    switch (log2n) {
+    case 1: itx_line<2, IQT>(load, store, shift); break;
+    case 2: itx_line<4, IQT>(load, store, shift); break;
+    case 3: itx_line<8, IQT>(load, store, shift); break;
+    case 4: itx_line<16, IQT>(load, store, shift); break;
+    case 5: itx_line<32, IQT>(load, store, shift); break;
+    default: itx_line<64, IQT>(load, store, shift); break;
+    }
+}
+
+}  // namespace xb

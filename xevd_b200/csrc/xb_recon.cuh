@@ -1,0 +1,384 @@
+// xb_recon.cuh -- per-picture CU reconstruction kernel (inter CUs): one CTA reconstructs one CTU.
+//
+// Replaces xevd_ctu_row_rec_mt -> xevd_recon_tree -> xevd_recon_unit (src_base/xevd.c:1470,1019,678;
+// Main src_main/xevdm.c:2463,1854,1230) for CUs whose motion is already resolved:
+//   phase A  residual:  coefficient stream -> dequant -> inverse DCT-2 (two passes) -> s16 residual in smem
+//            (xevd_sub_block_itdq, src_base/xevd_itdq.c:544-621; xevdm_sub_block_itdq, xevdm_itdq.c:790-887)
+//   phase B  prediction + reconstruction: warp per 16x16 tile, reference window staged in shared memory,
+//            separable 8-tap / 4-tap interpolation, bi-prediction average, + residual, clip, store
+//            (xevd_mc, src_base/xevd_mc.c:469-557; xevd_recon, src_base/xevd_recon.c:36-68)
+//   phase C  publish per-SCU maps (xevd_set_dec_info, src_base/xevd_util.c:1574-1650)
+#pragma once
+#include "xb_common.cuh"
+#include "xb_itdq.cuh"
+
+namespace xb {
+
+constexpr int kReconThreads = 256;
+constexpr int kReconWarps = kReconThreads / 32;
+constexpr int kMcScratchPerWarp = 1536;     // int16 elements: luma window 23x24 + intermediate 23x16 + slack
+
+// shared memory carve-up for a CTU of size S = 1 << log2_ctu (S = 64: ~39 KB)
+struct ReconSmem {
+    int S, Sc;
+    int *tmp_y, *tmp_u, *tmp_v;            // pass-1 results, row stride S+1 / Sc+1 (bank-conflict free)
+    int16_t *res_y, *res_u, *res_v;        // residual, row stride S+2 / Sc+2
+    uint16_t *cu_of_scu;                   // CU index (relative to the CTU's first CU) covering each SCU
+    int16_t *mc;                           // per-warp interpolation scratch (aliases tmp_*)
+    __device__ __forceinline__ void carve(unsigned char *base, int log2_ctu)
+    {
+        S = 1 << log2_ctu; Sc = S >> 1;
+        tmp_y = (int *)base;
+        tmp_u = tmp_y + S * (S + 1);
+        tmp_v = tmp_u + Sc * (Sc + 1);
+        mc = (int16_t *)base;
+        size_t tmp_bytes = sizeof(int) * (S * (S + 1) + 2 * Sc * (Sc + 1));
+        size_t mc_bytes = sizeof(int16_t) * kMcScratchPerWarp * kReconWarps;
+        size_t a = tmp_bytes > mc_bytes ? tmp_bytes : mc_bytes;
+        a = (a + 15) & ~(size_t)15;
+        res_y = (int16_t *)(base + a);
+        res_u = res_y + S * (S + 2);
+        res_v = res_u + Sc * (Sc + 2);
+        cu_of_scu = (uint16_t *)(res_v + Sc * (Sc + 2));
+    }
+    static size_t bytes(int log2_ctu)
+    {
+        int S = 1 << log2_ctu, Sc = S >> 1;
+        size_t tmp_bytes = sizeof(int) * (S * (S + 1) + 2 * Sc * (Sc + 1));
+        size_t mc_bytes = sizeof(int16_t) * kMcScratchPerWarp * kReconWarps;
+        size_t a = tmp_bytes > mc_bytes ? tmp_bytes : mc_bytes;
+        a = (a + 15) & ~(size_t)15;
+        return a + sizeof(int16_t) * (S * (S + 2) + 2 * Sc * (Sc + 2)) + sizeof(uint16_t) * (S / 4) * (S / 4) + 16;
+    }
+};
+
+// ---- motion vector clipping: xevd_mv_clip (src_base/xevd_mc.c:435-467) ---------------------------------
+__device__ __forceinline__ void mv_clip(int x, int y, int pic_w, int pic_h, int w, int h, int mvx, int mvy, int &cx, int &cy)
+{
+    const int qx = x << 2, qy = y << 2, qw = w << 2, qh = h << 2;
+    const int lo = -(128 << 2), hx = (pic_w - 1 + 128) << 2, hy = (pic_h - 1 + 128) << 2;
+    cx = mvx; cy = mvy;
+    if (qx + mvx < lo) cx = lo - qx;
+    if (qy + mvy < lo) cy = lo - qy;
+    if (qx + mvx + qw - 4 > hx) cx = hx - qx - qw + 4;
+    if (qy + mvy + qh - 4 > hy) cy = hy - qy - qh + 4;
+    cx = (int16_t)cx; cy = (int16_t)cy;
+}
+
+// ---- one interpolated tile, computed by one warp ----------------------------------------------------------
+// Tile of tw x th samples (powers of two, <= 16).  Lane l owns column (l % tw) and `rpl` consecutive rows
+// starting at (l / tw) * rpl.  Result in pr[0..rpl).  NTAP = 8 (luma) or 4 (chroma).
+//   ref     : sample at integer position of the tile's top-left output (before the -NTAP/2+1 tap offset)
+//   cx, cy  : taps for the horizontal / vertical phase;  fx, fy : variant selected by the UNCLIPPED mv (T3)
+template <int NTAP>
+__device__ __forceinline__ void mc_tile(const pel *__restrict__ ref, int stride, const int16_t *cx, const int16_t *cy,
+                                        bool fx, bool fy, int tw, int th, int rpl, int bd, int16_t *scr, int lane, int (&pr)[8])
+{
+    constexpr int HALF = NTAP / 2 - 1;
+    const int maxv = (1 << bd) - 1;
+    const int col = lane & (tw - 1), r0 = (lane / tw) * rpl;
+    const bool active = r0 < th;
+    if (!fx && !fy) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < rpl && active) pr[i] = ref[(r0 + i) * stride + col];
+        return;
+    }
+    // stage the reference window: rows [-HALF, th+NTAP-1-HALF) if fy, cols [-HALF, tw+NTAP-1-HALF) if fx
+    const int wrows = fy ? th + NTAP - 1 : th, wcols = fx ? tw + NTAP - 1 : tw;
+    const int wstride = 24;
+    const pel *wbase = ref - (fy ? HALF * stride : 0) - (fx ? HALF : 0);
+    for (int r = 0; r < wrows; r++)
+        if (lane < wcols) scr[r * wstride + lane] = wbase[r * stride + lane];
+    __syncwarp();
+    int16_t *win = scr;
+    int16_t *mid = scr + 23 * wstride;              // horizontal-pass output, row stride tw
+    if (fx) {
+        int c[NTAP];
+#pragma unroll
+        for (int t = 0; t < NTAP; t++) c[t] = cx[t];
+        const int s1 = fy ? min(4, bd - 8) : 6;
+        for (int idx = lane; idx < wrows * tw; idx += 32) {
+            const int r = idx / tw, cc = idx & (tw - 1);
+            int acc = 0;
+#pragma unroll
+            for (int t = 0; t < NTAP; t++) acc += c[t] * win[r * wstride + cc + t];
+            acc >>= s1;
+            if (!fy) acc = xb_clip3(0, maxv, acc);   // 1-D: (sum + 0) >> 6, clipped (xevd_mc.c:203, T1)
+            mid[idx] = (int16_t)acc;                 // 2-D: kept as s16 (xevd_mc.c:243,264)
+        }
+        __syncwarp();
+        if (!fy) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                if (i < rpl && active) pr[i] = mid[(r0 + i) * tw + col];
+            __syncwarp();
+            return;
+        }
+    }
+    {
+        int c[NTAP];
+#pragma unroll
+        for (int t = 0; t < NTAP; t++) c[t] = cy[t];
+        const int16_t *src = fx ? mid : win;
+        const int sst = fx ? tw : wstride;
+        const int s2 = fx ? max(8, 20 - bd) : 6, rnd = fx ? (1 << (s2 - 1)) : 0;
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < rpl) {
+                    int acc = rnd;
+#pragma unroll
+                    for (int t = 0; t < NTAP; t++) acc += c[t] * src[(r0 + i + t) * sst + col];
+                    pr[i] = xb_clip3(0, maxv, acc >> s2);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// prediction of one tile from one or two references, result pr[] (bi-pred averaged): xevd_mc body
+template <int NTAP>
+__device__ __forceinline__ void pred_tile(const XbFrameArgs &a, const XB200_CU &cu, int plane, int tx, int ty, int tw, int th,
+                                          int rpl, int16_t *scr, int lane, int (&pr)[8])
+{
+    constexpr bool LUMA = NTAP == 8;
+    const int cuw = 1 << cu.log2w, cuh = 1 << cu.log2h;
+    const int bd = LUMA ? a.bd_l : a.bd_c;
+    const int stride = LUMA ? a.s_l : a.s_c;
+    int mvc[2][2];
+    mv_clip(cu.x, cu.y, a.w, a.h, cuw, cuh, cu.mv[0][0], cu.mv[0][1], mvc[0][0], mvc[0][1]);
+    mv_clip(cu.x, cu.y, a.w, a.h, cuw, cuh, cu.mv[1][0], cu.mv[1][1], mvc[1][0], mvc[1][1]);
+    bool use[2] = {cu.refi[0] >= 0, cu.refi[1] >= 0};
+    // identical motion: same picture (POC) and same clipped vector -> list 0 only (xevd_mc.c:513-519)
+    if (use[0] && use[1] && a.ref_poc[0][cu.refi[0]] == a.ref_poc[1][cu.refi[1]] && mvc[0][0] == mvc[1][0] && mvc[0][1] == mvc[1][1])
+        use[1] = false;
+    int n = 0;
+    int p0[8];
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        if (!use[l]) continue;
+        const int ri = cu.refi[l];
+        const pel *rp = plane == 0 ? a.ref_y[l][ri] : (plane == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
+        const int mvx = mvc[l][0], mvy = mvc[l][1];
+        int ix, iy, phx, phy;
+        bool fx, fy;
+        if (LUMA) {
+            ix = cu.x + tx + (mvx >> 2); iy = cu.y + ty + (mvy >> 2);
+            phx = (mvx & 3) << 2; phy = (mvy & 3) << 2;
+            fx = (cu.mv[l][0] & 3) != 0; fy = (cu.mv[l][1] & 3) != 0;       // variant from the unclipped vector (T3)
+        } else {
+            ix = (cu.x >> 1) + tx + (mvx >> 3); iy = (cu.y >> 1) + ty + (mvy >> 3);
+            phx = (mvx & 7) << 2; phy = (mvy & 7) << 2;
+            fx = (cu.mv[l][0] & 7) != 0; fy = (cu.mv[l][1] & 7) != 0;
+        }
+        const int16_t *cx = LUMA ? c_mc_l[a.main_tables][phx] : c_mc_c[a.main_tables][phx];
+        const int16_t *cy = LUMA ? c_mc_l[a.main_tables][phy] : c_mc_c[a.main_tables][phy];
+        if (n == 0) {
+            mc_tile<NTAP>(rp + iy * stride + ix, stride, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, p0);
+        } else {
+            mc_tile<NTAP>(rp + iy * stride + ix, stride, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, pr);
+        }
+        n++;
+    }
+    if (n == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) pr[i] = (p0[i] + pr[i] + 1) >> 1;      // xevd_average_16b_no_clip
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) pr[i] = p0[i];
+    }
+}
+
+// ---- residual phase helpers -------------------------------------------------------------------------------
+// transform-block geometry of plane `pl` for the CU covering a position
+struct TuGeom {
+    int lw, lh;         // log2 size of the transform block
+    int x0, y0;         // position inside the CTU plane
+    int coef;           // offset of the block's top-left coefficient inside the stream
+    int cstride;        // row stride of the coefficient block (the CU plane width)
+    int qp;
+    bool coded;
+};
+
+__device__ __forceinline__ int plane_coef_base(const XB200_CU &cu, int pl)
+{
+    const int n = 1 << (cu.log2w + cu.log2h);
+    int off = cu.coef_off;
+    if (pl >= 1 && (cu.cbf & 0x00f)) off += n;
+    if (pl == 2 && (cu.cbf & 0x0f0)) off += n >> 2;
+    return off;
+}
+
+template <bool IQT>
+__global__ void __launch_bounds__(kReconThreads)
+k_recon_inter(const __grid_constant__ XbFrameArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ReconSmem sm;
+    sm.carve(smem_raw, a.log2_ctu);
+    const int S = sm.S, Sc = sm.Sc, nscu = S >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctu = blockIdx.x;
+    const int ctu_x = (ctu % a.w_ctu) << a.log2_ctu, ctu_y = (ctu / a.w_ctu) << a.log2_ctu;
+    const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
+    const XB200_CU *cus = a.cus + cu0;
+    const int ncu = cu1 - cu0;
+
+    // ---- SCU -> CU map, zero residual -------------------------------------------------------------------
+    for (int i = tid; i < nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;
+    for (int i = tid; i < S * (S + 2) / 2; i += kReconThreads) ((int *)sm.res_y)[i] = 0;
+    for (int i = tid; i < Sc * (Sc + 2); i += kReconThreads) ((int *)sm.res_u)[i] = 0;     // res_u and res_v are contiguous
+    __syncthreads();
+    for (int i = tid; i < ncu; i += kReconThreads) {
+        const XB200_CU cu = cus[i];
+        const int sx = (cu.x - ctu_x) >> 2, sy = (cu.y - ctu_y) >> 2;
+        const int nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
+        for (int y = 0; y < nh; y++)
+            for (int x = 0; x < nw; x++) sm.cu_of_scu[(sy + y) * nscu + sx + x] = (uint16_t)i;
+    }
+    __syncthreads();
+
+    // ---- phase A1: column transforms -------------------------------------------------------------------------
+    // slot = (plane column, SCU row); a slot is live when a coded transform block starts at that SCU row
+    {
+        const int sh1 = IQT ? 7 : 0;
+        const int luma_slots = S * nscu, chroma_slots = Sc * nscu;
+        for (int s = tid; s < luma_slots + 2 * chroma_slots; s += kReconThreads) {
+            int pl, x, ys;
+            if (s < luma_slots) { pl = 0; ys = s / S; x = s - ys * S; }
+            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; ys = t / Sc; x = t - ys * Sc; }
+            const int xs = pl == 0 ? (x >> 2) : (x >> 1);
+            const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
+            if (ci == 0xffff) continue;
+            const XB200_CU cu = cus[ci];
+            const int bits = (cu.cbf >> (4 * pl)) & 15;
+            if (!bits) continue;
+            const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
+            const int ry = ys - cy_scu;                    // SCU row inside the CU
+            const int lhs = min((int)cu.log2h, 6) - 2;     // log2 of the transform-block height in SCUs
+            if (ry & ((1 << lhs) - 1)) continue;           // not the first row of a transform block
+            const int sub_j = ry >> lhs, sub_i = (xs - cx_scu) >> (min((int)cu.log2w, 6) - 2);
+            if (!((bits >> ((sub_j << 1) | sub_i)) & 1)) continue;
+            const int sh = pl ? 1 : 0;
+            const int lw = min((int)cu.log2w, 6) - sh, lh = min((int)cu.log2h, 6) - sh;
+            const int pw = (1 << cu.log2w) >> sh;           // CU plane width = coefficient row stride
+            const int px = x - (((cu.x - ctu_x)) >> sh);    // column inside the CU plane
+            const int py = ((ry << 2) >> sh);               // first row of the block inside the CU plane
+            const int16_t *src = a.coef + plane_coef_base(cu, pl) + py * pw + px;
+            Dequant dq;
+            dq.init(lw, lh, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l, IQT);
+            int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
+            const int ts = (pl == 0 ? S : Sc) + 1;
+            int *dst = tmp + (((ys << 2) >> sh)) * ts + x;
+            itx_line_dyn<IQT>(lh, [&](int k) { return dq.apply(src[k * pw]); }, [&](int n, int v) { dst[n * ts] = v; }, sh1);
+        }
+    }
+    __syncthreads();
+    // ---- phase A2: row transforms ------------------------------------------------------------------------------
+    {
+        const int sh2 = IQT ? 12 - (a.bd_l - 8) : 19 - (a.bd_l - 8);
+        const int luma_slots = S * nscu, chroma_slots = Sc * nscu;
+        for (int s = tid; s < luma_slots + 2 * chroma_slots; s += kReconThreads) {
+            int pl, y, xs;
+            if (s < luma_slots) { pl = 0; xs = s / S; y = s - xs * S; }
+            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; xs = t / Sc; y = t - xs * Sc; }
+            const int ys = pl == 0 ? (y >> 2) : (y >> 1);
+            const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
+            if (ci == 0xffff) continue;
+            const XB200_CU cu = cus[ci];
+            const int bits = (cu.cbf >> (4 * pl)) & 15;
+            if (!bits) continue;
+            const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
+            const int rx = xs - cx_scu;
+            const int lws = min((int)cu.log2w, 6) - 2;
+            if (rx & ((1 << lws) - 1)) continue;
+            const int sub_i = rx >> lws, sub_j = (ys - cy_scu) >> (min((int)cu.log2h, 6) - 2);
+            if (!((bits >> ((sub_j << 1) | sub_i)) & 1)) continue;
+            const int sh = pl ? 1 : 0;
+            const int lw = min((int)cu.log2w, 6) - sh;
+            const int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
+            int16_t *res = pl == 0 ? sm.res_y : (pl == 1 ? sm.res_u : sm.res_v);
+            const int ts = (pl == 0 ? S : Sc) + 1, rs = (pl == 0 ? S : Sc) + 2;
+            const int x0 = (xs << 2) >> sh;
+            const int *srow = tmp + y * ts + x0;
+            int16_t *drow = res + y * rs + x0;
+            itx_line_dyn<false>(lw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase B: prediction + reconstruction, warp per 16x16 luma tile ----------------------------------------------
+    {
+        int16_t *scr = sm.mc + warp * kMcScratchPerWarp;
+        const int tiles = S >> 4;
+        for (int t = warp; t < tiles * tiles; t += kReconWarps) {
+            const int t_x = (t % tiles) << 4, t_y = (t / tiles) << 4;        // tile origin inside the CTU (luma)
+            if (ctu_x + t_x >= a.w || ctu_y + t_y >= a.h) continue;
+            // walk the (up to 16) CUs that start inside this tile, or the single CU that covers it
+            for (int sy = 0; sy < 4; sy++) {
+                for (int sx = 0; sx < 4; sx++) {
+                    const unsigned ci = sm.cu_of_scu[((t_y >> 2) + sy) * nscu + (t_x >> 2) + sx];
+                    if (ci == 0xffff) continue;
+                    const XB200_CU cu = cus[ci];
+                    const int cx = cu.x - ctu_x, cy = cu.y - ctu_y;
+                    // piece of the CU inside this tile; handled when this SCU is the piece's top-left
+                    const int px = max(cx, t_x), py = max(cy, t_y);
+                    if (px != t_x + (sx << 2) || py != t_y + (sy << 2)) continue;
+                    const int tw = min(1 << cu.log2w, 16), th = min(1 << cu.log2h, 16);
+                    int pr[8];
+                    // luma
+                    {
+                        const int rpl = max(1, (tw * th) >> 5);
+                        pred_tile<8>(a, cu, 0, px - cx, py - cy, tw, th, rpl, scr, lane, pr);
+                        const int col = lane & (tw - 1), r0 = (lane / tw) * rpl;
+                        if (r0 < th) {
+                            pel *dst = a.cur.y + (ctu_y + py + r0) * a.s_l + ctu_x + px + col;
+                            const int16_t *res = sm.res_y + (py + r0) * (S + 2) + px + col;
+                            const int maxv = (1 << a.bd_l) - 1;
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (i < rpl) dst[i * a.s_l] = (pel)xb_clip3(0, maxv, (int16_t)(pr[i] + res[i * (S + 2)]));
+                        }
+                    }
+                    // chroma (4:2:0): both planes
+                    {
+                        const int cw = tw >> 1, ch = th >> 1;
+                        const int rpl = max(1, (cw * ch) >> 5);
+#pragma unroll
+                        for (int pl = 1; pl <= 2; pl++) {
+                            pred_tile<4>(a, cu, pl, (px - cx) >> 1, (py - cy) >> 1, cw, ch, rpl, scr, lane, pr);
+                            const int col = lane & (cw - 1), r0 = (lane / cw) * rpl;
+                            if (r0 < ch) {
+                                pel *dst = (pl == 1 ? a.cur.u : a.cur.v) + (((ctu_y + py) >> 1) + r0) * a.s_c + ((ctu_x + px) >> 1) + col;
+                                const int16_t *res = (pl == 1 ? sm.res_u : sm.res_v) + ((py >> 1) + r0) * (Sc + 2) + (px >> 1) + col;
+                                const int maxv = (1 << a.bd_l) - 1;      // the reference clips chroma with the luma depth (xevd_recon.c:70-91)
+#pragma unroll
+                                for (int i = 0; i < 8; i++)
+                                    if (i < rpl) dst[i * a.s_c] = (pel)xb_clip3(0, maxv, (int16_t)(pr[i] + res[i * (Sc + 2)]));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- phase C: publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------
+    for (int i = tid; i < nscu * nscu; i += kReconThreads) {
+        const unsigned ci = sm.cu_of_scu[i];
+        if (ci == 0xffff) continue;
+        const XB200_CU cu = cus[ci];
+        const int gx = (ctu_x >> 2) + (i % nscu), gy = (ctu_y >> 2) + (i / nscu);
+        const int p = gy * a.w_scu + gx;
+        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31);
+        if (cu.cbf & 1) m |= 1u << 24;
+        if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
+        a.map_scu[p] = m;
+        ((int2 *)a.map_mv)[p] = make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        ((int16_t *)a.map_refi)[p] = *(const int16_t *)cu.refi;
+    }
+}
+
+}  // namespace xb
