@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the XEVD reconstruction hot path on B200.
+
+Metric (BASELINE.json): 4K 10-bit frames/s of the MC + ITDQ + recon path on synthetic pre-parsed CU arrays,
+with the achieved fraction of the HBM roofline, next to the reference's own CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 4k-2A|...]
+
+A "step" is one batch of FRAMES_PER_STEP distinct pictures (reference picture, CU array, coefficient stream and
+output picture all distinct per slot, ~85 MB each at 4K, so a step streams > 10x the 126 MB L2).  Per picture the
+step runs xb200_recon_frame_dev (the picture-level replacement of xevd_ctu_row_rec_mt) followed by xb200_pad
+(xevd_picbuf_expand).  `value` times that with every input already resident in HBM; `e2e` times the same pictures
+through the host-buffer C ABI call xb200_recon_frame with pinned host inputs (H2D inside the timed region) and a
+D2H of every decoded picture.
+
+Under torchrun each rank drives its own GPU on its own share of pictures (GOP-level sharding: no data-path
+collective); the timed region is bracketed by barriers and the max over ranks is reported.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (w, h, bit_depth, variant)
+    "4k-2A": (3840, 2160, 10, "A"),
+    "4k-2B": (3840, 2160, 10, "B"),
+    "1080p-2A": (1920, 1080, 10, "A"),
+    "1080p-2B": (1920, 1080, 10, "B"),
+    "8k-2A": (7680, 4320, 10, "A"),
+}
+METRIC = "4k_10bit_frames_per_sec"
+UNIT = "frames/s"
+
+
+def algorithmic_bytes(w, h, cl, prm_bi_frac=0.0):
+    """compulsory traffic, each datum once: reference read 2 B/sample per prediction direction,
+    coefficients 2 B per coded sample, reconstruction write 2 B/sample, plus the CU descriptors."""
+    cus = cl.cus
+    samples = (1 << (cus["log2w"].astype(np.int64) + cus["log2h"].astype(np.int64))) * 3 // 2
+    ndir = (cus["refi"][:, 0] >= 0).astype(np.int64) + (cus["refi"][:, 1] >= 0).astype(np.int64)
+    ref = int((samples * ndir).sum()) * 2
+    coef = int(cl.coef.size) * 2
+    rec = int(samples.sum()) * 2
+    desc = cus.nbytes + cl.ctu_first.nbytes
+    return ref + coef + rec + desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_workload(name, n_distinct, seed0=1):
+    from xevd_b200 import synth
+    w, h, bd, variant = WORKLOADS[name]
+    frames = []
+    for i in range(n_distinct):
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=seed0 + i, n_refs=1 if variant == "A" else 2)
+        frames.append((prm, cl))
+    return w, h, bd, variant, frames
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, dispatched AVX2 kernels:
+    xevd_mc + xevdm_sub_block_itdq + xevd_recon per CU, then xevd_picbuf_expand), one single-threaded decoder
+    instance per host core, each on its own pictures (GOP-level parallelism, the only way the reference scales
+    past XEVD_MAX_TASK_CNT).  A step is a bounded sample: one picture per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.pyoracle import have_reference
+    kind = "reference" if have_reference() else "port"
+    cores = len(os.sched_getaffinity(0))
+    w, h, bd, variant, frames = make_workload(args.workload, 1)
+    prm, cl = frames[0]
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    start = ctx.Barrier(cores)
+
+    def worker(idx):
+        from oracle.pyoracle import Oracle, Reference
+        from xevd_b200 import synth
+        from xevd_b200.frame import HostPicture
+        be = Reference(2) if kind == "reference" else Oracle()
+        refs = synth.make_refs(w, h, bd, 1 if variant == "A" else 2, seed=50 + idx)
+        cur = HostPicture(w, h, prm.poc)
+        for _ in range(args.warmup):
+            be.recon_frame(prm, cur, refs, refs[::-1], cl); be.pad(cur)
+        start.wait()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            be.recon_frame(prm, cur, refs, refs[::-1], cl); be.pad(cur)
+        q.put(time.perf_counter() - t0)
+
+    procs = [ctx.Process(target=worker, args=(i,)) for i in range(cores)]
+    for p in procs:
+        p.start()
+    times = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    elapsed = max(times)
+    fps = cores * args.steps / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "s16", "data": "synthetic",
+        "config": {"workload": args.workload, "frames_per_step": cores, "inputs": "larger than L2 (host arm)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{cores} single-threaded decoder instances x {args.steps} pictures of {args.workload} each (recon + pad)"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(workload, seconds_budget=20.0):
+    """bounded CPU sample on rank 0: the reference (or the oracle port) single-threaded on whole pictures"""
+    from oracle.pyoracle import Oracle, Reference, have_reference
+    from xevd_b200 import synth
+    from xevd_b200.frame import HostPicture
+    kind = "reference" if have_reference() else "port"
+    be = Reference(2) if kind == "reference" else Oracle()
+    w, h, bd, variant, frames = make_workload(workload, 1)
+    prm, cl = frames[0]
+    refs = synth.make_refs(w, h, bd, 1 if variant == "A" else 2, seed=77)
+    cur = HostPicture(w, h, prm.poc)
+    be.recon_frame(prm, cur, refs, refs[::-1], cl)       # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        be.recon_frame(prm, cur, refs, refs[::-1], cl); be.pad(cur)
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt > seconds_budget or n >= 50:
+            break
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{n} pictures of {workload} (recon + pad), 1 thread, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from xevd_b200.device import Context
+    from xevd_b200.frame import HostPicture
+    from xevd_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    F = args.frames_per_step
+    w, h, bd, variant, frames = make_workload(args.workload, min(4, F), seed0=1 + 10 * rank)
+    n_refs = 1 if variant == "A" else 2
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = Context(local)
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- resident inputs: F slots, each with its own reference picture(s), CU array, coefficients, output picture
+    host_refs = synth.make_refs(w, h, bd, 2, seed=1000 + rank)
+    slots = []
+    with torch.cuda.stream(stream):
+        for i in range(F):
+            prm, cl = frames[i % len(frames)]
+            refs = [ctx.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
+            for j, r in enumerate(refs):
+                r.set_poc(host_refs[(i + j) % 2].poc if n_refs > 1 else 0)
+            cur = ctx.pic_alloc(w, h)
+            d_cus = torch.from_numpy(cl.cus.view(np.uint8).copy()).to(dev)
+            d_first = torch.from_numpy(cl.ctu_first.view(np.int32).copy()).to(dev)
+            d_ext = torch.from_numpy(cl.ext.view(np.uint8).copy()).to(dev)
+            d_coef = torch.from_numpy(cl.coef.copy()).to(dev)
+            slots.append(dict(prm=prm, cl=cl, refs=refs, cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef))
+    torch.cuda.synchronize()
+
+    def step_resident():
+        for s in slots:
+            cl = s["cl"]
+            ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs"][::-1], s["d_cus"].data_ptr(), cl.n_cu,
+                                s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size)
+            ctx.pad(s["cur"])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs ----------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+    barrier()
+    launches = ctx.launches - l0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    fps = world * F * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (k_recon_inter): per-launch CUDA-event timing on the launching stream --------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * min(args.steps, 4))]
+    k = 0
+    with torch.cuda.stream(stream):
+        for _ in range(min(args.steps, 4)):
+            for s in slots:
+                cl = s["cl"]
+                ev[k][0].record(stream)
+                ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs"][::-1], s["d_cus"].data_ptr(), cl.n_cu,
+                                    s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size)
+                ev[k][1].record(stream)
+                ctx.pad(s["cur"])
+                k += 1
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    alg = float(np.mean([algorithmic_bytes(w, h, s["cl"]) for s in slots]))
+    peak, peak_src = measured_peak()
+    achieved = alg / (kern_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------------------------------------
+    n_ctx = 3
+    ctxs, streams = [], []
+    for i in range(n_ctx):
+        st = torch.cuda.Stream(device=dev)
+        c = Context(local)
+        c.set_stream(st.cuda_stream)
+        ctxs.append(c); streams.append(st)
+    pinned = []
+    for i in range(F):
+        prm, cl = frames[i % len(frames)]
+        pc = dict(cus=torch.from_numpy(cl.cus.view(np.uint8).copy()).pin_memory(),
+                  first=torch.from_numpy(cl.ctu_first.view(np.int32).copy()).pin_memory(),
+                  ext=torch.from_numpy(cl.ext.view(np.uint8).copy()).pin_memory(),
+                  coef=torch.from_numpy(cl.coef.copy()).pin_memory(),
+                  out_y=torch.empty((h, w), dtype=torch.int16).pin_memory(),
+                  out_u=torch.empty((h // 2, w // 2), dtype=torch.int16).pin_memory(),
+                  out_v=torch.empty((h // 2, w // 2), dtype=torch.int16).pin_memory())
+        pinned.append(pc)
+    # pictures owned per context (a device picture belongs to the stream that fills it)
+    e2e_slots = []
+    for i in range(F):
+        c = ctxs[i % n_ctx]
+        refs = [c.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
+        e2e_slots.append(dict(ctx=c, refs=refs, cur=c.pic_alloc(w, h)))
+    torch.cuda.synchronize()
+    h2d = int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
+    d2h = F * (w * h * 3 // 2) * 2
+
+    def step_e2e():
+        for i in range(F):
+            prm, cl = frames[i % len(frames)]
+            s, p = e2e_slots[i], pinned[i]
+            c = s["ctx"]
+            c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
+                                           (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
+                                           (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), n_refs,
+                                           p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
+                                           p["ext"].data_ptr(), len(cl.ext), p["coef"].data_ptr(), cl.coef.size), "xb200_recon_frame")
+            c.pad(s["cur"])
+            c._chk(c.lib.xb200_pic_download(c.handle, s["cur"].handle, p["out_y"].data_ptr(), w, p["out_u"].data_ptr(), w // 2,
+                                            p["out_v"].data_ptr(), w // 2), "xb200_pic_download")
+        for c in ctxs:
+            c.sync()
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_fps = world * F * e2e_steps / t_e2e
+    # a decoded sample read back on the host proves the D2H happened
+    checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(args.workload)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16", "data": "synthetic",
+            "config": {"workload": args.workload, "frames_per_step": F * world, "picture": f"{w}x{h} 4:2:0 {bd}-bit",
+                       "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
+                       "per_picture": "xb200_recon_frame_dev + xb200_pad", "parallelism": f"gop-sharded x{world}",
+                       "l2": f"inputs larger than L2 ({F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per step per GPU)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_recon_inter", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
+            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "contexts": n_ctx, "checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="4k-2A", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
