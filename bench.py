@@ -233,14 +233,16 @@ def run_ours(args):
             d_first = torch.from_numpy(cl.ctu_first.view(np.int32).copy()).to(dev)
             d_ext = torch.from_numpy(cl.ext.view(np.uint8).copy()).to(dev)
             d_coef = torch.from_numpy(cl.coef.copy()).to(dev)
-            slots.append(dict(prm=prm, cl=cl, refs=refs, cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef))
+            slots.append(dict(prm=prm, cl=cl, refs=refs, cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef,
+                              max_cu=int(np.diff(cl.ctu_first.astype(np.int64)).max())))
     torch.cuda.synchronize()
 
     def step_resident():
         for s in slots:
             cl = s["cl"]
             ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs"][::-1], s["d_cus"].data_ptr(), cl.n_cu,
-                                s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size)
+                                s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
+                                max_cu_per_ctu=s["max_cu"])
             ctx.pad(s["cur"])
 
     def barrier():
@@ -282,7 +284,8 @@ def run_ours(args):
                 cl = s["cl"]
                 ev[k][0].record(stream)
                 ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs"][::-1], s["d_cus"].data_ptr(), cl.n_cu,
-                                    s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size)
+                                    s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
+                                max_cu_per_ctu=s["max_cu"])
                 ev[k][1].record(stream)
                 ctx.pad(s["cur"])
                 k += 1

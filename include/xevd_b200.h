@@ -90,7 +90,9 @@ typedef struct XB200_CU {
     uint16_t reserved;
     uint32_t coef_off;        /* offset (in int16 units) of this CU's coefficients inside the
                                  coefficient stream: [Y w*h][Cb w*h/4][Cr w*h/4], CU-raster;
-                                 planes whose cbf bits are all 0 are absent (no bytes)           */
+                                 planes whose cbf bits are all 0 are absent (no bytes); every
+                                 plane block starts on a multiple of 8 int16 (16 bytes) and is
+                                 zero-padded up to one (only 4-wide/4-high CUs ever need pad)    */
 } XB200_CU;
 
 /* extension record, 32 bytes: meaning depends on XB200_CU.mode */
@@ -192,7 +194,8 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
                        xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
                        const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
                        const void *d_ext, int n_ext,
-                       const void *d_coef, size_t n_coef, int has_intra);
+                       const void *d_coef, size_t n_coef, int has_intra, int max_cu_per_ctu);
+/* max_cu_per_ctu: upper bound of ctu_first[k+1]-ctu_first[k] (sizes on-chip work lists); 0 = unknown (worst case) */
 
 /* ---- picture-wide in-loop filters ------------------------------------------------------------------ */
 /* edge flags, one byte per SCU */

@@ -55,8 +55,9 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         const int16_t *c = coef + cu->coef_off;
         const int has_y = (cu->cbf & 0x00f) != 0, has_u = (cu->cbf & 0x0f0) != 0, has_v = (cu->cbf & 0xf00) != 0;
 
-        if (has_y) { memcpy(ry, c, sizeof(int16_t) * w * h); c += w * h; }
-        if (has_u) { memcpy(ru, c, sizeof(int16_t) * cw * ch); c += cw * ch; }
+        /* plane blocks are padded to multiples of 8 coefficients (include/xevd_b200.h) */
+        if (has_y) { memcpy(ry, c, sizeof(int16_t) * w * h); c += (w * h + 7) & ~7; }
+        if (has_u) { memcpy(ru, c, sizeof(int16_t) * cw * ch); c += (cw * ch + 7) & ~7; }
         if (has_v) { memcpy(rv, c, sizeof(int16_t) * cw * ch); }
         orc_itdq_cu(prm, cu, ry, ru, rv);
 

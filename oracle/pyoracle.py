@@ -45,8 +45,24 @@ def orc_pic(p: HostPicture) -> OrcPic:
 
 
 def build(force: bool = False) -> None:
-    """compile the C restatement (and the reference harness when /root/reference is present)"""
-    subprocess.run(["make", "-s", "-C", str(HERE), "-j8", "all"] + (["-B"] if force else []), check=True)
+    """compile the C restatement (and the reference harness when /root/reference is present).
+    make is a no-op when the libraries are newer than their sources."""
+    subprocess.run(["make", "-s", "-C", str(HERE), "-j8", "all"] + (["-B"] if force else []), check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+_built = False
+
+
+def _ensure_built():
+    global _built
+    if not _built:
+        try:
+            build()
+        except (OSError, subprocess.CalledProcessError):
+            if not ORACLE_SO.exists():
+                raise
+        _built = True
 
 
 def _ptr_array(pics):
@@ -122,8 +138,7 @@ class _Backend:
 
 class Oracle(_Backend):
     def __init__(self):
-        if not ORACLE_SO.exists():
-            build()
+        _ensure_built()
         super().__init__(ORACLE_SO, "orc_")
         L = self.lib
         L.orc_dct2_matrix.restype = C.POINTER(C.c_int8)
@@ -152,6 +167,7 @@ class Reference(_Backend):
     """the unmodified reference library; impl 0 = plain C, 1 = SSE4.1, 2 = AVX2 (dispatched on x86)"""
 
     def __init__(self, impl: int = 2):
+        _ensure_built()
         super().__init__(REF_SO, "ref_")
         self.lib.ref_set_impl.argtypes = [C.c_int]
         self.lib.ref_set_impl(impl)

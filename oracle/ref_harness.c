@@ -189,8 +189,8 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             is_coef[l] = bits != 0;
             for (i = 0; i < MAX_SUB_TB_NUM; i++) nnz_sub[l][i] = (bits >> i) & 1;
         }
-        if (is_coef[Y_C]) { memcpy(s->coef[Y_C], c, sizeof(s16) * w * h); c += w * h; }
-        if (is_coef[U_C]) { memcpy(s->coef[U_C], c, sizeof(s16) * cw * ch); c += cw * ch; }
+        if (is_coef[Y_C]) { memcpy(s->coef[Y_C], c, sizeof(s16) * w * h); c += (w * h + 7) & ~7; }
+        if (is_coef[U_C]) { memcpy(s->coef[U_C], c, sizeof(s16) * cw * ch); c += (cw * ch + 7) & ~7; }
         if (is_coef[V_C]) { memcpy(s->coef[V_C], c, sizeof(s16) * cw * ch); }
         if (cu->cbf)
             xevdm_sub_block_itdq(g_ctx, s->coef, cu->log2w, cu->log2h, cu->qp_y, cu->qp_u, cu->qp_v, is_coef, nnz_sub,

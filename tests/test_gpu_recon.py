@@ -69,3 +69,51 @@ def test_pad(ctx, oracle):
     want = oracle.pad(p.copy())
     assert np.array_equal(got.buf_y, want.buf_y) and np.array_equal(got.buf_u, want.buf_u) and np.array_equal(got.buf_v, want.buf_v)
     d.free()
+
+
+def test_fast_and_generic_kernels_agree(oracle, monkeypatch):
+    """the throughput kernel (xb_recon2.cuh) and the generic kernel (xb_recon.cuh) are two implementations of the
+    same contract: run both on one picture (XB200_FORCE_GENERIC selects the generic one at context creation)"""
+    from xevd_b200.device import Context
+    w, h, bd = 320, 192, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=21, n_refs=2, coded_frac=0.7)
+    refs = synth.make_refs(w, h, bd, 2, seed=22)
+    outs = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("XB200_FORCE_GENERIC", force)
+        c = Context(0)
+        drefs = [c.pic_alloc(w, h).upload(r) for r in refs]
+        cur = c.pic_alloc(w, h)
+        c.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        outs.append(cur.download(maps=True))
+        c.close()
+    for a, b in zip(outs[0].planes(), outs[1].planes()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(outs[0].map_mv, outs[1].map_mv) and np.array_equal(outs[0].map_scu, outs[1].map_scu)
+
+
+def test_inter_4x4_cus(ctx, oracle):
+    # smallest Baseline CUs: 4x4 luma with 2x2 chroma transform blocks, multiple MC rounds per CTU
+    _run(ctx, oracle, 64, 64, 10, "A", seed=9, log2_cu=2)
+
+
+def test_inter_64x64_cus(ctx, oracle):
+    _run(ctx, oracle, 256, 128, 10, "A", seed=10, log2_cu=6, n_refs=2, bi_frac=0.5)
+
+
+def test_recon_saturating_residual(ctx, oracle):
+    # huge coefficients: dequant clips to s16, the residual add wraps to 16 bits before the pixel clip (xevd_recon.c:60)
+    w, h, bd = 128, 64, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="A", seed=12, n_refs=1)
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, cl.coef.size, 200)
+    cl.coef[idx] = rng.choice(np.array([-32768, 32767, -20000, 20000], np.int16), 200)
+    cl.coef[cl.cus["coef_off"][::7]] = 3000      # large DC terms: residuals beyond +-2^15 before the clip
+    refs = synth.make_refs(w, h, bd, 1, seed=13)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs, cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs, cl)
+    got = cur.download()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"

@@ -12,6 +12,7 @@
 #include "xb_common.cuh"
 #include "xb_itdq.cuh"
 #include "xb_recon.cuh"
+#include "xb_recon2.cuh"
 #include "xb_filters.cuh"
 #include "xb_micro.cuh"
 
@@ -20,6 +21,7 @@ struct xb200_pic {
     size_t luma_elems, chroma_elems;
     pel *buf;                    // one allocation: Y | U | V padded planes
     pel *y, *u, *v;              // sample (0,0)
+    CUtensorMap *d_tmaps;        // device copy of 3 TMA descriptors (whole padded Y, U, V planes)
     int16_t *map_mv;
     int8_t *map_refi;
     uint32_t *map_scu;
@@ -41,6 +43,7 @@ struct xb200_ctx {
     Staging ring[3];
     int ring_pos;
     int sm_count;
+    bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
 
 #define CK(ctx, call)                                                                              \
@@ -87,6 +90,9 @@ xb200_ctx *xb200_create(int device, int *err)
     // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB)
     cudaFuncSetAttribute(xb::k_recon_inter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
     cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
     if (err) *err = XB200_OK;
     return c;
 }
@@ -124,6 +130,44 @@ int xb200_set_stream(xb200_ctx *c, void *s)
 long long xb200_launch_count(xb200_ctx *c) { return c ? c->launches : 0; }
 
 // ---- pictures ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// TMA descriptors over the whole padded planes: box 40x23 (luma) / 24x11 (chroma) = the 8-sample-aligned superset of
+// the interpolation window of a 16x16 tile (8-tap: +7, 4-tap: +3)
+static int make_tensor_maps(xb200_ctx *c, xb200_pic *p)
+{
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {
+            snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled unavailable");
+            return XB200_ERR_CUDA;
+        }
+        encode = (PFN_encodeTiled)fn;
+    }
+    alignas(64) CUtensorMap maps[3];
+    for (int pl = 0; pl < 3; pl++) {
+        const bool luma = pl == 0;
+        void *base = luma ? (void *)p->buf : (void *)(p->buf + p->luma_elems + (pl == 2 ? p->chroma_elems : 0));
+        const cuuint64_t dims[2] = {(cuuint64_t)(luma ? p->s_l : p->s_c), (cuuint64_t)(luma ? p->h + 2 * p->pad_l : p->h_c + 2 * p->pad_c)};
+        const cuuint64_t strides[1] = {(cuuint64_t)(luma ? p->s_l : p->s_c) * 2};
+        const cuuint32_t box[2] = {luma ? (cuuint32_t)xb::kBoxLW : (cuuint32_t)xb::kBoxCW, luma ? (cuuint32_t)xb::kBoxLH : (cuuint32_t)xb::kBoxCH};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled failed (%d) plane %d", (int)r, pl);
+            return XB200_ERR_CUDA;
+        }
+    }
+    CK(c, cudaMemcpyAsync(p->d_tmaps, maps, sizeof(maps), cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
 xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
 {
     if (!c || w <= 0 || h <= 0 || (w & 7) || (h & 7)) { if (err) *err = XB200_ERR_INVALID_ARGUMENT; return nullptr; }
@@ -132,7 +176,8 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     if (!p) { if (err) *err = XB200_ERR_OUT_OF_MEMORY; return nullptr; }
     p->w = w; p->h = h; p->w_c = w >> 1; p->h_c = h >> 1;
     p->pad_l = 144; p->pad_c = 72;                       // PIC_PAD_SIZE_L / _C (xevd_def.h:211-212)
-    p->s_l = w + 2 * p->pad_l; p->s_c = p->w_c + 2 * p->pad_c;
+    // strides: the reference's (w + 2*pad), chroma rounded up to 8 samples so every row is 16-byte aligned (TMA)
+    p->s_l = w + 2 * p->pad_l; p->s_c = (p->w_c + 2 * p->pad_c + 7) & ~7;
     p->w_scu = (w + 3) >> 2; p->h_scu = (h + 3) >> 2;
     p->poc = 0;
     p->luma_elems = (size_t)p->s_l * (h + 2 * p->pad_l);
@@ -140,7 +185,7 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     const size_t nscu = (size_t)p->w_scu * p->h_scu;
     const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
     const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
-    const size_t total = pix_al + nscu * (8 + 4 + 2) + 256;
+    const size_t total = pix_al + ((nscu * (8 + 4 + 2) + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
     if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
         delete p;
@@ -155,6 +200,13 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     p->map_mv = (int16_t *)m;
     p->map_scu = (uint32_t *)(m + nscu * 8);
     p->map_refi = (int8_t *)(m + nscu * 12);
+    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 14 + 255) & ~(size_t)255));
+    if (make_tensor_maps(c, p) != XB200_OK) {
+        cudaFree(p->buf);
+        delete p;
+        if (err) *err = XB200_ERR_CUDA;
+        return nullptr;
+    }
     if (err) *err = XB200_OK;
     return p;
 }
@@ -201,9 +253,12 @@ int xb200_pic_download(xb200_ctx *c, xb200_pic *p, xb200_pel *y, int sy, xb200_p
 int xb200_pic_download_padded(xb200_ctx *c, xb200_pic *p, xb200_pel *y, xb200_pel *u, xb200_pel *v)
 {
     if (!c || !p || !y || !u || !v) return XB200_ERR_INVALID_ARGUMENT;
+    // host layout = the reference's (stride w + 2*pad); the device chroma stride may be wider
+    const int hs_c = p->w_c + 2 * p->pad_c;
     CK(c, cudaMemcpyAsync(y, p->buf, p->luma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(u, p->buf + p->luma_elems, p->chroma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(v, p->buf + p->luma_elems + p->chroma_elems, p->chroma_elems * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(u, hs_c * 2, p->buf + p->luma_elems, p->s_c * 2, hs_c * 2, p->h_c + 2 * p->pad_c, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(v, hs_c * 2, p->buf + p->luma_elems + p->chroma_elems, p->s_c * 2, hs_c * 2, p->h_c + 2 * p->pad_c,
+                            cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return XB200_OK;
 }
@@ -238,6 +293,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
             if (!lst || !lst[i] || lst[i]->w != cur->w || lst[i]->h != cur->h) return XB200_ERR_INVALID_ARGUMENT;
             a.ref_y[l][i] = lst[i]->y; a.ref_u[l][i] = lst[i]->u; a.ref_v[l][i] = lst[i]->v;
             a.ref_poc[l][i] = lst[i]->poc;
+            a.ref_tmap[l * XB_MAX_REFS + i] = lst[i]->d_tmaps;
         }
     }
     a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
@@ -255,7 +311,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
 int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
                           xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
                           const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
-                          const void *d_ext, int n_ext, const void *d_coef, size_t n_coef, int has_intra)
+                          const void *d_ext, int n_ext, const void *d_coef, size_t n_coef, int has_intra, int max_cu_per_ctu)
 {
     XbFrameArgs a;
     int r = fill_args(c, prm, cur, l0, n0, l1, n1, a);
@@ -269,9 +325,19 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
-    const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
-    if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
-    else       xb::k_recon_inter<false><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
+    if (!a.iqt && a.log2_ctu == 6 && !c->force_generic) {
+        // throughput kernel (xb_recon2.cuh): Baseline transform path, 64x64 CTUs
+        int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
+        max_cu = (max_cu + 15) & ~15;
+        const bool bi = n1 > 0;
+        const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu);
+        if (bi) xb::k_recon_inter_v2<true><<<a.n_ctu, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        else    xb::k_recon_inter_v2<false><<<a.n_ctu, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+    } else {
+        const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
+        if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
+        else       xb::k_recon_inter<false><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     return XB200_OK;
@@ -314,11 +380,12 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     memcpy(hp + b_cu, ctu_first, (size_t)(n_ctu + 1) * 4);
     if (ext && n_ext > 0) memcpy(hp + b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT));
     if (coef && n_coef) memcpy(hp + b_cu + b_first + b_ext, coef, n_coef * 2);
-    int has_intra = 0;
+    int has_intra = 0, max_cu = 0;
     for (int i = 0; i < n_cu; i++) has_intra |= (cus[i].mode == XB200_MODE_INTRA);
+    for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
     CK(c, cudaMemcpyAsync(dp, hp, b_cu + b_first + b_ext + b_coef, cudaMemcpyHostToDevice, c->stream));
     r = xb200_recon_frame_dev(c, prm, cur, l0, n0, l1, n1, dp, n_cu, dp + b_cu, n_ctu, dp + b_cu + b_first, n_ext,
-                              dp + b_cu + b_first + b_ext, n_coef, has_intra);
+                              dp + b_cu + b_first + b_ext, n_coef, has_intra, max_cu);
     CK(c, cudaEventRecord(s->done, c->stream));
     s->busy = true;
     return r;

@@ -5,6 +5,7 @@
 // map_refi and ctx->map_scu.  CU work items, the coefficient stream and the per-CTU index are the
 // flat arrays of include/xevd_b200.h.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/xevd_b200.h"
@@ -24,6 +25,7 @@ struct XbFrameArgs {
     const pel *ref_u[2][XB_MAX_REFS];
     const pel *ref_v[2][XB_MAX_REFS];
     int ref_poc[2][XB_MAX_REFS];
+    const CUtensorMap *ref_tmap[2 * XB_MAX_REFS];   // per reference picture: 3 TMA descriptors (Y, U, V) in device memory
     int s_l, s_c;               // strides in pels (same geometry for every picture of a sequence)
     int w, h;                   // luma size
     int bd_l, bd_c;

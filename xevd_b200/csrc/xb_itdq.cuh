@@ -100,3 +100,70 @@ __device__ __forceinline__ void itx_line_dyn(int log2n, LoadFn load, StoreFn sto
 }
 
 }  // namespace xb
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed first pass: inputs are dequantised coefficients (s16 range), kernel entries are s8, so two
+// multiply-adds fit one IDP.2A (dp2a: s16x2 . s8x2 + s32).  Same even/odd factorisation; the pairs
+// (X[k], X[k+2s]) are packed once per level and reused by every output of that level.
+// Measured on B200 (profiles/r1/int_pipes_b200.txt): IDP.2A and IMAD both issue at 64 lanes/clk/SM, so this
+// halves the multiplier-pipe work of the pass.
+namespace xb {
+
+__device__ __forceinline__ constexpr int pk8(int lo, int hi) { return (lo & 0xff) | ((hi & 0xff) << 8); }
+__device__ __forceinline__ int pack16(int lo, int hi) { return __byte_perm(lo, hi, 0x5410); }
+
+// M-point inverse DCT-2 over v[S * k], k = 0..M-1 (v values must fit s16)
+template <int M, int S, int NV> struct InvDct2P {
+    static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[M])
+    {
+        int E[M / 2];
+        InvDct2P<M / 2, 2 * S, NV>::run(v, E);
+        int pr[M / 4];
+#pragma unroll
+        for (int j = 0; j < M / 4; j++) pr[j] = pack16(v[S * (4 * j + 1)], v[S * (4 * j + 3)]);
+#pragma unroll
+        for (int n = 0; n < M / 2; n++) {
+            int o = 0;
+#pragma unroll
+            for (int j = 0; j < M / 4; j++) o = __dp2a_lo(pr[j], pk8(tm<M>(4 * j + 1, n), tm<M>(4 * j + 3, n)), o);
+            out[n] = E[n] + o;
+            out[M - 1 - n] = E[n] - o;
+        }
+    }
+};
+template <int S, int NV> struct InvDct2P<2, S, NV> {
+    static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[2])
+    {
+        const int p = pack16(v[0], v[S]);
+        out[0] = __dp2a_lo(p, pk8(64, 64), 0);
+        out[1] = __dp2a_lo(p, pk8(64, -64), 0);
+    }
+};
+
+// second pass on s32 inputs with the rounding constant folded into the 2-point base case
+template <int N> struct InvDct2R {
+    static __device__ __forceinline__ void run(const int (&in)[N], int (&out)[N], int rnd)
+    {
+        int ev[N / 2], E[N / 2];
+#pragma unroll
+        for (int k = 0; k < N / 2; k++) ev[k] = in[2 * k];
+        InvDct2R<N / 2>::run(ev, E, rnd);
+#pragma unroll
+        for (int n = 0; n < N / 2; n++) {
+            int o = 0;
+#pragma unroll
+            for (int k = 1; k < N; k += 2) o += tm<N>(k, n) * in[k];
+            out[n] = E[n] + o;
+            out[N - 1 - n] = E[n] - o;
+        }
+    }
+};
+template <> struct InvDct2R<2> {
+    static __device__ __forceinline__ void run(const int (&in)[2], int (&out)[2], int rnd)
+    {
+        out[0] = 64 * (in[0] + in[1]) + rnd;
+        out[1] = 64 * (in[0] - in[1]) + rnd;
+    }
+};
+
+}  // namespace xb

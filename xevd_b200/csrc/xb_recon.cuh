@@ -206,8 +206,8 @@ __device__ __forceinline__ int plane_coef_base(const XB200_CU &cu, int pl)
 {
     const int n = 1 << (cu.log2w + cu.log2h);
     int off = cu.coef_off;
-    if (pl >= 1 && (cu.cbf & 0x00f)) off += n;
-    if (pl == 2 && (cu.cbf & 0x0f0)) off += n >> 2;
+    if (pl >= 1 && (cu.cbf & 0x00f)) off += (n + 7) & ~7;
+    if (pl == 2 && (cu.cbf & 0x0f0)) off += ((n >> 2) + 7) & ~7;
     return off;
 }
 

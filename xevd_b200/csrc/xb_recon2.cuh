@@ -1,0 +1,630 @@
+// xb_recon2.cuh -- throughput-oriented inter reconstruction kernel (Baseline transform path, 64x64 CTUs).
+//
+// Same contract as k_recon_inter (xb_recon.cuh): one CTA reconstructs one CTU from the flat CU work items.
+// What is different is how the work is laid onto the SM:
+//
+//   * reference windows arrive by TMA (cp.async.bulk.tensor.2d): one 40x23 (luma) / 24x11 (chroma) box per
+//     16x16 tile, issued up front so the HBM latency hides behind the residual phase; completion by mbarrier.
+//     The hardware wants the box to start on a 16-byte boundary (measured: profiles/microbench/tma_probe*.cu), so
+//     the box is the 8-sample-aligned superset of the window and the horizontal stage absorbs the 0..7 sample
+//     offset (word offset by addressing, odd offsets by swapping the tap sets of even and odd outputs).
+//   * residual: thread-per-line butterflies in registers.  The Baseline 2-D inverse DCT is an exact integer
+//     matrix product modulo 2^32, so the row pass is done first on the s16 inputs with IDP.2A
+//     (packed s16x2 . s8x2) and the column pass second with IMAD on the s32 intermediate.
+//   * interpolation: IDP.2A on packed pixel pairs; the horizontal stage emits vertical pairs so the vertical
+//     stage needs no repacking; variants 00/n0/0n/nn are one code path (phase-0 taps are an exact copy).
+//   * reconstruction: VIADDMNMX.S16x2.RELU = clip3(0, max, (s16)(pred + resid)) for two samples per instruction.
+//
+// Reference arithmetic restated: xevd_mc (src_base/xevd_mc.c:169-557), xevd_itdq / xevd_dquant
+// (src_base/xevd_itdq.c:472-542), xevd_recon (src_base/xevd_recon.c:36-68), xevd_set_dec_info
+// (src_base/xevd_util.c:1574-1650).
+#pragma once
+#include <cuda.h>
+#include "xb_common.cuh"
+#include "xb_itdq.cuh"
+#include "xb_recon.cuh"
+
+namespace xb {
+
+constexpr int kR2Threads = 256;
+constexpr int kTileCap = 16;                 // 16x16 luma tiles staged per round (a whole 64x64 CTU)
+constexpr int kBoxLW = 40, kBoxLH = 23;      // luma TMA box: (offset <= 7) + 16 + 7 = 30 -> 40 samples keeps the row stride
+constexpr int kBoxCW = 24, kBoxCH = 11;      //   at 20 words (8 rows = 8 distinct bank quads); chroma: 7 + 8 + 3 = 18 -> 24
+constexpr int kWinLBytes = 1920;             // 40 x 23 x 2 = 1840, rounded to a multiple of 128
+constexpr int kWinCBytes = 640;              // 24 x 11 x 2 = 528
+constexpr int kWinLStrideW = kBoxLW / 2;     // window row stride in 32-bit words
+constexpr int kWinCStrideW = kBoxCW / 2;
+constexpr int kM2LStrideW = 20;              // vertical-pair buffer row stride (16 columns + 4 pad), words
+constexpr int kM2LWords = 12 * kM2LStrideW;  // 12 pair-rows
+constexpr int kM2CStrideW = 12;              // 8 columns + 4 pad
+constexpr int kM2CWords = 6 * kM2CStrideW;   // 6 pair-rows
+constexpr int kTmpLStride = 68;              // pass-1 result row stride, words (64 + 4)
+constexpr int kTmpCStride = 36;
+constexpr int kResLStride = 72;              // residual row stride, int16 (64 + 8)
+constexpr int kResCStride = 40;
+
+struct TuDesc {                              // one transform block (16 bytes)
+    uint32_t coef_off;                       // first coefficient, int16 units
+    uint16_t tmp_off;                        // word offset of (0,0) inside the plane's pass-1 buffer
+    uint16_t res_off;                        // int16 offset of (0,0) inside the plane's residual buffer
+    uint8_t lw_lh;                           // log2w | log2h << 4
+    uint8_t plane_wide;                      // plane | wide << 2
+    uint8_t cstride_log2;                    // log2 of the coefficient row stride
+    uint8_t shift;
+    int32_t mul;
+};
+
+struct TileDesc {                            // one <=16x16 luma tile of a CU (8 bytes) + per-list data
+    uint16_t cu;
+    uint8_t px, py;                          // origin inside the CTU (luma samples)
+    uint8_t tw, th;                          // luma size
+    uint8_t nl;                              // number of prediction lists actually used (1 or 2)
+    uint8_t pad;
+};
+struct TilePred {                            // 16 bytes, per (tile, used list)
+    int16_t wx, wy;                          // luma window origin, padded-plane coordinates
+    int16_t cwx, cwy;                        // chroma window origin
+    uint8_t phx, phy, cphx, cphy;            // tap table rows (clipped vector)
+    uint8_t two_d, ctwo_d;                   // variant nn selected by the UNCLIPPED vector (T3)
+    uint8_t ref;                             // list * XB_MAX_REFS + refi
+    uint8_t offs;                            // sample offset of the window inside its 8-aligned box: luma | chroma << 4
+};
+
+struct R2Layout {                            // byte offsets inside dynamic shared memory
+    int win_l, win_c, scratch, res_y, res_u, res_v, cus, tus, lines1, lines2, tiles, preds, misc, taps, total;
+    __host__ __device__ static R2Layout make(int nl, int max_cu)
+    {
+        R2Layout L;
+        int o = 128;                                                       // [0,128): mbarrier + counters
+        L.misc = 0;
+        L.win_l = o; o += nl * kTileCap * kWinLBytes;
+        L.win_c = o; o += nl * kTileCap * 2 * kWinCBytes;
+        const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
+        const int m2_bytes = 4 * nl * kTileCap * (kM2LWords + 2 * kM2CWords);
+        L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
+        L.res_y = o; o += 2 * 64 * kResLStride;
+        L.res_u = o; o += 2 * 32 * kResCStride;
+        L.res_v = o; o += 2 * 32 * kResCStride;
+        L.cus = o; o += 32 * max_cu;
+        L.tus = o; o += 16 * 3 * max_cu;
+        // lines per pass: sum over CUs of (h + 2 * h/2) <= 2 * 64*64/4 = 2048 (all 4-wide CUs), and <= 128 per CU
+        const int max_lines = max_cu * 128 > 2048 ? 2048 : max_cu * 128;
+        L.lines1 = o; o += max_lines * 2;              // uint16 entries
+        L.lines2 = o; o += max_lines * 2;
+        const int max_tiles = max_cu < 16 ? 16 : max_cu;
+        L.tiles = o; o += 8 * max_tiles;
+        L.preds = o; o += 16 * 2 * max_tiles;
+        L.taps = o; o += 4 * (16 * 9 + 32 * 6);
+        L.total = (o + 127) & ~127;
+        return L;
+    }
+};
+
+// ---- small PTX wrappers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int pack_sat16(int lo, int hi)
+{
+    int r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
+
+// Packed tap words for IDP.2A.  A filter applied to packed sample pairs p[0..4] (5 words = 10 samples) is a sequence
+// of five (lo, hi) tap pairs T0..T4, stored as three registers r0 = T0 | T1 << 16, r1 = T2 | T3 << 16, r2 = T4.
+//   output aligned to p[0].lo          : A0 = (c0,c1)(c2,c3)(c4,c5)(c6,c7)(0,0)
+//   output starting at p[0].hi         : B  = (0,c0)(c1,c2)(c3,c4)(c5,c6)(c7,0)
+//   output aligned to p[1].lo          : A1 = (0,0)(c0,c1)(c2,c3)(c4,c5)(c6,c7)
+// With an even sample offset even outputs use A0 and odd outputs B; with an odd offset even outputs use B and odd
+// outputs A1 -- the same five words either way, so the stage is branch-free.
+struct Taps5 { int r0, r1, r2; };
+__device__ __forceinline__ int fir5(const Taps5 &t, int p0, int p1, int p2, int p3, int p4, int acc)
+{
+    acc = __dp2a_lo(p0, t.r0, acc); acc = __dp2a_hi(p1, t.r0, acc);
+    acc = __dp2a_lo(p2, t.r1, acc); acc = __dp2a_hi(p3, t.r1, acc);
+    acc = __dp2a_lo(p4, t.r2, acc);
+    return acc;
+}
+// 4-tap: three pairs T0..T2 in two registers (r0 = T0 | T1 << 16, r1 = T2)
+struct Taps3 { int r0, r1; };
+__device__ __forceinline__ int fir3(const Taps3 &t, int p0, int p1, int p2, int acc)
+{
+    acc = __dp2a_lo(p0, t.r0, acc); acc = __dp2a_hi(p1, t.r0, acc);
+    acc = __dp2a_lo(p2, t.r1, acc);
+    return acc;
+}
+__device__ __forceinline__ int pk2(int lo, int hi) { return (lo & 0xff) | ((hi & 0xff) << 8); }
+// tap-set tables in shared memory: luma [phase][set 0..2 = A0, B, A1][3 regs], chroma [phase][set][2 regs]
+__device__ __forceinline__ void build_taps8(const int16_t *c, int *dst)
+{
+    const int a0 = pk2(c[0], c[1]), a1 = pk2(c[2], c[3]), a2 = pk2(c[4], c[5]), a3 = pk2(c[6], c[7]);
+    const int b0 = pk2(0, c[0]), b1 = pk2(c[1], c[2]), b2 = pk2(c[3], c[4]), b3 = pk2(c[5], c[6]), b4 = pk2(c[7], 0);
+    dst[0] = a0 | (a1 << 16); dst[1] = a2 | (a3 << 16); dst[2] = 0;
+    dst[3] = b0 | (b1 << 16); dst[4] = b2 | (b3 << 16); dst[5] = b4;
+    dst[6] = (a0 << 16);      dst[7] = a1 | (a2 << 16); dst[8] = a3;
+}
+__device__ __forceinline__ void build_taps4(const int16_t *c, int *dst)
+{
+    const int a0 = pk2(c[0], c[1]), a1 = pk2(c[2], c[3]);
+    const int b0 = pk2(0, c[0]), b1 = pk2(c[1], c[2]), b2 = pk2(c[3], 0);
+    dst[0] = a0 | (a1 << 16); dst[1] = 0;
+    dst[2] = b0 | (b1 << 16); dst[3] = b2;
+    dst[4] = (a0 << 16);      dst[5] = a1;
+}
+
+// ---- residual pass 1: one row of a transform block -----------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int *__restrict__ dst, int mul, int off, int shift, bool wide)
+{
+    int v[N];
+    if (N >= 8) {
+#pragma unroll
+        for (int q = 0; q < N / 8; q++) {
+            const int4 w = __ldg((const int4 *)src + q);
+            const int ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[8 * q + 2 * j] = (int)(int16_t)(ww[j] & 0xffff); v[8 * q + 2 * j + 1] = ww[j] >> 16; }
+        }
+    } else if (N == 4) {
+        const int2 w = __ldg((const int2 *)src);
+        v[0] = (int)(int16_t)(w.x & 0xffff); v[1] = w.x >> 16; v[2] = (int)(int16_t)(w.y & 0xffff); v[3] = w.y >> 16;
+    } else {
+        const int w = __ldg((const int *)src);
+        v[0] = (int)(int16_t)(w & 0xffff); v[1] = w >> 16;
+    }
+    // xevd_dquant: clip16((c * scale + offset) >> shift)
+    if (!wide) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = xb_clip16((v[k] * mul + off) >> shift);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = xb_clip16((int)(((long long)v[k] * mul + (long long)off) >> shift));
+    }
+    int out[N];
+    InvDct2P<N, 1, N>::run(v, out);
+    if (N >= 4 && ((smem_u32(dst) & 15) == 0)) {
+#pragma unroll
+        for (int q = 0; q < N / 4; q++) ((int4 *)dst)[q] = make_int4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+    } else {            // chroma blocks of ternary-split CUs can start on an 8-byte boundary only
+#pragma unroll
+        for (int q = 0; q < N / 2; q++) ((int2 *)dst)[q] = make_int2(out[2 * q], out[2 * q + 1]);
+    }
+}
+
+// ---- residual pass 2: one column of a transform block -----------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstride, int16_t *__restrict__ dst, int dstride, int sh2)
+{
+    int in[N], out[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) in[k] = src[k * sstride];
+    InvDct2R<N>::run(in, out, 1 << (sh2 - 1));
+#pragma unroll
+    for (int k = 0; k < N; k++) dst[k * dstride] = (int16_t)xb_clip16(out[k] >> sh2);
+}
+
+template <bool BI>
+__global__ void __launch_bounds__(kR2Threads, 2)
+k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NL = BI ? 2 : 1;
+    const R2Layout L = R2Layout::make(NL, max_cu);
+    uint64_t *mbar = (uint64_t *)smem;
+    int *cnt = (int *)(smem + 16);           // [0] luma lines p1, [1] all lines p1, [2] luma lines p2, [3] all p2, [4] tiles, [5] TUs
+    XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
+    TuDesc *s_tu = (TuDesc *)(smem + L.tus);
+    uint16_t *s_l1 = (uint16_t *)(smem + L.lines1), *s_l2 = (uint16_t *)(smem + L.lines2);
+    TileDesc *s_tile = (TileDesc *)(smem + L.tiles);
+    TilePred *s_pred = (TilePred *)(smem + L.preds);
+    int *s_tmp = (int *)(smem + L.scratch);
+    int16_t *s_res = (int16_t *)(smem + L.res_y);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctu = blockIdx.x;
+    const int ctu_x = (ctu % a.w_ctu) << 6, ctu_y = (ctu / a.w_ctu) << 6;
+    const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
+
+    // ---- stage CU descriptors, zero the residual, init barrier --------------------------------------------------------------
+    {
+        const int4 *g = (const int4 *)(a.cus + cu0);
+        int4 *s = (int4 *)s_cu;
+        for (int i = tid; i < ncu * 2; i += kR2Threads) s[i] = __ldg(g + i);
+        int4 *z = (int4 *)s_res;
+        const int nz = (2 * 64 * kResLStride + 4 * 32 * kResCStride) / 16;
+        for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
+        if (tid == 0) mbar_init(mbar, 1);
+        // packed tap words for every phase of the active table (per-lane lookups later: shared, not constant, memory)
+        int *t8 = (int *)(smem + L.taps), *t4 = t8 + 16 * 9;
+        if (tid < 16) build_taps8(c_mc_l[a.main_tables][tid], t8 + tid * 9);
+        else if (tid >= 32 && tid < 64) build_taps4(c_mc_c[a.main_tables][tid - 32], t4 + (tid - 32) * 6);
+    }
+    const int *s_t8 = (const int *)(smem + L.taps), *s_t4 = s_t8 + 16 * 9;
+    auto ld_taps5 = [&](int ph, int set) { Taps5 t; const int *q = s_t8 + (ph & 15) * 9 + set * 3; t.r0 = q[0]; t.r1 = q[1]; t.r2 = q[2]; return t; };
+    auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
+    __syncthreads();
+
+    // ---- warp 0: per-CU counts -> exclusive prefix sums -> every CU expands its own work lists ------------------------------
+    // counts per CU: luma rows (pass 1), chroma rows, luma cols (pass 2), chroma cols, tiles, TUs
+    // (ncu <= 256: 8 CUs per lane)
+    if (warp == 0) {
+        int run[6] = {0, 0, 0, 0, 0, 0};
+        for (int base = 0; base < ncu; base += 32) {
+            const int i = base + lane;
+            int c[6] = {0, 0, 0, 0, 0, 0};
+            if (i < ncu) {
+                const XB200_CU cu = s_cu[i];
+                const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+                const int ny = (cu.cbf & 15) ? 1 : 0, nc = ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0);
+                c[0] = ny * h; c[1] = nc * (h >> 1); c[2] = ny * w; c[3] = nc * (w >> 1);
+                c[4] = max(1, w >> 4) * max(1, h >> 4);
+                c[5] = ny + nc;
+            }
+            int inc[6];
+#pragma unroll
+            for (int q = 0; q < 6; q++) {
+                int v = c[q];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+                inc[q] = v;
+            }
+            if (i < ncu) {
+                // stash exclusive offsets in the (otherwise unused) reserved / padding fields of a side array: reuse s_tile
+                int *offs = (int *)(smem + L.preds) + i * 6;      // preds area is free until tiles are expanded below
+#pragma unroll
+                for (int q = 0; q < 6; q++) offs[q] = run[q] + inc[q] - c[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 6; q++) run[q] += __shfl_sync(0xffffffffu, inc[q], 31);
+        }
+        if (lane == 0) { cnt[0] = run[0]; cnt[1] = run[0] + run[1]; cnt[2] = run[2]; cnt[3] = run[2] + run[3]; cnt[4] = run[4]; cnt[5] = run[5]; }
+    }
+    __syncthreads();
+    const int n_l1y = cnt[0], n_l1 = cnt[1], n_l2y = cnt[2], n_l2 = cnt[3], n_tiles = cnt[4];
+    __syncthreads();                          // offsets are read below before preds is overwritten
+    {
+        // expansion: one thread per CU
+        int my_offs[6];
+        XB200_CU cu;
+        const bool have = tid < ncu;
+        if (have) {
+            const int *offs = (const int *)(smem + L.preds) + tid * 6;
+#pragma unroll
+            for (int q = 0; q < 6; q++) my_offs[q] = offs[q];
+            cu = s_cu[tid];
+        }
+        __syncthreads();
+        if (have) {
+            const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+            const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
+            // transform blocks (CUs <= 64 in both dimensions carry one per plane)
+            int tu = my_offs[5];
+            int coef = cu.coef_off;
+            int l1y = my_offs[0], l1c = n_l1y + my_offs[1], l2y = my_offs[2], l2c = n_l2y + my_offs[3];
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) {
+                if (!((cu.cbf >> (4 * pl)) & 15)) continue;
+                const int sh = pl ? 1 : 0;
+                const int lw = cu.log2w - sh, lh = cu.log2h - sh;
+                TuDesc d;
+                d.coef_off = coef;
+                coef += ((1 << (lw + lh)) + 7) & ~7;
+                d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
+                d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
+                d.lw_lh = (uint8_t)(lw | (lh << 4));
+                d.cstride_log2 = (uint8_t)lw;
+                const int qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
+                const int odd = (lw + lh) & 1;
+                const int shift = 6 - (15 - a.bd_l - ((lw + lh) >> 1)) + (odd ? 8 : 0);
+                const long long mul = (long long)(c_dq_scale[0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
+                d.shift = (uint8_t)shift;
+                d.mul = (int)mul;
+                d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
+                s_tu[tu] = d;
+                uint16_t *p1 = s_l1 + (pl ? l1c : l1y), *p2 = s_l2 + (pl ? l2c : l2y);
+                for (int r = 0; r < (1 << lh); r++) p1[r] = (uint16_t)((tu << 6) | r);
+                for (int c = 0; c < (1 << lw); c++) p2[c] = (uint16_t)((tu << 6) | c);
+                if (pl) { l1c += 1 << lh; l2c += 1 << lw; }
+                tu++;
+            }
+            // prediction tiles
+            int mvc[2][2];
+            mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[0][0], cu.mv[0][1], mvc[0][0], mvc[0][1]);
+            mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[1][0], cu.mv[1][1], mvc[1][0], mvc[1][1]);
+            bool use0 = cu.refi[0] >= 0, use1 = cu.refi[1] >= 0;
+            if (use0 && use1 && a.ref_poc[0][cu.refi[0]] == a.ref_poc[1][cu.refi[1]] && mvc[0][0] == mvc[1][0] && mvc[0][1] == mvc[1][1])
+                use1 = false;                 // identical motion -> list 0 only (xevd_mc.c:513-519)
+            const int tw = min(w, 16), th = min(h, 16);
+            int t = my_offs[4];
+            for (int ty = 0; ty < h; ty += 16)
+                for (int tx = 0; tx < w; tx += 16, t++) {
+                    TileDesc td;
+                    td.cu = (uint16_t)tid; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
+                    td.tw = (uint8_t)tw; td.th = (uint8_t)th; td.nl = (uint8_t)((use0 ? 1 : 0) + (use1 ? 1 : 0)); td.pad = 0;
+                    s_tile[t] = td;
+                    int k = 0;
+#pragma unroll
+                    for (int l = 0; l < 2; l++) {
+                        if (!(l ? use1 : use0)) continue;
+                        if (k < NL) {
+                            const int mvx = mvc[l][0], mvy = mvc[l][1];
+                            TilePred p;
+                            p.wx = (int16_t)(144 + cu.x + tx + (mvx >> 2) - 3);
+                            p.wy = (int16_t)(144 + cu.y + ty + (mvy >> 2) - 3);
+                            p.cwx = (int16_t)(72 + ((cu.x + tx) >> 1) + (mvx >> 3) - 1);
+                            p.cwy = (int16_t)(72 + ((cu.y + ty) >> 1) + (mvy >> 3) - 1);
+                            p.phx = (uint8_t)((mvx & 3) << 2); p.phy = (uint8_t)((mvy & 3) << 2);
+                            p.cphx = (uint8_t)((mvx & 7) << 2); p.cphy = (uint8_t)((mvy & 7) << 2);
+                            p.two_d = (uint8_t)(((cu.mv[l][0] & 3) != 0) && ((cu.mv[l][1] & 3) != 0));
+                            p.ctwo_d = (uint8_t)(((cu.mv[l][0] & 7) != 0) && ((cu.mv[l][1] & 7) != 0));
+                            p.ref = (uint8_t)(l * XB_MAX_REFS + cu.refi[l]);
+                            p.offs = (uint8_t)((p.wx & 7) | ((p.cwx & 7) << 4));
+                            s_pred[t * NL + k] = p;
+                        }
+                        k++;
+                    }
+                }
+        }
+    }
+    __syncthreads();
+
+    // ---- MC rounds (normally one: a CTU of >=16x16 CUs has at most 16 tiles) -----------------------------------------------
+    const int n_rounds = (n_tiles + kTileCap - 1) / kTileCap;
+    auto issue_round = [&](int round) {
+        // warp 0: lane = slot + 16 * list
+        if (warp == 0) {
+            const int t0 = round * kTileCap, nt = min(kTileCap, n_tiles - t0);
+            if (lane == 0) {
+                int n = 0;
+                for (int i = 0; i < nt; i++) n += min((int)s_tile[t0 + i].nl, NL);
+                mbar_expect_tx(mbar, (uint32_t)n * 2 * (kBoxLW * kBoxLH + 2 * kBoxCW * kBoxCH));
+            }
+            __syncwarp();
+            const int slot = lane & 15, l = lane >> 4;
+            if (slot < nt && l < NL && l < s_tile[t0 + slot].nl) {
+                const TilePred p = s_pred[(t0 + slot) * NL + l];
+                const CUtensorMap *tm = a.ref_tmap[p.ref];
+                tma_load_2d(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes, tm + 0, p.wx & ~7, p.wy, mbar);
+                tma_load_2d(smem + L.win_c + ((l * kTileCap + slot) * 2 + 0) * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, mbar);
+                tma_load_2d(smem + L.win_c + ((l * kTileCap + slot) * 2 + 1) * kWinCBytes, tm + 2, p.cwx & ~7, p.cwy, mbar);
+            }
+        }
+    };
+    issue_round(0);
+
+    // ---- residual pass 1 (rows, IDP.2A) -------------------------------------------------------------------------------------
+    for (int i = tid; i < n_l1; i += kR2Threads) {
+        const int e = s_l1[i];
+        const TuDesc d = s_tu[e >> 6];
+        const int r = e & 63, lw = d.lw_lh & 15, pl = d.plane_wide & 3;
+        const int16_t *src = a.coef + d.coef_off + (r << d.cstride_log2);
+        int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off +
+                   r * (pl ? kTmpCStride : kTmpLStride);
+        const int off = d.shift ? (1 << (d.shift - 1)) : 0;
+        const bool wide = (d.plane_wide & 4) != 0;
+        switch (lw) {
+        case 1: row_pass<2>(src, dst, d.mul, off, d.shift, wide); break;
+        case 2: row_pass<4>(src, dst, d.mul, off, d.shift, wide); break;
+        case 3: row_pass<8>(src, dst, d.mul, off, d.shift, wide); break;
+        case 4: row_pass<16>(src, dst, d.mul, off, d.shift, wide); break;
+        case 5: row_pass<32>(src, dst, d.mul, off, d.shift, wide); break;
+        default: row_pass<64>(src, dst, d.mul, off, d.shift, wide); break;
+        }
+    }
+    __syncthreads();
+    // ---- residual pass 2 (columns, IMAD) --------------------------------------------------------------------------------------
+    {
+        const int sh2 = 19 - (a.bd_l - 8);
+        for (int i = tid; i < n_l2; i += kR2Threads) {
+            const int e = s_l2[i];
+            const TuDesc d = s_tu[e >> 6];
+            const int c = e & 63, lh = d.lw_lh >> 4, pl = d.plane_wide & 3;
+            const int *src = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + c;
+            int16_t *dst = s_res + (pl == 0 ? 0 : (pl == 1 ? 64 * kResLStride : 64 * kResLStride + 32 * kResCStride)) + d.res_off + c;
+            const int ss = pl ? kTmpCStride : kTmpLStride, ds = pl ? kResCStride : kResLStride;
+            switch (lh) {
+            case 1: col_pass<2>(src, ss, dst, ds, sh2); break;
+            case 2: col_pass<4>(src, ss, dst, ds, sh2); break;
+            case 3: col_pass<8>(src, ss, dst, ds, sh2); break;
+            case 4: col_pass<16>(src, ss, dst, ds, sh2); break;
+            case 5: col_pass<32>(src, ss, dst, ds, sh2); break;
+            default: col_pass<64>(src, ss, dst, ds, sh2); break;
+            }
+        }
+    }
+    __syncthreads();              // residual complete; pass-1 buffer is free and becomes the vertical-pair buffers
+
+    int *s_m2l = s_tmp;                                        // [NL][16][kM2LWords]
+    int *s_m2c = s_tmp + NL * kTileCap * kM2LWords;            // [NL][16][2][kM2CWords]
+    const int maxv2 = ((1 << a.bd_l) - 1) * 0x00010001;        // the reference clips all planes with the luma depth
+    const int s1l = min(4, a.bd_l - 8), s2l = max(8, 20 - a.bd_l);
+    const int s1c = min(4, a.bd_c - 8), s2c = max(8, 20 - a.bd_c);
+
+    for (int round = 0; round < n_rounds; round++) {
+        const int t0 = round * kTileCap, nt = min(kTileCap, n_tiles - t0);
+        if (round > 0) issue_round(round);
+        mbar_wait(mbar, round & 1);
+
+        // ---- horizontal stage: tasks of 2 rows x 8 columns, output = vertical pairs -------------------------------------------
+        // per (slot, list): luma 12 pair-rows x 2 halves = 24 tasks, chroma 2 planes x 6 pair-rows = 12 tasks
+        for (int id = tid; id < kTileCap * NL * 36; id += kR2Threads) {
+            const int sl = id / 36, k = id - sl * 36;
+            const int slot = sl & (kTileCap - 1), l = sl / kTileCap;
+            if (slot >= nt) continue;
+            const TileDesc td = s_tile[t0 + slot];
+            if (l >= td.nl) continue;
+            const TilePred p = s_pred[(t0 + slot) * NL + l];
+            if (k < 24) {
+                const int rp = k >> 1, half = k & 1;
+                if (2 * rp >= td.th + 7 || half * 8 >= td.tw) continue;
+                const int offx = p.offs & 7, par = offx & 1;
+                const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
+                const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
+                const int sh = p.two_d ? s1l : 6;
+                int hv[2][8];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
+                    int q[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) q[j] = rowp[j];
+#pragma unroll
+                    for (int o = 0; o < 4; o++) {
+                        hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                        hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                    }
+                }
+                int4 *dst = (int4 *)(s_m2l + (l * kTileCap + slot) * kM2LWords + rp * kM2LStrideW + half * 8);
+                dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+            } else {
+                const int kk = k - 24, pl = kk / 6, rp = kk - pl * 6;
+                if (2 * rp >= (td.th >> 1) + 3) continue;
+                const int offx = p.offs >> 4, par = offx & 1;
+                const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
+                const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
+                const int sh = p.ctwo_d ? s1c : 6;
+                int hv[2][8];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
+                    int q[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) q[j] = rowp[j];
+#pragma unroll
+                    for (int o = 0; o < 4; o++) {
+                        hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                        hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                    }
+                }
+                int4 *dst = (int4 *)(s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + rp * kM2CStrideW);
+                dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+            }
+        }
+        __syncthreads();
+
+        // ---- vertical stage + reconstruction: luma tasks = 2 columns x 8 rows, chroma tasks = 2 columns x 4 rows ----------------
+        // per slot: 16 luma tasks (8 column pairs x 2 row groups) + 16 chroma tasks (2 planes x 4 column pairs x 2 row groups)
+        for (int id = tid; id < nt * 32; id += kR2Threads) {
+            const int slot = id >> 5, k = id & 31;
+            const TileDesc td = s_tile[t0 + slot];
+            if (k < 16) {
+                const int cp = k & 7, rg = k >> 3;
+                if (2 * cp >= td.tw || 8 * rg >= td.th) continue;
+                int outp[8];                                   // packed (col, col+1) per row
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    if (l >= td.nl) continue;
+                    const TilePred p = s_pred[(t0 + slot) * NL + l];
+                    const Taps5 te = ld_taps5(p.phy, 0), to = ld_taps5(p.phy, 1);
+                    const int sh = p.two_d ? s2l : 6, rnd = p.two_d ? (1 << (s2l - 1)) : 0;
+                    const int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + (4 * rg) * kM2LStrideW + 2 * cp;
+                    int P[8][2];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { const int2 v = *(const int2 *)(m2 + j * kM2LStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        int e0 = fir5(te, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], 0, rnd) >> sh;
+                        int e1 = fir5(te, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], 0, rnd) >> sh;
+                        int o0 = fir5(to, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], P[q + 4][0], rnd) >> sh;
+                        int o1 = fir5(to, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], P[q + 4][1], rnd) >> sh;
+                        int pe = __vimin_s16x2_relu(pack16(e0, e1), maxv2);
+                        int po = __vimin_s16x2_relu(pack16(o0, o1), maxv2);
+                        if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                        else {      // xevd_average_16b_no_clip on two clipped, non-negative predictions
+                            outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                            outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                        }
+                    }
+                }
+                const int x = td.px + 2 * cp, y = td.py + 8 * rg;
+                const int *res = (const int *)(s_res + y * kResLStride + x);
+                pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    if (8 * rg + r < td.th)
+                        *(int *)(dst + (size_t)r * a.s_l) = __viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+            } else {
+                const int kk = k - 16, pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
+                const int cw = td.tw >> 1, ch = td.th >> 1;
+                if (2 * cp >= cw || 4 * rg >= ch) continue;
+                int outp[4];
+#pragma unroll
+                for (int l = 0; l < NL; l++) {
+                    if (l >= td.nl) continue;
+                    const TilePred p = s_pred[(t0 + slot) * NL + l];
+                    const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
+                    const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
+                    const int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
+                    int P[4][2];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int e0 = fir3(te, P[q][0], P[q + 1][0], 0, rnd) >> sh;
+                        int e1 = fir3(te, P[q][1], P[q + 1][1], 0, rnd) >> sh;
+                        int o0 = fir3(to, P[q][0], P[q + 1][0], P[q + 2][0], rnd) >> sh;
+                        int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
+                        const int maxc = ((1 << a.bd_c) - 1) * 0x00010001;
+                        int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc);
+                        int po = __vimin_s16x2_relu(pack16(o0, o1), maxc);
+                        if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                        else {
+                            outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                            outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                        }
+                    }
+                }
+                const int x = (td.px >> 1) + 2 * cp, y = (td.py >> 1) + 4 * rg;
+                const int *res = (const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + y * kResCStride + x);
+                pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (4 * rg + r < ch)
+                        *(int *)(dst + (size_t)r * a.s_c) = __viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------------------------
+    for (int i = tid; i < ncu; i += kR2Threads) {
+        const XB200_CU cu = s_cu[i];
+        const int sx = cu.x >> 2, sy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
+        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31);
+        if (cu.cbf & 1) m |= 1u << 24;
+        if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
+        const int2 mv = make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        const int16_t rf = *(const int16_t *)cu.refi;
+        for (int y = 0; y < nh; y++)
+            for (int x = 0; x < nw; x++) {
+                const int p = (sy + y) * a.w_scu + sx + x;
+                a.map_scu[p] = m;
+                ((int2 *)a.map_mv)[p] = mv;
+                ((int16_t *)a.map_refi)[p] = rf;
+            }
+    }
+}
+
+}  // namespace xb

@@ -151,11 +151,13 @@ class Context:
 
     # -- device-resident entry point (inputs already in HBM; pointers are raw device addresses) --------------
     def recon_frame_dev(self, prm: abi.Params, cur: DevicePicture, refs_l0, refs_l1, d_cus: int, n_cu: int,
-                        d_first: int, n_ctu: int, d_ext: int, n_ext: int, d_coef: int, n_coef: int, has_intra: bool = False):
+                        d_first: int, n_ctu: int, d_ext: int, n_ext: int, d_coef: int, n_coef: int, has_intra: bool = False,
+                        max_cu_per_ctu: int = 0):
         cur.set_poc(prm.poc)
         self._chk(self.lib.xb200_recon_frame_dev(self.handle, C.byref(prm), cur.handle,
                                                  _handles(refs_l0), len(refs_l0), _handles(refs_l1), len(refs_l1),
-                                                 d_cus, n_cu, d_first, n_ctu, d_ext, n_ext, d_coef, n_coef, int(has_intra)),
+                                                 d_cus, n_cu, d_first, n_ctu, d_ext, n_ext, d_coef, n_coef, int(has_intra),
+                                                 int(max_cu_per_ctu)),
                   "xb200_recon_frame_dev")
 
     def itdq_blocks_dev(self, d_in: int, d_out: int, n: int, log2w: int, log2h: int, qp: int, bit_depth: int, iqt: bool = False):

@@ -104,7 +104,8 @@ def cu_coef_count(cu) -> int:
     """number of int16 coefficients a CU contributes to the stream (planes with cbf == 0 are absent)"""
     n = 1 << (int(cu["log2w"]) + int(cu["log2h"]))
     cbf = int(cu["cbf"])
-    return (n if cbf & 0x00F else 0) + (n // 4 if cbf & 0x0F0 else 0) + (n // 4 if cbf & 0xF00 else 0)
+    a8 = lambda v: (v + 7) & ~7   # plane blocks are padded to multiples of 8 int16
+    return (a8(n) if cbf & 0x00F else 0) + (a8(n // 4) if cbf & 0x0F0 else 0) + (a8(n // 4) if cbf & 0xF00 else 0)
 
 
 @dataclass

@@ -151,7 +151,8 @@ def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A",
         # ~10 % non-zero levels: Laplacian scale ~ 0.22 of a quantiser step (dq_scale/64)
         resid_scale = 0.22 * dq_scale(qp_y, iqt) / 64.0
     sizes = 1 << (cus["log2w"].astype(np.int64) + cus["log2h"].astype(np.int64))
-    per_cu = np.where(coded, sizes + sizes // 2, 0)
+    a8 = lambda v: (v + 7) & ~7          # plane blocks padded to multiples of 8 int16
+    per_cu = np.where(coded, a8(sizes) + 2 * a8(sizes // 4), 0)
     off = np.concatenate(([0], np.cumsum(per_cu)))
     cus["coef_off"] = off[:-1].astype(np.uint32)
     coef = np.zeros(int(off[-1]), np.int16)
@@ -163,8 +164,11 @@ def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A",
         ry = rng.laplace(0.0, resid_scale, (len(sel), s, s))
         rc = rng.laplace(0.0, resid_scale, (len(sel), 2, s // 2, s // 2))
         ly = quantised_dct(ry, qp_y, iqt).reshape(len(sel), -1)
-        lc = quantised_dct(rc, qp_y, iqt).reshape(len(sel), -1)
-        blk = np.concatenate([ly, lc], axis=1)
+        lc = quantised_dct(rc, qp_y, iqt).reshape(len(sel), 2, -1)
+        nc = a8(s * s // 4)
+        lcp = np.zeros((len(sel), 2, nc), np.int16)
+        lcp[:, :, :lc.shape[2]] = lc
+        blk = np.concatenate([ly, lcp.reshape(len(sel), -1)], axis=1)
         idx = off[sel][:, None] + np.arange(blk.shape[1])[None, :]
         coef[idx] = blk
     prm = make_params(w, h, bit_depth=bit_depth, log2_ctu=log2_ctu, poc=8, tool_iqt=int(iqt), tool_admvp=int(main_mv))
