@@ -380,8 +380,9 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     memcpy(hp + b_cu, ctu_first, (size_t)(n_ctu + 1) * 4);
     if (ext && n_ext > 0) memcpy(hp + b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT));
     if (coef && n_coef) memcpy(hp + b_cu + b_first + b_ext, coef, n_coef * 2);
-    int has_intra = 0, max_cu = 0;
-    for (int i = 0; i < n_cu; i++) has_intra |= (cus[i].mode == XB200_MODE_INTRA);
+    int has_intra = 0, max_cu = 0, any_l1 = 0;
+    for (int i = 0; i < n_cu; i++) { has_intra |= (cus[i].mode == XB200_MODE_INTRA); any_l1 |= (cus[i].mode != XB200_MODE_INTRA && cus[i].refi[1] >= 0); }
+    if (!any_l1) n1 = 0;          // P picture: no CU predicts from list 1 (selects the single-list kernel)
     for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
     CK(c, cudaMemcpyAsync(dp, hp, b_cu + b_first + b_ext + b_coef, cudaMemcpyHostToDevice, c->stream));
     r = xb200_recon_frame_dev(c, prm, cur, l0, n0, l1, n1, dp, n_cu, dp + b_cu, n_ctu, dp + b_cu + b_first, n_ext,

@@ -111,8 +111,15 @@ namespace xb {
 
 __device__ __forceinline__ constexpr int pk8(int lo, int hi) { return (lo & 0xff) | ((hi & 0xff) << 8); }
 __device__ __forceinline__ int pack16(int lo, int hi) { return __byte_perm(lo, hi, 0x5410); }
+__device__ __forceinline__ int pack_sat16(int lo, int hi)
+{
+    int r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
 
-// M-point inverse DCT-2 over v[S * k], k = 0..M-1 (v values must fit s16)
+// M-point inverse DCT-2 over v[S * k], k = 0..M-1; every input is used by exactly one pair, and the saturating
+// pack (I2IP.S16.S32.SAT) applies the s16 clip of xevd_dquant on the way
 template <int M, int S, int NV> struct InvDct2P {
     static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[M])
     {
@@ -120,7 +127,7 @@ template <int M, int S, int NV> struct InvDct2P {
         InvDct2P<M / 2, 2 * S, NV>::run(v, E);
         int pr[M / 4];
 #pragma unroll
-        for (int j = 0; j < M / 4; j++) pr[j] = pack16(v[S * (4 * j + 1)], v[S * (4 * j + 3)]);
+        for (int j = 0; j < M / 4; j++) pr[j] = pack_sat16(v[S * (4 * j + 1)], v[S * (4 * j + 3)]);
 #pragma unroll
         for (int n = 0; n < M / 2; n++) {
             int o = 0;
@@ -134,7 +141,7 @@ template <int M, int S, int NV> struct InvDct2P {
 template <int S, int NV> struct InvDct2P<2, S, NV> {
     static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[2])
     {
-        const int p = pack16(v[0], v[S]);
+        const int p = pack_sat16(v[0], v[S]);
         out[0] = __dp2a_lo(p, pk8(64, 64), 0);
         out[1] = __dp2a_lo(p, pk8(64, -64), 0);
     }

@@ -70,30 +70,30 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
     uint8_t offs;                            // sample offset of the window inside its 8-aligned box: luma | chroma << 4
 };
 
-struct R2Layout {                            // byte offsets inside dynamic shared memory
-    int win_l, win_c, scratch, res_y, res_u, res_v, cus, tus, lines1, lines2, tiles, preds, misc, taps, total;
+// Dynamic shared memory map.  Transform blocks are kept in two tables (luma first, then chroma) so that a warp's
+// 32 consecutive line tasks run the same butterfly size; line -> block lookup is a binary search over the
+// per-block line prefix sums (no per-line lists).
+struct R2Layout {
+    int win_l, win_c, scratch, res_y, cus, tus, pre1, pre2, tiles, preds, offs, taps, total;
     __host__ __device__ static R2Layout make(int nl, int max_cu)
     {
         R2Layout L;
         int o = 128;                                                       // [0,128): mbarrier + counters
-        L.misc = 0;
         L.win_l = o; o += nl * kTileCap * kWinLBytes;
         L.win_c = o; o += nl * kTileCap * 2 * kWinCBytes;
         const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
         const int m2_bytes = 4 * nl * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
-        L.res_y = o; o += 2 * 64 * kResLStride;
-        L.res_u = o; o += 2 * 32 * kResCStride;
-        L.res_v = o; o += 2 * 32 * kResCStride;
+        L.res_y = o; o += 2 * (64 * kResLStride + 2 * 32 * kResCStride);
         L.cus = o; o += 32 * max_cu;
         L.tus = o; o += 16 * 3 * max_cu;
-        // lines per pass: sum over CUs of (h + 2 * h/2) <= 2 * 64*64/4 = 2048 (all 4-wide CUs), and <= 128 per CU
-        const int max_lines = max_cu * 128 > 2048 ? 2048 : max_cu * 128;
-        L.lines1 = o; o += max_lines * 2;              // uint16 entries
-        L.lines2 = o; o += max_lines * 2;
+        L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
+        L.pre2 = o; o += 2 * (3 * max_cu + 2);
+        o = (o + 15) & ~15;
         const int max_tiles = max_cu < 16 ? 16 : max_cu;
         L.tiles = o; o += 8 * max_tiles;
         L.preds = o; o += 16 * 2 * max_tiles;
+        L.offs = o; o += 4 * 8 * max_cu;                // per-CU exclusive offsets (scan output)
         L.taps = o; o += 4 * (16 * 9 + 32 * 6);
         L.total = (o + 127) & ~127;
         return L;
@@ -122,12 +122,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0,
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ int pack_sat16(int lo, int hi)
-{
-    int r;
-    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
-    return r;
 }
 
 // Packed tap words for IDP.2A.  A filter applied to packed sample pairs p[0..4] (5 words = 10 samples) is a sequence
@@ -192,13 +186,14 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int *_
         const int w = __ldg((const int *)src);
         v[0] = (int)(int16_t)(w & 0xffff); v[1] = w >> 16;
     }
-    // xevd_dquant: clip16((c * scale + offset) >> shift)
+    // xevd_dquant: clip16((c * scale + offset) >> shift); the clip happens in the saturating pack (I2IP.S16.S32.SAT)
+    // that forms the butterfly's operand pairs
     if (!wide) {
 #pragma unroll
-        for (int k = 0; k < N; k++) v[k] = xb_clip16((v[k] * mul + off) >> shift);
+        for (int k = 0; k < N; k++) v[k] = (v[k] * mul + off) >> shift;
     } else {
 #pragma unroll
-        for (int k = 0; k < N; k++) v[k] = xb_clip16((int)(((long long)v[k] * mul + (long long)off) >> shift));
+        for (int k = 0; k < N; k++) v[k] = (int)(((long long)v[k] * mul + (long long)off) >> shift);
     }
     int out[N];
     InvDct2P<N, 1, N>::run(v, out);
@@ -220,7 +215,7 @@ __device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstrid
     for (int k = 0; k < N; k++) in[k] = src[k * sstride];
     InvDct2R<N>::run(in, out, 1 << (sh2 - 1));
 #pragma unroll
-    for (int k = 0; k < N; k++) dst[k * dstride] = (int16_t)xb_clip16(out[k] >> sh2);
+    for (int k = 0; k < N; k++) dst[k * dstride] = (int16_t)pack_sat16(out[k] >> sh2, 0);
 }
 
 template <bool BI>
@@ -231,12 +226,13 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     constexpr int NL = BI ? 2 : 1;
     const R2Layout L = R2Layout::make(NL, max_cu);
     uint64_t *mbar = (uint64_t *)smem;
-    int *cnt = (int *)(smem + 16);           // [0] luma lines p1, [1] all lines p1, [2] luma lines p2, [3] all p2, [4] tiles, [5] TUs
+    int *cnt = (int *)(smem + 16);           // totals: [0] luma blocks [1] chroma blocks [2,3] pass-1 lines y,c [4,5] pass-2 y,c [6] tiles
     XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
     TuDesc *s_tu = (TuDesc *)(smem + L.tus);
-    uint16_t *s_l1 = (uint16_t *)(smem + L.lines1), *s_l2 = (uint16_t *)(smem + L.lines2);
+    uint16_t *s_pre1 = (uint16_t *)(smem + L.pre1), *s_pre2 = (uint16_t *)(smem + L.pre2);
     TileDesc *s_tile = (TileDesc *)(smem + L.tiles);
     TilePred *s_pred = (TilePred *)(smem + L.preds);
+    int *s_offs = (int *)(smem + L.offs);
     int *s_tmp = (int *)(smem + L.scratch);
     int16_t *s_res = (int16_t *)(smem + L.res_y);
 
@@ -245,146 +241,128 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int ctu_x = (ctu % a.w_ctu) << 6, ctu_y = (ctu / a.w_ctu) << 6;
     const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
 
-    // ---- stage CU descriptors, zero the residual, init barrier --------------------------------------------------------------
+    // ---- stage CU descriptors, zero the residual, init barrier, build tap tables --------------------------------------------
     {
         const int4 *g = (const int4 *)(a.cus + cu0);
         int4 *s = (int4 *)s_cu;
         for (int i = tid; i < ncu * 2; i += kR2Threads) s[i] = __ldg(g + i);
         int4 *z = (int4 *)s_res;
-        const int nz = (2 * 64 * kResLStride + 4 * 32 * kResCStride) / 16;
+        const int nz = 2 * (64 * kResLStride + 2 * 32 * kResCStride) / 16;
         for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
         if (tid == 0) mbar_init(mbar, 1);
-        // packed tap words for every phase of the active table (per-lane lookups later: shared, not constant, memory)
         int *t8 = (int *)(smem + L.taps), *t4 = t8 + 16 * 9;
-        if (tid < 16) build_taps8(c_mc_l[a.main_tables][tid], t8 + tid * 9);
-        else if (tid >= 32 && tid < 64) build_taps4(c_mc_c[a.main_tables][tid - 32], t4 + (tid - 32) * 6);
+        if (tid >= 64 && tid < 80) build_taps8(c_mc_l[a.main_tables][tid - 64], t8 + (tid - 64) * 9);
+        else if (tid >= 96 && tid < 128) build_taps4(c_mc_c[a.main_tables][tid - 96], t4 + (tid - 96) * 6);
     }
     const int *s_t8 = (const int *)(smem + L.taps), *s_t4 = s_t8 + 16 * 9;
     auto ld_taps5 = [&](int ph, int set) { Taps5 t; const int *q = s_t8 + (ph & 15) * 9 + set * 3; t.r0 = q[0]; t.r1 = q[1]; t.r2 = q[2]; return t; };
     auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
     __syncthreads();
 
-    // ---- warp 0: per-CU counts -> exclusive prefix sums -> every CU expands its own work lists ------------------------------
-    // counts per CU: luma rows (pass 1), chroma rows, luma cols (pass 2), chroma cols, tiles, TUs
-    // (ncu <= 256: 8 CUs per lane)
+    // ---- warp 0: per-CU counts -> exclusive prefix sums ------------------------------------------------------------------------
+    // q: 0 luma blocks, 1 chroma blocks, 2 pass-1 luma lines, 3 pass-1 chroma lines, 4 pass-2 luma lines, 5 pass-2 chroma, 6 tiles
     if (warp == 0) {
-        int run[6] = {0, 0, 0, 0, 0, 0};
+        int run[7] = {0, 0, 0, 0, 0, 0, 0};
         for (int base = 0; base < ncu; base += 32) {
             const int i = base + lane;
-            int c[6] = {0, 0, 0, 0, 0, 0};
+            int c[7] = {0, 0, 0, 0, 0, 0, 0};
             if (i < ncu) {
                 const XB200_CU cu = s_cu[i];
                 const int w = 1 << cu.log2w, h = 1 << cu.log2h;
                 const int ny = (cu.cbf & 15) ? 1 : 0, nc = ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0);
-                c[0] = ny * h; c[1] = nc * (h >> 1); c[2] = ny * w; c[3] = nc * (w >> 1);
-                c[4] = max(1, w >> 4) * max(1, h >> 4);
-                c[5] = ny + nc;
+                c[0] = ny; c[1] = nc; c[2] = ny * h; c[3] = nc * (h >> 1); c[4] = ny * w; c[5] = nc * (w >> 1);
+                c[6] = max(1, w >> 4) * max(1, h >> 4);
             }
-            int inc[6];
 #pragma unroll
-            for (int q = 0; q < 6; q++) {
+            for (int q = 0; q < 7; q++) {
                 int v = c[q];
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
-                inc[q] = v;
+                if (i < ncu) s_offs[i * 8 + q] = run[q] + v - c[q];
+                run[q] += __shfl_sync(0xffffffffu, v, 31);
             }
-            if (i < ncu) {
-                // stash exclusive offsets in the (otherwise unused) reserved / padding fields of a side array: reuse s_tile
-                int *offs = (int *)(smem + L.preds) + i * 6;      // preds area is free until tiles are expanded below
-#pragma unroll
-                for (int q = 0; q < 6; q++) offs[q] = run[q] + inc[q] - c[q];
-            }
-#pragma unroll
-            for (int q = 0; q < 6; q++) run[q] += __shfl_sync(0xffffffffu, inc[q], 31);
         }
-        if (lane == 0) { cnt[0] = run[0]; cnt[1] = run[0] + run[1]; cnt[2] = run[2]; cnt[3] = run[2] + run[3]; cnt[4] = run[4]; cnt[5] = run[5]; }
+        if (lane < 7) cnt[lane] = run[lane];
     }
     __syncthreads();
-    const int n_l1y = cnt[0], n_l1 = cnt[1], n_l2y = cnt[2], n_l2 = cnt[3], n_tiles = cnt[4];
-    __syncthreads();                          // offsets are read below before preds is overwritten
-    {
-        // expansion: one thread per CU
-        int my_offs[6];
-        XB200_CU cu;
-        const bool have = tid < ncu;
-        if (have) {
-            const int *offs = (const int *)(smem + L.preds) + tid * 6;
+    const int n_tuy = cnt[0], n_tuc = cnt[1], n_l1y = cnt[2], n_l1c = cnt[3], n_l2y = cnt[4], n_l2c = cnt[5], n_tiles = cnt[6];
+    const int n_tu = n_tuy + n_tuc;
+
+    // ---- one thread per CU: transform-block and tile descriptors ------------------------------------------------------------------
+    if (tid < ncu) {
+        const XB200_CU cu = s_cu[tid];
+        const int *of = s_offs + tid * 8;
+        const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+        const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
+        int coef = cu.coef_off;
+        int tuc = n_tuy + of[1], l1c = of[3], l2c = of[5];
 #pragma unroll
-            for (int q = 0; q < 6; q++) my_offs[q] = offs[q];
-            cu = s_cu[tid];
-        }
-        __syncthreads();
-        if (have) {
-            const int w = 1 << cu.log2w, h = 1 << cu.log2h;
-            const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
-            // transform blocks (CUs <= 64 in both dimensions carry one per plane)
-            int tu = my_offs[5];
-            int coef = cu.coef_off;
-            int l1y = my_offs[0], l1c = n_l1y + my_offs[1], l2y = my_offs[2], l2c = n_l2y + my_offs[3];
-#pragma unroll
-            for (int pl = 0; pl < 3; pl++) {
-                if (!((cu.cbf >> (4 * pl)) & 15)) continue;
-                const int sh = pl ? 1 : 0;
-                const int lw = cu.log2w - sh, lh = cu.log2h - sh;
-                TuDesc d;
-                d.coef_off = coef;
-                coef += ((1 << (lw + lh)) + 7) & ~7;
-                d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
-                d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
-                d.lw_lh = (uint8_t)(lw | (lh << 4));
-                d.cstride_log2 = (uint8_t)lw;
-                const int qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
-                const int odd = (lw + lh) & 1;
-                const int shift = 6 - (15 - a.bd_l - ((lw + lh) >> 1)) + (odd ? 8 : 0);
-                const long long mul = (long long)(c_dq_scale[0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
-                d.shift = (uint8_t)shift;
-                d.mul = (int)mul;
-                d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
-                s_tu[tu] = d;
-                uint16_t *p1 = s_l1 + (pl ? l1c : l1y), *p2 = s_l2 + (pl ? l2c : l2y);
-                for (int r = 0; r < (1 << lh); r++) p1[r] = (uint16_t)((tu << 6) | r);
-                for (int c = 0; c < (1 << lw); c++) p2[c] = (uint16_t)((tu << 6) | c);
-                if (pl) { l1c += 1 << lh; l2c += 1 << lw; }
-                tu++;
+        for (int pl = 0; pl < 3; pl++) {
+            if (!((cu.cbf >> (4 * pl)) & 15)) continue;
+            const int sh = pl ? 1 : 0;
+            const int lw = cu.log2w - sh, lh = cu.log2h - sh;
+            TuDesc d;
+            d.coef_off = coef;
+            coef += ((1 << (lw + lh)) + 7) & ~7;
+            d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
+            d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
+            d.lw_lh = (uint8_t)(lw | (lh << 4));
+            d.cstride_log2 = (uint8_t)lw;
+            const int qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
+            const int odd = (lw + lh) & 1;
+            const int shift = 6 - (15 - a.bd_l - ((lw + lh) >> 1)) + (odd ? 8 : 0);
+            const long long mul = (long long)(c_dq_scale[0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
+            d.shift = (uint8_t)shift;
+            d.mul = (int)mul;
+            d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
+            if (pl == 0) {
+                s_tu[of[0]] = d; s_pre1[of[0]] = (uint16_t)of[2]; s_pre2[of[0]] = (uint16_t)of[4];
+            } else {
+                s_tu[tuc] = d; s_pre1[tuc + 1] = (uint16_t)l1c; s_pre2[tuc + 1] = (uint16_t)l2c;   // chroma tables sit after a luma end marker
+                tuc++; l1c += 1 << lh; l2c += 1 << lw;
             }
-            // prediction tiles
-            int mvc[2][2];
-            mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[0][0], cu.mv[0][1], mvc[0][0], mvc[0][1]);
-            mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[1][0], cu.mv[1][1], mvc[1][0], mvc[1][1]);
-            bool use0 = cu.refi[0] >= 0, use1 = cu.refi[1] >= 0;
-            if (use0 && use1 && a.ref_poc[0][cu.refi[0]] == a.ref_poc[1][cu.refi[1]] && mvc[0][0] == mvc[1][0] && mvc[0][1] == mvc[1][1])
-                use1 = false;                 // identical motion -> list 0 only (xevd_mc.c:513-519)
-            const int tw = min(w, 16), th = min(h, 16);
-            int t = my_offs[4];
-            for (int ty = 0; ty < h; ty += 16)
-                for (int tx = 0; tx < w; tx += 16, t++) {
-                    TileDesc td;
-                    td.cu = (uint16_t)tid; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
-                    td.tw = (uint8_t)tw; td.th = (uint8_t)th; td.nl = (uint8_t)((use0 ? 1 : 0) + (use1 ? 1 : 0)); td.pad = 0;
-                    s_tile[t] = td;
-                    int k = 0;
-#pragma unroll
-                    for (int l = 0; l < 2; l++) {
-                        if (!(l ? use1 : use0)) continue;
-                        if (k < NL) {
-                            const int mvx = mvc[l][0], mvy = mvc[l][1];
-                            TilePred p;
-                            p.wx = (int16_t)(144 + cu.x + tx + (mvx >> 2) - 3);
-                            p.wy = (int16_t)(144 + cu.y + ty + (mvy >> 2) - 3);
-                            p.cwx = (int16_t)(72 + ((cu.x + tx) >> 1) + (mvx >> 3) - 1);
-                            p.cwy = (int16_t)(72 + ((cu.y + ty) >> 1) + (mvy >> 3) - 1);
-                            p.phx = (uint8_t)((mvx & 3) << 2); p.phy = (uint8_t)((mvy & 3) << 2);
-                            p.cphx = (uint8_t)((mvx & 7) << 2); p.cphy = (uint8_t)((mvy & 7) << 2);
-                            p.two_d = (uint8_t)(((cu.mv[l][0] & 3) != 0) && ((cu.mv[l][1] & 3) != 0));
-                            p.ctwo_d = (uint8_t)(((cu.mv[l][0] & 7) != 0) && ((cu.mv[l][1] & 7) != 0));
-                            p.ref = (uint8_t)(l * XB_MAX_REFS + cu.refi[l]);
-                            p.offs = (uint8_t)((p.wx & 7) | ((p.cwx & 7) << 4));
-                            s_pred[t * NL + k] = p;
-                        }
-                        k++;
-                    }
-                }
         }
+        // prediction tiles
+        int mvc[2][2];
+        mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[0][0], cu.mv[0][1], mvc[0][0], mvc[0][1]);
+        mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[1][0], cu.mv[1][1], mvc[1][0], mvc[1][1]);
+        bool use0 = cu.refi[0] >= 0, use1 = cu.refi[1] >= 0;
+        if (use0 && use1 && a.ref_poc[0][cu.refi[0]] == a.ref_poc[1][cu.refi[1]] && mvc[0][0] == mvc[1][0] && mvc[0][1] == mvc[1][1])
+            use1 = false;                 // identical motion -> list 0 only (xevd_mc.c:513-519)
+        const int tw = min(w, 16), th = min(h, 16);
+        int t = of[6];
+        for (int ty = 0; ty < h; ty += 16)
+            for (int tx = 0; tx < w; tx += 16, t++) {
+                TileDesc td;
+                td.cu = (uint16_t)tid; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
+                td.tw = (uint8_t)tw; td.th = (uint8_t)th; td.nl = (uint8_t)((use0 ? 1 : 0) + (use1 ? 1 : 0)); td.pad = 0;
+                s_tile[t] = td;
+                int k = 0;
+#pragma unroll
+                for (int l = 0; l < 2; l++) {
+                    if (!(l ? use1 : use0)) continue;
+                    if (k < NL) {
+                        const int mvx = mvc[l][0], mvy = mvc[l][1];
+                        TilePred p;
+                        p.wx = (int16_t)(144 + cu.x + tx + (mvx >> 2) - 3);
+                        p.wy = (int16_t)(144 + cu.y + ty + (mvy >> 2) - 3);
+                        p.cwx = (int16_t)(72 + ((cu.x + tx) >> 1) + (mvx >> 3) - 1);
+                        p.cwy = (int16_t)(72 + ((cu.y + ty) >> 1) + (mvy >> 3) - 1);
+                        p.phx = (uint8_t)((mvx & 3) << 2); p.phy = (uint8_t)((mvy & 3) << 2);
+                        p.cphx = (uint8_t)((mvx & 7) << 2); p.cphy = (uint8_t)((mvy & 7) << 2);
+                        p.two_d = (uint8_t)(((cu.mv[l][0] & 3) != 0) && ((cu.mv[l][1] & 3) != 0));
+                        p.ctwo_d = (uint8_t)(((cu.mv[l][0] & 7) != 0) && ((cu.mv[l][1] & 7) != 0));
+                        p.ref = (uint8_t)(l * XB_MAX_REFS + cu.refi[l]);
+                        p.offs = (uint8_t)((p.wx & 7) | ((p.cwx & 7) << 4));
+                        s_pred[t * NL + k] = p;
+                    }
+                    k++;
+                }
+            }
+    }
+    if (tid == 0) {         // end markers of the two prefix tables: [0..n_tuy) luma, [n_tuy] end, [n_tuy+1 .. n_tu+1) chroma, [n_tu+1] end
+        s_pre1[n_tuy] = (uint16_t)n_l1y; s_pre2[n_tuy] = (uint16_t)n_l2y;
+        s_pre1[n_tu + 1] = (uint16_t)n_l1c; s_pre2[n_tu + 1] = (uint16_t)n_l2c;
     }
     __syncthreads();
 
@@ -412,11 +390,20 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     };
     issue_round(0);
 
-    // ---- residual pass 1 (rows, IDP.2A) -------------------------------------------------------------------------------------
-    for (int i = tid; i < n_l1; i += kR2Threads) {
-        const int e = s_l1[i];
-        const TuDesc d = s_tu[e >> 6];
-        const int r = e & 63, lw = d.lw_lh & 15, pl = d.plane_wide & 3;
+    // block lookup: largest b in [lo, hi) with pre[b] <= i
+    auto find_tu = [&](const uint16_t *pre, int lo, int hi, int i) {
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)pre[mid] <= i) lo = mid; else hi = mid; }
+        return lo;
+    };
+
+    // ---- residual pass 1 (rows, IDP.2A): luma lines first, then chroma lines ---------------------------------------------------
+    for (int i = tid; i < n_l1y + n_l1c; i += kR2Threads) {
+        const bool chroma = i >= n_l1y;
+        const int li = chroma ? i - n_l1y : i;
+        const int b = chroma ? find_tu(s_pre1 + 1, n_tuy, n_tu, li) : find_tu(s_pre1, 0, n_tuy, li);
+        const TuDesc d = s_tu[b];
+        const int r = li - (int)(chroma ? s_pre1[b + 1] : s_pre1[b]);
+        const int lw = d.lw_lh & 15, pl = d.plane_wide & 3;
         const int16_t *src = a.coef + d.coef_off + (r << d.cstride_log2);
         int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off +
                    r * (pl ? kTmpCStride : kTmpLStride);
@@ -435,10 +422,13 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     // ---- residual pass 2 (columns, IMAD) --------------------------------------------------------------------------------------
     {
         const int sh2 = 19 - (a.bd_l - 8);
-        for (int i = tid; i < n_l2; i += kR2Threads) {
-            const int e = s_l2[i];
-            const TuDesc d = s_tu[e >> 6];
-            const int c = e & 63, lh = d.lw_lh >> 4, pl = d.plane_wide & 3;
+        for (int i = tid; i < n_l2y + n_l2c; i += kR2Threads) {
+            const bool chroma = i >= n_l2y;
+            const int li = chroma ? i - n_l2y : i;
+            const int b = chroma ? find_tu(s_pre2 + 1, n_tuy, n_tu, li) : find_tu(s_pre2, 0, n_tuy, li);
+            const TuDesc d = s_tu[b];
+            const int c = li - (int)(chroma ? s_pre2[b + 1] : s_pre2[b]);
+            const int lh = d.lw_lh >> 4, pl = d.plane_wide & 3;
             const int *src = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + c;
             int16_t *dst = s_res + (pl == 0 ? 0 : (pl == 1 ? 64 * kResLStride : 64 * kResLStride + 32 * kResCStride)) + d.res_off + c;
             const int ss = pl ? kTmpCStride : kTmpLStride, ds = pl ? kResCStride : kResLStride;
@@ -457,6 +447,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     int *s_m2l = s_tmp;                                        // [NL][16][kM2LWords]
     int *s_m2c = s_tmp + NL * kTileCap * kM2LWords;            // [NL][16][2][kM2CWords]
     const int maxv2 = ((1 << a.bd_l) - 1) * 0x00010001;        // the reference clips all planes with the luma depth
+    const int maxc2 = ((1 << a.bd_c) - 1) * 0x00010001;
     const int s1l = min(4, a.bd_l - 8), s2l = max(8, 20 - a.bd_l);
     const int s1c = min(4, a.bd_c - 8), s2c = max(8, 20 - a.bd_c);
 
@@ -465,144 +456,167 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (round > 0) issue_round(round);
         mbar_wait(mbar, round & 1);
 
-        // ---- horizontal stage: tasks of 2 rows x 8 columns, output = vertical pairs -------------------------------------------
-        // per (slot, list): luma 12 pair-rows x 2 halves = 24 tasks, chroma 2 planes x 6 pair-rows = 12 tasks
-        for (int id = tid; id < kTileCap * NL * 36; id += kR2Threads) {
-            const int sl = id / 36, k = id - sl * 36;
-            const int slot = sl & (kTileCap - 1), l = sl / kTileCap;
-            if (slot >= nt) continue;
-            const TileDesc td = s_tile[t0 + slot];
-            if (l >= td.nl) continue;
-            const TilePred p = s_pred[(t0 + slot) * NL + l];
-            if (k < 24) {
-                const int rp = k >> 1, half = k & 1;
-                if (2 * rp >= td.th + 7 || half * 8 >= td.tw) continue;
-                const int offx = p.offs & 7, par = offx & 1;
-                const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
-                const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
-                const int sh = p.two_d ? s1l : 6;
-                int hv[2][8];
+        // ---- horizontal stage: output = vertical pairs --------------------------------------------------------------------------
+        // luma: 12 threads per (slot, list) = 2 column halves x 6 interleaved groups of two row-pairs {g, g+6};
+        // chroma: 4 threads per (slot, list) = 2 planes x 2 halves of three row-pairs.  16 slots: 192 + 64 threads per list.
+#pragma unroll 1
+        for (int l = 0; l < NL; l++) {
+            if (tid < 192) {
+                const int slot = tid / 12, rem = tid - slot * 12, half = rem / 6, g = rem - half * 6;
+                if (slot < nt && l < s_tile[t0 + slot].nl) {
+                    const TileDesc td = s_tile[t0 + slot];
+                    const TilePred p = s_pred[(t0 + slot) * NL + l];
+                    if (half * 8 < td.tw) {
+                        const int offx = p.offs & 7, par = offx & 1;
+                        const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
+                        const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
+                        const int sh = p.two_d ? s1l : 6;
+                        int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + half * 8;
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
-                    int q[8];
+                        for (int it = 0; it < 2; it++) {
+                            const int rp = g + 6 * it;
+                            if (2 * rp >= td.th + 7) continue;
+                            int hv[2][8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) q[j] = rowp[j];
+                            for (int rr = 0; rr < 2; rr++) {
+                                const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
+                                int q[8];
 #pragma unroll
-                    for (int o = 0; o < 4; o++) {
-                        hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
-                        hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                                for (int j = 0; j < 8; j++) q[j] = rowp[j];
+#pragma unroll
+                                for (int o = 0; o < 4; o++) {
+                                    hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                                    hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                                }
+                            }
+                            int4 *dst = (int4 *)(m2 + rp * kM2LStrideW);
+                            dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                            dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+                        }
                     }
                 }
-                int4 *dst = (int4 *)(s_m2l + (l * kTileCap + slot) * kM2LWords + rp * kM2LStrideW + half * 8);
-                dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
-                dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
             } else {
-                const int kk = k - 24, pl = kk / 6, rp = kk - pl * 6;
-                if (2 * rp >= (td.th >> 1) + 3) continue;
-                const int offx = p.offs >> 4, par = offx & 1;
-                const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
-                const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
-                const int sh = p.ctwo_d ? s1c : 6;
-                int hv[2][8];
+                const int id = tid - 192, slot = id >> 2, pl = (id >> 1) & 1, hh = id & 1;
+                if (slot < nt && l < s_tile[t0 + slot].nl) {
+                    const TileDesc td = s_tile[t0 + slot];
+                    const TilePred p = s_pred[(t0 + slot) * NL + l];
+                    const int offx = p.offs >> 4, par = offx & 1;
+                    const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
+                    const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
+                    const int sh = p.ctwo_d ? s1c : 6;
+                    int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords;
 #pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
-                    int q[6];
+                    for (int it = 0; it < 3; it++) {
+                        const int rp = hh * 3 + it;
+                        if (2 * rp >= (td.th >> 1) + 3) continue;
+                        int hv[2][8];
 #pragma unroll
-                    for (int j = 0; j < 6; j++) q[j] = rowp[j];
+                        for (int rr = 0; rr < 2; rr++) {
+                            const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
+                            int q[6];
 #pragma unroll
-                    for (int o = 0; o < 4; o++) {
-                        hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
-                        hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                            for (int j = 0; j < 6; j++) q[j] = rowp[j];
+#pragma unroll
+                            for (int o = 0; o < 4; o++) {
+                                hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                                hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                            }
+                        }
+                        int4 *dst = (int4 *)(m2 + rp * kM2CStrideW);
+                        dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                        dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
                     }
                 }
-                int4 *dst = (int4 *)(s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + rp * kM2CStrideW);
-                dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
-                dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
             }
         }
         __syncthreads();
 
-        // ---- vertical stage + reconstruction: luma tasks = 2 columns x 8 rows, chroma tasks = 2 columns x 4 rows ----------------
-        // per slot: 16 luma tasks (8 column pairs x 2 row groups) + 16 chroma tasks (2 planes x 4 column pairs x 2 row groups)
-        for (int id = tid; id < nt * 32; id += kR2Threads) {
-            const int slot = id >> 5, k = id & 31;
-            const TileDesc td = s_tile[t0 + slot];
-            if (k < 16) {
-                const int cp = k & 7, rg = k >> 3;
-                if (2 * cp >= td.tw || 8 * rg >= td.th) continue;
-                int outp[8];                                   // packed (col, col+1) per row
+        // ---- vertical stage + reconstruction -------------------------------------------------------------------------------------------
+        // luma: one thread = 2 columns x 8 rows, 16 threads per slot (8 column pairs x 2 row groups)
+        {
+            const int slot = tid >> 4, k = tid & 15;
+            const int cp = k & 7, rg = k >> 3;
+            if (slot < nt) {
+                const TileDesc td = s_tile[t0 + slot];
+                if (2 * cp < td.tw && 8 * rg < td.th) {
+                    int outp[8];                                   // packed (col, col+1) per row
 #pragma unroll
-                for (int l = 0; l < NL; l++) {
-                    if (l >= td.nl) continue;
-                    const TilePred p = s_pred[(t0 + slot) * NL + l];
-                    const Taps5 te = ld_taps5(p.phy, 0), to = ld_taps5(p.phy, 1);
-                    const int sh = p.two_d ? s2l : 6, rnd = p.two_d ? (1 << (s2l - 1)) : 0;
-                    const int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + (4 * rg) * kM2LStrideW + 2 * cp;
-                    int P[8][2];
+                    for (int l = 0; l < NL; l++) {
+                        if (l >= td.nl) continue;
+                        const TilePred p = s_pred[(t0 + slot) * NL + l];
+                        const Taps5 te = ld_taps5(p.phy, 0), to = ld_taps5(p.phy, 1);
+                        const int sh = p.two_d ? s2l : 6, rnd = p.two_d ? (1 << (s2l - 1)) : 0;
+                        const int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + (4 * rg) * kM2LStrideW + 2 * cp;
+                        int P[8][2];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { const int2 v = *(const int2 *)(m2 + j * kM2LStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+                        for (int j = 0; j < 8; j++) { const int2 v = *(const int2 *)(m2 + j * kM2LStrideW); P[j][0] = v.x; P[j][1] = v.y; }
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        int e0 = fir5(te, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], 0, rnd) >> sh;
-                        int e1 = fir5(te, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], 0, rnd) >> sh;
-                        int o0 = fir5(to, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], P[q + 4][0], rnd) >> sh;
-                        int o1 = fir5(to, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], P[q + 4][1], rnd) >> sh;
-                        int pe = __vimin_s16x2_relu(pack16(e0, e1), maxv2);
-                        int po = __vimin_s16x2_relu(pack16(o0, o1), maxv2);
-                        if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
-                        else {      // xevd_average_16b_no_clip on two clipped, non-negative predictions
-                            outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
-                            outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                        for (int q = 0; q < 4; q++) {
+                            int e0 = fir5(te, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], 0, rnd) >> sh;
+                            int e1 = fir5(te, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], 0, rnd) >> sh;
+                            int o0 = fir5(to, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], P[q + 4][0], rnd) >> sh;
+                            int o1 = fir5(to, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], P[q + 4][1], rnd) >> sh;
+                            int pe = __vimin_s16x2_relu(pack16(e0, e1), maxv2);
+                            int po = __vimin_s16x2_relu(pack16(o0, o1), maxv2);
+                            if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                            else {      // xevd_average_16b_no_clip on two clipped, non-negative predictions
+                                outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                                outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                            }
                         }
                     }
-                }
-                const int x = td.px + 2 * cp, y = td.py + 8 * rg;
-                const int *res = (const int *)(s_res + y * kResLStride + x);
-                pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
+                    const int x = td.px + 2 * cp, y = td.py + 8 * rg;
+                    const int *res = (const int *)(s_res + y * kResLStride + x);
+                    pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
 #pragma unroll
-                for (int r = 0; r < 8; r++)
-                    if (8 * rg + r < td.th)
-                        *(int *)(dst + (size_t)r * a.s_l) = __viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
-            } else {
-                const int kk = k - 16, pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
+                    for (int r = 0; r < 8; r++)
+                        if (8 * rg + r < td.th)
+                            *(int *)(dst + (size_t)r * a.s_l) = __viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+                }
+            }
+        }
+        // chroma: one thread = 2 columns x 4 rows, 16 threads per slot (2 planes x 4 column pairs x 2 row groups)
+        {
+            const int slot = tid >> 4, kk = tid & 15;
+            const int pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
+            if (slot < nt) {
+                const TileDesc td = s_tile[t0 + slot];
                 const int cw = td.tw >> 1, ch = td.th >> 1;
-                if (2 * cp >= cw || 4 * rg >= ch) continue;
-                int outp[4];
+                if (2 * cp < cw && 4 * rg < ch) {
+                    int outp[4];
 #pragma unroll
-                for (int l = 0; l < NL; l++) {
-                    if (l >= td.nl) continue;
-                    const TilePred p = s_pred[(t0 + slot) * NL + l];
-                    const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
-                    const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
-                    const int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
-                    int P[4][2];
+                    for (int l = 0; l < NL; l++) {
+                        if (l >= td.nl) continue;
+                        const TilePred p = s_pred[(t0 + slot) * NL + l];
+                        const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
+                        const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
+                        const int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
+                        int P[4][2];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+                        for (int j = 0; j < 4; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
 #pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        int e0 = fir3(te, P[q][0], P[q + 1][0], 0, rnd) >> sh;
-                        int e1 = fir3(te, P[q][1], P[q + 1][1], 0, rnd) >> sh;
-                        int o0 = fir3(to, P[q][0], P[q + 1][0], P[q + 2][0], rnd) >> sh;
-                        int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
-                        const int maxc = ((1 << a.bd_c) - 1) * 0x00010001;
-                        int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc);
-                        int po = __vimin_s16x2_relu(pack16(o0, o1), maxc);
-                        if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
-                        else {
-                            outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
-                            outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                        for (int q = 0; q < 2; q++) {
+                            int e0 = fir3(te, P[q][0], P[q + 1][0], 0, rnd) >> sh;
+                            int e1 = fir3(te, P[q][1], P[q + 1][1], 0, rnd) >> sh;
+                            int o0 = fir3(to, P[q][0], P[q + 1][0], P[q + 2][0], rnd) >> sh;
+                            int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
+                            int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
+                            int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
+                            if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                            else {
+                                outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                                outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                            }
                         }
                     }
-                }
-                const int x = (td.px >> 1) + 2 * cp, y = (td.py >> 1) + 4 * rg;
-                const int *res = (const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + y * kResCStride + x);
-                pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
+                    const int x = (td.px >> 1) + 2 * cp, y = (td.py >> 1) + 4 * rg;
+                    const int *res = (const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + y * kResCStride + x);
+                    pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
 #pragma unroll
-                for (int r = 0; r < 4; r++)
-                    if (4 * rg + r < ch)
-                        *(int *)(dst + (size_t)r * a.s_c) = __viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+                    for (int r = 0; r < 4; r++)
+                        if (4 * rg + r < ch)
+                            *(int *)(dst + (size_t)r * a.s_c) = __viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+                }
             }
         }
         __syncthreads();
