@@ -92,7 +92,10 @@ typedef struct XB200_CU {
                                  coefficient stream: [Y w*h][Cb w*h/4][Cr w*h/4], CU-raster;
                                  planes whose cbf bits are all 0 are absent (no bytes); every
                                  plane block starts on a multiple of 8 int16 (16 bytes) and is
-                                 zero-padded up to one (only 4-wide/4-high CUs ever need pad)    */
+                                 zero-padded up to one (only 4-wide/4-high CUs ever need pad).
+                                 The stream is in decoding order: coef_off of CU k+1 equals
+                                 coef_off of CU k plus the (padded) size of CU k's coded planes,
+                                 also for CUs without coefficients (size 0)                      */
 } XB200_CU;
 
 /* extension record, 32 bytes: meaning depends on XB200_CU.mode */

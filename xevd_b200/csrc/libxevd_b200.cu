@@ -93,6 +93,28 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
+    {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
+        int16_t hl[2][16][8], hc[2][32][4];
+        cudaMemcpyFromSymbol(hl, c_mc_l, sizeof(hl));
+        cudaMemcpyFromSymbol(hc, c_mc_c, sizeof(hc));
+        int t5[2][16 * 9], t3[2][32 * 6];
+        for (int m = 0; m < 2; m++) {
+            for (int ph = 0; ph < 16; ph++) xb::build_taps8(hl[m][ph], t5[m] + ph * 9);
+            for (int ph = 0; ph < 32; ph++) xb::build_taps4(hc[m][ph], t3[m] + ph * 6);
+        }
+        cudaMemcpyToSymbol(xb::c_taps5, t5, sizeof(t5));
+        cudaMemcpyToSymbol(xb::c_taps3, t3, sizeof(t3));
+    }
+    if (getenv("XB200_DEBUG")) {
+        for (int nl = 1; nl <= 2; nl++)
+            for (int mc = 16; mc <= 256; mc *= 4) {
+                int nb = 0;
+                const int sm = xb::R2Layout::make(nl, mc).total;
+                if (nl == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<false>, xb::kR2Threads, sm);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<true>, xb::kR2Threads, sm);
+                fprintf(stderr, "[xb200] k_recon_inter_v2 lists=%d max_cu=%d: %d B dynamic smem, %d CTAs/SM\n", nl, mc, sm, nb);
+            }
+    }
     if (err) *err = XB200_OK;
     return c;
 }
@@ -319,6 +341,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     (void)n_ext; (void)n_coef;
     if (has_intra) return XB200_ERR_UNSUPPORTED;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
     a.cus = (const XB200_CU *)d_cus;
     a.ctu_first = (const uint32_t *)d_ctu_first;
@@ -331,8 +354,9 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         max_cu = (max_cu + 15) & ~15;
         const bool bi = n1 > 0;
         const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu);
-        if (bi) xb::k_recon_inter_v2<true><<<a.n_ctu, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-        else    xb::k_recon_inter_v2<false><<<a.n_ctu, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        const dim3 grid(a.w_ctu, a.n_ctu / a.w_ctu);
+        if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        else    xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
     } else {
         const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
         if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);

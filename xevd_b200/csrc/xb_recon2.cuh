@@ -74,7 +74,7 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
 // 32 consecutive line tasks run the same butterfly size; line -> block lookup is a binary search over the
 // per-block line prefix sums (no per-line lists).
 struct R2Layout {
-    int win_l, win_c, scratch, res_y, cus, tus, pre1, pre2, tiles, preds, offs, taps, total;
+    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, tiles, preds, offs, taps, total;
     __host__ __device__ static R2Layout make(int nl, int max_cu)
     {
         R2Layout L;
@@ -84,7 +84,7 @@ struct R2Layout {
         const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
         const int m2_bytes = 4 * nl * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
-        L.res_y = o; o += 2 * (64 * kResLStride + 2 * 32 * kResCStride);
+        L.res_y = o; L.coef = o; o += 2 * (64 * kResLStride + 2 * 32 * kResCStride);
         L.cus = o; o += 32 * max_cu;
         L.tus = o; o += 16 * 3 * max_cu;
         L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
@@ -147,9 +147,12 @@ __device__ __forceinline__ int fir3(const Taps3 &t, int p0, int p1, int p2, int 
     acc = __dp2a_lo(p2, t.r1, acc);
     return acc;
 }
-__device__ __forceinline__ int pk2(int lo, int hi) { return (lo & 0xff) | ((hi & 0xff) << 8); }
-// tap-set tables in shared memory: luma [phase][set 0..2 = A0, B, A1][3 regs], chroma [phase][set][2 regs]
-__device__ __forceinline__ void build_taps8(const int16_t *c, int *dst)
+__host__ __device__ __forceinline__ int pk2(int lo, int hi) { return (lo & 0xff) | ((hi & 0xff) << 8); }
+// tap-set tables: luma [phase][set 0..2 = A0, B, A1][3 regs], chroma [phase][set][2 regs]; built on the host at
+// context creation (xb_build_tap_tables) and copied into shared memory by every CTA
+__constant__ int c_taps5[2][16 * 9];
+__constant__ int c_taps3[2][32 * 6];
+__host__ __device__ __forceinline__ void build_taps8(const int16_t *c, int *dst)
 {
     const int a0 = pk2(c[0], c[1]), a1 = pk2(c[2], c[3]), a2 = pk2(c[4], c[5]), a3 = pk2(c[6], c[7]);
     const int b0 = pk2(0, c[0]), b1 = pk2(c[1], c[2]), b2 = pk2(c[3], c[4]), b3 = pk2(c[5], c[6]), b4 = pk2(c[7], 0);
@@ -157,7 +160,7 @@ __device__ __forceinline__ void build_taps8(const int16_t *c, int *dst)
     dst[3] = b0 | (b1 << 16); dst[4] = b2 | (b3 << 16); dst[5] = b4;
     dst[6] = (a0 << 16);      dst[7] = a1 | (a2 << 16); dst[8] = a3;
 }
-__device__ __forceinline__ void build_taps4(const int16_t *c, int *dst)
+__host__ __device__ __forceinline__ void build_taps4(const int16_t *c, int *dst)
 {
     const int a0 = pk2(c[0], c[1]), a1 = pk2(c[2], c[3]);
     const int b0 = pk2(0, c[0]), b1 = pk2(c[1], c[2]), b2 = pk2(c[3], 0);
@@ -237,8 +240,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     int16_t *s_res = (int16_t *)(smem + L.res_y);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ctu = blockIdx.x;
-    const int ctu_x = (ctu % a.w_ctu) << 6, ctu_y = (ctu / a.w_ctu) << 6;
+    const int ctu = blockIdx.y * a.w_ctu + blockIdx.x;
+    const int ctu_x = blockIdx.x << 6, ctu_y = blockIdx.y << 6;
     const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
 
     // ---- stage CU descriptors, zero the residual, init barrier, build tap tables --------------------------------------------
@@ -246,43 +249,63 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         const int4 *g = (const int4 *)(a.cus + cu0);
         int4 *s = (int4 *)s_cu;
         for (int i = tid; i < ncu * 2; i += kR2Threads) s[i] = __ldg(g + i);
-        int4 *z = (int4 *)s_res;
+        int4 *z = (int4 *)s_res;            // uncoded blocks must read as zero residual
         const int nz = 2 * (64 * kResLStride + 2 * 32 * kResCStride) / 16;
         for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
         if (tid == 0) mbar_init(mbar, 1);
         int *t8 = (int *)(smem + L.taps), *t4 = t8 + 16 * 9;
-        if (tid >= 64 && tid < 80) build_taps8(c_mc_l[a.main_tables][tid - 64], t8 + (tid - 64) * 9);
-        else if (tid >= 96 && tid < 128) build_taps4(c_mc_c[a.main_tables][tid - 96], t4 + (tid - 96) * 6);
+        if (tid < 16 * 9) t8[tid] = c_taps5[a.main_tables][tid];
+        if (tid < 32 * 6) t4[tid] = c_taps3[a.main_tables][tid];
     }
     const int *s_t8 = (const int *)(smem + L.taps), *s_t4 = s_t8 + 16 * 9;
     auto ld_taps5 = [&](int ph, int set) { Taps5 t; const int *q = s_t8 + (ph & 15) * 9 + set * 3; t.r0 = q[0]; t.r1 = q[1]; t.r2 = q[2]; return t; };
     auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
     __syncthreads();
 
-    // ---- warp 0: per-CU counts -> exclusive prefix sums ------------------------------------------------------------------------
+    // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the
+    //      stream.  Pull it towards L1 now (fire-and-forget prefetches); the row pass reads it two barriers later.
+    //      (A cp.async.bulk of the slice into shared memory was measured 35 % slower end to end: profiles/r1.)
+    int coef_base = 0;
+    if (ncu > 0) {
+        const XB200_CU c0 = s_cu[0], c1 = s_cu[ncu - 1];
+        coef_base = c0.coef_off;
+        const int n1 = 1 << (c1.log2w + c1.log2h);
+        int end = c1.coef_off;
+        if (c1.cbf & 0x00f) end += (n1 + 7) & ~7;
+        if (c1.cbf & 0x0f0) end += ((n1 >> 2) + 7) & ~7;
+        if (c1.cbf & 0xf00) end += ((n1 >> 2) + 7) & ~7;
+        for (int o = coef_base + tid * 64; o < end; o += kR2Threads * 64)      // one 128-byte line per thread
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.coef + o));
+    }
+
+    // ---- per-CU counts -> exclusive prefix sums: warp q scans quantity q -------------------------------------------------------
     // q: 0 luma blocks, 1 chroma blocks, 2 pass-1 luma lines, 3 pass-1 chroma lines, 4 pass-2 luma lines, 5 pass-2 chroma, 6 tiles
-    if (warp == 0) {
-        int run[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (warp < 7) {
+        int run = 0;
         for (int base = 0; base < ncu; base += 32) {
             const int i = base + lane;
-            int c[7] = {0, 0, 0, 0, 0, 0, 0};
+            int c = 0;
             if (i < ncu) {
                 const XB200_CU cu = s_cu[i];
                 const int w = 1 << cu.log2w, h = 1 << cu.log2h;
                 const int ny = (cu.cbf & 15) ? 1 : 0, nc = ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0);
-                c[0] = ny; c[1] = nc; c[2] = ny * h; c[3] = nc * (h >> 1); c[4] = ny * w; c[5] = nc * (w >> 1);
-                c[6] = max(1, w >> 4) * max(1, h >> 4);
+                switch (warp) {
+                case 0: c = ny; break;
+                case 1: c = nc; break;
+                case 2: c = ny * h; break;
+                case 3: c = nc * (h >> 1); break;
+                case 4: c = ny * w; break;
+                case 5: c = nc * (w >> 1); break;
+                default: c = max(1, w >> 4) * max(1, h >> 4); break;
+                }
             }
+            int v = c;
 #pragma unroll
-            for (int q = 0; q < 7; q++) {
-                int v = c[q];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
-                if (i < ncu) s_offs[i * 8 + q] = run[q] + v - c[q];
-                run[q] += __shfl_sync(0xffffffffu, v, 31);
-            }
+            for (int d = 1; d < 32; d <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += t; }
+            if (i < ncu) s_offs[i * 8 + warp] = run + v - c;
+            run += __shfl_sync(0xffffffffu, v, 31);
         }
-        if (lane < 7) cnt[lane] = run[lane];
+        if (lane == 0) cnt[warp] = run;
     }
     __syncthreads();
     const int n_tuy = cnt[0], n_tuc = cnt[1], n_l1y = cnt[2], n_l1c = cnt[3], n_l2y = cnt[4], n_l2c = cnt[5], n_tiles = cnt[6];
@@ -302,7 +325,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             const int sh = pl ? 1 : 0;
             const int lw = cu.log2w - sh, lh = cu.log2h - sh;
             TuDesc d;
-            d.coef_off = coef;
+            d.coef_off = coef - coef_base;      // relative to the staged slice
             coef += ((1 << (lw + lh)) + 7) & ~7;
             d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
             d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
@@ -390,21 +413,34 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     };
     issue_round(0);
 
-    // block lookup: largest b in [lo, hi) with pre[b] <= i
-    auto find_tu = [&](const uint16_t *pre, int lo, int hi, int i) {
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)pre[mid] <= i) lo = mid; else hi = mid; }
-        return lo;
+    // Block lookup for a warp's 32 consecutive lines li0 .. li0+31 (all lanes participate): blocks are sorted by first
+    // line, so block(li0 + lane) = #{starts <= li0} - 1 + #{starts in (li0, li0 + lane]}.  One coalesced load of the
+    // prefix table, one ballot and one warp OR-reduction per 32 blocks instead of a per-lane binary search.
+    auto find_tu = [&](const uint16_t *pre, int lo, int hi, int li0) {
+        int c0 = 0;
+        unsigned m = 0;
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = k0 + lane;
+            const int p = k < hi ? (int)pre[k] : 0x7fffffff;
+            c0 += __popc(__ballot_sync(0xffffffffu, p <= li0));
+            const int dd = p - li0;
+            m |= __reduce_or_sync(0xffffffffu, (dd > 0 && dd < 32) ? (1u << dd) : 0u);
+            if (__shfl_sync(0xffffffffu, p, 31) > li0 + 31) break;
+        }
+        return lo + c0 - 1 + __popc(m & (0xffffffffu >> (31 - lane)));
     };
 
-    // ---- residual pass 1 (rows, IDP.2A): luma lines first, then chroma lines ---------------------------------------------------
-    for (int i = tid; i < n_l1y + n_l1c; i += kR2Threads) {
-        const bool chroma = i >= n_l1y;
-        const int li = chroma ? i - n_l1y : i;
-        const int b = chroma ? find_tu(s_pre1 + 1, n_tuy, n_tu, li) : find_tu(s_pre1, 0, n_tuy, li);
+    // ---- residual pass 1 (rows, IDP.2A): luma lines first, then chroma lines (each padded to whole warps) -----------------------
+    const int n_l1y_w = (n_l1y + 31) & ~31, n_l1c_w = (n_l1c + 31) & ~31;
+    for (int i0 = warp * 32; i0 < n_l1y_w + n_l1c_w; i0 += kR2Threads) {
+        const bool chroma = i0 >= n_l1y_w;
+        const int li0 = chroma ? i0 - n_l1y_w : i0, li = li0 + lane;
+        const int b = chroma ? find_tu(s_pre1 + 1, n_tuy, n_tu, li0) : find_tu(s_pre1, 0, n_tuy, li0);
+        if (li >= (chroma ? n_l1c : n_l1y)) continue;
         const TuDesc d = s_tu[b];
         const int r = li - (int)(chroma ? s_pre1[b + 1] : s_pre1[b]);
         const int lw = d.lw_lh & 15, pl = d.plane_wide & 3;
-        const int16_t *src = a.coef + d.coef_off + (r << d.cstride_log2);
+        const int16_t *src = a.coef + coef_base + d.coef_off + (r << d.cstride_log2);
         int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off +
                    r * (pl ? kTmpCStride : kTmpLStride);
         const int off = d.shift ? (1 << (d.shift - 1)) : 0;
@@ -422,10 +458,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     // ---- residual pass 2 (columns, IMAD) --------------------------------------------------------------------------------------
     {
         const int sh2 = 19 - (a.bd_l - 8);
-        for (int i = tid; i < n_l2y + n_l2c; i += kR2Threads) {
-            const bool chroma = i >= n_l2y;
-            const int li = chroma ? i - n_l2y : i;
-            const int b = chroma ? find_tu(s_pre2 + 1, n_tuy, n_tu, li) : find_tu(s_pre2, 0, n_tuy, li);
+        const int n_l2y_w = (n_l2y + 31) & ~31, n_l2c_w = (n_l2c + 31) & ~31;
+        for (int i0 = warp * 32; i0 < n_l2y_w + n_l2c_w; i0 += kR2Threads) {
+            const bool chroma = i0 >= n_l2y_w;
+            const int li0 = chroma ? i0 - n_l2y_w : i0, li = li0 + lane;
+            const int b = chroma ? find_tu(s_pre2 + 1, n_tuy, n_tu, li0) : find_tu(s_pre2, 0, n_tuy, li0);
+            if (li >= (chroma ? n_l2c : n_l2y)) continue;
             const TuDesc d = s_tu[b];
             const int c = li - (int)(chroma ? s_pre2[b + 1] : s_pre2[b]);
             const int lh = d.lw_lh >> 4, pl = d.plane_wide & 3;
@@ -456,59 +494,52 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (round > 0) issue_round(round);
         mbar_wait(mbar, round & 1);
 
-        // ---- horizontal stage: output = vertical pairs --------------------------------------------------------------------------
-        // luma: 12 threads per (slot, list) = 2 column halves x 6 interleaved groups of two row-pairs {g, g+6};
-        // chroma: 4 threads per (slot, list) = 2 planes x 2 halves of three row-pairs.  16 slots: 192 + 64 threads per list.
+        // ---- horizontal stage (warp-local: warp w owns tile slots 2w, 2w+1 through both stages), output = vertical pairs ------
+        // luma: 24 tasks per slot (2 column halves x 12 row-pairs), chroma: 12 per slot (2 planes x 6 row-pairs)
 #pragma unroll 1
         for (int l = 0; l < NL; l++) {
-            if (tid < 192) {
-                const int slot = tid / 12, rem = tid - slot * 12, half = rem / 6, g = rem - half * 6;
-                if (slot < nt && l < s_tile[t0 + slot].nl) {
-                    const TileDesc td = s_tile[t0 + slot];
-                    const TilePred p = s_pred[(t0 + slot) * NL + l];
-                    if (half * 8 < td.tw) {
-                        const int offx = p.offs & 7, par = offx & 1;
-                        const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
-                        const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
-                        const int sh = p.two_d ? s1l : 6;
-                        int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + half * 8;
+#pragma unroll 1
+            for (int it = 0; it < 2; it++) {
+                const int task = it * 32 + lane;
+                if (task >= 48) continue;
+                const int sidx = task >= 24 ? 1 : 0, k = task - 24 * sidx, half = k >= 12 ? 1 : 0, rp = k - 12 * half;
+                const int slot = 2 * warp + sidx;
+                if (slot >= nt) continue;
+                const TileDesc td = s_tile[t0 + slot];
+                if (l >= td.nl || half * 8 >= td.tw || 2 * rp >= td.th + 7) continue;
+                const TilePred p = s_pred[(t0 + slot) * NL + l];
+                const int offx = p.offs & 7, par = offx & 1;
+                const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
+                const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
+                const int sh = p.two_d ? s1l : 6;
+                int hv[2][8];
 #pragma unroll
-                        for (int it = 0; it < 2; it++) {
-                            const int rp = g + 6 * it;
-                            if (2 * rp >= td.th + 7) continue;
-                            int hv[2][8];
+                for (int rr = 0; rr < 2; rr++) {
+                    const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
+                    int q[8];
 #pragma unroll
-                            for (int rr = 0; rr < 2; rr++) {
-                                const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
-                                int q[8];
+                    for (int j = 0; j < 8; j++) q[j] = rowp[j];
 #pragma unroll
-                                for (int j = 0; j < 8; j++) q[j] = rowp[j];
-#pragma unroll
-                                for (int o = 0; o < 4; o++) {
-                                    hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
-                                    hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
-                                }
-                            }
-                            int4 *dst = (int4 *)(m2 + rp * kM2LStrideW);
-                            dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
-                            dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
-                        }
+                    for (int o = 0; o < 4; o++) {
+                        hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                        hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
                     }
                 }
-            } else {
-                const int id = tid - 192, slot = id >> 2, pl = (id >> 1) & 1, hh = id & 1;
-                if (slot < nt && l < s_tile[t0 + slot].nl) {
+                int4 *dst = (int4 *)(s_m2l + (l * kTileCap + slot) * kM2LWords + half * 8 + rp * kM2LStrideW);
+                dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+            }
+            if (lane < 24) {
+                const int sidx = lane >= 12 ? 1 : 0, k = lane - 12 * sidx, pl = k >= 6 ? 1 : 0, rp = k - 6 * pl;
+                const int slot = 2 * warp + sidx;
+                if (slot < nt) {
                     const TileDesc td = s_tile[t0 + slot];
-                    const TilePred p = s_pred[(t0 + slot) * NL + l];
-                    const int offx = p.offs >> 4, par = offx & 1;
-                    const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
-                    const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
-                    const int sh = p.ctwo_d ? s1c : 6;
-                    int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords;
-#pragma unroll
-                    for (int it = 0; it < 3; it++) {
-                        const int rp = hh * 3 + it;
-                        if (2 * rp >= (td.th >> 1) + 3) continue;
+                    if (l < td.nl && 2 * rp < (td.th >> 1) + 3) {
+                        const TilePred p = s_pred[(t0 + slot) * NL + l];
+                        const int offx = p.offs >> 4, par = offx & 1;
+                        const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
+                        const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
+                        const int sh = p.ctwo_d ? s1c : 6;
                         int hv[2][8];
 #pragma unroll
                         for (int rr = 0; rr < 2; rr++) {
@@ -522,14 +553,14 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                                 hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
                             }
                         }
-                        int4 *dst = (int4 *)(m2 + rp * kM2CStrideW);
+                        int4 *dst = (int4 *)(s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + rp * kM2CStrideW);
                         dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
                         dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
                     }
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
 
         // ---- vertical stage + reconstruction -------------------------------------------------------------------------------------------
         // luma: one thread = 2 columns x 8 rows, 16 threads per slot (8 column pairs x 2 row groups)
@@ -619,7 +650,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 }
             }
         }
-        __syncthreads();
+        if (round + 1 < n_rounds) __syncthreads();      // the next round's TMA overwrites every warp's windows
     }
 
     // ---- publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------------------------

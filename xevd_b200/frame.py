@@ -141,6 +141,10 @@ class CuList:
         idx = (c["y"] // ctu).astype(np.int64) * wc + c["x"] // ctu
         owner = np.repeat(np.arange(self.n_ctu), np.diff(self.ctu_first.astype(np.int64)))
         assert np.array_equal(idx, owner), "CUs not grouped by CTU in raster order"
+        sizes = np.array([cu_coef_count(cu) for cu in c], np.int64)
+        run = np.concatenate(([0], np.cumsum(sizes)))
+        assert np.array_equal(c["coef_off"].astype(np.int64), run[:-1]), "coefficient stream not in decoding order"
+        assert run[-1] == self.coef.size
         return self
 
     def edge_flags(self) -> np.ndarray:
