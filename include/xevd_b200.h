@@ -166,6 +166,12 @@ void *xb200_stream(xb200_ctx *ctx);                       /* the cudaStream_t al
 int  xb200_set_stream(xb200_ctx *ctx, void *cuda_stream); /* use a caller-owned stream                   */
 long long xb200_launch_count(xb200_ctx *ctx);             /* kernels launched by this context so far     */
 
+/* page-locked host memory: buffers handed to the host-pointer entry points are copied by DMA without an
+ * intermediate copy when they come from here (XEVD_CU_DATA.coef in the reference is a plain xevd_malloc,
+ * src_base/xevd.c:1685-1738; an integration allocates it with xb200_host_alloc instead) */
+void *xb200_host_alloc(size_t bytes);
+void  xb200_host_free(void *p);
+
 /* ---- pictures (PICBUF_ALLOCATOR) ------------------------------------------------------------------ */
 xb200_pic *xb200_pic_alloc(xb200_ctx *ctx, int w, int h, int *err);
 void xb200_pic_free(xb200_ctx *ctx, xb200_pic *pic);

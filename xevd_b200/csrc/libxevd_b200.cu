@@ -151,6 +151,15 @@ int xb200_set_stream(xb200_ctx *c, void *s)
 }
 long long xb200_launch_count(xb200_ctx *c) { return c ? c->launches : 0; }
 
+// ---- page-locked host memory for the producer side (coefficient stream, CU arrays, output planes) ---------------------
+void *xb200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void xb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 // ---- pictures ---------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -400,15 +409,23 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     int r = stage_acquire(c, b_cu + b_first + b_ext + b_coef, &s);
     if (r < 0) return r;
     unsigned char *hp = (unsigned char *)s->pinned, *dp = (unsigned char *)s->dev;
-    memcpy(hp, cus, (size_t)n_cu * sizeof(XB200_CU));
-    memcpy(hp + b_cu, ctu_first, (size_t)(n_ctu + 1) * 4);
-    if (ext && n_ext > 0) memcpy(hp + b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT));
-    if (coef && n_coef) memcpy(hp + b_cu + b_first + b_ext, coef, n_coef * 2);
+    // Page-locked caller memory (xb200_host_alloc, cudaHostRegister, ...) is DMA'd straight to the device slot; pageable
+    // memory goes through the context's pinned staging buffer first.
+    auto h2d = [&](size_t off, const void *src, size_t bytes) -> cudaError_t {
+        if (!src || !bytes) return cudaSuccess;
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        if (!pinned) { cudaGetLastError(); memcpy(hp + off, src, bytes); src = hp + off; }
+        return cudaMemcpyAsync(dp + off, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    };
     int has_intra = 0, max_cu = 0, any_l1 = 0;
     for (int i = 0; i < n_cu; i++) { has_intra |= (cus[i].mode == XB200_MODE_INTRA); any_l1 |= (cus[i].mode != XB200_MODE_INTRA && cus[i].refi[1] >= 0); }
     if (!any_l1) n1 = 0;          // P picture: no CU predicts from list 1 (selects the single-list kernel)
     for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
-    CK(c, cudaMemcpyAsync(dp, hp, b_cu + b_first + b_ext + b_coef, cudaMemcpyHostToDevice, c->stream));
+    CK(c, h2d(0, cus, (size_t)n_cu * sizeof(XB200_CU)));
+    CK(c, h2d(b_cu, ctu_first, (size_t)(n_ctu + 1) * 4));
+    if (n_ext > 0) CK(c, h2d(b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT)));
+    CK(c, h2d(b_cu + b_first + b_ext, coef, n_coef * 2));
     r = xb200_recon_frame_dev(c, prm, cur, l0, n0, l1, n1, dp, n_cu, dp + b_cu, n_ctu, dp + b_cu + b_first, n_ext,
                               dp + b_cu + b_first + b_ext, n_coef, has_intra, max_cu);
     CK(c, cudaEventRecord(s->done, c->stream));
