@@ -153,6 +153,7 @@ typedef struct XB200_PIC_INFO {
     void   *dev_map_scu;          /* uint32[w_scu*h_scu], bit layout xevd_def.h:372-437                 */
     int32_t w_scu, h_scu;
     int32_t poc;
+    void   *dev_map_edge;         /* uint8[w_scu*h_scu], XB200_EDGE_* flags written by xb200_recon_frame      */
 } XB200_PIC_INFO;
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -186,6 +187,7 @@ int  xb200_pic_download(xb200_ctx *ctx, xb200_pic *pic,
 /* full padded planes (incl. borders), for checking xb200_pad against xevd_picbuf_expand */
 int  xb200_pic_download_padded(xb200_ctx *ctx, xb200_pic *pic, xb200_pel *y, xb200_pel *u, xb200_pel *v);
 int  xb200_pic_download_maps(xb200_ctx *ctx, xb200_pic *pic, int16_t *map_mv, int8_t *map_refi, uint32_t *map_scu);
+int  xb200_pic_download_edge_map(xb200_ctx *ctx, xb200_pic *pic, uint8_t *map_edge);
 
 /* ---- per-picture reconstruction (xevd_ctu_row_rec_mt) ---------------------------------------------- */
 /*
@@ -210,12 +212,19 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
 /* edge flags, one byte per SCU */
 #define XB200_EDGE_LEFT   0x01    /* a CU/TU boundary runs along the left side of this SCU           */
 #define XB200_EDGE_TOP    0x02    /* ... along the top side                                          */
+/* Both passes (vertical edges, then horizontal edges) over the whole picture, in place.  The per-SCU maps
+ * (map_scu, map_mv, map_refi) and the edge flags are the ones xb200_recon_frame left in `cur`; edge_flags
+ * (host, w_scu*h_scu bytes) optionally replaces the device edge map first.  refs_* are only needed by the
+ * Main-profile filter (tool_addb), which compares reference PICTURES rather than indices.                  */
 int  xb200_deblock(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
                    xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
-                   const uint8_t *edge_flags /* host, w_scu*h_scu */);
-int  xb200_deblock_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
-                   xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
-                   const void *d_edge_flags);
+                   const uint8_t *edge_flags);
+/* chroma QP mapping used by deblocking: what xevd_qp_chroma_dynamic[0..1][0..57] holds for the sequence
+ * (src_base/xevd_tbl.c:359-425); the context starts with the Baseline default table                         */
+int  xb200_set_chroma_qp_table(xb200_ctx *ctx, const int32_t *tbl /* [2][58] */);
+/* test support: overwrite the per-SCU maps of a device picture from host arrays (any pointer may be NULL)   */
+int  xb200_pic_upload_maps(xb200_ctx *ctx, xb200_pic *pic, const int16_t *map_mv, const int8_t *map_refi,
+                           const uint32_t *map_scu, const uint8_t *map_edge);
 int  xb200_pad(xb200_ctx *ctx, xb200_pic *pic);           /* xevd_picbuf_expand                        */
 
 /* ---- batched leaf kernels (micro-benchmarks, BASELINE.json config 5) ------------------------------ */

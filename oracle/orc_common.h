@@ -71,4 +71,8 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                     const XB200_CU *cus, int n_cu, const XB200_CU_EXT *ext, const int16_t *coef);
 void orc_pad(ORC_PIC *pic);
 
+/* orc_df.c */
+int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl);
+const uint8_t *orc_df_strength_table(void);
+
 #endif

@@ -130,6 +130,25 @@ class _Backend:
             raise RuntimeError(f"{self.prefix}recon_frame failed: {r}")
         return cur
 
+    def deblock_frame(self, prm: Params, pic: HostPicture, cl: CuList, chroma_qp_tbl: np.ndarray, tool_addb: bool = False):
+        """both deblocking passes in place on `pic` (uses pic.map_scu / map_mv / map_refi)"""
+        o = orc_pic(pic)
+        cus = np.ascontiguousarray(cl.cus)
+        tbl = np.ascontiguousarray(chroma_qp_tbl, np.int32)
+        assert tbl.shape == (2, 58)
+        fn = getattr(self.lib, self.prefix + "deblock_frame")
+        fn.restype = C.c_int
+        if self.prefix == "ref_":
+            fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data, int(tool_addb))
+        else:
+            assert not tool_addb
+            fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p]
+            r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data)
+        if r < 0:
+            raise RuntimeError(f"{self.prefix}deblock_frame failed: {r}")
+        return pic
+
     def pad(self, pic: HostPicture):
         o = orc_pic(pic)
         getattr(self.lib, self.prefix + "pad")(C.byref(o))

@@ -29,6 +29,8 @@
 #include "xevd_recon_avx.h"
 #include "xevd_recon_sse.h"
 #include "xevd_dbk_sse.h"
+#include "xevd_df.h"
+#include "xevdm_df.h"
 #include "../include/xevd_b200.h"
 #include "orc_common.h"
 
@@ -218,4 +220,67 @@ void ref_pad(ORC_PIC *pic)
     XEVD_PIC p;
     wrap_pic(pic, &p);
     xevd_picbuf_lc_expand(&p, pic->pad_l, pic->pad_c);
+}
+
+/* ---- deblocking, Baseline filter through the Main library's CU walkers (tool_addb == 0) ----------------------------------
+ * Mirrors xevdm_deblock + deblock_tree's leaves (src_main/xevdm.c:1935-2103) for one tile / one slice: COD bits cleared,
+ * every CU visited in decoding order by xevdm_deblock_cu_ver (pass 1) then xevdm_deblock_cu_hor (pass 2), CUs larger than
+ * MAX_TR_SIZE visited as two halves. */
+int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl, int tool_addb)
+{
+    static XEVD_SPS sps;
+    XEVDM_CTX *m = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX));
+    XEVD_CTX *ctx = &m->bctx;
+    XEVD_PIC xp;
+    const int f_scu = pic->w_scu * pic->h_scu;
+    u32 *map_scu = (u32 *)malloc(sizeof(u32) * f_scu);
+    TREE_CONS tc = { FALSE, TREE_LC, eAll };
+    int pass, n, i;
+    ensure_init();
+    memset(&sps, 0, sizeof(sps));
+    sps.bit_depth_luma_minus8 = prm->bit_depth_luma - 8;
+    sps.bit_depth_chroma_minus8 = prm->bit_depth_chroma - 8;
+    sps.chroma_format_idc = prm->chroma_format_idc;
+    sps.tool_addb = tool_addb;
+    ctx->sps = &sps;
+    memcpy(map_scu, pic->map_scu, sizeof(u32) * f_scu);
+    ctx->map_scu = map_scu;
+    ctx->map_refi = (s8(*)[REFP_NUM])pic->map_refi;
+    ctx->map_mv = (s16(*)[REFP_NUM][MV_D])pic->map_mv;
+    m->map_unrefined_mv = ctx->map_mv;
+    ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu; ctx->w = pic->w_l; ctx->h = pic->h_l;
+    ctx->log2_max_cuwh = prm->log2_ctu;
+    ctx->map_tidx = (u8 *)calloc(f_scu, 1);
+    ctx->map_cu_mode = (u32 *)calloc(f_scu, sizeof(u32));
+    m->map_ats_inter = (u8 *)calloc(f_scu, 1);
+    ctx->fn_dbk = g_ctx->fn_dbk; ctx->fn_dbk_chroma = g_ctx->fn_dbk_chroma;
+    wrap_pic(pic, &xp);
+    xp.pic_qp_u_offset = prm->qp_u_offset; xp.pic_qp_v_offset = prm->qp_v_offset;
+    xp.pic_deblock_alpha_offset = prm->deblock_alpha_offset; xp.pic_deblock_beta_offset = prm->deblock_beta_offset;
+    /* chroma QP mapping: same set-up as sequence_init (src_main/xevdm.c:471-486) with the caller's table */
+    xevd_set_chroma_qp_tbl_loc(prm->bit_depth_chroma);
+    memcpy(xevd_qp_chroma_dynamic[0], chroma_qp_tbl, sizeof(int) * XEVD_MAX_QP_TABLE_SIZE);
+    memcpy(xevd_qp_chroma_dynamic[1], chroma_qp_tbl + XEVD_MAX_QP_TABLE_SIZE, sizeof(int) * XEVD_MAX_QP_TABLE_SIZE);
+
+    for (pass = 0; pass < 2; pass++) {
+        for (i = 0; i < f_scu; i++) MCU_CLR_COD(map_scu[i]);
+        for (n = 0; n < n_cu; n++) {
+            const int x = cus[n].x, y = cus[n].y, w = 1 << cus[n].log2w, h = 1 << cus[n].log2h;
+            if (pass == 0) {
+                const int parts = w > MAX_TR_SIZE ? 2 : 1;
+                for (i = 0; i < parts; i++)
+                    xevdm_deblock_cu_ver(ctx, &xp, x + i * MAX_TR_SIZE, y, w / parts, h, ctx->map_scu, ctx->map_refi, m->map_unrefined_mv, ctx->w_scu,
+                                         ctx->log2_max_cuwh, ctx->map_cu_mode, ctx->refp, 0, tc, ctx->map_tidx, 0, tool_addb, m->map_ats_inter,
+                                         prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+            } else {
+                const int parts = h > MAX_TR_SIZE ? 2 : 1;
+                for (i = 0; i < parts; i++)
+                    xevdm_deblock_cu_hor(ctx, &xp, x, y + i * MAX_TR_SIZE, w, h / parts, ctx->map_scu, ctx->map_refi, m->map_unrefined_mv, ctx->w_scu,
+                                         ctx->log2_max_cuwh, ctx->refp, 0, tc, ctx->map_tidx, 0, tool_addb, m->map_ats_inter,
+                                         prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+            }
+        }
+    }
+    free(ctx->map_tidx); free(ctx->map_cu_mode); free(m->map_ats_inter); free(map_scu); free(m);
+    return XB200_OK;
 }

@@ -1,0 +1,90 @@
+"""GPU parity: picture-wide passes (deblocking, padding) through the C ABI against the CPU oracle."""
+import numpy as np
+import pytest
+
+from xevd_b200 import synth
+from xevd_b200.frame import HostPicture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from xevd_b200.device import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _smooth(pic, bd):
+    for pl in pic.planes():
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,main_tbl", [("B", 4, 10, 0), ("A", 2, 10, 0), ("A", 3, 8, 1), ("B", 4, 8, 0), ("A", 6, 10, 1)])
+def test_deblock_baseline(ctx, oracle, variant, log2_cu, bd, main_tbl):
+    w, h = 192, 136
+    rng = np.random.default_rng(40 + log2_cu + bd)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=31, n_refs=2, coded_frac=0.5, log2_cu=log2_cu,
+                                     bi_frac=0.3, mv_range_px=3)
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    refs = synth.make_refs(w, h, bd, 2, seed=32)
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    _smooth(base, bd)
+    synth.randomize_deblock_maps(base, cl, rng)
+    tbl = synth.chroma_qp_table(bool(main_tbl))
+    want = oracle.deblock_frame(prm, base.copy(), cl, tbl)
+
+    d = ctx.pic_alloc(w, h).upload(base, padded=False).upload_maps(base, cl.edge_flags())
+    ctx.set_chroma_qp_table(tbl)
+    ctx.deblock(prm, d)
+    got = d.download()
+    d.free()
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+def test_recon_then_deblock_pipeline(ctx, oracle):
+    """recon -> deblock -> pad on the device with the maps and edge flags the recon kernel itself published"""
+    w, h, bd = 320, 200, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=51, n_refs=2, coded_frac=0.6, mv_range_px=24)
+    cl.cus["qp_map"] = np.random.default_rng(3).integers(30, 46, cl.n_cu)
+    refs = synth.make_refs(w, h, bd, 2, seed=52)
+    for r in refs:                       # smooth references -> small edge steps -> the filter acts
+        _smooth(r, bd)
+        r.pad_borders()
+    tbl = synth.chroma_qp_table(False)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    pre = want.copy()
+    oracle.deblock_frame(prm, want, cl, tbl)
+    oracle.pad(want)
+    assert sum(int((x != y).sum()) for x, y in zip(want.planes(), pre.planes())) > 1000
+
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    i = cur.info()
+    ctx.deblock(prm, cur)
+    ctx.pad(cur)
+    got = cur.download_padded()
+    for p in drefs + [cur]:
+        p.free()
+    assert np.array_equal(got.buf_y, want.buf_y) and np.array_equal(got.buf_u, want.buf_u) and np.array_equal(got.buf_v, want.buf_v)
+
+
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_edge_map_published_by_recon(oracle, monkeypatch, force):
+    """both recon kernels publish the CU/TU edge flags the deblocking pass consumes"""
+    from xevd_b200.device import Context
+    monkeypatch.setenv("XB200_FORCE_GENERIC", force)
+    c = Context(0)
+    w, h, bd = 256, 128, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=61, n_refs=1)
+    refs = synth.make_refs(w, h, bd, 1, seed=62)
+    drefs = [c.pic_alloc(w, h).upload(r) for r in refs]
+    cur = c.pic_alloc(w, h)
+    c.recon_frame(prm, cur, drefs, drefs, cl)
+    edge = cur.download_edge_map()
+    assert np.array_equal(edge, cl.edge_flags())
+    c.close()

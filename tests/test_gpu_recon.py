@@ -117,3 +117,20 @@ def test_recon_saturating_residual(ctx, oracle):
     got = cur.download()
     for a, b, n in zip(got.planes(), want.planes(), "YUV"):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+def test_reference_index_outside_lists_is_rejected(ctx):
+    """bi-predicted CUs but an empty list 1: the host entry point refuses instead of launching"""
+    from xevd_b200.device import XevdB200Error
+    from xevd_b200 import abi
+    w, h, bd = 128, 64, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=71, n_refs=1)
+    assert (cl.cus["refi"][:, 1] >= 0).any()
+    refs = synth.make_refs(w, h, bd, 1, seed=72)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    with pytest.raises(XevdB200Error) as e:
+        ctx.recon_frame(prm, cur, drefs, [], cl)
+    assert e.value.code == abi.XB200_ERR_INVALID_ARGUMENT
+    for p in drefs + [cur]:
+        p.free()

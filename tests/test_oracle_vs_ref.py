@@ -103,3 +103,27 @@ def test_pad(oracle, reference):
     b = reference.pad(p.copy())
     assert np.array_equal(a.buf_y, b.buf_y) and np.array_equal(a.buf_u, b.buf_u) and np.array_equal(a.buf_v, b.buf_v)
     assert np.array_equal(a.buf_y, p.copy().pad_borders().buf_y)
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,main_tbl", [("B", 4, 10, 0), ("A", 2, 10, 0), ("A", 3, 8, 1), ("B", 4, 8, 0), ("A", 6, 10, 1)])
+def test_deblock_baseline_filter(oracle, reference, variant, log2_cu, bd, main_tbl):
+    """Baseline deblocking filter (tool_addb = 0) through the reference's CU walkers vs the oracle, all four strength
+    classes, QP 18..51, chroma QP offsets, 4x4 CUs (order-dependent chroma chains) and 64x64 CUs"""
+    w, h = 192, 136
+    rng = np.random.default_rng(40 + log2_cu + bd)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=31, n_refs=2, coded_frac=0.5, log2_cu=log2_cu,
+                                     bi_frac=0.3, mv_range_px=3)
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    refs = synth.make_refs(w, h, bd, 2, seed=32)
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    # smooth the picture so that edge steps are in the range the filter acts on
+    for pl in base.planes():
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+    synth.randomize_deblock_maps(base, cl, rng)
+    tbl = synth.chroma_qp_table(bool(main_tbl))
+    a = oracle.deblock_frame(prm, base.copy(), cl, tbl)
+    b = reference.deblock_frame(prm, base.copy(), cl, tbl)
+    changed = sum(int((x != y).sum()) for x, y in zip(a.planes(), base.planes()))
+    assert changed > 500, "test picture does not exercise the filter"
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

@@ -75,6 +75,7 @@ class PicInfo(C.Structure):
         ("dev_y", C.c_void_p), ("dev_u", C.c_void_p), ("dev_v", C.c_void_p),
         ("dev_map_mv", C.c_void_p), ("dev_map_refi", C.c_void_p), ("dev_map_scu", C.c_void_p),
         ("w_scu", C.c_int32), ("h_scu", C.c_int32), ("poc", C.c_int32),
+        ("dev_map_edge", C.c_void_p),
     ]
 
 
@@ -113,6 +114,7 @@ _SIGS = {
     "xb200_pic_download": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p, C.c_int] * 3),
     "xb200_pic_download_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_pic_download_edge_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_recon_frame": (
         C.c_int,
         [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
@@ -124,7 +126,8 @@ _SIGS = {
          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int],
     ),
     "xb200_deblock": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
-    "xb200_deblock_dev": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "xb200_set_chroma_qp_table": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xb200_pic_upload_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pad": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xb200_itdq_blocks_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "xb200_mc_blocks_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

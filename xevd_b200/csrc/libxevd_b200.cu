@@ -25,6 +25,7 @@ struct xb200_pic {
     int16_t *map_mv;
     int8_t *map_refi;
     uint32_t *map_scu;
+    uint8_t *map_edge;
 };
 
 struct Staging {                 // one slot of the host->device staging ring
@@ -43,6 +44,7 @@ struct xb200_ctx {
     Staging ring[3];
     int ring_pos;
     int sm_count;
+    int8_t chroma_qp[2][58];     // xevd_qp_chroma_dynamic for the sequence
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
 
@@ -92,6 +94,11 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
+        static const int8_t base[58] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                                        29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41};
+        memcpy(c->chroma_qp[0], base, 58); memcpy(c->chroma_qp[1], base, 58);
+    }
     { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
     {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
         int16_t hl[2][16][8], hc[2][32][4];
@@ -216,7 +223,7 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     const size_t nscu = (size_t)p->w_scu * p->h_scu;
     const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
     const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
-    const size_t total = pix_al + ((nscu * (8 + 4 + 2) + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
+    const size_t total = pix_al + ((nscu * (8 + 4 + 2 + 1) + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
     if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
         delete p;
@@ -231,7 +238,8 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     p->map_mv = (int16_t *)m;
     p->map_scu = (uint32_t *)(m + nscu * 8);
     p->map_refi = (int8_t *)(m + nscu * 12);
-    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 14 + 255) & ~(size_t)255));
+    p->map_edge = (uint8_t *)(m + nscu * 14);
+    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 15 + 255) & ~(size_t)255));
     if (make_tensor_maps(c, p) != XB200_OK) {
         cudaFree(p->buf);
         delete p;
@@ -257,7 +265,7 @@ int xb200_pic_info(xb200_pic *p, XB200_PIC_INFO *i)
     i->s_l = p->s_l; i->s_c = p->s_c; i->pad_l = p->pad_l; i->pad_c = p->pad_c;
     i->dev_y = p->y; i->dev_u = p->u; i->dev_v = p->v;
     i->dev_map_mv = p->map_mv; i->dev_map_refi = p->map_refi; i->dev_map_scu = p->map_scu;
-    i->w_scu = p->w_scu; i->h_scu = p->h_scu; i->poc = p->poc;
+    i->w_scu = p->w_scu; i->h_scu = p->h_scu; i->poc = p->poc; i->dev_map_edge = p->map_edge;
     return XB200_OK;
 }
 
@@ -305,6 +313,14 @@ int xb200_pic_download_maps(xb200_ctx *c, xb200_pic *p, int16_t *map_mv, int8_t 
     return XB200_OK;
 }
 
+int xb200_pic_download_edge_map(xb200_ctx *c, xb200_pic *p, uint8_t *map_edge)
+{
+    if (!c || !p || !map_edge) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpyAsync(map_edge, p->map_edge, (size_t)p->w_scu * p->h_scu, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
 // ---- reconstruction ------------------------------------------------------------------------------------------------
 static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
                      XbFrameArgs &a)
@@ -334,7 +350,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.n_ctu = a.w_ctu * ((cur->h + (1 << a.log2_ctu) - 1) >> a.log2_ctu);
     a.main_tables = prm->tool_admvp ? 1 : 0;
     a.iqt = prm->tool_iqt ? 1 : 0;
-    a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu;
+    a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     return XB200_OK;
 }
@@ -419,7 +435,14 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         return cudaMemcpyAsync(dp + off, src, bytes, cudaMemcpyHostToDevice, c->stream);
     };
     int has_intra = 0, max_cu = 0, any_l1 = 0;
-    for (int i = 0; i < n_cu; i++) { has_intra |= (cus[i].mode == XB200_MODE_INTRA); any_l1 |= (cus[i].mode != XB200_MODE_INTRA && cus[i].refi[1] >= 0); }
+    for (int i = 0; i < n_cu; i++) {
+        const bool intra = cus[i].mode == XB200_MODE_INTRA;
+        has_intra |= intra;
+        if (intra) continue;
+        any_l1 |= cus[i].refi[1] >= 0;
+        // a reference index outside the lists the caller supplied would dereference a missing picture on the device
+        if (cus[i].refi[0] >= n0 || cus[i].refi[1] >= n1 || (cus[i].refi[0] < 0 && cus[i].refi[1] < 0)) return XB200_ERR_INVALID_ARGUMENT;
+    }
     if (!any_l1) n1 = 0;          // P picture: no CU predicts from list 1 (selects the single-list kernel)
     for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
     CK(c, h2d(0, cus, (size_t)n_cu * sizeof(XB200_CU)));
@@ -444,20 +467,51 @@ int xb200_pad(xb200_ctx *c, xb200_pic *p)
     return XB200_OK;
 }
 
-int xb200_deblock_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0,
-                      xb200_pic *const *l1, int n1, const void *d_edge_flags)
+int xb200_set_chroma_qp_table(xb200_ctx *c, const int32_t *tbl)
 {
-    (void)prm; (void)cur; (void)l0; (void)n0; (void)l1; (void)n1; (void)d_edge_flags;
-    if (!c) return XB200_ERR_INVALID_ARGUMENT;
-    return XB200_ERR_UNSUPPORTED;
+    if (!c || !tbl) return XB200_ERR_INVALID_ARGUMENT;
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < 58; i++) {
+            if (tbl[k * 58 + i] < -128 || tbl[k * 58 + i] > 127) return XB200_ERR_INVALID_ARGUMENT;
+            c->chroma_qp[k][i] = (int8_t)tbl[k * 58 + i];
+        }
+    return XB200_OK;
+}
+
+int xb200_pic_upload_maps(xb200_ctx *c, xb200_pic *p, const int16_t *map_mv, const int8_t *map_refi, const uint32_t *map_scu, const uint8_t *map_edge)
+{
+    if (!c || !p) return XB200_ERR_INVALID_ARGUMENT;
+    const size_t n = (size_t)p->w_scu * p->h_scu;
+    if (map_mv) CK(c, cudaMemcpyAsync(p->map_mv, map_mv, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (map_refi) CK(c, cudaMemcpyAsync(p->map_refi, map_refi, n * 2, cudaMemcpyHostToDevice, c->stream));
+    if (map_scu) CK(c, cudaMemcpyAsync(p->map_scu, map_scu, n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (map_edge) CK(c, cudaMemcpyAsync(p->map_edge, map_edge, n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
 }
 
 int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0,
                   xb200_pic *const *l1, int n1, const uint8_t *edge_flags)
 {
-    (void)prm; (void)cur; (void)l0; (void)n0; (void)l1; (void)n1; (void)edge_flags;
-    if (!c) return XB200_ERR_INVALID_ARGUMENT;
-    return XB200_ERR_UNSUPPORTED;
+    (void)l0; (void)n0; (void)l1; (void)n1;
+    if (!c || !prm || !cur) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->chroma_format_idc != 1) return XB200_ERR_UNSUPPORTED;
+    if (prm->tool_addb) return XB200_ERR_UNSUPPORTED;
+    cudaSetDevice(c->device);
+    if (edge_flags) {
+        CK(c, cudaMemcpyAsync(cur->map_edge, edge_flags, (size_t)cur->w_scu * cur->h_scu, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));      // the caller's buffer may be pageable and short-lived
+    }
+    xb::DbkArgs a;
+    a.y = cur->y; a.u = cur->u; a.v = cur->v; a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
+    a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
+    a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma; a.qp_u_offset = prm->qp_u_offset; a.qp_v_offset = prm->qp_v_offset;
+    a.map_scu = cur->map_scu; a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
+    memcpy(a.cq, c->chroma_qp, sizeof(a.cq));
+    xb::launch_deblock(a, c->stream);
+    c->launches += 2;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
 }
 
 // ---- batched leaf kernels ---------------------------------------------------------------------------------------------

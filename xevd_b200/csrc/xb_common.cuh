@@ -38,6 +38,7 @@ struct XbFrameArgs {
     int16_t *map_mv;            // [scu][2][2]
     int8_t *map_refi;           // [scu][2]
     uint32_t *map_scu;
+    uint8_t *map_edge;          // XB200_EDGE_* per SCU: CU boundaries + the 64-sample transform split of larger CUs
     int w_scu, h_scu;
 };
 

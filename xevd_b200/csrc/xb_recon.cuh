@@ -378,6 +378,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         a.map_scu[p] = m;
         ((int2 *)a.map_mv)[p] = make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
         ((int16_t *)a.map_refi)[p] = *(const int16_t *)cu.refi;
+        a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0));
     }
 }
 

@@ -90,7 +90,7 @@ struct R2Layout {
         L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
         L.pre2 = o; o += 2 * (3 * max_cu + 2);
         o = (o + 15) & ~15;
-        const int max_tiles = max_cu < 16 ? 16 : max_cu;
+        const int max_tiles = max_cu + 16;              // a CU larger than 16x16 is several tiles: at most 15 extra per CTU
         L.tiles = o; o += 8 * max_tiles;
         L.preds = o; o += 16 * 2 * max_tiles;
         L.offs = o; o += 4 * 8 * max_cu;                // per-CU exclusive offsets (scan output)
@@ -668,6 +668,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 a.map_scu[p] = m;
                 ((int2 *)a.map_mv)[p] = mv;
                 ((int16_t *)a.map_refi)[p] = rf;
+                a.map_edge[p] = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
             }
     }
 }

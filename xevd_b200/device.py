@@ -66,6 +66,18 @@ class DevicePicture:
                                                     out.map_refi.ctypes.data, out.map_scu.ctypes.data), "xb200_pic_download_maps")
         return out
 
+    def download_edge_map(self) -> np.ndarray:
+        out = np.zeros(((self.w + 3) >> 2) * ((self.h + 3) >> 2), np.uint8)
+        self.ctx._chk(self.ctx.lib.xb200_pic_download_edge_map(self.ctx.handle, self.handle, out.ctypes.data), "xb200_pic_download_edge_map")
+        return out
+
+    def upload_maps(self, pic: HostPicture, edge: np.ndarray | None = None):
+        e = np.ascontiguousarray(edge, np.uint8) if edge is not None else None
+        self.ctx._chk(self.ctx.lib.xb200_pic_upload_maps(self.ctx.handle, self.handle, pic.map_mv.ctypes.data, pic.map_refi.ctypes.data,
+                                                         pic.map_scu.ctypes.data, e.ctypes.data if e is not None else None),
+                      "xb200_pic_upload_maps")
+        return self
+
     def download_padded(self) -> HostPicture:
         out = HostPicture(self.w, self.h, self.poc)
         self.ctx._chk(self.ctx.lib.xb200_pic_download_padded(self.ctx.handle, self.handle, out.buf_y.ctypes.data,
@@ -133,6 +145,16 @@ class Context:
         if not hnd:
             raise XevdB200Error(err.value, "xb200_pic_alloc", (self.lib.xb200_last_error(self.handle) or b"").decode())
         return DevicePicture(self, hnd, w, h)
+
+    def set_chroma_qp_table(self, tbl: np.ndarray):
+        t = np.ascontiguousarray(tbl, np.int32)
+        assert t.shape == (2, 58)
+        self._chk(self.lib.xb200_set_chroma_qp_table(self.handle, t.ctypes.data), "xb200_set_chroma_qp_table")
+
+    def deblock(self, prm: abi.Params, cur: DevicePicture, refs_l0=(), refs_l1=(), edge_flags: np.ndarray | None = None):
+        e = np.ascontiguousarray(edge_flags, np.uint8) if edge_flags is not None else None
+        self._chk(self.lib.xb200_deblock(self.handle, C.byref(prm), cur.handle, _handles(refs_l0), len(refs_l0), _handles(refs_l1),
+                                         len(refs_l1), e.ctypes.data if e is not None else None), "xb200_deblock")
 
     def pad(self, pic: DevicePicture):
         self._chk(self.lib.xb200_pad(self.handle, pic.handle), "xb200_pad")

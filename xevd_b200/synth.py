@@ -181,3 +181,30 @@ def make_refs(w: int, h: int, bit_depth: int, n: int, seed: int = 1):
     rng = np.random.default_rng(seed)
     pocs = [0, 16, 4, 12, 2, 14, 6, 10]
     return [HostPicture.random(w, h, bit_depth, rng, poc=pocs[i % len(pocs)]).pad_borders() for i in range(n)]
+
+
+# default chroma QP mapping tables (xevd_tbl_qp_chroma_adjust_base / _main, src_base/xevd_tbl.c:334-355): what
+# xevd_qp_chroma_dynamic holds when the SPS carries no chroma_qp_table
+CHROMA_QP_BASE = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                           29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41], np.int32)
+CHROMA_QP_MAIN = np.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                           29, 30, 31, 32, 33, 34, 35, 36, 37, 37, 38, 39, 40, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54], np.int32)
+
+
+def chroma_qp_table(main: bool = False) -> np.ndarray:
+    t = CHROMA_QP_MAIN if main else CHROMA_QP_BASE
+    return np.stack([t, t]).copy()
+
+
+def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp_lo=18, qp_hi=51):
+    """give every CU of a reconstructed picture its own QP / intra flag in map_scu (per-CU constant, as the decoder
+    would publish them) so that all four deblocking strength classes and a wide QP range occur"""
+    ws = pic.w_scu
+    for cu in cl.cus:
+        x0, y0 = int(cu["x"]) >> 2, int(cu["y"]) >> 2
+        nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+        qp = int(rng.integers(qp_lo, qp_hi + 1))
+        m = (1 << 31) | (qp << 16) | (int(rng.random() < intra_frac) << 15) | ((int(cu["cbf"]) & 1) << 24)
+        for j in range(nh):
+            pic.map_scu[(y0 + j) * ws + x0:(y0 + j) * ws + x0 + nw] = m
+    return pic
