@@ -71,6 +71,11 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                     const XB200_CU *cus, int n_cu, const XB200_CU_EXT *ext, const int16_t *coef);
 void orc_pad(ORC_PIC *pic);
 
+/* orc_ipred.c */
+void orc_intra_neighbours(const pel *rec, int s, int w, int h, int unit, uint64_t up_mask, uint64_t left_mask, int up_left_avail,
+                          int bit_depth, pel *up, pel *left);
+void orc_ipred_base(const pel *left, const pel *up, pel *dst, int mode, int w, int h);
+
 /* orc_df.c */
 int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl);
 const uint8_t *orc_df_strength_table(void);

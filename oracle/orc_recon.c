@@ -63,6 +63,23 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
 
         if (cu->mode == XB200_MODE_INTER) {
             orc_inter_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, py, pu, pv);
+        } else if (cu->mode == XB200_MODE_INTRA && !prm->tool_eipd) {
+            /* xevd_recon_unit intra branch (src_base/xevd.c:732-741): neighbours from the CURRENT picture, so CUs must be
+             * reconstructed in decoding order; refi[] carries ipm[0..1], mv[1] the index of the availability masks */
+            uint32_t ei;
+            pel nb_up[2 * 128 + 2], nb_le[2 * 128 + 2];
+            memcpy(&ei, cu->mv[1], 4);
+            const XB200_CU_EXT *e = &ext[ei];
+            const int ul = (cu->avail >> 2) & 1;
+            orc_intra_neighbours(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, ul,
+                                 prm->bit_depth_luma, nb_up + 1, nb_le + 1);
+            orc_ipred_base(nb_le + 1, nb_up + 1, py, cu->refi[0], w, h);
+            for (int k = 0; k < 2; k++) {
+                pel *pl = k ? cur->v : cur->u;
+                orc_intra_neighbours(pl + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, cw, ch, 2, e->u.intra.up, e->u.intra.left, ul,
+                                     prm->bit_depth_luma, nb_up + 1, nb_le + 1);
+                orc_ipred_base(nb_le + 1, nb_up + 1, k ? pv : pu, cu->refi[1], cw, ch);
+            }
         } else {
             free(pred); free(res);
             return XB200_ERR_UNSUPPORTED;

@@ -30,6 +30,9 @@
 #include "xevd_recon_sse.h"
 #include "xevd_dbk_sse.h"
 #include "xevd_df.h"
+#include "xevd_ipred.h"
+#include "xevdm_ipred.h"
+#include "xevd_util.h"
 #include "xevdm_df.h"
 #include "../include/xevd_b200.h"
 #include "orc_common.h"
@@ -162,7 +165,7 @@ static void wrap_pic(const ORC_PIC *o, XEVD_PIC *p)
     p->poc = o->poc;
 }
 
-typedef struct { pel pred[REFP_NUM][N_C][MAX_CU_DIM]; s16 coef[N_C][MAX_CU_DIM]; } REF_SCRATCH;
+typedef struct { pel pred[REFP_NUM][N_C][MAX_CU_DIM]; s16 coef[N_C][MAX_CU_DIM]; pel nb[N_C][N_REF][MAX_CU_SIZE * 3]; } REF_SCRATCH;
 
 int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                     const ORC_PIC *const *refs_l0, int n_l0, const ORC_PIC *const *refs_l1, int n_l1,
@@ -178,6 +181,10 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
     memset(refp, 0, sizeof(refp));
     for (i = 0; i < n_l0; i++) { wrap_pic(refs_l0[i], &rp[0][i]); refp[i][REFP_0].pic = &rp[0][i]; refp[i][REFP_0].poc = rp[0][i].poc; }
     for (i = 0; i < n_l1; i++) { wrap_pic(refs_l1[i], &rp[1][i]); refp[i][REFP_1].pic = &rp[1][i]; refp[i][REFP_1].poc = rp[1][i].poc; }
+    /* decoding-order state the intra path reads: COD bits of map_scu (set as each CU is reconstructed), one tile */
+    const int f_scu = cur->w_scu * cur->h_scu;
+    u32 *map_scu = (u32 *)calloc(f_scu, sizeof(u32));
+    u8 *map_tidx = (u8 *)calloc(f_scu, 1);
 
     for (n = 0; n < n_cu; n++) {
         const XB200_CU *cu = &cus[n];
@@ -197,21 +204,34 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         if (cu->cbf)
             xevdm_sub_block_itdq(g_ctx, s->coef, cu->log2w, cu->log2h, cu->qp_y, cu->qp_u, cu->qp_v, is_coef, nnz_sub,
                                  prm->tool_iqt, 0, 0, 0, prm->bit_depth_luma, prm->chroma_format_idc);
-        if (cu->mode != XB200_MODE_INTER) { free(s); return XB200_ERR_UNSUPPORTED; }
-        if (prm->tool_admvp) {
-            select_mc_tables(1);
-        } else {
-            select_mc_tables(0);
-        }
-        /* Baseline xevd_mc (src_base/xevd_mc.c:469); identical to xevdm_mc with DMVR off apart from the table switch */
-        xevd_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, mv, refp, s->pred, prm->poc,
-                prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+        const int scup = (cu->y >> 2) * cur->w_scu + (cu->x >> 2);
+        if (cu->mode == XB200_MODE_INTRA && !prm->tool_eipd) {
+            /* xevd_recon_unit intra branch (src_base/xevd.c:732-741) with the reference's own availability logic */
+            const u16 avail_cu = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
+            const int bdl = prm->bit_depth_luma;
+            xevd_get_nbr_b(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
+                           Y_C, 0, map_tidx, bdl, 1);
+            xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+                           cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
+            xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+                           cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
+            xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
+            xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
+            xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
+        } else if (cu->mode == XB200_MODE_INTER) {
+            select_mc_tables(prm->tool_admvp ? 1 : 0);
+            /* Baseline xevd_mc (src_base/xevd_mc.c:469); identical to xevdm_mc with DMVR off apart from the table switch */
+            xevd_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, mv, refp, s->pred, prm->poc,
+                    prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+        } else { free(s); free(map_scu); free(map_tidx); return XB200_ERR_UNSUPPORTED; }
+        for (l = 0; l < (h >> 2); l++)
+            for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
         /* xevd_recon_yuv (src_base/xevd_recon.c:70-91) */
         g_ctx->fn_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, prm->bit_depth_luma);
         g_ctx->fn_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
         g_ctx->fn_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
     }
-    free(s);
+    free(s); free(map_scu); free(map_tidx);
     return XB200_OK;
 }
 

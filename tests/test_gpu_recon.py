@@ -134,3 +134,44 @@ def test_reference_index_outside_lists_is_rejected(ctx):
     assert e.value.code == abi.XB200_ERR_INVALID_ARGUMENT
     for p in drefs + [cur]:
         p.free()
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,intra_frac", [("B", 4, 10, 1.0), ("A", 2, 10, 1.0), ("B", 4, 8, 0.4), ("A", 6, 10, 1.0), ("A", 3, 10, 0.5)])
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_intra_baseline(oracle, monkeypatch, variant, log2_cu, bd, intra_frac, force):
+    """I pictures and mixed pictures: inter CUs by the parallel kernel, intra CUs by the CTU wavefront kernel"""
+    from xevd_b200.device import Context
+    monkeypatch.setenv("XB200_FORCE_GENERIC", force)
+    c = Context(0)
+    w, h = 200, 136
+    rng = np.random.default_rng(7)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.7, log2_cu=log2_cu)
+    synth.add_intra_cus(cl, rng, intra_frac)
+    refs = synth.make_refs(w, h, bd, 2, seed=82)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [c.pic_alloc(w, h).upload(r) for r in refs]
+    cur = c.pic_alloc(w, h)
+    c.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    c.close()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
+def test_intra_1080p_wavefront(ctx, oracle):
+    """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
+    w, h, bd = 1920, 1080, 10
+    rng = np.random.default_rng(9)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="A", seed=91, n_refs=1, coded_frac=0.5)
+    synth.add_intra_cus(cl, rng, 1.0)
+    refs = synth.make_refs(w, h, bd, 1, seed=92)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs, cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs, cl)
+    got = cur.download()
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"

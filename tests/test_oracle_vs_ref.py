@@ -127,3 +127,19 @@ def test_deblock_baseline_filter(oracle, reference, variant, log2_cu, bd, main_t
     assert changed > 500, "test picture does not exercise the filter"
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,intra_frac", [("B", 4, 10, 1.0), ("A", 2, 10, 1.0), ("B", 4, 8, 0.4), ("A", 6, 10, 1.0), ("A", 3, 10, 0.5)])
+def test_recon_frame_intra_baseline(oracle, reference, variant, log2_cu, bd, intra_frac):
+    """Baseline intra CUs (5 modes, luma + chroma) inside I and mixed pictures.  The reference derives neighbour availability
+    from its own COD bits in decoding order; the oracle consumes the masks synth.add_intra_cus derived - so this also pins the
+    mask derivation."""
+    w, h = 200, 136
+    rng = np.random.default_rng(7)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.7, log2_cu=log2_cu)
+    synth.add_intra_cus(cl, rng, intra_frac)
+    refs = synth.make_refs(w, h, bd, 2, seed=82)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

@@ -13,6 +13,7 @@
 #include "xb_itdq.cuh"
 #include "xb_recon.cuh"
 #include "xb_recon2.cuh"
+#include "xb_intra.cuh"
 #include "xb_filters.cuh"
 #include "xb_micro.cuh"
 
@@ -44,6 +45,8 @@ struct xb200_ctx {
     Staging ring[3];
     int ring_pos;
     int sm_count;
+    int *d_sync;                 // wavefront state of the intra kernel: [0] ticket, [1..] per-CTU done flags
+    int sync_cap;
     int8_t chroma_qp[2][58];     // xevd_qp_chroma_dynamic for the sequence
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
@@ -83,6 +86,7 @@ xb200_ctx *xb200_create(int device, int *err)
     c->launches = 0;
     c->err[0] = 0;
     c->ring_pos = 0;
+    c->d_sync = nullptr; c->sync_cap = 0;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         if (err) *err = XB200_ERR_CUDA;
@@ -92,6 +96,8 @@ xb200_ctx *xb200_create(int device, int *err)
     // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB)
     cudaFuncSetAttribute(xb::k_recon_inter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
     cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
+    cudaFuncSetAttribute(xb::k_recon_intra<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
+    cudaFuncSetAttribute(xb::k_recon_intra<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
@@ -136,6 +142,7 @@ void xb200_destroy(xb200_ctx *c)
         if (s.dev) cudaFree(s.dev);
         if (s.done) cudaEventDestroy(s.done);
     }
+    if (c->d_sync) cudaFree(c->d_sync);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -364,7 +371,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     int r = fill_args(c, prm, cur, l0, n0, l1, n1, a);
     if (r < 0) return r;
     (void)n_ext; (void)n_coef;
-    if (has_intra) return XB200_ERR_UNSUPPORTED;
+    if (has_intra && prm->tool_eipd) return XB200_ERR_UNSUPPORTED;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
@@ -389,6 +396,21 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     }
     c->launches++;
     CK(c, cudaGetLastError());
+    if (has_intra) {
+        // intra CUs: CTU wavefront over the picture the inter kernel just completed
+        if (c->sync_cap < a.n_ctu + 1) {
+            if (c->d_sync) cudaFree(c->d_sync);
+            c->sync_cap = a.n_ctu + 1;
+            CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * c->sync_cap));
+        }
+        CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (a.n_ctu + 1), c->stream));
+        xb::IntraSync sy{c->d_sync, c->d_sync + 1};
+        const size_t sm = xb::IntraSmem::bytes();
+        if (a.iqt) xb::k_recon_intra<true><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        else       xb::k_recon_intra<false><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
     return XB200_OK;
 }
 

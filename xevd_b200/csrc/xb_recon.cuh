@@ -254,7 +254,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
             const int bits = (cu.cbf >> (4 * pl)) & 15;
-            if (!bits) continue;
+            if (!bits || cu.mode == XB200_MODE_INTRA) continue;      // intra CUs belong to the wavefront kernel
             const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
             const int ry = ys - cy_scu;                    // SCU row inside the CU
             const int lhs = min((int)cu.log2h, 6) - 2;     // log2 of the transform-block height in SCUs
@@ -289,7 +289,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
             const int bits = (cu.cbf >> (4 * pl)) & 15;
-            if (!bits) continue;
+            if (!bits || cu.mode == XB200_MODE_INTRA) continue;
             const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
             const int rx = xs - cx_scu;
             const int lws = min((int)cu.log2w, 6) - 2;
@@ -322,6 +322,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     const unsigned ci = sm.cu_of_scu[((t_y >> 2) + sy) * nscu + (t_x >> 2) + sx];
                     if (ci == 0xffff) continue;
                     const XB200_CU cu = cus[ci];
+                    if (cu.mode == XB200_MODE_INTRA) continue;
                     const int cx = cu.x - ctu_x, cy = cu.y - ctu_y;
                     // piece of the CU inside this tile; handled when this SCU is the piece's top-left
                     const int px = max(cx, t_x), py = max(cy, t_y);
@@ -372,12 +373,13 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const XB200_CU cu = cus[ci];
         const int gx = (ctu_x >> 2) + (i % nscu), gy = (ctu_y >> 2) + (i / nscu);
         const int p = gy * a.w_scu + gx;
-        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31);
+        const bool intra = cu.mode == XB200_MODE_INTRA;
+        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u);
         if (cu.cbf & 1) m |= 1u << 24;
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         a.map_scu[p] = m;
-        ((int2 *)a.map_mv)[p] = make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
-        ((int16_t *)a.map_refi)[p] = *(const int16_t *)cu.refi;
+        ((int2 *)a.map_mv)[p] = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        ((int16_t *)a.map_refi)[p] = intra ? (int16_t)-1 : *(const int16_t *)cu.refi;
         a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0));
     }
 }

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .abi import CU_DTYPE, CUF_CHROMA, CUF_LUMA, MODE_INTER, make_params
+from .abi import CU_DTYPE, EXT_DTYPE, CUF_CHROMA, CUF_LUMA, MODE_INTER, MODE_INTRA, make_params
 from .frame import CuList, HostPicture
 
 _DQ_BASE = (40, 45, 51, 57, 64, 71)
@@ -208,3 +208,43 @@ def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp
         for j in range(nh):
             pic.map_scu[(y0 + j) * ws + x0:(y0 + j) * ws + x0 + nw] = m
     return pic
+
+
+def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, constrained: bool = False):
+    """Turn a fraction of the CUs of a picture into intra CUs (Baseline modes 0..4 for luma and chroma) and derive their
+    neighbour-availability masks the way the decoder does: a neighbouring SCU is available when it lies inside the picture
+    and was reconstructed earlier in decoding order (COD bit of map_scu; xevd_get_nbr_b, src_base/xevd_ipred.c:49-91).
+    With `constrained` (pps.constrained_intra_pred_flag) it must also be intra."""
+    cus = cl.cus
+    n = len(cus)
+    w_scu, h_scu = (cl.w + 3) >> 2, (cl.h + 3) >> 2
+    is_intra = rng.random(n) < intra_frac
+    cus["mode"] = np.where(is_intra, MODE_INTRA, MODE_INTER)
+    ipm = rng.integers(0, n_modes, (n, 2)).astype(np.int8)
+    cus["refi"] = np.where(is_intra[:, None], ipm, cus["refi"])
+    cus["mv"][is_intra] = 0
+    ext = [np.zeros(1, EXT_DTYPE)[0]]
+    cod = np.zeros((h_scu, w_scu), bool)
+    intra_map = np.zeros((h_scu, w_scu), bool)
+    for i in range(n):
+        cu = cus[i]
+        xs, ys = int(cu["x"]) >> 2, int(cu["y"]) >> 2
+        nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+        if is_intra[i]:
+            ok = (lambda yy, xx: cod[yy, xx] and (not constrained or intra_map[yy, xx]))
+            up = left = 0
+            for k in range(nw + nh):
+                if ys > 0 and xs + k < w_scu and ok(ys - 1, xs + k):
+                    up |= 1 << k
+                if xs > 0 and ys + k < h_scu and ok(ys + k, xs - 1):
+                    left |= 1 << k
+            ul = int(ys > 0 and xs > 0 and ok(ys - 1, xs - 1))
+            e = np.zeros(1, EXT_DTYPE)[0]
+            e["q"][0], e["q"][1] = up, left
+            cu["avail"] = (int(cu["avail"]) & 3) | (ul << 2)
+            cu["mv"][1] = np.frombuffer(np.uint32(len(ext)).tobytes(), np.int16)
+            ext.append(e)
+        cod[ys:ys + nh, xs:xs + nw] = True
+        intra_map[ys:ys + nh, xs:xs + nw] = is_intra[i]
+    cl.ext = np.array(ext, EXT_DTYPE)
+    return cl
