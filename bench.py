@@ -200,14 +200,11 @@ def run_ours(args):
     from xevd_b200.frame import HostPicture
     from xevd_b200 import synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from xevd_b200 import dist as xdist
+    rank, world, local = xdist.init("nccl")        # GOP-level sharding: one process per GPU, no data-path collective
     dist = None
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
@@ -269,10 +266,7 @@ def run_ours(args):
     launches = ctx.launches - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = xdist.max_over_ranks(ms, dev)
     fps = world * F * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_recon_inter): per-launch CUDA-event timing on the launching stream --------
@@ -349,10 +343,7 @@ def run_ours(args):
         step_e2e()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    t_e2e = xdist.max_over_ranks(t_e2e, dev)
     e2e_fps = world * F * e2e_steps / t_e2e
     # a decoded sample read back on the host proves the D2H happened
     checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())

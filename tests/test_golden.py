@@ -1,0 +1,65 @@
+"""The CPU oracle against the committed golden vectors (tests/golden/*.npz), which are outputs of the unmodified reference
+(dispatched AVX2 code) recorded by tests/golden/make_golden.py.  Runs anywhere: needs neither /root/reference nor a GPU."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from xevd_b200 import synth
+from xevd_b200.frame import HostPicture
+
+G = Path(__file__).resolve().parent / "golden"
+
+
+def test_golden_itdq(oracle):
+    z = np.load(G / "itdq_blocks.npz")
+    n = 0
+    for key in z.files:
+        if not key.startswith("in_"):
+            continue
+        _, iqt, bd, lw, lh = key.split("_")
+        out = oracle.itdq_block(z[key], 32 + 6 * (int(bd) - 8), int(bd), int(iqt))
+        assert np.array_equal(out, z["out" + key[2:]]), key
+        n += 1
+    assert n == 2 * 2 * 36
+
+
+def test_golden_mc(oracle):
+    z = np.load(G / "mc_blocks.npz")
+    for bd in (8, 10):
+        plane = z[f"plane_{bd}"]
+        for t, (w, h, gx, gy, ox, oy, chroma, main) in enumerate(z[f"cases_{bd}"]):
+            got = oracle.mc(plane, (24, 20), (int(gx), int(gy)), (int(ox), int(oy)), int(w), int(h), bd, bool(chroma), bool(main))
+            assert np.array_equal(got, z[f"mc_{bd}_{t}"]), (bd, t)
+
+
+FRAME_CFGS = [("inter_A_10", dict(variant="A", bit_depth=10), 0.0), ("inter_B_8", dict(variant="B", bit_depth=8), 0.0),
+              ("inter_B_10_iqt", dict(variant="B", bit_depth=10, iqt=True), 0.0), ("mixed_B_10", dict(variant="B", bit_depth=10), 0.4),
+              ("intra_A8_10", dict(variant="A", bit_depth=10, log2_cu=3), 1.0)]
+
+
+def golden_frame_inputs(name, kw, intra):
+    """the seeded inputs make_golden.py used"""
+    w, h = 128, 72
+    prm, cl = synth.make_inter_frame(w, h, seed=5, n_refs=2, coded_frac=0.7, **kw)
+    if intra > 0:
+        synth.add_intra_cus(cl, np.random.default_rng(6), intra)
+    refs = synth.make_refs(w, h, kw["bit_depth"], 2, seed=9)
+    return w, h, prm, cl, refs
+
+
+@pytest.mark.parametrize("name,kw,intra", FRAME_CFGS)
+def test_golden_frames(oracle, name, kw, intra):
+    z = np.load(G / "frames.npz")
+    w, h, prm, cl, refs = golden_frame_inputs(name, kw, intra)
+    bd = kw["bit_depth"]
+    pic = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl, k in zip(pic.planes(), "yuv"):
+        assert np.array_equal(pl, z[f"{name}_{k}"]), (name, k)
+    if not kw.get("iqt"):
+        for pl in pic.planes():
+            pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+        synth.randomize_deblock_maps(pic, cl, np.random.default_rng(8))
+        oracle.deblock_frame(prm, pic, cl, synth.chroma_qp_table(False))
+        oracle.pad(pic)
+        assert np.array_equal(pic.buf_y, z[f"{name}_dbk_y"]) and np.array_equal(pic.buf_u, z[f"{name}_dbk_u"]) and np.array_equal(pic.buf_v, z[f"{name}_dbk_v"])

@@ -175,3 +175,31 @@ def test_intra_1080p_wavefront(ctx, oracle):
         p.free()
     for a, b, n in zip(got.planes(), want.planes(), "YUV"):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+def test_golden_frames_gpu(ctx):
+    """the CUDA path against the committed golden vectors of the unmodified reference (tests/golden/frames.npz):
+    recon, then deblocking + padding of the same picture"""
+    from pathlib import Path
+    from tests.test_golden import FRAME_CFGS, golden_frame_inputs
+    z = np.load(Path(__file__).resolve().parent / "golden" / "frames.npz")
+    for name, kw, intra in FRAME_CFGS:
+        w, h, prm, cl, refs = golden_frame_inputs(name, kw, intra)
+        bd = kw["bit_depth"]
+        drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+        cur = ctx.pic_alloc(w, h)
+        ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        got = cur.download(maps=True)
+        for pl, k in zip(got.planes(), "yuv"):
+            assert np.array_equal(pl, z[f"{name}_{k}"]), (name, k)
+        if not kw.get("iqt"):
+            for pl in got.planes():
+                pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+            synth.randomize_deblock_maps(got, cl, np.random.default_rng(8))
+            cur.upload(got, padded=False).upload_maps(got)
+            ctx.deblock(prm, cur)
+            ctx.pad(cur)
+            out = cur.download_padded()
+            assert np.array_equal(out.buf_y, z[f"{name}_dbk_y"]) and np.array_equal(out.buf_u, z[f"{name}_dbk_u"]) and np.array_equal(out.buf_v, z[f"{name}_dbk_v"]), name
+        for p in drefs + [cur]:
+            p.free()

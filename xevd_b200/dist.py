@@ -1,0 +1,74 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for rendezvous / barrier / reductions.
+
+Frames of one EVC stream shard across GPUs only at closed-GOP (IDR) boundaries: an IDR flushes the DPB
+(picman_flush_pb, src_base/xevd_picman.c:112-156) and restarts POC, so GOPs are independent units.  Ranks therefore
+decode disjoint GOPs with no data-path collective; the only communication is the barrier around a timed region, the
+max-over-ranks of the elapsed time, and (for a consumer that wants one ordered stream) gathering decoded pictures or
+their digests in display order on rank 0.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, List, Sequence
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def gop_shards(n_gops: int, world: int) -> List[List[int]]:
+    """round-robin assignment of GOP indices to ranks (keeps every rank busy from the first GOP on)"""
+    return [list(range(r, n_gops, world)) for r in range(world)]
+
+
+def my_gops(n_gops: int, rank: int, world: int) -> List[int]:
+    return gop_shards(n_gops, world)[rank]
+
+
+def init(backend: str | None = None, device_index: int | None = None):
+    """initialise torch.distributed from the torchrun environment (no-op for a single process)"""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = env_rank_world()
+    if world == 1 or dist.is_initialized():
+        return rank, world, local
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl":
+        torch.cuda.set_device(local if device_index is None else device_index)
+        kw["device_id"] = torch.device("cuda", local if device_index is None else device_index)
+    dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """the slowest rank defines the time of a step"""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_in_display_order(local: Sequence[tuple], dst: int = 0) -> List[Any] | None:
+    """local: [(gop_index, poc, payload), ...] of this rank.  Returns, on rank dst, every rank's payloads sorted by
+    (gop_index, poc) - the order xevd_pull would have delivered them from a single decoder - and None elsewhere."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [p for _, _, p in sorted(local, key=lambda t: (t[0], t[1]))]
+    rank, world = dist.get_rank(), dist.get_world_size()
+    bucket: List[Any] = [None] * world if rank == dst else None
+    dist.gather_object(list(local), bucket, dst=dst)
+    if rank != dst:
+        return None
+    merged = [item for part in bucket for item in part]
+    return [p for _, _, p in sorted(merged, key=lambda t: (t[0], t[1]))]

@@ -197,12 +197,17 @@ def chroma_qp_table(main: bool = False) -> np.ndarray:
 
 
 def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp_lo=18, qp_hi=51):
-    """give every CU of a reconstructed picture its own QP / intra flag in map_scu (per-CU constant, as the decoder
+    """publish the CUs' motion into map_mv / map_refi (what xevd_set_dec_info leaves there) and give every CU of a reconstructed picture its own QP / intra flag in map_scu (per-CU constant, as the decoder
     would publish them) so that all four deblocking strength classes and a wide QP range occur"""
     ws = pic.w_scu
     for cu in cl.cus:
         x0, y0 = int(cu["x"]) >> 2, int(cu["y"]) >> 2
         nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+        intra = int(cu["mode"]) == MODE_INTRA
+        for j in range(nh):
+            sl = slice((y0 + j) * ws + x0, (y0 + j) * ws + x0 + nw)
+            pic.map_mv[sl] = 0 if intra else cu["mv"]
+            pic.map_refi[sl] = -1 if intra else cu["refi"]
         qp = int(rng.integers(qp_lo, qp_hi + 1))
         m = (1 << 31) | (qp << 16) | (int(rng.random() < intra_frac) << 15) | ((int(cu["cbf"]) & 1) << 24)
         for j in range(nh):
