@@ -79,5 +79,8 @@ void orc_ipred_base(const pel *left, const pel *up, pel *dst, int mode, int w, i
 /* orc_df.c */
 int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl);
 const uint8_t *orc_df_strength_table(void);
+int orc_deblock_frame_addb(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl,
+                           const int *ref_id_l0, const int *ref_id_l1);
+const uint8_t *orc_addb_tables(int which);
 
 #endif

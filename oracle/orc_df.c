@@ -143,3 +143,169 @@ int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     free(c.cod);
     return XB200_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------
+ * Main-profile deblocking (sps->tool_addb == 1): an H.264-style filter.
+ * Restates get_bs (src_main/xevdm_df.c:361-513), deblock_scu_line_luma / _chroma (:584-781) and the CU walkers
+ * deblock_addb_cu_hor / _ver (:835-1135) for one tile / one slice, TREE_LC, no ATS-inter.
+ *   - only edges on the 8x8 luma grid are filtered (:853,1054,1109)
+ *   - bS: 4 intra and the two SCUs in different CTUs, 3 intra or IBC, 2 luma cbf, else 1 / 0 from comparing the reference
+ *     PICTURES (not indices) and the motion vectors
+ *   - QP = (qp_cur + qp_nb + 1) >> 1; alpha/beta/c1 from the tables below (src_main/xevdm_tbl.c:377-388)
+ *   - quirks kept: get_index takes (u8 qp, u8 offset) so negative values wrap before the clip; beta and c1 are u8
+ * ---------------------------------------------------------------------------------------------------------------------- */
+static const uint8_t k_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22, 25, 28, 32, 36, 40, 45,
+                                    50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
+static const uint8_t k_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10,
+                                   11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+static const uint8_t k_clip[52][5] = {
+    {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0},
+    {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0},
+    {0, 0, 0, 0, 0}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 1, 1, 1}, {0, 0, 1, 1, 1}, {0, 1, 1, 1, 1},
+    {0, 1, 1, 1, 1}, {0, 1, 1, 1, 1}, {0, 1, 1, 1, 1}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 2, 3, 3},
+    {0, 1, 2, 3, 3}, {0, 2, 2, 3, 3}, {0, 2, 2, 4, 4}, {0, 2, 3, 4, 4}, {0, 2, 3, 4, 4}, {0, 3, 3, 5, 5}, {0, 3, 4, 6, 6}, {0, 3, 4, 6, 6},
+    {0, 4, 5, 7, 7}, {0, 4, 5, 8, 8}, {0, 4, 6, 9, 9}, {0, 5, 7, 10, 10}, {0, 6, 8, 11, 11}, {0, 6, 8, 13, 13}, {0, 7, 10, 14, 14}, {0, 8, 11, 16, 16},
+    {0, 9, 12, 18, 18}, {0, 10, 13, 20, 20}, {0, 11, 15, 23, 23}, {0, 13, 17, 25, 25}};
+const uint8_t *orc_addb_tables(int which) { return which == 0 ? k_alpha : (which == 1 ? k_beta : &k_clip[0][0]); }
+
+typedef struct {
+    const XB200_PARAMS *prm;
+    ORC_PIC *pic;
+    const int *cq[2];
+    const int *ref_id[2];        /* identity of the picture behind (list, refi) */
+    uint8_t *cod;
+} AddbCtx;
+
+static int addb_index(int qp, int offset) { return orc_clip3(0, 51, (int)(uint8_t)qp + (int)(uint8_t)offset); }
+static int near_mv(const int *a, const int *b) { return abs(a[0] - b[0]) < 4 && abs(a[1] - b[1]) < 4; }
+
+static int addb_bs(const AddbCtx *c, int cur, int nb, int x0, int y0, int x1, int y1)
+{
+    const ORC_PIC *p = c->pic;
+    const uint32_t m0 = p->map_scu[cur], m1 = p->map_scu[nb];
+    const int lg = c->prm->log2_ctu;
+    const int intra = ((m0 >> 15) & 1) || ((m1 >> 15) & 1);
+    if (intra && ((x0 >> lg) != (x1 >> lg) || (y0 >> lg) != (y1 >> lg))) return 4;
+    if (intra) return 3;
+    if (((m0 >> 26) & 1) || ((m1 >> 26) & 1)) return 3;
+    if (((m0 >> 24) & 1) || ((m1 >> 24) & 1)) return 2;
+    const int8_t *r0 = p->map_refi + 2 * cur, *r1 = p->map_refi + 2 * nb;
+    const int16_t *v0 = p->map_mv + 4 * cur, *v1 = p->map_mv + 4 * nb;
+    int pa[2], pb[2], a[2][2], b[2][2];
+    for (int l = 0; l < 2; l++) {
+        pa[l] = r0[l] >= 0 ? c->ref_id[l][r0[l]] : -1;          /* NULL picture */
+        pb[l] = r1[l] >= 0 ? c->ref_id[l][r1[l]] : -1;
+        for (int d = 0; d < 2; d++) { a[l][d] = r0[l] >= 0 ? v0[l * 2 + d] : 0; b[l][d] = r1[l] >= 0 ? v1[l * 2 + d] : 0; }
+    }
+    if ((pa[0] == pb[0] && pa[1] == pb[1]) || (pa[0] == pb[1] && pa[1] == pb[0])) {
+        if (pa[0] == pa[1]) return (near_mv(a[0], b[0]) && near_mv(a[1], b[1]) && near_mv(a[0], b[1]) && near_mv(a[1], b[0])) ? 0 : 1;
+        if (pa[0] == pb[0] && pa[1] == pb[1]) return (near_mv(a[0], b[0]) && near_mv(a[1], b[1])) ? 0 : 1;
+        return (near_mv(a[0], b[1]) && near_mv(a[1], b[0])) ? 0 : 1;
+    }
+    return 1;
+}
+
+/* one line across the edge: q[i] = buf[i*s], p[i] = buf[-(i+1)*s] */
+static void addb_line_luma(pel *buf, int s, int bs, int alpha, int beta, int c1, int bd)
+{
+    int p[4], q[4], po[4], qo[4];
+    const int maxv = (1 << bd) - 1;
+    for (int i = 0; i < 4; i++) { q[i] = buf[i * s]; p[i] = buf[-(i + 1) * s]; po[i] = p[i]; qo[i] = q[i]; }
+    if (!(bs && abs(p[0] - q[0]) < alpha && abs(p[1] - p[0]) < beta && abs(q[1] - q[0]) < beta)) return;
+    const int ap = abs(p[0] - p[2]) < beta, aq = abs(q[0] - q[2]) < beta;
+    if (bs == 4) {
+        const int small = abs(p[0] - q[0]) < ((alpha >> 2) + 2);
+        if (ap && small) {
+            po[0] = (p[2] + 2 * (p[1] + p[0] + q[0]) + q[1] + 4) >> 3;
+            po[1] = (p[2] + p[1] + p[0] + q[0] + 2) >> 2;
+            po[2] = (2 * p[3] + 3 * p[2] + p[1] + p[0] + q[0] + 4) >> 3;
+        } else po[0] = (2 * p[1] + p[0] + q[1] + 2) >> 2;
+        if (aq && small) {
+            qo[0] = (q[2] + 2 * (q[1] + q[0] + p[0]) + p[1] + 4) >> 3;
+            qo[1] = (q[2] + q[1] + q[0] + p[0] + 2) >> 2;
+            qo[2] = (2 * q[3] + 3 * q[2] + q[1] + q[0] + p[0] + 4) >> 3;
+        } else qo[0] = (2 * q[1] + q[0] + p[1] + 2) >> 2;
+    } else {
+        const int c0 = (uint8_t)(c1 + ((ap + aq) << orc_max(0, bd - 9)));
+        const int d0 = orc_clip3(-c0, c0, (4 * (q[0] - p[0]) + p[1] - q[1] + 4) >> 3);
+        po[0] = orc_clip3(0, maxv, p[0] + d0);
+        qo[0] = orc_clip3(0, maxv, q[0] - d0);
+        if (ap) po[1] = (int16_t)(p[1] + orc_clip3(-c1, c1, (((p[2] + p[0] + q[0]) * 3) - 8 * p[1] - q[1]) >> 4));
+        if (aq) qo[1] = (int16_t)(q[1] + orc_clip3(-c1, c1, (((q[2] + q[0] + p[0]) * 3) - 8 * q[1] - p[1]) >> 4));
+    }
+    for (int i = 0; i < 4; i++) { buf[i * s] = (pel)orc_clip3(0, maxv, qo[i]); buf[-(i + 1) * s] = (pel)orc_clip3(0, maxv, po[i]); }
+}
+static void addb_line_chroma(pel *buf, int s, int bs, int alpha, int beta, int c0, int bd)
+{
+    int p[2], q[2], po[2], qo[2];
+    const int maxv = (1 << bd) - 1;
+    for (int i = 0; i < 2; i++) { q[i] = buf[i * s]; p[i] = buf[-(i + 1) * s]; po[i] = p[i]; qo[i] = q[i]; }
+    if (!(bs && abs(p[0] - q[0]) < alpha && abs(p[1] - p[0]) < beta && abs(q[1] - q[0]) < beta)) return;
+    if (bs == 4) {
+        po[0] = (2 * p[1] + p[0] + q[1] + 2) >> 2;
+        qo[0] = (2 * q[1] + q[0] + p[1] + 2) >> 2;
+    } else {
+        const int d0 = orc_clip3(-c0, c0, (4 * (q[0] - p[0]) + p[1] - q[1] + 4) >> 3);
+        po[0] = orc_clip3(0, maxv, p[0] + d0);
+        qo[0] = orc_clip3(0, maxv, q[0] - d0);
+    }
+    for (int i = 0; i < 2; i++) { buf[i * s] = (pel)orc_clip3(0, maxv, qo[i]); buf[-(i + 1) * s] = (pel)orc_clip3(0, maxv, po[i]); }
+}
+
+static void addb_segment(AddbCtx *c, int cur, int nb, int x, int y, int vertical)
+{
+    ORC_PIC *p = c->pic;
+    const XB200_PARAMS *prm = c->prm;
+    const int bdl = prm->bit_depth_luma, bdc = prm->bit_depth_chroma, scale = bdl - 8;
+    const int bs = addb_bs(c, cur, nb, x, y, vertical ? x - 1 : x, vertical ? y : y - 1);
+    const int qp = (((p->map_scu[cur] >> 16) & 0x7f) + ((p->map_scu[nb] >> 16) & 0x7f) + 1) >> 1;
+    int ia = addb_index(qp, prm->deblock_alpha_offset), ib = addb_index(qp, prm->deblock_beta_offset);
+    int alpha = (uint16_t)(k_alpha[ia] << scale), beta = (uint8_t)(k_beta[ib] << scale);
+    int c1 = (uint8_t)(k_clip[ia][bs] << orc_max(0, bdl - 9));
+    pel *q = p->y + y * p->s_l + x;
+    for (int i = 0; i < 4; i++) vertical ? addb_line_luma(q + i * p->s_l, 1, bs, alpha, beta, c1, bdl) : addb_line_luma(q + i, p->s_l, bs, alpha, beta, c1, bdl);
+    for (int k = 0; k < 2; k++) {
+        const int qc = orc_clip3(-6 * (bdc - 8), 57, qp + (k ? prm->qp_v_offset : prm->qp_u_offset));
+        const int qm = qc < 0 ? qc : c->cq[k][qc];
+        ia = addb_index(qm, prm->deblock_alpha_offset); ib = addb_index(qm, prm->deblock_beta_offset);
+        alpha = (uint16_t)(k_alpha[ia] << scale); beta = (uint8_t)(k_beta[ib] << scale);
+        const int c0 = (uint8_t)((k_clip[ia][bs] + 1) << orc_max(0, bdc - 9));
+        pel *qq = (k ? p->v : p->u) + (y >> 1) * p->s_c + (x >> 1);
+        for (int i = 0; i < 2; i++) vertical ? addb_line_chroma(qq + i * p->s_c, 1, bs, alpha, beta, c0, bdc) : addb_line_chroma(qq + i, p->s_c, bs, alpha, beta, c0, bdc);
+    }
+}
+
+static void addb_visit(AddbCtx *c, int x, int y, int w, int h, int pass)
+{
+    ORC_PIC *p = c->pic;
+    const int ws = p->w_scu, sx = x >> 2, sy = y >> 2, nw = w >> 2, nh = h >> 2;
+    const int t = sy * ws + sx;
+    if (pass == 0) {
+        if ((x & 7) == 0 && x > 0 && c->cod[t - 1])
+            for (int i = 0; i < nh; i++) addb_segment(c, t + i * ws, t + i * ws - 1, x, y + 4 * i, 1);
+        if (((x + w) & 7) == 0 && x + w < p->w_l && c->cod[t + nw])
+            for (int i = 0; i < nh; i++) addb_segment(c, t + i * ws + nw, t + i * ws + nw - 1, x + w, y + 4 * i, 1);
+    } else if ((y & 7) == 0 && y > 0) {
+        for (int i = 0; i < nw; i++) addb_segment(c, t + i, t + i - ws, x + 4 * i, y, 0);
+    }
+    for (int j = 0; j < nh; j++) memset(c->cod + t + j * ws, 1, nw);
+}
+
+int orc_deblock_frame_addb(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl,
+                           const int *ref_id_l0, const int *ref_id_l1)
+{
+    AddbCtx c;
+    c.prm = prm; c.pic = pic; c.cq[0] = chroma_qp_tbl; c.cq[1] = chroma_qp_tbl + 58; c.ref_id[0] = ref_id_l0; c.ref_id[1] = ref_id_l1;
+    c.cod = (uint8_t *)malloc((size_t)pic->w_scu * pic->h_scu);
+    for (int pass = 0; pass < 2; pass++) {
+        memset(c.cod, 0, (size_t)pic->w_scu * pic->h_scu);
+        for (int n = 0; n < n_cu; n++) {
+            const int w = 1 << cus[n].log2w, h = 1 << cus[n].log2h;
+            if (pass == 0 && w > 64) { addb_visit(&c, cus[n].x, cus[n].y, w >> 1, h, pass); addb_visit(&c, cus[n].x + 64, cus[n].y, w >> 1, h, pass); }
+            else if (pass == 1 && h > 64) { addb_visit(&c, cus[n].x, cus[n].y, w, h >> 1, pass); addb_visit(&c, cus[n].x, cus[n].y + 64, w, h >> 1, pass); }
+            else addb_visit(&c, cus[n].x, cus[n].y, w, h, pass);
+        }
+    }
+    free(c.cod);
+    return XB200_OK;
+}

@@ -130,19 +130,28 @@ class _Backend:
             raise RuntimeError(f"{self.prefix}recon_frame failed: {r}")
         return cur
 
-    def deblock_frame(self, prm: Params, pic: HostPicture, cl: CuList, chroma_qp_tbl: np.ndarray, tool_addb: bool = False):
-        """both deblocking passes in place on `pic` (uses pic.map_scu / map_mv / map_refi)"""
+    def deblock_frame(self, prm: Params, pic: HostPicture, cl: CuList, chroma_qp_tbl: np.ndarray, tool_addb: bool = False,
+                      ref_ids=((0, 1, 2, 3), (0, 1, 2, 3))):
+        """both deblocking passes in place on `pic` (uses pic.map_scu / map_mv / map_refi).  ref_ids[l][i] identifies the
+        PICTURE behind reference index i of list l (the Main-profile filter compares pictures, not indices)."""
         o = orc_pic(pic)
         cus = np.ascontiguousarray(cl.cus)
         tbl = np.ascontiguousarray(chroma_qp_tbl, np.int32)
         assert tbl.shape == (2, 58)
-        fn = getattr(self.lib, self.prefix + "deblock_frame")
-        fn.restype = C.c_int
+        r0, r1 = np.array(ref_ids[0], np.int32), np.array(ref_ids[1], np.int32)
         if self.prefix == "ref_":
-            fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-            r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data, int(tool_addb))
+            fn = self.lib.ref_deblock_frame
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data, int(tool_addb), r0.ctypes.data, len(r0), r1.ctypes.data, len(r1))
+        elif tool_addb:
+            fn = self.lib.orc_deblock_frame_addb
+            fn.restype = C.c_int
+            fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data, r0.ctypes.data, r1.ctypes.data)
         else:
-            assert not tool_addb
+            fn = self.lib.orc_deblock_frame
+            fn.restype = C.c_int
             fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_int, C.c_void_p]
             r = fn(C.byref(prm), C.byref(o), cus.ctypes.data, len(cus), tbl.ctypes.data)
         if r < 0:

@@ -246,8 +246,11 @@ void ref_pad(ORC_PIC *pic)
  * Mirrors xevdm_deblock + deblock_tree's leaves (src_main/xevdm.c:1935-2103) for one tile / one slice: COD bits cleared,
  * every CU visited in decoding order by xevdm_deblock_cu_ver (pass 1) then xevdm_deblock_cu_hor (pass 2), CUs larger than
  * MAX_TR_SIZE visited as two halves. */
-int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl, int tool_addb)
+int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl, int tool_addb,
+                      const int *ref_id_l0, int n_l0, const int *ref_id_l1, int n_l1)
 {
+    /* get_bs compares XEVD_PIC pointers: pictures with the same id share one dummy XEVD_PIC */
+    static XEVD_PIC dummy[64];
     static XEVD_SPS sps;
     XEVDM_CTX *m = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX));
     XEVD_CTX *ctx = &m->bctx;
@@ -274,6 +277,8 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     ctx->map_cu_mode = (u32 *)calloc(f_scu, sizeof(u32));
     m->map_ats_inter = (u8 *)calloc(f_scu, 1);
     ctx->fn_dbk = g_ctx->fn_dbk; ctx->fn_dbk_chroma = g_ctx->fn_dbk_chroma;
+    for (i = 0; i < n_l0 && ref_id_l0; i++) ctx->refp[i][REFP_0].pic = &dummy[ref_id_l0[i] & 63];
+    for (i = 0; i < n_l1 && ref_id_l1; i++) ctx->refp[i][REFP_1].pic = &dummy[ref_id_l1[i] & 63];
     wrap_pic(pic, &xp);
     xp.pic_qp_u_offset = prm->qp_u_offset; xp.pic_qp_v_offset = prm->qp_v_offset;
     xp.pic_deblock_alpha_offset = prm->deblock_alpha_offset; xp.pic_deblock_beta_offset = prm->deblock_beta_offset;

@@ -88,3 +88,32 @@ def test_edge_map_published_by_recon(oracle, monkeypatch, force):
     edge = cur.download_edge_map()
     assert np.array_equal(edge, cl.edge_flags())
     c.close()
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,aoff,boff", [("B", 4, 10, 0, 0), ("A", 2, 10, 2, -2), ("A", 3, 8, -3, 4), ("B", 4, 8, 6, 6), ("A", 6, 10, 0, 0), ("B", 4, 12, 0, 2)])
+def test_deblock_addb(ctx, oracle, variant, log2_cu, bd, aoff, boff):
+    """Main-profile deblocking (tool_addb) incl. reference-picture aliasing between indices and lists"""
+    w, h = 192, 136
+    rng = np.random.default_rng(140 + log2_cu + bd)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=33, n_refs=3, coded_frac=0.4, log2_cu=log2_cu,
+                                     bi_frac=0.4, mv_range_px=2)
+    prm.tool_addb = 1
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    prm.deblock_alpha_offset, prm.deblock_beta_offset = aoff, boff
+    refs = synth.make_refs(w, h, bd, 3, seed=34)
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    _smooth(base, bd)
+    synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)
+    tbl = synth.chroma_qp_table(True)
+    want = oracle.deblock_frame(prm, base.copy(), cl, tbl, True, ((0, 1, 0), (2, 1, 0)))
+
+    pics = [ctx.pic_alloc(w, h) for _ in range(3)]          # three distinct reference pictures: ids 0, 1, 2
+    d = ctx.pic_alloc(w, h).upload(base, padded=False).upload_maps(base, cl.edge_flags())
+    ctx.set_chroma_qp_table(tbl)
+    ctx.deblock(prm, d, [pics[0], pics[1], pics[0]], [pics[2], pics[1], pics[0]])
+    got = d.download()
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+    for p in pics + [d]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"

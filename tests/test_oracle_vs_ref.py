@@ -143,3 +143,29 @@ def test_recon_frame_intra_baseline(oracle, reference, variant, log2_cu, bd, int
     b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("variant,log2_cu,bd,aoff,boff", [("B", 4, 10, 0, 0), ("A", 2, 10, 2, -2), ("A", 3, 8, -3, 4), ("B", 4, 8, 6, 6), ("A", 6, 10, 0, 0), ("B", 4, 12, 0, 2)])
+def test_deblock_addb(oracle, reference, variant, log2_cu, bd, aoff, boff):
+    """Main-profile deblocking (tool_addb): bS 0..4 incl. the cross-CTU intra case, picture (not index) comparison with two
+    reference indices aliasing one picture, alpha/beta offsets (negative ones wrap in the reference's u8 arguments)"""
+    w, h = 192, 136
+    rng = np.random.default_rng(140 + log2_cu + bd)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=33, n_refs=3, coded_frac=0.4, log2_cu=log2_cu,
+                                     bi_frac=0.4, mv_range_px=2)
+    prm.tool_addb = 1
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    prm.deblock_alpha_offset, prm.deblock_beta_offset = aoff, boff
+    refs = synth.make_refs(w, h, bd, 3, seed=34)
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl in base.planes():
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+    synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)
+    tbl = synth.chroma_qp_table(True)
+    ids = ((0, 1, 0), (2, 1, 0))          # L0 index 2 aliases picture 0; L1 is a permutation
+    a = oracle.deblock_frame(prm, base.copy(), cl, tbl, True, ids)
+    b = reference.deblock_frame(prm, base.copy(), cl, tbl, True, ids)
+    changed = sum(int((x != y).sum()) for x, y in zip(a.planes(), base.planes()))
+    assert changed > 300, "test picture does not exercise the filter"
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

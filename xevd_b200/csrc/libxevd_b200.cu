@@ -515,10 +515,9 @@ int xb200_pic_upload_maps(xb200_ctx *c, xb200_pic *p, const int16_t *map_mv, con
 int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_pic *const *l0, int n0,
                   xb200_pic *const *l1, int n1, const uint8_t *edge_flags)
 {
-    (void)l0; (void)n0; (void)l1; (void)n1;
     if (!c || !prm || !cur) return XB200_ERR_INVALID_ARGUMENT;
     if (prm->chroma_format_idc != 1) return XB200_ERR_UNSUPPORTED;
-    if (prm->tool_addb) return XB200_ERR_UNSUPPORTED;
+    if (n0 < 0 || n1 < 0 || n0 > XB_MAX_REFS || n1 > XB_MAX_REFS) return XB200_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     if (edge_flags) {
         CK(c, cudaMemcpyAsync(cur->map_edge, edge_flags, (size_t)cur->w_scu * cur->h_scu, cudaMemcpyHostToDevice, c->stream));
@@ -530,7 +529,20 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma; a.qp_u_offset = prm->qp_u_offset; a.qp_v_offset = prm->qp_v_offset;
     a.map_scu = cur->map_scu; a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
     memcpy(a.cq, c->chroma_qp, sizeof(a.cq));
-    xb::launch_deblock(a, c->stream);
+    a.alpha_offset = prm->deblock_alpha_offset; a.beta_offset = prm->deblock_beta_offset; a.log2_ctu = prm->log2_ctu;
+    {   // picture identity of every reference index: first position of the same picture in (list 0 ++ list 1)
+        xb200_pic *all[2 * XB_MAX_REFS];
+        int n = 0;
+        for (int l = 0; l < 2; l++)
+            for (int i = 0; i < (l ? n1 : n0); i++) {
+                xb200_pic *p = (l ? l1 : l0) ? (l ? l1 : l0)[i] : nullptr;
+                int id = -1;
+                for (int k = 0; k < n; k++) if (all[k] == p) { id = k; break; }
+                if (id < 0) { all[n] = p; id = n++; }
+                a.ref_id[l][i] = (int8_t)id;
+            }
+    }
+    xb::launch_deblock(a, prm->tool_addb != 0, c->stream);
     c->launches += 2;
     CK(c, cudaGetLastError());
     return XB200_OK;

@@ -71,6 +71,9 @@ struct DbkArgs {
     const int8_t *map_refi;
     const uint8_t *map_edge;
     int8_t cq[2][58];            // chroma QP mapping for qp >= 0 (xevd_qp_chroma_dynamic); identity below 0
+    // Main-profile filter (tool_addb)
+    int alpha_offset, beta_offset, log2_ctu;
+    int8_t ref_id[2][XB_MAX_REFS];   // identity of the PICTURE behind (list, refi): get_bs compares pictures, not indices
 };
 
 __device__ __forceinline__ int dbk_st(int cls, int q)
@@ -213,11 +216,167 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
     }
 }
 
-inline void launch_deblock(const DbkArgs &a, cudaStream_t st)
+// ---- Main-profile deblocking (sps->tool_addb): H.264-style filter on the 8x8 luma grid -------------------------------------
+// Replaces get_bs, deblock_scu_line_luma / _chroma and deblock_addb_cu_hor / _ver (src_main/xevdm_df.c:361-1135) for one tile /
+// one slice, TREE_LC, no ATS-inter.  Edges are 8 luma samples apart and a line touches at most 4 samples per side, so every
+// segment is independent: one thread per 4-line segment, no ordering constraints.
+__constant__ uint8_t c_addb_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22, 25, 28, 32, 36, 40, 45,
+                                         50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
+__constant__ uint8_t c_addb_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10,
+                                        11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+__constant__ uint8_t c_addb_clip[52][5] = {
+    {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0},
+    {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0},
+    {0, 0, 0, 0, 0}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 0, 1, 1}, {0, 0, 1, 1, 1}, {0, 0, 1, 1, 1}, {0, 1, 1, 1, 1},
+    {0, 1, 1, 1, 1}, {0, 1, 1, 1, 1}, {0, 1, 1, 1, 1}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 1, 2, 2}, {0, 1, 2, 3, 3},
+    {0, 1, 2, 3, 3}, {0, 2, 2, 3, 3}, {0, 2, 2, 4, 4}, {0, 2, 3, 4, 4}, {0, 2, 3, 4, 4}, {0, 3, 3, 5, 5}, {0, 3, 4, 6, 6}, {0, 3, 4, 6, 6},
+    {0, 4, 5, 7, 7}, {0, 4, 5, 8, 8}, {0, 4, 6, 9, 9}, {0, 5, 7, 10, 10}, {0, 6, 8, 11, 11}, {0, 6, 8, 13, 13}, {0, 7, 10, 14, 14}, {0, 8, 11, 16, 16},
+    {0, 9, 12, 18, 18}, {0, 10, 13, 20, 20}, {0, 11, 15, 23, 23}, {0, 13, 17, 25, 25}};
+
+__device__ __forceinline__ int addb_index(int qp, int offset) { return xb_clip3(0, 51, (qp & 0xff) + (offset & 0xff)); }   // u8 arguments in the reference
+__device__ __forceinline__ bool addb_near(int ax, int ay, int bx, int by) { return abs(ax - bx) < 4 && abs(ay - by) < 4; }
+
+__device__ __forceinline__ int addb_bs(const DbkArgs &a, int cur, int nb, int x0, int y0, int x1, int y1)
+{
+    const uint32_t m0 = a.map_scu[cur], m1 = a.map_scu[nb];
+    const bool intra = ((m0 | m1) >> 15) & 1;
+    if (intra) return ((x0 >> a.log2_ctu) != (x1 >> a.log2_ctu) || (y0 >> a.log2_ctu) != (y1 >> a.log2_ctu)) ? 4 : 3;
+    if (((m0 | m1) >> 26) & 1) return 3;
+    if (((m0 | m1) >> 24) & 1) return 2;
+    const int16_t r0 = ((const int16_t *)a.map_refi)[cur], r1 = ((const int16_t *)a.map_refi)[nb];
+    const int8_t r00 = (int8_t)(r0 & 0xff), r01 = (int8_t)(r0 >> 8), r10 = (int8_t)(r1 & 0xff), r11 = (int8_t)(r1 >> 8);
+    const int pa0 = r00 >= 0 ? a.ref_id[0][r00] : -1, pa1 = r01 >= 0 ? a.ref_id[1][r01] : -1;
+    const int pb0 = r10 >= 0 ? a.ref_id[0][r10] : -1, pb1 = r11 >= 0 ? a.ref_id[1][r11] : -1;
+    const int2 v0 = ((const int2 *)a.map_mv)[cur], v1 = ((const int2 *)a.map_mv)[nb];
+    int a0x = (int16_t)(v0.x & 0xffff), a0y = v0.x >> 16, a1x = (int16_t)(v0.y & 0xffff), a1y = v0.y >> 16;
+    int b0x = (int16_t)(v1.x & 0xffff), b0y = v1.x >> 16, b1x = (int16_t)(v1.y & 0xffff), b1y = v1.y >> 16;
+    if (r00 < 0) a0x = a0y = 0;
+    if (r01 < 0) a1x = a1y = 0;
+    if (r10 < 0) b0x = b0y = 0;
+    if (r11 < 0) b1x = b1y = 0;
+    const bool same = pa0 == pb0 && pa1 == pb1, cross = pa0 == pb1 && pa1 == pb0;
+    if (!(same || cross)) return 1;
+    const bool s00 = addb_near(a0x, a0y, b0x, b0y), s11 = addb_near(a1x, a1y, b1x, b1y);
+    const bool s01 = addb_near(a0x, a0y, b1x, b1y), s10 = addb_near(a1x, a1y, b0x, b0y);
+    if (pa0 == pa1) return (s00 && s11 && s01 && s10) ? 0 : 1;
+    if (same) return (s00 && s11) ? 0 : 1;
+    return (s01 && s10) ? 0 : 1;
+}
+
+// deblock_scu_line_luma (xevdm_df.c:584-706): p[i] = sample i+1 before the edge, q[i] = sample i after it
+__device__ __forceinline__ void addb_luma(int (&p)[4], int (&q)[4], int bs, int alpha, int beta, int c1, int bd)
+{
+    if (!(bs && abs(p[0] - q[0]) < alpha && abs(p[1] - p[0]) < beta && abs(q[1] - q[0]) < beta)) return;
+    const int maxv = (1 << bd) - 1;
+    const int ap = abs(p[0] - p[2]) < beta, aq = abs(q[0] - q[2]) < beta;
+    int po0 = p[0], po1 = p[1], po2 = p[2], qo0 = q[0], qo1 = q[1], qo2 = q[2];
+    if (bs == 4) {
+        const bool small = abs(p[0] - q[0]) < ((alpha >> 2) + 2);
+        if (ap && small) {
+            po0 = (p[2] + 2 * (p[1] + p[0] + q[0]) + q[1] + 4) >> 3;
+            po1 = (p[2] + p[1] + p[0] + q[0] + 2) >> 2;
+            po2 = (2 * p[3] + 3 * p[2] + p[1] + p[0] + q[0] + 4) >> 3;
+        } else po0 = (2 * p[1] + p[0] + q[1] + 2) >> 2;
+        if (aq && small) {
+            qo0 = (q[2] + 2 * (q[1] + q[0] + p[0]) + p[1] + 4) >> 3;
+            qo1 = (q[2] + q[1] + q[0] + p[0] + 2) >> 2;
+            qo2 = (2 * q[3] + 3 * q[2] + q[1] + q[0] + p[0] + 4) >> 3;
+        } else qo0 = (2 * q[1] + q[0] + p[1] + 2) >> 2;
+    } else {
+        const int c0 = (c1 + ((ap + aq) << max(0, bd - 9))) & 0xff;
+        const int d0 = xb_clip3(-c0, c0, (4 * (q[0] - p[0]) + p[1] - q[1] + 4) >> 3);
+        po0 = xb_clip3(0, maxv, p[0] + d0);
+        qo0 = xb_clip3(0, maxv, q[0] - d0);
+        if (ap) po1 = (int16_t)(p[1] + xb_clip3(-c1, c1, (((p[2] + p[0] + q[0]) * 3) - 8 * p[1] - q[1]) >> 4));
+        if (aq) qo1 = (int16_t)(q[1] + xb_clip3(-c1, c1, (((q[2] + q[0] + p[0]) * 3) - 8 * q[1] - p[1]) >> 4));
+    }
+    p[0] = xb_clip3(0, maxv, po0); p[1] = xb_clip3(0, maxv, po1); p[2] = xb_clip3(0, maxv, po2); p[3] = xb_clip3(0, maxv, p[3]);
+    q[0] = xb_clip3(0, maxv, qo0); q[1] = xb_clip3(0, maxv, qo1); q[2] = xb_clip3(0, maxv, qo2); q[3] = xb_clip3(0, maxv, q[3]);
+}
+__device__ __forceinline__ void addb_chroma(int (&p)[2], int (&q)[2], int bs, int alpha, int beta, int c0, int bd)
+{
+    if (!(bs && abs(p[0] - q[0]) < alpha && abs(p[1] - p[0]) < beta && abs(q[1] - q[0]) < beta)) return;
+    const int maxv = (1 << bd) - 1;
+    int po0, qo0;
+    if (bs == 4) {
+        po0 = (2 * p[1] + p[0] + q[1] + 2) >> 2;
+        qo0 = (2 * q[1] + q[0] + p[1] + 2) >> 2;
+    } else {
+        const int d0 = xb_clip3(-c0, c0, (4 * (q[0] - p[0]) + p[1] - q[1] + 4) >> 3);
+        po0 = p[0] + d0; qo0 = q[0] - d0;
+    }
+    p[0] = xb_clip3(0, maxv, po0); q[0] = xb_clip3(0, maxv, qo0);
+    p[1] = xb_clip3(0, maxv, p[1]); q[1] = xb_clip3(0, maxv, q[1]);
+}
+
+template <bool VERTICAL>
+__global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ DbkArgs a)
+{
+    const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (sx >= a.w_scu || sy >= a.h_scu) return;
+    if (!dbk_has_edge(a, sx, sy, VERTICAL)) return;
+    if ((VERTICAL ? sx : sy) & 1) return;                                   // 8x8 luma grid only
+    const int cur = sy * a.w_scu + sx, nb = VERTICAL ? cur - 1 : cur - a.w_scu;
+    const int x = sx << 2, y = sy << 2;
+    const int bs = addb_bs(a, cur, nb, x, y, VERTICAL ? x - 1 : x, VERTICAL ? y : y - 1);
+    const int qp = (((a.map_scu[cur] >> 16) & 0x7f) + ((a.map_scu[nb] >> 16) & 0x7f) + 1) >> 1;
+    const int scale = a.bd_l - 8;
+    {
+        const int ia = addb_index(qp, a.alpha_offset), ib = addb_index(qp, a.beta_offset);
+        const int alpha = (c_addb_alpha[ia] << scale) & 0xffff, beta = (c_addb_beta[ib] << scale) & 0xff;
+        const int c1 = (c_addb_clip[ia][bs] << max(0, a.bd_l - 9)) & 0xff;
+        pel *base = a.y + (size_t)y * a.s_l + x;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int p[4], q[4];
+            if (VERTICAL) {
+                pel *r = base + (size_t)i * a.s_l;
+                const int2 lo = *(const int2 *)(r - 4), hi = *(const int2 *)r;
+                p[3] = (int16_t)(lo.x & 0xffff); p[2] = lo.x >> 16; p[1] = (int16_t)(lo.y & 0xffff); p[0] = lo.y >> 16;
+                q[0] = (int16_t)(hi.x & 0xffff); q[1] = hi.x >> 16; q[2] = (int16_t)(hi.y & 0xffff); q[3] = hi.y >> 16;
+                addb_luma(p, q, bs, alpha, beta, c1, a.bd_l);
+                *(int2 *)(r - 4) = make_int2((p[3] & 0xffff) | (p[2] << 16), (p[1] & 0xffff) | (p[0] << 16));
+                *(int2 *)r = make_int2((q[0] & 0xffff) | (q[1] << 16), (q[2] & 0xffff) | (q[3] << 16));
+            } else {
+                pel *c = base + i;
+#pragma unroll
+                for (int k = 0; k < 4; k++) { q[k] = c[(ptrdiff_t)k * a.s_l]; p[k] = c[-(ptrdiff_t)(k + 1) * a.s_l]; }
+                addb_luma(p, q, bs, alpha, beta, c1, a.bd_l);
+#pragma unroll
+                for (int k = 0; k < 4; k++) { c[(ptrdiff_t)k * a.s_l] = (pel)q[k]; c[-(ptrdiff_t)(k + 1) * a.s_l] = (pel)p[k]; }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int qc = xb_clip3(-6 * (a.bd_c - 8), 57, qp + (k ? a.qp_v_offset : a.qp_u_offset));
+        const int qm = qc < 0 ? qc : a.cq[k][qc];
+        const int ia = addb_index(qm, a.alpha_offset), ib = addb_index(qm, a.beta_offset);
+        const int alpha = (c_addb_alpha[ia] << scale) & 0xffff, beta = (c_addb_beta[ib] << scale) & 0xff;
+        const int c0 = ((c_addb_clip[ia][bs] + 1) << max(0, a.bd_c - 9)) & 0xff;
+        pel *base = (k ? a.v : a.u) + (size_t)(y >> 1) * a.s_c + (x >> 1);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            int p[2], q[2];
+            const ptrdiff_t st = VERTICAL ? 1 : a.s_c;
+            pel *c = VERTICAL ? base + (size_t)i * a.s_c : base + i;
+            q[0] = c[0]; q[1] = c[st]; p[0] = c[-st]; p[1] = c[-2 * st];
+            addb_chroma(p, q, bs, alpha, beta, c0, a.bd_c);
+            c[0] = (pel)q[0]; c[st] = (pel)q[1]; c[-st] = (pel)p[0]; c[-2 * st] = (pel)p[1];
+        }
+    }
+}
+
+inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
 {
     const dim3 grid((a.w_scu + 31) / 32, (a.h_scu + 7) / 8);
-    k_deblock<true><<<grid, 256, 0, st>>>(a);
-    k_deblock<false><<<grid, 256, 0, st>>>(a);
+    if (addb) {
+        k_deblock_addb<true><<<grid, 256, 0, st>>>(a);
+        k_deblock_addb<false><<<grid, 256, 0, st>>>(a);
+    } else {
+        k_deblock<true><<<grid, 256, 0, st>>>(a);
+        k_deblock<false><<<grid, 256, 0, st>>>(a);
+    }
 }
 
 }  // namespace xb
