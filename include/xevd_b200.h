@@ -225,6 +225,18 @@ int  xb200_set_chroma_qp_table(xb200_ctx *ctx, const int32_t *tbl /* [2][58] */)
 /* test support: overwrite the per-SCU maps of a device picture from host arrays (any pointer may be NULL)   */
 int  xb200_pic_upload_maps(xb200_ctx *ctx, xb200_pic *pic, const int16_t *map_mv, const int8_t *map_refi,
                            const uint32_t *map_scu, const uint8_t *map_edge);
+/* Adaptive loop filter (Main profile, mctx->fn_alf = xevd_alf, src_main/xevdm.c:2105 -> alf_process,
+ * src_main/xevdm_alf.c:1167): what reaches the filter after the APS has been parsed and alf_recon_coef
+ * (src_main/xevdm_alf.c:700-794) has run on the host.                                                     */
+typedef struct XB200_ALF {
+    int16_t coef_luma[25][13];    /* alf->coef_final: 25 classes x 13 coefficients of the 7x7 diamond       */
+    int16_t coef_chroma[7];       /* alf_slice_param.chroma_coef: 5x5 diamond                               */
+    uint8_t enable[3];            /* alf_slice_param.enable_flag[Y, Cb, Cr]                                 */
+    uint8_t reserved;
+} XB200_ALF;
+/* ctb_flag_luma: host array, one byte per CTU (alf_ctb_flag[Y_C]); NULL = every CTU on; luma is filtered
+ * where enable[0] and the CTU flag are both set, chroma wherever enable[c] is set.  In place.              */
+int  xb200_alf(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
 int  xb200_pad(xb200_ctx *ctx, xb200_pic *pic);           /* xevd_picbuf_expand                        */
 
 /* ---- batched leaf kernels (micro-benchmarks, BASELINE.json config 5) ------------------------------ */

@@ -76,6 +76,9 @@ void orc_intra_neighbours(const pel *rec, int s, int w, int h, int unit, uint64_
                           int bit_depth, pel *up, pel *left);
 void orc_ipred_base(const pel *left, const pel *up, pel *dst, int mode, int w, int h);
 
+/* orc_alf.c */
+int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
+
 /* orc_df.c */
 int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl);
 const uint8_t *orc_df_strength_table(void);

@@ -158,6 +158,18 @@ class _Backend:
             raise RuntimeError(f"{self.prefix}deblock_frame failed: {r}")
         return pic
 
+    def alf_frame(self, prm: Params, pic: HostPicture, alf, ctb_flag_luma: np.ndarray | None = None):
+        """adaptive loop filter in place; alf = xevd_b200.abi.AlfParams"""
+        o = orc_pic(pic)
+        fn = getattr(self.lib, self.prefix + "alf_frame")
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(Params), C.POINTER(OrcPic), C.c_void_p, C.c_void_p]
+        f = np.ascontiguousarray(ctb_flag_luma, np.uint8) if ctb_flag_luma is not None else None
+        r = fn(C.byref(prm), C.byref(o), C.addressof(alf), f.ctypes.data if f is not None else None)
+        if r < 0:
+            raise RuntimeError(f"{self.prefix}alf_frame failed: {r}")
+        return pic
+
     def pad(self, pic: HostPicture):
         o = orc_pic(pic)
         getattr(self.lib, self.prefix + "pad")(C.byref(o))

@@ -30,6 +30,7 @@
 #include "xevd_recon_sse.h"
 #include "xevd_dbk_sse.h"
 #include "xevd_df.h"
+#include "xevdm_alf.h"
 #include "xevd_ipred.h"
 #include "xevdm_ipred.h"
 #include "xevd_util.h"
@@ -307,5 +308,56 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
         }
     }
     free(ctx->map_tidx); free(ctx->map_cu_mode); free(m->map_ats_inter); free(map_scu); free(m);
+    return XB200_OK;
+}
+
+/* ---- adaptive loop filter: the reference's own per-tile driver alf_process_tile (src_main/xevdm_alf.c:901) ----------------
+ * with the final coefficients installed directly (alf->coef_final / chroma_coef), one tile covering the picture. */
+int alf_process_tile(void *arg);
+typedef struct { ADAPTIVE_LOOP_FILTER *alf; CODING_STRUCTURE *cs; ALF_SLICE_PARAM *alf_slice_param; int tile_idx; int tsk_num; } REF_ALF_TMP;
+
+int ref_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *ap, const uint8_t *ctb_flag_luma)
+{
+    static XEVD_SPS sps;
+    XEVDM_CTX *m = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX));
+    XEVD_CTX *ctx = &m->bctx;
+    XEVD_PIC xp;
+    CODING_STRUCTURE cs;
+    ALF_SLICE_PARAM *sp = (ALF_SLICE_PARAM *)calloc(1, sizeof(ALF_SLICE_PARAM));
+    ADAPTIVE_LOOP_FILTER *alf;
+    REF_ALF_TMP tmp;
+    const int ctu = 1 << prm->log2_ctu;
+    int i, c;
+    ensure_init();
+    if (!ap->enable[0] && !ap->enable[1] && !ap->enable[2]) { free(m); free(sp); return XB200_OK; }
+    memset(&sps, 0, sizeof(sps));
+    sps.chroma_format_idc = 1;
+    sps.pic_width_in_luma_samples = pic->w_l; sps.pic_height_in_luma_samples = pic->h_l;
+    ctx->sps = &sps;
+    ctx->w = pic->w_l; ctx->h = pic->h_l; ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu;
+    ctx->log2_max_cuwh = prm->log2_ctu; ctx->max_cuwh = ctu;
+    ctx->w_lcu = (pic->w_l + ctu - 1) / ctu; ctx->h_lcu = (pic->h_l + ctu - 1) / ctu; ctx->f_lcu = ctx->w_lcu * ctx->h_lcu;
+    ctx->w_tile = ctx->h_tile = 1;
+    ctx->tile = (XEVD_TILE *)calloc(1, sizeof(XEVD_TILE));
+    ctx->tile[0].ctba_rs_first = 0; ctx->tile[0].w_ctb = ctx->w_lcu; ctx->tile[0].h_ctb = ctx->h_lcu;
+    ctx->pps.loop_filter_across_tiles_enabled_flag = 0;
+    wrap_pic(pic, &xp);
+    cs.ctx = ctx; cs.pic = &xp;
+    alf = new_alf(prm->bit_depth_luma);
+    xevd_alf_create(alf, pic->w_l, pic->h_l, ctu, ctu, 5, 1, prm->bit_depth_luma);
+    for (c = 0; c < 3; c++) sp->enable_flag[c] = ap->enable[c];
+    memcpy(sp->chroma_coef, ap->coef_chroma, sizeof(short) * 7);
+    memcpy(alf->coef_final, ap->coef_luma, sizeof(short) * 25 * 13);
+    sp->alf_ctb_flag = (u8 *)malloc(3 * ctx->f_lcu);
+    for (i = 0; i < ctx->f_lcu; i++) {
+        sp->alf_ctb_flag[i] = (u8)((ap->enable[0] && (!ctb_flag_luma || ctb_flag_luma[i])) ? 1 : 0);
+        sp->alf_ctb_flag[ctx->f_lcu + i] = ap->enable[1];
+        sp->alf_ctb_flag[2 * ctx->f_lcu + i] = ap->enable[2];
+    }
+    for (c = 0; c < 3; c++) alf->ctu_enable_flag[c] = sp->alf_ctb_flag + ctx->f_lcu * c;
+    tmp.alf = alf; tmp.cs = &cs; tmp.alf_slice_param = sp; tmp.tile_idx = 0; tmp.tsk_num = 0;
+    alf_process_tile(&tmp);
+    xevd_alf_destroy(alf); delete_alf(alf);
+    free(sp->alf_ctb_flag); free(sp); free(ctx->tile); free(m);
     return XB200_OK;
 }

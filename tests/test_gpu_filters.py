@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from xevd_b200 import synth
+from xevd_b200 import abi, synth
 from xevd_b200.frame import HostPicture
 
 pytestmark = pytest.mark.gpu
@@ -117,3 +117,29 @@ def test_deblock_addb(ctx, oracle, variant, log2_cu, bd, aoff, boff):
         p.free()
     for a, b, n in zip(got.planes(), want.planes(), "YUV"):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+@pytest.mark.parametrize("w,h,bd,log2_ctu,enable", [(192, 136, 10, 6, (1, 1, 1)), (200, 72, 8, 6, (1, 0, 1)), (128, 128, 10, 5, (1, 1, 0)), (72, 200, 10, 6, (0, 1, 1)),
+                                                    (256, 136, 10, 7, (1, 1, 1)), (1920, 1080, 10, 6, (1, 1, 1))])
+def test_alf(ctx, oracle, w, h, bd, log2_ctu, enable):
+    """adaptive loop filter (xevdm_alf.c) bit-exact: classes, transposes, mirrored picture borders, partial CTUs, CTU flags"""
+    rng = np.random.default_rng(w * 3 + h + bd)
+    p = HostPicture.random(w, h, bd, rng)
+    yy, xx = np.mgrid[0:h, 0:w]
+    p.y[...] = np.clip((p.y.astype(np.int32) >> 3) + ((xx * 3 + yy * 5) % 97) * (1 << (bd - 8)) + ((xx // 8 + yy // 8) % 2) * (40 << (bd - 8)), 0, (1 << bd) - 1).astype(np.int16)
+    prm = abi.make_params(w, h, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+    alf = synth.make_alf_params(rng, enable)
+    n_ctu = ((w + (1 << log2_ctu) - 1) >> log2_ctu) * ((h + (1 << log2_ctu) - 1) >> log2_ctu)
+    flags = (rng.random(n_ctu) < 0.8).astype(np.uint8)
+    want = oracle.alf_frame(prm, p.copy(), alf, flags)
+    d = ctx.pic_alloc(w, h).upload(p, padded=False)
+    ctx.alf(prm, d, alf, flags)
+    got = d.download()
+    for pa, pb, name in zip(got.planes(), want.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()), np.argwhere(pa != pb)[:5])
+    # all CTUs on (NULL flags), twice in a row through the same context (scratch reuse)
+    want2 = oracle.alf_frame(prm, want.copy(), alf, None)
+    ctx.alf(prm, d, alf, None)
+    got2 = d.download()
+    for pa, pb, name in zip(got2.planes(), want2.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

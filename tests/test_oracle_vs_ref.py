@@ -169,3 +169,22 @@ def test_deblock_addb(oracle, reference, variant, log2_cu, bd, aoff, boff):
     assert changed > 300, "test picture does not exercise the filter"
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("w,h,bd,log2_ctu,enable", [(192, 136, 10, 6, (1, 1, 1)), (200, 72, 8, 6, (1, 0, 1)), (128, 128, 10, 5, (1, 1, 0)), (72, 200, 10, 6, (0, 1, 1)), (256, 136, 10, 7, (1, 1, 1))])
+def test_alf(oracle, reference, w, h, bd, log2_ctu, enable):
+    """adaptive loop filter: classification, 7x7 / 5x5 diamonds, mirrored margins at picture edges, partial CTUs, per-CTU flags"""
+    rng = np.random.default_rng(w + h + bd)
+    p = HostPicture.random(w, h, bd, rng)
+    # structured content so that all direction classes occur: gradients + texture
+    yy, xx = np.mgrid[0:h, 0:w]
+    p.y[...] = np.clip((p.y.astype(np.int32) >> 3) + ((xx * 3 + yy * 5) % 97) * (1 << (bd - 8)) + ((xx // 8 + yy // 8) % 2) * (40 << (bd - 8)), 0, (1 << bd) - 1).astype(np.int16)
+    prm = __import__("xevd_b200.abi", fromlist=["make_params"]).make_params(w, h, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+    alf = synth.make_alf_params(rng, enable)
+    n_ctu = ((w + (1 << log2_ctu) - 1) >> log2_ctu) * ((h + (1 << log2_ctu) - 1) >> log2_ctu)
+    flags = (rng.random(n_ctu) < 0.8).astype(np.uint8)
+    a = oracle.alf_frame(prm, p.copy(), alf, flags)
+    b = reference.alf_frame(prm, p.copy(), alf, flags)
+    assert sum(int((x != y).sum()) for x, y in zip(a.planes(), p.planes())) > 1000
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

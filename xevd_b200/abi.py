@@ -66,6 +66,12 @@ class Params(C.Structure):
 assert C.sizeof(Params) == 128
 
 
+class AlfParams(C.Structure):
+    """struct XB200_ALF"""
+
+    _fields_ = [("coef_luma", (C.c_int16 * 13) * 25), ("coef_chroma", C.c_int16 * 7), ("enable", C.c_uint8 * 3), ("reserved", C.c_uint8)]
+
+
 class PicInfo(C.Structure):
     """struct XB200_PIC_INFO"""
 
@@ -129,6 +135,7 @@ _SIGS = {
     "xb200_set_chroma_qp_table": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xb200_pic_upload_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pad": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xb200_alf": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(AlfParams), C.c_void_p]),
     "xb200_itdq_blocks_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "xb200_mc_blocks_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
 }

@@ -16,6 +16,7 @@
 #include "xb_intra.cuh"
 #include "xb_filters.cuh"
 #include "xb_micro.cuh"
+#include "xb_alf.cuh"
 
 struct xb200_pic {
     int w, h, w_c, h_c, s_l, s_c, pad_l, pad_c, w_scu, h_scu, poc;
@@ -48,6 +49,11 @@ struct xb200_ctx {
     int *d_sync;                 // wavefront state of the intra kernel: [0] ticket, [1..] per-CTU done flags
     int sync_cap;
     int8_t chroma_qp[2][58];     // xevd_qp_chroma_dynamic for the sequence
+    pel *alf_copy;               // pre-ALF copy of the picture being filtered
+    size_t alf_cap;
+    uint8_t *alf_flags_pinned, *alf_flags_dev;
+    int alf_flags_cap;
+    cudaEvent_t alf_flags_done;
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
 
@@ -143,6 +149,10 @@ void xb200_destroy(xb200_ctx *c)
         if (s.done) cudaEventDestroy(s.done);
     }
     if (c->d_sync) cudaFree(c->d_sync);
+    if (c->alf_copy) cudaFree(c->alf_copy);
+    if (c->alf_flags_pinned) cudaFreeHost(c->alf_flags_pinned);
+    if (c->alf_flags_dev) cudaFree(c->alf_flags_dev);
+    if (c->alf_flags_done) cudaEventDestroy(c->alf_flags_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -484,6 +494,62 @@ int xb200_pad(xb200_ctx *c, xb200_pic *p)
     if (!c || !p) return XB200_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     xb::launch_pad(p->y, p->s_l, p->w, p->h, p->pad_l, p->u, p->v, p->s_c, p->w_c, p->h_c, p->pad_c, c->stream);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_ALF *alf, const uint8_t *ctb_flag_luma)
+{
+    if (!c || !prm || !p || !alf) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->w != p->w || prm->h != p->h || prm->log2_ctu < 5 || prm->log2_ctu > 7 || prm->bit_depth_luma < 8 || prm->bit_depth_luma > 14) {
+        snprintf(c->err, sizeof(c->err), "xb200_alf: picture %dx%d / params %dx%d, log2_ctu %d, bit depth %d", p->w, p->h, prm->w, prm->h, prm->log2_ctu, prm->bit_depth_luma);
+        return XB200_ERR_INVALID_ARGUMENT;
+    }
+    if (prm->chroma_format_idc != 1) return XB200_ERR_UNSUPPORTED;
+    if (!alf->enable[0] && !alf->enable[1] && !alf->enable[2]) return XB200_OK;   // alf_process :1172
+    cudaSetDevice(c->device);
+    const size_t ny = (size_t)p->s_l * p->h, nc = (size_t)p->s_c * p->h_c;
+    if (c->alf_cap < ny + 2 * nc) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (c->alf_copy) cudaFree(c->alf_copy);
+        c->alf_copy = nullptr; c->alf_cap = 0;
+        CK(c, cudaMalloc(&c->alf_copy, (ny + 2 * nc) * sizeof(pel)));
+        c->alf_cap = ny + 2 * nc;
+    }
+    xb::AlfArgs a;
+    a.sy = c->alf_copy; a.su = c->alf_copy + ny; a.sv = c->alf_copy + ny + nc;
+    a.dy = p->y; a.du = p->u; a.dv = p->v;
+    a.s_l = p->s_l; a.s_c = p->s_c; a.w = p->w; a.h = p->h; a.log2_ctu = prm->log2_ctu; a.bd = prm->bit_depth_luma;
+    a.w_ctu = (p->w + (1 << prm->log2_ctu) - 1) >> prm->log2_ctu;
+    a.ctb_flag = nullptr;
+    memcpy(a.coef_l, alf->coef_luma, sizeof(a.coef_l));
+    memcpy(a.coef_c, alf->coef_chroma, sizeof(a.coef_c));
+    memcpy(a.enable, alf->enable, 3);
+    if (ctb_flag_luma && alf->enable[0]) {
+        const int n = a.w_ctu * ((p->h + (1 << prm->log2_ctu) - 1) >> prm->log2_ctu);
+        if (c->alf_flags_cap < n) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            if (c->alf_flags_pinned) cudaFreeHost(c->alf_flags_pinned);
+            if (c->alf_flags_dev) cudaFree(c->alf_flags_dev);
+            c->alf_flags_pinned = c->alf_flags_dev = nullptr; c->alf_flags_cap = 0;
+            CK(c, cudaMallocHost(&c->alf_flags_pinned, n));
+            CK(c, cudaMalloc(&c->alf_flags_dev, n));
+            if (!c->alf_flags_done) CK(c, cudaEventCreateWithFlags(&c->alf_flags_done, cudaEventDisableTiming));
+            c->alf_flags_cap = n;
+        } else {
+            CK(c, cudaEventSynchronize(c->alf_flags_done));    // previous upload has left the pinned buffer
+        }
+        memcpy(c->alf_flags_pinned, ctb_flag_luma, n);
+        CK(c, cudaMemcpyAsync(c->alf_flags_dev, c->alf_flags_pinned, n, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaEventRecord(c->alf_flags_done, c->stream));
+        a.ctb_flag = c->alf_flags_dev;
+    }
+    if (alf->enable[0]) CK(c, cudaMemcpy2DAsync((void *)a.sy, p->s_l * 2, p->y, p->s_l * 2, p->w * 2, p->h, cudaMemcpyDeviceToDevice, c->stream));
+    if (alf->enable[1]) CK(c, cudaMemcpy2DAsync((void *)a.su, p->s_c * 2, p->u, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToDevice, c->stream));
+    if (alf->enable[2]) CK(c, cudaMemcpy2DAsync((void *)a.sv, p->s_c * 2, p->v, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToDevice, c->stream));
+    const dim3 grid((p->w + xb::kAlfT - 1) / xb::kAlfT, (p->h + xb::kAlfT - 1) / xb::kAlfT);
+    xb::k_alf<<<grid, 256, 0, c->stream>>>(a);
     c->launches++;
     CK(c, cudaGetLastError());
     return XB200_OK;

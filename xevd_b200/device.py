@@ -156,6 +156,11 @@ class Context:
         self._chk(self.lib.xb200_deblock(self.handle, C.byref(prm), cur.handle, _handles(refs_l0), len(refs_l0), _handles(refs_l1),
                                          len(refs_l1), e.ctypes.data if e is not None else None), "xb200_deblock")
 
+    def alf(self, prm: abi.Params, pic: DevicePicture, alf: abi.AlfParams, ctb_flag_luma=None):
+        """mctx->fn_alf (xevd_alf, src_main/xevdm.c:2105): adaptive loop filter in place"""
+        f = np.ascontiguousarray(ctb_flag_luma, np.uint8) if ctb_flag_luma is not None else None
+        self._chk(self.lib.xb200_alf(self.handle, C.byref(prm), pic.handle, C.byref(alf), f.ctypes.data if f is not None else None), "xb200_alf")
+
     def pad(self, pic: DevicePicture):
         self._chk(self.lib.xb200_pad(self.handle, pic.handle), "xb200_pad")
 

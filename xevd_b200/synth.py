@@ -253,3 +253,22 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
         intra_map[ys:ys + nh, xs:xs + nw] = is_intra[i]
     cl.ext = np.array(ext, EXT_DTYPE)
     return cl
+
+
+def make_alf_params(rng, enable=(1, 1, 1)):
+    """random but well-formed ALF filters: every filter sums to 512 (unity gain at shift 9), side taps within the ranges
+    alf_recon_coef enforces (src_main/xevdm_alf.c:751,763)"""
+    from .abi import AlfParams
+    a = AlfParams()
+    for c in range(25):
+        side = rng.integers(-40, 41, 12)
+        for i in range(12):
+            a.coef_luma[c][i] = int(side[i])
+        a.coef_luma[c][12] = int(512 - 2 * side.sum())
+    side = rng.integers(-40, 41, 6)
+    for i in range(6):
+        a.coef_chroma[i] = int(side[i])
+    a.coef_chroma[6] = int(512 - 2 * side.sum())
+    for i in range(3):
+        a.enable[i] = enable[i]
+    return a
