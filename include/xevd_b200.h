@@ -71,6 +71,8 @@ typedef int16_t xb200_pel;           /* pel == s16 always (src_base/xevd_port.h:
  * derivation (src_base/xevd.c:567-730), flattened.  32 bytes, little endian, no pointers.
  * The producer is the host motion-derivation pass or a synthetic generator.
  */
+#define XB200_ATS_INTER_IDX(a)   (((a) >> 2) & 7)
+#define XB200_ATS_INTER_POS(a)   (((a) >> 5) & 1)
 typedef struct XB200_CU {
     uint16_t x, y;            /* luma position of the CU's top-left sample                       */
     uint8_t  log2w, log2h;    /* 2..7                                                            */
@@ -85,7 +87,13 @@ typedef struct XB200_CU {
     int16_t  mv[2][2];        /* inter: final UNCLIPPED motion vectors [list][x,y], quarter-pel
                                  intra / affine: mv[1] holds a uint32 index into the extension
                                  array (XB200_CU_EXT), mv[0] is unused                           */
-    uint8_t  ats;             /* bits 0-1 ats_mode_h/v, bits 2-7 ats_inter_info                  */
+    uint8_t  ats;             /* Main, tool_ats.  bits 0-1: ats_intra mode (ats_intra_mode_h << 1 | ats_intra_mode_v,
+                                 0 = DST-7, 1 = DCT-8), used when flags has XB200_CUF_ATS_INTRA;
+                                 bits 2-4: ats_inter_idx (0 none, 1 vertical half, 2 horizontal half, 3 vertical
+                                 quarter, 4 horizontal quarter), bit 5: ats_inter_pos -- i.e. ats_inter_info =
+                                 idx | pos << 4 of xevdm_def.h:232-236.  With ats_inter_idx != 0 the CU's three
+                                 coefficient blocks hold only the sub-block transform unit (TU-raster, TU size per
+                                 xevdm_get_tu_size, xevdm_util.c:3585-3608)                            */
     uint8_t  avail;           /* avail_lr (bits 0-1) | up-left available (bit 2)                 */
     uint16_t reserved;
     uint32_t coef_off;        /* offset (in int16 units) of this CU's coefficients inside the
@@ -212,6 +220,8 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
 /* edge flags, one byte per SCU */
 #define XB200_EDGE_LEFT   0x01    /* a CU/TU boundary runs along the left side of this SCU           */
 #define XB200_EDGE_TOP    0x02    /* ... along the top side                                          */
+#define XB200_EDGE_ATS    0x04    /* the SCU belongs to an ats_inter CU (mctx->map_ats_inter != 0): raises the Main
+                                     deblocking strength to "coded" (xevdm_df.c:902-906,977-981)            */
 /* Both passes (vertical edges, then horizontal edges) over the whole picture, in place.  The per-SCU maps
  * (map_scu, map_mv, map_refi) and the edge flags are the ones xb200_recon_frame left in `cur`; edge_flags
  * (host, w_scu*h_scu bytes) optionally replaces the device edge map first.  refs_* are only needed by the

@@ -62,6 +62,8 @@ void orc_inter_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const i
 void orc_dequant(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);
 void orc_inv_dct2(int16_t *coef, int log2w, int log2h, int bit_depth, int iqt);
 void orc_itdq_block(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);
+void orc_inv_ats(int16_t *coef, int log2w, int log2h, int bit_depth, int ats_mode);
+void orc_ats_inter_tu(int ats, int log2w, int log2h, int *tlw, int *tlh, int *xoff, int *yoff);
 /* whole-CU residual (xevd_sub_block_itdq / xevdm_sub_block_itdq): coef[c] CU-raster, in place */
 void orc_itdq_cu(const XB200_PARAMS *prm, const XB200_CU *cu, int16_t *cy, int16_t *cu_, int16_t *cv);
 
@@ -75,6 +77,10 @@ void orc_pad(ORC_PIC *pic);
 void orc_intra_neighbours(const pel *rec, int s, int w, int h, int unit, uint64_t up_mask, uint64_t left_mask, int up_left_avail,
                           int bit_depth, pel *up, pel *left);
 void orc_ipred_base(const pel *left, const pel *up, pel *dst, int mode, int w, int h);
+void orc_intra_neighbours_main(const pel *rec, int s, int w, int h, int unit, uint64_t up_mask, uint64_t left_mask, uint64_t right_mask,
+                               int up_left_avail, int bit_depth, pel *up, pel *left, pel *right);
+void orc_ipred_main(const pel *left, const pel *up, const pel *right, int avail_lr, pel *dst, int ipm, int w, int h, int bit_depth);
+void orc_ipred_uv_main(const pel *left, const pel *up, const pel *right, int avail_lr, pel *dst, int ipm_c, int ipm, int w, int h, int bit_depth);
 
 /* orc_alf.c */
 int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);

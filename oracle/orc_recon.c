@@ -9,15 +9,22 @@
 #include <stdlib.h>
 #include "orc_common.h"
 
-static void put_block(pel *rec, int s_rec, const pel *pred, const int16_t *res, int w, int h, int bd)
+/* rec = clip(pred + residual); the residual block is tw x th at (tx, ty) inside the w x h prediction block - the whole block
+ * normally, the sub-block TU for ats_inter CUs (xevdm_recon, src_main/xevdm_recon.c:42-126) */
+static void put_block_tu(pel *rec, int s_rec, const pel *pred, const int16_t *res, int w, int h, int bd, int tx, int ty, int tw, int th)
 {
     const int maxv = (1 << bd) - 1;
     for (int i = 0; i < h; i++)
         for (int j = 0; j < w; j++) {
+            const int in_tu = res && i >= ty && i < ty + th && j >= tx && j < tx + tw;
             /* t0 is an s16 in the reference (xevd_recon.c:40,60): the sum wraps to 16 bits first */
-            int16_t t = (int16_t)((res ? res[i * w + j] : 0) + pred[i * w + j]);
+            int16_t t = (int16_t)((in_tu ? res[(i - ty) * tw + (j - tx)] : 0) + pred[i * w + j]);
             rec[i * s_rec + j] = (pel)orc_clip3(0, maxv, t);
         }
+}
+static void put_block(pel *rec, int s_rec, const pel *pred, const int16_t *res, int w, int h, int bd)
+{
+    put_block_tu(rec, s_rec, pred, res, w, h, bd, 0, 0, w, h);
 }
 
 static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu)
@@ -29,7 +36,14 @@ static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *
             const int p = (y0 + j) * cur->w_scu + x0 + i;
             /* MCU_SET_IF_SN_QP | CBFL | SF | COD (xevd_def.h:372-437); slice number 0 */
             uint32_t m = ((uint32_t)(cu->qp_map & 0x7f) << 16) | ((uint32_t)intra << 15) | (1u << 31);
-            if (cu->cbf & 1) m |= 1u << 24;
+            int cbfl = cu->cbf & 1;
+            if (cbfl && prm->tool_ats && !intra && cu->mode != XB200_MODE_IBC && XB200_ATS_INTER_IDX(cu->ats)) {
+                /* xevdm_set_cu_cbf_flags (src_main/xevdm_util.c:3669-3714): luma cbf only on the SCUs of the sub-block TU */
+                int tlw, tlh, xo, yo;
+                orc_ats_inter_tu(cu->ats, cu->log2w, cu->log2h, &tlw, &tlh, &xo, &yo);
+                cbfl = 4 * i >= xo && 4 * i < xo + (1 << tlw) && 4 * j >= yo && 4 * j < yo + (1 << tlh);
+            }
+            if (cbfl) m |= 1u << 24;
             if (cu->flags & XB200_CUF_SKIP) m |= 1u << 23;
             cur->map_scu[p] = m;
             for (int l = 0; l < 2; l++) {
@@ -55,10 +69,13 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         const int16_t *c = coef + cu->coef_off;
         const int has_y = (cu->cbf & 0x00f) != 0, has_u = (cu->cbf & 0x0f0) != 0, has_v = (cu->cbf & 0xf00) != 0;
 
-        /* plane blocks are padded to multiples of 8 coefficients (include/xevd_b200.h) */
-        if (has_y) { memcpy(ry, c, sizeof(int16_t) * w * h); c += (w * h + 7) & ~7; }
-        if (has_u) { memcpy(ru, c, sizeof(int16_t) * cw * ch); c += (cw * ch + 7) & ~7; }
-        if (has_v) { memcpy(rv, c, sizeof(int16_t) * cw * ch); }
+        /* plane blocks are padded to multiples of 8 coefficients (include/xevd_b200.h); an ats_inter CU carries only its TU */
+        int tlw = cu->log2w, tlh = cu->log2h, txo = 0, tyo = 0;
+        if (prm->tool_ats && cu->mode != XB200_MODE_INTRA && cu->mode != XB200_MODE_IBC) orc_ats_inter_tu(cu->ats, cu->log2w, cu->log2h, &tlw, &tlh, &txo, &tyo);
+        const int tw = 1 << tlw, th = 1 << tlh;
+        if (has_y) { memcpy(ry, c, sizeof(int16_t) * tw * th); c += (tw * th + 7) & ~7; }
+        if (has_u) { memcpy(ru, c, sizeof(int16_t) * (tw * th / 4)); c += (tw * th / 4 + 7) & ~7; }
+        if (has_v) { memcpy(rv, c, sizeof(int16_t) * (tw * th / 4)); }
         orc_itdq_cu(prm, cu, ry, ru, rv);
 
         if (cu->mode == XB200_MODE_INTER) {
@@ -80,14 +97,31 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                                      prm->bit_depth_luma, nb_up + 1, nb_le + 1);
                 orc_ipred_base(nb_le + 1, nb_up + 1, k ? pv : pu, cu->refi[1], cw, ch);
             }
+        } else if (cu->mode == XB200_MODE_INTRA) {
+            /* Main profile, tool_eipd (src_main/xevdm.c:1344-1361): three reference arrays, 33 luma / 5 chroma modes; chroma is
+             * predicted with the CHROMA bit depth, neighbours default to the LUMA depth's mid value (xevdm.c:600-652) */
+            uint32_t ei;
+            pel nb_up[2 * 128 + 2], nb_le[2 * 128 + 2], nb_ri[2 * 128 + 2];
+            memcpy(&ei, cu->mv[1], 4);
+            const XB200_CU_EXT *e = &ext[ei];
+            const int ul = (cu->avail >> 2) & 1, lr = cu->avail & 3;
+            orc_intra_neighbours_main(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, e->u.intra.right, ul,
+                                      prm->bit_depth_luma, nb_up + 1, nb_le + 1, nb_ri + 1);
+            orc_ipred_main(nb_le + 1, nb_up + 1, nb_ri + 1, lr, py, cu->refi[0], w, h, prm->bit_depth_luma);
+            for (int k = 0; k < 2; k++) {
+                pel *pl = k ? cur->v : cur->u;
+                orc_intra_neighbours_main(pl + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, cw, ch, 2, e->u.intra.up, e->u.intra.left,
+                                          e->u.intra.right, ul, prm->bit_depth_luma, nb_up + 1, nb_le + 1, nb_ri + 1);
+                orc_ipred_uv_main(nb_le + 1, nb_up + 1, nb_ri + 1, lr, k ? pv : pu, cu->refi[1], cu->refi[0], cw, ch, prm->bit_depth_chroma);
+            }
         } else {
             free(pred); free(res);
             return XB200_ERR_UNSUPPORTED;
         }
-        put_block(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma);
+        put_block_tu(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma, txo, tyo, tw, th);
         /* the reference passes the LUMA bit depth to all three planes (xevd_recon.c:70-91) */
-        put_block(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma);
-        put_block(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma);
+        put_block_tu(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
+        put_block_tu(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
         publish_maps(prm, cur, cu);
     }
     free(pred); free(res);

@@ -199,12 +199,20 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             is_coef[l] = bits != 0;
             for (i = 0; i < MAX_SUB_TB_NUM; i++) nnz_sub[l][i] = (bits >> i) & 1;
         }
-        if (is_coef[Y_C]) { memcpy(s->coef[Y_C], c, sizeof(s16) * w * h); c += (w * h + 7) & ~7; }
-        if (is_coef[U_C]) { memcpy(s->coef[U_C], c, sizeof(s16) * cw * ch); c += (cw * ch + 7) & ~7; }
-        if (is_coef[V_C]) { memcpy(s->coef[V_C], c, sizeof(s16) * cw * ch); }
+        /* ATS syntax elements as xevdm_itdq_main passes them (src_main/xevdm.c:599-603) */
+        const int ats_on = prm->tool_ats && cu->mode != XB200_MODE_IBC;
+        const u8 ats_intra_cu = (ats_on && cu->mode == XB200_MODE_INTRA && (cu->flags & XB200_CUF_ATS_INTRA)) ? 1 : 0;
+        const u8 ats_mode = ats_intra_cu ? (cu->ats & 3) : 0;
+        const u8 ats_inter_info = (ats_on && cu->mode != XB200_MODE_INTRA) ? get_ats_inter_info(XB200_ATS_INTER_IDX(cu->ats), XB200_ATS_INTER_POS(cu->ats)) : 0;
+        int tlw = cu->log2w, tlh = cu->log2h;
+        if (ats_inter_info) xevdm_get_tu_size(ats_inter_info, cu->log2w, cu->log2h, &tlw, &tlh);
+        const int tn = 1 << (tlw + tlh);
+        if (is_coef[Y_C]) { memcpy(s->coef[Y_C], c, sizeof(s16) * tn); c += (tn + 7) & ~7; }
+        if (is_coef[U_C]) { memcpy(s->coef[U_C], c, sizeof(s16) * (tn / 4)); c += (tn / 4 + 7) & ~7; }
+        if (is_coef[V_C]) { memcpy(s->coef[V_C], c, sizeof(s16) * (tn / 4)); }
         if (cu->cbf)
             xevdm_sub_block_itdq(g_ctx, s->coef, cu->log2w, cu->log2h, cu->qp_y, cu->qp_u, cu->qp_v, is_coef, nnz_sub,
-                                 prm->tool_iqt, 0, 0, 0, prm->bit_depth_luma, prm->chroma_format_idc);
+                                 prm->tool_iqt, ats_intra_cu, ats_mode, ats_inter_info, prm->bit_depth_luma, prm->chroma_format_idc);
         const int scup = (cu->y >> 2) * cur->w_scu + (cu->x >> 2);
         if (cu->mode == XB200_MODE_INTRA && !prm->tool_eipd) {
             /* xevd_recon_unit intra branch (src_base/xevd.c:732-741) with the reference's own availability logic */
@@ -219,6 +227,20 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
             xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
             xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
+        } else if (cu->mode == XB200_MODE_INTRA) {
+            /* Main-profile intra branch of xevd_recon_unit (src_main/xevdm.c:1344-1361) with the reference's own availability logic */
+            const u16 avail_cu = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
+            const u16 avail_lr = xevd_check_nev_avail(cu->x >> 2, cu->y >> 2, w, h, cur->w_scu, cur->h_scu, map_scu, map_tidx);
+            const int bdl = prm->bit_depth_luma, bdc = prm->bit_depth_chroma;
+            xevdm_get_nbr(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
+                          Y_C, 0, map_tidx, bdl, 1);
+            xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+                          cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
+            xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+                          cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
+            xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
+            xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
+            xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
         } else if (cu->mode == XB200_MODE_INTER) {
             select_mc_tables(prm->tool_admvp ? 1 : 0);
             /* Baseline xevd_mc (src_base/xevd_mc.c:469); identical to xevdm_mc with DMVR off apart from the table switch */
@@ -227,6 +249,13 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         } else { free(s); free(map_scu); free(map_tidx); return XB200_ERR_UNSUPPORTED; }
         for (l = 0; l < (h >> 2); l++)
             for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
+        if (prm->tool_ats) {
+            /* Main profile: xevdm_recon_yuv (src_main/xevdm_recon.c:128-151), which places the ats_inter TU */
+            xevdm_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, ats_inter_info, prm->bit_depth_luma);
+            xevdm_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
+            xevdm_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
+            continue;
+        }
         /* xevd_recon_yuv (src_base/xevd_recon.c:70-91) */
         g_ctx->fn_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, prm->bit_depth_luma);
         g_ctx->fn_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);

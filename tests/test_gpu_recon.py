@@ -159,6 +159,55 @@ def test_intra_baseline(oracle, monkeypatch, variant, log2_cu, bd, intra_frac, f
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
 
 
+@pytest.mark.parametrize("kw,bd", [({}, 10), (dict(log2_ctu=7), 10), (dict(log2_ctu=5), 8), (dict(suco=False), 10), (dict(iqt=True), 10)])
+def test_inter_btt(ctx, oracle, kw, bd):
+    """Main-profile partitions: non-square CUs, 32/64/128 CTUs, 128-sample CUs with gated 64x64 transform sub-blocks"""
+    _run(ctx, oracle, 256, 136, bd, "C", seed=31, coded_frac=0.8, **kw)
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac", [("C", {}, 10, 1.0), ("C", dict(log2_ctu=7), 10, 1.0), ("C", dict(log2_ctu=5), 8, 0.5),
+                                                      ("B", {}, 10, 1.0), ("A", dict(log2_cu=2), 10, 1.0), ("C", dict(suco=False), 12, 0.7),
+                                                      ("C", dict(iqt=True), 10, 0.6)])
+def test_intra_eipd(ctx, oracle, variant, kw, bd, intra_frac):
+    """Main-profile intra (tool_eipd): 33 luma / 5 chroma modes, left / up / right reference arrays, every avail_lr case"""
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=21, n_refs=2, coded_frac=0.7, **kw)
+    prm.tool_eipd = 1
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True)
+    refs = synth.make_refs(w, h, bd, 2, seed=9)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac,iqt", [("C", {}, 10, 0.5, 0), ("C", dict(log2_ctu=7), 10, 0.3, 1), ("C", dict(log2_ctu=5), 8, 0.5, 0),
+                                                          ("B", {}, 10, 0.0, 1), ("A", dict(log2_cu=3), 10, 1.0, 0)])
+def test_ats(ctx, oracle, variant, kw, bd, intra_frac, iqt):
+    """Main tool_ats: DST-7 / DCT-8 luma transforms of intra CUs and sub-block transforms (half / quarter TU) of inter CUs"""
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=41, n_refs=2, coded_frac=0.8, ats_inter_frac=0.6, iqt=bool(iqt), **kw)
+    prm.tool_eipd = 1
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True, ats_intra_frac=0.7)
+    refs = synth.make_refs(w, h, bd, 2, seed=9)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
 def test_intra_1080p_wavefront(ctx, oracle):
     """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
     w, h, bd = 1920, 1080, 10

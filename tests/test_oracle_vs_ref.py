@@ -188,3 +188,61 @@ def test_alf(oracle, reference, w, h, bd, log2_ctu, enable):
     assert sum(int((x != y).sum()) for x, y in zip(a.planes(), p.planes())) > 1000
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+MAIN_PART_CASES = [("C", {}, 10), ("C", dict(log2_ctu=7), 10), ("C", dict(log2_ctu=5), 8), ("C", dict(suco=False), 10)]
+
+
+@pytest.mark.parametrize("variant,kw,bd", MAIN_PART_CASES)
+def test_recon_frame_inter_btt(oracle, reference, variant, kw, bd):
+    """Main-profile partitions: non-square CUs (1:2, 1:4), 32/64/128 CTUs, CUs of 128 with 64x64 transform sub-blocks gated by
+    nnz_sub (xevdm_sub_block_itdq, src_main/xevdm_itdq.c:790-887)"""
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=31, n_refs=2, coded_frac=0.8, **kw)
+    cl.validate()
+    refs = synth.make_refs(w, h, bd, 2, seed=32)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac", [("C", {}, 10, 1.0), ("C", dict(log2_ctu=7), 10, 1.0), ("C", dict(log2_ctu=5), 8, 0.5),
+                                                      ("B", {}, 10, 1.0), ("A", dict(log2_cu=2), 10, 1.0), ("C", dict(suco=False), 12, 0.7)])
+def test_recon_frame_intra_eipd(oracle, reference, variant, kw, bd, intra_frac):
+    """Main-profile intra (tool_eipd): xevdm_get_nbr + xevdm_ipred / xevdm_ipred_uv, 33 luma and 5 chroma modes, all four avail_lr
+    cases (right neighbours decoded first under SUCO order).  The reference derives availability and avail_lr from its own COD
+    bits; the oracle consumes the masks of synth.add_intra_cus."""
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=21, n_refs=2, coded_frac=0.7, **kw)
+    prm.tool_eipd = 1
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True)
+    if variant == "C" and kw.get("suco", True):
+        lr = set((cl.cus["avail"][cl.cus["mode"] == 0] & 3).tolist())
+        assert lr == {0, 1, 2, 3}, "test picture does not reach every avail_lr case"
+    refs = synth.make_refs(w, h, bd, 2, seed=9)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+ATS_CASES = [("C", {}, 10, 0.5, 0), ("C", dict(log2_ctu=7), 10, 0.3, 1), ("C", dict(log2_ctu=5), 8, 0.5, 0), ("B", {}, 10, 0.0, 1), ("A", dict(log2_cu=3), 10, 1.0, 0)]
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac,iqt", ATS_CASES)
+def test_recon_frame_ats(oracle, reference, variant, kw, bd, intra_frac, iqt):
+    """Main tool_ats: ats_intra (DST-7 / DCT-8 luma transforms of intra CUs, xevdm_it_MxN_ats_intra) and ats_inter (sub-block
+    transform: half / quarter TU at either side, position-dependent kernels, TU placement by xevdm_recon), combined with both
+    DCT-2 flavours (Baseline and IQT) for the remaining blocks"""
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=41, n_refs=2, coded_frac=0.8, ats_inter_frac=0.6, iqt=bool(iqt), **kw)
+    prm.tool_eipd = 1
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True, ats_intra_frac=0.7)
+    cl.validate()
+    assert (((cl.cus["ats"] >> 2) & 7) != 0).sum() > 10
+    refs = synth.make_refs(w, h, bd, 2, seed=9)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

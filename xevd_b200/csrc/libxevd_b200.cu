@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <new>
 
 #include "xb_common.cuh"
@@ -123,6 +124,25 @@ xb200_ctx *xb200_create(int device, int *err)
         }
         cudaMemcpyToSymbol(xb::c_taps5, t5, sizeof(t5));
         cudaMemcpyToSymbol(xb::c_taps3, t3, sizeof(t3));
+    }
+    {   // inverse DST-7 / DCT-8 kernels for tool_ats: the reference generates them at start-up with double-precision sin / cos
+        // (xevdm_init_multi_tbl / xevd_init_multi_inv_tbl, src_main/xevdm_itdq.c:81-159); same expression here
+        static int16_t m[2][1360];
+        const double PI = 3.14159265358979323846;
+        int off = 0;
+        for (int lg = 2; lg <= 5; lg++) {
+            const int n = 1 << lg;
+            const double sc = sqrt((double)n) * 64.0;
+            for (int k = 0; k < n; k++)
+                for (int j = 0; j < n; j++) {
+                    double v = cos(PI * (k + 0.5) * (j + 0.5) / (n + 0.5)) * sqrt(2.0 / (n + 0.5));
+                    m[0][off + j * n + k] = (int16_t)(sc * v + (v > 0 ? 0.5 : -0.5));
+                    v = sin(PI * (k + 0.5) * (j + 1) / (n + 0.5)) * sqrt(2.0 / (n + 0.5));
+                    m[1][off + j * n + k] = (int16_t)(sc * v + (v > 0 ? 0.5 : -0.5));
+                }
+            off += n * n;
+        }
+        cudaMemcpyToSymbol(xb::g_ats_inv, m, sizeof(m));
     }
     if (getenv("XB200_DEBUG")) {
         for (int nl = 1; nl <= 2; nl++)
@@ -367,6 +387,8 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.n_ctu = a.w_ctu * ((cur->h + (1 << a.log2_ctu) - 1) >> a.log2_ctu);
     a.main_tables = prm->tool_admvp ? 1 : 0;
     a.iqt = prm->tool_iqt ? 1 : 0;
+    a.eipd = prm->tool_eipd ? 1 : 0;
+    a.ats = prm->tool_ats ? 1 : 0;
     a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     return XB200_OK;
@@ -381,7 +403,6 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     int r = fill_args(c, prm, cur, l0, n0, l1, n1, a);
     if (r < 0) return r;
     (void)n_ext; (void)n_coef;
-    if (has_intra && prm->tool_eipd) return XB200_ERR_UNSUPPORTED;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
@@ -390,7 +411,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
-    if (!a.iqt && a.log2_ctu == 6 && !c->force_generic) {
+    if (!a.iqt && !a.ats && a.log2_ctu == 6 && !c->force_generic) {
         // throughput kernel (xb_recon2.cuh): Baseline transform path, 64x64 CTUs
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;

@@ -25,7 +25,7 @@ struct IntraSmem {
     // residual of the current CU, CU-raster: luma up to 128x128, chroma 2 x 64x64
     static constexpr int kResElems = 128 * 128 + 2 * 64 * 64;
     static constexpr int kTmpElems = 64 * 65;          // pass-1 buffer of one transform block
-    static constexpr int kNbElems = 2 * (2 * 128 + 8); // up[-1..w+h), left[-1..w+h)
+    static constexpr int kNbElems = 3 * (2 * 128 + 8); // up[-1..w+h), left[-1..w+h), right[-1..w+h)
     static size_t bytes() { return sizeof(int16_t) * kResElems + sizeof(int) * kTmpElems + sizeof(int16_t) * 3 * kNbElems + 64; }
 };
 
@@ -33,7 +33,7 @@ struct IntraSmem {
 // by the nnz_sub bits; the result lands CU-raster in `res` (stride = plane width)
 template <bool IQT>
 __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int lh, int lmax, int bits, int qp, int bd,
-                                  int16_t *res, int *tmp, int tid, int nthreads)
+                                  int16_t *res, int *tmp, int tid, int nthreads, int ats = -1)
 {
     const int pw = 1 << lw, ph = 1 << lh;
     for (int i = tid; i < pw * ph; i += nthreads) res[i] = 0;
@@ -50,13 +50,15 @@ __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int 
             __syncthreads();
             for (int x = tid; x < w; x += nthreads) {
                 int *dst = tmp + x;
-                itx_line_dyn<IQT>(slh, [&](int k) { return dq.apply(src[k * pw + x]); }, [&](int n, int v) { dst[n * ts] = v; }, sh1);
+                if (ats >= 0) ats_line_dyn(slh, ats & 1, [&](int k) { return dq.apply(src[k * pw + x]); }, [&](int n, int v) { dst[n * ts] = v; }, 7);
+                else itx_line_dyn<IQT>(slh, [&](int k) { return dq.apply(src[k * pw + x]); }, [&](int n, int v) { dst[n * ts] = v; }, sh1);
             }
             __syncthreads();
             for (int y = tid; y < h; y += nthreads) {
                 const int *srow = tmp + y * ts;
                 int16_t *drow = res + ((j << slh) + y) * pw + (i << slw);
-                itx_line_dyn<false>(slw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
+                if (ats >= 0) ats_line_dyn(slw, ats >> 1, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, 20 - bd);
+                else itx_line_dyn<false>(slw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
             }
         }
     __syncthreads();
@@ -114,6 +116,161 @@ __device__ void intra_pred_recon(pel *rec, int s, int w, int h, int lw, int mode
     }
 }
 
+// ---- Main profile (tool_eipd) ------------------------------------------------------------------------------------------
+// xevdm_get_nbr (src_main/xevdm_ipred.c:39-150): unavailable units repeat the last filled sample, scanning away from the
+// corner.  In closed form: the value at unit k is the sample itself when the unit is available, else the last sample of the
+// nearest available unit before it, else the scan's start value.  The corner up[-1] becomes up[0] when the up-left unit is
+// unavailable (the reference's loop over the units left of the corner overwrites it, :85-104).
+struct NbSrc {
+    const pel *rec;
+    int s, w, ush, dflt;
+    unsigned long long um, lm, rm;
+    bool ul;
+    __device__ __forceinline__ int up(int i) const
+    {
+        const int k = i >> ush;
+        if ((um >> k) & 1) return __ldcg(rec - s + i);
+        const unsigned long long m = um & ((1ull << k) - 1);
+        if (m) return __ldcg(rec - s + (((63 - __clzll((long long)m)) + 1) << ush) - 1);
+        return ul ? __ldcg(rec - s - 1) : dflt;
+    }
+    __device__ __forceinline__ int corner() const { return ul ? __ldcg(rec - s - 1) : up(0); }
+    __device__ __forceinline__ int side(int i, unsigned long long mask, int col, int start) const
+    {
+        const int k = i >> ush;
+        if ((mask >> k) & 1) return __ldcg(rec + (ptrdiff_t)i * s + col);
+        const unsigned long long m = mask & ((1ull << k) - 1);
+        if (m) return __ldcg(rec + (ptrdiff_t)((((63 - __clzll((long long)m)) + 1) << ush) - 1) * s + col);
+        return start;
+    }
+};
+
+__device__ void intra_gather_main(const NbSrc &nb, int h, int16_t *up, int16_t *left, int16_t *right, int tid, int nthreads)
+{
+    const int n = nb.w + h;
+    for (int i = tid; i < 3 * n + 3; i += nthreads) {
+        if (i < n) up[i] = (int16_t)nb.up(i);
+        else if (i < 2 * n) left[i - n] = (int16_t)nb.side(i - n, nb.lm, -1, nb.corner());
+        else if (i < 3 * n) right[i - 2 * n] = (int16_t)nb.side(i - 2 * n, nb.rm, nb.w, nb.up(nb.w));
+        else if (i == 3 * n) up[-1] = (int16_t)nb.corner();
+        else if (i == 3 * n + 1) left[-1] = (int16_t)nb.corner();
+        else right[-1] = (int16_t)nb.up(nb.w);
+    }
+}
+
+__constant__ int c_inv_size_plus1[8] = {2048, 1365, 819, 455, 241, 124, 63, 32};          // xevd_ipred.c:108
+__constant__ short c_ipred_dxdy[33][2] = {                                                   // xevd_tbl_ipred_dxdy, xevd_tbl.c:294-304
+    {0, 0}, {0, 0}, {0, 0}, {2816, 372}, {2048, 512}, {1408, 744}, {1024, 1024}, {744, 1408}, {512, 2048}, {372, 2816}, {256, 4096},
+    {128, 8192}, {0, 0}, {128, 8192}, {256, 4096}, {372, 2816}, {512, 2048}, {744, 1408}, {1024, 1024}, {1408, 744}, {2048, 512},
+    {2816, 372}, {4096, 256}, {8192, 128}, {0, 0}, {8192, 128}, {4096, 256}, {2816, 372}, {2048, 512}, {1408, 744}, {1024, 1024},
+    {744, 1408}, {512, 2048}};
+
+// one angular sample: ipred_ang_val (src_base/xevd_ipred.c:377-570); 4-tap filter {32-f, 64-f, 32+f, f}, positions clamped to [-1, w+h-1]
+__device__ __forceinline__ int intra_ang_px(const int16_t *up, const int16_t *le, const int16_t *ri, int lr, int ipm, int i, int j, int w, int h, int maxv)
+{
+    const int mdx = c_ipred_dxdy[ipm][0], mdy = c_ipred_dxdy[ipm][1];
+    const bool right_ok = lr >= 2;
+    const int dxy = (ipm > 24 || ipm < 12) ? -1 : 1;
+    const int16_t *src;
+    int pos, frac, step;
+    auto proj = [&](int m, int d) { const int t = d * m; const int whole = t >> 10; frac = (t >> 5) - (whole << 5); return whole; };
+    if (ipm < 12) {
+        const int t = proj(mdx, j + 1);
+        if (right_ok && i >= w - t) { const int ty = proj(mdy, w - i); src = ri; pos = j - ty; step = dxy > 0 ? 1 : -1; }
+        else { src = up; pos = i + t; step = dxy < 0 ? 1 : -1; }
+    } else if (ipm > 24) {
+        if (right_ok) {
+            const int ty = proj(mdy, w - i);
+            if (j < ty) { const int t = proj(mdx, w - i); src = up; pos = i + t; step = dxy < 0 ? 1 : -1; }
+            else { src = ri; pos = j - ty; step = dxy > 0 ? 1 : -1; }
+        } else { const int ty = proj(mdy, i + 1); src = le; pos = j + ty; step = dxy < 0 ? 1 : -1; }
+    } else {
+        const int ty = proj(mdy, i + 1);
+        if (j < ty) { const int t = proj(mdx, j + 1); src = up; pos = i - t; step = dxy < 0 ? 1 : -1; }
+        else if (lr == 2) { const int ty2 = proj(mdy, w - i); src = ri; pos = j + ty2; step = dxy > 0 ? 1 : -1; }
+        else { src = le; pos = j - ty; step = dxy < 0 ? 1 : -1; }
+    }
+    const int hi = w + h - 1;
+    const int p0 = xb_clip3(-1, hi, pos - step), p1 = xb_clip3(-1, hi, pos), p2 = xb_clip3(-1, hi, pos + step), p3 = xb_clip3(-1, hi, pos + 2 * step);
+    const int v = (int16_t)((src[p0] * (32 - frac) + src[p1] * (64 - frac) + src[p2] * (32 + frac) + src[p3] * frac + 64) >> 7);
+    return xb_clip3(0, maxv, v);
+}
+
+// xevdm_ipred / xevdm_ipred_uv + xevdm_recon for one plane (src_main/xevdm_ipred.c:153-305; shared predictors
+// src_base/xevd_ipred.c:110-372).  ipm: 0 DC, 1 planar, 2 bilinear, 12 vertical, 24 horizontal, others angular.
+// pmax clips the predictor (plane bit depth), rmax the reconstruction (luma bit depth, xevdm_recon.c).
+__device__ void intra_pred_recon_main(pel *rec, int s, int w, int h, int lw, int lh, int ipm, int lr, const int16_t *up, const int16_t *le,
+                                      const int16_t *ri, const int16_t *res, bool coded, int pmax, int rmax, int *scr, int tid, int nthreads)
+{
+    // scalars of the mode (warp 0): scr[0..3]
+    if (ipm <= 2) {
+        if (tid < 32) {
+            if (ipm == 0) {
+                int acc = 0;
+                for (int i = tid; i < w; i += 32) acc += up[i];
+                for (int i = tid; i < h; i += 32) acc += (lr == 3 ? le[i] + ri[i] : (lr == 2 ? ri[i] : le[i]));
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                if (tid == 0) {
+                    const int lhh = lr == 3 ? lh + 1 : lh;
+                    acc += lr == 3 ? (w + h + h) >> 1 : (w + h) >> 1;
+                    scr[0] = (acc * c_inv_size_plus1[lw > lhh ? lw - lhh : lhh - lw]) >> (min(lw, lhh) + 12);
+                }
+            } else if (ipm == 1) {
+                const bool fr = lr >= 2;
+                const int16_t *sd = fr ? ri : le;
+                const int w2 = w >> 1, h2 = h >> 1;
+                int ch = 0, cv = 0;
+                for (int x = 1 + tid; x <= w2; x += 32) ch += fr ? x * (up[w2 - x] - up[w2 + x]) : x * (up[w2 - 1 + x] - up[w2 - 1 - x]);
+                for (int y = 1 + tid; y <= h2; y += 32) cv += y * (sd[h2 - 1 + y] - sd[h2 - 1 - y]);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, d); cv += __shfl_xor_sync(0xffffffffu, cv, d); }
+                if (tid == 0) {
+                    const int mult[6] = {13, 17, 5, 11, 23, 47}, shft[6] = {7, 10, 11, 15, 19, 23};
+                    const int iw = lw < 2 ? 0 : lw - 2, ih = lh < 2 ? 0 : lh - 2;
+                    const int a = (sd[h - 1] + (fr ? up[0] : up[w - 1])) << 4;
+                    const int b = ((ch << 5) * mult[iw] + (1 << (shft[iw] - 1))) >> shft[iw];
+                    const int c = ((cv << 5) * mult[ih] + (1 << (shft[ih] - 1))) >> shft[ih];
+                    scr[0] = a - (h2 - 1) * c - (w2 - 1) * b + 16; scr[1] = b; scr[2] = c;
+                }
+            } else if (tid == 0 && lr != 3) {
+                const int tbl_wc[6] = {-1, 341, 205, 114, 60, 31};
+                const bool fr = lr == 2;
+                const int a = fr ? up[-1] : up[w], b = fr ? ri[h] : le[h];
+                const int lmin = min(lw, lh);
+                const int c = w == h ? (a + b + 1) >> 1 : (((a << lw) + (b << lh)) * tbl_wc[lw > lh ? lw - lh : lh - lw] + (1 << (lmin + 9))) >> (lmin + 10);
+                scr[0] = a; scr[1] = b; scr[2] = (c << 1) - a - b;
+            }
+        }
+        __syncthreads();
+    }
+    const int s0 = scr[0], s1 = scr[1], s2 = scr[2];
+    const int mul_w = c_inv_size_plus1[lw];
+    for (int i = tid; i < w * h; i += nthreads) {
+        const int y = i >> lw, x = i & (w - 1);
+        int p;
+        if (ipm == 12) p = up[x];
+        else if (ipm == 24) p = lr == 3 ? (int16_t)(((le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w) >> 12) : (lr == 2 ? ri[y] : le[y]);
+        else if (ipm == 0) p = s0;
+        else if (ipm == 1) p = xb_clip3(0, pmax, (s0 + y * s2 + (lr >= 2 ? w - 1 - x : x) * s1) >> 5);
+        else if (ipm == 2) {
+            if (lr == 3) {
+                const int hb = (le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w >> 12;
+                const int hl = (le[h - 1] * (w - x) + ri[h - 1] * (x + 1) + (w >> 1)) * mul_w >> 12;
+                const int vb = (up[x] * (h - 1 - y) + hl * (y + 1) + (h >> 1)) >> lh;
+                p = (int16_t)((hb + vb + 1) >> 1);
+            } else {
+                const bool fr = lr == 2;
+                const int sd = fr ? ri[y] : le[y], k = fr ? w - 1 - x : x;
+                const int px = (sd << lw) + (k + 1) * (s0 - sd), py = (up[x] << lh) + (y + 1) * (s1 - up[x]);
+                p = xb_clip3(0, pmax, (int16_t)(((px << lh) + (py << lw) + k * y * s2 + (1 << (lw + lh))) >> (lw + lh + 1)));
+            }
+        } else p = intra_ang_px(up, le, ri, lr, ipm, x, y, w, h, pmax);
+        const int r = coded ? res[i] : 0;
+        rec[(size_t)y * s + x] = (pel)xb_clip3(0, rmax, (int16_t)(p + r));
+    }
+}
+
 struct IntraSync {
     int *ticket;        // next CTU to hand out
     int *done;          // [n_ctu] 1 when every CU of the CTU is final
@@ -127,7 +284,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     int16_t *s_res = (int16_t *)smem_raw;
     int *s_tmp = (int *)(s_res + IntraSmem::kResElems);
     int16_t *s_nb = (int16_t *)(s_tmp + IntraSmem::kTmpElems);
-    __shared__ int s_ctu, s_scratch;
+    __shared__ int s_ctu, s_scratch, s_scr4[4];
     const int tid = threadIdx.x;
 
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
@@ -169,12 +326,34 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 if (!bits) continue;
                 const int lw = cu.log2w - (pl ? 1 : 0), lh = cu.log2h - (pl ? 1 : 0);
                 cu_plane_residual<IQT>(coef, lw, lh, pl ? 5 : 6, bits, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l, res[pl], s_tmp,
-                                       tid, kIntraThreads);
+                                       tid, kIntraThreads, (a.ats && pl == 0 && (cu.flags & XB200_CUF_ATS_INTRA)) ? (cu.ats & 3) : -1);
                 coef += ((1 << (lw + lh)) + 7) & ~7;
             }
             // neighbours of all three planes, then prediction + reconstruction
-            int16_t *up[3], *le[3];
-            for (int pl = 0; pl < 3; pl++) { up[pl] = s_nb + pl * IntraSmem::kNbElems + 4; le[pl] = up[pl] + (2 * 128 + 8); }
+            int16_t *up[3], *le[3], *ri[3];
+            for (int pl = 0; pl < 3; pl++) { up[pl] = s_nb + pl * IntraSmem::kNbElems + 4; le[pl] = up[pl] + (2 * 128 + 8); ri[pl] = le[pl] + (2 * 128 + 8); }
+            if (a.eipd) {
+                const int lr = cu.avail & 3;
+                const int pmax_c = (1 << a.bd_c) - 1;
+                static const int8_t kChromaToLuma[5] = {-1, 2, 0, 24, 12};       // IPD_BI_C, DC_C, HOR_C, VER_C -> luma mode ids (xevdm_ipred.c:267-305)
+                const int ipm_c = cu.refi[1] == 0 ? cu.refi[0] : kChromaToLuma[cu.refi[1]];
+                for (int pl = 0; pl < 3; pl++) {
+                    NbSrc nb;
+                    nb.rec = pl == 0 ? a.cur.y + (size_t)cu.y * a.s_l + cu.x : (pl == 1 ? a.cur.u : a.cur.v) + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1);
+                    nb.s = pl ? a.s_c : a.s_l; nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
+                    nb.um = ex.u.intra.up; nb.lm = ex.u.intra.left; nb.rm = ex.u.intra.right; nb.ul = ul;
+                    intra_gather_main(nb, pl ? ch : h, up[pl], le[pl], ri[pl], tid, kIntraThreads);
+                }
+                __syncthreads();
+                for (int pl = 0; pl < 3; pl++) {
+                    pel *rec = pl == 0 ? a.cur.y + (size_t)cu.y * a.s_l + cu.x : (pl == 1 ? a.cur.u : a.cur.v) + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1);
+                    intra_pred_recon_main(rec, pl ? a.s_c : a.s_l, pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0),
+                                          pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl], res[pl], ((cu.cbf >> (4 * pl)) & 15) != 0,
+                                          pl ? pmax_c : maxv, maxv, s_scr4, tid, kIntraThreads);
+                    __syncthreads();
+                }
+                continue;
+            }
             intra_gather(a.cur.y + (size_t)cu.y * a.s_l + cu.x, a.s_l, w, h, 4, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[0], le[0], tid, kIntraThreads);
             intra_gather(a.cur.u + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[1], le[1],
                          tid, kIntraThreads);

@@ -85,6 +85,41 @@ __device__ __forceinline__ void itx_line(LoadFn load, StoreFn store, int shift)
     }
 }
 
+// ---- ATS (Main, tool_ats): inverse DST-7 / DCT-8, full matrix product per line --------------------------------------------
+// xevdm_itrans_ats_intra_{DST7,DCT8}_B{4,8,16,32} (src_main/xevdm_itdq.c:163-402): out[n] = clip16((sum_k inv[n][k] in[k] + rnd) >> shift).
+// The matrices are generated on the host with the reference's own double-precision expression (xevdm_itdq.c:81-159)
+// at context creation and uploaded here: [type 0 = DCT-8, 1 = DST-7][log2 n = 2..5 at offsets 0, 16, 80, 336], inv[n][k] at n * N + k.
+__device__ int16_t g_ats_inv[2][1360];
+__device__ __forceinline__ int ats_offset(int log2n) { return log2n == 2 ? 0 : (log2n == 3 ? 16 : (log2n == 4 ? 80 : 336)); }
+
+template <int N, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void ats_line(const int16_t *__restrict__ m, LoadFn load, StoreFn store, int shift)
+{
+    int in[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) in[k] = load(k);
+    const int rnd = 1 << (shift - 1);
+#pragma unroll 4
+    for (int n = 0; n < N; n++) {
+        int acc = rnd;
+#pragma unroll
+        for (int k = 0; k < N; k++) acc += (int)__ldg(m + n * N + k) * in[k];
+        store(n, xb_clip16(acc >> shift));
+    }
+}
+// type: 0 = DST-7, 1 = DCT-8 (the ats_mode bit, xevd_tbl_tr_subset_intra, xevdm_tbl.c:51)
+template <typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void ats_line_dyn(int log2n, int type, LoadFn load, StoreFn store, int shift)
+{
+    const int16_t *m = g_ats_inv[type ? 0 : 1] + ats_offset(log2n);
+    switch (log2n) {
+    case 2: ats_line<4>(m, load, store, shift); break;
+    case 3: ats_line<8>(m, load, store, shift); break;
+    case 4: ats_line<16>(m, load, store, shift); break;
+    default: ats_line<32>(m, load, store, shift); break;
+    }
+}
+
 // dispatch on the line length (2..64)
 template <bool IQT, typename LoadFn, typename StoreFn>
 __device__ __forceinline__ void itx_line_dyn(int log2n, LoadFn load, StoreFn store, int shift)

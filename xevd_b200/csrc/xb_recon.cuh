@@ -192,16 +192,10 @@ __device__ __forceinline__ void pred_tile(const XbFrameArgs &a, const XB200_CU &
 }
 
 // ---- residual phase helpers -------------------------------------------------------------------------------
-// transform-block geometry of plane `pl` for the CU covering a position
-struct TuGeom {
-    int lw, lh;         // log2 size of the transform block
-    int x0, y0;         // position inside the CTU plane
-    int coef;           // offset of the block's top-left coefficient inside the stream
-    int cstride;        // row stride of the coefficient block (the CU plane width)
-    int qp;
-    bool coded;
-};
-
+// The coded transform block of plane `pl` covering SCU (xs, ys) (CTU-relative SCU coordinates) of a CU, or false when that SCU
+// carries no coefficients.  Normal CUs: the CU plane cut into <= 64-sample (chroma 32) blocks gated by the nnz_sub bits
+// (xevd_sub_block_itdq, src_base/xevd_itdq.c:544-621).  ats_inter CUs (Main): one sub-block TU at the side the syntax names
+// (xevdm_get_tu_size / get_tu_pos_offset, src_main/xevdm_util.c:3585-3634); their coefficient blocks hold the TU only.
 __device__ __forceinline__ int plane_coef_base(const XB200_CU &cu, int pl)
 {
     const int n = 1 << (cu.log2w + cu.log2h);
@@ -209,6 +203,68 @@ __device__ __forceinline__ int plane_coef_base(const XB200_CU &cu, int pl)
     if (pl >= 1 && (cu.cbf & 0x00f)) off += (n + 7) & ~7;
     if (pl == 2 && (cu.cbf & 0x0f0)) off += ((n >> 2) + 7) & ~7;
     return off;
+}
+
+struct TbInfo {
+    int lw, lh;         // log2 size of the transform block (plane samples)
+    int px0, py0;       // origin inside the CTU plane (plane samples)
+    int sx0, sy0;       // first SCU column / row (CTU-relative)
+    int coef;           // offset of the block's top-left coefficient inside the stream
+    int cstride;        // coefficient row stride
+    int qp;
+    int ats;            // -1: DCT-2; else horizontal << 1 | vertical, 0 = DST-7, 1 = DCT-8
+};
+
+__device__ __forceinline__ int ats_inter_idx(const XB200_CU &cu) { return (cu.mode == XB200_MODE_INTRA || cu.mode == XB200_MODE_IBC) ? 0 : XB200_ATS_INTER_IDX(cu.ats); }
+
+// log2 TU size and offset (luma samples) of an ats_inter CU
+__device__ __forceinline__ void ats_inter_tu(const XB200_CU &cu, int idx, int &tlw, int &tlh, int &xo, int &yo)
+{
+    const int pos = XB200_ATS_INTER_POS(cu.ats), sh = (idx >= 3) ? 2 : 1;
+    tlw = cu.log2w; tlh = cu.log2h; xo = 0; yo = 0;
+    if (idx == 2 || idx == 4) { tlh -= sh; yo = pos ? (1 << cu.log2h) - (1 << tlh) : 0; }
+    else { tlw -= sh; xo = pos ? (1 << cu.log2w) - (1 << tlw) : 0; }
+}
+
+__device__ __forceinline__ bool tb_at(const XbFrameArgs &a, const XB200_CU &cu, int pl, int ctu_x, int ctu_y, int xs, int ys, TbInfo &t)
+{
+    const int bits = (cu.cbf >> (4 * pl)) & 15;
+    if (!bits) return false;
+    const int sh = pl ? 1 : 0;
+    const int cx_scu = (cu.x - ctu_x) >> 2, cy_scu = (cu.y - ctu_y) >> 2;
+    const int rx = xs - cx_scu, ry = ys - cy_scu;            // SCU position inside the CU
+    t.qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
+    t.ats = -1;
+    const int idx = a.ats ? ats_inter_idx(cu) : 0;
+    if (idx) {
+        int tlw, tlh, xo, yo;
+        ats_inter_tu(cu, idx, tlw, tlh, xo, yo);
+        if ((rx << 2) < xo || (rx << 2) >= xo + (1 << tlw) || (ry << 2) < yo || (ry << 2) >= yo + (1 << tlh)) return false;
+        t.lw = tlw - sh; t.lh = tlh - sh;
+        t.px0 = ((cu.x - ctu_x) + xo) >> sh; t.py0 = ((cu.y - ctu_y) + yo) >> sh;
+        t.sx0 = cx_scu + (xo >> 2); t.sy0 = cy_scu + (yo >> 2);
+        int off = cu.coef_off;
+        const int n = 1 << (tlw + tlh);
+        if (pl >= 1 && (cu.cbf & 0x00f)) off += (n + 7) & ~7;
+        if (pl == 2 && (cu.cbf & 0x0f0)) off += ((n >> 2) + 7) & ~7;
+        t.coef = off; t.cstride = 1 << t.lw;
+        if (pl == 0 && cu.log2w <= 5 && cu.log2h <= 5) {       // xevdm_get_ats_inter_trs (xevdm_util.c:3636-3667)
+            const int first = XB200_ATS_INTER_POS(cu.ats) == 0 ? 1 : 0;
+            t.ats = (idx == 2 || idx == 4) ? first : (first << 1);
+        }
+        return true;
+    }
+    const int lws = min((int)cu.log2w, 6) - 2, lhs = min((int)cu.log2h, 6) - 2;     // log2 block size in SCUs
+    const int sub_i = rx >> lws, sub_j = ry >> lhs;
+    if (!((bits >> ((sub_j << 1) | sub_i)) & 1)) return false;
+    t.lw = lws + 2 - sh; t.lh = lhs + 2 - sh;
+    t.sx0 = cx_scu + (sub_i << lws); t.sy0 = cy_scu + (sub_j << lhs);
+    t.px0 = (t.sx0 << 2) >> sh; t.py0 = (t.sy0 << 2) >> sh;
+    const int pw = (1 << cu.log2w) >> sh;
+    t.cstride = pw;
+    t.coef = plane_coef_base(cu, pl) + (((sub_j << lhs) << 2) >> sh) * pw + (((sub_i << lws) << 2) >> sh);
+    if (a.ats && pl == 0 && cu.mode == XB200_MODE_INTRA && (cu.flags & XB200_CUF_ATS_INTRA)) t.ats = cu.ats & 3;
+    return true;
 }
 
 template <bool IQT>
@@ -253,26 +309,17 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            const int bits = (cu.cbf >> (4 * pl)) & 15;
-            if (!bits || cu.mode == XB200_MODE_INTRA) continue;      // intra CUs belong to the wavefront kernel
-            const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
-            const int ry = ys - cy_scu;                    // SCU row inside the CU
-            const int lhs = min((int)cu.log2h, 6) - 2;     // log2 of the transform-block height in SCUs
-            if (ry & ((1 << lhs) - 1)) continue;           // not the first row of a transform block
-            const int sub_j = ry >> lhs, sub_i = (xs - cx_scu) >> (min((int)cu.log2w, 6) - 2);
-            if (!((bits >> ((sub_j << 1) | sub_i)) & 1)) continue;
-            const int sh = pl ? 1 : 0;
-            const int lw = min((int)cu.log2w, 6) - sh, lh = min((int)cu.log2h, 6) - sh;
-            const int pw = (1 << cu.log2w) >> sh;           // CU plane width = coefficient row stride
-            const int px = x - (((cu.x - ctu_x)) >> sh);    // column inside the CU plane
-            const int py = ((ry << 2) >> sh);               // first row of the block inside the CU plane
-            const int16_t *src = a.coef + plane_coef_base(cu, pl) + py * pw + px;
+            if (cu.mode == XB200_MODE_INTRA) continue;           // intra CUs belong to the wavefront kernel
+            TbInfo t;
+            if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sy0 != ys) continue;
+            const int16_t *src = a.coef + t.coef + (x - t.px0);
             Dequant dq;
-            dq.init(lw, lh, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l, IQT);
+            dq.init(t.lw, t.lh, t.qp, a.bd_l, IQT);
             int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
-            const int ts = (pl == 0 ? S : Sc) + 1;
-            int *dst = tmp + (((ys << 2) >> sh)) * ts + x;
-            itx_line_dyn<IQT>(lh, [&](int k) { return dq.apply(src[k * pw]); }, [&](int n, int v) { dst[n * ts] = v; }, sh1);
+            const int ts = (pl == 0 ? S : Sc) + 1, cs = t.cstride;
+            int *dst = tmp + t.py0 * ts + x;
+            if (t.ats >= 0) ats_line_dyn(t.lh, t.ats & 1, [&](int k) { return dq.apply(src[k * cs]); }, [&](int n, int v) { dst[n * ts] = v; }, 7);
+            else itx_line_dyn<IQT>(t.lh, [&](int k) { return dq.apply(src[k * cs]); }, [&](int n, int v) { dst[n * ts] = v; }, sh1);
         }
     }
     __syncthreads();
@@ -288,23 +335,16 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            const int bits = (cu.cbf >> (4 * pl)) & 15;
-            if (!bits || cu.mode == XB200_MODE_INTRA) continue;
-            const int cy_scu = (cu.y - ctu_y) >> 2, cx_scu = (cu.x - ctu_x) >> 2;
-            const int rx = xs - cx_scu;
-            const int lws = min((int)cu.log2w, 6) - 2;
-            if (rx & ((1 << lws) - 1)) continue;
-            const int sub_i = rx >> lws, sub_j = (ys - cy_scu) >> (min((int)cu.log2h, 6) - 2);
-            if (!((bits >> ((sub_j << 1) | sub_i)) & 1)) continue;
-            const int sh = pl ? 1 : 0;
-            const int lw = min((int)cu.log2w, 6) - sh;
+            if (cu.mode == XB200_MODE_INTRA) continue;
+            TbInfo t;
+            if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sx0 != xs) continue;
             const int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
             int16_t *res = pl == 0 ? sm.res_y : (pl == 1 ? sm.res_u : sm.res_v);
             const int ts = (pl == 0 ? S : Sc) + 1, rs = (pl == 0 ? S : Sc) + 2;
-            const int x0 = (xs << 2) >> sh;
-            const int *srow = tmp + y * ts + x0;
-            int16_t *drow = res + y * rs + x0;
-            itx_line_dyn<false>(lw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
+            const int *srow = tmp + y * ts + t.px0;
+            int16_t *drow = res + y * rs + t.px0;
+            if (t.ats >= 0) ats_line_dyn(t.lw, t.ats >> 1, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, 20 - a.bd_l);
+            else itx_line_dyn<false>(t.lw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
         }
     }
     __syncthreads();
@@ -327,7 +367,9 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     // piece of the CU inside this tile; handled when this SCU is the piece's top-left
                     const int px = max(cx, t_x), py = max(cy, t_y);
                     if (px != t_x + (sx << 2) || py != t_y + (sy << 2)) continue;
-                    const int tw = min(1 << cu.log2w, 16), th = min(1 << cu.log2h, 16);
+                    // the piece ends at the CU's or the tile's edge, whichever comes first: the middle part of a ternary split
+                    // (size s at offset s/2) is not aligned to its own size, so a 16-wide CU can straddle two tiles
+                    const int tw = min(cx + (1 << cu.log2w), t_x + 16) - px, th = min(cy + (1 << cu.log2h), t_y + 16) - py;
                     int pr[8];
                     // luma
                     {
@@ -375,12 +417,21 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const int p = gy * a.w_scu + gx;
         const bool intra = cu.mode == XB200_MODE_INTRA;
         uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u);
-        if (cu.cbf & 1) m |= 1u << 24;
+        bool cbfl = (cu.cbf & 1) != 0;
+        const int aidx = a.ats ? ats_inter_idx(cu) : 0;
+        if (aidx && cbfl) {          // xevdm_set_cu_cbf_flags (xevdm_util.c:3669-3714): luma cbf only on the SCUs of the sub-block TU
+            int tlw, tlh, xo, yo;
+            ats_inter_tu(cu, aidx, tlw, tlh, xo, yo);
+            const int rx = (gx << 2) - cu.x, ry = (gy << 2) - cu.y;
+            cbfl = rx >= xo && rx < xo + (1 << tlw) && ry >= yo && ry < yo + (1 << tlh);
+        }
+        if (cbfl) m |= 1u << 24;
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         a.map_scu[p] = m;
         ((int2 *)a.map_mv)[p] = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
         ((int16_t *)a.map_refi)[p] = intra ? (int16_t)-1 : *(const int16_t *)cu.refi;
-        a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0));
+        a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0) |
+                                  (aidx ? XB200_EDGE_ATS : 0));
     }
 }
 

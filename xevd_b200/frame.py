@@ -100,9 +100,22 @@ class HostPicture:
         return self
 
 
+def ats_inter_tu(ats: int, log2w: int, log2h: int):
+    """(log2 tu_w, log2 tu_h, x offset, y offset) of the sub-block transform unit of an ats_inter CU
+    (xevdm_get_tu_size / get_tu_pos_offset, src_main/xevdm_util.c:3585-3634); the whole CU when ats_inter_idx == 0"""
+    idx, pos = (ats >> 2) & 7, (ats >> 5) & 1
+    if idx == 0:
+        return log2w, log2h, 0, 0
+    sh = 2 if idx in (3, 4) else 1
+    if idx in (2, 4):
+        return log2w, log2h - sh, 0, ((1 << log2h) - (1 << (log2h - sh))) if pos else 0
+    return log2w - sh, log2h, ((1 << log2w) - (1 << (log2w - sh))) if pos else 0, 0
+
+
 def cu_coef_count(cu) -> int:
     """number of int16 coefficients a CU contributes to the stream (planes with cbf == 0 are absent)"""
-    n = 1 << (int(cu["log2w"]) + int(cu["log2h"]))
+    lw, lh = ats_inter_tu(int(cu["ats"]), int(cu["log2w"]), int(cu["log2h"]))[:2] if int(cu["mode"]) != 0 else (int(cu["log2w"]), int(cu["log2h"]))
+    n = 1 << (lw + lh)
     cbf = int(cu["cbf"])
     a8 = lambda v: (v + 7) & ~7   # plane blocks are padded to multiples of 8 int16
     return (a8(n) if cbf & 0x00F else 0) + (a8(n // 4) if cbf & 0x0F0 else 0) + (a8(n // 4) if cbf & 0xF00 else 0)

@@ -101,21 +101,76 @@ def partition_quadtree(w: int, h: int, log2_ctu: int, rng, leaf_prob=(0.1, 1.0 /
     return out, first
 
 
+def partition_btt(w: int, h: int, log2_ctu: int, rng, suco: bool = True, min_log2: int = 3, leaf_bias: float = 0.35):
+    """Main-profile style partition: binary / ternary splits in both directions from the CTU (sps_btt_flag), aspect ratios up
+    to 1:4, optional right-to-left child order for vertical splits (sps_suco_flag, src_main/xevdm.c:1854-1933), so that
+    non-square CUs and CUs whose RIGHT neighbour is decoded first occur.  CUs with a dimension of 128 occur for 128x128 CTUs
+    (they carry up to four 64x64 transform sub-blocks)."""
+    out = []
+    first = [0]
+    ctu = 1 << log2_ctu
+
+    def rec(x, y, lw, lh, depth):
+        if x >= w or y >= h:
+            return
+        cw, ch = 1 << lw, 1 << lh
+        over_x, over_y = x + cw > w, y + ch > h
+        opts = []
+        if lw - 1 >= min_log2 and lw - 1 >= lh - 2:
+            opts.append("bv")
+        if lh - 1 >= min_log2 and lh - 1 >= lw - 2:
+            opts.append("bh")
+        if lw - 2 >= min_log2 and lw - 2 >= lh - 2 and not over_x:
+            opts.append("tv")
+        if lh - 2 >= min_log2 and lh - 2 >= lw - 2 and not over_y:
+            opts.append("th")
+        must = over_x or over_y
+        if must:
+            opts = [o for o in opts if (o == "bv" and over_x) or (o == "bh" and over_y)] or opts
+        if opts and (must or rng.random() >= min(1.0, leaf_bias * (depth + 1) * 0.5)):
+            o = opts[int(rng.integers(0, len(opts)))]
+            rtl = suco and o in ("bv", "tv") and rng.random() < 0.5
+            if o == "bv":
+                ch_ = [(x, y, lw - 1, lh), (x + (cw >> 1), y, lw - 1, lh)]
+            elif o == "bh":
+                ch_ = [(x, y, lw, lh - 1), (x, y + (ch >> 1), lw, lh - 1)]
+            elif o == "tv":
+                ch_ = [(x, y, lw - 2, lh), (x + (cw >> 2), y, lw - 1, lh), (x + 3 * (cw >> 2), y, lw - 2, lh)]
+            else:
+                ch_ = [(x, y, lw, lh - 2), (x, y + (ch >> 2), lw, lh - 1), (x, y + 3 * (ch >> 2), lw, lh - 2)]
+            if rtl:
+                ch_ = ch_[::-1]
+            for c in ch_:
+                rec(*c, depth + 1)
+        else:
+            out.append((x, y, lw, lh))
+
+    for cy in range(0, h, ctu):
+        for cx in range(0, w, ctu):
+            rec(cx, cy, log2_ctu, log2_ctu, 0)
+            first.append(len(out))
+    return out, first
+
+
 def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A", seed: int = 1,
                      n_refs: int = 1, bi_frac: float | None = None, coded_frac: float = 1.0,
                      mv_range_px: int = 32, resid_scale: float | None = None, iqt: bool = False,
-                     log2_cu: int = 4, main_mv: bool = False):
+                     log2_cu: int = 4, main_mv: bool = False, log2_ctu: int = 6, suco: bool = True, ats_inter_frac: float = 0.0):
     """Config-2 style inter picture.
 
     variant "A": uniform 16x16 CUs, uni-prediction, every CU coded in all three planes.
     variant "B": random quadtree {64,32,16,8}, 50 % bi-prediction.
+    variant "C": Main-profile binary/ternary partition (non-square CUs, optional SUCO order, CTU 32/64/128), 50 % bi-prediction;
+                 CUs with a 128 dimension carry a random non-empty subset of their 64x64 transform sub-blocks.
     Returns (params, CuList).  Reference pictures are produced separately (make_refs).
     """
     rng = np.random.default_rng(seed)
-    log2_ctu = 6
     if variant == "A":
         parts, first = partition_uniform(w, h, log2_ctu, log2_cu)
         bi = 0.0 if bi_frac is None else bi_frac
+    elif variant == "C":
+        parts, first = partition_btt(w, h, log2_ctu, rng, suco=suco)
+        bi = 0.5 if bi_frac is None else bi_frac
     else:
         parts, first = partition_quadtree(w, h, log2_ctu, rng)
         bi = 0.5 if bi_frac is None else bi_frac
@@ -144,34 +199,69 @@ def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A",
     cus["refi"] = refi
     cus["mv"] = mv
     coded = rng.random(n) < coded_frac
-    cus["cbf"] = np.where(coded, 0x111, 0).astype(np.uint16)
+    lw_a, lh_a = cus["log2w"].astype(np.int64), cus["log2h"].astype(np.int64)
+    if ats_inter_frac > 0:
+        # ats_inter (sub-block transform, Main tool_ats): coded inter CUs up to 64x64; split kinds allowed by size as in
+        # xevdm_check_ats_inter_info_coded (src_main/xevdm_util.c:3565-3583): halves need >= 8, quarters >= 16
+        pick = rng.random(n) < ats_inter_frac
+        for i in np.nonzero(pick & coded & (lw_a <= 6) & (lh_a <= 6))[0]:
+            kinds = [k for k, ok in ((1, lw_a[i] >= 3), (2, lh_a[i] >= 3), (3, lw_a[i] >= 4), (4, lh_a[i] >= 4)) if ok]
+            if kinds:
+                cus["ats"][i] = (int(kinds[int(rng.integers(0, len(kinds)))]) << 2) | (int(rng.integers(0, 2)) << 5)
+    # nnz_sub bits: one per 64x64 luma (32x32 chroma) transform sub-block, bit (j << 1) | i (xevd_eco.c:618-625)
+    nsx, nsy = np.where(lw_a > 6, 2, 1), np.where(lh_a > 6, 2, 1)
+    full = np.where(nsx == 2, np.where(nsy == 2, 0xF, 0x3), np.where(nsy == 2, 0x5, 0x1))
+    sub = np.zeros((n, 3), np.int64)
+    for c in range(3):
+        pick = rng.integers(1, 16, n) & full
+        sub[:, c] = np.where((full == 1) | (pick == 0), full, pick)
+    cus["cbf"] = np.where(coded, sub[:, 0] | (sub[:, 1] << 4) | (sub[:, 2] << 8), 0).astype(np.uint16)
 
-    # coefficient stream: quantised forward DCT of Laplacian residuals
+    # coefficient stream: quantised forward DCT of Laplacian residuals, per transform sub-block, stored CU-raster
     if resid_scale is None:
         # ~10 % non-zero levels: Laplacian scale ~ 0.22 of a quantiser step (dq_scale/64)
         resid_scale = 0.22 * dq_scale(qp_y, iqt) / 64.0
-    sizes = 1 << (cus["log2w"].astype(np.int64) + cus["log2h"].astype(np.int64))
+    from .frame import ats_inter_tu
+    tu = np.array([ats_inter_tu(int(a_), int(w_), int(h_))[:2] for a_, w_, h_ in zip(cus["ats"], lw_a, lh_a)], np.int64).reshape(n, 2)
+    tlw_a, tlh_a = tu[:, 0], tu[:, 1]                  # coded block = the TU (the whole CU without ats_inter)
+    sizes = 1 << (tlw_a + tlh_a)
     a8 = lambda v: (v + 7) & ~7          # plane blocks padded to multiples of 8 int16
     per_cu = np.where(coded, a8(sizes) + 2 * a8(sizes // 4), 0)
     off = np.concatenate(([0], np.cumsum(per_cu)))
     cus["coef_off"] = off[:-1].astype(np.uint32)
     coef = np.zeros(int(off[-1]), np.int16)
-    for lg in np.unique(cus["log2w"]):
-        sel = np.nonzero((cus["log2w"] == lg) & coded)[0]
+
+    def plane_levels(m, pw, ph, bits, tmax):
+        """levels of m planes of pw x ph, transform sub-blocks of at most tmax, uncoded sub-blocks zero"""
+        tw, th = min(pw, tmax), min(ph, tmax)
+        nx, ny = pw // tw, ph // th
+        r = rng.laplace(0.0, resid_scale, (m, ny, nx, th, tw))
+        lev = quantised_dct(r, qp_y, iqt)
+        for j in range(ny):
+            for i in range(nx):
+                lev[:, j, i][((bits >> ((j << 1) | i)) & 1) == 0] = 0
+        return lev.transpose(0, 1, 3, 2, 4).reshape(m, ph * pw)
+
+    shapes = np.unique(np.stack([tlw_a, tlh_a], 1), axis=0)
+    for lw_, lh_ in shapes:
+        sel = np.nonzero((tlw_a == lw_) & (tlh_a == lh_) & coded)[0]
         if len(sel) == 0:
             continue
-        s = 1 << int(lg)
-        ry = rng.laplace(0.0, resid_scale, (len(sel), s, s))
-        rc = rng.laplace(0.0, resid_scale, (len(sel), 2, s // 2, s // 2))
-        ly = quantised_dct(ry, qp_y, iqt).reshape(len(sel), -1)
-        lc = quantised_dct(rc, qp_y, iqt).reshape(len(sel), 2, -1)
-        nc = a8(s * s // 4)
+        cw_, ch_ = 1 << int(lw_), 1 << int(lh_)
+        ly = plane_levels(len(sel), cw_, ch_, sub[sel, 0], 64)
+        lu = plane_levels(len(sel), cw_ // 2, ch_ // 2, sub[sel, 1], 32)
+        lv = plane_levels(len(sel), cw_ // 2, ch_ // 2, sub[sel, 2], 32)
+        nc = a8(cw_ * ch_ // 4)
         lcp = np.zeros((len(sel), 2, nc), np.int16)
-        lcp[:, :, :lc.shape[2]] = lc
-        blk = np.concatenate([ly, lcp.reshape(len(sel), -1)], axis=1)
+        lcp[:, 0, :lu.shape[1]] = lu
+        lcp[:, 1, :lv.shape[1]] = lv
+        lyp = np.zeros((len(sel), a8(cw_ * ch_)), np.int16)
+        lyp[:, :ly.shape[1]] = ly
+        blk = np.concatenate([lyp, lcp.reshape(len(sel), -1)], axis=1)
         idx = off[sel][:, None] + np.arange(blk.shape[1])[None, :]
         coef[idx] = blk
-    prm = make_params(w, h, bit_depth=bit_depth, log2_ctu=log2_ctu, poc=8, tool_iqt=int(iqt), tool_admvp=int(main_mv))
+    prm = make_params(w, h, bit_depth=bit_depth, log2_ctu=log2_ctu, poc=8, tool_iqt=int(iqt), tool_admvp=int(main_mv),
+                      tool_ats=int(ats_inter_frac > 0))
     cl = CuList(w=w, h=h, log2_ctu=log2_ctu, cus=cus, ctu_first=np.array(first, np.uint32), coef=coef)
     return prm, cl
 
@@ -215,17 +305,29 @@ def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp
     return pic
 
 
-def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, constrained: bool = False):
+def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, constrained: bool = False, eipd: bool = False,
+                  ats_intra_frac: float = 0.0):
     """Turn a fraction of the CUs of a picture into intra CUs (Baseline modes 0..4 for luma and chroma) and derive their
     neighbour-availability masks the way the decoder does: a neighbouring SCU is available when it lies inside the picture
     and was reconstructed earlier in decoding order (COD bit of map_scu; xevd_get_nbr_b, src_base/xevd_ipred.c:49-91).
-    With `constrained` (pps.constrained_intra_pred_flag) it must also be intra."""
+    With `constrained` (pps.constrained_intra_pred_flag) it must also be intra.
+    eipd: Main-profile mode set (33 luma modes, chroma modes DM/BI/DC/HOR/VER = 0..4) plus the right-column mask and
+    avail_lr (xevd_check_nev_avail, src_base/xevd_util.c:1156-1174) that xevdm_get_nbr / xevdm_ipred consume."""
     cus = cl.cus
     n = len(cus)
     w_scu, h_scu = (cl.w + 3) >> 2, (cl.h + 3) >> 2
-    is_intra = rng.random(n) < intra_frac
+    is_intra = (rng.random(n) < intra_frac) & (((cus["ats"] >> 2) & 7) == 0)       # ats_inter CUs stay inter
+    if ats_intra_frac > 0:
+        # ats_intra_cu (Main tool_ats): intra CUs of at most 32x32 with coded luma; ats mode = h << 1 | v (0 DST-7, 1 DCT-8)
+        from .abi import CUF_ATS_INTRA
+        ok = is_intra & (cus["log2w"] <= 5) & (cus["log2h"] <= 5) & ((cus["cbf"] & 15) != 0) & (rng.random(n) < ats_intra_frac)
+        cus["flags"] = np.where(ok, cus["flags"] | CUF_ATS_INTRA, cus["flags"])
+        cus["ats"] = np.where(ok, rng.integers(0, 4, n), cus["ats"]).astype(np.uint8)
     cus["mode"] = np.where(is_intra, MODE_INTRA, MODE_INTER)
     ipm = rng.integers(0, n_modes, (n, 2)).astype(np.int8)
+    if eipd:
+        ipm[:, 0] = rng.integers(0, 33, n)
+        ipm[:, 1] = rng.integers(0, 5, n)
     cus["refi"] = np.where(is_intra[:, None], ipm, cus["refi"])
     cus["mv"][is_intra] = 0
     ext = [np.zeros(1, EXT_DTYPE)[0]]
@@ -237,16 +339,20 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
         nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
         if is_intra[i]:
             ok = (lambda yy, xx: cod[yy, xx] and (not constrained or intra_map[yy, xx]))
-            up = left = 0
+            up = left = right = 0
             for k in range(nw + nh):
                 if ys > 0 and xs + k < w_scu and ok(ys - 1, xs + k):
                     up |= 1 << k
                 if xs > 0 and ys + k < h_scu and ok(ys + k, xs - 1):
                     left |= 1 << k
+                if xs + nw < w_scu and ys + k < h_scu and ok(ys + k, xs + nw):
+                    right |= 1 << k
             ul = int(ys > 0 and xs > 0 and ok(ys - 1, xs - 1))
+            # avail_lr looks at COD only (no constrained-intra test)
+            lr = int(xs > 0 and cod[ys, xs - 1]) | (int(xs + nw < w_scu and cod[ys, xs + nw]) << 1)
             e = np.zeros(1, EXT_DTYPE)[0]
-            e["q"][0], e["q"][1] = up, left
-            cu["avail"] = (int(cu["avail"]) & 3) | (ul << 2)
+            e["q"][0], e["q"][1], e["q"][2] = up, left, right
+            cu["avail"] = lr | (ul << 2)
             cu["mv"][1] = np.frombuffer(np.uint32(len(ext)).tobytes(), np.int16)
             ext.append(e)
         cod[ys:ys + nh, xs:xs + nw] = True
