@@ -55,7 +55,8 @@ typedef int16_t xb200_pel;           /* pel == s16 always (src_base/xevd_port.h:
 /* prediction modes of a CU work item (values follow xevd_def.h:287-290 for the first three) */
 #define XB200_MODE_INTRA   0
 #define XB200_MODE_INTER   1         /* MODE_INTER / MODE_SKIP / MODE_DIR once motion is resolved */
-#define XB200_MODE_IBC     4
+#define XB200_MODE_IBC     4         /* intra block copy: mv[0] = block vector in whole samples, refi = {-1,-1}; the vector must
+                                        stay inside the current CTU row at or left of the CU's CTU (as conforming streams do) */
 #define XB200_MODE_AFFINE  5
 
 /* XB200_CU.flags */

@@ -147,7 +147,7 @@ int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
 /* ------------------------------------------------------------------------------------------------------------------------
  * Main-profile deblocking (sps->tool_addb == 1): an H.264-style filter.
  * Restates get_bs (src_main/xevdm_df.c:361-513), deblock_scu_line_luma / _chroma (:584-781) and the CU walkers
- * deblock_addb_cu_hor / _ver (:835-1135) for one tile / one slice, TREE_LC, no ATS-inter.
+ * deblock_addb_cu_hor / _ver (:835-1135) for one tile / one slice, TREE_LC.
  *   - only edges on the 8x8 luma grid are filtered (:853,1054,1109)
  *   - bS: 4 intra and the two SCUs in different CTUs, 3 intra or IBC, 2 luma cbf, else 1 / 0 from comparing the reference
  *     PICTURES (not indices) and the motion vectors
@@ -174,6 +174,7 @@ typedef struct {
     const int *cq[2];
     const int *ref_id[2];        /* identity of the picture behind (list, refi) */
     uint8_t *cod;
+    uint8_t *ats;                /* mctx->map_ats_inter: non-zero on the SCUs of ats_inter CUs (tool_ats) */
 } AddbCtx;
 
 static int addb_index(int qp, int offset) { return orc_clip3(0, 51, (int)(uint8_t)qp + (int)(uint8_t)offset); }
@@ -188,7 +189,7 @@ static int addb_bs(const AddbCtx *c, int cur, int nb, int x0, int y0, int x1, in
     if (intra && ((x0 >> lg) != (x1 >> lg) || (y0 >> lg) != (y1 >> lg))) return 4;
     if (intra) return 3;
     if (((m0 >> 26) & 1) || ((m1 >> 26) & 1)) return 3;
-    if (((m0 >> 24) & 1) || ((m1 >> 24) & 1)) return 2;
+    if (((m0 >> 24) & 1) || ((m1 >> 24) & 1) || c->ats[cur] || c->ats[nb]) return 2;       /* ats_present, xevdm_df.c:415,902-906 */
     const int8_t *r0 = p->map_refi + 2 * cur, *r1 = p->map_refi + 2 * nb;
     const int16_t *v0 = p->map_mv + 4 * cur, *v1 = p->map_mv + 4 * nb;
     int pa[2], pb[2], a[2][2], b[2][2];
@@ -297,6 +298,12 @@ int orc_deblock_frame_addb(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU
     AddbCtx c;
     c.prm = prm; c.pic = pic; c.cq[0] = chroma_qp_tbl; c.cq[1] = chroma_qp_tbl + 58; c.ref_id[0] = ref_id_l0; c.ref_id[1] = ref_id_l1;
     c.cod = (uint8_t *)malloc((size_t)pic->w_scu * pic->h_scu);
+    c.ats = (uint8_t *)calloc((size_t)pic->w_scu * pic->h_scu, 1);
+    if (prm->tool_ats)
+        for (int n = 0; n < n_cu; n++)
+            if (cus[n].mode != XB200_MODE_INTRA && cus[n].mode != XB200_MODE_IBC && XB200_ATS_INTER_IDX(cus[n].ats))
+                for (int j = 0; j < (1 << (cus[n].log2h - 2)); j++)
+                    memset(c.ats + ((cus[n].y >> 2) + j) * pic->w_scu + (cus[n].x >> 2), 1, 1 << (cus[n].log2w - 2));
     for (int pass = 0; pass < 2; pass++) {
         memset(c.cod, 0, (size_t)pic->w_scu * pic->h_scu);
         for (int n = 0; n < n_cu; n++) {
@@ -306,6 +313,6 @@ int orc_deblock_frame_addb(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU
             else addb_visit(&c, cus[n].x, cus[n].y, w, h, pass);
         }
     }
-    free(c.cod);
+    free(c.cod); free(c.ats);
     return XB200_OK;
 }

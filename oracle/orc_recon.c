@@ -36,6 +36,7 @@ static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *
             const int p = (y0 + j) * cur->w_scu + x0 + i;
             /* MCU_SET_IF_SN_QP | CBFL | SF | COD (xevd_def.h:372-437); slice number 0 */
             uint32_t m = ((uint32_t)(cu->qp_map & 0x7f) << 16) | ((uint32_t)intra << 15) | (1u << 31);
+            if (cu->mode == XB200_MODE_IBC) m |= 1u << 26;                /* MCU_SET_IBC (xevdm_def.h:325) */
             int cbfl = cu->cbf & 1;
             if (cbfl && prm->tool_ats && !intra && cu->mode != XB200_MODE_IBC && XB200_ATS_INTER_IDX(cu->ats)) {
                 /* xevdm_set_cu_cbf_flags (src_main/xevdm_util.c:3669-3714): luma cbf only on the SCUs of the sub-block TU */
@@ -47,7 +48,7 @@ static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *
             if (cu->flags & XB200_CUF_SKIP) m |= 1u << 23;
             cur->map_scu[p] = m;
             for (int l = 0; l < 2; l++) {
-                cur->map_refi[p * 2 + l] = intra ? -1 : cu->refi[l];
+                cur->map_refi[p * 2 + l] = (intra || cu->mode == XB200_MODE_IBC) ? -1 : cu->refi[l];
                 cur->map_mv[(p * 2 + l) * 2 + 0] = intra ? 0 : cu->mv[l][0];
                 cur->map_mv[(p * 2 + l) * 2 + 1] = intra ? 0 : cu->mv[l][1];
             }
@@ -80,6 +81,14 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
 
         if (cu->mode == XB200_MODE_INTER) {
             orc_inter_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, py, pu, pv);
+        } else if (cu->mode == XB200_MODE_IBC) {
+            /* xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the current picture; chroma vector = luma >> 1 */
+            const int bx = cu->mv[0][0], by = cu->mv[0][1];
+            for (int i = 0; i < h; i++) memcpy(py + i * w, cur->y + (cu->y + by + i) * cur->s_l + cu->x + bx, sizeof(pel) * w);
+            for (int i = 0; i < ch; i++) {
+                memcpy(pu + i * cw, cur->u + ((cu->y >> 1) + (by >> 1) + i) * cur->s_c + (cu->x >> 1) + (bx >> 1), sizeof(pel) * cw);
+                memcpy(pv + i * cw, cur->v + ((cu->y >> 1) + (by >> 1) + i) * cur->s_c + (cu->x >> 1) + (bx >> 1), sizeof(pel) * cw);
+            }
         } else if (cu->mode == XB200_MODE_INTRA && !prm->tool_eipd) {
             /* xevd_recon_unit intra branch (src_base/xevd.c:732-741): neighbours from the CURRENT picture, so CUs must be
              * reconstructed in decoding order; refi[] carries ipm[0..1], mv[1] the index of the availability masks */

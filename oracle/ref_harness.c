@@ -227,6 +227,11 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
             xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
             xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
+        } else if (cu->mode == XB200_MODE_IBC) {
+            XEVD_PIC cp;
+            TREE_CONS tc = { FALSE, TREE_LC, eAll };
+            wrap_pic(cur, &cp);
+            xevdm_IBC_mc(cu->x, cu->y, cu->log2w, cu->log2h, mv[0], &cp, s->pred[0], tc, prm->chroma_format_idc);
         } else if (cu->mode == XB200_MODE_INTRA) {
             /* Main-profile intra branch of xevd_recon_unit (src_main/xevdm.c:1344-1361) with the reference's own availability logic */
             const u16 avail_cu = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
@@ -306,6 +311,14 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     ctx->map_tidx = (u8 *)calloc(f_scu, 1);
     ctx->map_cu_mode = (u32 *)calloc(f_scu, sizeof(u32));
     m->map_ats_inter = (u8 *)calloc(f_scu, 1);
+    if (prm->tool_ats)          /* what xevdm_set_dec_info leaves in map_ats_inter (src_main/xevdm_util.c:4307-4311) */
+        for (n = 0; n < n_cu; n++)
+            if (cus[n].mode != XB200_MODE_INTRA && cus[n].mode != XB200_MODE_IBC && XB200_ATS_INTER_IDX(cus[n].ats)) {
+                int j;
+                for (j = 0; j < (1 << (cus[n].log2h - 2)); j++)
+                    memset(m->map_ats_inter + ((cus[n].y >> 2) + j) * pic->w_scu + (cus[n].x >> 2),
+                           get_ats_inter_info(XB200_ATS_INTER_IDX(cus[n].ats), XB200_ATS_INTER_POS(cus[n].ats)), 1 << (cus[n].log2w - 2));
+            }
     ctx->fn_dbk = g_ctx->fn_dbk; ctx->fn_dbk_chroma = g_ctx->fn_dbk_chroma;
     for (i = 0; i < n_l0 && ref_id_l0; i++) ctx->refp[i][REFP_0].pic = &dummy[ref_id_l0[i] & 63];
     for (i = 0; i < n_l1 && ref_id_l1; i++) ctx->refp[i][REFP_1].pic = &dummy[ref_id_l1[i] & 63];

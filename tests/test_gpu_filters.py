@@ -143,3 +143,21 @@ def test_alf(ctx, oracle, w, h, bd, log2_ctu, enable):
     got2 = d.download()
     for pa, pb, name in zip(got2.planes(), want2.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("kw,bd,addb", [({}, 10, 1), (dict(log2_ctu=7), 10, 1), (dict(log2_ctu=5), 8, 1), ({}, 10, 0), (dict(log2_ctu=7), 8, 0)])
+def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
+    """both deblocking filters on Main-profile partitions (non-square CUs, ternary-split edges, 128-sample CUs, ats_inter CUs)"""
+    from tests.test_oracle_vs_ref import deblock_main_inputs
+    w, h, prm, cl, base, tbl, ids = deblock_main_inputs(oracle, kw, bd, addb)
+    want = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    pics = [ctx.pic_alloc(w, h) for _ in range(3)]
+    d = ctx.pic_alloc(w, h).upload(base, padded=False).upload_maps(base, cl.edge_flags())
+    ctx.set_chroma_qp_table(tbl)
+    ctx.deblock(prm, d, [pics[0], pics[1], pics[0]], [pics[2], pics[1], pics[0]])
+    got = d.download()
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+    for p in pics + [d]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"

@@ -208,6 +208,24 @@ def test_ats(ctx, oracle, variant, kw, bd, intra_frac, iqt):
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
 
 
+@pytest.mark.parametrize("variant,kw,bd,intra_frac", [("C", {}, 10, 0.3), ("C", dict(log2_ctu=7), 10, 0.3), ("C", dict(log2_ctu=5), 8, 0.5), ("B", {}, 10, 0.0),
+                                                      ("A", dict(log2_cu=3), 10, 0.2)])
+def test_ibc(ctx, oracle, variant, kw, bd, intra_frac):
+    """intra block copy CUs in the wavefront kernel, mixed with intra, inter and ats_inter CUs"""
+    from tests.test_oracle_vs_ref import ibc_inputs
+    w, h, prm, cl, refs = ibc_inputs(variant, kw, bd, intra_frac)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
 def test_intra_1080p_wavefront(ctx, oracle):
     """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
     w, h, bd = 1920, 1080, 10

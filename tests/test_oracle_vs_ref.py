@@ -246,3 +246,59 @@ def test_recon_frame_ats(oracle, reference, variant, kw, bd, intra_frac, iqt):
     b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+DBK_MAIN_CASES = [({}, 10, 1), (dict(log2_ctu=7), 10, 1), (dict(log2_ctu=5), 8, 1), ({}, 10, 0), (dict(log2_ctu=7), 8, 0)]
+
+
+def deblock_main_inputs(oracle, kw, bd, addb):
+    w, h = 256, 136
+    rng = np.random.default_rng(170 + bd + addb)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="C", seed=35, n_refs=3, coded_frac=0.4, bi_frac=0.4, mv_range_px=2,
+                                     ats_inter_frac=0.3, **kw)
+    prm.tool_addb = addb
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    refs = synth.make_refs(w, h, bd, 3, seed=34)
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl in base.planes():
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+    synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)
+    return w, h, prm, cl, base, synth.chroma_qp_table(True), ((0, 1, 0), (2, 1, 0))
+
+
+@pytest.mark.parametrize("kw,bd,addb", DBK_MAIN_CASES)
+def test_deblock_main_partitions(oracle, reference, kw, bd, addb):
+    """both deblocking filters on Main-profile partitions: non-square CUs, edges off the 8x8 grid (ternary splits), 128-sample CUs
+    with their 64-sample transform edge, and ats_inter CUs (ats_present raises the ADDB strength to 'coded', xevdm_df.c:415,902)"""
+    w, h, prm, cl, base, tbl, ids = deblock_main_inputs(oracle, kw, bd, addb)
+    a = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    b = reference.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    changed = sum(int((x != y).sum()) for x, y in zip(a.planes(), base.planes()))
+    assert changed > 300, "test picture does not exercise the filter"
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+IBC_CASES = [("C", {}, 10, 0.3), ("C", dict(log2_ctu=7), 10, 0.3), ("C", dict(log2_ctu=5), 8, 0.5), ("B", {}, 10, 0.0), ("A", dict(log2_cu=3), 10, 0.2)]
+
+
+def ibc_inputs(variant, kw, bd, intra_frac):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=51, n_refs=2, coded_frac=0.8, ats_inter_frac=0.3, **kw)
+    prm.tool_eipd = 1
+    prm.tool_ibc = 1
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True, ats_intra_frac=0.5, ibc_frac=0.6)
+    cl.validate()
+    assert (cl.cus["mode"] == 4).sum() >= 5
+    return w, h, prm, cl, synth.make_refs(w, h, bd, 2, seed=9)
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac", IBC_CASES)
+def test_recon_frame_ibc(oracle, reference, variant, kw, bd, intra_frac):
+    """intra block copy (xevdm_IBC_mc): whole-sample copies from the decoded part of the current picture, odd vectors included
+    (chroma vector = luma >> 1), mixed with intra, inter and ats_inter CUs"""
+    w, h, prm, cl, refs = ibc_inputs(variant, kw, bd, intra_frac)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

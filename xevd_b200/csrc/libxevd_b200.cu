@@ -489,7 +489,7 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     };
     int has_intra = 0, max_cu = 0, any_l1 = 0;
     for (int i = 0; i < n_cu; i++) {
-        const bool intra = cus[i].mode == XB200_MODE_INTRA;
+        const bool intra = xb_wavefront_mode(cus[i].mode);
         has_intra |= intra;
         if (intra) continue;
         any_l1 |= cus[i].refi[1] >= 0;

@@ -42,6 +42,10 @@ struct XbFrameArgs {
     int w_scu, h_scu;
 };
 
+// CUs that read samples of the CURRENT picture (intra prediction, intra block copy) are reconstructed by the CTU wavefront
+// kernel (xb_intra.cuh); everything else by the fully parallel inter kernels
+__host__ __device__ __forceinline__ bool xb_wavefront_mode(int mode) { return mode == XB200_MODE_INTRA || mode == XB200_MODE_IBC; }
+
 __device__ __forceinline__ int xb_clip3(int lo, int hi, int v) { return max(lo, min(hi, v)); }
 __device__ __forceinline__ int xb_clip16(int v) { return max(-32768, min(32767, v)); }
 

@@ -242,7 +242,7 @@ __device__ __forceinline__ int addb_bs(const DbkArgs &a, int cur, int nb, int x0
     const bool intra = ((m0 | m1) >> 15) & 1;
     if (intra) return ((x0 >> a.log2_ctu) != (x1 >> a.log2_ctu) || (y0 >> a.log2_ctu) != (y1 >> a.log2_ctu)) ? 4 : 3;
     if (((m0 | m1) >> 26) & 1) return 3;
-    if (((m0 | m1) >> 24) & 1) return 2;
+    if ((((m0 | m1) >> 24) & 1) || ((a.map_edge[cur] | a.map_edge[nb]) & XB200_EDGE_ATS)) return 2;     // luma cbf or ats_present (xevdm_df.c:415)
     const int16_t r0 = ((const int16_t *)a.map_refi)[cur], r1 = ((const int16_t *)a.map_refi)[nb];
     const int8_t r00 = (int8_t)(r0 & 0xff), r01 = (int8_t)(r0 >> 8), r10 = (int8_t)(r1 & 0xff), r11 = (int8_t)(r1 >> 8);
     const int pa0 = r00 >= 0 ? a.ref_id[0][r00] : -1, pa1 = r01 >= 0 ? a.ref_id[1][r01] : -1;

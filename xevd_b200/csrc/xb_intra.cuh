@@ -296,7 +296,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 
     // any intra CU here?  (uniform: every thread scans the same descriptors through L1)
     bool any = false;
-    for (int i = cu0 + tid; i < cu1; i += kIntraThreads) any |= a.cus[i].mode == XB200_MODE_INTRA;
+    for (int i = cu0 + tid; i < cu1; i += kIntraThreads) any |= xb_wavefront_mode(a.cus[i].mode);
     any = __syncthreads_or(any);
     if (any) {
         if (tid < 4) {
@@ -311,7 +311,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         __syncthreads();
         for (int i = cu0; i < cu1; i++) {
             const XB200_CU cu = a.cus[i];
-            if (cu.mode != XB200_MODE_INTRA) continue;              // uniform
+            if (!xb_wavefront_mode(cu.mode)) continue;              // uniform
             const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
             uint32_t ei;
             memcpy(&ei, cu.mv[1], 4);
@@ -328,6 +328,25 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 cu_plane_residual<IQT>(coef, lw, lh, pl ? 5 : 6, bits, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l, res[pl], s_tmp,
                                        tid, kIntraThreads, (a.ats && pl == 0 && (cu.flags & XB200_CUF_ATS_INTRA)) ? (cu.ats & 3) : -1);
                 coef += ((1 << (lw + lh)) + 7) & ~7;
+            }
+            if (cu.mode == XB200_MODE_IBC) {
+                // xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the already reconstructed part of the CURRENT
+                // picture (block vector mv[0], chroma vector = luma >> 1), then xevdm_recon.  Conforming vectors stay inside the
+                // current CTU row at or left of this CTU, which the wavefront has completed.
+                const int bx = cu.mv[0][0], by = cu.mv[0][1];
+                for (int pl = 0; pl < 3; pl++) {
+                    const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, s = pl ? a.s_c : a.s_l, lwp = cu.log2w - sh;
+                    pel *rec = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)(cu.y >> sh) * s + (cu.x >> sh);
+                    const pel *src = rec + (ptrdiff_t)(by >> sh) * s + (bx >> sh);
+                    const bool coded = ((cu.cbf >> (4 * pl)) & 15) != 0;
+                    for (int i = tid; i < pw * ph; i += kIntraThreads) {
+                        const int y = i >> lwp, x = i & (pw - 1);
+                        const int p = __ldcg(src + (size_t)y * s + x);
+                        rec[(size_t)y * s + x] = (pel)xb_clip3(0, maxv, (int16_t)(p + (coded ? res[pl][i] : 0)));
+                    }
+                }
+                __syncthreads();
+                continue;
             }
             // neighbours of all three planes, then prediction + reconstruction
             int16_t *up[3], *le[3], *ri[3];

@@ -309,7 +309,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            if (cu.mode == XB200_MODE_INTRA) continue;           // intra CUs belong to the wavefront kernel
+            if (xb_wavefront_mode(cu.mode)) continue;            // intra / IBC CUs belong to the wavefront kernel
             TbInfo t;
             if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sy0 != ys) continue;
             const int16_t *src = a.coef + t.coef + (x - t.px0);
@@ -335,7 +335,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            if (cu.mode == XB200_MODE_INTRA) continue;
+            if (xb_wavefront_mode(cu.mode)) continue;
             TbInfo t;
             if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sx0 != xs) continue;
             const int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
@@ -362,7 +362,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     const unsigned ci = sm.cu_of_scu[((t_y >> 2) + sy) * nscu + (t_x >> 2) + sx];
                     if (ci == 0xffff) continue;
                     const XB200_CU cu = cus[ci];
-                    if (cu.mode == XB200_MODE_INTRA) continue;
+                    if (xb_wavefront_mode(cu.mode)) continue;
                     const int cx = cu.x - ctu_x, cy = cu.y - ctu_y;
                     // piece of the CU inside this tile; handled when this SCU is the piece's top-left
                     const int px = max(cx, t_x), py = max(cy, t_y);
@@ -415,8 +415,8 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const XB200_CU cu = cus[ci];
         const int gx = (ctu_x >> 2) + (i % nscu), gy = (ctu_y >> 2) + (i / nscu);
         const int p = gy * a.w_scu + gx;
-        const bool intra = cu.mode == XB200_MODE_INTRA;
-        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u);
+        const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
+        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);     // MCU_SET_IBC
         bool cbfl = (cu.cbf & 1) != 0;
         const int aidx = a.ats ? ats_inter_idx(cu) : 0;
         if (aidx && cbfl) {          // xevdm_set_cu_cbf_flags (xevdm_util.c:3669-3714): luma cbf only on the SCUs of the sub-block TU
@@ -429,7 +429,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         a.map_scu[p] = m;
         ((int2 *)a.map_mv)[p] = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
-        ((int16_t *)a.map_refi)[p] = intra ? (int16_t)-1 : *(const int16_t *)cu.refi;
+        ((int16_t *)a.map_refi)[p] = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
         a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0) |
                                   (aidx ? XB200_EDGE_ATS : 0));
     }

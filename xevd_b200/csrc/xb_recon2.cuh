@@ -288,7 +288,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             if (i < ncu) {
                 const XB200_CU cu = s_cu[i];
                 const int w = 1 << cu.log2w, h = 1 << cu.log2h;
-                const bool inter = cu.mode != XB200_MODE_INTRA;      // intra CUs belong to the wavefront kernel: no work items here
+                const bool inter = !xb_wavefront_mode(cu.mode);      // intra / IBC CUs belong to the wavefront kernel: no work items here
                 const int ny = (inter && (cu.cbf & 15)) ? 1 : 0, nc = inter ? ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0) : 0;
                 switch (warp) {
                 case 0: c = ny; break;
@@ -313,7 +313,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int n_tu = n_tuy + n_tuc;
 
     // ---- one thread per CU: transform-block and tile descriptors ------------------------------------------------------------------
-    if (tid < ncu && s_cu[tid].mode != XB200_MODE_INTRA) {
+    if (tid < ncu && !xb_wavefront_mode(s_cu[tid].mode)) {
         const XB200_CU cu = s_cu[tid];
         const int *of = s_offs + tid * 8;
         const int w = 1 << cu.log2w, h = 1 << cu.log2h;
@@ -658,12 +658,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     for (int i = tid; i < ncu; i += kR2Threads) {
         const XB200_CU cu = s_cu[i];
         const int sx = cu.x >> 2, sy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
-        const bool intra = cu.mode == XB200_MODE_INTRA;
-        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u);
+        const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
+        uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);
         if (cu.cbf & 1) m |= 1u << 24;
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         const int2 mv = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
-        const int16_t rf = intra ? (int16_t)-1 : *(const int16_t *)cu.refi;
+        const int16_t rf = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
         for (int y = 0; y < nh; y++)
             for (int x = 0; x < nw; x++) {
                 const int p = (sy + y) * a.w_scu + sx + x;

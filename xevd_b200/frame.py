@@ -161,7 +161,7 @@ class CuList:
         return self
 
     def edge_flags(self) -> np.ndarray:
-        """one byte per SCU: bit0 = CU/TU boundary on the left side, bit1 = on the top side
+        """one byte per SCU: bit0 = CU/TU boundary on the left side, bit1 = on the top side, bit2 = ats_inter CU
         (what deblock_tree derives from map_split, src_base/xevd.c:1057-1114: CU boundaries plus the
         64-sample transform split of larger CUs)"""
         w_scu, h_scu = (self.w + 3) >> 2, (self.h + 3) >> 2
@@ -173,4 +173,6 @@ class CuList:
                 f[y0:y0 + nh, xs] |= 1
             for ys in range(y0, y0 + nh, 16):
                 f[ys, x0:x0 + nw] |= 2
+            if int(cu["mode"]) not in (0, 4) and (int(cu["ats"]) >> 2) & 7:
+                f[y0:y0 + nh, x0:x0 + nw] |= 4          # XB200_EDGE_ATS: SCUs of ats_inter CUs (map_ats_inter != 0)
         return f.reshape(-1)

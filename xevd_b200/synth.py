@@ -306,11 +306,13 @@ def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp
 
 
 def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, constrained: bool = False, eipd: bool = False,
-                  ats_intra_frac: float = 0.0):
+                  ats_intra_frac: float = 0.0, ibc_frac: float = 0.0):
     """Turn a fraction of the CUs of a picture into intra CUs (Baseline modes 0..4 for luma and chroma) and derive their
     neighbour-availability masks the way the decoder does: a neighbouring SCU is available when it lies inside the picture
     and was reconstructed earlier in decoding order (COD bit of map_scu; xevd_get_nbr_b, src_base/xevd_ipred.c:49-91).
     With `constrained` (pps.constrained_intra_pred_flag) it must also be intra.
+    ibc_frac: fraction of the remaining inter CUs turned into intra-block-copy CUs (Main, sps ibc_flag) whose block vector points
+    into the already decoded part of the current or the left neighbouring CTU (the legal range of EVC block vectors).
     eipd: Main-profile mode set (33 luma modes, chroma modes DM/BI/DC/HOR/VER = 0..4) plus the right-column mask and
     avail_lr (xevd_check_nev_avail, src_base/xevd_util.c:1156-1174) that xevdm_get_nbr / xevdm_ipred consume."""
     cus = cl.cus
@@ -333,10 +335,30 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     ext = [np.zeros(1, EXT_DTYPE)[0]]
     cod = np.zeros((h_scu, w_scu), bool)
     intra_map = np.zeros((h_scu, w_scu), bool)
+    from .abi import MODE_IBC
+    ctu_scu = (1 << cl.log2_ctu) >> 2
+    want_ibc = (~is_intra) & (((cus["ats"] >> 2) & 7) == 0) & (rng.random(n) < ibc_frac) if ibc_frac > 0 else np.zeros(n, bool)
     for i in range(n):
         cu = cus[i]
         xs, ys = int(cu["x"]) >> 2, int(cu["y"]) >> 2
         nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+        if want_ibc[i]:
+            # candidate source blocks: SCU-aligned or not, fully decoded, inside the current / left CTU of this CTU row
+            x0, y0, cw_, ch_ = int(cu["x"]), int(cu["y"]), 4 * nw, 4 * nh
+            cy0 = (ys // ctu_scu) * ctu_scu * 4
+            cx0 = max(0, ((xs // ctu_scu) - 1) * ctu_scu * 4)
+            for _ in range(24):
+                sx = int(rng.integers(cx0, x0 + cw_))
+                sy = int(rng.integers(cy0, min(cy0 + 4 * ctu_scu, cl.h) - ch_ + 1))
+                if sx + cw_ > cl.w or sx < 1 or sy < 1:
+                    continue
+                # odd vectors floor towards the upper left for chroma (>> 1): require one more decoded sample there
+                if cod[(sy - 1) >> 2:((sy + ch_ - 1) >> 2) + 1, (sx - 1) >> 2:((sx + cw_ - 1) >> 2) + 1].all():
+                    cu["mode"] = MODE_IBC
+                    cu["refi"] = -1
+                    cu["mv"] = 0
+                    cu["mv"][0] = (sx - x0, sy - y0)
+                    break
         if is_intra[i]:
             ok = (lambda yy, xx: cod[yy, xx] and (not constrained or intra_map[yy, xx]))
             up = left = right = 0
