@@ -96,7 +96,9 @@ typedef struct XB200_CU {
                                  coefficient blocks hold only the sub-block transform unit (TU-raster, TU size per
                                  xevdm_get_tu_size, xevdm_util.c:3585-3608)                            */
     uint8_t  avail;           /* avail_lr (bits 0-1) | up-left available (bit 2)                 */
-    uint16_t reserved;
+    uint16_t avail_cu;        /* Main tool_htdf: the AVAIL_* bits xevd_get_avail_intra yields for this CU when it is
+                                 reconstructed (src_base/xevd_util.c:689-745; bit numbers xevd_def.h:237-247: UP 0,
+                                 LE 1, RI 3, UP_LE 5, UP_RI 6, LO_LE 7, LO_RI 8); 0 when the tool is off               */
     uint32_t coef_off;        /* offset (in int16 units) of this CU's coefficients inside the
                                  coefficient stream: [Y w*h][Cb w*h/4][Cr w*h/4], CU-raster;
                                  planes whose cbf bits are all 0 are absent (no bytes); every
@@ -215,7 +217,8 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
                        const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
                        const void *d_ext, int n_ext,
                        const void *d_coef, size_t n_coef, int has_intra, int max_cu_per_ctu);
-/* max_cu_per_ctu: upper bound of ctu_first[k+1]-ctu_first[k] (sizes on-chip work lists); 0 = unknown (worst case) */
+/* has_intra: non-zero when the wavefront pass is needed: the picture has intra or IBC CUs, or tool_htdf is on and some CU has a
+ * luma residual.  max_cu_per_ctu: upper bound of ctu_first[k+1]-ctu_first[k] (sizes on-chip work lists); 0 = unknown (worst case) */
 
 /* ---- picture-wide in-loop filters ------------------------------------------------------------------ */
 /* edge flags, one byte per SCU */

@@ -82,6 +82,10 @@ void orc_intra_neighbours_main(const pel *rec, int s, int w, int h, int unit, ui
 void orc_ipred_main(const pel *left, const pel *up, const pel *right, int avail_lr, pel *dst, int ipm, int w, int h, int bit_depth);
 void orc_ipred_uv_main(const pel *left, const pel *up, const pel *right, int avail_lr, pel *dst, int ipm_c, int ipm, int w, int h, int bit_depth);
 
+/* orc_htdf.c */
+void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth);
+const uint8_t *orc_htdf_table(int idx);
+
 /* orc_alf.c */
 int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
 

@@ -131,6 +131,9 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         /* the reference passes the LUMA bit depth to all three planes (xevd_recon.c:70-91) */
         put_block_tu(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
         put_block_tu(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
+        /* Main tool_htdf (src_main/xevdm.c:1381-1391): luma post-filter of CUs with a luma residual and of every intra CU, slice QP */
+        if (prm->tool_htdf && cu->mode != XB200_MODE_IBC && (has_y || cu->mode == XB200_MODE_INTRA) && (cu->flags & XB200_CUF_LUMA))
+            orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma);
         publish_maps(prm, cur, cu);
     }
     free(pred); free(res);

@@ -254,11 +254,20 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         } else { free(s); free(map_scu); free(map_tidx); return XB200_ERR_UNSUPPORTED; }
         for (l = 0; l < (h >> 2); l++)
             for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
-        if (prm->tool_ats) {
+        if (prm->tool_ats || prm->tool_htdf) {
             /* Main profile: xevdm_recon_yuv (src_main/xevdm_recon.c:128-151), which places the ats_inter TU */
             xevdm_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, ats_inter_info, prm->bit_depth_luma);
             xevdm_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
             xevdm_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
+            if (cu->mode != XB200_MODE_IBC && prm->tool_htdf && (is_coef[Y_C] || cu->mode == XB200_MODE_INTRA)) {
+                /* src_main/xevdm.c:1381-1391; the COD bits of this CU are cleared around the call as they are in the decoder */
+                u16 av;
+                for (l = 0; l < (h >> 2); l++) for (i = 0; i < (w >> 2); i++) MCU_CLR_COD(map_scu[scup + l * cur->w_scu + i]);
+                av = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
+                xevdm_htdf(cur->y + cu->y * cur->s_l + cu->x, prm->slice_qp, w, h, cur->s_l, cu->mode == XB200_MODE_INTRA,
+                           cur->y + cu->y * cur->s_l + cu->x, cur->s_l, av, scup, cur->w_scu, cur->h_scu, map_scu, 0, prm->bit_depth_luma);
+                for (l = 0; l < (h >> 2); l++) for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
+            }
             continue;
         }
         /* xevd_recon_yuv (src_base/xevd_recon.c:70-91) */

@@ -226,6 +226,24 @@ def test_ibc(ctx, oracle, variant, kw, bd, intra_frac):
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
 
 
+@pytest.mark.parametrize("variant,kw,bd,intra_frac,qp", [("C", {}, 10, 0.3, 32), ("C", dict(log2_ctu=7), 10, 0.3, 45), ("C", dict(log2_ctu=5), 8, 0.5, 22),
+                                                         ("B", {}, 10, 0.0, 37), ("A", dict(log2_cu=3), 10, 0.2, 27), ("B", {}, 10, 1.0, 17), ("B", {}, 12, 1.0, 51)])
+def test_htdf(ctx, oracle, variant, kw, bd, intra_frac, qp):
+    """Main tool_htdf: in-order luma post-filter in the wavefront kernel (intra CUs and inter CUs with a luma residual)"""
+    from tests.test_oracle_vs_ref import htdf_inputs
+    w, h, prm, cl, refs = htdf_inputs(variant, kw, bd, intra_frac, qp)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
 def test_intra_1080p_wavefront(ctx, oracle):
     """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
     w, h, bd = 1920, 1080, 10

@@ -302,3 +302,33 @@ def test_recon_frame_ibc(oracle, reference, variant, kw, bd, intra_frac):
     b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+HTDF_CASES = [("C", {}, 10, 0.3, 32), ("C", dict(log2_ctu=7), 10, 0.3, 45), ("C", dict(log2_ctu=5), 8, 0.5, 22), ("B", {}, 10, 0.0, 37),
+              ("A", dict(log2_cu=3), 10, 0.2, 27), ("B", {}, 10, 1.0, 17), ("B", {}, 12, 1.0, 51)]
+
+
+def htdf_inputs(variant, kw, bd, intra_frac, qp):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=61, n_refs=2, coded_frac=0.7, ats_inter_frac=0.3, **kw)
+    prm.tool_eipd = prm.tool_ibc = prm.tool_htdf = 1
+    prm.slice_qp = qp
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True, ats_intra_frac=0.5, ibc_frac=0.3)
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    return w, h, prm, cl, synth.make_refs(w, h, bd, 2, seed=9)
+
+
+@pytest.mark.parametrize("variant,kw,bd,intra_frac,qp", HTDF_CASES)
+def test_recon_frame_htdf(oracle, reference, variant, kw, bd, intra_frac, qp):
+    """Main tool_htdf: the in-loop Hadamard-domain luma filter after every intra CU and every CU with a luma residual, all five QP
+    tables, the size / QP skip rules, ring samples from whichever neighbours xevd_get_avail_intra reports (right ones under SUCO)"""
+    w, h, prm, cl, refs = htdf_inputs(variant, kw, bd, intra_frac, qp)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    if qp > 17:
+        prm.tool_htdf = 0
+        c = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        assert (a.y != c.y).sum() > 1000, "test picture does not exercise the filter"

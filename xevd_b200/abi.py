@@ -33,7 +33,7 @@ CU_DTYPE = np.dtype(
         ("refi", "i1", (2,)),
         ("cbf", "<u2"),
         ("mv", "<i2", (2, 2)),
-        ("ats", "u1"), ("avail", "u1"), ("reserved", "<u2"),
+        ("ats", "u1"), ("avail", "u1"), ("avail_cu", "<u2"),
         ("coef_off", "<u4"),
     ],
     align=False,

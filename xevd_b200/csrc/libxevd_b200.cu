@@ -389,6 +389,8 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.iqt = prm->tool_iqt ? 1 : 0;
     a.eipd = prm->tool_eipd ? 1 : 0;
     a.ats = prm->tool_ats ? 1 : 0;
+    a.htdf = prm->tool_htdf ? 1 : 0;
+    a.slice_qp = prm->slice_qp;
     a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     return XB200_OK;
@@ -490,7 +492,7 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     int has_intra = 0, max_cu = 0, any_l1 = 0;
     for (int i = 0; i < n_cu; i++) {
         const bool intra = xb_wavefront_mode(cus[i].mode);
-        has_intra |= intra;
+        has_intra |= intra || (prm->tool_htdf && (cus[i].cbf & 15));       // HTDF-filtered inter CUs are finished by the wavefront kernel too
         if (intra) continue;
         any_l1 |= cus[i].refi[1] >= 0;
         // a reference index outside the lists the caller supplied would dereference a missing picture on the device

@@ -271,6 +271,84 @@ __device__ void intra_pred_recon_main(pel *rec, int s, int w, int h, int lw, int
     }
 }
 
+// ---- HTDF (Main, tool_htdf): xevdm_htdf (src_main/xevdm_recon.c:153-385) ------------------------------------------------------------
+// 2x2 Hadamard windows slide over the CU plus a one-sample ring (neighbours where xevd_get_avail_intra says so, else replicated;
+// the row below is always replicated); the three AC terms are shrunk through a table chosen by the slice QP; every sample becomes
+// the rounded average of its four windows.  All windows see unfiltered input (the reference overwrites a sample only after its last
+// window), so the filter is a per-sample gather.
+__constant__ uint8_t c_htdf_thr_log2[5] = {6, 7, 7, 8, 8};
+__constant__ uint8_t c_htdf_tbl[5][16] = {
+    {0, 0, 2, 6, 10, 14, 19, 23, 28, 32, 36, 41, 45, 49, 53, 57},       {0, 0, 5, 12, 20, 29, 38, 47, 56, 65, 73, 82, 90, 98, 107, 115},
+    {0, 0, 1, 4, 9, 16, 24, 32, 41, 50, 59, 68, 77, 86, 94, 103},       {0, 0, 3, 9, 19, 32, 47, 64, 81, 99, 117, 135, 154, 179, 205, 230},
+    {0, 0, 0, 2, 6, 11, 18, 27, 38, 51, 64, 96, 128, 160, 192, 224}};
+
+__device__ __forceinline__ int htdf_shrink(int z, const uint8_t *tbl, int thr, int shift, int round)
+{
+    const int av = abs(z);
+    if (av >= thr) return z;
+    const int v = tbl[((av + round) & thr) >> shift];
+    return z < 0 ? -v : v;
+}
+// output `which` (0..3 = (0,0) (0,1) (1,0) (1,1)) of the window whose top-left sample is t[0]
+__device__ __forceinline__ int htdf_window(const int16_t *t, int s, int which, const uint8_t *tbl, int thr, int shift, int round)
+{
+    const int x0 = t[0], x1 = t[1], x2 = t[s], x3 = t[s + 1];
+    const int y0 = x0 + x2, y1 = x1 + x3, y2 = x0 - x2, y3 = x1 - x3;
+    const int z0 = y0 + y1;
+    const int z1 = htdf_shrink(y0 - y1, tbl, thr, shift, round), z2 = htdf_shrink(y2 + y3, tbl, thr, shift, round), z3 = htdf_shrink(y2 - y3, tbl, thr, shift, round);
+    const int i0 = z0 + z2, i1 = z1 + z3, i2 = z0 - z2, i3 = z1 - z3;
+    return (which == 0 ? i0 + i1 : (which == 1 ? i0 - i1 : (which == 2 ? i2 + i3 : i2 - i3))) >> 2;
+}
+
+// true when the CU is filtered (xevdm.c:1383 + xevdm_htdf_skip_condition, xevdm_recon.c:271-297); qp receives the table QP
+__device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_CU &cu, int &qp)
+{
+    if (!a.htdf || cu.mode == XB200_MODE_IBC || !(cu.flags & XB200_CUF_LUMA)) return false;
+    const bool intra = cu.mode == XB200_MODE_INTRA;
+    if (!intra && !(cu.cbf & 15)) return false;
+    qp = a.slice_qp;
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+    if (qp <= 17 || w * h < 64 || max(w, h) >= 128) return false;
+    if (!intra) return min(w, h) < 32;
+    if (w == h && w >= 32) qp -= 8;
+    return true;
+}
+
+__device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, int qp, int16_t *t, int tid, int nthreads)
+{
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h, we = w + 2, he = h + 2, s = a.s_l;
+    pel *rec = a.cur.y + (size_t)cu.y * s + cu.x;
+    const int av = cu.avail_cu;
+    const bool up = av & 1, le = (av >> 1) & 1, ri = (av >> 3) & 1;
+    for (int idx = tid; idx < we * he; idx += nthreads) {
+        const int r = idx / we, c = idx - r * we, i = r - 1, j = c - 1;
+        int si = min(max(i, 0), h - 1), sj = min(max(j, 0), w - 1);          // replicated by default
+        if (i >= 0 && i < h) { if (j < 0 && le) sj = -1; else if (j >= w && ri) sj = w; }
+        else if (i < 0) {
+            if (j >= 0 && j < w) { if (up) si = -1; }
+            else if (j < 0) { if ((av >> 5) & 1) { si = -1; sj = -1; } }
+            else if ((av >> 6) & 1) { si = -1; sj = w; }
+        } else if (j < 0) { if ((av >> 7) & 1) { si = h; sj = -1; } }
+        else if (j >= w) { if ((av >> 8) & 1) { si = h; sj = w; } }
+        t[idx] = __ldcg(rec + (ptrdiff_t)si * s + sj);
+    }
+    __syncthreads();
+    int k = (qp - 20 + 4) >> 3;
+    k = min(max(k, 0), 4);
+    const int lg = c_htdf_thr_log2[k], shift = lg - 4, round = (1 << shift) >> 1, thr = (1 << lg) - (1 << shift);
+    const uint8_t *tbl = c_htdf_tbl[k];
+    const int maxv = (1 << a.bd_l) - 1;
+    for (int idx = tid; idx < w * h; idx += nthreads) {
+        const int i = (idx >> cu.log2w) + 1, j = (idx & (w - 1)) + 1;
+        int acc = htdf_window(t + (i - 1) * we + (j - 1), we, 3, tbl, thr, shift, round);
+        acc = (int16_t)(acc + htdf_window(t + (i - 1) * we + j, we, 2, tbl, thr, shift, round));
+        acc = (int16_t)(acc + htdf_window(t + i * we + (j - 1), we, 1, tbl, thr, shift, round));
+        acc = (int16_t)(acc + htdf_window(t + i * we + j, we, 0, tbl, thr, shift, round));
+        rec[(size_t)(i - 1) * s + (j - 1)] = (pel)xb_clip3(0, maxv, (acc + 2) >> 2);
+    }
+    __syncthreads();
+}
+
 struct IntraSync {
     int *ticket;        // next CTU to hand out
     int *done;          // [n_ctu] 1 when every CU of the CTU is final
@@ -296,7 +374,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 
     // any intra CU here?  (uniform: every thread scans the same descriptors through L1)
     bool any = false;
-    for (int i = cu0 + tid; i < cu1; i += kIntraThreads) any |= xb_wavefront_mode(a.cus[i].mode);
+    for (int i = cu0 + tid; i < cu1; i += kIntraThreads) { int q; any |= xb_wavefront_mode(a.cus[i].mode) || htdf_applies(a, a.cus[i], q); }
     any = __syncthreads_or(any);
     if (any) {
         if (tid < 4) {
@@ -311,7 +389,13 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         __syncthreads();
         for (int i = cu0; i < cu1; i++) {
             const XB200_CU cu = a.cus[i];
-            if (!xb_wavefront_mode(cu.mode)) continue;              // uniform
+            int hq = 0;
+            const bool do_htdf = htdf_applies(a, cu, hq);            // uniform
+            if (!xb_wavefront_mode(cu.mode)) {
+                // inter CU: reconstructed by the inter kernel; only the in-order HTDF pass is left
+                if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+                continue;
+            }
             const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
             uint32_t ei;
             memcpy(&ei, cu.mv[1], 4);
@@ -371,6 +455,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                                           pl ? pmax_c : maxv, maxv, s_scr4, tid, kIntraThreads);
                     __syncthreads();
                 }
+                if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
                 continue;
             }
             intra_gather(a.cur.y + (size_t)cu.y * a.s_l + cu.x, a.s_l, w, h, 4, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[0], le[0], tid, kIntraThreads);
@@ -388,6 +473,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             intra_pred_recon(a.cur.v + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, cu.log2w - 1, cu.refi[1], up[2], le[2], res[2],
                              (cu.cbf & 0xf00) != 0, maxv, &s_scratch, tid, kIntraThreads);
             __syncthreads();         // the next CU may read these samples (global writes are visible block-wide after the barrier)
+            if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
         }
     }
     __threadfence();

@@ -383,6 +383,34 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     return cl
 
 
+def derive_avail_cu(cl: CuList):
+    """XB200_CU.avail_cu for every CU: what xevd_get_avail_intra (src_base/xevd_util.c:689-745) returns when the CU is reached in
+    decoding order (one tile, one slice) - consumed by the HTDF ring fetch (src_main/xevdm_recon.c:299-385)"""
+    w_scu, h_scu = (cl.w + 3) >> 2, (cl.h + 3) >> 2
+    cod = np.zeros((h_scu, w_scu), bool)
+    for cu in cl.cus:
+        xs, ys = int(cu["x"]) >> 2, int(cu["y"]) >> 2
+        nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+        a = 0
+        if xs > 0 and cod[ys, xs - 1]:
+            a |= 1 << 1                                                           # AVAIL_LE
+            if ys + nh + nw - 1 < h_scu and cod[ys + nh + nw - 1, xs - 1]:
+                a |= 1 << 7                                                       # AVAIL_LO_LE
+        if ys > 0:
+            a |= (1 << 0) | (1 << 9)                                              # AVAIL_UP, AVAIL_RI_UP (single tile)
+            if xs > 0 and cod[ys - 1, xs - 1]:
+                a |= 1 << 5                                                       # AVAIL_UP_LE
+            if xs + nw < w_scu and cod[ys - 1, xs + nw]:
+                a |= 1 << 6                                                       # AVAIL_UP_RI
+        if xs + nw < w_scu and cod[ys, xs + nw]:
+            a |= 1 << 3                                                           # AVAIL_RI
+            if ys + nh + nw - 1 < h_scu and cod[ys + nh + nw - 1, xs + nw]:
+                a |= 1 << 8                                                       # AVAIL_LO_RI
+        cu["avail_cu"] = a
+        cod[ys:ys + nh, xs:xs + nw] = True
+    return cl
+
+
 def make_alf_params(rng, enable=(1, 1, 1)):
     """random but well-formed ALF filters: every filter sums to 512 (unity gain at shift 9), side taps within the ranges
     alf_recon_coef enforces (src_main/xevdm_alf.c:751,763)"""
