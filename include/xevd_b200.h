@@ -165,6 +165,9 @@ typedef struct XB200_PIC_INFO {
     int32_t w_scu, h_scu;
     int32_t poc;
     void   *dev_map_edge;         /* uint8[w_scu*h_scu], XB200_EDGE_* flags written by xb200_recon_frame      */
+    void   *dev_map_unrefined_mv; /* int16[w_scu*h_scu][2][2]: vectors before DMVR refinement (mctx->map_unrefined_mv,
+                                     read by spatial MV prediction and by deblocking); dev_map_mv holds the refined ones
+                                     (read by temporal MV prediction)                                */
 } XB200_PIC_INFO;
 
 /* ---- context ------------------------------------------------------------------------------------- */
@@ -198,6 +201,7 @@ int  xb200_pic_download(xb200_ctx *ctx, xb200_pic *pic,
 /* full padded planes (incl. borders), for checking xb200_pad against xevd_picbuf_expand */
 int  xb200_pic_download_padded(xb200_ctx *ctx, xb200_pic *pic, xb200_pel *y, xb200_pel *u, xb200_pel *v);
 int  xb200_pic_download_maps(xb200_ctx *ctx, xb200_pic *pic, int16_t *map_mv, int8_t *map_refi, uint32_t *map_scu);
+int  xb200_pic_download_unrefined_mv(xb200_ctx *ctx, xb200_pic *pic, int16_t *map_unrefined_mv);
 int  xb200_pic_download_edge_map(xb200_ctx *ctx, xb200_pic *pic, uint8_t *map_edge);
 
 /* ---- per-picture reconstruction (xevd_ctu_row_rec_mt) ---------------------------------------------- */

@@ -33,6 +33,7 @@ typedef struct ORC_PIC {
     int8_t   *map_refi;      /* [h_scu*w_scu][2]                                              */
     uint32_t *map_scu;       /* [h_scu*w_scu]                                                 */
     int  w_scu, h_scu;
+    int16_t  *map_unrefined_mv; /* Main: the vectors before DMVR refinement (mctx->map_unrefined_mv); map_mv holds the refined ones */
 } ORC_PIC;
 
 static inline int orc_clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -51,12 +52,20 @@ void orc_mc_luma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x, 
                  pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables);
 void orc_mc_chroma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x, int ori_mv_y,
                    pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables);
+void orc_interp(const pel *ref, int s_ref, int ix, int iy, const int16_t *cx, const int16_t *cy,
+                int fx, int fy, int ntap, pel *pred, int s_pred, int w, int h, int bd);
 void orc_mv_clip(int x, int y, int pic_w, int pic_h, int w, int h, const int8_t refi[2],
                  const int16_t mv[2][2], int16_t mv_t[2][2]);
 /* full inter prediction of one CU: pred[c] is w*h (luma) / (w/2)*(h/2) (chroma), CU raster */
 void orc_inter_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const int8_t refi[2],
                     const int16_t mv[2][2], const ORC_PIC *const *refs_l0, const ORC_PIC *const *refs_l1,
                     pel *pred_y, pel *pred_u, pel *pred_v);
+
+/* orc_dmvr.c: decoder-side motion vector refinement (Main, tool_dmvr).  Returns 1 and fills the two per-list predictions of all
+ * three planes (pred[l][c], CU raster) plus the refined quarter-pel vectors per SCU (dmvr_mv[scu][l][xy], CU-raster SCU order) when
+ * the CU is refined; returns 0 (nothing written) when xevdm_mc's conditions rule DMVR out. */
+int orc_dmvr_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const int8_t refi[2], const int16_t mv[2][2],
+                  const ORC_PIC *const *refs_l0, const ORC_PIC *const *refs_l1, pel *pred[2][3], int16_t *dmvr_mv);
 
 /* orc_itdq.c */
 void orc_dequant(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);

@@ -15,6 +15,9 @@
 #include <stdlib.h>
 #include "orc_common.h"
 
+/* deblocking compares the vectors BEFORE DMVR refinement (map_unrefined_mv, src_main/xevdm.c:2009-2041) */
+#define DF_MV(p) ((p)->map_unrefined_mv ? (p)->map_unrefined_mv : (p)->map_mv)
+
 /* xevd_tbl_df_st (src_base/xevd_tbl.c:306-324) */
 static const uint8_t k_df_st[4][52] = {
     {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 12, 12, 12, 12, 12},
@@ -93,7 +96,7 @@ static void edge_segment(DfCtx *c, int cur, int nb, int x, int y, int vertical)
     ORC_PIC *p = c->pic;
     const int bdl = c->prm->bit_depth_luma, bdc = c->prm->bit_depth_chroma;
     const int cls = strength_class(p->map_scu[cur], p->map_scu[nb], p->map_refi + 2 * cur, p->map_refi + 2 * nb,
-                                   p->map_mv + 4 * cur, p->map_mv + 4 * nb);
+                                   DF_MV(p) + 4 * cur, DF_MV(p) + 4 * nb);
     const int qp = (p->map_scu[cur] >> 16) & 0x7f;                       /* QP of the CURRENT side only (T7) */
     const int st = st_lookup(cls, qp) << (bdl - 8);
     if (st) {
@@ -191,7 +194,7 @@ static int addb_bs(const AddbCtx *c, int cur, int nb, int x0, int y0, int x1, in
     if (((m0 >> 26) & 1) || ((m1 >> 26) & 1)) return 3;
     if (((m0 >> 24) & 1) || ((m1 >> 24) & 1) || c->ats[cur] || c->ats[nb]) return 2;       /* ats_present, xevdm_df.c:415,902-906 */
     const int8_t *r0 = p->map_refi + 2 * cur, *r1 = p->map_refi + 2 * nb;
-    const int16_t *v0 = p->map_mv + 4 * cur, *v1 = p->map_mv + 4 * nb;
+    const int16_t *v0 = DF_MV(p) + 4 * cur, *v1 = DF_MV(p) + 4 * nb;
     int pa[2], pb[2], a[2][2], b[2][2];
     for (int l = 0; l < 2; l++) {
         pa[l] = r0[l] >= 0 ? c->ref_id[l][r0[l]] : -1;          /* NULL picture */

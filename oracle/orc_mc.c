@@ -19,8 +19,8 @@ static int frac_c(int v) { return (v | (v >> 1) | (v >> 2) | (v >> 3) | (v >> 4)
  *   2-D variant : H pass (sum >> min(4, bd-8)) kept as s16, then
  *                 V pass (sum + 2^(s2-1)) >> s2, s2 = max(8, 20-bd), clipped   (xevd_mc.c:239-284)
  */
-static void interp(const pel *ref, int s_ref, int ix, int iy, const int16_t *cx, const int16_t *cy,
-                   int fx, int fy, int ntap, pel *pred, int s_pred, int w, int h, int bd)
+void orc_interp(const pel *ref, int s_ref, int ix, int iy, const int16_t *cx, const int16_t *cy,
+                int fx, int fy, int ntap, pel *pred, int s_pred, int w, int h, int bd)
 {
     const int half = ntap / 2 - 1;        /* taps start `half` samples before the integer position */
     const int maxv = (1 << bd) - 1;
@@ -72,7 +72,7 @@ void orc_mc_luma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x, 
                  pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables)
 {
     const int16_t *taps = orc_mc_luma_taps(main_tables);
-    interp(ref, s_ref, gmv_x >> 4, gmv_y >> 4, taps + 8 * (gmv_x & 15), taps + 8 * (gmv_y & 15),
+    orc_interp(ref, s_ref, gmv_x >> 4, gmv_y >> 4, taps + 8 * (gmv_x & 15), taps + 8 * (gmv_y & 15),
            frac_l(ori_mv_x), frac_l(ori_mv_y), 8, pred, s_pred, w, h, bit_depth);
 }
 
@@ -81,7 +81,7 @@ void orc_mc_chroma(const pel *ref, int s_ref, int gmv_x, int gmv_y, int ori_mv_x
                    pel *pred, int s_pred, int w, int h, int bit_depth, int main_tables)
 {
     const int16_t *taps = orc_mc_chroma_taps(main_tables);
-    interp(ref, s_ref, gmv_x >> 5, gmv_y >> 5, taps + 4 * (gmv_x & 31), taps + 4 * (gmv_y & 31),
+    orc_interp(ref, s_ref, gmv_x >> 5, gmv_y >> 5, taps + 4 * (gmv_x & 31), taps + 4 * (gmv_y & 31),
            frac_c(ori_mv_x), frac_c(ori_mv_y), 4, pred, s_pred, w, h, bit_depth);
 }
 

@@ -27,7 +27,7 @@ static void put_block(pel *rec, int s_rec, const pel *pred, const int16_t *res, 
     put_block_tu(rec, s_rec, pred, res, w, h, bd, 0, 0, w, h);
 }
 
-static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu)
+static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu, const int16_t *dmvr_mv)
 {
     const int x0 = cu->x >> 2, y0 = cu->y >> 2, nw = 1 << (cu->log2w - 2), nh = 1 << (cu->log2h - 2);
     const int intra = cu->mode == XB200_MODE_INTRA;
@@ -46,11 +46,17 @@ static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *
             }
             if (cbfl) m |= 1u << 24;
             if (cu->flags & XB200_CUF_SKIP) m |= 1u << 23;
+            if (dmvr_mv) m |= 1u << 25;                                   /* MCU_SET_DMVRF (xevdm_def.h:318) */
             cur->map_scu[p] = m;
             for (int l = 0; l < 2; l++) {
                 cur->map_refi[p * 2 + l] = (intra || cu->mode == XB200_MODE_IBC) ? -1 : cu->refi[l];
-                cur->map_mv[(p * 2 + l) * 2 + 0] = intra ? 0 : cu->mv[l][0];
-                cur->map_mv[(p * 2 + l) * 2 + 1] = intra ? 0 : cu->mv[l][1];
+                for (int d = 0; d < 2; d++) {
+                    /* xevdm_set_dec_info (xevdm_util.c:4313-4340): map_mv gets the refined vectors of a DMVR CU, map_unrefined_mv the
+                     * signalled ones (spatial prediction and deblocking read the latter) */
+                    const int16_t v = intra ? 0 : cu->mv[l][d];
+                    cur->map_mv[(p * 2 + l) * 2 + d] = dmvr_mv ? dmvr_mv[((j * nw + i) * 2 + l) * 2 + d] : v;
+                    if (cur->map_unrefined_mv) cur->map_unrefined_mv[(p * 2 + l) * 2 + d] = v;
+                }
             }
         }
 }
@@ -61,6 +67,7 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
 {
     pel     *pred = (pel *)malloc(3 * 128 * 128 * sizeof(pel));
     int16_t *res  = (int16_t *)malloc(3 * 128 * 128 * sizeof(int16_t));
+    int16_t *dmvr_mv = (int16_t *)malloc(32 * 32 * 4 * sizeof(int16_t));
     (void)ext; (void)n_l0; (void)n_l1;
     for (int n = 0; n < n_cu; n++) {
         const XB200_CU *cu = &cus[n];
@@ -79,7 +86,20 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         if (has_v) { memcpy(rv, c, sizeof(int16_t) * (tw * th / 4)); }
         orc_itdq_cu(prm, cu, ry, ru, rv);
 
-        if (cu->mode == XB200_MODE_INTER) {
+        int dmvr = 0;
+        if (cu->mode == XB200_MODE_INTER && prm->tool_dmvr && (cu->flags & XB200_CUF_DMVR)) {
+            /* xevdm_mc with apply_DMVR (src_main/xevdm_mc.c:1860-2038): both list predictions come from the refinement, then average */
+            pel *p1 = (pel *)malloc(sizeof(pel) * (w * h + 2 * cw * ch));
+            pel *pp[2][3] = { { py, pu, pv }, { p1, p1 + w * h, p1 + w * h + cw * ch } };
+            dmvr = orc_dmvr_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, pp, dmvr_mv);
+            if (dmvr) {
+                for (int i = 0; i < w * h; i++) py[i] = (pel)((py[i] + pp[1][0][i] + 1) >> 1);
+                for (int i = 0; i < cw * ch; i++) { pu[i] = (pel)((pu[i] + pp[1][1][i] + 1) >> 1); pv[i] = (pel)((pv[i] + pp[1][2][i] + 1) >> 1); }
+            }
+            free(p1);
+        }
+        if (dmvr) {
+        } else if (cu->mode == XB200_MODE_INTER) {
             orc_inter_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, py, pu, pv);
         } else if (cu->mode == XB200_MODE_IBC) {
             /* xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the current picture; chroma vector = luma >> 1 */
@@ -124,7 +144,7 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                 orc_ipred_uv_main(nb_le + 1, nb_up + 1, nb_ri + 1, lr, k ? pv : pu, cu->refi[1], cu->refi[0], cw, ch, prm->bit_depth_chroma);
             }
         } else {
-            free(pred); free(res);
+            free(pred); free(res); free(dmvr_mv);
             return XB200_ERR_UNSUPPORTED;
         }
         put_block_tu(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma, txo, tyo, tw, th);
@@ -134,9 +154,9 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         /* Main tool_htdf (src_main/xevdm.c:1381-1391): luma post-filter of CUs with a luma residual and of every intra CU, slice QP */
         if (prm->tool_htdf && cu->mode != XB200_MODE_IBC && (has_y || cu->mode == XB200_MODE_INTRA) && (cu->flags & XB200_CUF_LUMA))
             orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma);
-        publish_maps(prm, cur, cu);
+        publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL);
     }
-    free(pred); free(res);
+    free(pred); free(res); free(dmvr_mv);
     return XB200_OK;
 }
 

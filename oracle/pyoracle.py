@@ -30,6 +30,7 @@ class OrcPic(C.Structure):
         ("pad_l", C.c_int), ("pad_c", C.c_int), ("poc", C.c_int),
         ("map_mv", C.c_void_p), ("map_refi", C.c_void_p), ("map_scu", C.c_void_p),
         ("w_scu", C.c_int), ("h_scu", C.c_int),
+        ("map_unrefined_mv", C.c_void_p),
     ]
 
 
@@ -41,6 +42,7 @@ def orc_pic(p: HostPicture) -> OrcPic:
     o.pad_l, o.pad_c, o.poc = p.pad_l, p.pad_c, p.poc
     o.map_mv, o.map_refi, o.map_scu = p.map_mv.ctypes.data, p.map_refi.ctypes.data, p.map_scu.ctypes.data
     o.w_scu, o.h_scu = p.w_scu, p.h_scu
+    o.map_unrefined_mv = p.map_unrefined_mv.ctypes.data
     return o
 
 

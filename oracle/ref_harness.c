@@ -246,6 +246,25 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
             xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
             xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
+        } else if (cu->mode == XB200_MODE_INTER && prm->tool_dmvr) {
+            /* Main xevdm_mc with the DMVR scratch buffers of XEVDM_CORE (src_main/xevdm_def.h:505-530); it leaves the averaged
+             * prediction in pred[0], the refined vectors per SCU in dmvr_mv and restores mv[] */
+            static pel tmpl[MAX_CU_DIM];
+            static pel interp[REFP_NUM][(MAX_CU_SIZE + ((DMVR_NEW_VERSION_ITER_COUNT + 1) * REF_PRED_EXTENTION_PEL_COUNT)) * (MAX_CU_SIZE + ((DMVR_NEW_VERSION_ITER_COUNT + 1) * REF_PRED_EXTENTION_PEL_COUNT))];
+            static pel halfp[REFP_NUM][(MAX_CU_SIZE + 1) * (MAX_CU_SIZE + 1)];
+            static pel padbuf[REFP_NUM][N_C][PAD_BUFFER_STRIDE * PAD_BUFFER_STRIDE];
+            static s16 dmvr_mv[MAX_CU_CNT_IN_LCU][REFP_NUM][MV_D];
+            u8 dmvr_flag = 0;
+            xevdm_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, mv, refp, s->pred, prm->poc, tmpl, interp, halfp, (cu->flags & XB200_CUF_DMVR) ? 1 : 0,
+                     padbuf, &dmvr_flag, dmvr_mv, prm->tool_admvp, prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+            if (cur->map_mv)          /* what xevdm_set_dec_info would publish: refined vectors for DMVR CUs */
+                for (l = 0; l < (h >> 2); l++)
+                    for (i = 0; i < (w >> 2); i++) {
+                        s16 *o = cur->map_mv + (scup + l * cur->w_scu + i) * 4;
+                        const int k = l * (w >> 2) + i;
+                        o[0] = dmvr_flag ? dmvr_mv[k][0][0] : mv[0][0]; o[1] = dmvr_flag ? dmvr_mv[k][0][1] : mv[0][1];
+                        o[2] = dmvr_flag ? dmvr_mv[k][1][0] : mv[1][0]; o[3] = dmvr_flag ? dmvr_mv[k][1][1] : mv[1][1];
+                    }
         } else if (cu->mode == XB200_MODE_INTER) {
             select_mc_tables(prm->tool_admvp ? 1 : 0);
             /* Baseline xevd_mc (src_base/xevd_mc.c:469); identical to xevdm_mc with DMVR off apart from the table switch */
@@ -314,7 +333,7 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     ctx->map_scu = map_scu;
     ctx->map_refi = (s8(*)[REFP_NUM])pic->map_refi;
     ctx->map_mv = (s16(*)[REFP_NUM][MV_D])pic->map_mv;
-    m->map_unrefined_mv = ctx->map_mv;
+    m->map_unrefined_mv = pic->map_unrefined_mv ? (s16(*)[REFP_NUM][MV_D])pic->map_unrefined_mv : ctx->map_mv;
     ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu; ctx->w = pic->w_l; ctx->h = pic->h_l;
     ctx->log2_max_cuwh = prm->log2_ctu;
     ctx->map_tidx = (u8 *)calloc(f_scu, 1);

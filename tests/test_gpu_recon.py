@@ -244,6 +244,25 @@ def test_htdf(ctx, oracle, variant, kw, bd, intra_frac, qp):
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
 
 
+@pytest.mark.parametrize("variant,kw,bd,noise", [("C", {}, 10, 3), ("C", dict(log2_ctu=7), 10, 0), ("C", dict(log2_ctu=5), 8, 2), ("B", {}, 10, 40),
+                                                 ("A", dict(log2_cu=3), 10, 1), ("B", dict(main_mv=True), 12, 6), ("B", dict(iqt=True), 10, 2)])
+def test_dmvr(ctx, oracle, variant, kw, bd, noise):
+    """Main tool_dmvr: per-sub-PU refinement in the inter kernel; planes, refined map_mv, map_unrefined_mv and the DMVR flag bit"""
+    w, h = 256, 136
+    prm, cl, refs = synth.make_dmvr_case(w, h, bit_depth=bd, variant=variant, seed=71, noise=noise, coded_frac=0.5, **kw)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+    assert np.array_equal(got.map_unrefined_mv, want.map_unrefined_mv)
+
+
 def test_intra_1080p_wavefront(ctx, oracle):
     """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
     w, h, bd = 1920, 1080, 10

@@ -332,3 +332,34 @@ def test_recon_frame_htdf(oracle, reference, variant, kw, bd, intra_frac, qp):
         prm.tool_htdf = 0
         c = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
         assert (a.y != c.y).sum() > 1000, "test picture does not exercise the filter"
+
+
+DMVR_CASES = [("C", {}, 10, 3), ("C", dict(log2_ctu=7), 10, 0), ("C", dict(log2_ctu=5), 8, 2), ("B", {}, 10, 40), ("A", dict(log2_cu=3), 10, 1),
+              ("B", dict(main_mv=True), 12, 6)]
+
+
+@pytest.mark.parametrize("variant,kw,bd,noise", DMVR_CASES)
+def test_recon_frame_dmvr(oracle, reference, variant, kw, bd, noise):
+    """Main tool_dmvr (xevdm_mc / processDMVR): bilinear search planes, mirrored 5-point SAD search over two rounds, early exits,
+    parabolic sub-sample step, final prediction from the replicated-border window, per 16x16 sub-PU; pictures AND the refined
+    vectors published per SCU are compared"""
+    w, h = 256, 136
+    prm, cl, refs = synth.make_dmvr_case(w, h, bit_depth=bd, variant=variant, seed=71, noise=noise, coded_frac=0.5, **kw)
+    cl.validate()
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    refined = ((a.map_scu >> 25) & 1).astype(bool)
+    assert refined.sum() > 100 and (a.map_mv != a.map_unrefined_mv).any(axis=(1, 2)).sum() > 50, "test picture does not exercise DMVR"
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    inter = cl_inter_mask(cl, a.w_scu)
+    assert np.array_equal(a.map_mv[inter], b.map_mv[inter])
+
+
+def cl_inter_mask(cl, w_scu):
+    """SCUs covered by inter CUs (the reference harness publishes vectors only for those)"""
+    m = np.zeros(((cl.h + 3) >> 2, w_scu), bool)
+    for cu in cl.cus:
+        if int(cu["mode"]) == 1:
+            m[int(cu["y"]) >> 2:(int(cu["y"]) >> 2) + (1 << (int(cu["log2h"]) - 2)), int(cu["x"]) >> 2:(int(cu["x"]) >> 2) + (1 << (int(cu["log2w"]) - 2))] = True
+    return m.reshape(-1)

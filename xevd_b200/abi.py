@@ -81,7 +81,7 @@ class PicInfo(C.Structure):
         ("dev_y", C.c_void_p), ("dev_u", C.c_void_p), ("dev_v", C.c_void_p),
         ("dev_map_mv", C.c_void_p), ("dev_map_refi", C.c_void_p), ("dev_map_scu", C.c_void_p),
         ("w_scu", C.c_int32), ("h_scu", C.c_int32), ("poc", C.c_int32),
-        ("dev_map_edge", C.c_void_p),
+        ("dev_map_edge", C.c_void_p), ("dev_map_unrefined_mv", C.c_void_p),
     ]
 
 
@@ -121,6 +121,7 @@ _SIGS = {
     "xb200_pic_download_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_edge_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_pic_download_unrefined_mv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_recon_frame": (
         C.c_int,
         [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

@@ -26,6 +26,7 @@ struct xb200_pic {
     pel *y, *u, *v;              // sample (0,0)
     CUtensorMap *d_tmaps;        // device copy of 3 TMA descriptors (whole padded Y, U, V planes)
     int16_t *map_mv;
+    int16_t *map_unrefined_mv;   // Main: vectors before DMVR refinement (mctx->map_unrefined_mv); equal to map_mv elsewhere
     int8_t *map_refi;
     uint32_t *map_scu;
     uint8_t *map_edge;
@@ -260,7 +261,7 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     const size_t nscu = (size_t)p->w_scu * p->h_scu;
     const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
     const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
-    const size_t total = pix_al + ((nscu * (8 + 4 + 2 + 1) + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
+    const size_t total = pix_al + ((nscu * 24 + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
     if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
         delete p;
@@ -276,7 +277,8 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     p->map_scu = (uint32_t *)(m + nscu * 8);
     p->map_refi = (int8_t *)(m + nscu * 12);
     p->map_edge = (uint8_t *)(m + nscu * 14);
-    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 15 + 255) & ~(size_t)255));
+    p->map_unrefined_mv = (int16_t *)(m + nscu * 16);
+    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 24 + 255) & ~(size_t)255));
     if (make_tensor_maps(c, p) != XB200_OK) {
         cudaFree(p->buf);
         delete p;
@@ -302,7 +304,7 @@ int xb200_pic_info(xb200_pic *p, XB200_PIC_INFO *i)
     i->s_l = p->s_l; i->s_c = p->s_c; i->pad_l = p->pad_l; i->pad_c = p->pad_c;
     i->dev_y = p->y; i->dev_u = p->u; i->dev_v = p->v;
     i->dev_map_mv = p->map_mv; i->dev_map_refi = p->map_refi; i->dev_map_scu = p->map_scu;
-    i->w_scu = p->w_scu; i->h_scu = p->h_scu; i->poc = p->poc; i->dev_map_edge = p->map_edge;
+    i->w_scu = p->w_scu; i->h_scu = p->h_scu; i->poc = p->poc; i->dev_map_edge = p->map_edge; i->dev_map_unrefined_mv = p->map_unrefined_mv;
     return XB200_OK;
 }
 
@@ -350,6 +352,14 @@ int xb200_pic_download_maps(xb200_ctx *c, xb200_pic *p, int16_t *map_mv, int8_t 
     return XB200_OK;
 }
 
+int xb200_pic_download_unrefined_mv(xb200_ctx *c, xb200_pic *p, int16_t *map_unrefined_mv)
+{
+    if (!c || !p || !map_unrefined_mv) return XB200_ERR_INVALID_ARGUMENT;
+    CK(c, cudaMemcpyAsync(map_unrefined_mv, p->map_unrefined_mv, (size_t)p->w_scu * p->h_scu * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return XB200_OK;
+}
+
 int xb200_pic_download_edge_map(xb200_ctx *c, xb200_pic *p, uint8_t *map_edge)
 {
     if (!c || !p || !map_edge) return XB200_ERR_INVALID_ARGUMENT;
@@ -390,8 +400,10 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.eipd = prm->tool_eipd ? 1 : 0;
     a.ats = prm->tool_ats ? 1 : 0;
     a.htdf = prm->tool_htdf ? 1 : 0;
+    a.dmvr = prm->tool_dmvr ? 1 : 0;
+    a.poc = prm->poc;
     a.slice_qp = prm->slice_qp;
-    a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
+    a.map_mv = cur->map_mv; a.map_unrefined_mv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     return XB200_OK;
 }
@@ -413,7 +425,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
-    if (!a.iqt && !a.ats && a.log2_ctu == 6 && !c->force_generic) {
+    if (!a.iqt && !a.ats && !a.dmvr && a.log2_ctu == 6 && !c->force_generic) {
         // throughput kernel (xb_recon2.cuh): Baseline transform path, 64x64 CTUs
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;
@@ -594,6 +606,7 @@ int xb200_pic_upload_maps(xb200_ctx *c, xb200_pic *p, const int16_t *map_mv, con
     if (!c || !p) return XB200_ERR_INVALID_ARGUMENT;
     const size_t n = (size_t)p->w_scu * p->h_scu;
     if (map_mv) CK(c, cudaMemcpyAsync(p->map_mv, map_mv, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (map_mv) CK(c, cudaMemcpyAsync(p->map_unrefined_mv, map_mv, n * 8, cudaMemcpyHostToDevice, c->stream));
     if (map_refi) CK(c, cudaMemcpyAsync(p->map_refi, map_refi, n * 2, cudaMemcpyHostToDevice, c->stream));
     if (map_scu) CK(c, cudaMemcpyAsync(p->map_scu, map_scu, n * 4, cudaMemcpyHostToDevice, c->stream));
     if (map_edge) CK(c, cudaMemcpyAsync(p->map_edge, map_edge, n, cudaMemcpyHostToDevice, c->stream));
@@ -616,7 +629,7 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     a.y = cur->y; a.u = cur->u; a.v = cur->v; a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma; a.qp_u_offset = prm->qp_u_offset; a.qp_v_offset = prm->qp_v_offset;
-    a.map_scu = cur->map_scu; a.map_mv = cur->map_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
+    a.map_scu = cur->map_scu; a.map_mv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;   // bS compares the vectors before DMVR (T7)
     memcpy(a.cq, c->chroma_qp, sizeof(a.cq));
     a.alpha_offset = prm->deblock_alpha_offset; a.beta_offset = prm->deblock_beta_offset; a.log2_ctu = prm->log2_ctu;
     {   // picture identity of every reference index: first position of the same picture in (list 0 ++ list 1)

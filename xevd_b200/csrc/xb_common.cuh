@@ -30,12 +30,13 @@ struct XbFrameArgs {
     int w, h;                   // luma size
     int bd_l, bd_c;
     int log2_ctu, w_ctu, n_ctu;
-    int main_tables, iqt, eipd, ats, htdf, slice_qp;
+    int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc;
     const XB200_CU *cus;
     const uint32_t *ctu_first;
     const int16_t *coef;
     const XB200_CU_EXT *ext;
     int16_t *map_mv;            // [scu][2][2]
+    int16_t *map_unrefined_mv;  // [scu][2][2] vectors before DMVR refinement (equal to map_mv elsewhere)
     int8_t *map_refi;           // [scu][2]
     uint32_t *map_scu;
     uint8_t *map_edge;          // XB200_EDGE_* per SCU: CU boundaries + the 64-sample transform split of larger CUs

@@ -70,9 +70,11 @@ __device__ __forceinline__ void mv_clip(int x, int y, int pic_w, int pic_h, int 
 // starting at (l / tw) * rpl.  Result in pr[0..rpl).  NTAP = 8 (luma) or 4 (chroma).
 //   ref     : sample at integer position of the tile's top-left output (before the -NTAP/2+1 tap offset)
 //   cx, cy  : taps for the horizontal / vertical phase;  fx, fy : variant selected by the UNCLIPPED mv (T3)
-template <int NTAP>
-__device__ __forceinline__ void mc_tile(const pel *__restrict__ ref, int stride, const int16_t *cx, const int16_t *cy,
-                                        bool fx, bool fy, int tw, int th, int rpl, int bd, int16_t *scr, int lane, int (&pr)[8])
+//   ld(r, c): sample of the tile's full (th + NTAP - 1) x (tw + NTAP - 1) window, (0, 0) = HALF samples up-left of the tile's
+//             integer position
+template <int NTAP, typename Ld>
+__device__ __forceinline__ void mc_tile_ld(Ld ld, const int16_t *cx, const int16_t *cy, bool fx, bool fy, int tw, int th, int rpl, int bd,
+                                           int16_t *scr, int lane, int (&pr)[8])
 {
     constexpr int HALF = NTAP / 2 - 1;
     const int maxv = (1 << bd) - 1;
@@ -81,15 +83,15 @@ __device__ __forceinline__ void mc_tile(const pel *__restrict__ ref, int stride,
     if (!fx && !fy) {
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < rpl && active) pr[i] = ref[(r0 + i) * stride + col];
+            if (i < rpl && active) pr[i] = ld(r0 + i + HALF, col + HALF);
         return;
     }
     // stage the reference window: rows [-HALF, th+NTAP-1-HALF) if fy, cols [-HALF, tw+NTAP-1-HALF) if fx
     const int wrows = fy ? th + NTAP - 1 : th, wcols = fx ? tw + NTAP - 1 : tw;
     const int wstride = 24;
-    const pel *wbase = ref - (fy ? HALF * stride : 0) - (fx ? HALF : 0);
+    const int ro = fy ? 0 : HALF, co = fx ? 0 : HALF;
     for (int r = 0; r < wrows; r++)
-        if (lane < wcols) scr[r * wstride + lane] = wbase[r * stride + lane];
+        if (lane < wcols) scr[r * wstride + lane] = (int16_t)ld(r + ro, lane + co);
     __syncwarp();
     int16_t *win = scr;
     int16_t *mid = scr + 23 * wstride;              // horizontal-pass output, row stride tw
@@ -136,6 +138,15 @@ __device__ __forceinline__ void mc_tile(const pel *__restrict__ ref, int stride,
         }
     }
     __syncwarp();
+}
+
+template <int NTAP>
+__device__ __forceinline__ void mc_tile(const pel *__restrict__ ref, int stride, const int16_t *cx, const int16_t *cy,
+                                        bool fx, bool fy, int tw, int th, int rpl, int bd, int16_t *scr, int lane, int (&pr)[8])
+{
+    constexpr int HALF = NTAP / 2 - 1;
+    const pel *base = ref - HALF * stride - HALF;
+    mc_tile_ld<NTAP>([&](int r, int c) { return (int)base[r * stride + c]; }, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, pr);
 }
 
 // prediction of one tile from one or two references, result pr[] (bi-pred averaged): xevd_mc body
@@ -189,6 +200,195 @@ __device__ __forceinline__ void pred_tile(const XbFrameArgs &a, const XB200_CU &
 #pragma unroll
         for (int i = 0; i < 8; i++) pr[i] = p0[i];
     }
+}
+
+// ---- DMVR (Main, tool_dmvr): decoder-side motion vector refinement ----------------------------------------------------------
+// xevdm_mc's DMVR branch (src_main/xevdm_mc.c:1860-2038): processDMVR (:1638-1825) per 16x16 sub-PU - bilinear search planes of both
+// lists (xevdm_bl_mc_l), two rounds of a 5-point mirrored SAD search (xevd_DMVR_refine), parabolic sub-sample step
+// (xevd_SubPelErrorSrfc), final 8/4-tap prediction from the window of the INITIAL vector extended by 2 (1) replicated samples
+// (prefetch_for_mc + final_paddedMC_forDMVR).  One warp per sub-PU.
+
+// does xevdm_mc refine this CU?  (:1893-1911)
+__device__ __forceinline__ bool dmvr_applies(const XbFrameArgs &a, const XB200_CU &cu, int (&start)[2][2])
+{
+    if (!a.dmvr || cu.mode != XB200_MODE_INTER || !(cu.flags & XB200_CUF_DMVR) || cu.refi[0] < 0 || cu.refi[1] < 0) return false;
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+    if (w < 8 || h < 8) return false;
+    const int p0 = a.ref_poc[0][cu.refi[0]], p1 = a.ref_poc[1][cu.refi[1]];
+    const int d0 = a.poc - p0, d1 = a.poc - p1;
+    if (!(d0 * d1 < 0 && abs(d0) == abs(d1))) return false;
+    mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[0][0], cu.mv[0][1], start[0][0], start[0][1]);
+    mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[1][0], cu.mv[1][1], start[1][0], start[1][1]);
+    return !(p0 == p1 && start[0][0] == start[1][0] && start[0][1] == start[1][1]);
+}
+
+// one sample of xevdm_bl_mc_l at 1/16 position (gx, gy) + (j, i)
+__device__ __forceinline__ int dmvr_bilinear(const pel *__restrict__ ref, int s, int gx, int gy, int i, int j, int bd)
+{
+    const int dx = gx & 15, dy = gy & 15, maxv = (1 << bd) - 1;
+    const pel *p = ref + (ptrdiff_t)((gy >> 4) + i) * s + (gx >> 4) + j;
+    const int cx0 = 64 - 4 * dx, cx1 = 4 * dx, cy0 = 64 - 4 * dy, cy1 = 4 * dy;
+    if (!dx && !dy) return p[0];
+    if (!dy) return xb_clip3(0, maxv, (cx0 * p[0] + cx1 * p[1]) >> 6);
+    if (!dx) return xb_clip3(0, maxv, (cy0 * p[0] + cy1 * p[s]) >> 6);
+    const int s1 = min(4, bd - 8), s2 = max(8, 20 - bd);
+    const int t0 = (int16_t)((cx0 * p[0] + cx1 * p[1]) >> s1), t1 = (int16_t)((cx0 * p[s] + cx1 * p[s + 1]) >> s1);
+    return xb_clip3(0, maxv, (cy0 * t0 + cy1 * t1 + (1 << (s2 - 1))) >> s2);
+}
+
+__device__ __forceinline__ int dmvr_div_q7(long long n, long long d)       // div_for_maxq7 (:1338-1375)
+{
+    const bool neg = n < 0;
+    if (neg) n = -n;
+    int q = 0;
+    d <<= 3;
+    if (n >= d) { n -= d; q++; }
+    q <<= 1; d >>= 1;
+    if (n >= d) { n -= d; q++; }
+    q <<= 1;
+    if (n >= (d >> 1)) q++;
+    return neg ? -q : q;
+}
+__device__ __forceinline__ int dmvr_subpel(int c, int minus, int plus)     // one axis of xevd_SubPelErrorSrfc (:1376-1428)
+{
+    const long long num = (long long)((minus - plus) << 4), den = (long long)(minus + plus - (c << 1));
+    if (den == 0) return 0;
+    if (minus != c && plus != c) return dmvr_div_q7(num, den);
+    return minus == c ? -8 : 8;
+}
+// mv_clip_only_one_ref_dmvr (:939-978)
+__device__ __forceinline__ bool dmvr_clip_one(int x, int y, int pic_w, int pic_h, int w, int h, int mvx, int mvy, int &cx, int &cy)
+{
+    const int qx = x << 2, qy = y << 2, qw = w << 2, qh = h << 2;
+    const int lo = -(128 << 2), hx = (pic_w - 1 + 128) << 2, hy = (pic_h - 1 + 128) << 2;
+    bool f = false;
+    cx = mvx; cy = mvy;
+    if (qx + mvx < lo) { f = true; cx = lo - qx; }
+    if (qy + mvy < lo) { f = true; cy = lo - qy; }
+    if (qx + mvx + qw - 4 > hx) { f = true; cx = hx - qx - qw + 4; }
+    if (qy + mvy + qh - 4 > hy) { f = true; cy = hy - qy - qh + 4; }
+    cx = (int16_t)cx; cy = (int16_t)cy;
+    return f;
+}
+
+// SAD of the dx x dy blocks at p0 and p1 (row stride bs) over the warp
+__device__ __forceinline__ int dmvr_sad(const int16_t *p0, const int16_t *p1, int bs, int dx, int dy, int lane)
+{
+    int acc = 0;
+    for (int idx = lane; idx < dx * dy; idx += 32) {
+        const int r = idx / dx, c = idx - r * dx;
+        acc += abs(p0[r * bs + c] - p1[r * bs + c]);
+    }
+    return __reduce_add_sync(0xffffffffu, acc);
+}
+
+// Refinement + prediction + reconstruction of one sub-PU (sx, sy, dx x dy) of a DMVR CU by one warp
+__device__ void dmvr_sub_pu(const XbFrameArgs &a, const XB200_CU &cu, const int (&start)[2][2], int sx, int sy, int dx, int dy,
+                            const int16_t *res_y, const int16_t *res_u, const int16_t *res_v, int rs_l, int rs_c, int ctu_x, int ctu_y,
+                            int16_t *scr, int lane)
+{
+    const int w = 1 << cu.log2w;
+    const pel *ry[2] = {a.ref_y[0][cu.refi[0]], a.ref_y[1][cu.refi[1]]};
+    constexpr int IT = 2;
+    const int bs = dx + 2 * IT;
+    int16_t *bl0 = scr, *bl1 = scr + bs * (dy + 2 * IT);
+    // bilinear search planes of this sub-PU: (dx + 4) x (dy + 4) around the start position of each list
+    for (int l = 0; l < 2; l++) {
+        const int gx = (((cu.x + sx) << 2) + start[l][0] - (IT << 2)) << 2, gy = (((cu.y + sy) << 2) + start[l][1] - (IT << 2)) << 2;
+        int16_t *d = l ? bl1 : bl0;
+        for (int idx = lane; idx < bs * (dy + 2 * IT); idx += 32) {
+            const int i = idx / bs, j = idx - i * bs;
+            d[idx] = (int16_t)dmvr_bilinear(ry[l], a.s_l, gx, gy, i, j, a.bd_l);
+        }
+    }
+    __syncwarp();
+    const int16_t *c0 = bl0 + IT * bs + IT, *c1 = bl1 + IT * bs + IT;
+    int totx = 0, toty = 0, min_cost = 0x7fffffff, centre = 0x7fffffff, cost[5];
+    bool not_zero = true;
+    for (int it = 0; it < IT; it++) {
+        const int16_t *a0 = c0 + totx + toty * bs, *a1 = c1 - (totx + toty * bs);
+#pragma unroll
+        for (int k = 0; k < 5; k++) cost[k] = 0x7fffffff;
+        centre = 0x7fffffff;
+        if (it == 0) min_cost = dmvr_sad(a0, a1, bs, dx, dy, lane);
+        if ((it > 0 && min_cost == 0) || (it == 0 && min_cost < dx * dy)) { not_zero = false; break; }
+        centre = min_cost;
+        int ox[5] = {0, 0, 1, -1, 0}, oy[5] = {1, -1, 0, 0, 0}, bx = 0, by = 0;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            cost[k] = dmvr_sad(a0 + ox[k] + oy[k] * bs, a1 - ox[k] - oy[k] * bs, bs, dx, dy, lane);
+            if (k == 3) { oy[4] = cost[0] <= cost[1] ? 1 : -1; ox[4] = cost[2] <= cost[3] ? 1 : -1; }
+            if (cost[k] < min_cost) { min_cost = cost[k]; bx = ox[k]; by = oy[k]; }
+        }
+        if (bx == 0 && by == 0) break;
+        totx += bx; toty += by;
+    }
+    int ddx = totx << 4, ddy = toty << 4;
+    if (not_zero && min_cost == centre) { ddx += dmvr_subpel(centre, cost[3], cost[2]); ddy += dmvr_subpel(centre, cost[1], cost[0]); }
+    int refined[2][2];
+    refined[0][0] = (start[0][0] << 2) + (int16_t)ddx; refined[0][1] = (start[0][1] << 2) + (int16_t)ddy;
+    refined[1][0] = (start[1][0] << 2) - (int16_t)ddx; refined[1][1] = (start[1][1] << 2) - (int16_t)ddy;
+    __syncwarp();
+    // refined vectors of the sub-PU's SCUs -> map_mv (xevdm_set_dec_info publishes dmvr_mv for DMVR CUs)
+    if (lane < (dx >> 2) * (dy >> 2)) {
+        const int i = lane % (dx >> 2), j = lane / (dx >> 2);
+        const int p = ((cu.y + sy) >> 2) * a.w_scu + ((cu.x + sx) >> 2) + j * a.w_scu + i;
+        int16_t *o = a.map_mv + (size_t)p * 4;
+        o[0] = (int16_t)(refined[0][0] >> 2); o[1] = (int16_t)(refined[0][1] >> 2);
+        o[2] = (int16_t)(refined[1][0] >> 2); o[3] = (int16_t)(refined[1][1] >> 2);
+    }
+    // final prediction: both lists, three planes, from the padded windows
+    const int px = cu.x + sx, py = cu.y + sy;
+    int pl0[3][8], pl1[3][8];
+    const int rpl_l = max(1, (dx * dy) >> 5), rpl_c = max(1, ((dx >> 1) * (dy >> 1)) >> 5);
+    for (int l = 0; l < 2; l++) {
+        int clx, cly;
+        const bool clipped = dmvr_clip_one(px, py, a.w, a.h, dx, dy, refined[l][0] >> 2, refined[l][1] >> 2, clx, cly);
+        const int wgx = ((px << 2) + start[l][0]) << 2, wgy = ((py << 2) + start[l][1]) << 2;       // window of the start vector
+        int gx, gy, dlx, dly, dcx, dcy;
+        if (clipped) {
+            gx = (px << 4) + (clx << 2); gy = (py << 4) + (cly << 2);
+            dlx = (clx >> 2) - (start[l][0] >> 2); dly = (cly >> 2) - (start[l][1] >> 2);
+            dcx = (clx >> 3) - (start[l][0] >> 3); dcy = (cly >> 3) - (start[l][1] >> 3);
+        } else {
+            gx = (px << 4) + refined[l][0]; gy = (py << 4) + refined[l][1];
+            dlx = (refined[l][0] >> 4) - (start[l][0] >> 2); dly = (refined[l][1] >> 4) - (start[l][1] >> 2);
+            dcx = (refined[l][0] >> 5) - (start[l][0] >> 3); dcy = (refined[l][1] >> 5) - (start[l][1] >> 3);
+        }
+        const int ri = cu.refi[l];
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            const pel *plane = pl == 0 ? a.ref_y[l][ri] : (pl == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
+            const int s = pl ? a.s_c : a.s_l;
+            const int wx = pl ? (wgx >> 5) - 1 : (wgx >> 4) - 3, wy = pl ? (wgy >> 5) - 1 : (wgy >> 4) - 3;
+            const int bw = pl ? dx >> 1 : dx, bh = pl ? dy >> 1 : dy;
+            const int ww = bw + (pl ? 3 : 7), wh = bh + (pl ? 3 : 7), ddxi = pl ? dcx : dlx, ddyi = pl ? dcy : dly;
+            auto ld = [&](int r, int c) { return (int)plane[(ptrdiff_t)(wy + min(max(ddyi + r, 0), wh - 1)) * s + wx + min(max(ddxi + c, 0), ww - 1)]; };
+            int (&dst)[8] = l ? pl1[pl] : pl0[pl];
+            if (pl == 0) {
+                const bool fx = (gx & 15) != 0, fy = (gy & 15) != 0;
+                mc_tile_ld<8>(ld, c_mc_l[a.main_tables][gx & 15], c_mc_l[a.main_tables][gy & 15], fx, fy, bw, bh, rpl_l, a.bd_l, scr, lane, dst);
+            } else {
+                const bool fx = (gx & 31) != 0, fy = (gy & 31) != 0;
+                mc_tile_ld<4>(ld, c_mc_c[a.main_tables][gx & 31], c_mc_c[a.main_tables][gy & 31], fx, fy, bw, bh, rpl_c, a.bd_c, scr, lane, dst);
+            }
+        }
+    }
+    // average, residual, clip, store (xevd_average_16b_no_clip + xevdm_recon)
+    const int maxv = (1 << a.bd_l) - 1;
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++) {
+        const int sh = pl ? 1 : 0, bw = dx >> sh, bh = dy >> sh, rpl = pl ? rpl_c : rpl_l;
+        const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+        if (r0 >= bh) continue;
+        const int lx = ((cu.x + sx - ctu_x) >> sh) + col, ly = ((cu.y + sy - ctu_y) >> sh) + r0;
+        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * (pl ? rs_c : rs_l) + lx;
+        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + lx;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < rpl) dst[(size_t)i * (pl ? a.s_c : a.s_l)] = (pel)xb_clip3(0, maxv, (int16_t)(((pl0[pl][i] + pl1[pl][i] + 1) >> 1) + res[i * (pl ? rs_c : rs_l)]));
+    }
+    (void)w;
 }
 
 // ---- residual phase helpers -------------------------------------------------------------------------------
@@ -363,6 +563,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     if (ci == 0xffff) continue;
                     const XB200_CU cu = cus[ci];
                     if (xb_wavefront_mode(cu.mode)) continue;
+                    if (a.dmvr) { int st[2][2]; if (dmvr_applies(a, cu, st)) continue; }      // refined CUs: phase B2
                     const int cx = cu.x - ctu_x, cy = cu.y - ctu_y;
                     // piece of the CU inside this tile; handled when this SCU is the piece's top-left
                     const int px = max(cx, t_x), py = max(cy, t_y);
@@ -408,6 +609,23 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         }
     }
 
+    // ---- phase B2: DMVR CUs, one warp per 16x16 sub-PU ---------------------------------------------------------------------------
+    if (a.dmvr) {
+        int16_t *scr = sm.mc + warp * kMcScratchPerWarp;
+        int k = 0;
+        for (int i = 0; i < ncu; i++) {
+            const XB200_CU cu = cus[i];
+            int st[2][2];
+            if (!dmvr_applies(a, cu, st)) continue;
+            const int w = 1 << cu.log2w, h = 1 << cu.log2h, dx = min(w, 16), dy = min(h, 16);
+            for (int sy = 0; sy < h; sy += dy)
+                for (int sx = 0; sx < w; sx += dx, k++)
+                    if ((k & (kReconWarps - 1)) == warp)
+                        dmvr_sub_pu(a, cu, st, sx, sy, dx, dy, sm.res_y, sm.res_u, sm.res_v, S + 2, Sc + 2, ctu_x, ctu_y, scr, lane);
+        }
+        __syncthreads();        // refined vectors are in map_mv before phase C decides what to publish
+    }
+
     // ---- phase C: publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------
     for (int i = tid; i < nscu * nscu; i += kReconThreads) {
         const unsigned ci = sm.cu_of_scu[i];
@@ -427,8 +645,13 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         }
         if (cbfl) m |= 1u << 24;
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
+        bool refined = false;
+        if (a.dmvr) { int st[2][2]; refined = dmvr_applies(a, cu, st); }
+        if (refined) m |= 1u << 25;                                       // MCU_SET_DMVRF; map_mv already holds the refined vectors
         a.map_scu[p] = m;
-        ((int2 *)a.map_mv)[p] = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        const int2 mvw = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        if (!refined) ((int2 *)a.map_mv)[p] = mvw;
+        ((int2 *)a.map_unrefined_mv)[p] = mvw;
         ((int16_t *)a.map_refi)[p] = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
         a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0) |
                                   (aidx ? XB200_EDGE_ATS : 0));

@@ -669,6 +669,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 const int p = (sy + y) * a.w_scu + sx + x;
                 a.map_scu[p] = m;
                 ((int2 *)a.map_mv)[p] = mv;
+                ((int2 *)a.map_unrefined_mv)[p] = mv;
                 ((int16_t *)a.map_refi)[p] = rf;
                 a.map_edge[p] = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
             }

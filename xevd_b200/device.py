@@ -64,6 +64,8 @@ class DevicePicture:
         if maps:
             self.ctx._chk(L.xb200_pic_download_maps(self.ctx.handle, self.handle, out.map_mv.ctypes.data,
                                                     out.map_refi.ctypes.data, out.map_scu.ctypes.data), "xb200_pic_download_maps")
+            self.ctx._chk(L.xb200_pic_download_unrefined_mv(self.ctx.handle, self.handle, out.map_unrefined_mv.ctypes.data),
+                          "xb200_pic_download_unrefined_mv")
         return out
 
     def download_edge_map(self) -> np.ndarray:

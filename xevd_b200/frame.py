@@ -37,6 +37,7 @@ class HostPicture:
         self.w_scu, self.h_scu = (w + 3) >> 2, (h + 3) >> 2
         n = self.w_scu * self.h_scu
         self.map_mv = np.zeros((n, 2, 2), np.int16)
+        self.map_unrefined_mv = np.zeros((n, 2, 2), np.int16)     # Main: vectors before DMVR refinement (map_mv holds the refined ones)
         self.map_refi = np.full((n, 2), -1, np.int8)
         self.map_scu = np.zeros(n, np.uint32)
 
@@ -73,6 +74,7 @@ class HostPicture:
         o.buf_u[...] = self.buf_u
         o.buf_v[...] = self.buf_v
         o.map_mv[...] = self.map_mv
+        o.map_unrefined_mv[...] = self.map_unrefined_mv
         o.map_refi[...] = self.map_refi
         o.map_scu[...] = self.map_scu
         return o

@@ -297,6 +297,7 @@ def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp
         for j in range(nh):
             sl = slice((y0 + j) * ws + x0, (y0 + j) * ws + x0 + nw)
             pic.map_mv[sl] = 0 if intra else cu["mv"]
+            pic.map_unrefined_mv[sl] = pic.map_mv[sl]
             pic.map_refi[sl] = -1 if intra else cu["refi"]
         qp = int(rng.integers(qp_lo, qp_hi + 1))
         m = (1 << 31) | (qp << 16) | (int(rng.random() < intra_frac) << 15) | ((int(cu["cbf"]) & 1) << 24)
@@ -409,6 +410,48 @@ def derive_avail_cu(cl: CuList):
         cu["avail_cu"] = a
         cod[ys:ys + nh, xs:xs + nw] = True
     return cl
+
+
+def make_dmvr_case(w: int, h: int, *, bit_depth: int = 10, variant: str = "C", seed: int = 1, flag_frac: float = 0.8, noise: int = 3, **kw):
+    """Picture exercising decoder-side motion vector refinement (Main tool_dmvr): two reference pictures at equal POC distance
+    on either side of the current one whose content is the same texture displaced by a few samples (plus noise), bi-predicted
+    CUs with roughly mirrored vectors that are off by up to two samples, so the SAD search moves, stops early on (near-)zero
+    cost and takes the parabolic sub-sample step; XB200_CUF_DMVR is set on a fraction of the CUs (also on some that fail
+    xevdm_mc's own conditions: uni-prediction, both lists on the same side, CUs narrower than 8)."""
+    from .abi import CUF_DMVR
+    rng = np.random.default_rng(seed + 7000)
+    prm, cl = make_inter_frame(w, h, bit_depth=bit_depth, variant=variant, seed=seed, n_refs=2, bi_frac=0.8, mv_range_px=6, **kw)
+    prm.tool_dmvr = 1
+    cus = cl.cus
+    n = len(cus)
+    bi = (cus["refi"][:, 0] >= 0) & (cus["refi"][:, 1] >= 0)
+    # mirrored motion with a small error for most bi-predicted CUs
+    mirror = bi & (rng.random(n) < 0.85)
+    err = rng.integers(-8, 9, (n, 2)).astype(np.int16)
+    cus["mv"][mirror, 1, :] = -cus["mv"][mirror, 0, :] + err[mirror]
+    cus["flags"] = np.where(rng.random(n) < flag_frac, cus["flags"] | CUF_DMVR, cus["flags"]).astype(np.uint8)
+    # reference pictures: one smooth random texture per plane; picture 1 shows it displaced by (3, -2) luma samples, plus noise
+    hi = (1 << bit_depth) - 1
+
+    def texture(hh, ww):
+        base = rng.integers(0, hi + 1, (hh // 4 + 6, ww // 4 + 6)).astype(np.float64)
+        up = np.kron(base, np.ones((4, 4)))
+        k = np.ones(5) / 5.0
+        up = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, up)
+        return np.apply_along_axis(lambda c: np.convolve(c, k, mode="same"), 0, up)
+
+    tex = [texture(h, w), texture(h // 2, w // 2), texture(h // 2, w // 2)]
+    pics = []
+    for poc, (sx, sy) in ((0, (0, 0)), (16, (3, -2))):
+        p = HostPicture(w, h, poc)
+        for k_, pl in enumerate(p.planes()):
+            dx_, dy_ = (sx, sy) if k_ == 0 else (sx // 2, sy // 2)
+            v = tex[k_][8 + dy_:8 + dy_ + pl.shape[0], 8 + dx_:8 + dx_ + pl.shape[1]]
+            if poc:
+                v = v + rng.integers(-noise, noise + 1, pl.shape)
+            pl[...] = np.clip(np.rint(v), 0, hi).astype(np.int16)
+        pics.append(p.pad_borders())
+    return prm, cl, pics
 
 
 def make_alf_params(rng, enable=(1, 1, 1)):
