@@ -86,6 +86,7 @@ typedef struct XB200_CU {
     uint16_t cbf;             /* nnz_sub: bits 0-3 luma 64x64 sub-blocks, 4-7 Cb, 8-11 Cr
                                  (bit (j<<1)|i as xevd_eco.c:618-625); for CUs <= 64 only bit 0  */
     int16_t  mv[2][2];        /* inter: final UNCLIPPED motion vectors [list][x,y], quarter-pel
+                                 IBC: mv[0] = block vector in whole samples
                                  intra / affine: mv[1] holds a uint32 index into the extension
                                  array (XB200_CU_EXT), mv[0] is unused                           */
     uint8_t  ats;             /* Main, tool_ats.  bits 0-1: ats_intra mode (ats_intra_mode_h << 1 | ats_intra_mode_v,
@@ -118,9 +119,10 @@ typedef struct XB200_CU_EXT {
             uint64_t right;   /* Main/SUCO: column right                                                 */
             uint64_t pad;
         } intra;
-        struct {              /* XB200_MODE_AFFINE: control point MVs [list][vertex][x,y], 1/4 pel       */
-            int16_t cp[2][3][2];
-            int16_t pad[4];
+        struct {              /* XB200_MODE_AFFINE: control point MVs [list][vertex][x,y], 1/4 pel (mcore->affine_mv);   */
+            int16_t cp[2][3][2];  /* vertex 2 is used only with XB200_CUF_AFF6                                            */
+            int16_t mv_unref[2][2]; /* core->mv[list] when xevdm_set_dec_info runs: published to map_unrefined_mv, and to
+                                       map_mv of a list without reference (xevdm_util.c:4313-4340)                      */
         } affine;
     } u;
 } XB200_CU_EXT;

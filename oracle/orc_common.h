@@ -67,6 +67,12 @@ void orc_inter_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const i
 int orc_dmvr_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const int8_t refi[2], const int16_t mv[2][2],
                   const ORC_PIC *const *refs_l0, const ORC_PIC *const *refs_l1, pel *pred[2][3], int16_t *dmvr_mv);
 
+/* orc_affine.c */
+void orc_affine_subblock(const int16_t cp[2][3][2], const int8_t refi[2], int w, int h, int six, int *sub_w, int *sub_h, int *mem_ok);
+void orc_affine_pred(const XB200_PARAMS *prm, int x, int y, int w, int h, const int8_t refi[2], const int16_t cp[2][3][2], int six,
+                     const ORC_PIC *const *refs_l0, const ORC_PIC *const *refs_l1, pel *py, pel *pu, pel *pv);
+void orc_affine_map_mv(const int16_t cp[2][3][2], const int8_t refi[2], int log2w, int log2h, int six, int l, int16_t *out);
+
 /* orc_itdq.c */
 void orc_dequant(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, int iqt);
 void orc_inv_dct2(int16_t *coef, int log2w, int log2h, int bit_depth, int iqt);

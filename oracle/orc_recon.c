@@ -27,8 +27,16 @@ static void put_block(pel *rec, int s_rec, const pel *pred, const int16_t *res, 
     put_block_tu(rec, s_rec, pred, res, w, h, bd, 0, 0, w, h);
 }
 
-static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu, const int16_t *dmvr_mv)
+/* dmvr_mv: refined vectors per SCU of a DMVR CU (or NULL); aff: extension record of an affine CU (or NULL) */
+static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu, const int16_t *dmvr_mv, const XB200_CU_EXT *aff)
 {
+    int16_t *amv[2] = { NULL, NULL };
+    if (aff)
+        for (int l = 0; l < 2; l++)
+            if (cu->refi[l] >= 0) {
+                amv[l] = (int16_t *)malloc(sizeof(int16_t) * 2 * 32 * 32);
+                orc_affine_map_mv(aff->u.affine.cp, cu->refi, cu->log2w, cu->log2h, (cu->flags & XB200_CUF_AFF6) != 0, l, amv[l]);
+            }
     const int x0 = cu->x >> 2, y0 = cu->y >> 2, nw = 1 << (cu->log2w - 2), nh = 1 << (cu->log2h - 2);
     const int intra = cu->mode == XB200_MODE_INTRA;
     for (int j = 0; j < nh; j++)
@@ -47,18 +55,22 @@ static void publish_maps(const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *
             if (cbfl) m |= 1u << 24;
             if (cu->flags & XB200_CUF_SKIP) m |= 1u << 23;
             if (dmvr_mv) m |= 1u << 25;                                   /* MCU_SET_DMVRF (xevdm_def.h:318) */
+            if (aff) m |= ((cu->flags & XB200_CUF_AFF6) ? 2u : 1u) << 8;  /* MCU_SET_AFF (xevdm_def.h:336) */
             cur->map_scu[p] = m;
             for (int l = 0; l < 2; l++) {
                 cur->map_refi[p * 2 + l] = (intra || cu->mode == XB200_MODE_IBC) ? -1 : cu->refi[l];
                 for (int d = 0; d < 2; d++) {
                     /* xevdm_set_dec_info (xevdm_util.c:4313-4340): map_mv gets the refined vectors of a DMVR CU, map_unrefined_mv the
                      * signalled ones (spatial prediction and deblocking read the latter) */
-                    const int16_t v = intra ? 0 : cu->mv[l][d];
-                    cur->map_mv[(p * 2 + l) * 2 + d] = dmvr_mv ? dmvr_mv[((j * nw + i) * 2 + l) * 2 + d] : v;
+                    /* affine CUs: core->mv as the host passes it (extension record) in map_unrefined_mv and in the lists without a
+                     * reference; xevdm_set_affine_mvf's sub-block vectors in map_mv of the lists with one */
+                    const int16_t v = intra ? 0 : (aff ? aff->u.affine.mv_unref[l][d] : cu->mv[l][d]);
+                    cur->map_mv[(p * 2 + l) * 2 + d] = dmvr_mv ? dmvr_mv[((j * nw + i) * 2 + l) * 2 + d] : (amv[l] ? amv[l][(j * nw + i) * 2 + d] : v);
                     if (cur->map_unrefined_mv) cur->map_unrefined_mv[(p * 2 + l) * 2 + d] = v;
                 }
             }
         }
+    free(amv[0]); free(amv[1]);
 }
 
 int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
@@ -98,7 +110,13 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             }
             free(p1);
         }
+        const XB200_CU_EXT *aff = NULL;
         if (dmvr) {
+        } else if (cu->mode == XB200_MODE_AFFINE) {
+            uint32_t ei;
+            memcpy(&ei, cu->mv[1], 4);
+            aff = &ext[ei];
+            orc_affine_pred(prm, cu->x, cu->y, w, h, cu->refi, aff->u.affine.cp, (cu->flags & XB200_CUF_AFF6) != 0, refs_l0, refs_l1, py, pu, pv);
         } else if (cu->mode == XB200_MODE_INTER) {
             orc_inter_pred(prm, cu->x, cu->y, w, h, cu->refi, cu->mv, refs_l0, refs_l1, py, pu, pv);
         } else if (cu->mode == XB200_MODE_IBC) {
@@ -154,7 +172,7 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         /* Main tool_htdf (src_main/xevdm.c:1381-1391): luma post-filter of CUs with a luma residual and of every intra CU, slice QP */
         if (prm->tool_htdf && cu->mode != XB200_MODE_IBC && (has_y || cu->mode == XB200_MODE_INTRA) && (cu->flags & XB200_CUF_LUMA))
             orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma);
-        publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL);
+        publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL, aff);
     }
     free(pred); free(res); free(dmvr_mv);
     return XB200_OK;

@@ -246,6 +246,34 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
             xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
             xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
+        } else if (cu->mode == XB200_MODE_AFFINE) {
+            /* xevdm_affine_mc (src_main/xevdm_mc.c:2606) + the per-SCU vectors of xevdm_set_affine_mvf (src_main/xevdm_util.c:4095) */
+            static pel eif_tmp[(MAX_CU_SIZE + 2) * (MAX_CU_SIZE + 2)];
+            static XEVDM_CTX *fctx; static XEVDM_CORE *fcore;
+            uint32_t ei;
+            s16 amv[REFP_NUM][VER_NUM][MV_D];
+            int v;
+            memcpy(&ei, cu->mv[1], 4);
+            memset(amv, 0, sizeof(amv));
+            for (l = 0; l < 2; l++) for (v = 0; v < 3; v++) { amv[l][v][0] = ext[ei].u.affine.cp[l][v][0]; amv[l][v][1] = ext[ei].u.affine.cp[l][v][1]; }
+            select_mc_tables(prm->tool_admvp ? 1 : 0);
+            xevdm_affine_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, amv, refp, s->pred, (cu->flags & XB200_CUF_AFF6) ? 3 : 2, eif_tmp,
+                            prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+            if (cur->map_mv) {
+                if (!fctx) { fctx = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX)); fcore = (XEVDM_CORE *)calloc(1, sizeof(XEVDM_CORE)); }
+                for (l = 0; l < (h >> 2); l++)
+                    for (i = 0; i < (w >> 2); i++) {          /* xevdm_set_dec_info first stores core->mv everywhere */
+                        s16 *o = cur->map_mv + (scup + l * cur->w_scu + i) * 4;
+                        o[0] = ext[ei].u.affine.mv_unref[0][0]; o[1] = ext[ei].u.affine.mv_unref[0][1];
+                        o[2] = ext[ei].u.affine.mv_unref[1][0]; o[3] = ext[ei].u.affine.mv_unref[1][1];
+                    }
+                fctx->bctx.map_mv = (s16(*)[REFP_NUM][MV_D])cur->map_mv; fctx->bctx.w_scu = cur->w_scu;
+                fcore->core.scup = scup; fcore->core.log2_cuw = cu->log2w; fcore->core.log2_cuh = cu->log2h;
+                fcore->core.refi[0] = refi[0]; fcore->core.refi[1] = refi[1];
+                fcore->affine_flag = (cu->flags & XB200_CUF_AFF6) ? 2 : 1;
+                memcpy(fcore->affine_mv, amv, sizeof(amv));
+                xevdm_set_affine_mvf(&fctx->bctx, &fcore->core);
+            }
         } else if (cu->mode == XB200_MODE_INTER && prm->tool_dmvr) {
             /* Main xevdm_mc with the DMVR scratch buffers of XEVDM_CORE (src_main/xevdm_def.h:505-530); it leaves the averaged
              * prediction in pred[0], the refined vectors per SCU in dmvr_mv and restores mv[] */

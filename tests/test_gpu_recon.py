@@ -263,6 +263,25 @@ def test_dmvr(ctx, oracle, variant, kw, bd, noise):
     assert np.array_equal(got.map_unrefined_mv, want.map_unrefined_mv)
 
 
+@pytest.mark.parametrize("variant,kw,bd", [("C", {}, 10), ("C", dict(log2_ctu=7), 10), ("C", dict(log2_ctu=5), 8), ("B", {}, 10), ("A", dict(log2_cu=3), 10),
+                                           ("B", {}, 12), ("C", dict(mv_range_px=400), 10), ("B", dict(iqt=True), 10)])
+def test_affine(ctx, oracle, variant, kw, bd):
+    """Main tool_affine: sub-block and EIF prediction in the inter kernel, per-SCU model vectors in map_mv"""
+    from tests.test_oracle_vs_ref import affine_inputs
+    w, h, prm, cl, refs = affine_inputs(variant, kw, bd)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+    assert np.array_equal(got.map_unrefined_mv, want.map_unrefined_mv)
+
+
 def test_intra_1080p_wavefront(ctx, oracle):
     """a full-size I picture: 510 CTUs through the wavefront (ticket + done flags)"""
     w, h, bd = 1920, 1080, 10

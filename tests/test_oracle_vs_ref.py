@@ -363,3 +363,38 @@ def cl_inter_mask(cl, w_scu):
         if int(cu["mode"]) == 1:
             m[int(cu["y"]) >> 2:(int(cu["y"]) >> 2) + (1 << (int(cu["log2h"]) - 2)), int(cu["x"]) >> 2:(int(cu["x"]) >> 2) + (1 << (int(cu["log2w"]) - 2))] = True
     return m.reshape(-1)
+
+
+AFFINE_CASES = [("C", {}, 10), ("C", dict(log2_ctu=7), 10), ("C", dict(log2_ctu=5), 8), ("B", {}, 10), ("A", dict(log2_cu=3), 10), ("B", {}, 12),
+                ("C", dict(mv_range_px=400), 10)]
+
+
+def affine_inputs(variant, kw, bd):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.5, main_mv=True, ats_inter_frac=0.2, **kw)
+    prm.tool_affine = 1
+    synth.add_affine_cus(cl, np.random.default_rng(5), 0.7)
+    cl.validate()
+    return w, h, prm, cl, synth.make_refs(w, h, bd, 2, seed=9)
+
+
+def cu_mask(cl, mode, w_scu):
+    m = np.zeros(((cl.h + 3) >> 2, w_scu), bool)
+    for cu in cl.cus[cl.cus["mode"] == mode]:
+        m[int(cu["y"]) >> 2:(int(cu["y"]) >> 2) + (1 << (int(cu["log2h"]) - 2)), int(cu["x"]) >> 2:(int(cu["x"]) >> 2) + (1 << (int(cu["log2w"]) - 2))] = True
+    return m.reshape(-1)
+
+
+@pytest.mark.parametrize("variant,kw,bd", AFFINE_CASES)
+def test_recon_frame_affine(oracle, reference, variant, kw, bd):
+    """Main tool_affine (xevdm_affine_mc): 4- and 6-parameter models, the sub-block path (one vector per CU as the reference computes
+    it), EIF with and without the clamped vector window, uni- and bi-prediction; pictures and the per-SCU vectors of
+    xevdm_set_affine_mvf are compared"""
+    w, h, prm, cl, refs = affine_inputs(variant, kw, bd)
+    assert (cl.cus["mode"] == 5).sum() > 20
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    m = cu_mask(cl, 5, a.w_scu)
+    assert np.array_equal(a.map_mv[m], b.map_mv[m])

@@ -402,6 +402,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.htdf = prm->tool_htdf ? 1 : 0;
     a.dmvr = prm->tool_dmvr ? 1 : 0;
     a.poc = prm->poc;
+    a.affine = prm->tool_affine ? 1 : 0;
     a.slice_qp = prm->slice_qp;
     a.map_mv = cur->map_mv; a.map_unrefined_mv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
@@ -425,7 +426,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
-    if (!a.iqt && !a.ats && !a.dmvr && a.log2_ctu == 6 && !c->force_generic) {
+    if (!a.iqt && !a.ats && !a.dmvr && !a.affine && a.log2_ctu == 6 && !c->force_generic) {
         // throughput kernel (xb_recon2.cuh): Baseline transform path, 64x64 CTUs
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;

@@ -30,7 +30,7 @@ struct XbFrameArgs {
     int w, h;                   // luma size
     int bd_l, bd_c;
     int log2_ctu, w_ctu, n_ctu;
-    int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc;
+    int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine;
     const XB200_CU *cus;
     const uint32_t *ctu_first;
     const int16_t *coef;

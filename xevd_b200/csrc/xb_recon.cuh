@@ -391,6 +391,175 @@ __device__ void dmvr_sub_pu(const XbFrameArgs &a, const XB200_CU &cu, const int 
     (void)w;
 }
 
+// ---- affine (Main, tool_affine) -------------------------------------------------------------------------------------------------
+// xevdm_affine_mc (src_main/xevdm_mc.c:2606-2685): per list either ordinary interpolation with one vector for the whole CU (sub-blocks
+// of at least 8x8; the reference evaluates the model at (sub_w/2, sub_h/2) for every sub-block, :2359-2360) or EIF - per-sample
+// bilinear fetch at the model vector followed by a separable {-1, 10, -1} filter with s16 intermediates (:2425-2604).
+struct AffineModel {
+    int sub_w, sub_h;
+    bool mem_ok;
+};
+__device__ __forceinline__ int aff_round(int v, int sh) { return (v + (sh > 0 ? 1 << (sh - 1) : 0) - (v >= 0)) >> sh; }
+__device__ __forceinline__ void aff_gradients(const int16_t (*cp)[2], int lw, int lh, bool six, int (&dh)[2], int (&dv)[2])
+{
+    dh[0] = ((cp[1][0] - cp[0][0]) << 7) >> lw; dh[1] = ((cp[1][1] - cp[0][1]) << 7) >> lw;
+    if (six) { dv[0] = ((cp[2][0] - cp[0][0]) << 7) >> lh; dv[1] = ((cp[2][1] - cp[0][1]) << 7) >> lh; }
+    else { dv[0] = -dh[1]; dv[1] = dh[0]; }
+}
+// xevdm_derive_affine_subblock_size_bi + xevdm_check_eif_applicability_bi (src_main/xevdm_util.c:1870-2122)
+__device__ __forceinline__ AffineModel aff_model(const XB200_CU &cu, const XB200_CU_EXT &ex)
+{
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+    const bool six = (cu.flags & XB200_CUF_AFF6) != 0;
+    AffineModel m;
+    m.sub_w = w; m.sub_h = h; m.mem_ok = true;
+    bool apply = true;
+    for (int l = 0; l < 2; l++) {
+        if (cu.refi[l] < 0) continue;
+        int dh[2], dv[2];
+        aff_gradients(ex.u.affine.cp[l], cu.log2w, cu.log2h, six, dh, dv);
+        const int wx = max(abs(dh[0]), abs(dh[1])), wy = max(abs(dv[0]), abs(dv[1]));
+        m.sub_w = min(m.sub_w, wx > 4 ? 4 : (wx == 0 ? w : (wx == 1 ? 32 : (wx == 2 ? 16 : 8))));
+        m.sub_h = min(m.sub_h, wy > 4 ? 4 : (wy == 0 ? h : (wy == 1 ? 32 : (wy == 2 ? 16 : 8))));
+    }
+    for (int l = 0; l < 2 && apply; l++) {
+        if (cu.refi[l] < 0) continue;
+        int dh[2], dv[2];
+        aff_gradients(ex.u.affine.cp[l], cu.log2w, cu.log2h, six, dh, dv);
+        // fetch area of a 4x4 block (calculate_bounding_box_size) against MAX_MEMORY_ACCESS_BI = 72
+        const int x1 = 5 * (dh[0] + 512), x2 = 5 * dv[0], y1 = 5 * dh[1], y2 = 5 * (dv[1] + 512);
+        const int bw = ((max(max(0, x1), max(x2, x1 + x2)) - min(min(0, x1), min(x2, x1 + x2)) + 511) >> 9) + 2;
+        const int bh = ((max(max(0, y1), max(y2, y1 + y2)) - min(min(0, y1), min(y2, y1 + y2)) + 511) >> 9) + 2;
+        if (dv[1] < -512 || (max(0, dv[1]) + abs(dh[1])) * 5 > 512) apply = false;
+        m.mem_ok = m.mem_ok && (bw * bh <= 72);
+    }
+    if (!apply) { m.sub_w = max(m.sub_w, 8); m.sub_h = max(m.sub_h, 8); }
+    return m;
+}
+// vector xevdm_set_affine_mvf stores for SCU (sx, sy) of the CU, list l (src_main/xevdm_util.c:4095-4203)
+__device__ __forceinline__ int aff_map_mv(const XB200_CU &cu, const XB200_CU_EXT &ex, const AffineModel &m, int l, int sx, int sy)
+{
+    const int16_t (*v)[2] = ex.u.affine.cp[l];
+    const bool six = (cu.flags & XB200_CUF_AFF6) != 0;
+    const int wc = 1 << (cu.log2w - 2), hc = 1 << (cu.log2h - 2), sws = m.sub_w >> 2, shs = m.sub_h >> 2;
+    const int bx = sx - sx % sws, by = sy - sy % shs;                  // first SCU of the sub-block
+    int mx, my;
+    if (bx == 0 && by == 0) { mx = v[0][0]; my = v[0][1]; }
+    else if (bx + sws == wc && by == 0) { mx = v[1][0]; my = v[1][1]; }
+    else if (bx == 0 && by + shs == hc && six) { mx = v[2][0]; my = v[2][1]; }
+    else {
+        const int dhx = (v[1][0] - v[0][0]) << (7 - cu.log2w), dhy = (v[1][1] - v[0][1]) << (7 - cu.log2w);
+        const int dvx = six ? (v[2][0] - v[0][0]) << (7 - cu.log2h) : -dhy, dvy = six ? (v[2][1] - v[0][1]) << (7 - cu.log2h) : dhx;
+        const int px = (bx << 2) + (m.sub_w >> 1), py = (by << 2) + (m.sub_h >> 1);
+        mx = xb_clip3(-(1 << 17), (1 << 17) - 1, aff_round((v[0][0] << 7) + dhx * px + dvx * py, 5)) >> 2;
+        my = xb_clip3(-(1 << 17), (1 << 17) - 1, aff_round((v[0][1] << 7) + dhy * px + dvy * py, 5)) >> 2;
+    }
+    return (mx & 0xffff) | (my << 16);
+}
+
+// one <=16x16 luma tile (tx, ty) of an affine CU by one warp: both lists, three planes, average, residual, store
+__device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB200_CU_EXT &ex, const AffineModel &m, int tx, int ty, int tw, int th,
+                            const int16_t *res_y, const int16_t *res_u, const int16_t *res_v, int rs_l, int rs_c, int ctu_x, int ctu_y,
+                            int16_t *scr, int lane)
+{
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h;
+    const bool six = (cu.flags & XB200_CUF_AFF6) != 0, eif = m.sub_w < 8 || m.sub_h < 8;
+    int acc[3][8];
+    int nl = 0;
+    const int rpl_l = max(1, (tw * th) >> 5), rpl_c = max(1, ((tw >> 1) * (th >> 1)) >> 5);
+    for (int l = 0; l < 2; l++) {
+        if (cu.refi[l] < 0) continue;
+        const int ri = cu.refi[l];
+        int dh[2], dv[2];
+        aff_gradients(ex.u.affine.cp[l], cu.log2w, cu.log2h, six, dh, dv);
+        const int sc[2] = {ex.u.affine.cp[l][0][0] << 7, ex.u.affine.cp[l][0][1] << 7};
+        int mxv[2], mnv[2], mvo[2], mvc[2];
+        if (eif) {       // eif_derive_mv_clip_range (xevdm_mc.c:2108-2150), 1/32 sample
+            const int pmx[2] = {(a.w + 128 - cu.x - w - 1) << 5, (a.h + 128 - cu.y - h - 1) << 5}, pmn[2] = {(-cu.x - 128) << 5, (-cu.y - 128) << 5};
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                if (m.mem_ok) { mxv[c] = pmx[c]; mnv[c] = pmn[c]; }
+                else {
+                    const int centre = aff_round(sc[c] + dh[c] * (w >> 1) + dv[c] * (h >> 1), 4);
+                    const int lg = (c == 0 ? cu.log2w : cu.log2h) - 3;
+                    const int spread = lg == 0 ? 128 : (lg == 1 ? 256 : (lg == 2 ? 544 : (lg == 3 ? 1120 : 2272)));
+                    mnv[c] = centre - spread; mxv[c] = centre + spread;
+                    if (mnv[c] < pmn[c]) { mnv[c] = pmn[c]; mxv[c] = min(pmx[c], pmn[c] + 2 * spread); }
+                    else if (mxv[c] > pmx[c]) { mxv[c] = pmx[c]; mnv[c] = max(pmn[c], pmx[c] - 2 * spread); }
+                }
+                mxv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mxv[c]);
+                mnv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mnv[c]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 2; c++) mvo[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, aff_round(sc[c] + dh[c] * (m.sub_w >> 1) + dv[c] * (m.sub_h >> 1), 5));
+            mvc[0] = min((a.w + 128 - cu.x - w) << 4, max((-128 - cu.x) << 4, mvo[0]));
+            mvc[1] = min((a.h + 128 - cu.y - h) << 4, max((-128 - cu.y) << 4, mvo[1]));
+        }
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+            const int sh = pl ? 1 : 0, bw = tw >> sh, bh = th >> sh, rpl = pl ? rpl_c : rpl_l, bd = pl ? a.bd_c : a.bd_l, s = pl ? a.s_c : a.s_l;
+            const pel *plane = pl == 0 ? a.ref_y[l][ri] : (pl == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
+            int pr[8];
+            if (!eif) {
+                const int gx = ((cu.x + tx) << 4) + mvc[0], gy = ((cu.y + ty) << 4) + mvc[1];
+                if (pl == 0) {
+                    const pel *ref = plane + (ptrdiff_t)(gy >> 4) * s + (gx >> 4);
+                    mc_tile<8>(ref, s, c_mc_l[a.main_tables][gx & 15], c_mc_l[a.main_tables][gy & 15], (mvo[0] & 15) != 0, (mvo[1] & 15) != 0, bw, bh, rpl, bd, scr, lane, pr);
+                } else {
+                    const pel *ref = plane + (ptrdiff_t)(gy >> 5) * s + (gx >> 5);
+                    mc_tile<4>(ref, s, c_mc_c[a.main_tables][gx & 31], c_mc_c[a.main_tables][gy & 31], (mvo[0] & 31) != 0, (mvo[1] & 31) != 0, bw, bh, rpl, bd, scr, lane, pr);
+                }
+            } else {
+                // bilinear samples of the (bw + 2) x (bh + 2) neighbourhood of the tile, positions relative to the CU plane
+                const int mv0x = sc[0] >> sh, mv0y = sc[1] >> sh, lim_x0 = mnv[0] >> sh, lim_x1 = mxv[0] >> sh, lim_y0 = mnv[1] >> sh, lim_y1 = mxv[1] >> sh;
+                const int ox = (cu.x >> sh), oy = (cu.y >> sh), px0 = tx >> sh, py0 = ty >> sh;
+                const int s1 = min(4, bd - 8), s2 = max(8, 20 - bd), sh_h = max(bd + 5 - 16, 0), sh_v = 6 - sh_h;
+                const int st = bw + 2;
+                int16_t *bb = scr, *hb = scr + 18 * 18;
+                for (int idx = lane; idx < st * (bh + 2); idx += 32) {
+                    const int j = idx / st - 1 + py0, i = idx % st - 1 + px0;          // sample position inside the CU plane
+                    const int vx = xb_clip3(lim_x0, lim_x1, (mv0x + i * dh[0] + j * dv[0]) >> 4), vy = xb_clip3(lim_y0, lim_y1, (mv0y + i * dh[1] + j * dv[1]) >> 4);
+                    const pel *r = plane + (ptrdiff_t)(oy + j + (vy >> 5)) * s + ox + i + (vx >> 5);
+                    const int fx = vx & 31, fy = vy & 31;
+                    const int a0 = (int16_t)(((64 - 2 * fx) * r[0] + 2 * fx * r[1]) >> s1), a1 = (int16_t)(((64 - 2 * fx) * r[s] + 2 * fx * r[s + 1]) >> s1);
+                    bb[idx] = (int16_t)(((64 - 2 * fy) * a0 + 2 * fy * a1 + (1 << (s2 - 1))) >> s2);
+                }
+                __syncwarp();
+                for (int idx = lane; idx < bw * (bh + 2); idx += 32) {
+                    const int j = idx / bw, i = idx % bw;
+                    hb[idx] = (int16_t)((-bb[j * st + i] + 10 * bb[j * st + i + 1] - bb[j * st + i + 2] + (sh_h ? 1 << (sh_h - 1) : 0)) >> sh_h);
+                }
+                __syncwarp();
+                const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    if (i < rpl && r0 < bh) {
+                        const int v = (int16_t)((-hb[(r0 + i) * bw + col] + 10 * hb[(r0 + i + 1) * bw + col] - hb[(r0 + i + 2) * bw + col] + (1 << (sh_v - 1))) >> sh_v);
+                        pr[i] = xb_clip3(0, (1 << bd) - 1, v);
+                    }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[pl][i] = nl ? (acc[pl][i] + pr[i] + 1) >> 1 : pr[i];
+        }
+        nl++;
+    }
+    const int maxv = (1 << a.bd_l) - 1;
+#pragma unroll
+    for (int pl = 0; pl < 3; pl++) {
+        const int sh = pl ? 1 : 0, bw = tw >> sh, bh = th >> sh, rpl = pl ? rpl_c : rpl_l;
+        const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+        if (r0 >= bh) continue;
+        const int lx = ((cu.x + tx - ctu_x) >> sh) + col, ly = ((cu.y + ty - ctu_y) >> sh) + r0;
+        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * (pl ? rs_c : rs_l) + lx;
+        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + lx;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (i < rpl) dst[(size_t)i * (pl ? a.s_c : a.s_l)] = (pel)xb_clip3(0, maxv, (int16_t)(acc[pl][i] + res[i * (pl ? rs_c : rs_l)]));
+    }
+}
+
 // ---- residual phase helpers -------------------------------------------------------------------------------
 // The coded transform block of plane `pl` covering SCU (xs, ys) (CTU-relative SCU coordinates) of a CU, or false when that SCU
 // carries no coefficients.  Normal CUs: the CU plane cut into <= 64-sample (chroma 32) blocks gated by the nnz_sub bits
@@ -564,6 +733,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     const XB200_CU cu = cus[ci];
                     if (xb_wavefront_mode(cu.mode)) continue;
                     if (a.dmvr) { int st[2][2]; if (dmvr_applies(a, cu, st)) continue; }      // refined CUs: phase B2
+                    if (cu.mode == XB200_MODE_AFFINE) continue;                               // affine CUs: phase B3
                     const int cx = cu.x - ctu_x, cy = cu.y - ctu_y;
                     // piece of the CU inside this tile; handled when this SCU is the piece's top-left
                     const int px = max(cx, t_x), py = max(cy, t_y);
@@ -626,6 +796,25 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         __syncthreads();        // refined vectors are in map_mv before phase C decides what to publish
     }
 
+    // ---- phase B3: affine CUs, one warp per 16x16 tile -----------------------------------------------------------------------------
+    if (a.affine) {
+        int16_t *scr = sm.mc + warp * kMcScratchPerWarp;
+        int k = 0;
+        for (int i = 0; i < ncu; i++) {
+            const XB200_CU cu = cus[i];
+            if (cu.mode != XB200_MODE_AFFINE) continue;
+            uint32_t ei;
+            memcpy(&ei, cu.mv[1], 4);
+            const XB200_CU_EXT ex = a.ext[ei];
+            const AffineModel m = aff_model(cu, ex);
+            const int w = 1 << cu.log2w, h = 1 << cu.log2h, tw = min(w, 16), th = min(h, 16);
+            for (int ty = 0; ty < h; ty += th)
+                for (int tx = 0; tx < w; tx += tw, k++)
+                    if ((k & (kReconWarps - 1)) == warp)
+                        affine_tile(a, cu, ex, m, tx, ty, tw, th, sm.res_y, sm.res_u, sm.res_v, S + 2, Sc + 2, ctu_x, ctu_y, scr, lane);
+        }
+    }
+
     // ---- phase C: publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------
     for (int i = tid; i < nscu * nscu; i += kReconThreads) {
         const unsigned ci = sm.cu_of_scu[i];
@@ -648,9 +837,23 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         bool refined = false;
         if (a.dmvr) { int st[2][2]; refined = dmvr_applies(a, cu, st); }
         if (refined) m |= 1u << 25;                                       // MCU_SET_DMVRF; map_mv already holds the refined vectors
+        int2 mvw = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
+        int2 mvm = mvw;
+        if (cu.mode == XB200_MODE_AFFINE) {
+            // xevdm_set_dec_info publishes core->mv (extension record); xevdm_set_affine_mvf then overwrites map_mv of the lists in use
+            uint32_t ei;
+            memcpy(&ei, cu.mv[1], 4);
+            const XB200_CU_EXT ex = a.ext[ei];
+            const AffineModel am = aff_model(cu, ex);
+            mvw = make_int2(((const int *)ex.u.affine.mv_unref)[0], ((const int *)ex.u.affine.mv_unref)[1]);
+            mvm = mvw;
+            const int sx = gx - (cu.x >> 2), sy = gy - (cu.y >> 2);
+            if (cu.refi[0] >= 0) mvm.x = aff_map_mv(cu, ex, am, 0, sx, sy);
+            if (cu.refi[1] >= 0) mvm.y = aff_map_mv(cu, ex, am, 1, sx, sy);
+            m |= ((cu.flags & XB200_CUF_AFF6) ? 2u : 1u) << 8;             // MCU_SET_AFF
+        }
         a.map_scu[p] = m;
-        const int2 mvw = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
-        if (!refined) ((int2 *)a.map_mv)[p] = mvw;
+        if (!refined) ((int2 *)a.map_mv)[p] = mvm;
         ((int2 *)a.map_unrefined_mv)[p] = mvw;
         ((int16_t *)a.map_refi)[p] = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
         a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0) |

@@ -384,6 +384,46 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     return cl
 
 
+def add_affine_cus(cl: CuList, rng, frac: float = 0.5):
+    """Turn a fraction of the inter CUs of at least 8x8 into affine CUs (Main tool_affine): control point vectors = the CU's vectors
+    plus per-vertex offsets drawn from a wide range, so that the 8x8-or-larger sub-block path, the per-sample EIF path (with and
+    without the clamped vector window) and 4- / 6-parameter models all occur; extension records carry the control points and the
+    value xevdm_set_dec_info would publish as unrefined vector."""
+    from .abi import CUF_AFF6, MODE_AFFINE
+    cus = cl.cus
+    ext = list(cl.ext)
+    scales = np.array([0, 0, 1, 2, 4, 10, 40])
+    for i in range(len(cus)):
+        cu = cus[i]
+        if int(cu["mode"]) != MODE_INTER or int(cu["log2w"]) < 3 or int(cu["log2h"]) < 3 or rng.random() >= frac:
+            continue
+        e = np.zeros(1, EXT_DTYPE)[0]
+        rec = np.zeros(16, np.int16)            # cp[2][3][2] then mv_unref[2][2]
+        sc = int(scales[int(rng.integers(0, len(scales)))])
+        for l in range(2):
+            base = cu["mv"][l].astype(np.int64)
+            for v in range(3):
+                d = rng.integers(-sc, sc + 1, 2) if (v and sc) else np.zeros(2, np.int64)
+                rec[(l * 3 + v) * 2:(l * 3 + v) * 2 + 2] = base + d
+        rec[12:16] = rng.integers(-64, 65, 4)
+        six = rng.random() < 0.5
+        if six and rng.random() < 0.3:
+            # strong horizontal stretch with a flat vertical gradient: EIF stays applicable but its fetch area exceeds the
+            # memory-bandwidth bound, which switches on the clamped vector window (eif_derive_mv_clip_range)
+            for l in range(2):
+                rec[(l * 3 + 1) * 2] += (3 + int(rng.integers(0, 3))) << int(cu["log2w"])
+                rec[(l * 3 + 2) * 2:(l * 3 + 2) * 2 + 2] = rec[(l * 3) * 2:(l * 3) * 2 + 2]
+        e["q"] = rec.view(np.uint64)
+        cu["mode"] = MODE_AFFINE
+        if six:
+            cu["flags"] = int(cu["flags"]) | CUF_AFF6
+        cu["mv"] = 0
+        cu["mv"][1] = np.frombuffer(np.uint32(len(ext)).tobytes(), np.int16)
+        ext.append(e)
+    cl.ext = np.array(ext, EXT_DTYPE)
+    return cl
+
+
 def derive_avail_cu(cl: CuList):
     """XB200_CU.avail_cu for every CU: what xevd_get_avail_intra (src_base/xevd_util.c:689-745) returns when the CU is reached in
     decoding order (one tile, one slice) - consumed by the HTDF ring fetch (src_main/xevdm_recon.c:299-385)"""
