@@ -86,10 +86,38 @@ def golden_frames(ref):
     np.savez_compressed(OUT / "frames.npz", **out)
 
 
+MAIN_CFGS = [("main_ctu64_iqt_10", dict(bit_depth=10, seed=3, log2_ctu=6, iqt=True)), ("main_ctu128_10", dict(bit_depth=10, seed=4, log2_ctu=7, iqt=False)),
+             ("main_ctu32_iqt_8", dict(bit_depth=8, seed=5, log2_ctu=5, iqt=True))]
+
+
+def golden_main(ref):
+    """BASELINE config 3 in miniature: every Main-profile hot-path tool on, through the reference's own per-CU calls, then the
+    reference's ADDB deblocking, ALF and border padding.  Per-SCU maps between the stages are the oracle's (the harness has no
+    slice-level state); the oracle's maps are pinned separately (tests/test_oracle_vs_ref.py)."""
+    from oracle.pyoracle import Oracle
+    orc = Oracle()
+    out = {}
+    w, h = 256, 136
+    for name, kw in MAIN_CFGS:
+        prm, cl, refs, alf, flags = synth.make_main_frame(w, h, **kw)
+        pic = ref.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        o = orc.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        out[f"{name}_rec_y"], out[f"{name}_rec_u"], out[f"{name}_rec_v"] = pic.y.copy(), pic.u.copy(), pic.v.copy()
+        out[f"{name}_map_mv"], out[f"{name}_map_scu"] = o.map_mv.copy(), o.map_scu.copy()
+        for k in ("map_mv", "map_refi", "map_scu", "map_unrefined_mv"):
+            getattr(pic, k)[...] = getattr(o, k)
+        ref.deblock_frame(prm, pic, cl, synth.chroma_qp_table(True), True, ((0, 1), (1, 0)))
+        ref.alf_frame(prm, pic, alf, flags)
+        ref.pad(pic)
+        out[f"{name}_fin_y"], out[f"{name}_fin_u"], out[f"{name}_fin_v"] = pic.buf_y.copy(), pic.buf_u.copy(), pic.buf_v.copy()
+    np.savez_compressed(OUT / "main_frames.npz", **out)
+
+
 if __name__ == "__main__":
     r = Reference(2)
     golden_itdq(r)
     golden_mc(r)
     golden_frames(r)
+    golden_main(r)
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

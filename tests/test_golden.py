@@ -63,3 +63,23 @@ def test_golden_frames(oracle, name, kw, intra):
         oracle.deblock_frame(prm, pic, cl, synth.chroma_qp_table(False))
         oracle.pad(pic)
         assert np.array_equal(pic.buf_y, z[f"{name}_dbk_y"]) and np.array_equal(pic.buf_u, z[f"{name}_dbk_u"]) and np.array_equal(pic.buf_v, z[f"{name}_dbk_v"])
+
+
+MAIN_CFGS = [("main_ctu64_iqt_10", dict(bit_depth=10, seed=3, log2_ctu=6, iqt=True)), ("main_ctu128_10", dict(bit_depth=10, seed=4, log2_ctu=7, iqt=False)),
+             ("main_ctu32_iqt_8", dict(bit_depth=8, seed=5, log2_ctu=5, iqt=True))]
+
+
+@pytest.mark.parametrize("name,kw", MAIN_CFGS)
+def test_golden_main_pipeline(oracle, name, kw):
+    """BASELINE config 3 in miniature (all Main tools, then ADDB deblocking + ALF + padding) against the reference's recorded output"""
+    z = np.load(G / "main_frames.npz")
+    w, h = 256, 136
+    prm, cl, refs, alf, flags = synth.make_main_frame(w, h, **kw)
+    pic = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl, k in zip(pic.planes(), "yuv"):
+        assert np.array_equal(pl, z[f"{name}_rec_{k}"]), (name, k)
+    assert np.array_equal(pic.map_mv, z[f"{name}_map_mv"]) and np.array_equal(pic.map_scu, z[f"{name}_map_scu"])
+    oracle.deblock_frame(prm, pic, cl, synth.chroma_qp_table(True), True, ((0, 1), (1, 0)))
+    oracle.alf_frame(prm, pic, alf, flags)
+    oracle.pad(pic)
+    assert np.array_equal(pic.buf_y, z[f"{name}_fin_y"]) and np.array_equal(pic.buf_u, z[f"{name}_fin_u"]) and np.array_equal(pic.buf_v, z[f"{name}_fin_v"])

@@ -326,3 +326,30 @@ def test_golden_frames_gpu(ctx):
             assert np.array_equal(out.buf_y, z[f"{name}_dbk_y"]) and np.array_equal(out.buf_u, z[f"{name}_dbk_u"]) and np.array_equal(out.buf_v, z[f"{name}_dbk_v"]), name
         for p in drefs + [cur]:
             p.free()
+
+
+def test_golden_main_pipeline_gpu(ctx):
+    """BASELINE config 3 in miniature through the C ABI on the GPU - xb200_recon_frame (all Main tools) -> xb200_deblock (ADDB, with
+    the maps the reconstruction published) -> xb200_alf -> xb200_pad - against the recorded output of the unmodified reference"""
+    from pathlib import Path
+    from tests.test_golden import MAIN_CFGS
+    z = np.load(Path(__file__).resolve().parent / "golden" / "main_frames.npz")
+    w, h = 256, 136
+    for name, kw in MAIN_CFGS:
+        prm, cl, refs, alf, flags = synth.make_main_frame(w, h, **kw)
+        drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+        cur = ctx.pic_alloc(w, h)
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(True))
+        ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        got = cur.download(maps=True)
+        for pl, k in zip(got.planes(), "yuv"):
+            assert np.array_equal(pl, z[f"{name}_rec_{k}"]), (name, k)
+        assert np.array_equal(got.map_mv, z[f"{name}_map_mv"]) and np.array_equal(got.map_scu, z[f"{name}_map_scu"]), name
+        ctx.deblock(prm, cur, drefs, drefs[::-1])
+        ctx.alf(prm, cur, alf, flags)
+        ctx.pad(cur)
+        out = cur.download_padded()
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+        for p in drefs + [cur]:
+            p.free()
+        assert np.array_equal(out.buf_y, z[f"{name}_fin_y"]) and np.array_equal(out.buf_u, z[f"{name}_fin_u"]) and np.array_equal(out.buf_v, z[f"{name}_fin_v"]), name

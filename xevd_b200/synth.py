@@ -494,6 +494,26 @@ def make_dmvr_case(w: int, h: int, *, bit_depth: int = 10, variant: str = "C", s
     return prm, cl, pics
 
 
+def make_main_frame(w: int, h: int, *, bit_depth: int = 10, seed: int = 1, log2_ctu: int = 6, slice_qp: int = 34, intra_frac: float = 0.25,
+                    iqt: bool = True, coded_frac: float = 0.6):
+    """BASELINE config 3 in miniature: one Main-profile picture with every hot-path tool on - binary/ternary partition with SUCO order,
+    1/16-pel interpolation, IQT, ATS (intra + sub-block inter), EIPD intra, IBC, HTDF, DMVR, affine - plus the parameters of the
+    picture-wide passes (ADDB deblocking, ALF).  Returns (params, CuList, reference pictures, ALF parameters, ALF CTB flags)."""
+    rng = np.random.default_rng(seed + 9000)
+    prm, cl, refs = make_dmvr_case(w, h, bit_depth=bit_depth, variant="C", seed=seed, noise=3, coded_frac=coded_frac, main_mv=True,
+                                   ats_inter_frac=0.3, iqt=iqt, log2_ctu=log2_ctu)
+    prm.tool_eipd = prm.tool_ibc = prm.tool_htdf = prm.tool_affine = prm.tool_addb = prm.tool_alf = 1
+    prm.slice_qp = slice_qp
+    prm.qp_u_offset, prm.qp_v_offset = 1, -2
+    cl.cus["qp_map"] = rng.integers(24, 46, cl.n_cu)
+    add_intra_cus(cl, rng, intra_frac, eipd=True, ats_intra_frac=0.5, ibc_frac=0.15)
+    add_affine_cus(cl, rng, 0.3)
+    derive_avail_cu(cl)
+    ctu = 1 << log2_ctu
+    n_ctu = ((w + ctu - 1) // ctu) * ((h + ctu - 1) // ctu)
+    return prm, cl, refs, make_alf_params(rng), (rng.random(n_ctu) < 0.8).astype(np.uint8)
+
+
 def make_alf_params(rng, enable=(1, 1, 1)):
     """random but well-formed ALF filters: every filter sums to 512 (unity gain at shift 9), side taps within the ranges
     alf_recon_coef enforces (src_main/xevdm_alf.c:751,763)"""
