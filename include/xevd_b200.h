@@ -148,7 +148,11 @@ typedef struct XB200_PARAMS {
     int32_t qp_u_offset, qp_v_offset;        /* pic_qp_u/v_offset used by deblock chroma QP            */
     int32_t deblock_alpha_offset, deblock_beta_offset;
     int32_t poc;                  /* POC of the current picture                                         */
-    int32_t reserved[10];
+    int32_t ctu_row0, ctu_rows;   /* band mode (intra-picture multi-GPU sharding): when ctu_rows > 0 only CTU rows
+                                     [ctu_row0, ctu_row0 + ctu_rows) are reconstructed; cus / ctu_first / n_ctu describe just
+                                     those CTUs (n_ctu = ctu_rows * CTUs per row).  Inter CUs only: intra / IBC / HTDF need the
+                                     bands above, which live on other GPUs (bands that are tiles would lift this)            */
+    int32_t reserved[8];
 } XB200_PARAMS;
 
 typedef struct xb200_ctx xb200_ctx;   /* device context: stream, uploaded tables, scratch              */
@@ -258,6 +262,15 @@ typedef struct XB200_ALF {
  * where enable[0] and the CTU flag are both set, chroma wherever enable[c] is set.  In place.              */
 int  xb200_alf(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
 int  xb200_pad(xb200_ctx *ctx, xb200_pic *pic);           /* xevd_picbuf_expand                        */
+
+/* ---- band exchange (intra-picture sharding across GPUs, BASELINE config 4) ---------------------------------------------------
+ * A band = luma rows [y0, y0 + rows) of a picture (y0, rows multiples of the CTU size; the last band may be shorter) with the
+ * matching chroma rows and per-SCU map rows.  pack copies it into one contiguous device buffer - the unit of the all-gather
+ * that follows reconstruction - and unpack writes a band received from another GPU into the picture.
+ * Layout: Y rows (w samples each) | U | V | map_mv | map_unrefined_mv | map_scu | map_refi | map_edge.                        */
+size_t xb200_band_bytes(xb200_pic *pic, int rows);
+int  xb200_band_pack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, void *d_dst);
+int  xb200_band_unpack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, const void *d_src);
 
 /* ---- batched leaf kernels (micro-benchmarks, BASELINE.json config 5) ------------------------------ */
 /* n blocks of (1<<log2w) x (1<<log2h) coefficients, contiguous, in place semantics of

@@ -353,3 +353,37 @@ def test_golden_main_pipeline_gpu(ctx):
         for p in drefs + [cur]:
             p.free()
         assert np.array_equal(out.buf_y, z[f"{name}_fin_y"]) and np.array_equal(out.buf_u, z[f"{name}_fin_u"]) and np.array_equal(out.buf_v, z[f"{name}_fin_v"]), name
+
+
+@pytest.mark.parametrize("variant,lg", [("B", 6), ("C", 6), ("C", 7), ("C", 5)])
+def test_band_mode_single_gpu(ctx, oracle, variant, lg):
+    """band mode of xb200_recon_frame (BASELINE config 4): the picture reconstructed as three separate CTU-row bands into a second
+    device picture, moved over by xb200_band_pack / xb200_band_unpack, equals the whole-picture call (planes and maps)"""
+    import torch
+    from xevd_b200 import dist as xdist
+    w, h, bd = 256, 328, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=91, n_refs=2, coded_frac=0.8, log2_ctu=lg)
+    refs = synth.make_refs(w, h, bd, 2, seed=92)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    part, whole = ctx.pic_alloc(w, h), ctx.pic_alloc(w, h)
+    ctu = 1 << lg
+    for r0, k in xdist.band_partition(h, lg, 3):
+        prm.ctu_row0, prm.ctu_rows = r0, k
+        ctx.recon_frame(prm, part, drefs, drefs[::-1], cl.band(r0, k))
+        y0, rows = r0 * ctu, min(k * ctu, h - r0 * ctu)
+        buf = torch.empty(ctx.band_bytes(part, rows), dtype=torch.uint8, device="cuda")
+        ctx.band_pack(part, y0, rows, buf.data_ptr())
+        ctx.band_unpack(whole, y0, rows, buf.data_ptr())
+        ctx.sync()
+    prm.ctu_row0 = prm.ctu_rows = 0
+    got = whole.download(maps=True)
+    edge_got = whole.download_edge_map()
+    ctx.recon_frame(prm, part, drefs, drefs[::-1], cl)
+    edge_want = part.download_edge_map()
+    for p in drefs + [part, whole]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+    assert np.array_equal(edge_got, edge_want)

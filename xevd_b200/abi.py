@@ -59,7 +59,8 @@ class Params(C.Structure):
         ("slice_qp", C.c_int32), ("qp_u_offset", C.c_int32), ("qp_v_offset", C.c_int32),
         ("deblock_alpha_offset", C.c_int32), ("deblock_beta_offset", C.c_int32),
         ("poc", C.c_int32),
-        ("reserved", C.c_int32 * 10),
+        ("ctu_row0", C.c_int32), ("ctu_rows", C.c_int32),
+        ("reserved", C.c_int32 * 8),
     ]
 
 
@@ -121,6 +122,9 @@ _SIGS = {
     "xb200_pic_download_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_edge_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_band_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "xb200_band_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "xb200_band_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "xb200_pic_download_unrefined_mv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_recon_frame": (
         C.c_int,

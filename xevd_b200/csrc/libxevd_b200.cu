@@ -395,6 +395,11 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.log2_ctu = prm->log2_ctu;
     a.w_ctu = (cur->w + (1 << a.log2_ctu) - 1) >> a.log2_ctu;
     a.n_ctu = a.w_ctu * ((cur->h + (1 << a.log2_ctu) - 1) >> a.log2_ctu);
+    if (prm->ctu_rows > 0) {        // band mode: this launch covers CTU rows [ctu_row0, ctu_row0 + ctu_rows)
+        if (prm->ctu_row0 < 0 || (prm->ctu_row0 + prm->ctu_rows) * a.w_ctu > a.n_ctu) return XB200_ERR_INVALID_ARGUMENT;
+        a.ctu_row0 = prm->ctu_row0;
+        a.n_ctu = prm->ctu_rows * a.w_ctu;
+    }
     a.main_tables = prm->tool_admvp ? 1 : 0;
     a.iqt = prm->tool_iqt ? 1 : 0;
     a.eipd = prm->tool_eipd ? 1 : 0;
@@ -419,6 +424,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     if (r < 0) return r;
     (void)n_ext; (void)n_coef;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
+    if (has_intra && prm->ctu_rows > 0) return XB200_ERR_UNSUPPORTED;          // the wavefront crosses band boundaries
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
     a.cus = (const XB200_CU *)d_cus;
@@ -650,6 +656,53 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     CK(c, cudaGetLastError());
     return XB200_OK;
 }
+
+// ---- band exchange -------------------------------------------------------------------------------------------------------
+static void band_geometry(xb200_pic *p, int y0, int rows, int &yc0, int &rc, int &s0, int &sr)
+{
+    yc0 = y0 >> 1; rc = (rows + 1) >> 1;                    // chroma rows
+    s0 = y0 >> 2; sr = (rows + 3) >> 2;                     // SCU rows
+    (void)p;
+}
+size_t xb200_band_bytes(xb200_pic *p, int rows)
+{
+    if (!p || rows <= 0) return 0;
+    int yc0, rc, s0, sr;
+    band_geometry(p, 0, rows, yc0, rc, s0, sr);
+    const size_t b = (size_t)rows * p->w * 2 + 2 * (size_t)rc * p->w_c * 2 + (size_t)sr * p->w_scu * (8 + 8 + 4 + 2 + 1);
+    return (b + 255) & ~(size_t)255;
+}
+static int band_copy(xb200_ctx *c, xb200_pic *p, int y0, int rows, unsigned char *buf, bool pack)
+{
+    if (!c || !p || !buf || y0 < 0 || rows <= 0 || y0 + rows > p->h || (y0 & 3)) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    int yc0, rc, s0, sr;
+    band_geometry(p, y0, rows, yc0, rc, s0, sr);
+    if (yc0 + rc > p->h_c) rc = p->h_c - yc0;
+    if (s0 + sr > p->h_scu) sr = p->h_scu - s0;
+    size_t off = 0;
+    auto plane = [&](pel *base, int stride, int w, int r0, int nr) -> cudaError_t {
+        pel *pp = base + (size_t)r0 * stride;
+        cudaError_t e = pack ? cudaMemcpy2DAsync(buf + off, (size_t)w * 2, pp, (size_t)stride * 2, (size_t)w * 2, nr, cudaMemcpyDeviceToDevice, c->stream)
+                             : cudaMemcpy2DAsync(pp, (size_t)stride * 2, buf + off, (size_t)w * 2, (size_t)w * 2, nr, cudaMemcpyDeviceToDevice, c->stream);
+        off += (size_t)w * 2 * nr;
+        return e;
+    };
+    auto map = [&](void *base, int bytes_per_scu) -> cudaError_t {
+        unsigned char *pp = (unsigned char *)base + (size_t)s0 * p->w_scu * bytes_per_scu;
+        const size_t n = (size_t)sr * p->w_scu * bytes_per_scu;
+        cudaError_t e = pack ? cudaMemcpyAsync(buf + off, pp, n, cudaMemcpyDeviceToDevice, c->stream) : cudaMemcpyAsync(pp, buf + off, n, cudaMemcpyDeviceToDevice, c->stream);
+        off += n;
+        return e;
+    };
+    CK(c, plane(p->y, p->s_l, p->w, y0, rows));
+    CK(c, plane(p->u, p->s_c, p->w_c, yc0, rc));
+    CK(c, plane(p->v, p->s_c, p->w_c, yc0, rc));
+    CK(c, map(p->map_mv, 8)); CK(c, map(p->map_unrefined_mv, 8)); CK(c, map(p->map_scu, 4)); CK(c, map(p->map_refi, 2)); CK(c, map(p->map_edge, 1));
+    return XB200_OK;
+}
+int xb200_band_pack(xb200_ctx *c, xb200_pic *p, int y0, int rows, void *d_dst) { return band_copy(c, p, y0, rows, (unsigned char *)d_dst, true); }
+int xb200_band_unpack(xb200_ctx *c, xb200_pic *p, int y0, int rows, const void *d_src) { return band_copy(c, p, y0, rows, (unsigned char *)d_src, false); }
 
 // ---- batched leaf kernels ---------------------------------------------------------------------------------------------
 int xb200_itdq_blocks_dev(xb200_ctx *c, const void *d_in, void *d_out, int n, int log2w, int log2h, int qp, int bit_depth, int iqt)

@@ -30,6 +30,7 @@ struct XbFrameArgs {
     int w, h;                   // luma size
     int bd_l, bd_c;
     int log2_ctu, w_ctu, n_ctu;
+    int ctu_row0;               // band mode: first CTU row of this launch (the CU arrays / ctu_first index CTUs relative to it)
     int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine;
     const XB200_CU *cus;
     const uint32_t *ctu_first;

@@ -646,7 +646,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     const int S = sm.S, Sc = sm.Sc, nscu = S >> 2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctu = blockIdx.x;
-    const int ctu_x = (ctu % a.w_ctu) << a.log2_ctu, ctu_y = (ctu / a.w_ctu) << a.log2_ctu;
+    const int ctu_x = (ctu % a.w_ctu) << a.log2_ctu, ctu_y = (ctu / a.w_ctu + a.ctu_row0) << a.log2_ctu;
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
     const XB200_CU *cus = a.cus + cu0;
     const int ncu = cu1 - cu0;

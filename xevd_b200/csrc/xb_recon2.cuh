@@ -241,7 +241,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctu = blockIdx.y * a.w_ctu + blockIdx.x;
-    const int ctu_x = blockIdx.x << 6, ctu_y = blockIdx.y << 6;
+    const int ctu_x = blockIdx.x << 6, ctu_y = (blockIdx.y + a.ctu_row0) << 6;
     const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
 
     // ---- stage CU descriptors, zero the residual, init barrier, build tap tables --------------------------------------------

@@ -163,6 +163,16 @@ class Context:
         f = np.ascontiguousarray(ctb_flag_luma, np.uint8) if ctb_flag_luma is not None else None
         self._chk(self.lib.xb200_alf(self.handle, C.byref(prm), pic.handle, C.byref(alf), f.ctypes.data if f is not None else None), "xb200_alf")
 
+    # -- band exchange (intra-picture multi-GPU sharding) ------------------------------------------------
+    def band_bytes(self, pic: DevicePicture, rows: int) -> int:
+        return int(self.lib.xb200_band_bytes(pic.handle, rows))
+
+    def band_pack(self, pic: DevicePicture, y0: int, rows: int, d_dst: int):
+        self._chk(self.lib.xb200_band_pack(self.handle, pic.handle, y0, rows, d_dst), "xb200_band_pack")
+
+    def band_unpack(self, pic: DevicePicture, y0: int, rows: int, d_src: int):
+        self._chk(self.lib.xb200_band_unpack(self.handle, pic.handle, y0, rows, d_src), "xb200_band_unpack")
+
     def pad(self, pic: DevicePicture):
         self._chk(self.lib.xb200_pad(self.handle, pic.handle), "xb200_pad")
 

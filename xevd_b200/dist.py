@@ -25,6 +25,48 @@ def my_gops(n_gops: int, rank: int, world: int) -> List[int]:
     return gop_shards(n_gops, world)[rank]
 
 
+def band_partition(h: int, log2_ctu: int, world: int) -> List[tuple]:
+    """(first CTU row, CTU rows) per rank: contiguous bands of CTU rows, sizes differing by at most one row (8K has
+    68 CTU rows -> four bands of 9 and four of 8)"""
+    n = (h + (1 << log2_ctu) - 1) >> log2_ctu
+    base, extra = divmod(n, world)
+    out, r0 = [], 0
+    for r in range(world):
+        k = base + (1 if r < extra else 0)
+        out.append((r0, k))
+        r0 += k
+    return out
+
+
+class BandExchange:
+    """Per-picture exchange step of intra-picture sharding: every rank has reconstructed its band of the current picture into its
+    own copy of the device picture; one in-place all-gather over NCCL (NVLink / NVSwitch) of the packed bands - planes plus
+    per-SCU maps - completes the picture on every GPU, where it serves as a reference for the next pictures.
+    Chunks are sized for the largest band so that a single equal-sized all-gather does the job."""
+
+    def __init__(self, ctx, pic, log2_ctu: int, rank: int, world: int, device):
+        import torch
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.bands = band_partition(pic.h, log2_ctu, world)
+        ctu = 1 << log2_ctu
+        self.rows = [(r0 * ctu, min(k * ctu, pic.h - r0 * ctu)) for r0, k in self.bands]       # luma rows (y0, rows)
+        self.chunk = max(ctx.band_bytes(pic, rows) for _, rows in self.rows if rows > 0)
+        self.buf = torch.empty(self.chunk * world, dtype=torch.uint8, device=device)
+
+    def exchange(self, pic):
+        import torch.distributed as dist
+        base = self.buf.data_ptr()
+        y0, rows = self.rows[self.rank]
+        if rows > 0:
+            self.ctx.band_pack(pic, y0, rows, base + self.rank * self.chunk)
+        if self.world > 1:
+            mine = self.buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
+            dist.all_gather_into_tensor(self.buf, mine)                 # in place: rank r's chunk is slot r of the output
+        for r, (yr, nr) in enumerate(self.rows):
+            if r != self.rank and nr > 0:
+                self.ctx.band_unpack(pic, yr, nr, base + r * self.chunk)
+
+
 def init(backend: str | None = None, device_index: int | None = None):
     """initialise torch.distributed from the torchrun environment (no-op for a single process)"""
     import torch

@@ -162,6 +162,19 @@ class CuList:
         assert run[-1] == self.coef.size
         return self
 
+    def band(self, ctu_row0: int, ctu_rows: int) -> "CuList":
+        """the work of CTU rows [ctu_row0, ctu_row0 + ctu_rows) as a self-contained list (band mode of xb200_recon_frame): CUs are in
+        CTU-raster order, so the band is one contiguous slice of the CU array and of the coefficient stream; offsets are rebased"""
+        ctu = 1 << self.log2_ctu
+        w_ctu = (self.w + ctu - 1) // ctu
+        c0, c1 = int(self.ctu_first[ctu_row0 * w_ctu]), int(self.ctu_first[(ctu_row0 + ctu_rows) * w_ctu])
+        cus = self.cus[c0:c1].copy()
+        k0 = int(self.cus["coef_off"][c0]) if c0 < len(self.cus) else self.coef.size
+        k1 = int(self.cus["coef_off"][c1]) if c1 < len(self.cus) else self.coef.size
+        cus["coef_off"] -= k0
+        first = (self.ctu_first[ctu_row0 * w_ctu:(ctu_row0 + ctu_rows) * w_ctu + 1].astype(np.int64) - c0).astype(np.uint32)
+        return CuList(w=self.w, h=self.h, log2_ctu=self.log2_ctu, cus=cus, ctu_first=first, coef=self.coef[k0:k1].copy(), ext=self.ext)
+
     def edge_flags(self) -> np.ndarray:
         """one byte per SCU: bit0 = CU/TU boundary on the left side, bit1 = on the top side, bit2 = ats_inter CU
         (what deblock_tree derives from map_split, src_base/xevd.c:1057-1114: CU boundaries plus the
