@@ -222,7 +222,18 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     F = args.frames_per_step
-    w, h, bd, variant, frames = make_workload(args.workload, min(4, F), seed0=1 + 10 * rank)
+    band = args.sharding == "band"
+    # GOP sharding: every rank has its own pictures.  Band sharding: every rank works on the SAME pictures, one CTU-row band each.
+    w, h, bd, variant, frames = make_workload(args.workload, min(4, F), seed0=1 + (0 if band else 10 * rank))
+    if band:
+        bands = xdist.band_partition(h, 6, world)
+        r0, k = bands[rank]
+        banded = []
+        for prm, cl in frames:
+            bp = type(prm).from_buffer_copy(prm)
+            bp.ctu_row0, bp.ctu_rows = r0, k
+            banded.append((bp, cl.band(r0, k)))
+        full_frames, frames = frames, banded
     n_refs = 1 if variant == "A" else 2
 
     stream = torch.cuda.Stream(device=dev)
@@ -230,7 +241,7 @@ def run_ours(args):
     ctx.set_stream(stream.cuda_stream)
 
     # ---- resident inputs: F slots, each with its own reference picture(s), CU array, coefficients, output picture
-    host_refs = synth.make_refs(w, h, bd, 2, seed=1000 + rank)
+    host_refs = synth.make_refs(w, h, bd, 2, seed=1000 + (0 if band else rank))
     slots = []
     with torch.cuda.stream(stream):
         for i in range(F):
@@ -246,13 +257,18 @@ def run_ours(args):
             slots.append(dict(prm=prm, cl=cl, refs=refs, refs_l1=(refs[::-1] if variant != "A" else []), cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef,
                               max_cu=int(np.diff(cl.ctu_first.astype(np.int64)).max())))
     torch.cuda.synchronize()
+    exch = xdist.BandExchange(ctx, slots[0]["cur"], 6, rank, world, dev) if band else None
 
     def step_resident():
         for s in slots:
             cl = s["cl"]
-            ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
-                                s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
-                                max_cu_per_ctu=s["max_cu"])
+            if cl.n_cu:
+                ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
+                                    s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
+                                    max_cu_per_ctu=s["max_cu"])
+            if exch is not None:
+                with torch.cuda.stream(stream):
+                    exch.exchange(s["cur"])              # one in-place NCCL all-gather of the packed bands per picture
             ctx.pad(s["cur"])
 
     def barrier():
@@ -280,7 +296,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     ms = xdist.max_over_ranks(ms, dev)
-    fps = world * F * args.steps / (ms * 1e-3)
+    fps = (1 if band else world) * F * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_recon_inter): per-launch CUDA-event timing on the launching stream --------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * min(args.steps, 4))]
@@ -298,16 +314,16 @@ def run_ours(args):
                 k += 1
     torch.cuda.synchronize()
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    alg = float(np.mean([algorithmic_bytes(w, h, s["cl"]) for s in slots]))
+    alg = float(np.mean([algorithmic_bytes(w, h, s["cl"]) for s in slots]))       # band mode: this rank's band
     peak, peak_src = measured_peak()
     achieved = alg / (kern_ms * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------------------------------------
-    n_ctx = 3
+    n_ctx = 1 if band else 3          # band mode: the exchange orders every picture on one stream
     ctxs, streams = [], []
     for i in range(n_ctx):
-        st = torch.cuda.Stream(device=dev)
-        c = Context(local)
+        st = stream if band else torch.cuda.Stream(device=dev)
+        c = ctx if band else Context(local)
         c.set_stream(st.cuda_stream)
         ctxs.append(c); streams.append(st)
     pinned = []
@@ -329,19 +345,25 @@ def run_ours(args):
         e2e_slots.append(dict(ctx=c, refs=refs, cur=c.pic_alloc(w, h)))
     torch.cuda.synchronize()
     h2d = int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
-    d2h = F * (w * h * 3 // 2) * 2
+    d2h = F * (w * h * 3 // 2) * 2 if (not band or rank == 0) else 0       # band mode: rank 0 hands the assembled pictures to the consumer
 
     def step_e2e():
         for i in range(F):
             prm, cl = frames[i % len(frames)]
             s, p = e2e_slots[i], pinned[i]
             c = s["ctx"]
-            c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
-                                           (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
-                                           (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
-                                           p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
-                                           p["ext"].data_ptr(), len(cl.ext), p["coef"].data_ptr(), cl.coef.size), "xb200_recon_frame")
+            if cl.n_cu:
+                c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
+                                               (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
+                                               (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
+                                               p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
+                                               p["ext"].data_ptr(), len(cl.ext), p["coef"].data_ptr(), cl.coef.size), "xb200_recon_frame")
+            if exch is not None:
+                with torch.cuda.stream(stream):
+                    exch.exchange(s["cur"])
             c.pad(s["cur"])
+            if band and rank != 0:
+                continue
             c._chk(c.lib.xb200_pic_download(c.handle, s["cur"].handle, p["out_y"].data_ptr(), w, p["out_u"].data_ptr(), w // 2,
                                             p["out_v"].data_ptr(), w // 2), "xb200_pic_download")
         for c in ctxs:
@@ -357,7 +379,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     t_e2e = xdist.max_over_ranks(t_e2e, dev)
-    e2e_fps = world * F * e2e_steps / t_e2e
+    e2e_fps = (1 if band else world) * F * e2e_steps / t_e2e
     # a decoded sample read back on the host proves the D2H happened
     checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())
 
@@ -368,11 +390,12 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if band else "weak", "vs_baseline": None,
             "dtype": "s16", "data": "synthetic",
-            "config": {"workload": args.workload, "frames_per_step": F * world, "picture": f"{w}x{h} 4:2:0 {bd}-bit",
+            "config": {"workload": args.workload, "frames_per_step": F * (1 if band else world), "picture": f"{w}x{h} 4:2:0 {bd}-bit",
                        "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
-                       "per_picture": "xb200_recon_frame_dev + xb200_pad", "parallelism": f"gop-sharded x{world}",
+                       "per_picture": "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad" if band else "xb200_recon_frame_dev + xb200_pad",
+                       "parallelism": f"ctu-row bands x{world} (one all-gather per picture)" if band else f"gop-sharded x{world}",
                        "l2": f"inputs larger than L2 ({F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per step per GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
@@ -398,6 +421,9 @@ def main():
     ap.add_argument("--workload", default="4k-2A", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="gop", choices=["gop", "band"],
+                    help="gop: independent pictures per GPU (weak scaling, default); band: every picture split into CTU-row bands across the GPUs, "
+                         "one NCCL all-gather per picture (strong scaling, BASELINE config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
