@@ -222,7 +222,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
 
     F = args.frames_per_step
-    band = args.sharding == "band"
+    band = args.sharding in ("band", "band-p2p")
+    p2p = args.sharding == "band-p2p"
     # GOP sharding: every rank has its own pictures.  Band sharding: every rank works on the SAME pictures, one CTU-row band each.
     w, h, bd, variant, frames = make_workload(args.workload, min(4, F), seed0=1 + (0 if band else 10 * rank))
     if band:
@@ -257,7 +258,18 @@ def run_ours(args):
             slots.append(dict(prm=prm, cl=cl, refs=refs, refs_l1=(refs[::-1] if variant != "A" else []), cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef,
                               max_cu=int(np.diff(cl.ctu_first.astype(np.int64)).max())))
     torch.cuda.synchronize()
-    exch = xdist.BandExchange(ctx, slots[0]["cur"], 6, rank, world, dev) if band else None
+    exch = xdist.BandExchange(ctx, slots[0]["cur"], 6, rank, world, dev) if (band and not p2p) else None
+    flag = torch.zeros(1, device=dev)
+    if p2p:
+        for s in slots:
+            xdist.open_peer_pictures(ctx, s["cur"])       # once per picture buffer: map the other ranks' copies (CUDA IPC)
+        torch.cuda.synchronize()
+        xdist.barrier()
+
+    def stream_barrier():
+        if dist is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(flag)                     # tiny collective in stream order: all peer stores of this picture have landed
 
     def step_resident():
         for s in slots:
@@ -269,6 +281,8 @@ def run_ours(args):
             if exch is not None:
                 with torch.cuda.stream(stream):
                     exch.exchange(s["cur"])              # one in-place NCCL all-gather of the packed bands per picture
+            elif p2p:
+                stream_barrier()
             ctx.pad(s["cur"])
 
     def barrier():
@@ -340,6 +354,9 @@ def run_ours(args):
     # pictures owned per context (a device picture belongs to the stream that fills it)
     e2e_slots = []
     for i in range(F):
+        if band:        # same pictures as the resident leg (their peer mappings / exchange buffers already exist)
+            e2e_slots.append(dict(ctx=ctx, refs=slots[i]["refs"], cur=slots[i]["cur"]))
+            continue
         c = ctxs[i % n_ctx]
         refs = [c.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
         e2e_slots.append(dict(ctx=c, refs=refs, cur=c.pic_alloc(w, h)))
@@ -361,6 +378,8 @@ def run_ours(args):
             if exch is not None:
                 with torch.cuda.stream(stream):
                     exch.exchange(s["cur"])
+            elif p2p:
+                stream_barrier()
             c.pad(s["cur"])
             if band and rank != 0:
                 continue
@@ -394,8 +413,9 @@ def run_ours(args):
             "dtype": "s16", "data": "synthetic",
             "config": {"workload": args.workload, "frames_per_step": F * (1 if band else world), "picture": f"{w}x{h} 4:2:0 {bd}-bit",
                        "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
-                       "per_picture": "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad" if band else "xb200_recon_frame_dev + xb200_pad",
-                       "parallelism": f"ctu-row bands x{world} (one all-gather per picture)" if band else f"gop-sharded x{world}",
+                       "per_picture": ("xb200_recon_frame_dev (band, stores fanned out to the peer GPUs over NVLink) + stream barrier + xb200_pad" if p2p else
+                                       "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad") if band else "xb200_recon_frame_dev + xb200_pad",
+                       "parallelism": (f"ctu-row bands x{world} (peer stores fused into the kernel)" if p2p else f"ctu-row bands x{world} (one all-gather per picture)") if band else f"gop-sharded x{world}",
                        "l2": f"inputs larger than L2 ({F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per step per GPU)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
@@ -421,7 +441,7 @@ def main():
     ap.add_argument("--workload", default="4k-2A", choices=sorted(WORKLOADS))
     ap.add_argument("--frames-per-step", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", default="gop", choices=["gop", "band"],
+    ap.add_argument("--sharding", default="gop", choices=["gop", "band", "band-p2p"],
                     help="gop: independent pictures per GPU (weak scaling, default); band: every picture split into CTU-row bands across the GPUs, "
                          "one NCCL all-gather per picture (strong scaling, BASELINE config 4)")
     args = ap.parse_args()

@@ -269,6 +269,14 @@ int  xb200_pad(xb200_ctx *ctx, xb200_pic *pic);           /* xevd_picbuf_expand 
  * that follows reconstruction - and unpack writes a band received from another GPU into the picture.
  * Layout: Y rows (w samples each) | U | V | map_mv | map_unrefined_mv | map_scu | map_refi | map_edge.                        */
 size_t xb200_band_bytes(xb200_pic *pic, int rows);
+/* Fused alternative (NVLink peer stores, no separate exchange): every rank exports its copy of the picture as a CUDA IPC handle
+ * (64 bytes, shipped to the other ranks by the host plumbing) and opens the others' handles; a band-mode xb200_recon_frame on a
+ * picture with open peers then writes every reconstructed sample and map entry into all copies directly from the kernel, so the
+ * transfer overlaps the arithmetic.  The ranks only need a barrier (any tiny collective on the stream) before using the picture.
+ * Pictures must have identical geometry on all ranks.  Available for the Baseline-transform 64x64-CTU kernel; other
+ * configurations use xb200_band_pack / all-gather / xb200_band_unpack.                                                      */
+int  xb200_pic_export(xb200_ctx *ctx, xb200_pic *pic, void *handle64);
+int  xb200_pic_open_peer(xb200_ctx *ctx, xb200_pic *pic, const void *handle64);
 int  xb200_band_pack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, void *d_dst);
 int  xb200_band_unpack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, const void *d_src);
 

@@ -15,6 +15,7 @@ def main():
     import torch
     from xevd_b200 import dist as xdist, synth
     from xevd_b200.device import Context
+    p2p = "--p2p" in sys.argv        # exchange fused into the kernel's stores (NVLink peer writes) instead of the all-gather
     rank, world, local = xdist.init("nccl")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -35,9 +36,19 @@ def main():
             ex = ex or xdist.BandExchange(ctx, cur, lg, rank, world, dev)
             r0, k = bands[rank]
             prm.ctu_row0, prm.ctu_rows = r0, k
+            if p2p:
+                ctx.sync()                                   # the zero-fill of the fresh pictures must not race the peers' stores
+                xdist.open_peer_pictures(ctx, cur)
+                xdist.barrier()
             if k > 0:
                 ctx.recon_frame(prm, cur, [d_ref], [], cl.band(r0, k))
-            ex.exchange(cur)
+            if p2p:
+                flag = torch.zeros(1, device=dev)
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(flag)                    # barrier on the stream: every rank's kernel (and its peer stores) is complete
+            else:
+                ex.exchange(cur)
             ctx.pad(cur)
             ctx.sync()
             prm.ctu_row0 = prm.ctu_rows = 0
@@ -59,7 +70,7 @@ def main():
     if int(t.item()):
         sys.exit(1)
     if rank == 0:
-        print(f"band sharding parity OK on {world} GPU(s)")
+        print(f"band sharding parity OK on {world} GPU(s)" + (" [peer stores]" if p2p else " [all-gather]"))
 
 
 if __name__ == "__main__":

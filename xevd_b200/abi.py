@@ -122,6 +122,8 @@ _SIGS = {
     "xb200_pic_download_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_edge_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_pic_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_pic_open_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_band_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "xb200_band_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "xb200_band_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -30,6 +30,9 @@ struct xb200_pic {
     int8_t *map_refi;
     uint32_t *map_scu;
     uint8_t *map_edge;
+    size_t alloc_bytes;
+    int n_peer;                  // twins of this picture on other GPUs, opened over CUDA IPC (band mode with P2P stores)
+    void *peer_base[7];
 };
 
 struct Staging {                 // one slot of the host->device staging ring
@@ -108,6 +111,8 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_intra<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256, true).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256, true).total);
     {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
         static const int8_t base[58] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                         29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41};
@@ -268,6 +273,8 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
         if (err) *err = XB200_ERR_OUT_OF_MEMORY;
         return nullptr;
     }
+    p->alloc_bytes = total;
+    p->n_peer = 0;
     cudaMemsetAsync(p->buf, 0, total, c->stream);
     p->y = p->buf + (size_t)p->pad_l * p->s_l + p->pad_l;
     p->u = p->buf + p->luma_elems + (size_t)p->pad_c * p->s_c + p->pad_c;
@@ -293,6 +300,7 @@ void xb200_pic_free(xb200_ctx *c, xb200_pic *p)
 {
     if (!p) return;
     if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    for (int k = 0; k < p->n_peer; k++) cudaIpcCloseMemHandle(p->peer_base[k]);
     cudaFree(p->buf);
     delete p;
 }
@@ -395,10 +403,14 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.log2_ctu = prm->log2_ctu;
     a.w_ctu = (cur->w + (1 << a.log2_ctu) - 1) >> a.log2_ctu;
     a.n_ctu = a.w_ctu * ((cur->h + (1 << a.log2_ctu) - 1) >> a.log2_ctu);
+    a.n_peer = 0;
     if (prm->ctu_rows > 0) {        // band mode: this launch covers CTU rows [ctu_row0, ctu_row0 + ctu_rows)
         if (prm->ctu_row0 < 0 || (prm->ctu_row0 + prm->ctu_rows) * a.w_ctu > a.n_ctu) return XB200_ERR_INVALID_ARGUMENT;
         a.ctu_row0 = prm->ctu_row0;
         a.n_ctu = prm->ctu_rows * a.w_ctu;
+        a.n_peer = cur->n_peer;
+        { const char *e = getenv("XB200_PEER_NOMAPS"); a.peer_maps = !(e && e[0] == '1'); }
+        for (int k = 0; k < cur->n_peer; k++) a.peer_delta[k] = (long long)((char *)cur->peer_base[k] - (char *)cur->buf);
     }
     a.main_tables = prm->tool_admvp ? 1 : 0;
     a.iqt = prm->tool_iqt ? 1 : 0;
@@ -425,6 +437,8 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     (void)n_ext; (void)n_coef;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
     if (has_intra && prm->ctu_rows > 0) return XB200_ERR_UNSUPPORTED;          // the wavefront crosses band boundaries
+    const bool fast = !a.iqt && !a.ats && !a.dmvr && !a.affine && a.log2_ctu == 6 && !c->force_generic;
+    if (a.n_peer > 0 && !fast) return XB200_ERR_UNSUPPORTED;                   // peer stores exist in the throughput kernel only; use the all-gather exchange
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
     a.cus = (const XB200_CU *)d_cus;
@@ -437,10 +451,14 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;
         const bool bi = n1 > 0;
-        const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu);
+        const bool peer = a.n_peer > 0;
+        const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu, peer);
         const dim3 grid(a.w_ctu, a.n_ctu / a.w_ctu);
-        if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-        else    xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        if (peer) {
+            if (bi) xb::k_recon_inter_v2<true, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+            else    xb::k_recon_inter_v2<false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        } else if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        else           xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
     } else {
         const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
         if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
@@ -654,6 +672,27 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     xb::launch_deblock(a, prm->tool_addb != 0, c->stream);
     c->launches += 2;
     CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+// ---- peer pictures (CUDA IPC): band mode with the exchange fused into the kernel's stores --------------------------------
+int xb200_pic_export(xb200_ctx *c, xb200_pic *p, void *handle64)
+{
+    if (!c || !p || !handle64) return XB200_ERR_INVALID_ARGUMENT;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaSetDevice(c->device);
+    CK(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, p->buf));
+    return XB200_OK;
+}
+int xb200_pic_open_peer(xb200_ctx *c, xb200_pic *p, const void *handle64)
+{
+    if (!c || !p || !handle64 || p->n_peer >= 7) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *base = nullptr;
+    CK(c, cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_base[p->n_peer++] = base;
     return XB200_OK;
 }
 

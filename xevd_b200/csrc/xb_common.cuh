@@ -30,6 +30,9 @@ struct XbFrameArgs {
     int w, h;                   // luma size
     int bd_l, bd_c;
     int log2_ctu, w_ctu, n_ctu;
+    int peer_maps;              // debug: 0 = keep the per-SCU maps local (XB200_PEER_NOMAPS=1)
+    int n_peer;                 // band mode over NVLink: every output store is repeated into the same picture on n_peer other GPUs
+    long long peer_delta[7];    //   byte distance from this GPU's picture allocation to the peer's mapping of its twin (same layout)
     int ctu_row0;               // band mode: first CTU row of this launch (the CU arrays / ctu_first index CTUs relative to it)
     int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine;
     const XB200_CU *cus;
@@ -47,6 +50,15 @@ struct XbFrameArgs {
 // CUs that read samples of the CURRENT picture (intra prediction, intra block copy) are reconstructed by the CTU wavefront
 // kernel (xb_intra.cuh); everything else by the fully parallel inter kernels
 __host__ __device__ __forceinline__ bool xb_wavefront_mode(int mode) { return mode == XB200_MODE_INTRA || mode == XB200_MODE_IBC; }
+
+// store to the local picture and to its twins on the peer GPUs (P2P stores over NVLink; no-op loop when n_peer == 0)
+template <typename T>
+__device__ __forceinline__ void xb_store_all(const XbFrameArgs &a, T *dst, T v, bool fan_out = true)
+{
+    *dst = v;
+    if (fan_out)
+        for (int k = 0; k < a.n_peer; k++) *(T *)((char *)dst + a.peer_delta[k]) = v;
+}
 
 __device__ __forceinline__ int xb_clip3(int lo, int hi, int v) { return max(lo, min(hi, v)); }
 __device__ __forceinline__ int xb_clip16(int v) { return max(-32768, min(32767, v)); }

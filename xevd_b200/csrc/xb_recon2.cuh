@@ -74,8 +74,8 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
 // 32 consecutive line tasks run the same butterfly size; line -> block lookup is a binary search over the
 // per-block line prefix sums (no per-line lists).
 struct R2Layout {
-    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, tiles, preds, offs, taps, total;
-    __host__ __device__ static R2Layout make(int nl, int max_cu)
+    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, tiles, preds, offs, taps, out, total;
+    __host__ __device__ static R2Layout make(int nl, int max_cu, bool peer = false)
     {
         R2Layout L;
         int o = 128;                                                       // [0,128): mbarrier + counters
@@ -95,6 +95,8 @@ struct R2Layout {
         L.preds = o; o += 16 * 2 * max_tiles;
         L.offs = o; o += 4 * 8 * max_cu;                // per-CU exclusive offsets (scan output)
         L.taps = o; o += 4 * (16 * 9 + 32 * 6);
+        o = (o + 15) & ~15;
+        L.out = o; if (peer) o += 2 * (64 * 64 + 2 * 32 * 32) + 256 * (8 + 4 + 2 + 1) + 16;   // PEER: reconstructed CTU + its map entries staged for wide row stores to every GPU
         L.total = (o + 127) & ~127;
         return L;
     }
@@ -221,13 +223,16 @@ __device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstrid
     for (int k = 0; k < N; k++) dst[k * dstride] = (int16_t)pack_sat16(out[k] >> sh2, 0);
 }
 
-template <bool BI>
+// PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
+// local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
+template <bool BI, bool PEER = false>
 __global__ void __launch_bounds__(kR2Threads, 2)
 k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NL = BI ? 2 : 1;
-    const R2Layout L = R2Layout::make(NL, max_cu);
+    const R2Layout L = R2Layout::make(NL, max_cu, PEER);
+    int16_t *s_out = (int16_t *)(smem + L.out);                 // [64][64] luma, then [2][32][32] chroma
     uint64_t *mbar = (uint64_t *)smem;
     int *cnt = (int *)(smem + 16);           // totals: [0] luma blocks [1] chroma blocks [2,3] pass-1 lines y,c [4,5] pass-2 y,c [6] tiles
     XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
@@ -602,8 +607,11 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
 #pragma unroll
                     for (int r = 0; r < 8; r++)
-                        if (8 * rg + r < td.th)
-                            *(int *)(dst + (size_t)r * a.s_l) = __viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+                        if (8 * rg + r < td.th) {
+                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+                            if (PEER) *(int *)(s_out + (y + r) * 64 + x) = v;
+                            else *(int *)(dst + (size_t)r * a.s_l) = v;
+                        }
                 }
             }
         }
@@ -646,15 +654,42 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
 #pragma unroll
                     for (int r = 0; r < 4; r++)
-                        if (4 * rg + r < ch)
-                            *(int *)(dst + (size_t)r * a.s_c) = __viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+                        if (4 * rg + r < ch) {
+                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+                            if (PEER) *(int *)(s_out + 64 * 64 + pl * 32 * 32 + (y + r) * 32 + x) = v;
+                            else *(int *)(dst + (size_t)r * a.s_c) = v;
+                        }
                 }
             }
         }
         if (round + 1 < n_rounds) __syncthreads();      // the next round's TMA overwrites every warp's windows
     }
 
+    if (PEER) {
+        // copy-out: 16 bytes per thread, eight threads cover one 128-byte luma row of the CTU; same words to every GPU
+        __syncthreads();
+        const int rows_l = min(64, a.h - ctu_y), cols_l = min(64, a.w - ctu_x);
+        for (int i = tid; i < 64 * 8; i += kR2Threads) {
+            const int r = i >> 3, c8 = (i & 7) << 3;
+            if (r < rows_l && c8 < cols_l)
+                xb_store_all(a, (int4 *)(a.cur.y + (size_t)(ctu_y + r) * a.s_l + ctu_x + c8), *(const int4 *)(s_out + r * 64 + c8));
+        }
+        for (int i = tid; i < 2 * 32 * 4; i += kR2Threads) {
+            const int pl = i >> 7, r = (i >> 2) & 31, c8 = (i & 3) << 3;
+            if (r < (rows_l >> 1) && c8 < (cols_l >> 1))
+                xb_store_all(a, (int4 *)((pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + r) * a.s_c + (ctu_x >> 1) + c8),
+                             *(const int4 *)(s_out + 64 * 64 + pl * 32 * 32 + r * 32 + c8));
+        }
+    }
+
     // ---- publish per-SCU maps (xevd_set_dec_info) ------------------------------------------------------------------------------
+    // PEER: entries are collected per CTU (16 x 16 SCUs) and written as 16-byte words, because narrow stores to peer memory cost one
+    // NVLink request each (measured: they doubled the kernel time, profiles/r1)
+    int2 *sm_mv = (int2 *)(s_out + 64 * 64 + 2 * 32 * 32);
+    uint32_t *sm_scu = (uint32_t *)(sm_mv + 256);
+    int16_t *sm_refi = (int16_t *)(sm_scu + 256);
+    uint8_t *sm_edge = (uint8_t *)(sm_refi + 256);
+    const bool wide_maps = PEER && (a.w_scu & 15) == 0;
     for (int i = tid; i < ncu; i += kR2Threads) {
         const XB200_CU cu = s_cu[i];
         const int sx = cu.x >> 2, sy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
@@ -666,13 +701,35 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         const int16_t rf = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
         for (int y = 0; y < nh; y++)
             for (int x = 0; x < nw; x++) {
+                const uint8_t e = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
+                if (wide_maps) {
+                    const int q = ((sy + y) & 15) * 16 + ((sx + x) & 15);
+                    sm_mv[q] = mv; sm_scu[q] = m; sm_refi[q] = rf; sm_edge[q] = e;
+                    continue;
+                }
                 const int p = (sy + y) * a.w_scu + sx + x;
-                a.map_scu[p] = m;
-                ((int2 *)a.map_mv)[p] = mv;
-                ((int2 *)a.map_unrefined_mv)[p] = mv;
-                ((int16_t *)a.map_refi)[p] = rf;
-                a.map_edge[p] = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
+                const bool fo = a.peer_maps != 0;
+                xb_store_all(a, a.map_scu + p, m, fo);
+                xb_store_all(a, (int2 *)a.map_mv + p, mv, fo);
+                xb_store_all(a, (int2 *)a.map_unrefined_mv + p, mv, fo);
+                xb_store_all(a, (int16_t *)a.map_refi + p, rf, fo);
+                xb_store_all(a, a.map_edge + p, e, fo);
             }
+    }
+    if (wide_maps) {
+        __syncthreads();
+        const int rows = min(16, a.h_scu - (ctu_y >> 2));
+        const int p0 = (ctu_y >> 2) * a.w_scu + (ctu_x >> 2);              // the CTU's 16 SCU columns all exist when w_scu % 16 == 0
+        for (int i = tid; i < 16 * 23; i += kR2Threads) {
+            const int r = i / 23, k = i - r * 23;
+            if (r >= rows) continue;
+            const int p = p0 + r * a.w_scu;
+            if (k < 8) { const int4 v = ((const int4 *)(sm_mv + r * 16))[k]; xb_store_all(a, (int4 *)((int2 *)a.map_mv + p) + k, v); xb_store_all(a, (int4 *)((int2 *)a.map_unrefined_mv + p) + k, v); }
+            else if (k < 16) continue;          // (slots 8..15: the unrefined map shares the store above)
+            else if (k < 20) xb_store_all(a, (int4 *)(a.map_scu + p) + (k - 16), ((const int4 *)(sm_scu + r * 16))[k - 16]);
+            else if (k < 22) xb_store_all(a, (int4 *)((int16_t *)a.map_refi + p) + (k - 20), ((const int4 *)(sm_refi + r * 16))[k - 20]);
+            else xb_store_all(a, (int4 *)(a.map_edge + p), *(const int4 *)(sm_edge + r * 16));
+        }
     }
 }
 

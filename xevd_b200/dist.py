@@ -67,6 +67,23 @@ class BandExchange:
                 self.ctx.band_unpack(pic, yr, nr, base + r * self.chunk)
 
 
+def open_peer_pictures(ctx, pic):
+    """band mode with peer stores: exchange the CUDA IPC handles of every rank's copy of `pic` (host plumbing, once per picture
+    buffer) and map the other ranks' copies into this process"""
+    import ctypes as C
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    h = (C.c_ubyte * 64)()
+    ctx._chk(ctx.lib.xb200_pic_export(ctx.handle, pic.handle, h), "xb200_pic_export")
+    handles = [None] * dist.get_world_size()
+    dist.all_gather_object(handles, bytes(h))
+    for r, hb in enumerate(handles):
+        if r != dist.get_rank():
+            buf = (C.c_ubyte * 64).from_buffer_copy(hb)
+            ctx._chk(ctx.lib.xb200_pic_open_peer(ctx.handle, pic.handle, buf), "xb200_pic_open_peer")
+
+
 def init(backend: str | None = None, device_index: int | None = None):
     """initialise torch.distributed from the torchrun environment (no-op for a single process)"""
     import torch
