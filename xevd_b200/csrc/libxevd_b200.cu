@@ -109,6 +109,8 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
     cudaFuncSetAttribute(xb::k_recon_intra<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
     cudaFuncSetAttribute(xb::k_recon_intra<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
+    cudaFuncSetAttribute(xb::k_itdq_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 65 * (int)sizeof(int));
+    cudaFuncSetAttribute(xb::k_itdq_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 65 * (int)sizeof(int));
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256, true).total);

@@ -21,22 +21,43 @@ namespace xb {
 
 constexpr int kIntraThreads = 256;
 
+// Shared memory of the wavefront kernel.  The serial chain CU -> CU is the critical path of an I picture, so everything a CU needs
+// is kept on chip: the residual of every wavefront CU of the CTU (computed BEFORE the CTA waits for its neighbour CTUs - it does
+// not depend on them), the CTU's reconstructed samples (inter CUs preloaded from the picture, wavefront CUs written as they
+// finish, mirrored to global memory), and the row above / column left of the CTU fetched once after the wait.
 struct IntraSmem {
-    // residual of the current CU, CU-raster: luma up to 128x128, chroma 2 x 64x64
-    static constexpr int kResElems = 128 * 128 + 2 * 64 * 64;
-    static constexpr int kTmpElems = 64 * 65;          // pass-1 buffer of one transform block
-    static constexpr int kNbElems = 3 * (2 * 128 + 8); // up[-1..w+h), left[-1..w+h), right[-1..w+h)
-    static size_t bytes() { return sizeof(int16_t) * kResElems + sizeof(int) * kTmpElems + sizeof(int16_t) * 3 * kNbElems + 64; }
+    static constexpr int kPlaneElems = 128 * 128 + 2 * 64 * 64;     // CTU-raster, luma then Cb, Cr (plane stride = plane CTU size)
+    static constexpr int kTopElems = 2 * 128 + 8;                   // per plane: x = -1 .. 2 * S - 1 of the row above
+    static constexpr int kLeftElems = 128;                          // per plane: the column left of the CTU
+    static constexpr int kTmpElems = 64 * 65;                       // pass-1 buffer of one transform block / HTDF ring block
+    static constexpr int kNbElems = 3 * (2 * 128 + 8);              // up[-1..w+h), left[-1..w+h), right[-1..w+h)
+    static size_t bytes()
+    {
+        return sizeof(int16_t) * (2 * kPlaneElems + 3 * kTopElems + 3 * kLeftElems + 3 * kNbElems) + sizeof(int) * kTmpElems + 64;
+    }
+};
+
+// one plane of the current CTU: on-chip samples + the global picture they mirror
+struct PlaneCtx {
+    int16_t *rec;       // [Sp][Sp] reconstructed samples of the CTU
+    int16_t *top;       // top[x], x = -1 .. 2 * Sp - 1: the row above the CTU
+    int16_t *left;      // left[y], y = 0 .. Sp - 1: the column left of the CTU
+    int16_t *res;       // [Sp][Sp] residual of the wavefront CUs
+    pel *g;             // global plane at the CTU origin
+    int gs, Sp;
+    // X, Y relative to the CTU; only positions the availability rules allow are ever asked for
+    __device__ __forceinline__ int get(int X, int Y) const { return Y < 0 ? top[X] : (X < 0 ? left[Y] : rec[Y * Sp + X]); }
+    __device__ __forceinline__ void put(int X, int Y, int v) const { rec[Y * Sp + X] = (int16_t)v; g[(size_t)Y * gs + X] = (pel)v; }
 };
 
 // residual of one plane of one CU (all threads of the CTA): blocks larger than 64 (chroma: 32) are cut into sub-blocks gated
 // by the nnz_sub bits; the result lands CU-raster in `res` (stride = plane width)
 template <bool IQT>
 __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int lh, int lmax, int bits, int qp, int bd,
-                                  int16_t *res, int *tmp, int tid, int nthreads, int ats = -1)
+                                  int16_t *res, int rs, int *tmp, int tid, int nthreads, int ats = -1)
 {
     const int pw = 1 << lw, ph = 1 << lh;
-    for (int i = tid; i < pw * ph; i += nthreads) res[i] = 0;
+    for (int i = tid; i < pw * ph; i += nthreads) res[(i >> lw) * rs + (i & (pw - 1))] = 0;
     const int slw = min(lw, lmax), slh = min(lh, lmax);
     const int nx = 1 << (lw - slw), ny = 1 << (lh - slh);
     const int w = 1 << slw, h = 1 << slh, ts = w + 1;
@@ -56,7 +77,7 @@ __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int 
             __syncthreads();
             for (int y = tid; y < h; y += nthreads) {
                 const int *srow = tmp + y * ts;
-                int16_t *drow = res + ((j << slh) + y) * pw + (i << slw);
+                int16_t *drow = res + ((j << slh) + y) * rs + (i << slw);
                 if (ats >= 0) ats_line_dyn(slw, ats >> 1, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, 20 - bd);
                 else itx_line_dyn<false>(slw, [&](int k) { return srow[k]; }, [&](int n, int v) { drow[n] = (int16_t)v; }, sh2);
             }
@@ -65,29 +86,30 @@ __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int 
 }
 
 // xevd_get_nbr_b for one plane: up[-1 .. w+h), left[-1 .. h+w); unit = samples per SCU (4 luma, 2 chroma)
-__device__ void intra_gather(const pel *rec, int s, int w, int h, int unit, unsigned long long up_mask, unsigned long long left_mask,
+// (cx, cy): position of the CU inside the CTU plane
+__device__ void intra_gather(const PlaneCtx &pc, int cx, int cy, int w, int h, int unit, unsigned long long up_mask, unsigned long long left_mask,
                              bool up_left, int dflt, int16_t *up, int16_t *left, int tid, int nthreads)
 {
     const int n = w + h;
     const int ush = unit == 4 ? 2 : 1;
     for (int i = tid; i < 2 * n + 1; i += nthreads) {
         if (i == 2 * n) {
-            // L2 loads: the line may sit stale in this SM's L1 from before a neighbouring CTA wrote it
-            const int v = up_left ? __ldcg(rec - s - 1) : dflt;
+            const int v = up_left ? pc.get(cx - 1, cy - 1) : dflt;
             up[-1] = (int16_t)v; left[-1] = (int16_t)v;
         } else if (i < n) {
-            up[i] = (int16_t)(((up_mask >> (i >> ush)) & 1) ? __ldcg(rec - s + i) : dflt);
+            up[i] = (int16_t)(((up_mask >> (i >> ush)) & 1) ? pc.get(cx + i, cy - 1) : dflt);
         } else {
             const int k = i - n;
-            left[k] = (int16_t)(((left_mask >> (k >> ush)) & 1) ? __ldcg(rec + (ptrdiff_t)k * s - 1) : dflt);
+            left[k] = (int16_t)(((left_mask >> (k >> ush)) & 1) ? pc.get(cx - 1, cy + k) : dflt);
         }
     }
 }
 
 // xevd_ipred_b + xevd_recon for one plane; modes IPD_DC_B 0, HOR 1, VER 2, UL 3, UR 4
-__device__ void intra_pred_recon(pel *rec, int s, int w, int h, int lw, int mode, const int16_t *up, const int16_t *left,
-                                 const int16_t *res, bool coded, int maxv, int *scratch, int tid, int nthreads)
+__device__ void intra_pred_recon(const PlaneCtx &pc, int cx, int cy, int w, int h, int lw, int mode, const int16_t *up, const int16_t *left,
+                                 bool coded, int maxv, int *scratch, int tid, int nthreads)
 {
+    const int16_t *res = pc.res + cy * pc.Sp + cx;
     if (mode == 0) {
         // DC = (sum(left[0..h)) + sum(up[0..w)) + w) >> (log2 w + 1): warp 0 reduces
         if (tid < 32) {
@@ -111,8 +133,8 @@ __device__ void intra_pred_recon(pel *rec, int s, int w, int h, int lw, int mode
         case 3: p = y > x ? left[y - x - 1] : (y == x ? up[-1] : up[x - y - 1]); break;
         default: p = (up[x + y + 1] + left[x + y + 1]) >> 1; break;
         }
-        const int r = coded ? res[i] : 0;
-        rec[(size_t)y * s + x] = (pel)xb_clip3(0, maxv, (int16_t)(p + r));      // xevd_recon: s16 wrap, then clip
+        const int r = coded ? res[y * pc.Sp + x] : 0;
+        pc.put(cx + x, cy + y, xb_clip3(0, maxv, (int16_t)(p + r)));            // xevd_recon: s16 wrap, then clip
     }
 }
 
@@ -122,25 +144,26 @@ __device__ void intra_pred_recon(pel *rec, int s, int w, int h, int lw, int mode
 // nearest available unit before it, else the scan's start value.  The corner up[-1] becomes up[0] when the up-left unit is
 // unavailable (the reference's loop over the units left of the corner overwrites it, :85-104).
 struct NbSrc {
-    const pel *rec;
-    int s, w, ush, dflt;
+    const PlaneCtx *pc;
+    int cx, cy;                 // CU position inside the CTU plane
+    int w, ush, dflt;
     unsigned long long um, lm, rm;
     bool ul;
     __device__ __forceinline__ int up(int i) const
     {
         const int k = i >> ush;
-        if ((um >> k) & 1) return __ldcg(rec - s + i);
+        if ((um >> k) & 1) return pc->get(cx + i, cy - 1);
         const unsigned long long m = um & ((1ull << k) - 1);
-        if (m) return __ldcg(rec - s + (((63 - __clzll((long long)m)) + 1) << ush) - 1);
-        return ul ? __ldcg(rec - s - 1) : dflt;
+        if (m) return pc->get(cx + (((63 - __clzll((long long)m)) + 1) << ush) - 1, cy - 1);
+        return ul ? pc->get(cx - 1, cy - 1) : dflt;
     }
-    __device__ __forceinline__ int corner() const { return ul ? __ldcg(rec - s - 1) : up(0); }
+    __device__ __forceinline__ int corner() const { return ul ? pc->get(cx - 1, cy - 1) : up(0); }
     __device__ __forceinline__ int side(int i, unsigned long long mask, int col, int start) const
     {
         const int k = i >> ush;
-        if ((mask >> k) & 1) return __ldcg(rec + (ptrdiff_t)i * s + col);
+        if ((mask >> k) & 1) return pc->get(cx + col, cy + i);
         const unsigned long long m = mask & ((1ull << k) - 1);
-        if (m) return __ldcg(rec + (ptrdiff_t)((((63 - __clzll((long long)m)) + 1) << ush) - 1) * s + col);
+        if (m) return pc->get(cx + col, cy + (((63 - __clzll((long long)m)) + 1) << ush) - 1);
         return start;
     }
 };
@@ -199,9 +222,10 @@ __device__ __forceinline__ int intra_ang_px(const int16_t *up, const int16_t *le
 // xevdm_ipred / xevdm_ipred_uv + xevdm_recon for one plane (src_main/xevdm_ipred.c:153-305; shared predictors
 // src_base/xevd_ipred.c:110-372).  ipm: 0 DC, 1 planar, 2 bilinear, 12 vertical, 24 horizontal, others angular.
 // pmax clips the predictor (plane bit depth), rmax the reconstruction (luma bit depth, xevdm_recon.c).
-__device__ void intra_pred_recon_main(pel *rec, int s, int w, int h, int lw, int lh, int ipm, int lr, const int16_t *up, const int16_t *le,
-                                      const int16_t *ri, const int16_t *res, bool coded, int pmax, int rmax, int *scr, int tid, int nthreads)
+__device__ void intra_pred_recon_main(const PlaneCtx &pc, int cx, int cy, int w, int h, int lw, int lh, int ipm, int lr, const int16_t *up, const int16_t *le,
+                                      const int16_t *ri, bool coded, int pmax, int rmax, int *scr, int tid, int nthreads)
 {
+    const int16_t *res = pc.res + cy * pc.Sp + cx;
     // scalars of the mode (warp 0): scr[0..3]
     if (ipm <= 2) {
         if (tid < 32) {
@@ -266,8 +290,8 @@ __device__ void intra_pred_recon_main(pel *rec, int s, int w, int h, int lw, int
                 p = xb_clip3(0, pmax, (int16_t)(((px << lh) + (py << lw) + k * y * s2 + (1 << (lw + lh))) >> (lw + lh + 1)));
             }
         } else p = intra_ang_px(up, le, ri, lr, ipm, x, y, w, h, pmax);
-        const int r = coded ? res[i] : 0;
-        rec[(size_t)y * s + x] = (pel)xb_clip3(0, rmax, (int16_t)(p + r));
+        const int r = coded ? res[y * pc.Sp + x] : 0;
+        pc.put(cx + x, cy + y, xb_clip3(0, rmax, (int16_t)(p + r)));
     }
 }
 
@@ -314,10 +338,9 @@ __device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_C
     return true;
 }
 
-__device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, int qp, int16_t *t, int tid, int nthreads)
+__device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, const PlaneCtx &pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads)
 {
-    const int w = 1 << cu.log2w, h = 1 << cu.log2h, we = w + 2, he = h + 2, s = a.s_l;
-    pel *rec = a.cur.y + (size_t)cu.y * s + cu.x;
+    const int w = 1 << cu.log2w, h = 1 << cu.log2h, we = w + 2, he = h + 2;
     const int av = cu.avail_cu;
     const bool up = av & 1, le = (av >> 1) & 1, ri = (av >> 3) & 1;
     for (int idx = tid; idx < we * he; idx += nthreads) {
@@ -330,7 +353,7 @@ __device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, int qp, int16_
             else if ((av >> 6) & 1) { si = -1; sj = w; }
         } else if (j < 0) { if ((av >> 7) & 1) { si = h; sj = -1; } }
         else if (j >= w) { if ((av >> 8) & 1) { si = h; sj = w; } }
-        t[idx] = __ldcg(rec + (ptrdiff_t)si * s + sj);
+        t[idx] = (int16_t)pc.get(cx + sj, cy + si);
     }
     __syncthreads();
     int k = (qp - 20 + 4) >> 3;
@@ -344,7 +367,7 @@ __device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, int qp, int16_
         acc = (int16_t)(acc + htdf_window(t + (i - 1) * we + j, we, 2, tbl, thr, shift, round));
         acc = (int16_t)(acc + htdf_window(t + i * we + (j - 1), we, 1, tbl, thr, shift, round));
         acc = (int16_t)(acc + htdf_window(t + i * we + j, we, 0, tbl, thr, shift, round));
-        rec[(size_t)(i - 1) * s + (j - 1)] = (pel)xb_clip3(0, maxv, (acc + 2) >> 2);
+        pc.put(cx + j - 1, cy + i - 1, xb_clip3(0, maxv, (acc + 2) >> 2));
     }
     __syncthreads();
 }
@@ -359,9 +382,12 @@ __global__ void __launch_bounds__(kIntraThreads)
 k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int16_t *s_res = (int16_t *)smem_raw;
-    int *s_tmp = (int *)(s_res + IntraSmem::kResElems);
-    int16_t *s_nb = (int16_t *)(s_tmp + IntraSmem::kTmpElems);
+    int16_t *s_rec = (int16_t *)smem_raw;
+    int16_t *s_res = s_rec + IntraSmem::kPlaneElems;
+    int16_t *s_top = s_res + IntraSmem::kPlaneElems;
+    int16_t *s_left = s_top + 3 * IntraSmem::kTopElems;
+    int16_t *s_nb = s_left + 3 * IntraSmem::kLeftElems;
+    int *s_tmp = (int *)(s_nb + 3 * IntraSmem::kNbElems);
     __shared__ int s_ctu, s_scratch, s_scr4[4];
     const int tid = threadIdx.x;
 
@@ -371,67 +397,106 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     if (ctu >= a.n_ctu) return;
     const int cx = ctu % a.w_ctu, cy = ctu / a.w_ctu;
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
+    const int S = 1 << a.log2_ctu, Sc = S >> 1;
+    const int ctu_x = cx << a.log2_ctu, ctu_y = cy << a.log2_ctu;
 
-    // any intra CU here?  (uniform: every thread scans the same descriptors through L1)
+    // any wavefront work here?  (uniform: every thread scans the same descriptors through L1)
     bool any = false;
     for (int i = cu0 + tid; i < cu1; i += kIntraThreads) { int q; any |= xb_wavefront_mode(a.cus[i].mode) || htdf_applies(a, a.cus[i], q); }
     any = __syncthreads_or(any);
     if (any) {
-        if (tid < 4) {
-            // left, upper-left, upper, upper-right
-            const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
-            if (nx >= 0 && nx < a.w_ctu && ny >= 0) {
-                volatile int *f = sy.done + ny * a.w_ctu + nx;
-                while (*f == 0) __nanosleep(64);
-            }
-            __threadfence();
+        PlaneCtx pc[3];
+        for (int pl = 0; pl < 3; pl++) {
+            const int Sp = pl ? Sc : S, po = pl == 0 ? 0 : (pl == 1 ? S * S : S * S + Sc * Sc);
+            pc[pl].rec = s_rec + po; pc[pl].res = s_res + po; pc[pl].Sp = Sp;
+            pc[pl].top = s_top + pl * IntraSmem::kTopElems + 4;
+            pc[pl].left = s_left + pl * IntraSmem::kLeftElems;
+            pc[pl].gs = pl ? a.s_c : a.s_l;
+            pc[pl].g = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)(ctu_y >> (pl ? 1 : 0)) * pc[pl].gs + (ctu_x >> (pl ? 1 : 0));
         }
-        __syncthreads();
+        // ---- before waiting: (1) the CTU's samples as the inter kernel left them (neighbours of intra CUs, HTDF input) -------------
+        for (int pl = 0; pl < 3; pl++) {
+            const int Sp = pc[pl].Sp, wv = min(Sp, ((a.w - ctu_x) >> (pl ? 1 : 0))), hv = min(Sp, ((a.h - ctu_y) >> (pl ? 1 : 0)));
+            for (int i = tid; i < Sp * hv; i += kIntraThreads) {
+                const int y = i / Sp, x = i - y * Sp;
+                if (x < wv) pc[pl].rec[y * Sp + x] = pc[pl].g[(size_t)y * pc[pl].gs + x];
+            }
+        }
+        // ---- (2) residual of every intra / IBC CU: independent of the neighbours, so it is off the critical path -------------------
         for (int i = cu0; i < cu1; i++) {
             const XB200_CU cu = a.cus[i];
-            int hq = 0;
-            const bool do_htdf = htdf_applies(a, cu, hq);            // uniform
-            if (!xb_wavefront_mode(cu.mode)) {
-                // inter CU: reconstructed by the inter kernel; only the in-order HTDF pass is left
-                if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
-                continue;
-            }
-            const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
-            uint32_t ei;
-            memcpy(&ei, cu.mv[1], 4);
-            const XB200_CU_EXT ex = a.ext[ei];
-            const bool ul = (cu.avail >> 2) & 1;
-            const int dflt = 1 << (a.bd_l - 1), maxv = (1 << a.bd_l) - 1;
-            // residual of the three planes (CU-raster in shared memory)
-            int16_t *res[3] = {s_res, s_res + w * h, s_res + w * h + cw * ch};
+            if (!xb_wavefront_mode(cu.mode)) continue;                                       // uniform
             const int16_t *coef = a.coef + cu.coef_off;
             for (int pl = 0; pl < 3; pl++) {
                 const int bits = (cu.cbf >> (4 * pl)) & 15;
                 if (!bits) continue;
-                const int lw = cu.log2w - (pl ? 1 : 0), lh = cu.log2h - (pl ? 1 : 0);
-                cu_plane_residual<IQT>(coef, lw, lh, pl ? 5 : 6, bits, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l, res[pl], s_tmp,
-                                       tid, kIntraThreads, (a.ats && pl == 0 && (cu.flags & XB200_CUF_ATS_INTRA)) ? (cu.ats & 3) : -1);
+                const int sh = pl ? 1 : 0, lw = cu.log2w - sh, lh = cu.log2h - sh;
+                cu_plane_residual<IQT>(coef, lw, lh, pl ? 5 : 6, bits, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l,
+                                       pc[pl].res + ((cu.y - ctu_y) >> sh) * pc[pl].Sp + ((cu.x - ctu_x) >> sh), pc[pl].Sp, s_tmp, tid, kIntraThreads,
+                                       (a.ats && pl == 0 && cu.mode == XB200_MODE_INTRA && (cu.flags & XB200_CUF_ATS_INTRA)) ? (cu.ats & 3) : -1);
                 coef += ((1 << (lw + lh)) + 7) & ~7;
             }
+        }
+        // ---- wait for the left, upper-left, upper and upper-right CTU ---------------------------------------------------------------
+        if (tid < 4) {
+            const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
+            if (nx >= 0 && nx < a.w_ctu && ny >= 0) {
+                volatile int *f = sy.done + ny * a.w_ctu + nx;
+                while (*f == 0) __nanosleep(32);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        // ---- the row above and the column left of the CTU (L2 loads: other CTAs wrote them) ------------------------------------------
+        for (int pl = 0; pl < 3; pl++) {
+            const int sh = pl ? 1 : 0, Sp = pc[pl].Sp, wp = a.w >> sh, hp = a.h >> sh, x0 = ctu_x >> sh, y0 = ctu_y >> sh;
+            for (int i = tid; i < 3 * Sp + 1; i += kIntraThreads) {
+                if (i <= 2 * Sp) {                                                            // top[x], x = i - 1
+                    const int x = i - 1;
+                    if (y0 > 0 && x0 + x >= 0 && x0 + x < wp) pc[pl].top[x] = __ldcg(pc[pl].g - pc[pl].gs + x);
+                } else {
+                    const int y = i - 2 * Sp - 1;
+                    if (x0 > 0 && y0 + y < hp) pc[pl].left[y] = __ldcg(pc[pl].g + (size_t)y * pc[pl].gs - 1);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- the CUs in decoding order --------------------------------------------------------------------------------------------
+        const int dflt = 1 << (a.bd_l - 1), maxv = (1 << a.bd_l) - 1;
+        for (int i = cu0; i < cu1; i++) {
+            const XB200_CU cu = a.cus[i];
+            int hq = 0;
+            const bool do_htdf = htdf_applies(a, cu, hq);            // uniform
+            const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
+            if (!xb_wavefront_mode(cu.mode)) {
+                // inter CU: reconstructed by the inter kernel; only the in-order HTDF pass is left
+                if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+                continue;
+            }
+            const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
             if (cu.mode == XB200_MODE_IBC) {
                 // xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the already reconstructed part of the CURRENT
                 // picture (block vector mv[0], chroma vector = luma >> 1), then xevdm_recon.  Conforming vectors stay inside the
-                // current CTU row at or left of this CTU, which the wavefront has completed.
+                // current CTU row at or left of this CTU: samples of this CTU come from shared memory, older ones from the picture.
                 const int bx = cu.mv[0][0], by = cu.mv[0][1];
                 for (int pl = 0; pl < 3; pl++) {
-                    const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, s = pl ? a.s_c : a.s_l, lwp = cu.log2w - sh;
-                    pel *rec = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)(cu.y >> sh) * s + (cu.x >> sh);
-                    const pel *src = rec + (ptrdiff_t)(by >> sh) * s + (bx >> sh);
+                    const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, lwp = cu.log2w - sh, Sp = pc[pl].Sp;
+                    const int ox = lx >> sh, oy = ly >> sh, vx = bx >> sh, vy = by >> sh;
                     const bool coded = ((cu.cbf >> (4 * pl)) & 15) != 0;
-                    for (int i = tid; i < pw * ph; i += kIntraThreads) {
-                        const int y = i >> lwp, x = i & (pw - 1);
-                        const int p = __ldcg(src + (size_t)y * s + x);
-                        rec[(size_t)y * s + x] = (pel)xb_clip3(0, maxv, (int16_t)(p + (coded ? res[pl][i] : 0)));
+                    // the source block is decoded earlier, so it cannot overlap this CU
+                    for (int k = tid; k < pw * ph; k += kIntraThreads) {
+                        const int y = k >> lwp, x = k & (pw - 1), X = ox + x + vx, Y = oy + y + vy;
+                        const int p = (X >= 0 && X < Sp && Y >= 0 && Y < Sp) ? pc[pl].rec[Y * Sp + X] : __ldcg(pc[pl].g + (ptrdiff_t)Y * pc[pl].gs + X);
+                        pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + (coded ? pc[pl].res[(oy + y) * Sp + ox + x] : 0))));
                     }
                 }
                 __syncthreads();
                 continue;
             }
+            uint32_t ei;
+            memcpy(&ei, cu.mv[1], 4);
+            const XB200_CU_EXT ex = a.ext[ei];
+            const bool ul = (cu.avail >> 2) & 1;
             // neighbours of all three planes, then prediction + reconstruction
             int16_t *up[3], *le[3], *ri[3];
             for (int pl = 0; pl < 3; pl++) { up[pl] = s_nb + pl * IntraSmem::kNbElems + 4; le[pl] = up[pl] + (2 * 128 + 8); ri[pl] = le[pl] + (2 * 128 + 8); }
@@ -442,38 +507,32 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 const int ipm_c = cu.refi[1] == 0 ? cu.refi[0] : kChromaToLuma[cu.refi[1]];
                 for (int pl = 0; pl < 3; pl++) {
                     NbSrc nb;
-                    nb.rec = pl == 0 ? a.cur.y + (size_t)cu.y * a.s_l + cu.x : (pl == 1 ? a.cur.u : a.cur.v) + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1);
-                    nb.s = pl ? a.s_c : a.s_l; nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
+                    nb.pc = &pc[pl]; nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
+                    nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
                     nb.um = ex.u.intra.up; nb.lm = ex.u.intra.left; nb.rm = ex.u.intra.right; nb.ul = ul;
                     intra_gather_main(nb, pl ? ch : h, up[pl], le[pl], ri[pl], tid, kIntraThreads);
                 }
                 __syncthreads();
                 for (int pl = 0; pl < 3; pl++) {
-                    pel *rec = pl == 0 ? a.cur.y + (size_t)cu.y * a.s_l + cu.x : (pl == 1 ? a.cur.u : a.cur.v) + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1);
-                    intra_pred_recon_main(rec, pl ? a.s_c : a.s_l, pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0),
-                                          pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl], res[pl], ((cu.cbf >> (4 * pl)) & 15) != 0,
+                    intra_pred_recon_main(pc[pl], lx >> (pl ? 1 : 0), ly >> (pl ? 1 : 0), pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0),
+                                          pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl], ((cu.cbf >> (4 * pl)) & 15) != 0,
                                           pl ? pmax_c : maxv, maxv, s_scr4, tid, kIntraThreads);
                     __syncthreads();
                 }
-                if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+                if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
                 continue;
             }
-            intra_gather(a.cur.y + (size_t)cu.y * a.s_l + cu.x, a.s_l, w, h, 4, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[0], le[0], tid, kIntraThreads);
-            intra_gather(a.cur.u + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[1], le[1],
-                         tid, kIntraThreads);
-            intra_gather(a.cur.v + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[2], le[2],
-                         tid, kIntraThreads);
+            intra_gather(pc[0], lx, ly, w, h, 4, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[0], le[0], tid, kIntraThreads);
+            intra_gather(pc[1], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[1], le[1], tid, kIntraThreads);
+            intra_gather(pc[2], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[2], le[2], tid, kIntraThreads);
             __syncthreads();
-            intra_pred_recon(a.cur.y + (size_t)cu.y * a.s_l + cu.x, a.s_l, w, h, cu.log2w, cu.refi[0], up[0], le[0], res[0], (cu.cbf & 0x00f) != 0, maxv,
-                             &s_scratch, tid, kIntraThreads);
+            intra_pred_recon(pc[0], lx, ly, w, h, cu.log2w, cu.refi[0], up[0], le[0], (cu.cbf & 0x00f) != 0, maxv, &s_scratch, tid, kIntraThreads);
             __syncthreads();
-            intra_pred_recon(a.cur.u + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, cu.log2w - 1, cu.refi[1], up[1], le[1], res[1],
-                             (cu.cbf & 0x0f0) != 0, maxv, &s_scratch, tid, kIntraThreads);
+            intra_pred_recon(pc[1], lx >> 1, ly >> 1, cw, ch, cu.log2w - 1, cu.refi[1], up[1], le[1], (cu.cbf & 0x0f0) != 0, maxv, &s_scratch, tid, kIntraThreads);
             __syncthreads();
-            intra_pred_recon(a.cur.v + (size_t)(cu.y >> 1) * a.s_c + (cu.x >> 1), a.s_c, cw, ch, cu.log2w - 1, cu.refi[1], up[2], le[2], res[2],
-                             (cu.cbf & 0xf00) != 0, maxv, &s_scratch, tid, kIntraThreads);
-            __syncthreads();         // the next CU may read these samples (global writes are visible block-wide after the barrier)
-            if (do_htdf) cu_htdf(a, cu, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+            intra_pred_recon(pc[2], lx >> 1, ly >> 1, cw, ch, cu.log2w - 1, cu.refi[1], up[2], le[2], (cu.cbf & 0xf00) != 0, maxv, &s_scratch, tid, kIntraThreads);
+            __syncthreads();         // the next CU reads these samples from shared memory
+            if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
         }
     }
     __threadfence();

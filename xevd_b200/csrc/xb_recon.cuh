@@ -637,7 +637,7 @@ __device__ __forceinline__ bool tb_at(const XbFrameArgs &a, const XB200_CU &cu, 
 }
 
 template <bool IQT>
-__global__ void __launch_bounds__(kReconThreads)
+__global__ void __launch_bounds__(kReconThreads, 2)
 k_recon_inter(const __grid_constant__ XbFrameArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
