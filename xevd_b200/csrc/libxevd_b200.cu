@@ -53,6 +53,8 @@ struct xb200_ctx {
     int sm_count;
     int *d_sync;                 // wavefront state of the intra kernel: [0] ticket, [1..] per-CTU done flags
     int sync_cap;
+    int *d_order;                // CTU addresses in wavefront order (x + 2y) for the current picture geometry
+    int order_w, order_n;
     int8_t chroma_qp[2][58];     // xevd_qp_chroma_dynamic for the sequence
     pel *alf_copy;               // pre-ALF copy of the picture being filtered
     size_t alf_cap;
@@ -98,6 +100,7 @@ xb200_ctx *xb200_create(int device, int *err)
     c->err[0] = 0;
     c->ring_pos = 0;
     c->d_sync = nullptr; c->sync_cap = 0;
+    c->d_order = nullptr; c->order_w = c->order_n = 0;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         if (err) *err = XB200_ERR_CUDA;
@@ -177,6 +180,7 @@ void xb200_destroy(xb200_ctx *c)
         if (s.done) cudaEventDestroy(s.done);
     }
     if (c->d_sync) cudaFree(c->d_sync);
+    if (c->d_order) cudaFree(c->d_order);
     if (c->alf_copy) cudaFree(c->alf_copy);
     if (c->alf_flags_pinned) cudaFreeHost(c->alf_flags_pinned);
     if (c->alf_flags_dev) cudaFree(c->alf_flags_dev);
@@ -475,8 +479,23 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
             c->sync_cap = a.n_ctu + 1;
             CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * c->sync_cap));
         }
+        if (c->order_w != a.w_ctu || c->order_n != a.n_ctu) {
+            // wavefront order: sort CTU addresses by x + 2y (a stable counting pass per index)
+            const int wc = a.w_ctu, hc = a.n_ctu / a.w_ctu;
+            int *h = (int *)malloc(sizeof(int) * a.n_ctu);
+            int k = 0;
+            for (int d = 0; d <= (wc - 1) + 2 * (hc - 1); d++)
+                for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
+            CK(c, cudaStreamSynchronize(c->stream));
+            if (c->d_order) cudaFree(c->d_order);
+            c->d_order = nullptr;
+            CK(c, cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu));
+            CK(c, cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice));
+            free(h);
+            c->order_w = a.w_ctu; c->order_n = a.n_ctu;
+        }
         CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (a.n_ctu + 1), c->stream));
-        xb::IntraSync sy{c->d_sync, c->d_sync + 1};
+        xb::IntraSync sy{c->d_sync, c->d_sync + 1, c->d_order};
         const size_t sm = xb::IntraSmem::bytes();
         if (a.iqt) xb::k_recon_intra<true><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);
         else       xb::k_recon_intra<false><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);

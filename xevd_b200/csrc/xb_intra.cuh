@@ -31,9 +31,11 @@ struct IntraSmem {
     static constexpr int kLeftElems = 128;                          // per plane: the column left of the CTU
     static constexpr int kTmpElems = 64 * 65;                       // pass-1 buffer of one transform block / HTDF ring block
     static constexpr int kNbElems = 3 * (2 * 128 + 8);              // up[-1..w+h), left[-1..w+h), right[-1..w+h)
+    static constexpr int kCuStage = 256;                            // CU descriptors + extension records staged on chip (the rest stay in L2)
     static size_t bytes()
     {
-        return sizeof(int16_t) * (2 * kPlaneElems + 3 * kTopElems + 3 * kLeftElems + 3 * kNbElems) + sizeof(int) * kTmpElems + 64;
+        return sizeof(int16_t) * (2 * kPlaneElems + 3 * kTopElems + 3 * kLeftElems + 3 * kNbElems) + sizeof(int) * kTmpElems +
+               kCuStage * (sizeof(XB200_CU) + sizeof(XB200_CU_EXT)) + 64;
     }
 };
 
@@ -373,8 +375,11 @@ __device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, const PlaneCtx
 }
 
 struct IntraSync {
-    int *ticket;        // next CTU to hand out
+    int *ticket;        // next position of `order` to hand out
     int *done;          // [n_ctu] 1 when every CU of the CTU is final
+    const int *order;   // CTU addresses sorted by wavefront index x + 2y: CTUs of one index are independent, so the CTAs resident at
+                        // any time span many CTU rows (raster order kept only ~2.5 rows busy: 148 resident CTAs / 60 CTUs per row);
+                        // every dependency has a smaller index, hence an earlier ticket -> no deadlock
 };
 
 template <bool IQT>
@@ -388,13 +393,15 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     int16_t *s_left = s_top + 3 * IntraSmem::kTopElems;
     int16_t *s_nb = s_left + 3 * IntraSmem::kLeftElems;
     int *s_tmp = (int *)(s_nb + 3 * IntraSmem::kNbElems);
+    XB200_CU *s_cu = (XB200_CU *)(s_tmp + IntraSmem::kTmpElems);
+    XB200_CU_EXT *s_ext = (XB200_CU_EXT *)(s_cu + IntraSmem::kCuStage);
     __shared__ int s_ctu, s_scratch, s_scr4[4];
     const int tid = threadIdx.x;
 
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
     __syncthreads();
-    const int ctu = s_ctu;
-    if (ctu >= a.n_ctu) return;
+    if (s_ctu >= a.n_ctu) return;
+    const int ctu = sy.order[s_ctu];
     const int cx = ctu % a.w_ctu, cy = ctu / a.w_ctu;
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
     const int S = 1 << a.log2_ctu, Sc = S >> 1;
@@ -405,6 +412,16 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     for (int i = cu0 + tid; i < cu1; i += kIntraThreads) { int q; any |= xb_wavefront_mode(a.cus[i].mode) || htdf_applies(a, a.cus[i], q); }
     any = __syncthreads_or(any);
     if (any) {
+        // CU descriptors and extension records on chip: two dependent L2 round trips per CU would sit on the critical path otherwise
+        const int n_stage = min(cu1 - cu0, IntraSmem::kCuStage);
+        for (int i = tid; i < n_stage * 2; i += kIntraThreads) ((int4 *)s_cu)[i] = __ldg((const int4 *)(a.cus + cu0) + i);
+        __syncthreads();
+        for (int i = tid; i < n_stage * 2; i += kIntraThreads) {
+            const XB200_CU &c = s_cu[i >> 1];
+            if (c.mode == XB200_MODE_INTRA) { uint32_t ei; memcpy(&ei, c.mv[1], 4); ((int4 *)s_ext)[i] = __ldg((const int4 *)(a.ext + ei) + (i & 1)); }
+        }
+        __syncthreads();
+        auto get_cu = [&](int i) -> XB200_CU { return i - cu0 < n_stage ? s_cu[i - cu0] : a.cus[i]; };
         PlaneCtx pc[3];
         for (int pl = 0; pl < 3; pl++) {
             const int Sp = pl ? Sc : S, po = pl == 0 ? 0 : (pl == 1 ? S * S : S * S + Sc * Sc);
@@ -424,7 +441,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         }
         // ---- (2) residual of every intra / IBC CU: independent of the neighbours, so it is off the critical path -------------------
         for (int i = cu0; i < cu1; i++) {
-            const XB200_CU cu = a.cus[i];
+            const XB200_CU cu = get_cu(i);
             if (!xb_wavefront_mode(cu.mode)) continue;                                       // uniform
             const int16_t *coef = a.coef + cu.coef_off;
             for (int pl = 0; pl < 3; pl++) {
@@ -464,7 +481,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         // ---- the CUs in decoding order --------------------------------------------------------------------------------------------
         const int dflt = 1 << (a.bd_l - 1), maxv = (1 << a.bd_l) - 1;
         for (int i = cu0; i < cu1; i++) {
-            const XB200_CU cu = a.cus[i];
+            const XB200_CU cu = get_cu(i);
             int hq = 0;
             const bool do_htdf = htdf_applies(a, cu, hq);            // uniform
             const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
@@ -495,7 +512,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             }
             uint32_t ei;
             memcpy(&ei, cu.mv[1], 4);
-            const XB200_CU_EXT ex = a.ext[ei];
+            const XB200_CU_EXT ex = i - cu0 < n_stage ? s_ext[i - cu0] : a.ext[ei];
             const bool ul = (cu.avail >> 2) & 1;
             // neighbours of all three planes, then prediction + reconstruction
             int16_t *up[3], *le[3], *ri[3];
