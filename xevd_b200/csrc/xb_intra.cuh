@@ -107,36 +107,27 @@ __device__ void intra_gather(const PlaneCtx &pc, int cx, int cy, int w, int h, i
     }
 }
 
-// xevd_ipred_b + xevd_recon for one plane; modes IPD_DC_B 0, HOR 1, VER 2, UL 3, UR 4
-__device__ void intra_pred_recon(const PlaneCtx &pc, int cx, int cy, int w, int h, int lw, int mode, const int16_t *up, const int16_t *left,
-                                 bool coded, int maxv, int *scratch, int tid, int nthreads)
+// xevd_ipred_b for one plane; modes IPD_DC_B 0, HOR 1, VER 2, UL 3, UR 4.  Split in two so that the three planes of a CU share
+// their barriers: the scalar of the mode (DC) by one warp per plane, then one joint sample loop over all planes.
+__device__ __forceinline__ void intra_scalars(int w, int h, int lw, int mode, const int16_t *up, const int16_t *left, int *scr, int lane)
 {
-    const int16_t *res = pc.res + cy * pc.Sp + cx;
-    if (mode == 0) {
-        // DC = (sum(left[0..h)) + sum(up[0..w)) + w) >> (log2 w + 1): warp 0 reduces
-        if (tid < 32) {
-            int acc = 0;
-            for (int i = tid; i < h; i += 32) acc += left[i];
-            for (int i = tid; i < w; i += 32) acc += up[i];
+    if (mode != 0) return;
+    // DC = (sum(left[0..h)) + sum(up[0..w)) + w) >> (log2 w + 1)
+    int acc = 0;
+    for (int i = lane; i < h; i += 32) acc += left[i];
+    for (int i = lane; i < w; i += 32) acc += up[i];
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (tid == 0) *scratch = (acc + w) >> (lw + 1);
-        }
-        __syncthreads();
-    }
-    const int dc = mode == 0 ? *scratch : 0;
-    for (int i = tid; i < w * h; i += nthreads) {
-        const int y = i >> lw, x = i & (w - 1);
-        int p;
-        switch (mode) {
-        case 0: p = dc; break;
-        case 1: p = left[y]; break;
-        case 2: p = up[x]; break;
-        case 3: p = y > x ? left[y - x - 1] : (y == x ? up[-1] : up[x - y - 1]); break;
-        default: p = (up[x + y + 1] + left[x + y + 1]) >> 1; break;
-        }
-        const int r = coded ? res[y * pc.Sp + x] : 0;
-        pc.put(cx + x, cy + y, xb_clip3(0, maxv, (int16_t)(p + r)));            // xevd_recon: s16 wrap, then clip
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane == 0) scr[0] = (acc + w) >> (lw + 1);
+}
+__device__ __forceinline__ int intra_px(int mode, int x, int y, const int16_t *up, const int16_t *left, const int *scr)
+{
+    switch (mode) {
+    case 0: return scr[0];
+    case 1: return left[y];
+    case 2: return up[x];
+    case 3: return y > x ? left[y - x - 1] : (y == x ? up[-1] : up[x - y - 1]);
+    default: return (up[x + y + 1] + left[x + y + 1]) >> 1;
     }
 }
 
@@ -221,80 +212,70 @@ __device__ __forceinline__ int intra_ang_px(const int16_t *up, const int16_t *le
     return xb_clip3(0, maxv, v);
 }
 
-// xevdm_ipred / xevdm_ipred_uv + xevdm_recon for one plane (src_main/xevdm_ipred.c:153-305; shared predictors
-// src_base/xevd_ipred.c:110-372).  ipm: 0 DC, 1 planar, 2 bilinear, 12 vertical, 24 horizontal, others angular.
-// pmax clips the predictor (plane bit depth), rmax the reconstruction (luma bit depth, xevdm_recon.c).
-__device__ void intra_pred_recon_main(const PlaneCtx &pc, int cx, int cy, int w, int h, int lw, int lh, int ipm, int lr, const int16_t *up, const int16_t *le,
-                                      const int16_t *ri, bool coded, int pmax, int rmax, int *scr, int tid, int nthreads)
+// xevdm_ipred / xevdm_ipred_uv for one plane (src_main/xevdm_ipred.c:153-305; shared predictors src_base/xevd_ipred.c:110-372).
+// ipm: 0 DC, 1 planar, 2 bilinear, 12 vertical, 24 horizontal, others angular.  Same split as above: mode scalars by one warp per plane
+// (scr[0..2]), then a per-sample function.  pmax clips the predictor (plane bit depth).
+__device__ __forceinline__ void intra_scalars_main(int w, int h, int lw, int lh, int ipm, int lr, const int16_t *up, const int16_t *le, const int16_t *ri,
+                                                   int *scr, int lane)
 {
-    const int16_t *res = pc.res + cy * pc.Sp + cx;
-    // scalars of the mode (warp 0): scr[0..3]
-    if (ipm <= 2) {
-        if (tid < 32) {
-            if (ipm == 0) {
-                int acc = 0;
-                for (int i = tid; i < w; i += 32) acc += up[i];
-                for (int i = tid; i < h; i += 32) acc += (lr == 3 ? le[i] + ri[i] : (lr == 2 ? ri[i] : le[i]));
+    if (ipm == 0) {
+        int acc = 0;
+        for (int i = lane; i < w; i += 32) acc += up[i];
+        for (int i = lane; i < h; i += 32) acc += (lr == 3 ? le[i] + ri[i] : (lr == 2 ? ri[i] : le[i]));
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-                if (tid == 0) {
-                    const int lhh = lr == 3 ? lh + 1 : lh;
-                    acc += lr == 3 ? (w + h + h) >> 1 : (w + h) >> 1;
-                    scr[0] = (acc * c_inv_size_plus1[lw > lhh ? lw - lhh : lhh - lw]) >> (min(lw, lhh) + 12);
-                }
-            } else if (ipm == 1) {
-                const bool fr = lr >= 2;
-                const int16_t *sd = fr ? ri : le;
-                const int w2 = w >> 1, h2 = h >> 1;
-                int ch = 0, cv = 0;
-                for (int x = 1 + tid; x <= w2; x += 32) ch += fr ? x * (up[w2 - x] - up[w2 + x]) : x * (up[w2 - 1 + x] - up[w2 - 1 - x]);
-                for (int y = 1 + tid; y <= h2; y += 32) cv += y * (sd[h2 - 1 + y] - sd[h2 - 1 - y]);
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, d); cv += __shfl_xor_sync(0xffffffffu, cv, d); }
-                if (tid == 0) {
-                    const int mult[6] = {13, 17, 5, 11, 23, 47}, shft[6] = {7, 10, 11, 15, 19, 23};
-                    const int iw = lw < 2 ? 0 : lw - 2, ih = lh < 2 ? 0 : lh - 2;
-                    const int a = (sd[h - 1] + (fr ? up[0] : up[w - 1])) << 4;
-                    const int b = ((ch << 5) * mult[iw] + (1 << (shft[iw] - 1))) >> shft[iw];
-                    const int c = ((cv << 5) * mult[ih] + (1 << (shft[ih] - 1))) >> shft[ih];
-                    scr[0] = a - (h2 - 1) * c - (w2 - 1) * b + 16; scr[1] = b; scr[2] = c;
-                }
-            } else if (tid == 0 && lr != 3) {
-                const int tbl_wc[6] = {-1, 341, 205, 114, 60, 31};
-                const bool fr = lr == 2;
-                const int a = fr ? up[-1] : up[w], b = fr ? ri[h] : le[h];
-                const int lmin = min(lw, lh);
-                const int c = w == h ? (a + b + 1) >> 1 : (((a << lw) + (b << lh)) * tbl_wc[lw > lh ? lw - lh : lh - lw] + (1 << (lmin + 9))) >> (lmin + 10);
-                scr[0] = a; scr[1] = b; scr[2] = (c << 1) - a - b;
-            }
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0) {
+            const int lhh = lr == 3 ? lh + 1 : lh;
+            acc += lr == 3 ? (w + h + h) >> 1 : (w + h) >> 1;
+            scr[0] = (acc * c_inv_size_plus1[lw > lhh ? lw - lhh : lhh - lw]) >> (min(lw, lhh) + 12);
         }
-        __syncthreads();
+    } else if (ipm == 1) {
+        const bool fr = lr >= 2;
+        const int16_t *sd = fr ? ri : le;
+        const int w2 = w >> 1, h2 = h >> 1;
+        int ch = 0, cv = 0;
+        for (int x = 1 + lane; x <= w2; x += 32) ch += fr ? x * (up[w2 - x] - up[w2 + x]) : x * (up[w2 - 1 + x] - up[w2 - 1 - x]);
+        for (int y = 1 + lane; y <= h2; y += 32) cv += y * (sd[h2 - 1 + y] - sd[h2 - 1 - y]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, d); cv += __shfl_xor_sync(0xffffffffu, cv, d); }
+        if (lane == 0) {
+            const int mult[6] = {13, 17, 5, 11, 23, 47}, shft[6] = {7, 10, 11, 15, 19, 23};
+            const int iw = lw < 2 ? 0 : lw - 2, ih = lh < 2 ? 0 : lh - 2;
+            const int a = (sd[h - 1] + (fr ? up[0] : up[w - 1])) << 4;
+            const int b = ((ch << 5) * mult[iw] + (1 << (shft[iw] - 1))) >> shft[iw];
+            const int c = ((cv << 5) * mult[ih] + (1 << (shft[ih] - 1))) >> shft[ih];
+            scr[0] = a - (h2 - 1) * c - (w2 - 1) * b + 16; scr[1] = b; scr[2] = c;
+        }
+    } else if (ipm == 2 && lane == 0 && lr != 3) {
+        const int tbl_wc[6] = {-1, 341, 205, 114, 60, 31};
+        const bool fr = lr == 2;
+        const int a = fr ? up[-1] : up[w], b = fr ? ri[h] : le[h];
+        const int lmin = min(lw, lh);
+        const int c = w == h ? (a + b + 1) >> 1 : (((a << lw) + (b << lh)) * tbl_wc[lw > lh ? lw - lh : lh - lw] + (1 << (lmin + 9))) >> (lmin + 10);
+        scr[0] = a; scr[1] = b; scr[2] = (c << 1) - a - b;
     }
-    const int s0 = scr[0], s1 = scr[1], s2 = scr[2];
+}
+__device__ __forceinline__ int intra_px_main(int ipm, int lr, int x, int y, int w, int h, int lw, int lh, const int16_t *up, const int16_t *le,
+                                             const int16_t *ri, const int *scr, int pmax)
+{
     const int mul_w = c_inv_size_plus1[lw];
-    for (int i = tid; i < w * h; i += nthreads) {
-        const int y = i >> lw, x = i & (w - 1);
-        int p;
-        if (ipm == 12) p = up[x];
-        else if (ipm == 24) p = lr == 3 ? (int16_t)(((le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w) >> 12) : (lr == 2 ? ri[y] : le[y]);
-        else if (ipm == 0) p = s0;
-        else if (ipm == 1) p = xb_clip3(0, pmax, (s0 + y * s2 + (lr >= 2 ? w - 1 - x : x) * s1) >> 5);
-        else if (ipm == 2) {
-            if (lr == 3) {
-                const int hb = (le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w >> 12;
-                const int hl = (le[h - 1] * (w - x) + ri[h - 1] * (x + 1) + (w >> 1)) * mul_w >> 12;
-                const int vb = (up[x] * (h - 1 - y) + hl * (y + 1) + (h >> 1)) >> lh;
-                p = (int16_t)((hb + vb + 1) >> 1);
-            } else {
-                const bool fr = lr == 2;
-                const int sd = fr ? ri[y] : le[y], k = fr ? w - 1 - x : x;
-                const int px = (sd << lw) + (k + 1) * (s0 - sd), py = (up[x] << lh) + (y + 1) * (s1 - up[x]);
-                p = xb_clip3(0, pmax, (int16_t)(((px << lh) + (py << lw) + k * y * s2 + (1 << (lw + lh))) >> (lw + lh + 1)));
-            }
-        } else p = intra_ang_px(up, le, ri, lr, ipm, x, y, w, h, pmax);
-        const int r = coded ? res[y * pc.Sp + x] : 0;
-        pc.put(cx + x, cy + y, xb_clip3(0, rmax, (int16_t)(p + r)));
+    if (ipm == 12) return up[x];
+    if (ipm == 24) return lr == 3 ? (int16_t)(((le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w) >> 12) : (lr == 2 ? ri[y] : le[y]);
+    if (ipm == 0) return scr[0];
+    if (ipm == 1) return xb_clip3(0, pmax, (scr[0] + y * scr[2] + (lr >= 2 ? w - 1 - x : x) * scr[1]) >> 5);
+    if (ipm == 2) {
+        if (lr == 3) {
+            const int hb = (le[y] * (w - x) + ri[y] * (x + 1) + (w >> 1)) * mul_w >> 12;
+            const int hl = (le[h - 1] * (w - x) + ri[h - 1] * (x + 1) + (w >> 1)) * mul_w >> 12;
+            const int vb = (up[x] * (h - 1 - y) + hl * (y + 1) + (h >> 1)) >> lh;
+            return (int16_t)((hb + vb + 1) >> 1);
+        }
+        const bool fr = lr == 2;
+        const int sd = fr ? ri[y] : le[y], k = fr ? w - 1 - x : x;
+        const int px = (sd << lw) + (k + 1) * (scr[0] - sd), py = (up[x] << lh) + (y + 1) * (scr[1] - up[x]);
+        return xb_clip3(0, pmax, (int16_t)(((px << lh) + (py << lw) + k * y * scr[2] + (1 << (lw + lh))) >> (lw + lh + 1)));
     }
+    return intra_ang_px(up, le, ri, lr, ipm, x, y, w, h, pmax);
 }
 
 // ---- HTDF (Main, tool_htdf): xevdm_htdf (src_main/xevdm_recon.c:153-385) ------------------------------------------------------------
@@ -395,7 +376,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     int *s_tmp = (int *)(s_nb + 3 * IntraSmem::kNbElems);
     XB200_CU *s_cu = (XB200_CU *)(s_tmp + IntraSmem::kTmpElems);
     XB200_CU_EXT *s_ext = (XB200_CU_EXT *)(s_cu + IntraSmem::kCuStage);
-    __shared__ int s_ctu, s_scratch, s_scr4[4];
+    __shared__ int s_ctu, s_scr12[12];
     const int tid = threadIdx.x;
 
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
@@ -436,24 +417,10 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             const int Sp = pc[pl].Sp, wv = min(Sp, ((a.w - ctu_x) >> (pl ? 1 : 0))), hv = min(Sp, ((a.h - ctu_y) >> (pl ? 1 : 0)));
             for (int i = tid; i < Sp * hv; i += kIntraThreads) {
                 const int y = i / Sp, x = i - y * Sp;
-                if (x < wv) pc[pl].rec[y * Sp + x] = pc[pl].g[(size_t)y * pc[pl].gs + x];
+                if (x < wv) pc[pl].rec[y * Sp + x] = pc[pl].res[y * Sp + x] = pc[pl].g[(size_t)y * pc[pl].gs + x];
             }
         }
-        // ---- (2) residual of every intra / IBC CU: independent of the neighbours, so it is off the critical path -------------------
-        for (int i = cu0; i < cu1; i++) {
-            const XB200_CU cu = get_cu(i);
-            if (!xb_wavefront_mode(cu.mode)) continue;                                       // uniform
-            const int16_t *coef = a.coef + cu.coef_off;
-            for (int pl = 0; pl < 3; pl++) {
-                const int bits = (cu.cbf >> (4 * pl)) & 15;
-                if (!bits) continue;
-                const int sh = pl ? 1 : 0, lw = cu.log2w - sh, lh = cu.log2h - sh;
-                cu_plane_residual<IQT>(coef, lw, lh, pl ? 5 : 6, bits, pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v), a.bd_l,
-                                       pc[pl].res + ((cu.y - ctu_y) >> sh) * pc[pl].Sp + ((cu.x - ctu_x) >> sh), pc[pl].Sp, s_tmp, tid, kIntraThreads,
-                                       (a.ats && pl == 0 && cu.mode == XB200_MODE_INTRA && (cu.flags & XB200_CUF_ATS_INTRA)) ? (cu.ats & 3) : -1);
-                coef += ((1 << (lw + lh)) + 7) & ~7;
-            }
-        }
+        //      intra / IBC areas hold the RESIDUAL there (parked by the inter kernel), which is why the preload fills both arrays
         // ---- wait for the left, upper-left, upper and upper-right CTU ---------------------------------------------------------------
         if (tid < 4) {
             const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
@@ -530,12 +497,21 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                     intra_gather_main(nb, pl ? ch : h, up[pl], le[pl], ri[pl], tid, kIntraThreads);
                 }
                 __syncthreads();
-                for (int pl = 0; pl < 3; pl++) {
-                    intra_pred_recon_main(pc[pl], lx >> (pl ? 1 : 0), ly >> (pl ? 1 : 0), pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0),
-                                          pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl], ((cu.cbf >> (4 * pl)) & 15) != 0,
-                                          pl ? pmax_c : maxv, maxv, s_scr4, tid, kIntraThreads);
-                    __syncthreads();
+                if ((tid >> 5) < 3) {
+                    const int pl = tid >> 5;
+                    intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl],
+                                       s_scr12 + 4 * pl, tid & 31);
                 }
+                __syncthreads();
+                for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
+                    const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
+                    const int lwp = cu.log2w - (pl ? 1 : 0), lhp = cu.log2h - (pl ? 1 : 0), wp = 1 << lwp, hp = 1 << lhp;
+                    const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
+                    const int p = intra_px_main(pl ? ipm_c : cu.refi[0], lr, x, y, wp, hp, lwp, lhp, up[pl], le[pl], ri[pl], s_scr12 + 4 * pl, pl ? pmax_c : maxv);
+                    const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc[pl].res[(oy + y) * pc[pl].Sp + ox + x] : 0;
+                    pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));
+                }
+                __syncthreads();
                 if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
                 continue;
             }
@@ -543,11 +519,19 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             intra_gather(pc[1], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[1], le[1], tid, kIntraThreads);
             intra_gather(pc[2], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[2], le[2], tid, kIntraThreads);
             __syncthreads();
-            intra_pred_recon(pc[0], lx, ly, w, h, cu.log2w, cu.refi[0], up[0], le[0], (cu.cbf & 0x00f) != 0, maxv, &s_scratch, tid, kIntraThreads);
+            if ((tid >> 5) < 3) {
+                const int pl = tid >> 5;
+                intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.refi[pl ? 1 : 0], up[pl], le[pl], s_scr12 + 4 * pl, tid & 31);
+            }
             __syncthreads();
-            intra_pred_recon(pc[1], lx >> 1, ly >> 1, cw, ch, cu.log2w - 1, cu.refi[1], up[1], le[1], (cu.cbf & 0x0f0) != 0, maxv, &s_scratch, tid, kIntraThreads);
-            __syncthreads();
-            intra_pred_recon(pc[2], lx >> 1, ly >> 1, cw, ch, cu.log2w - 1, cu.refi[1], up[2], le[2], (cu.cbf & 0xf00) != 0, maxv, &s_scratch, tid, kIntraThreads);
+            for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
+                const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
+                const int lwp = cu.log2w - (pl ? 1 : 0), wp = 1 << lwp;
+                const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
+                const int p = intra_px(cu.refi[pl ? 1 : 0], x, y, up[pl], le[pl], s_scr12 + 4 * pl);
+                const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc[pl].res[(oy + y) * pc[pl].Sp + ox + x] : 0;
+                pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));          // xevd_recon: s16 wrap, then clip
+            }
             __syncthreads();         // the next CU reads these samples from shared memory
             if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
         }

@@ -678,7 +678,6 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            if (xb_wavefront_mode(cu.mode)) continue;            // intra / IBC CUs belong to the wavefront kernel
             TbInfo t;
             if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sy0 != ys) continue;
             const int16_t *src = a.coef + t.coef + (x - t.px0);
@@ -704,7 +703,6 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
-            if (xb_wavefront_mode(cu.mode)) continue;
             TbInfo t;
             if (!tb_at(a, cu, pl, ctu_x, ctu_y, xs, ys, t) || t.sx0 != xs) continue;
             const int *tmp = pl == 0 ? sm.tmp_y : (pl == 1 ? sm.tmp_u : sm.tmp_v);
@@ -777,6 +775,20 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                 }
             }
         }
+    }
+
+    // ---- phase B1: intra / IBC CUs are predicted by the wavefront kernel; their residual (neighbour-independent, transformed above with
+    //      everything else) is parked in the picture, where that kernel picks it up with its CTU preload
+    for (int i = tid; i < S * S + 2 * Sc * Sc; i += kReconThreads) {
+        int pl, x, y;
+        if (i < S * S) { pl = 0; y = i / S; x = i - y * S; }
+        else { int t = i - S * S; pl = 1 + (t >= Sc * Sc); t -= (pl - 1) * Sc * Sc; y = t / Sc; x = t - y * Sc; }
+        const int sh = pl ? 1 : 0;
+        const unsigned ci = sm.cu_of_scu[((y << sh) >> 2) * nscu + ((x << sh) >> 2)];
+        if (ci == 0xffff || !xb_wavefront_mode(cus[ci].mode)) continue;
+        const int16_t *res = pl == 0 ? sm.res_y : (pl == 1 ? sm.res_u : sm.res_v);
+        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + y) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + x;
+        *dst = res[y * ((pl ? Sc : S) + 2) + x];
     }
 
     // ---- phase B2: DMVR CUs, one warp per 16x16 sub-PU ---------------------------------------------------------------------------

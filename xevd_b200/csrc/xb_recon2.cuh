@@ -285,6 +285,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 
     // ---- per-CU counts -> exclusive prefix sums: warp q scans quantity q -------------------------------------------------------
     // q: 0 luma blocks, 1 chroma blocks, 2 pass-1 luma lines, 3 pass-1 chroma lines, 4 pass-2 luma lines, 5 pass-2 chroma, 6 tiles
+    if (warp == 7) {            // number of intra / IBC CUs (their residual is parked in the picture below)
+        int n = 0;
+        for (int i = lane; i < ncu; i += 32) n += xb_wavefront_mode(s_cu[i].mode) ? 1 : 0;
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0) cnt[7] = n;
+    }
     if (warp < 7) {
         int run = 0;
         for (int base = 0; base < ncu; base += 32) {
@@ -293,8 +299,10 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             if (i < ncu) {
                 const XB200_CU cu = s_cu[i];
                 const int w = 1 << cu.log2w, h = 1 << cu.log2h;
-                const bool inter = !xb_wavefront_mode(cu.mode);      // intra / IBC CUs belong to the wavefront kernel: no work items here
-                const int ny = (inter && (cu.cbf & 15)) ? 1 : 0, nc = inter ? ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0) : 0;
+                // intra / IBC CUs are predicted by the wavefront kernel, but their residual does not depend on neighbours: it is
+                // transformed here with everything else and parked in the picture for that kernel to pick up
+                const bool inter = !xb_wavefront_mode(cu.mode);
+                const int ny = (cu.cbf & 15) ? 1 : 0, nc = ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0);
                 switch (warp) {
                 case 0: c = ny; break;
                 case 1: c = nc; break;
@@ -318,8 +326,9 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int n_tu = n_tuy + n_tuc;
 
     // ---- one thread per CU: transform-block and tile descriptors ------------------------------------------------------------------
-    if (tid < ncu && !xb_wavefront_mode(s_cu[tid].mode)) {
+    if (tid < ncu) {
         const XB200_CU cu = s_cu[tid];
+        const bool inter_cu = !xb_wavefront_mode(cu.mode);
         const int *of = s_offs + tid * 8;
         const int w = 1 << cu.log2w, h = 1 << cu.log2h;
         const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
@@ -351,7 +360,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 tuc++; l1c += 1 << lh; l2c += 1 << lw;
             }
         }
-        // prediction tiles
+        // prediction tiles (inter CUs only)
+        if (inter_cu) {
         int mvc[2][2];
         mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[0][0], cu.mv[0][1], mvc[0][0], mvc[0][1]);
         mv_clip(cu.x, cu.y, a.w, a.h, w, h, cu.mv[1][0], cu.mv[1][1], mvc[1][0], mvc[1][1]);
@@ -388,6 +398,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     k++;
                 }
             }
+        }
     }
     if (tid == 0) {         // end markers of the two prefix tables: [0..n_tuy) luma, [n_tuy] end, [n_tuy+1 .. n_tu+1) chroma, [n_tu+1] end
         s_pre1[n_tuy] = (uint16_t)n_l1y; s_pre2[n_tuy] = (uint16_t)n_l2y;
@@ -487,6 +498,23 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         }
     }
     __syncthreads();              // residual complete; pass-1 buffer is free and becomes the vertical-pair buffers
+
+    // ---- park the residual of intra / IBC CUs in the picture (s16 fits a pel; the wavefront kernel replaces it by the reconstruction)
+    for (int i = 0; i < ncu && cnt[7]; i++) {
+        const XB200_CU cu = s_cu[i];
+        if (!xb_wavefront_mode(cu.mode)) continue;                  // uniform
+        const int w = 1 << cu.log2w, h = 1 << cu.log2h, lx = cu.x - ctu_x, ly = cu.y - ctu_y;
+        for (int k = tid; k < (w * h) >> 1; k += kR2Threads) {      // luma, two samples per thread
+            const int y = k >> (cu.log2w - 1), x = (k & ((w >> 1) - 1)) << 1;
+            *(int *)(a.cur.y + (size_t)(cu.y + y) * a.s_l + cu.x + x) = *(const int *)(s_res + (ly + y) * kResLStride + lx + x);
+        }
+        for (int k = tid; k < (w * h) >> 2; k += kR2Threads) {      // chroma: both planes, two samples per thread
+            const int pl = k >= ((w * h) >> 3), kk = k - pl * ((w * h) >> 3);
+            const int y = kk >> (cu.log2w - 2), x = (kk & ((w >> 2) - 1)) << 1;
+            *(int *)((pl ? a.cur.v : a.cur.u) + (size_t)((cu.y >> 1) + y) * a.s_c + (cu.x >> 1) + x) =
+                *(const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + ((ly >> 1) + y) * kResCStride + (lx >> 1) + x);
+        }
+    }
 
     int *s_m2l = s_tmp;                                        // [NL][16][kM2LWords]
     int *s_m2c = s_tmp + NL * kTileCap * kM2LWords;            // [NL][16][2][kM2CWords]
