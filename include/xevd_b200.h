@@ -280,6 +280,22 @@ int  xb200_pic_open_peer(xb200_ctx *ctx, xb200_pic *pic, const void *handle64);
 int  xb200_band_pack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, void *d_dst);
 int  xb200_band_unpack(xb200_ctx *ctx, xb200_pic *pic, int y0, int rows, const void *d_src);
 
+/* ---- output path (xevd_pull: SURVEY 8f rows N2 and N4) ------------------------------------------------------------------------
+ * Pictures stay in the device-resident DPB; only what xevd_pull hands out crosses PCIe.  xb200_pic_pull applies, in one kernel,
+ * the Main-profile dynamic range adjustment (tool_dra: xevd_apply_filter -> xevd_apply_dra_chroma_plane / _luma_plane,
+ * src_main/xevdm.c:3311-3348, xevdm_dra.c:272-354; the LUTs are what xevd_init_dra built on the host from the APS), the SPS
+ * cropping window (src_main/xevdm.c:3366-3373) and optionally the application's 16 -> 8-bit conversion
+ * (app/xevd_app_util.h:359-381), then copies the result to the caller's host planes.  The device picture is not modified
+ * (the reference filters a copy too, xevdm.c:3376-3383).                                                                      */
+typedef struct XB200_DRA {
+    int32_t luma_inv_scale_lut[1024];          /* DRA_CONTROL.luma_inv_scale_lut                                              */
+    int32_t chroma_inv_scale_lut[2][1024];     /* DRA_CONTROL.int_chroma_inv_scale_lut                                        */
+} XB200_DRA;
+/* dra: NULL = no adjustment.  out_bits: 16 (int16 planes) or 8 (uint8 planes, (v + 2) >> 2 clipped).  Strides in samples.
+ * Asynchronous on the context stream like xb200_pic_download.                                                                */
+int  xb200_pic_pull(xb200_ctx *ctx, xb200_pic *pic, const XB200_DRA *dra, int out_bits, int crop_l, int crop_r, int crop_t, int crop_b,
+                    void *y, int sy, void *u, int su, void *v, int sv);
+
 /* ---- batched leaf kernels (micro-benchmarks, BASELINE.json config 5) ------------------------------ */
 /* n blocks of (1<<log2w) x (1<<log2h) coefficients, contiguous, in place semantics of
  * xevd_itdq (xevd_itdq.c:494-542): dequant with `scale` then 2-D inverse DCT-2.  iqt selects the Main

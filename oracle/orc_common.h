@@ -101,6 +101,10 @@ void orc_ipred_uv_main(const pel *left, const pel *up, const pel *right, int ava
 void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth);
 const uint8_t *orc_htdf_table(int idx);
 
+/* orc_output.c */
+void orc_dra_apply(ORC_PIC *pic, const XB200_DRA *d);
+void orc_output(const ORC_PIC *pic, int out_bits, int crop_l, int crop_r, int crop_t, int crop_b, void *y, int sy, void *u, int su, void *v, int sv);
+
 /* orc_alf.c */
 int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
 

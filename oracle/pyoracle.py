@@ -172,6 +172,15 @@ class _Backend:
             raise RuntimeError(f"{self.prefix}alf_frame failed: {r}")
         return pic
 
+    def dra_apply(self, pic: HostPicture, dra):
+        """dynamic range adjustment in place (what xevd_pull applies to a copy of the picture when tool_dra is on)"""
+        o = orc_pic(pic)
+        fn = getattr(self.lib, self.prefix + "dra_apply")
+        fn.restype = None
+        fn.argtypes = [C.POINTER(OrcPic), C.c_void_p]
+        fn(C.byref(o), C.addressof(dra))
+        return pic
+
     def pad(self, pic: HostPicture):
         o = orc_pic(pic)
         getattr(self.lib, self.prefix + "pad")(C.byref(o))
@@ -203,6 +212,20 @@ class Oracle(_Backend):
     def mc_taps(self, main_tables):
         return (np.ctypeslib.as_array(self.lib.orc_mc_luma_taps(int(main_tables)), (16, 8)).copy(),
                 np.ctypeslib.as_array(self.lib.orc_mc_chroma_taps(int(main_tables)), (32, 4)).copy())
+
+
+def oracle_output(oracle, pic: HostPicture, out_bits=16, crop=(0, 0, 0, 0)):
+    """orc_output: cropped 16- or 8-bit planes"""
+    cl, cr, ct, cb = crop
+    w, h = pic.w - cl - cr, pic.h - ct - cb
+    dt = np.uint8 if out_bits == 8 else np.int16
+    y, u, v = np.zeros((h, w), dt), np.zeros((h // 2, w // 2), dt), np.zeros((h // 2, w // 2), dt)
+    o = orc_pic(pic)
+    fn = oracle.lib.orc_output
+    fn.restype = None
+    fn.argtypes = [C.POINTER(OrcPic)] + [C.c_int] * 5 + [C.c_void_p, C.c_int] * 3
+    fn(C.byref(o), out_bits, cl, cr, ct, cb, y.ctypes.data, w, u.ctypes.data, w // 2, v.ctypes.data, w // 2)
+    return y, u, v
 
 
 class Reference(_Backend):

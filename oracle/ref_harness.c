@@ -409,6 +409,25 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     return XB200_OK;
 }
 
+/* ---- DRA on pull: the reference's plane functions (src_main/xevdm_dra.c:272-354) in the order xevd_apply_filter calls them --------- */
+#include "xevdm_dra.h"
+void ref_dra_apply(ORC_PIC *pic, const XB200_DRA *d)
+{
+    static DRA_CONTROL dc;
+    XEVD_IMGB im;
+    memset(&im, 0, sizeof(im));
+    memset(&dc, 0, sizeof(dc));
+    memcpy(dc.luma_inv_scale_lut, d->luma_inv_scale_lut, sizeof(dc.luma_inv_scale_lut));
+    memcpy(dc.int_chroma_inv_scale_lut, d->chroma_inv_scale_lut, sizeof(dc.int_chroma_inv_scale_lut));
+    im.np = 3;
+    im.a[0] = pic->y; im.a[1] = pic->u; im.a[2] = pic->v;
+    im.w[0] = pic->w_l; im.h[0] = pic->h_l; im.w[1] = im.w[2] = pic->w_c; im.h[1] = im.h[2] = pic->h_c;
+    im.s[0] = pic->s_l * 2; im.s[1] = im.s[2] = pic->s_c * 2;
+    xevd_apply_dra_chroma_plane(&im, &im, &dc, 1, TRUE);
+    xevd_apply_dra_chroma_plane(&im, &im, &dc, 2, TRUE);
+    xevd_apply_dra_luma_plane(&im, &im, &dc, 0, TRUE);
+}
+
 /* ---- adaptive loop filter: the reference's own per-tile driver alf_process_tile (src_main/xevdm_alf.c:901) ----------------
  * with the final coefficients installed directly (alf->coef_final / chroma_coef), one tile covering the picture. */
 int alf_process_tile(void *arg);

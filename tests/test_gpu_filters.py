@@ -161,3 +161,25 @@ def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
         p.free()
     for a, b, n in zip(got.planes(), want.planes(), "YUV"):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+@pytest.mark.parametrize("use_dra,out_bits,crop", [(0, 16, (0, 0, 0, 0)), (1, 16, (0, 0, 0, 0)), (0, 8, (8, 16, 2, 6)), (1, 8, (4, 0, 0, 10)), (1, 16, (2, 2, 2, 2))])
+def test_output_path(ctx, oracle, use_dra, out_bits, crop):
+    """SURVEY 8f N2 + N4: what xevd_pull hands out - DRA on a copy, SPS cropping window, optional 16 -> 8-bit conversion - in one kernel"""
+    from oracle.pyoracle import oracle_output
+    rng = np.random.default_rng(5 + use_dra + out_bits)
+    w, h = 200, 136
+    pic = HostPicture.random(w, h, 10, rng)
+    dra = synth.make_dra_params(rng) if use_dra else None
+    d = ctx.pic_alloc(w, h).upload(pic, padded=False)
+    got = d.pull(dra, out_bits, crop)
+    still = d.download()
+    d.free()
+    ref = pic.copy()
+    if use_dra:
+        oracle.dra_apply(ref, dra)
+    want = oracle_output(oracle, ref, out_bits, crop)
+    for a, b, n in zip(got, want, "YUV"):
+        assert a.shape == b.shape and np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    for a, b in zip(still.planes(), pic.planes()):
+        assert np.array_equal(a, b), "the device picture must stay unfiltered (it is a reference picture)"

@@ -398,3 +398,16 @@ def test_recon_frame_affine(oracle, reference, variant, kw, bd):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
     m = cu_mask(cl, 5, a.w_scu)
     assert np.array_equal(a.map_mv[m], b.map_mv[m])
+
+
+def test_dra_apply(oracle, reference):
+    """dynamic range adjustment on pull (xevd_apply_dra_chroma_plane / _luma_plane in the order xevd_apply_filter calls them)"""
+    rng = np.random.default_rng(77)
+    w, h = 192, 136
+    dra = synth.make_dra_params(rng)
+    pic = HostPicture.random(w, h, 10, rng)
+    a = oracle.dra_apply(pic.copy(), dra)
+    b = reference.dra_apply(pic.copy(), dra)
+    assert (a.y != pic.y).sum() > 1000 and (a.u != pic.u).sum() > 1000
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))

@@ -67,6 +67,12 @@ class Params(C.Structure):
 assert C.sizeof(Params) == 128
 
 
+class DraParams(C.Structure):
+    """struct XB200_DRA"""
+
+    _fields_ = [("luma_inv_scale_lut", C.c_int32 * 1024), ("chroma_inv_scale_lut", (C.c_int32 * 1024) * 2)]
+
+
 class AlfParams(C.Structure):
     """struct XB200_ALF"""
 
@@ -122,6 +128,8 @@ _SIGS = {
     "xb200_pic_download_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_download_edge_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "xb200_pic_pull": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "xb200_pic_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pic_open_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_band_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),

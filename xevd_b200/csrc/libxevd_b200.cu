@@ -61,6 +61,9 @@ struct xb200_ctx {
     uint8_t *alf_flags_pinned, *alf_flags_dev;
     int alf_flags_cap;
     cudaEvent_t alf_flags_done;
+    unsigned char *out_buf;      // output path: packed planes produced by k_output, then copied to the caller
+    size_t out_cap;
+    int *d_dra;                  // DRA LUTs on the device (3 x 1024 ints)
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
 
@@ -101,6 +104,7 @@ xb200_ctx *xb200_create(int device, int *err)
     c->ring_pos = 0;
     c->d_sync = nullptr; c->sync_cap = 0;
     c->d_order = nullptr; c->order_w = c->order_n = 0;
+    c->out_buf = nullptr; c->out_cap = 0; c->d_dra = nullptr;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         if (err) *err = XB200_ERR_CUDA;
@@ -181,6 +185,8 @@ void xb200_destroy(xb200_ctx *c)
     }
     if (c->d_sync) cudaFree(c->d_sync);
     if (c->d_order) cudaFree(c->d_order);
+    if (c->out_buf) cudaFree(c->out_buf);
+    if (c->d_dra) cudaFree(c->d_dra);
     if (c->alf_copy) cudaFree(c->alf_copy);
     if (c->alf_flags_pinned) cudaFreeHost(c->alf_flags_pinned);
     if (c->alf_flags_dev) cudaFree(c->alf_flags_dev);
@@ -488,6 +494,8 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
                 for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
             CK(c, cudaStreamSynchronize(c->stream));
             if (c->d_order) cudaFree(c->d_order);
+    if (c->out_buf) cudaFree(c->out_buf);
+    if (c->d_dra) cudaFree(c->d_dra);
             c->d_order = nullptr;
             CK(c, cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu));
             CK(c, cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice));
@@ -693,6 +701,45 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     xb::launch_deblock(a, prm->tool_addb != 0, c->stream);
     c->launches += 2;
     CK(c, cudaGetLastError());
+    return XB200_OK;
+}
+
+// ---- output path ----------------------------------------------------------------------------------------------------------
+int xb200_pic_pull(xb200_ctx *c, xb200_pic *p, const XB200_DRA *dra, int out_bits, int crop_l, int crop_r, int crop_t, int crop_b,
+                   void *y, int sy, void *u, int su, void *v, int sv)
+{
+    if (!c || !p || !y || !u || !v || (out_bits != 8 && out_bits != 16)) return XB200_ERR_INVALID_ARGUMENT;
+    if (crop_l < 0 || crop_r < 0 || crop_t < 0 || crop_b < 0 || ((crop_l | crop_r | crop_t | crop_b) & 1)) return XB200_ERR_INVALID_ARGUMENT;
+    const int w = p->w - crop_l - crop_r, h = p->h - crop_t - crop_b;
+    if (w <= 0 || h <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    const size_t bps = out_bits == 8 ? 1 : 2, ny = (size_t)w * h * bps, nc = (size_t)(w >> 1) * (h >> 1) * bps;
+    if (c->out_cap < ny + 2 * nc) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (c->out_buf) cudaFree(c->out_buf);
+        c->out_buf = nullptr; c->out_cap = 0;
+        CK(c, cudaMalloc(&c->out_buf, ny + 2 * nc));
+        c->out_cap = ny + 2 * nc;
+    }
+    xb::OutArgs a;
+    a.y = p->y; a.u = p->u; a.v = p->v; a.s_l = p->s_l; a.s_c = p->s_c;
+    a.x0 = crop_l; a.y0 = crop_t; a.w = w; a.h = h;
+    a.lut_l = a.lut_c = nullptr;
+    if (dra) {
+        if (!c->d_dra) CK(c, cudaMalloc((void **)&c->d_dra, 3 * 1024 * sizeof(int)));
+        CK(c, cudaMemcpyAsync(c->d_dra, dra, 3 * 1024 * sizeof(int), cudaMemcpyHostToDevice, c->stream));   // luma LUT, then the two chroma LUTs
+        CK(c, cudaStreamSynchronize(c->stream));        // the caller's struct may be short-lived
+        a.lut_l = c->d_dra; a.lut_c = c->d_dra + 1024;
+    }
+    a.out_y = c->out_buf; a.out_u = c->out_buf + ny; a.out_v = c->out_buf + ny + nc;
+    a.out8 = out_bits == 8;
+    const dim3 grid(((w >> 1) + 255) / 256, h >> 1);
+    xb::k_output<<<grid, 256, 0, c->stream>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpy2DAsync(y, (size_t)sy * bps, a.out_y, (size_t)w * bps, (size_t)w * bps, h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(u, (size_t)su * bps, a.out_u, (size_t)(w >> 1) * bps, (size_t)(w >> 1) * bps, h >> 1, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpy2DAsync(v, (size_t)sv * bps, a.out_v, (size_t)(w >> 1) * bps, (size_t)(w >> 1) * bps, h >> 1, cudaMemcpyDeviceToHost, c->stream));
     return XB200_OK;
 }
 

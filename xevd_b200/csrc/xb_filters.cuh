@@ -379,4 +379,48 @@ inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
     }
 }
 
+// ---- output path: DRA + crop + bit-depth conversion into packed planes (xb200_pic_pull) ---------------------------------------------
+struct OutArgs {
+    const pel *y, *u, *v;
+    int s_l, s_c;
+    int x0, y0, w, h;               // luma crop window (chroma = half)
+    const int *lut_l, *lut_c;       // device LUTs: luma_inv_scale_lut[1024], int_chroma_inv_scale_lut[2][1024]; null = no DRA
+    void *out_y, *out_u, *out_v;    // packed, row stride = plane width
+    int out8;
+};
+// one thread per chroma sample: its 2x2 luma samples and the two chroma samples
+__global__ void __launch_bounds__(256) k_output(const __grid_constant__ OutArgs a)
+{
+    const int cw = a.w >> 1, ch = a.h >> 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (k >= cw || j >= ch) return;
+    const pel *py = a.y + (size_t)(a.y0 + 2 * j) * a.s_l + a.x0 + 2 * k;
+    int l[4] = {py[0], py[1], py[a.s_l], py[a.s_l + 1]};
+    int c[2] = {a.u[(size_t)((a.y0 >> 1) + j) * a.s_c + (a.x0 >> 1) + k], a.v[(size_t)((a.y0 >> 1) + j) * a.s_c + (a.x0 >> 1) + k]};
+    if (a.lut_l) {
+        // chroma first, scaled by the factor of the UNMAPPED co-located luma sample (xevdm_dra.c:301-354), then luma (:272-300)
+        const int ref = max(l[0], 0);
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const int sv = (int16_t)(c[p] - 512);
+            int off = (abs(sv) * a.lut_c[p * 1024 + ref] + 256) >> 9;
+            c[p] = (int16_t)(512 + (sv < 0 ? -off : off));
+        }
+#pragma unroll
+        for (int p = 0; p < 4; p++) l[p] = (int16_t)a.lut_l[l[p]];
+    }
+    if (a.out8) {
+        uint8_t *oy = (uint8_t *)a.out_y + (size_t)(2 * j) * a.w + 2 * k;
+        oy[0] = (uint8_t)xb_clip3(0, 255, (l[0] + 2) >> 2); oy[1] = (uint8_t)xb_clip3(0, 255, (l[1] + 2) >> 2);
+        oy[a.w] = (uint8_t)xb_clip3(0, 255, (l[2] + 2) >> 2); oy[a.w + 1] = (uint8_t)xb_clip3(0, 255, (l[3] + 2) >> 2);
+        ((uint8_t *)a.out_u)[(size_t)j * cw + k] = (uint8_t)xb_clip3(0, 255, (c[0] + 2) >> 2);
+        ((uint8_t *)a.out_v)[(size_t)j * cw + k] = (uint8_t)xb_clip3(0, 255, (c[1] + 2) >> 2);
+    } else {
+        int16_t *oy = (int16_t *)a.out_y + (size_t)(2 * j) * a.w + 2 * k;
+        oy[0] = (int16_t)l[0]; oy[1] = (int16_t)l[1]; oy[a.w] = (int16_t)l[2]; oy[a.w + 1] = (int16_t)l[3];
+        ((int16_t *)a.out_u)[(size_t)j * cw + k] = (int16_t)c[0];
+        ((int16_t *)a.out_v)[(size_t)j * cw + k] = (int16_t)c[1];
+    }
+}
+
 }  // namespace xb

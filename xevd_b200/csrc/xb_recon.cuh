@@ -78,7 +78,8 @@ __device__ __forceinline__ void mc_tile_ld(Ld ld, const int16_t *cx, const int16
 {
     constexpr int HALF = NTAP / 2 - 1;
     const int maxv = (1 << bd) - 1;
-    const int col = lane & (tw - 1), r0 = (lane / tw) * rpl;
+    const int ltw = 31 - __clz(tw);                 // tile widths are powers of two: shifts instead of divisions in the sample loops
+    const int col = lane & (tw - 1), r0 = (lane >> ltw) * rpl;
     const bool active = r0 < th;
     if (!fx && !fy) {
 #pragma unroll
@@ -101,7 +102,7 @@ __device__ __forceinline__ void mc_tile_ld(Ld ld, const int16_t *cx, const int16
         for (int t = 0; t < NTAP; t++) c[t] = cx[t];
         const int s1 = fy ? min(4, bd - 8) : 6;
         for (int idx = lane; idx < wrows * tw; idx += 32) {
-            const int r = idx / tw, cc = idx & (tw - 1);
+            const int r = idx >> ltw, cc = idx & (tw - 1);
             int acc = 0;
 #pragma unroll
             for (int t = 0; t < NTAP; t++) acc += c[t] * win[r * wstride + cc + t];
@@ -672,8 +673,8 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const int luma_slots = S * nscu, chroma_slots = Sc * nscu;
         for (int s = tid; s < luma_slots + 2 * chroma_slots; s += kReconThreads) {
             int pl, x, ys;
-            if (s < luma_slots) { pl = 0; ys = s / S; x = s - ys * S; }
-            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; ys = t / Sc; x = t - ys * Sc; }
+            if (s < luma_slots) { pl = 0; ys = s >> a.log2_ctu; x = s - ys * S; }
+            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; ys = t >> (a.log2_ctu - 1); x = t - ys * Sc; }
             const int xs = pl == 0 ? (x >> 2) : (x >> 1);
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
@@ -697,8 +698,8 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const int luma_slots = S * nscu, chroma_slots = Sc * nscu;
         for (int s = tid; s < luma_slots + 2 * chroma_slots; s += kReconThreads) {
             int pl, y, xs;
-            if (s < luma_slots) { pl = 0; xs = s / S; y = s - xs * S; }
-            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; xs = t / Sc; y = t - xs * Sc; }
+            if (s < luma_slots) { pl = 0; xs = s >> a.log2_ctu; y = s - xs * S; }
+            else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; xs = t >> (a.log2_ctu - 1); y = t - xs * Sc; }
             const int ys = pl == 0 ? (y >> 2) : (y >> 1);
             const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
             if (ci == 0xffff) continue;
@@ -721,7 +722,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         int16_t *scr = sm.mc + warp * kMcScratchPerWarp;
         const int tiles = S >> 4;
         for (int t = warp; t < tiles * tiles; t += kReconWarps) {
-            const int t_x = (t % tiles) << 4, t_y = (t / tiles) << 4;        // tile origin inside the CTU (luma)
+            const int t_x = (t & (tiles - 1)) << 4, t_y = (t >> (a.log2_ctu - 4)) << 4;        // tile origin inside the CTU (luma)
             if (ctu_x + t_x >= a.w || ctu_y + t_y >= a.h) continue;
             // walk the (up to 16) CUs that start inside this tile, or the single CU that covers it
             for (int sy = 0; sy < 4; sy++) {
@@ -744,7 +745,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     {
                         const int rpl = max(1, (tw * th) >> 5);
                         pred_tile<8>(a, cu, 0, px - cx, py - cy, tw, th, rpl, scr, lane, pr);
-                        const int col = lane & (tw - 1), r0 = (lane / tw) * rpl;
+                        const int col = lane & (tw - 1), r0 = (lane >> (31 - __clz(tw))) * rpl;
                         if (r0 < th) {
                             pel *dst = a.cur.y + (ctu_y + py + r0) * a.s_l + ctu_x + px + col;
                             const int16_t *res = sm.res_y + (py + r0) * (S + 2) + px + col;
@@ -761,7 +762,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
 #pragma unroll
                         for (int pl = 1; pl <= 2; pl++) {
                             pred_tile<4>(a, cu, pl, (px - cx) >> 1, (py - cy) >> 1, cw, ch, rpl, scr, lane, pr);
-                            const int col = lane & (cw - 1), r0 = (lane / cw) * rpl;
+                            const int col = lane & (cw - 1), r0 = (lane >> (31 - __clz(cw))) * rpl;
                             if (r0 < ch) {
                                 pel *dst = (pl == 1 ? a.cur.u : a.cur.v) + (((ctu_y + py) >> 1) + r0) * a.s_c + ((ctu_x + px) >> 1) + col;
                                 const int16_t *res = (pl == 1 ? sm.res_u : sm.res_v) + ((py >> 1) + r0) * (Sc + 2) + (px >> 1) + col;
@@ -779,10 +780,13 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
 
     // ---- phase B1: intra / IBC CUs are predicted by the wavefront kernel; their residual (neighbour-independent, transformed above with
     //      everything else) is parked in the picture, where that kernel picks it up with its CTU preload
-    for (int i = tid; i < S * S + 2 * Sc * Sc; i += kReconThreads) {
+    bool any_wf = false;
+    for (int i = tid; i < ncu; i += kReconThreads) any_wf |= xb_wavefront_mode(cus[i].mode);
+    any_wf = __syncthreads_or(any_wf);
+    for (int i = tid; any_wf && i < S * S + 2 * Sc * Sc; i += kReconThreads) {
         int pl, x, y;
-        if (i < S * S) { pl = 0; y = i / S; x = i - y * S; }
-        else { int t = i - S * S; pl = 1 + (t >= Sc * Sc); t -= (pl - 1) * Sc * Sc; y = t / Sc; x = t - y * Sc; }
+        if (i < S * S) { pl = 0; y = i >> a.log2_ctu; x = i - y * S; }
+        else { int t = i - S * S; pl = 1 + (t >= Sc * Sc); t -= (pl - 1) * Sc * Sc; y = t >> (a.log2_ctu - 1); x = t - y * Sc; }
         const int sh = pl ? 1 : 0;
         const unsigned ci = sm.cu_of_scu[((y << sh) >> 2) * nscu + ((x << sh) >> 2)];
         if (ci == 0xffff || !xb_wavefront_mode(cus[ci].mode)) continue;
@@ -832,7 +836,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const unsigned ci = sm.cu_of_scu[i];
         if (ci == 0xffff) continue;
         const XB200_CU cu = cus[ci];
-        const int gx = (ctu_x >> 2) + (i % nscu), gy = (ctu_y >> 2) + (i / nscu);
+        const int gx = (ctu_x >> 2) + (i & (nscu - 1)), gy = (ctu_y >> 2) + (i >> (a.log2_ctu - 2));
         const int p = gy * a.w_scu + gx;
         const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
         uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);     // MCU_SET_IBC

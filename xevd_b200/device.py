@@ -68,6 +68,17 @@ class DevicePicture:
                           "xb200_pic_download_unrefined_mv")
         return out
 
+    def pull(self, dra=None, out_bits: int = 16, crop=(0, 0, 0, 0)):
+        """what xevd_pull hands out: optional DRA, crop (left, right, top, bottom in luma samples), 16- or 8-bit planes"""
+        cl, cr, ct, cb = crop
+        w, h = self.w - cl - cr, self.h - ct - cb
+        dt = np.uint8 if out_bits == 8 else np.int16
+        y, u, v = np.zeros((h, w), dt), np.zeros((h // 2, w // 2), dt), np.zeros((h // 2, w // 2), dt)
+        self.ctx._chk(self.ctx.lib.xb200_pic_pull(self.ctx.handle, self.handle, C.byref(dra) if dra is not None else None, out_bits, cl, cr, ct, cb,
+                                                  y.ctypes.data, w, u.ctypes.data, w // 2, v.ctypes.data, w // 2), "xb200_pic_pull")
+        self.ctx.sync()
+        return y, u, v
+
     def download_edge_map(self) -> np.ndarray:
         out = np.zeros(((self.w + 3) >> 2) * ((self.h + 3) >> 2), np.uint8)
         self.ctx._chk(self.ctx.lib.xb200_pic_download_edge_map(self.ctx.handle, self.handle, out.ctypes.data), "xb200_pic_download_edge_map")

@@ -531,3 +531,19 @@ def make_alf_params(rng, enable=(1, 1, 1)):
     for i in range(3):
         a.enable[i] = enable[i]
     return a
+
+
+def make_dra_params(rng, bit_depth: int = 10):
+    """random but plausible DRA look-up tables (what xevd_init_dra builds from an APS): a monotonic luma mapping within the 10-bit
+    range and chroma scale factors around 1.0 in 9 fractional bits"""
+    from .abi import DraParams
+    d = DraParams()
+    steps = rng.integers(0, 3, 1024)
+    lut = np.minimum(np.cumsum(steps) * 1023 // max(1, int(steps.sum())), 1023)
+    for i in range(1024):
+        d.luma_inv_scale_lut[i] = int(lut[i])
+    for c in range(2):
+        sc = np.clip(512 + np.cumsum(rng.integers(-3, 4, 1024)), 256, 1023)
+        for i in range(1024):
+            d.chroma_inv_scale_lut[c][i] = int(sc[i])
+    return d
