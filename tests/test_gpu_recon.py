@@ -387,3 +387,87 @@ def test_band_mode_single_gpu(ctx, oracle, variant, lg):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
     assert np.array_equal(edge_got, edge_want)
+
+
+@pytest.mark.parametrize("w,h", [(3840, 2160), (7680, 4320)])
+def test_full_size_identity_property(ctx, w, h):
+    """BASELINE full sizes (4K, 8K) through a size-independent property: zero motion + no coefficients must return the reference
+    picture exactly (every CTU, every tile, the TMA windows and the store path are exercised; no oracle run needed)"""
+    rng = np.random.default_rng(1)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=10, variant="A", seed=2, n_refs=1, coded_frac=0.0)
+    cl.cus["mv"] = 0
+    ref = HostPicture(w, h, 0)
+    ref.y[...] = rng.integers(0, 1024, (h, w), dtype=np.int16)
+    ref.u[...] = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.int16)
+    ref.v[...] = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.int16)
+    dref = ctx.pic_alloc(w, h).upload(ref)
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, [dref], [], cl)
+    got = cur.download()
+    dref.free(); cur.free()
+    for a, b, n in zip(got.planes(), ref.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+def test_full_size_integer_shift_property(ctx):
+    """4K: whole-sample motion (8, -4) with no coefficients = the reference picture displaced (interior samples)"""
+    w, h = 3840, 2160
+    rng = np.random.default_rng(3)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=10, variant="B", seed=4, n_refs=1, coded_frac=0.0, bi_frac=0.0)
+    cl.cus["mv"] = 0
+    cl.cus["mv"][:, 0, 0] = 8 * 4
+    cl.cus["mv"][:, 0, 1] = -4 * 4
+    cl.cus["refi"][:, 0] = 0
+    cl.cus["refi"][:, 1] = -1
+    ref = HostPicture(w, h, 0)
+    ref.y[...] = rng.integers(0, 1024, (h, w), dtype=np.int16)
+    ref.u[...] = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.int16)
+    ref.v[...] = rng.integers(0, 1024, (h // 2, w // 2), dtype=np.int16)
+    dref = ctx.pic_alloc(w, h).upload(ref)
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, [dref], [], cl)
+    got = cur.download()
+    dref.free(); cur.free()
+    assert np.array_equal(got.y[4:, :w - 8], ref.y[:h - 4, 8:])
+    assert np.array_equal(got.u[2:, :w // 2 - 4], ref.u[:h // 2 - 2, 4:]) and np.array_equal(got.v[2:, :w // 2 - 4], ref.v[:h // 2 - 2, 4:])
+
+
+def test_4k_parity_vs_oracle(ctx, oracle):
+    """the bench workload itself (4K config 2A and 2B) bit-exact against the oracle"""
+    for variant in ("A", "B"):
+        _run(ctx, oracle, 3840, 2160, 10, variant, seed=11, n_refs=2 if variant == "B" else 1)
+
+
+def test_empty_and_ragged_inputs(ctx, oracle):
+    """CTUs without any CU (ragged ctu_first) and a picture with no CU at all leave the picture untouched / succeed"""
+    w, h, bd = 256, 136, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=5, n_refs=2)
+    refs = synth.make_refs(w, h, bd, 2, seed=6)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    # drop the CUs of every second CTU
+    keep = np.ones(cl.n_cu, bool)
+    for k in range(0, cl.n_ctu, 2):
+        keep[int(cl.ctu_first[k]):int(cl.ctu_first[k + 1])] = False
+    sub = cl.band(0, (h + 63) // 64)
+    counts = np.array([keep[int(cl.ctu_first[k]):int(cl.ctu_first[k + 1])].sum() for k in range(cl.n_ctu)])
+    sub.cus = cl.cus[keep].copy()
+    sub.ctu_first = np.concatenate(([0], np.cumsum(counts))).astype(np.uint32)
+    sizes = np.array([__import__("xevd_b200.frame", fromlist=["cu_coef_count"]).cu_coef_count(c) for c in cl.cus])
+    pieces = [cl.coef[int(c["coef_off"]):int(c["coef_off"]) + int(s)] for c, s, kf in zip(cl.cus, sizes, keep) if kf]
+    sub.coef = np.concatenate(pieces) if pieces else np.zeros(0, np.int16)
+    sub.cus["coef_off"] = np.concatenate(([0], np.cumsum(sizes[keep])))[:-1]
+    sub.validate()
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], sub)
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], sub)
+    got = cur.download()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    # no CU at all
+    empty = cl.band(0, (h + 63) // 64)
+    empty.cus = cl.cus[:0].copy(); empty.coef = np.zeros(0, np.int16); empty.ctu_first = np.zeros(cl.n_ctu + 1, np.uint32)
+    cur2 = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur2, drefs, drefs[::-1], empty)
+    assert not cur2.download().y.any()
+    for p in drefs + [cur, cur2]:
+        p.free()
