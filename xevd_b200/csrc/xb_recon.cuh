@@ -168,7 +168,7 @@ __device__ __forceinline__ void pred_tile(const XbFrameArgs &a, const XB200_CU &
         use[1] = false;
     int n = 0;
     int p0[8];
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < 2; l++) {
         if (!use[l]) continue;
         const int ri = cu.refi[l];
@@ -187,19 +187,16 @@ __device__ __forceinline__ void pred_tile(const XbFrameArgs &a, const XB200_CU &
         }
         const int16_t *cx = LUMA ? c_mc_l[a.main_tables][phx] : c_mc_c[a.main_tables][phx];
         const int16_t *cy = LUMA ? c_mc_l[a.main_tables][phy] : c_mc_c[a.main_tables][phy];
-        if (n == 0) {
-            mc_tile<NTAP>(rp + iy * stride + ix, stride, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, p0);
-        } else {
-            mc_tile<NTAP>(rp + iy * stride + ix, stride, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, pr);
+        if (n == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) p0[i] = pr[i];
         }
+        mc_tile<NTAP>(rp + iy * stride + ix, stride, cx, cy, fx, fy, tw, th, rpl, bd, scr, lane, pr);      // one call site: code size matters here
         n++;
     }
     if (n == 2) {
 #pragma unroll
         for (int i = 0; i < 8; i++) pr[i] = (p0[i] + pr[i] + 1) >> 1;      // xevd_average_16b_no_clip
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) pr[i] = p0[i];
     }
 }
 
@@ -338,56 +335,57 @@ __device__ void dmvr_sub_pu(const XbFrameArgs &a, const XB200_CU &cu, const int 
         o[0] = (int16_t)(refined[0][0] >> 2); o[1] = (int16_t)(refined[0][1] >> 2);
         o[2] = (int16_t)(refined[1][0] >> 2); o[3] = (int16_t)(refined[1][1] >> 2);
     }
-    // final prediction: both lists, three planes, from the padded windows
+    // final prediction from the padded windows, plane by plane: both lists, average, residual, clip, store.  The loops stay rolled and
+    // every interpolation routine has ONE call site: this kernel is instruction-cache bound (profiles/r1), code size is time.
     const int px = cu.x + sx, py = cu.y + sy;
-    int pl0[3][8], pl1[3][8];
     const int rpl_l = max(1, (dx * dy) >> 5), rpl_c = max(1, ((dx >> 1) * (dy >> 1)) >> 5);
+    int gxv[2], gyv[2], dl[2][2], dc[2][2], wg[2][2];
+#pragma unroll
     for (int l = 0; l < 2; l++) {
         int clx, cly;
         const bool clipped = dmvr_clip_one(px, py, a.w, a.h, dx, dy, refined[l][0] >> 2, refined[l][1] >> 2, clx, cly);
-        const int wgx = ((px << 2) + start[l][0]) << 2, wgy = ((py << 2) + start[l][1]) << 2;       // window of the start vector
-        int gx, gy, dlx, dly, dcx, dcy;
+        wg[l][0] = ((px << 2) + start[l][0]) << 2; wg[l][1] = ((py << 2) + start[l][1]) << 2;       // window of the start vector
         if (clipped) {
-            gx = (px << 4) + (clx << 2); gy = (py << 4) + (cly << 2);
-            dlx = (clx >> 2) - (start[l][0] >> 2); dly = (cly >> 2) - (start[l][1] >> 2);
-            dcx = (clx >> 3) - (start[l][0] >> 3); dcy = (cly >> 3) - (start[l][1] >> 3);
+            gxv[l] = (px << 4) + (clx << 2); gyv[l] = (py << 4) + (cly << 2);
+            dl[l][0] = (clx >> 2) - (start[l][0] >> 2); dl[l][1] = (cly >> 2) - (start[l][1] >> 2);
+            dc[l][0] = (clx >> 3) - (start[l][0] >> 3); dc[l][1] = (cly >> 3) - (start[l][1] >> 3);
         } else {
-            gx = (px << 4) + refined[l][0]; gy = (py << 4) + refined[l][1];
-            dlx = (refined[l][0] >> 4) - (start[l][0] >> 2); dly = (refined[l][1] >> 4) - (start[l][1] >> 2);
-            dcx = (refined[l][0] >> 5) - (start[l][0] >> 3); dcy = (refined[l][1] >> 5) - (start[l][1] >> 3);
-        }
-        const int ri = cu.refi[l];
-#pragma unroll
-        for (int pl = 0; pl < 3; pl++) {
-            const pel *plane = pl == 0 ? a.ref_y[l][ri] : (pl == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
-            const int s = pl ? a.s_c : a.s_l;
-            const int wx = pl ? (wgx >> 5) - 1 : (wgx >> 4) - 3, wy = pl ? (wgy >> 5) - 1 : (wgy >> 4) - 3;
-            const int bw = pl ? dx >> 1 : dx, bh = pl ? dy >> 1 : dy;
-            const int ww = bw + (pl ? 3 : 7), wh = bh + (pl ? 3 : 7), ddxi = pl ? dcx : dlx, ddyi = pl ? dcy : dly;
-            auto ld = [&](int r, int c) { return (int)plane[(ptrdiff_t)(wy + min(max(ddyi + r, 0), wh - 1)) * s + wx + min(max(ddxi + c, 0), ww - 1)]; };
-            int (&dst)[8] = l ? pl1[pl] : pl0[pl];
-            if (pl == 0) {
-                const bool fx = (gx & 15) != 0, fy = (gy & 15) != 0;
-                mc_tile_ld<8>(ld, c_mc_l[a.main_tables][gx & 15], c_mc_l[a.main_tables][gy & 15], fx, fy, bw, bh, rpl_l, a.bd_l, scr, lane, dst);
-            } else {
-                const bool fx = (gx & 31) != 0, fy = (gy & 31) != 0;
-                mc_tile_ld<4>(ld, c_mc_c[a.main_tables][gx & 31], c_mc_c[a.main_tables][gy & 31], fx, fy, bw, bh, rpl_c, a.bd_c, scr, lane, dst);
-            }
+            gxv[l] = (px << 4) + refined[l][0]; gyv[l] = (py << 4) + refined[l][1];
+            dl[l][0] = (refined[l][0] >> 4) - (start[l][0] >> 2); dl[l][1] = (refined[l][1] >> 4) - (start[l][1] >> 2);
+            dc[l][0] = (refined[l][0] >> 5) - (start[l][0] >> 3); dc[l][1] = (refined[l][1] >> 5) - (start[l][1] >> 3);
         }
     }
-    // average, residual, clip, store (xevd_average_16b_no_clip + xevdm_recon)
     const int maxv = (1 << a.bd_l) - 1;
-#pragma unroll
+#pragma unroll 1
     for (int pl = 0; pl < 3; pl++) {
-        const int sh = pl ? 1 : 0, bw = dx >> sh, bh = dy >> sh, rpl = pl ? rpl_c : rpl_l;
-        const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+        const int sh = pl ? 1 : 0, bw = dx >> sh, bh = dy >> sh, rpl = pl ? rpl_c : rpl_l, s = pl ? a.s_c : a.s_l;
+        const int ww = bw + (pl ? 3 : 7), wh = bh + (pl ? 3 : 7);
+        int p0[8], pr[8];
+#pragma unroll 1
+        for (int l = 0; l < 2; l++) {
+            const int ri = cu.refi[l];
+            const pel *plane = pl == 0 ? a.ref_y[l][ri] : (pl == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
+            const int wgx = l ? wg[1][0] : wg[0][0], wgy = l ? wg[1][1] : wg[0][1], gx = l ? gxv[1] : gxv[0], gy = l ? gyv[1] : gyv[0];
+            const int wx = pl ? (wgx >> 5) - 1 : (wgx >> 4) - 3, wy = pl ? (wgy >> 5) - 1 : (wgy >> 4) - 3;
+            const int ddxi = pl ? (l ? dc[1][0] : dc[0][0]) : (l ? dl[1][0] : dl[0][0]), ddyi = pl ? (l ? dc[1][1] : dc[0][1]) : (l ? dl[1][1] : dl[0][1]);
+            auto ld = [&](int r, int c) { return (int)plane[(ptrdiff_t)(wy + min(max(ddyi + r, 0), wh - 1)) * s + wx + min(max(ddxi + c, 0), ww - 1)]; };
+            if (l == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) p0[i] = pr[i];
+            }
+            if (pl == 0) mc_tile_ld<8>(ld, c_mc_l[a.main_tables][gx & 15], c_mc_l[a.main_tables][gy & 15], (gx & 15) != 0, (gy & 15) != 0, bw, bh, rpl, a.bd_l, scr, lane, pr);
+            else mc_tile_ld<4>(ld, c_mc_c[a.main_tables][gx & 31], c_mc_c[a.main_tables][gy & 31], (gx & 31) != 0, (gy & 31) != 0, bw, bh, rpl, a.bd_c, scr, lane, pr);
+        }
+        // average, residual, clip, store (xevd_average_16b_no_clip + xevdm_recon)
+        const int col = lane & (bw - 1), r0 = (lane >> (31 - __clz(bw))) * rpl;
         if (r0 >= bh) continue;
         const int lx = ((cu.x + sx - ctu_x) >> sh) + col, ly = ((cu.y + sy - ctu_y) >> sh) + r0;
-        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * (pl ? rs_c : rs_l) + lx;
-        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + lx;
+        const int rs = pl ? rs_c : rs_l;
+        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * rs + lx;
+        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * s + (ctu_x >> sh) + lx;
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < rpl) dst[(size_t)i * (pl ? a.s_c : a.s_l)] = (pel)xb_clip3(0, maxv, (int16_t)(((pl0[pl][i] + pl1[pl][i] + 1) >> 1) + res[i * (pl ? rs_c : rs_l)]));
+            if (i < rpl) dst[(size_t)i * s] = (pel)xb_clip3(0, maxv, (int16_t)(((p0[i] + pr[i] + 1) >> 1) + res[i * rs]));
     }
     (void)w;
 }
@@ -465,44 +463,29 @@ __device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB20
 {
     const int w = 1 << cu.log2w, h = 1 << cu.log2h;
     const bool six = (cu.flags & XB200_CUF_AFF6) != 0, eif = m.sub_w < 8 || m.sub_h < 8;
-    int acc[3][8];
-    int nl = 0;
     const int rpl_l = max(1, (tw * th) >> 5), rpl_c = max(1, ((tw >> 1) * (th >> 1)) >> 5);
-    for (int l = 0; l < 2; l++) {
-        if (cu.refi[l] < 0) continue;
-        const int ri = cu.refi[l];
-        int dh[2], dv[2];
-        aff_gradients(ex.u.affine.cp[l], cu.log2w, cu.log2h, six, dh, dv);
-        const int sc[2] = {ex.u.affine.cp[l][0][0] << 7, ex.u.affine.cp[l][0][1] << 7};
-        int mxv[2], mnv[2], mvo[2], mvc[2];
-        if (eif) {       // eif_derive_mv_clip_range (xevdm_mc.c:2108-2150), 1/32 sample
-            const int pmx[2] = {(a.w + 128 - cu.x - w - 1) << 5, (a.h + 128 - cu.y - h - 1) << 5}, pmn[2] = {(-cu.x - 128) << 5, (-cu.y - 128) << 5};
-#pragma unroll
-            for (int c = 0; c < 2; c++) {
-                if (m.mem_ok) { mxv[c] = pmx[c]; mnv[c] = pmn[c]; }
-                else {
-                    const int centre = aff_round(sc[c] + dh[c] * (w >> 1) + dv[c] * (h >> 1), 4);
-                    const int lg = (c == 0 ? cu.log2w : cu.log2h) - 3;
-                    const int spread = lg == 0 ? 128 : (lg == 1 ? 256 : (lg == 2 ? 544 : (lg == 3 ? 1120 : 2272)));
-                    mnv[c] = centre - spread; mxv[c] = centre + spread;
-                    if (mnv[c] < pmn[c]) { mnv[c] = pmn[c]; mxv[c] = min(pmx[c], pmn[c] + 2 * spread); }
-                    else if (mxv[c] > pmx[c]) { mxv[c] = pmx[c]; mnv[c] = max(pmn[c], pmx[c] - 2 * spread); }
-                }
-                mxv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mxv[c]);
-                mnv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mnv[c]);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 2; c++) mvo[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, aff_round(sc[c] + dh[c] * (m.sub_w >> 1) + dv[c] * (m.sub_h >> 1), 5));
-            mvc[0] = min((a.w + 128 - cu.x - w) << 4, max((-128 - cu.x) << 4, mvo[0]));
-            mvc[1] = min((a.h + 128 - cu.y - h) << 4, max((-128 - cu.y) << 4, mvo[1]));
-        }
-#pragma unroll
-        for (int pl = 0; pl < 3; pl++) {
-            const int sh = pl ? 1 : 0, bw = tw >> sh, bh = th >> sh, rpl = pl ? rpl_c : rpl_l, bd = pl ? a.bd_c : a.bd_l, s = pl ? a.s_c : a.s_l;
+    const int maxv = (1 << a.bd_l) - 1;
+    // plane by plane, lists inside, loops rolled, one call site per interpolation routine (instruction-cache bound kernel: code size is time)
+#pragma unroll 1
+    for (int pl = 0; pl < 3; pl++) {
+        const int sh = pl ? 1 : 0, bw = tw >> sh, bh = th >> sh, rpl = pl ? rpl_c : rpl_l, bd = pl ? a.bd_c : a.bd_l, s = pl ? a.s_c : a.s_l;
+        int acc[8];
+        int nl = 0;
+#pragma unroll 1
+        for (int l = 0; l < 2; l++) {
+            if (cu.refi[l] < 0) continue;
+            const int ri = cu.refi[l];
+            int dh[2], dv[2];
+            aff_gradients(ex.u.affine.cp[l], cu.log2w, cu.log2h, six, dh, dv);
+            const int sc[2] = {ex.u.affine.cp[l][0][0] << 7, ex.u.affine.cp[l][0][1] << 7};
             const pel *plane = pl == 0 ? a.ref_y[l][ri] : (pl == 1 ? a.ref_u[l][ri] : a.ref_v[l][ri]);
             int pr[8];
             if (!eif) {
+                int mvo[2], mvc[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) mvo[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, aff_round(sc[c] + dh[c] * (m.sub_w >> 1) + dv[c] * (m.sub_h >> 1), 5));
+                mvc[0] = min((a.w + 128 - cu.x - w) << 4, max((-128 - cu.x) << 4, mvo[0]));
+                mvc[1] = min((a.h + 128 - cu.y - h) << 4, max((-128 - cu.y) << 4, mvo[1]));
                 const int gx = ((cu.x + tx) << 4) + mvc[0], gy = ((cu.y + ty) << 4) + mvc[1];
                 if (pl == 0) {
                     const pel *ref = plane + (ptrdiff_t)(gy >> 4) * s + (gx >> 4);
@@ -512,6 +495,23 @@ __device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB20
                     mc_tile<4>(ref, s, c_mc_c[a.main_tables][gx & 31], c_mc_c[a.main_tables][gy & 31], (mvo[0] & 31) != 0, (mvo[1] & 31) != 0, bw, bh, rpl, bd, scr, lane, pr);
                 }
             } else {
+                // eif_derive_mv_clip_range (xevdm_mc.c:2108-2150), 1/32 sample
+                int mxv[2], mnv[2];
+                const int pmx[2] = {(a.w + 128 - cu.x - w - 1) << 5, (a.h + 128 - cu.y - h - 1) << 5}, pmn[2] = {(-cu.x - 128) << 5, (-cu.y - 128) << 5};
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    if (m.mem_ok) { mxv[c] = pmx[c]; mnv[c] = pmn[c]; }
+                    else {
+                        const int centre = aff_round(sc[c] + dh[c] * (w >> 1) + dv[c] * (h >> 1), 4);
+                        const int lg = (c == 0 ? cu.log2w : cu.log2h) - 3;
+                        const int spread = lg == 0 ? 128 : (lg == 1 ? 256 : (lg == 2 ? 544 : (lg == 3 ? 1120 : 2272)));
+                        mnv[c] = centre - spread; mxv[c] = centre + spread;
+                        if (mnv[c] < pmn[c]) { mnv[c] = pmn[c]; mxv[c] = min(pmx[c], pmn[c] + 2 * spread); }
+                        else if (mxv[c] > pmx[c]) { mxv[c] = pmx[c]; mnv[c] = max(pmn[c], pmx[c] - 2 * spread); }
+                    }
+                    mxv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mxv[c]);
+                    mnv[c] = xb_clip3(-(1 << 17), (1 << 17) - 1, mnv[c]);
+                }
                 // bilinear samples of the (bw + 2) x (bh + 2) neighbourhood of the tile, positions relative to the CU plane
                 const int mv0x = sc[0] >> sh, mv0y = sc[1] >> sh, lim_x0 = mnv[0] >> sh, lim_x1 = mxv[0] >> sh, lim_y0 = mnv[1] >> sh, lim_y1 = mxv[1] >> sh;
                 const int ox = (cu.x >> sh), oy = (cu.y >> sh), px0 = tx >> sh, py0 = ty >> sh;
@@ -519,7 +519,7 @@ __device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB20
                 const int st = bw + 2;
                 int16_t *bb = scr, *hb = scr + 18 * 18;
                 for (int idx = lane; idx < st * (bh + 2); idx += 32) {
-                    const int j = idx / st - 1 + py0, i = idx % st - 1 + px0;          // sample position inside the CU plane
+                    const int jj = idx / st, j = jj - 1 + py0, i = idx - jj * st - 1 + px0;          // sample position inside the CU plane
                     const int vx = xb_clip3(lim_x0, lim_x1, (mv0x + i * dh[0] + j * dv[0]) >> 4), vy = xb_clip3(lim_y0, lim_y1, (mv0y + i * dh[1] + j * dv[1]) >> 4);
                     const pel *r = plane + (ptrdiff_t)(oy + j + (vy >> 5)) * s + ox + i + (vx >> 5);
                     const int fx = vx & 31, fy = vy & 31;
@@ -527,12 +527,13 @@ __device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB20
                     bb[idx] = (int16_t)(((64 - 2 * fy) * a0 + 2 * fy * a1 + (1 << (s2 - 1))) >> s2);
                 }
                 __syncwarp();
+                const int lbw = 31 - __clz(bw);
                 for (int idx = lane; idx < bw * (bh + 2); idx += 32) {
-                    const int j = idx / bw, i = idx % bw;
+                    const int j = idx >> lbw, i = idx & (bw - 1);
                     hb[idx] = (int16_t)((-bb[j * st + i] + 10 * bb[j * st + i + 1] - bb[j * st + i + 2] + (sh_h ? 1 << (sh_h - 1) : 0)) >> sh_h);
                 }
                 __syncwarp();
-                const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+                const int col = lane & (bw - 1), r0 = (lane >> lbw) * rpl;
 #pragma unroll
                 for (int i = 0; i < 8; i++)
                     if (i < rpl && r0 < bh) {
@@ -542,22 +543,18 @@ __device__ void affine_tile(const XbFrameArgs &a, const XB200_CU &cu, const XB20
                 __syncwarp();
             }
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[pl][i] = nl ? (acc[pl][i] + pr[i] + 1) >> 1 : pr[i];
+            for (int i = 0; i < 8; i++) acc[i] = nl ? (acc[i] + pr[i] + 1) >> 1 : pr[i];
+            nl++;
         }
-        nl++;
-    }
-    const int maxv = (1 << a.bd_l) - 1;
-#pragma unroll
-    for (int pl = 0; pl < 3; pl++) {
-        const int sh = pl ? 1 : 0, bw = tw >> sh, bh = th >> sh, rpl = pl ? rpl_c : rpl_l;
-        const int col = lane & (bw - 1), r0 = (lane / bw) * rpl;
+        const int col = lane & (bw - 1), r0 = (lane >> (31 - __clz(bw))) * rpl;
         if (r0 >= bh) continue;
         const int lx = ((cu.x + tx - ctu_x) >> sh) + col, ly = ((cu.y + ty - ctu_y) >> sh) + r0;
-        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * (pl ? rs_c : rs_l) + lx;
-        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + lx;
+        const int rs = pl ? rs_c : rs_l;
+        const int16_t *res = (pl == 0 ? res_y : (pl == 1 ? res_u : res_v)) + ly * rs + lx;
+        pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + ly) * s + (ctu_x >> sh) + lx;
 #pragma unroll
         for (int i = 0; i < 8; i++)
-            if (i < rpl) dst[(size_t)i * (pl ? a.s_c : a.s_l)] = (pel)xb_clip3(0, maxv, (int16_t)(acc[pl][i] + res[i * (pl ? rs_c : rs_l)]));
+            if (i < rpl) dst[(size_t)i * s] = (pel)xb_clip3(0, maxv, (int16_t)(acc[i] + res[i * rs]));
     }
 }
 
@@ -759,7 +756,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
                     {
                         const int cw = tw >> 1, ch = th >> 1;
                         const int rpl = max(1, (cw * ch) >> 5);
-#pragma unroll
+#pragma unroll 1
                         for (int pl = 1; pl <= 2; pl++) {
                             pred_tile<4>(a, cu, pl, (px - cx) >> 1, (py - cy) >> 1, cw, ch, rpl, scr, lane, pr);
                             const int col = lane & (cw - 1), r0 = (lane >> (31 - __clz(cw))) * rpl;
