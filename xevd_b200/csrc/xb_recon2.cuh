@@ -79,10 +79,13 @@ struct R2Layout {
     {
         R2Layout L;
         int o = 128;                                                       // [0,128): mbarrier + counters
-        L.win_l = o; o += nl * kTileCap * kWinLBytes;
-        L.win_c = o; o += nl * kTileCap * 2 * kWinCBytes;
+        // windows and vertical-pair buffers hold ONE prediction list at a time: the lists of a bi-predicted picture go through them one
+        // after the other (the running prediction lives in registers), so B pictures keep two CTAs per SM like P pictures
+        (void)nl;
+        L.win_l = o; o += kTileCap * kWinLBytes;
+        L.win_c = o; o += kTileCap * 2 * kWinCBytes;
         const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
-        const int m2_bytes = 4 * nl * kTileCap * (kM2LWords + 2 * kM2CWords);
+        const int m2_bytes = 4 * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
         L.res_y = o; L.coef = o; o += 2 * (64 * kResLStride + 2 * 32 * kResCStride);
         L.cus = o; o += 32 * max_cu;
@@ -408,27 +411,24 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 
     // ---- MC rounds (normally one: a CTU of >=16x16 CUs has at most 16 tiles) -----------------------------------------------
     const int n_rounds = (n_tiles + kTileCap - 1) / kTileCap;
-    auto issue_round = [&](int round) {
-        // warp 0: lane = slot + 16 * list
+    auto issue = [&](int round, int l) {
+        // warp 0, lane = slot: the windows of list l of this round's tiles
         if (warp == 0) {
             const int t0 = round * kTileCap, nt = min(kTileCap, n_tiles - t0);
-            if (lane == 0) {
-                int n = 0;
-                for (int i = 0; i < nt; i++) n += min((int)s_tile[t0 + i].nl, NL);
-                mbar_expect_tx(mbar, (uint32_t)n * 2 * (kBoxLW * kBoxLH + 2 * kBoxCW * kBoxCH));
-            }
+            const bool mine = lane < nt && l < s_tile[t0 + lane].nl;
+            const int n = __popc(__ballot_sync(0xffffffffu, mine));
+            if (lane == 0) mbar_expect_tx(mbar, (uint32_t)n * 2 * (kBoxLW * kBoxLH + 2 * kBoxCW * kBoxCH));      // n == 0 completes the phase at once
             __syncwarp();
-            const int slot = lane & 15, l = lane >> 4;
-            if (slot < nt && l < NL && l < s_tile[t0 + slot].nl) {
-                const TilePred p = s_pred[(t0 + slot) * NL + l];
+            if (mine) {
+                const TilePred p = s_pred[(t0 + lane) * NL + l];
                 const CUtensorMap *tm = a.ref_tmap[p.ref];
-                tma_load_2d(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes, tm + 0, p.wx & ~7, p.wy, mbar);
-                tma_load_2d(smem + L.win_c + ((l * kTileCap + slot) * 2 + 0) * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, mbar);
-                tma_load_2d(smem + L.win_c + ((l * kTileCap + slot) * 2 + 1) * kWinCBytes, tm + 2, p.cwx & ~7, p.cwy, mbar);
+                tma_load_2d(smem + L.win_l + lane * kWinLBytes, tm + 0, p.wx & ~7, p.wy, mbar);
+                tma_load_2d(smem + L.win_c + (lane * 2 + 0) * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, mbar);
+                tma_load_2d(smem + L.win_c + (lane * 2 + 1) * kWinCBytes, tm + 2, p.cwx & ~7, p.cwy, mbar);
             }
         }
     };
-    issue_round(0);
+    issue(0, 0);
 
     // Block lookup for a warp's 32 consecutive lines li0 .. li0+31 (all lanes participate): blocks are sorted by first
     // line, so block(li0 + lane) = #{starts <= li0} - 1 + #{starts in (li0, li0 + lane]}.  One coalesced load of the
@@ -516,22 +516,24 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         }
     }
 
-    int *s_m2l = s_tmp;                                        // [NL][16][kM2LWords]
-    int *s_m2c = s_tmp + NL * kTileCap * kM2LWords;            // [NL][16][2][kM2CWords]
+    int *s_m2l = s_tmp;                                        // [16][kM2LWords]
+    int *s_m2c = s_tmp + kTileCap * kM2LWords;                 // [16][2][kM2CWords]
     const int maxv2 = ((1 << a.bd_l) - 1) * 0x00010001;        // the reference clips all planes with the luma depth
     const int maxc2 = ((1 << a.bd_c) - 1) * 0x00010001;
     const int s1l = min(4, a.bd_l - 8), s2l = max(8, 20 - a.bd_l);
     const int s1c = min(4, a.bd_c - 8), s2c = max(8, 20 - a.bd_c);
 
+    int phase = 0;
     for (int round = 0; round < n_rounds; round++) {
         const int t0 = round * kTileCap, nt = min(kTileCap, n_tiles - t0);
-        if (round > 0) issue_round(round);
-        mbar_wait(mbar, round & 1);
-
-        // ---- horizontal stage (warp-local: warp w owns tile slots 2w, 2w+1 through both stages), output = vertical pairs ------
-        // luma: 24 tasks per slot (2 column halves x 12 row-pairs), chroma: 12 per slot (2 planes x 6 row-pairs)
+        // the running prediction of this thread's samples: luma 2 columns x 8 rows, chroma 2 columns x 4 rows (packed pairs)
+        int outp[8], outc[4];
 #pragma unroll 1
         for (int l = 0; l < NL; l++) {
+            mbar_wait(mbar, phase & 1);
+            phase++;
+            // ---- horizontal stage (warp-local: warp w owns tile slots 2w, 2w+1 through both stages), output = vertical pairs ------
+            // luma: 24 tasks per slot (2 column halves x 12 row-pairs), chroma: 12 per slot (2 planes x 6 row-pairs)
 #pragma unroll 1
             for (int it = 0; it < 2; it++) {
                 const int task = it * 32 + lane;
@@ -543,7 +545,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 if (l >= td.nl || half * 8 >= td.tw || 2 * rp >= td.th + 7) continue;
                 const TilePred p = s_pred[(t0 + slot) * NL + l];
                 const int offx = p.offs & 7, par = offx & 1;
-                const int *win = (const int *)(smem + L.win_l + (l * kTileCap + slot) * kWinLBytes) + (offx >> 1) + half * 4;
+                const int *win = (const int *)(smem + L.win_l + slot * kWinLBytes) + (offx >> 1) + half * 4;
                 const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
                 const int sh = p.two_d ? s1l : 6;
                 int hv[2][8];
@@ -559,7 +561,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                         hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
                     }
                 }
-                int4 *dst = (int4 *)(s_m2l + (l * kTileCap + slot) * kM2LWords + half * 8 + rp * kM2LStrideW);
+                int4 *dst = (int4 *)(s_m2l + slot * kM2LWords + half * 8 + rp * kM2LStrideW);
                 dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
                 dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
             }
@@ -571,7 +573,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     if (l < td.nl && 2 * rp < (td.th >> 1) + 3) {
                         const TilePred p = s_pred[(t0 + slot) * NL + l];
                         const int offx = p.offs >> 4, par = offx & 1;
-                        const int *win = (const int *)(smem + L.win_c + ((l * kTileCap + slot) * 2 + pl) * kWinCBytes) + (offx >> 1);
+                        const int *win = (const int *)(smem + L.win_c + (slot * 2 + pl) * kWinCBytes) + (offx >> 1);
                         const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
                         const int sh = p.ctwo_d ? s1c : 6;
                         int hv[2][8];
@@ -587,31 +589,30 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                                 hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
                             }
                         }
-                        int4 *dst = (int4 *)(s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + rp * kM2CStrideW);
+                        int4 *dst = (int4 *)(s_m2c + (slot * 2 + pl) * kM2CWords + rp * kM2CStrideW);
                         dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
                         dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
                     }
                 }
             }
-        }
-        __syncwarp();
+            // every warp is done with the windows: the next batch (other list of this round, or the next round) loads while the vertical
+            // stage of this one runs
+            const bool more = l + 1 < NL || round + 1 < n_rounds;
+            if (more) { __syncthreads(); if (l + 1 < NL) issue(round, l + 1); else issue(round + 1, 0); }
+            else __syncwarp();
 
-        // ---- vertical stage + reconstruction -------------------------------------------------------------------------------------------
-        // luma: one thread = 2 columns x 8 rows, 16 threads per slot (8 column pairs x 2 row groups)
-        {
-            const int slot = tid >> 4, k = tid & 15;
-            const int cp = k & 7, rg = k >> 3;
-            if (slot < nt) {
-                const TileDesc td = s_tile[t0 + slot];
-                if (2 * cp < td.tw && 8 * rg < td.th) {
-                    int outp[8];                                   // packed (col, col+1) per row
-#pragma unroll
-                    for (int l = 0; l < NL; l++) {
-                        if (l >= td.nl) continue;
+            // ---- vertical stage: this list's prediction into the running registers (xevd_average_16b_no_clip for the second list) -----
+            // luma: one thread = 2 columns x 8 rows, 16 threads per slot (8 column pairs x 2 row groups)
+            {
+                const int slot = tid >> 4, k = tid & 15;
+                const int cp = k & 7, rg = k >> 3;
+                if (slot < nt) {
+                    const TileDesc td = s_tile[t0 + slot];
+                    if (2 * cp < td.tw && 8 * rg < td.th && l < td.nl) {
                         const TilePred p = s_pred[(t0 + slot) * NL + l];
                         const Taps5 te = ld_taps5(p.phy, 0), to = ld_taps5(p.phy, 1);
                         const int sh = p.two_d ? s2l : 6, rnd = p.two_d ? (1 << (s2l - 1)) : 0;
-                        const int *m2 = s_m2l + (l * kTileCap + slot) * kM2LWords + (4 * rg) * kM2LStrideW + 2 * cp;
+                        const int *m2 = s_m2l + slot * kM2LWords + (4 * rg) * kM2LStrideW + 2 * cp;
                         int P[8][2];
 #pragma unroll
                         for (int j = 0; j < 8; j++) { const int2 v = *(const int2 *)(m2 + j * kM2LStrideW); P[j][0] = v.x; P[j][1] = v.y; }
@@ -624,41 +625,26 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                             int pe = __vimin_s16x2_relu(pack16(e0, e1), maxv2);
                             int po = __vimin_s16x2_relu(pack16(o0, o1), maxv2);
                             if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
-                            else {      // xevd_average_16b_no_clip on two clipped, non-negative predictions
+                            else {      // two clipped, non-negative predictions
                                 outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
                                 outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                             }
                         }
                     }
-                    const int x = td.px + 2 * cp, y = td.py + 8 * rg;
-                    const int *res = (const int *)(s_res + y * kResLStride + x);
-                    pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
-#pragma unroll
-                    for (int r = 0; r < 8; r++)
-                        if (8 * rg + r < td.th) {
-                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
-                            if (PEER) *(int *)(s_out + (y + r) * 64 + x) = v;
-                            else *(int *)(dst + (size_t)r * a.s_l) = v;
-                        }
                 }
             }
-        }
-        // chroma: one thread = 2 columns x 4 rows, 16 threads per slot (2 planes x 4 column pairs x 2 row groups)
-        {
-            const int slot = tid >> 4, kk = tid & 15;
-            const int pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
-            if (slot < nt) {
-                const TileDesc td = s_tile[t0 + slot];
-                const int cw = td.tw >> 1, ch = td.th >> 1;
-                if (2 * cp < cw && 4 * rg < ch) {
-                    int outp[4];
-#pragma unroll
-                    for (int l = 0; l < NL; l++) {
-                        if (l >= td.nl) continue;
+            // chroma: one thread = 2 columns x 4 rows, 16 threads per slot (2 planes x 4 column pairs x 2 row groups)
+            {
+                const int slot = tid >> 4, kk = tid & 15;
+                const int pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
+                if (slot < nt) {
+                    const TileDesc td = s_tile[t0 + slot];
+                    const int cw = td.tw >> 1, ch = td.th >> 1;
+                    if (2 * cp < cw && 4 * rg < ch && l < td.nl) {
                         const TilePred p = s_pred[(t0 + slot) * NL + l];
                         const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
                         const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
-                        const int *m2 = s_m2c + ((l * kTileCap + slot) * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
+                        const int *m2 = s_m2c + (slot * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
                         int P[4][2];
 #pragma unroll
                         for (int j = 0; j < 4; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
@@ -670,27 +656,52 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                             int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
                             int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
                             int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
-                            if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                            if (l == 0) { outc[2 * q] = pe; outc[2 * q + 1] = po; }
                             else {
-                                outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
-                                outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                                outc[2 * q] = ((outc[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                                outc[2 * q + 1] = ((outc[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                             }
                         }
                     }
-                    const int x = (td.px >> 1) + 2 * cp, y = (td.py >> 1) + 4 * rg;
+                }
+            }
+            __syncwarp();           // the pair buffers of this warp's tiles are rewritten by the next list / round
+        }
+
+        // ---- reconstruction: prediction + residual, clip, store -----------------------------------------------------------------------
+        {
+            const int slot = tid >> 4, k = tid & 15;
+            const int cp = k & 7, rg = k >> 3;
+            if (slot < nt) {
+                const TileDesc td = s_tile[t0 + slot];
+                if (2 * cp < td.tw && 8 * rg < td.th) {
+                    const int x = td.px + 2 * cp, y = td.py + 8 * rg;
+                    const int *res = (const int *)(s_res + y * kResLStride + x);
+                    pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
+#pragma unroll
+                    for (int r = 0; r < 8; r++)
+                        if (8 * rg + r < td.th) {
+                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+                            if (PEER) *(int *)(s_out + (y + r) * 64 + x) = v;
+                            else *(int *)(dst + (size_t)r * a.s_l) = v;
+                        }
+                }
+                const int pl = k >> 3, ccp = k & 3, crg = (k >> 2) & 1;
+                const int cw = td.tw >> 1, ch = td.th >> 1;
+                if (2 * ccp < cw && 4 * crg < ch) {
+                    const int x = (td.px >> 1) + 2 * ccp, y = (td.py >> 1) + 4 * crg;
                     const int *res = (const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + y * kResCStride + x);
                     pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
 #pragma unroll
                     for (int r = 0; r < 4; r++)
-                        if (4 * rg + r < ch) {
-                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResCStride / 2)], maxv2);
+                        if (4 * crg + r < ch) {
+                            const int v = (int)__viaddmin_s16x2_relu(outc[r], res[r * (kResCStride / 2)], maxv2);
                             if (PEER) *(int *)(s_out + 64 * 64 + pl * 32 * 32 + (y + r) * 32 + x) = v;
                             else *(int *)(dst + (size_t)r * a.s_c) = v;
                         }
                 }
             }
         }
-        if (round + 1 < n_rounds) __syncthreads();      // the next round's TMA overwrites every warp's windows
     }
 
     if (PEER) {
