@@ -106,6 +106,13 @@ def main():
         wk_i = upload_work(cl_i)
         timed("recon_intra wavefront (I picture, " + ("EIPD + HTDF" if eipd else "Baseline modes") + ")",
               lambda i: recon(prm_i, curs[i], drefs[:1], [], wk_i, True), alg_recon(cl_i))
+    # P pictures with a share of intra CUs: throughput inter kernel + wavefront kernel over the CTUs that hold intra CUs
+    for frac in (0.02, 0.1):
+        prm_x, cl_x = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=21, n_refs=2, coded_frac=0.7)
+        synth.add_intra_cus(cl_x, np.random.default_rng(6), frac)
+        synth.derive_avail_cu(cl_x)
+        wk_x = upload_work(cl_x)
+        timed(f"recon P picture, {int(frac * 100)} % intra CUs (inter v2 + wavefront)", lambda i: recon(prm_x, curs[i], drefs, drefs[::-1], wk_x, True), alg_recon(cl_x))
     # picture-wide passes on reconstructed pictures (maps left by the Main inter reconstruction above)
     for i in range(args.npic):
         recon(prm_m, curs[i], dm, dm[::-1], wk_m, False)

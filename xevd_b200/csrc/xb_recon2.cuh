@@ -43,6 +43,8 @@ constexpr int kTmpCStride = 36;
 constexpr int kResLStride = 72;              // residual row stride, int16 (64 + 8)
 constexpr int kResCStride = 40;
 
+constexpr int kCoefStageBytes = 2 * 2 * 64 * 64;
+
 struct TuDesc {                              // one transform block (16 bytes)
     uint32_t coef_off;                       // first coefficient, int16 units
     uint16_t tmp_off;                        // word offset of (0,0) inside the plane's pass-1 buffer
@@ -87,7 +89,10 @@ struct R2Layout {
         const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
         const int m2_bytes = 4 * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
-        L.res_y = o; L.coef = o; o += 2 * (64 * kResLStride + 2 * 32 * kResCStride);
+        // residual planes; before the row pass the same bytes stage the CTU's slice of the coefficient stream, fetched by one bulk copy
+        // while the descriptors are built (at most 2 int16 per luma sample: 4x4 CUs with their chroma blocks padded to 8)
+        const int res_bytes = 2 * (64 * kResLStride + 2 * 32 * kResCStride);
+        L.res_y = o; L.coef = o; o += res_bytes > kCoefStageBytes ? res_bytes : kCoefStageBytes;
         L.cus = o; o += 32 * max_cu;
         L.tus = o; o += 16 * 3 * max_cu;
         L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
@@ -122,6 +127,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n\t.reg .pred p;\n\t"
         "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra W;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar)
 {
@@ -182,16 +192,16 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int *_
     if (N >= 8) {
 #pragma unroll
         for (int q = 0; q < N / 8; q++) {
-            const int4 w = __ldg((const int4 *)src + q);
+            const int4 w = ((const int4 *)src)[q];
             const int ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) { v[8 * q + 2 * j] = (int)(int16_t)(ww[j] & 0xffff); v[8 * q + 2 * j + 1] = ww[j] >> 16; }
         }
     } else if (N == 4) {
-        const int2 w = __ldg((const int2 *)src);
+        const int2 w = *(const int2 *)src;
         v[0] = (int)(int16_t)(w.x & 0xffff); v[1] = w.x >> 16; v[2] = (int)(int16_t)(w.y & 0xffff); v[3] = w.y >> 16;
     } else {
-        const int w = __ldg((const int *)src);
+        const int w = *(const int *)src;
         v[0] = (int)(int16_t)(w & 0xffff); v[1] = w >> 16;
     }
     // xevd_dquant: clip16((c * scale + offset) >> shift); the clip happens in the saturating pack (I2IP.S16.S32.SAT)
@@ -236,7 +246,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     constexpr int NL = BI ? 2 : 1;
     const R2Layout L = R2Layout::make(NL, max_cu, PEER);
     int16_t *s_out = (int16_t *)(smem + L.out);                 // [64][64] luma, then [2][32][32] chroma
-    uint64_t *mbar = (uint64_t *)smem;
+    uint64_t *mbar = (uint64_t *)smem, *mbar_coef = (uint64_t *)(smem + 8);
     int *cnt = (int *)(smem + 16);           // totals: [0] luma blocks [1] chroma blocks [2,3] pass-1 lines y,c [4,5] pass-2 y,c [6] tiles
     XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
     TuDesc *s_tu = (TuDesc *)(smem + L.tus);
@@ -252,15 +262,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int ctu_x = blockIdx.x << 6, ctu_y = (blockIdx.y + a.ctu_row0) << 6;
     const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
 
-    // ---- stage CU descriptors, zero the residual, init barrier, build tap tables --------------------------------------------
+    // ---- stage CU descriptors, init barriers, build tap tables ----------------------------------------------------------------
     {
         const int4 *g = (const int4 *)(a.cus + cu0);
         int4 *s = (int4 *)s_cu;
         for (int i = tid; i < ncu * 2; i += kR2Threads) s[i] = __ldg(g + i);
-        int4 *z = (int4 *)s_res;            // uncoded blocks must read as zero residual
-        const int nz = 2 * (64 * kResLStride + 2 * 32 * kResCStride) / 16;
-        for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
-        if (tid == 0) mbar_init(mbar, 1);
+        if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar_coef, 1); }
         int *t8 = (int *)(smem + L.taps), *t4 = t8 + 16 * 9;
         if (tid < 16 * 9) t8[tid] = c_taps5[a.main_tables][tid];
         if (tid < 32 * 6) t4[tid] = c_taps3[a.main_tables][tid];
@@ -270,10 +277,10 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
     __syncthreads();
 
-    // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the
-    //      stream.  Pull it towards L1 now (fire-and-forget prefetches); the row pass reads it two barriers later.
-    //      (A cp.async.bulk of the slice into shared memory was measured 35 % slower end to end: profiles/r1.)
-    int coef_base = 0;
+    // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the stream.  One bulk
+    //      copy brings it on chip while the descriptors are built; the row pass, two barriers later, reads shared memory instead of
+    //      waiting on DRAM (its barrier used to collect 13 % of all stall samples: the slowest warp's miss held the other seven).
+    int coef_base = 0, coef_bytes = 0;
     if (ncu > 0) {
         const XB200_CU c0 = s_cu[0], c1 = s_cu[ncu - 1];
         coef_base = c0.coef_off;
@@ -282,8 +289,11 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (c1.cbf & 0x00f) end += (n1 + 7) & ~7;
         if (c1.cbf & 0x0f0) end += ((n1 >> 2) + 7) & ~7;
         if (c1.cbf & 0xf00) end += ((n1 >> 2) + 7) & ~7;
-        for (int o = coef_base + tid * 64; o < end; o += kR2Threads * 64)      // one 128-byte line per thread
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.coef + o));
+        coef_bytes = 2 * (end - coef_base);
+        if (tid == 0 && coef_bytes > 0) {
+            mbar_expect_tx(mbar_coef, (uint32_t)coef_bytes);
+            bulk_load(smem + L.coef, a.coef + coef_base, (uint32_t)coef_bytes, mbar_coef);
+        }
     }
 
     // ---- per-CU counts -> exclusive prefix sums: warp q scans quantity q -------------------------------------------------------
@@ -449,6 +459,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 
     // ---- residual pass 1 (rows, IDP.2A): luma lines first, then chroma lines (each padded to whole warps) -----------------------
     const int n_l1y_w = (n_l1y + 31) & ~31, n_l1c_w = (n_l1c + 31) & ~31;
+    const int16_t *s_coef = (const int16_t *)(smem + L.coef);
+    if (coef_bytes > 0) mbar_wait(mbar_coef, 0);
     for (int i0 = warp * 32; i0 < n_l1y_w + n_l1c_w; i0 += kR2Threads) {
         const bool chroma = i0 >= n_l1y_w;
         const int li0 = chroma ? i0 - n_l1y_w : i0, li = li0 + lane;
@@ -457,7 +469,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         const TuDesc d = s_tu[b];
         const int r = li - (int)(chroma ? s_pre1[b + 1] : s_pre1[b]);
         const int lw = d.lw_lh & 15, pl = d.plane_wide & 3;
-        const int16_t *src = a.coef + coef_base + d.coef_off + (r << d.cstride_log2);
+        const int16_t *src = s_coef + d.coef_off + (r << d.cstride_log2);
         int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off +
                    r * (pl ? kTmpCStride : kTmpLStride);
         const int off = d.shift ? (1 << (d.shift - 1)) : 0;
@@ -472,6 +484,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         }
     }
     __syncthreads();
+    if (n_tu < 3 * ncu) {         // the coefficient slice is consumed: uncoded blocks must read as zero residual
+        int4 *z = (int4 *)s_res;
+        const int nz = 2 * (64 * kResLStride + 2 * 32 * kResCStride) / 16;
+        for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
+        __syncthreads();
+    }
     // ---- residual pass 2 (columns, IMAD) --------------------------------------------------------------------------------------
     {
         const int sh2 = 19 - (a.bd_l - 8);
