@@ -300,6 +300,32 @@ def test_intra_1080p_wavefront(ctx, oracle):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("frac,eipd,kw", [(0.05, 0, {}), (0.2, 0, {}), (0.5, 0, {}), (0.2, 1, {}), (0.2, 1, dict(log2_ctu=7)), (0.3, 0, dict(log2_ctu=5))])
+def test_mixed_picture_sparse_wavefront(ctx, oracle, frac, eipd, kw):
+    """P/B pictures with scattered intra CUs: without HTDF and IBC a CTU waits only for the neighbour CTUs whose intra CUs lie under the
+    reference samples of its own border CUs.  A missed dependency is a race, so the picture is decoded several times."""
+    w, h, bd = 1280, 712, 10
+    rng = np.random.default_rng(17)
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="C", seed=61, n_refs=2, coded_frac=0.6, **kw)
+    prm.tool_eipd = eipd
+    synth.add_intra_cus(cl, rng, frac, eipd=bool(eipd))
+    synth.derive_avail_cu(cl)
+    refs = synth.make_refs(w, h, bd, 2, seed=62)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    try:
+        for rep in range(4):
+            ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+            got = cur.download()
+            for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+                assert np.array_equal(a, b), f"repetition {rep}, plane {n}: {int((a != b).sum())} samples differ"
+    finally:
+        for p in drefs + [cur]:
+            p.free()
+
+
 def test_golden_frames_gpu(ctx):
     """the CUDA path against the committed golden vectors of the unmodified reference (tests/golden/frames.npz):
     recon, then deblocking + padding of the same picture"""

@@ -429,6 +429,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.eipd = prm->tool_eipd ? 1 : 0;
     a.ats = prm->tool_ats ? 1 : 0;
     a.htdf = prm->tool_htdf ? 1 : 0;
+    a.ibc = prm->tool_ibc ? 1 : 0;
     a.dmvr = prm->tool_dmvr ? 1 : 0;
     a.poc = prm->poc;
     a.affine = prm->tool_affine ? 1 : 0;

@@ -34,7 +34,7 @@ struct XbFrameArgs {
     int n_peer;                 // band mode over NVLink: every output store is repeated into the same picture on n_peer other GPUs
     long long peer_delta[7];    //   byte distance from this GPU's picture allocation to the peer's mapping of its twin (same layout)
     int ctu_row0;               // band mode: first CTU row of this launch (the CU arrays / ctu_first index CTUs relative to it)
-    int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine;
+    int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine, ibc;
     const XB200_CU *cus;
     const uint32_t *ctu_first;
     const int16_t *coef;

@@ -377,6 +377,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     XB200_CU *s_cu = (XB200_CU *)(s_tmp + IntraSmem::kTmpElems);
     XB200_CU_EXT *s_ext = (XB200_CU_EXT *)(s_cu + IntraSmem::kCuStage);
     __shared__ int s_ctu, s_scr12[12];
+    __shared__ unsigned s_req[4], s_has[4];
     const int tid = threadIdx.x;
 
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
@@ -421,8 +422,50 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             }
         }
         //      intra / IBC areas hold the RESIDUAL there (parked by the inter kernel), which is why the preload fills both arrays
-        // ---- wait for the left, upper-left, upper and upper-right CTU ---------------------------------------------------------------
-        if (tid < 4) {
+        // ---- which of the left, upper-left, upper and upper-right CTU this one really depends on -----------------------------------
+        // Without HTDF and IBC the wavefront kernel changes nothing but the samples of intra CUs, and an intra CU reads the row above
+        // it (up[-1 .. w+h)) and the column left of it (left[-1 .. h+w)) only.  Inter CUs are final when this kernel starts, so a
+        // neighbour CTU matters only where one of ITS intra CUs lies under those samples: per 4-sample unit, the columns of the
+        // neighbour's bottom row / rows of its right column covered by intra CUs against the units this CTU's border CUs read.
+        // In P/B pictures with scattered intra CUs most CTUs then start at once instead of queueing on a 128-step wavefront.
+        const bool prune = !a.htdf && !a.ibc;
+        if (tid < 4) { s_req[tid] = 0; s_has[tid] = 0; }
+        __syncthreads();
+        if (prune) {
+            const int n = S >> 2;
+            auto bits = [](int lo, int hi) -> unsigned { return hi <= lo ? 0u : ((hi - lo >= 32 ? 0u : (1u << (hi - lo))) - 1u) << lo; };   // [lo, hi)
+            for (int i = cu0 + tid; i < cu1; i += kIntraThreads) {
+                const XB200_CU cu = get_cu(i);
+                if (cu.mode != XB200_MODE_INTRA) continue;
+                const int X = (cu.x - ctu_x) >> 2, Y = (cu.y - ctu_y) >> 2, W = 1 << (cu.log2w - 2), H = 1 << (cu.log2h - 2);
+                if (Y == 0) {                       // columns X-1 .. X+W+H of the row above
+                    if (X == 0) atomicOr(&s_req[1], 1u);
+                    atomicOr(&s_req[2], bits(max(X - 1, 0), min(X + W + H + 1, n)));
+                    if (X + W + H + 1 > n) atomicOr(&s_req[3], bits(0, min(X + W + H + 1 - n, n)));
+                }
+                if (X == 0) {                       // rows Y-1 .. Y+H+W of the column to the left (below the CTU: never available)
+                    if (Y == 0) atomicOr(&s_req[1], 1u);
+                    atomicOr(&s_req[0], bits(max(Y - 1, 0), min(Y + H + W + 1, n)));
+                }
+            }
+            for (int k = 0; k < 4; k++) {
+                const int nx = cx + (k == 0 ? -1 : k - 2), ny = cy - (k == 0 ? 0 : 1);
+                if (nx < 0 || nx >= a.w_ctu || ny < 0) continue;
+                const int nc = ny * a.w_ctu + nx, ox = nx << a.log2_ctu, oy = ny << a.log2_ctu;
+                for (int i = a.ctu_first[nc] + tid; i < a.ctu_first[nc + 1]; i += kIntraThreads) {
+                    const XB200_CU cu = a.cus[i];
+                    if (cu.mode != XB200_MODE_INTRA) continue;
+                    const int X = (cu.x - ox) >> 2, Y = (cu.y - oy) >> 2, W = 1 << (cu.log2w - 2), H = 1 << (cu.log2h - 2);
+                    const bool at_right = X + W == n, at_bottom = Y + H == n;
+                    if (k == 0) { if (at_right) atomicOr(&s_has[0], bits(Y, Y + H)); }
+                    else if (k == 1) { if (at_right && at_bottom) atomicOr(&s_has[1], 1u); }
+                    else if (at_bottom) atomicOr(&s_has[k], bits(X, X + W));
+                }
+            }
+            __syncthreads();
+        }
+        // ---- wait for them ----------------------------------------------------------------------------------------------------------
+        if (tid < 4 && (!prune || (s_req[tid] & s_has[tid]))) {
             const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
             if (nx >= 0 && nx < a.w_ctu && ny >= 0) {
                 volatile int *f = sy.done + ny * a.w_ctu + nx;
