@@ -89,21 +89,19 @@ __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int 
 
 // xevd_get_nbr_b for one plane: up[-1 .. w+h), left[-1 .. h+w); unit = samples per SCU (4 luma, 2 chroma)
 // (cx, cy): position of the CU inside the CTU plane
-__device__ void intra_gather(const PlaneCtx &pc, int cx, int cy, int w, int h, int unit, unsigned long long up_mask, unsigned long long left_mask,
-                             bool up_left, int dflt, int16_t *up, int16_t *left, int tid, int nthreads)
+// element i of the 2 * (w + h) + 1 neighbour samples of one plane (the three planes of a CU are gathered by one joint loop, so that a
+// small CU keeps three warps busy for one pass instead of one warp for three)
+__device__ __forceinline__ void intra_gather_elem(const PlaneCtx &pc, int cx, int cy, int n, int ush, unsigned long long up_mask, unsigned long long left_mask,
+                                                  bool up_left, int dflt, int16_t *up, int16_t *left, int i)
 {
-    const int n = w + h;
-    const int ush = unit == 4 ? 2 : 1;
-    for (int i = tid; i < 2 * n + 1; i += nthreads) {
-        if (i == 2 * n) {
-            const int v = up_left ? pc.get(cx - 1, cy - 1) : dflt;
-            up[-1] = (int16_t)v; left[-1] = (int16_t)v;
-        } else if (i < n) {
-            up[i] = (int16_t)(((up_mask >> (i >> ush)) & 1) ? pc.get(cx + i, cy - 1) : dflt);
-        } else {
-            const int k = i - n;
-            left[k] = (int16_t)(((left_mask >> (k >> ush)) & 1) ? pc.get(cx - 1, cy + k) : dflt);
-        }
+    if (i == 2 * n) {
+        const int v = up_left ? pc.get(cx - 1, cy - 1) : dflt;
+        up[-1] = (int16_t)v; left[-1] = (int16_t)v;
+    } else if (i < n) {
+        up[i] = (int16_t)(((up_mask >> (i >> ush)) & 1) ? pc.get(cx + i, cy - 1) : dflt);
+    } else {
+        const int k = i - n;
+        left[k] = (int16_t)(((left_mask >> (k >> ush)) & 1) ? pc.get(cx - 1, cy + k) : dflt);
     }
 }
 
@@ -161,17 +159,15 @@ struct NbSrc {
     }
 };
 
-__device__ void intra_gather_main(const NbSrc &nb, int h, int16_t *up, int16_t *left, int16_t *right, int tid, int nthreads)
+// element i of the 3 * (w + h) + 3 neighbour samples of one plane
+__device__ __forceinline__ void intra_gather_main_elem(const NbSrc &nb, int n, int16_t *up, int16_t *left, int16_t *right, int i)
 {
-    const int n = nb.w + h;
-    for (int i = tid; i < 3 * n + 3; i += nthreads) {
-        if (i < n) up[i] = (int16_t)nb.up(i);
-        else if (i < 2 * n) left[i - n] = (int16_t)nb.side(i - n, nb.lm, -1, nb.corner());
-        else if (i < 3 * n) right[i - 2 * n] = (int16_t)nb.side(i - 2 * n, nb.rm, nb.w, nb.up(nb.w));
-        else if (i == 3 * n) up[-1] = (int16_t)nb.corner();
-        else if (i == 3 * n + 1) left[-1] = (int16_t)nb.corner();
-        else right[-1] = (int16_t)nb.up(nb.w);
-    }
+    if (i < n) up[i] = (int16_t)nb.up(i);
+    else if (i < 2 * n) left[i - n] = (int16_t)nb.side(i - n, nb.lm, -1, nb.corner());
+    else if (i < 3 * n) right[i - 2 * n] = (int16_t)nb.side(i - 2 * n, nb.rm, nb.w, nb.up(nb.w));
+    else if (i == 3 * n) up[-1] = (int16_t)nb.corner();
+    else if (i == 3 * n + 1) left[-1] = (int16_t)nb.corner();
+    else right[-1] = (int16_t)nb.up(nb.w);
 }
 
 __constant__ int c_inv_size_plus1[8] = {2048, 1365, 819, 455, 241, 124, 63, 32};          // xevd_ipred.c:108
@@ -532,12 +528,16 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 const int pmax_c = (1 << a.bd_c) - 1;
                 static const int8_t kChromaToLuma[5] = {-1, 2, 0, 24, 12};       // IPD_BI_C, DC_C, HOR_C, VER_C -> luma mode ids (xevdm_ipred.c:267-305)
                 const int ipm_c = cu.refi[1] == 0 ? cu.refi[0] : kChromaToLuma[cu.refi[1]];
-                for (int pl = 0; pl < 3; pl++) {
-                    NbSrc nb;
-                    nb.pc = &pc[pl]; nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
-                    nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
-                    nb.um = ex.u.intra.up; nb.lm = ex.u.intra.left; nb.rm = ex.u.intra.right; nb.ul = ul;
-                    intra_gather_main(nb, pl ? ch : h, up[pl], le[pl], ri[pl], tid, kIntraThreads);
+                {
+                    const int n0 = 3 * (w + h) + 3, n1 = 3 * (cw + ch) + 3;
+                    for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
+                        const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2);
+                        NbSrc nb;
+                        nb.pc = &pc[pl]; nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
+                        nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
+                        nb.um = ex.u.intra.up; nb.lm = ex.u.intra.left; nb.rm = ex.u.intra.right; nb.ul = ul;
+                        intra_gather_main_elem(nb, pl ? cw + ch : w + h, up[pl], le[pl], ri[pl], k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
+                    }
                 }
                 __syncthreads();
                 if ((tid >> 5) < 3) {
@@ -558,9 +558,14 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
                 continue;
             }
-            intra_gather(pc[0], lx, ly, w, h, 4, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[0], le[0], tid, kIntraThreads);
-            intra_gather(pc[1], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[1], le[1], tid, kIntraThreads);
-            intra_gather(pc[2], lx >> 1, ly >> 1, cw, ch, 2, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[2], le[2], tid, kIntraThreads);
+            {
+                const int n0 = 2 * (w + h) + 1, n1 = 2 * (cw + ch) + 1;
+                for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
+                    const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2), sh = pl ? 1 : 0;
+                    intra_gather_elem(pc[pl], lx >> sh, ly >> sh, (w + h) >> sh, 2 - sh, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[pl], le[pl],
+                                      k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
+                }
+            }
             __syncthreads();
             if ((tid >> 5) < 3) {
                 const int pl = tid >> 5;
