@@ -280,20 +280,24 @@ __device__ __forceinline__ int intra_px_main(int ipm, int lr, int x, int y, int 
 // the rounded average of its four windows.  All windows see unfiltered input (the reference overwrites a sample only after its last
 // window), so the filter is a per-sample gather.
 __constant__ uint8_t c_htdf_thr_log2[5] = {6, 7, 7, 8, 8};
-__constant__ uint8_t c_htdf_tbl[5][16] = {
+__constant__ __align__(16) uint8_t c_htdf_tbl[5][16] = {
     {0, 0, 2, 6, 10, 14, 19, 23, 28, 32, 36, 41, 45, 49, 53, 57},       {0, 0, 5, 12, 20, 29, 38, 47, 56, 65, 73, 82, 90, 98, 107, 115},
     {0, 0, 1, 4, 9, 16, 24, 32, 41, 50, 59, 68, 77, 86, 94, 103},       {0, 0, 3, 9, 19, 32, 47, 64, 81, 99, 117, 135, 154, 179, 205, 230},
     {0, 0, 0, 2, 6, 11, 18, 27, 38, 51, 64, 96, 128, 160, 192, 224}};
 
-__device__ __forceinline__ int htdf_shrink(int z, const uint8_t *tbl, int thr, int shift, int round)
+// the 16-entry table row of the CU's QP lives in four registers: a per-lane index into __constant__ memory would be replayed once per
+// distinct address, twelve times per sample
+struct HtdfTbl { unsigned t0, t1, t2, t3; };
+__device__ __forceinline__ int htdf_shrink(int z, const HtdfTbl &tbl, int thr, int shift, int round)
 {
     const int av = abs(z);
     if (av >= thr) return z;
-    const int v = tbl[((av + round) & thr) >> shift];
+    const int idx = ((av + round) & thr) >> shift;
+    const int v = (int)((idx < 8 ? __byte_perm(tbl.t0, tbl.t1, idx & 7) : __byte_perm(tbl.t2, tbl.t3, idx & 7)) & 0xff);
     return z < 0 ? -v : v;
 }
 // output `which` (0..3 = (0,0) (0,1) (1,0) (1,1)) of the window whose top-left sample is t[0]
-__device__ __forceinline__ int htdf_window(const int16_t *t, int s, int which, const uint8_t *tbl, int thr, int shift, int round)
+__device__ __forceinline__ int htdf_window(const int16_t *t, int s, int which, const HtdfTbl &tbl, int thr, int shift, int round)
 {
     const int x0 = t[0], x1 = t[1], x2 = t[s], x3 = t[s + 1];
     const int y0 = x0 + x2, y1 = x1 + x3, y2 = x0 - x2, y3 = x1 - x3;
@@ -338,7 +342,8 @@ __device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, const PlaneCtx
     int k = (qp - 20 + 4) >> 3;
     k = min(max(k, 0), 4);
     const int lg = c_htdf_thr_log2[k], shift = lg - 4, round = (1 << shift) >> 1, thr = (1 << lg) - (1 << shift);
-    const uint8_t *tbl = c_htdf_tbl[k];
+    const uint4 tw = *(const uint4 *)c_htdf_tbl[k];
+    const HtdfTbl tbl = {tw.x, tw.y, tw.z, tw.w};
     const int maxv = (1 << a.bd_l) - 1;
     for (int idx = tid; idx < w * h; idx += nthreads) {
         const int i = (idx >> cu.log2w) + 1, j = (idx & (w - 1)) + 1;
@@ -540,12 +545,14 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                     }
                 }
                 __syncthreads();
-                if ((tid >> 5) < 3) {
-                    const int pl = tid >> 5;
-                    intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl],
-                                       s_scr12 + 4 * pl, tid & 31);
+                if (cu.refi[0] <= 2 || ipm_c <= 2) {          // DC / plane / bilinear: per-plane scalars first (angular modes need none)
+                    if ((tid >> 5) < 3) {
+                        const int pl = tid >> 5;
+                        intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl],
+                                           s_scr12 + 4 * pl, tid & 31);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
                     const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                     const int lwp = cu.log2w - (pl ? 1 : 0), lhp = cu.log2h - (pl ? 1 : 0), wp = 1 << lwp, hp = 1 << lhp;
@@ -567,11 +574,13 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 }
             }
             __syncthreads();
-            if ((tid >> 5) < 3) {
-                const int pl = tid >> 5;
-                intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.refi[pl ? 1 : 0], up[pl], le[pl], s_scr12 + 4 * pl, tid & 31);
+            if (cu.refi[0] == 0 || cu.refi[1] == 0) {         // DC value of the planes that use it
+                if ((tid >> 5) < 3) {
+                    const int pl = tid >> 5;
+                    intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.refi[pl ? 1 : 0], up[pl], le[pl], s_scr12 + 4 * pl, tid & 31);
+                }
+                __syncthreads();
             }
-            __syncthreads();
             for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
                 const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                 const int lwp = cu.log2w - (pl ? 1 : 0), wp = 1 << lwp;
