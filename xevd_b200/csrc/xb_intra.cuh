@@ -135,7 +135,7 @@ __device__ __forceinline__ int intra_px(int mode, int x, int y, const int16_t *u
 // nearest available unit before it, else the scan's start value.  The corner up[-1] becomes up[0] when the up-left unit is
 // unavailable (the reference's loop over the units left of the corner overwrites it, :85-104).
 struct NbSrc {
-    const PlaneCtx *pc;
+    PlaneCtx pc;
     int cx, cy;                 // CU position inside the CTU plane
     int w, ush, dflt;
     unsigned long long um, lm, rm;
@@ -143,18 +143,18 @@ struct NbSrc {
     __device__ __forceinline__ int up(int i) const
     {
         const int k = i >> ush;
-        if ((um >> k) & 1) return pc->get(cx + i, cy - 1);
+        if ((um >> k) & 1) return pc.get(cx + i, cy - 1);
         const unsigned long long m = um & ((1ull << k) - 1);
-        if (m) return pc->get(cx + (((63 - __clzll((long long)m)) + 1) << ush) - 1, cy - 1);
-        return ul ? pc->get(cx - 1, cy - 1) : dflt;
+        if (m) return pc.get(cx + (((63 - __clzll((long long)m)) + 1) << ush) - 1, cy - 1);
+        return ul ? pc.get(cx - 1, cy - 1) : dflt;
     }
-    __device__ __forceinline__ int corner() const { return ul ? pc->get(cx - 1, cy - 1) : up(0); }
+    __device__ __forceinline__ int corner() const { return ul ? pc.get(cx - 1, cy - 1) : up(0); }
     __device__ __forceinline__ int side(int i, unsigned long long mask, int col, int start) const
     {
         const int k = i >> ush;
-        if ((mask >> k) & 1) return pc->get(cx + col, cy + i);
+        if ((mask >> k) & 1) return pc.get(cx + col, cy + i);
         const unsigned long long m = mask & ((1ull << k) - 1);
-        if (m) return pc->get(cx + col, cy + (((63 - __clzll((long long)m)) + 1) << ush) - 1);
+        if (m) return pc.get(cx + col, cy + (((63 - __clzll((long long)m)) + 1) << ush) - 1);
         return start;
     }
 };
@@ -170,6 +170,8 @@ __device__ __forceinline__ void intra_gather_main_elem(const NbSrc &nb, int n, i
     else right[-1] = (int16_t)nb.up(nb.w);
 }
 
+// plane / bilinear mode tables of xevdm_ipred.c (kept out of local memory: a run-time index into a function-local array puts it on the stack)
+__constant__ int c_ipred_pl_mult[6] = {13, 17, 5, 11, 23, 47}, c_ipred_pl_shift[6] = {7, 10, 11, 15, 19, 23}, c_ipred_bi_wc[6] = {-1, 341, 205, 114, 60, 31};
 __constant__ int c_inv_size_plus1[8] = {2048, 1365, 819, 455, 241, 124, 63, 32};          // xevd_ipred.c:108
 __constant__ short c_ipred_dxdy[33][2] = {                                                   // xevd_tbl_ipred_dxdy, xevd_tbl.c:294-304
     {0, 0}, {0, 0}, {0, 0}, {2816, 372}, {2048, 512}, {1408, 744}, {1024, 1024}, {744, 1408}, {512, 2048}, {372, 2816}, {256, 4096},
@@ -235,19 +237,17 @@ __device__ __forceinline__ void intra_scalars_main(int w, int h, int lw, int lh,
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { ch += __shfl_xor_sync(0xffffffffu, ch, d); cv += __shfl_xor_sync(0xffffffffu, cv, d); }
         if (lane == 0) {
-            const int mult[6] = {13, 17, 5, 11, 23, 47}, shft[6] = {7, 10, 11, 15, 19, 23};
             const int iw = lw < 2 ? 0 : lw - 2, ih = lh < 2 ? 0 : lh - 2;
             const int a = (sd[h - 1] + (fr ? up[0] : up[w - 1])) << 4;
-            const int b = ((ch << 5) * mult[iw] + (1 << (shft[iw] - 1))) >> shft[iw];
-            const int c = ((cv << 5) * mult[ih] + (1 << (shft[ih] - 1))) >> shft[ih];
+            const int b = ((ch << 5) * c_ipred_pl_mult[iw] + (1 << (c_ipred_pl_shift[iw] - 1))) >> c_ipred_pl_shift[iw];
+            const int c = ((cv << 5) * c_ipred_pl_mult[ih] + (1 << (c_ipred_pl_shift[ih] - 1))) >> c_ipred_pl_shift[ih];
             scr[0] = a - (h2 - 1) * c - (w2 - 1) * b + 16; scr[1] = b; scr[2] = c;
         }
     } else if (ipm == 2 && lane == 0 && lr != 3) {
-        const int tbl_wc[6] = {-1, 341, 205, 114, 60, 31};
         const bool fr = lr == 2;
         const int a = fr ? up[-1] : up[w], b = fr ? ri[h] : le[h];
         const int lmin = min(lw, lh);
-        const int c = w == h ? (a + b + 1) >> 1 : (((a << lw) + (b << lh)) * tbl_wc[lw > lh ? lw - lh : lh - lw] + (1 << (lmin + 9))) >> (lmin + 10);
+        const int c = w == h ? (a + b + 1) >> 1 : (((a << lw) + (b << lh)) * c_ipred_bi_wc[lw > lh ? lw - lh : lh - lw] + (1 << (lmin + 9))) >> (lmin + 10);
         scr[0] = a; scr[1] = b; scr[2] = (c << 1) - a - b;
     }
 }
@@ -321,10 +321,9 @@ __device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_C
     return true;
 }
 
-__device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, const PlaneCtx &pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads)
+__device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log2h, int av, const PlaneCtx pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads)
 {
-    const int w = 1 << cu.log2w, h = 1 << cu.log2h, we = w + 2, he = h + 2;
-    const int av = cu.avail_cu;
+    const int w = 1 << log2w, h = 1 << log2h, we = w + 2, he = h + 2;
     const bool up = av & 1, le = (av >> 1) & 1, ri = (av >> 3) & 1;
     for (int idx = tid; idx < we * he; idx += nthreads) {
         const int r = idx / we, c = idx - r * we, i = r - 1, j = c - 1;
@@ -346,7 +345,7 @@ __device__ void cu_htdf(const XbFrameArgs &a, const XB200_CU &cu, const PlaneCtx
     const HtdfTbl tbl = {tw.x, tw.y, tw.z, tw.w};
     const int maxv = (1 << a.bd_l) - 1;
     for (int idx = tid; idx < w * h; idx += nthreads) {
-        const int i = (idx >> cu.log2w) + 1, j = (idx & (w - 1)) + 1;
+        const int i = (idx >> log2w) + 1, j = (idx & (w - 1)) + 1;
         int acc = htdf_window(t + (i - 1) * we + (j - 1), we, 3, tbl, thr, shift, round);
         acc = (int16_t)(acc + htdf_window(t + (i - 1) * we + j, we, 2, tbl, thr, shift, round));
         acc = (int16_t)(acc + htdf_window(t + i * we + (j - 1), we, 1, tbl, thr, shift, round));
@@ -365,7 +364,7 @@ struct IntraSync {
 };
 
 template <bool IQT>
-__global__ void __launch_bounds__(kIntraThreads)
+__global__ void __launch_bounds__(kIntraThreads, 1)
 k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -405,21 +404,29 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         }
         __syncthreads();
         auto get_cu = [&](int i) -> XB200_CU { return i - cu0 < n_stage ? s_cu[i - cu0] : a.cus[i]; };
-        PlaneCtx pc[3];
-        for (int pl = 0; pl < 3; pl++) {
-            const int Sp = pl ? Sc : S, po = pl == 0 ? 0 : (pl == 1 ? S * S : S * S + Sc * Sc);
-            pc[pl].rec = s_rec + po; pc[pl].res = s_res + po; pc[pl].Sp = Sp;
-            pc[pl].top = s_top + pl * IntraSmem::kTopElems + 4;
-            pc[pl].left = s_left + pl * IntraSmem::kLeftElems;
-            pc[pl].gs = pl ? a.s_c : a.s_l;
-            pc[pl].g = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)(ctu_y >> (pl ? 1 : 0)) * pc[pl].gs + (ctu_x >> (pl ? 1 : 0));
-        }
+        // plane contexts and neighbour arrays are rebuilt from the plane index by arithmetic: arrays of them indexed by a run-time plane
+        // would live in local memory, and every sample of the serial CU chain would pay its latency
+        pel *const g_y = a.cur.y + (size_t)ctu_y * a.s_l + ctu_x;
+        pel *const g_u = a.cur.u + (size_t)(ctu_y >> 1) * a.s_c + (ctu_x >> 1), *const g_v = a.cur.v + (size_t)(ctu_y >> 1) * a.s_c + (ctu_x >> 1);
+        auto pc = [&](int pl) -> PlaneCtx {
+            PlaneCtx c;
+            const int po = pl == 0 ? 0 : (pl == 1 ? S * S : S * S + Sc * Sc);
+            c.rec = s_rec + po; c.res = s_res + po; c.Sp = pl ? Sc : S;
+            c.top = s_top + pl * IntraSmem::kTopElems + 4;
+            c.left = s_left + pl * IntraSmem::kLeftElems;
+            c.gs = pl ? a.s_c : a.s_l;
+            c.g = pl == 0 ? g_y : (pl == 1 ? g_u : g_v);
+            return c;
+        };
+        auto up = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4; };
+        auto le = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + (2 * 128 + 8); };
+        auto ri = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + 2 * (2 * 128 + 8); };
         // ---- before waiting: (1) the CTU's samples as the inter kernel left them (neighbours of intra CUs, HTDF input) -------------
         for (int pl = 0; pl < 3; pl++) {
-            const int Sp = pc[pl].Sp, wv = min(Sp, ((a.w - ctu_x) >> (pl ? 1 : 0))), hv = min(Sp, ((a.h - ctu_y) >> (pl ? 1 : 0)));
+            const int Sp = pc(pl).Sp, wv = min(Sp, ((a.w - ctu_x) >> (pl ? 1 : 0))), hv = min(Sp, ((a.h - ctu_y) >> (pl ? 1 : 0)));
             for (int i = tid; i < Sp * hv; i += kIntraThreads) {
                 const int y = i / Sp, x = i - y * Sp;
-                if (x < wv) pc[pl].rec[y * Sp + x] = pc[pl].res[y * Sp + x] = pc[pl].g[(size_t)y * pc[pl].gs + x];
+                if (x < wv) pc(pl).rec[y * Sp + x] = pc(pl).res[y * Sp + x] = pc(pl).g[(size_t)y * pc(pl).gs + x];
             }
         }
         //      intra / IBC areas hold the RESIDUAL there (parked by the inter kernel), which is why the preload fills both arrays
@@ -477,14 +484,14 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         __syncthreads();
         // ---- the row above and the column left of the CTU (L2 loads: other CTAs wrote them) ------------------------------------------
         for (int pl = 0; pl < 3; pl++) {
-            const int sh = pl ? 1 : 0, Sp = pc[pl].Sp, wp = a.w >> sh, hp = a.h >> sh, x0 = ctu_x >> sh, y0 = ctu_y >> sh;
+            const int sh = pl ? 1 : 0, Sp = pc(pl).Sp, wp = a.w >> sh, hp = a.h >> sh, x0 = ctu_x >> sh, y0 = ctu_y >> sh;
             for (int i = tid; i < 3 * Sp + 1; i += kIntraThreads) {
                 if (i <= 2 * Sp) {                                                            // top[x], x = i - 1
                     const int x = i - 1;
-                    if (y0 > 0 && x0 + x >= 0 && x0 + x < wp) pc[pl].top[x] = __ldcg(pc[pl].g - pc[pl].gs + x);
+                    if (y0 > 0 && x0 + x >= 0 && x0 + x < wp) pc(pl).top[x] = __ldcg(pc(pl).g - pc(pl).gs + x);
                 } else {
                     const int y = i - 2 * Sp - 1;
-                    if (x0 > 0 && y0 + y < hp) pc[pl].left[y] = __ldcg(pc[pl].g + (size_t)y * pc[pl].gs - 1);
+                    if (x0 > 0 && y0 + y < hp) pc(pl).left[y] = __ldcg(pc(pl).g + (size_t)y * pc(pl).gs - 1);
                 }
             }
         }
@@ -496,11 +503,8 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             int hq = 0;
             const bool do_htdf = htdf_applies(a, cu, hq);            // uniform
             const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
-            if (!xb_wavefront_mode(cu.mode)) {
-                // inter CU: reconstructed by the inter kernel; only the in-order HTDF pass is left
-                if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
-                continue;
-            }
+            // inter CUs are reconstructed by the inter kernel; only the in-order HTDF pass below is left for them
+            if (xb_wavefront_mode(cu.mode)) do {
             const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
             if (cu.mode == XB200_MODE_IBC) {
                 // xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the already reconstructed part of the CURRENT
@@ -508,26 +512,24 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 // current CTU row at or left of this CTU: samples of this CTU come from shared memory, older ones from the picture.
                 const int bx = cu.mv[0][0], by = cu.mv[0][1];
                 for (int pl = 0; pl < 3; pl++) {
-                    const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, lwp = cu.log2w - sh, Sp = pc[pl].Sp;
+                    const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, lwp = cu.log2w - sh, Sp = pc(pl).Sp;
                     const int ox = lx >> sh, oy = ly >> sh, vx = bx >> sh, vy = by >> sh;
                     const bool coded = ((cu.cbf >> (4 * pl)) & 15) != 0;
                     // the source block is decoded earlier, so it cannot overlap this CU
                     for (int k = tid; k < pw * ph; k += kIntraThreads) {
                         const int y = k >> lwp, x = k & (pw - 1), X = ox + x + vx, Y = oy + y + vy;
-                        const int p = (X >= 0 && X < Sp && Y >= 0 && Y < Sp) ? pc[pl].rec[Y * Sp + X] : __ldcg(pc[pl].g + (ptrdiff_t)Y * pc[pl].gs + X);
-                        pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + (coded ? pc[pl].res[(oy + y) * Sp + ox + x] : 0))));
+                        const int p = (X >= 0 && X < Sp && Y >= 0 && Y < Sp) ? pc(pl).rec[Y * Sp + X] : __ldcg(pc(pl).g + (ptrdiff_t)Y * pc(pl).gs + X);
+                        pc(pl).put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + (coded ? pc(pl).res[(oy + y) * Sp + ox + x] : 0))));
                     }
                 }
                 __syncthreads();
-                continue;
+                break;
             }
             uint32_t ei;
             memcpy(&ei, cu.mv[1], 4);
             const XB200_CU_EXT ex = i - cu0 < n_stage ? s_ext[i - cu0] : a.ext[ei];
             const bool ul = (cu.avail >> 2) & 1;
             // neighbours of all three planes, then prediction + reconstruction
-            int16_t *up[3], *le[3], *ri[3];
-            for (int pl = 0; pl < 3; pl++) { up[pl] = s_nb + pl * IntraSmem::kNbElems + 4; le[pl] = up[pl] + (2 * 128 + 8); ri[pl] = le[pl] + (2 * 128 + 8); }
             if (a.eipd) {
                 const int lr = cu.avail & 3;
                 const int pmax_c = (1 << a.bd_c) - 1;
@@ -538,17 +540,17 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                     for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
                         const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2);
                         NbSrc nb;
-                        nb.pc = &pc[pl]; nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
+                        nb.pc = pc(pl); nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
                         nb.w = pl ? cw : w; nb.ush = pl ? 1 : 2; nb.dflt = dflt;
                         nb.um = ex.u.intra.up; nb.lm = ex.u.intra.left; nb.rm = ex.u.intra.right; nb.ul = ul;
-                        intra_gather_main_elem(nb, pl ? cw + ch : w + h, up[pl], le[pl], ri[pl], k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
+                        intra_gather_main_elem(nb, pl ? cw + ch : w + h, up(pl), le(pl), ri(pl), k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
                     }
                 }
                 __syncthreads();
                 if (cu.refi[0] <= 2 || ipm_c <= 2) {          // DC / plane / bilinear: per-plane scalars first (angular modes need none)
                     if ((tid >> 5) < 3) {
                         const int pl = tid >> 5;
-                        intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up[pl], le[pl], ri[pl],
+                        intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up(pl), le(pl), ri(pl),
                                            s_scr12 + 4 * pl, tid & 31);
                     }
                     __syncthreads();
@@ -557,19 +559,18 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                     const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                     const int lwp = cu.log2w - (pl ? 1 : 0), lhp = cu.log2h - (pl ? 1 : 0), wp = 1 << lwp, hp = 1 << lhp;
                     const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
-                    const int p = intra_px_main(pl ? ipm_c : cu.refi[0], lr, x, y, wp, hp, lwp, lhp, up[pl], le[pl], ri[pl], s_scr12 + 4 * pl, pl ? pmax_c : maxv);
-                    const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc[pl].res[(oy + y) * pc[pl].Sp + ox + x] : 0;
-                    pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));
+                    const int p = intra_px_main(pl ? ipm_c : cu.refi[0], lr, x, y, wp, hp, lwp, lhp, up(pl), le(pl), ri(pl), s_scr12 + 4 * pl, pl ? pmax_c : maxv);
+                    const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc(pl).res[(oy + y) * pc(pl).Sp + ox + x] : 0;
+                    pc(pl).put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));
                 }
                 __syncthreads();
-                if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
-                continue;
+                break;
             }
             {
                 const int n0 = 2 * (w + h) + 1, n1 = 2 * (cw + ch) + 1;
                 for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
                     const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2), sh = pl ? 1 : 0;
-                    intra_gather_elem(pc[pl], lx >> sh, ly >> sh, (w + h) >> sh, 2 - sh, ex.u.intra.up, ex.u.intra.left, ul, dflt, up[pl], le[pl],
+                    intra_gather_elem(pc(pl), lx >> sh, ly >> sh, (w + h) >> sh, 2 - sh, ex.u.intra.up, ex.u.intra.left, ul, dflt, up(pl), le(pl),
                                       k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
                 }
             }
@@ -577,7 +578,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             if (cu.refi[0] == 0 || cu.refi[1] == 0) {         // DC value of the planes that use it
                 if ((tid >> 5) < 3) {
                     const int pl = tid >> 5;
-                    intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.refi[pl ? 1 : 0], up[pl], le[pl], s_scr12 + 4 * pl, tid & 31);
+                    intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), (pl ? cu.refi[1] : cu.refi[0]), up(pl), le(pl), s_scr12 + 4 * pl, tid & 31);
                 }
                 __syncthreads();
             }
@@ -585,12 +586,14 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                 const int lwp = cu.log2w - (pl ? 1 : 0), wp = 1 << lwp;
                 const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
-                const int p = intra_px(cu.refi[pl ? 1 : 0], x, y, up[pl], le[pl], s_scr12 + 4 * pl);
-                const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc[pl].res[(oy + y) * pc[pl].Sp + ox + x] : 0;
-                pc[pl].put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));          // xevd_recon: s16 wrap, then clip
+                const int p = intra_px((pl ? cu.refi[1] : cu.refi[0]), x, y, up(pl), le(pl), s_scr12 + 4 * pl);
+                const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc(pl).res[(oy + y) * pc(pl).Sp + ox + x] : 0;
+                pc(pl).put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));          // xevd_recon: s16 wrap, then clip
             }
             __syncthreads();         // the next CU reads these samples from shared memory
-            if (do_htdf) cu_htdf(a, cu, pc[0], lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+            } while (0);
+            // one call site: the routine is not inlined, and a second copy of its operands would live in local memory
+            if (do_htdf && cu.mode != XB200_MODE_IBC) cu_htdf(a, cu.log2w, cu.log2h, cu.avail_cu, pc(0), lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
         }
     }
     __threadfence();
