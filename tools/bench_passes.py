@@ -84,17 +84,30 @@ def main():
         r1 = [] if variant == "A" else drefs[::-1]
         r0 = drefs[:1] if variant == "A" else drefs
         timed(f"recon_inter_v2 (config 2{variant})", lambda i: recon(works[i % 2][0], curs[i], r0, r1, works[i % 2][1], False), alg_recon(works[0][1]["cl"]))
-    # the same picture through the generic kernel (what Main-tool pictures use)
+    # Main-profile inter pictures: IQT + 1/16-pel tables go through the throughput kernel as well; with ATS / DMVR / affine enabled the CTUs
+    # that hold such CUs go through the generic kernel (per-CTU dispatch, two launches)
     prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=1, n_refs=2, iqt=True, main_mv=True)
     wk = upload_work(cl)
-    timed("recon_inter generic (IQT, 1/16-pel, quadtree)", lambda i: recon(prm, curs[i], drefs, drefs[::-1], wk, False), alg_recon(cl))
-    # Main inter picture with binary/ternary partition, ATS-inter, DMVR, affine
+    timed("recon_inter_v2 (IQT, 1/16-pel, quadtree)", lambda i: recon(prm, curs[i], drefs, drefs[::-1], wk, False), alg_recon(cl))
     prm_m, cl_m, refs_m = synth.make_dmvr_case(w, h, bit_depth=bd, variant="C", seed=5, coded_frac=0.6, main_mv=True, ats_inter_frac=0.3, iqt=True)
     prm_m.tool_affine = 1
     synth.add_affine_cus(cl_m, np.random.default_rng(3), 0.3)
     dm = [ctx.pic_alloc(w, h).upload(r) for r in refs_m]
     wk_m = upload_work(cl_m)
-    timed("recon_inter generic (Main: BTT, ATS, DMVR, affine)", lambda i: recon(prm_m, curs[i], dm, dm[::-1], wk_m, False), alg_recon(cl_m))
+    timed("recon Main picture: BTT, ATS, DMVR, affine (v2 + generic, per-CTU dispatch)", lambda i: recon(prm_m, curs[i], dm, dm[::-1], wk_m, False), alg_recon(cl_m))
+    # the same two pictures through the generic kernel alone
+    import os
+    os.environ["XB200_FORCE_GENERIC"] = "1"
+    ctx_g = Context(0)
+    del os.environ["XB200_FORCE_GENERIC"]
+    ctx_g.set_stream(stream.cuda_stream)
+
+    def recon_g(prm, cur, refs, refs1, wk):
+        cl = wk["cl"]
+        ctx_g.recon_frame_dev(prm, cur, refs, refs1, wk["cus"].data_ptr(), cl.n_cu, wk["first"].data_ptr(), cl.n_ctu, wk["ext"].data_ptr(), len(cl.ext),
+                              wk["coef"].data_ptr(), cl.coef.size, has_intra=False, max_cu_per_ctu=wk["max_cu"])
+    timed("recon_inter generic alone (IQT, 1/16-pel, quadtree)", lambda i: recon_g(prm, curs[i], drefs, drefs[::-1], wk), alg_recon(cl))
+    timed("recon_inter generic alone (Main: BTT, ATS, DMVR, affine)", lambda i: recon_g(prm_m, curs[i], dm, dm[::-1], wk_m), alg_recon(cl_m))
     # I picture: Baseline modes and EIPD + HTDF, through the wavefront kernel
     for eipd in (0, 1):
         prm_i, cl_i = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=9, n_refs=1, coded_frac=0.7, iqt=bool(eipd))

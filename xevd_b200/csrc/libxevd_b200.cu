@@ -122,6 +122,8 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256, true).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256, true).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
         static const int8_t base[58] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                         29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41};
@@ -450,8 +452,12 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     (void)n_ext; (void)n_coef;
     if (n_ctu != a.n_ctu || n_cu < 0 || !d_cus || !d_ctu_first) return XB200_ERR_INVALID_ARGUMENT;
     if (has_intra && prm->ctu_rows > 0) return XB200_ERR_UNSUPPORTED;          // the wavefront crosses band boundaries
-    const bool fast = !a.iqt && !a.ats && !a.dmvr && !a.affine && a.log2_ctu == 6 && !c->force_generic;
-    if (a.n_peer > 0 && !fast) return XB200_ERR_UNSUPPORTED;                   // peer stores exist in the throughput kernel only; use the all-gather exchange
+    // throughput kernel (xb_recon2.cuh): 64x64 CTUs, Baseline or IQT transform; with ATS / DMVR / affine enabled it takes the CTUs that hold
+    // no such CU and the generic kernel (xb_recon.cuh) the others
+    const bool fast = a.log2_ctu == 6 && !c->force_generic;
+    const bool mixed = fast && (a.ats || a.dmvr || a.affine);
+    a.dispatch = mixed ? 1 : 0;
+    if (a.n_peer > 0 && (!fast || mixed || a.iqt)) return XB200_ERR_UNSUPPORTED;        // peer stores exist in the throughput kernel only; use the all-gather exchange
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
     if (cur->poc != prm->poc) cur->poc = prm->poc;
     a.cus = (const XB200_CU *)d_cus;
@@ -459,8 +465,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
-    if (!a.iqt && !a.ats && !a.dmvr && !a.affine && a.log2_ctu == 6 && !c->force_generic) {
-        // throughput kernel (xb_recon2.cuh): Baseline transform path, 64x64 CTUs
+    if (fast) {
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;
         const bool bi = n1 > 0;
@@ -470,9 +475,14 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         if (peer) {
             if (bi) xb::k_recon_inter_v2<true, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
             else    xb::k_recon_inter_v2<false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        } else if (a.iqt) {
+            if (bi) xb::k_recon_inter_v2<true, false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+            else    xb::k_recon_inter_v2<false, false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
         } else if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
         else           xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-    } else {
+        if (mixed) { c->launches++; CK(c, cudaGetLastError()); }
+    }
+    if (!fast || mixed) {
         const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
         if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
         else       xb::k_recon_inter<false><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
@@ -495,8 +505,6 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
                 for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
             CK(c, cudaStreamSynchronize(c->stream));
             if (c->d_order) cudaFree(c->d_order);
-    if (c->out_buf) cudaFree(c->out_buf);
-    if (c->d_dra) cudaFree(c->d_dra);
             c->d_order = nullptr;
             CK(c, cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu));
             CK(c, cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice));

@@ -220,6 +220,22 @@ __device__ __forceinline__ bool dmvr_applies(const XbFrameArgs &a, const XB200_C
     return !(p0 == p1 && start[0][0] == start[1][0] && start[0][1] == start[1][1]);
 }
 
+// Per-CTU dispatch between the two inter kernels: a CU the throughput kernel (xb_recon2.cuh) has no code for
+__device__ __forceinline__ bool cu_needs_generic(const XbFrameArgs &a, const XB200_CU &cu)
+{
+    if (a.ats && (cu.ats || (cu.flags & XB200_CUF_ATS_INTRA))) return true;        // DST-7 / DCT-8 lines, sub-block transform units
+    if (cu.mode == XB200_MODE_AFFINE) return true;
+    int st[2][2];
+    return dmvr_applies(a, cu, st);
+}
+// true when some CU of the CTU needs the generic kernel (all threads of the CTA call this)
+__device__ __forceinline__ bool ctu_needs_generic(const XbFrameArgs &a, const XB200_CU *cus, int ncu, int tid, int nthreads)
+{
+    bool any = false;
+    for (int i = tid; i < ncu; i += nthreads) any |= cu_needs_generic(a, cus[i]);
+    return __syncthreads_or(any) != 0;
+}
+
 // one sample of xevdm_bl_mc_l at 1/16 position (gx, gy) + (j, i)
 __device__ __forceinline__ int dmvr_bilinear(const pel *__restrict__ ref, int s, int gx, int gy, int i, int j, int bd)
 {
@@ -648,6 +664,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
     const XB200_CU *cus = a.cus + cu0;
     const int ncu = cu1 - cu0;
+    if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) return;      // the throughput kernel has done this CTU
 
     // ---- SCU -> CU map, zero residual -------------------------------------------------------------------
     for (int i = tid; i < nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;

@@ -185,11 +185,16 @@ __host__ __device__ __forceinline__ void build_taps4(const int16_t *c, int *dst)
 }
 
 // ---- residual pass 1: one row of a transform block -----------------------------------------------------------------------
-template <int N>
-__device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int *__restrict__ dst, int mul, int off, int shift, bool wide)
+// Baseline: one ROW of the block (the reference's two passes have no rounding in between, so their order is free and rows are the
+// 16-byte-load-friendly choice).  IQT: the first pass rounds to s16, so it has to be the reference's first pass - one COLUMN, strided.
+template <int N, bool IQT>
+__device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int sstride, int *__restrict__ dst, int dstride, int mul, int off, int shift, bool wide)
 {
     int v[N];
-    if (N >= 8) {
+    if (IQT) {
+#pragma unroll
+        for (int k = 0; k < N; k++) v[k] = src[k * sstride];
+    } else if (N >= 8) {
 #pragma unroll
         for (int q = 0; q < N / 8; q++) {
             const int4 w = ((const int4 *)src)[q];
@@ -215,6 +220,11 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int *_
     }
     int out[N];
     InvDct2P<N, 1, N>::run(v, out);
+    if (IQT) {          // Main IQT: same kernel, first pass rounded to s16 (xevdm_itdq.c:35-39,714-716)
+#pragma unroll
+        for (int k = 0; k < N; k++) dst[k * dstride] = xb_clip16((out[k] + 64) >> 7);
+        return;
+    }
     if (N >= 4 && ((smem_u32(dst) & 15) == 0)) {
 #pragma unroll
         for (int q = 0; q < N / 4; q++) ((int4 *)dst)[q] = make_int4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
@@ -238,7 +248,7 @@ __device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstrid
 
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
 // local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
-template <bool BI, bool PEER = false>
+template <bool BI, bool PEER = false, bool IQT = false>
 __global__ void __launch_bounds__(kR2Threads, 2)
 k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 {
@@ -276,6 +286,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     auto ld_taps5 = [&](int ph, int set) { Taps5 t; const int *q = s_t8 + (ph & 15) * 9 + set * 3; t.r0 = q[0]; t.r1 = q[1]; t.r2 = q[2]; return t; };
     auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
     __syncthreads();
+    if (a.dispatch && ctu_needs_generic(a, s_cu, ncu, tid, kR2Threads)) return;      // CTUs with ATS / DMVR / affine CUs are left to the generic kernel
 
     // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the stream.  One bulk
     //      copy brings it on chip while the descriptors are built; the row pass, two barriers later, reads shared memory instead of
@@ -362,7 +373,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             const int qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
             const int odd = (lw + lh) & 1;
             const int shift = 6 - (15 - a.bd_l - ((lw + lh) >> 1)) + (odd ? 8 : 0);
-            const long long mul = (long long)(c_dq_scale[0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
+            const long long mul = (long long)(c_dq_scale[IQT ? 1 : 0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
             d.shift = (uint8_t)shift;
             d.mul = (int)mul;
             d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
@@ -457,30 +468,32 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         return lo + c0 - 1 + __popc(m & (0xffffffffu >> (31 - lane)));
     };
 
-    // ---- residual pass 1 (rows, IDP.2A): luma lines first, then chroma lines (each padded to whole warps) -----------------------
-    const int n_l1y_w = (n_l1y + 31) & ~31, n_l1c_w = (n_l1c + 31) & ~31;
+    // ---- residual pass 1 (IDP.2A): luma lines first, then chroma lines (each padded to whole warps).  Baseline: rows; IQT: columns
+    const uint16_t *preA = IQT ? s_pre2 : s_pre1, *preB = IQT ? s_pre1 : s_pre2;
+    const int nAy = IQT ? n_l2y : n_l1y, nAc = IQT ? n_l2c : n_l1c, nBy = IQT ? n_l1y : n_l2y, nBc = IQT ? n_l1c : n_l2c;
+    const int nAy_w = (nAy + 31) & ~31, nAc_w = (nAc + 31) & ~31;
     const int16_t *s_coef = (const int16_t *)(smem + L.coef);
     if (coef_bytes > 0) mbar_wait(mbar_coef, 0);
-    for (int i0 = warp * 32; i0 < n_l1y_w + n_l1c_w; i0 += kR2Threads) {
-        const bool chroma = i0 >= n_l1y_w;
-        const int li0 = chroma ? i0 - n_l1y_w : i0, li = li0 + lane;
-        const int b = chroma ? find_tu(s_pre1 + 1, n_tuy, n_tu, li0) : find_tu(s_pre1, 0, n_tuy, li0);
-        if (li >= (chroma ? n_l1c : n_l1y)) continue;
+    for (int i0 = warp * 32; i0 < nAy_w + nAc_w; i0 += kR2Threads) {
+        const bool chroma = i0 >= nAy_w;
+        const int li0 = chroma ? i0 - nAy_w : i0, li = li0 + lane;
+        const int b = chroma ? find_tu(preA + 1, n_tuy, n_tu, li0) : find_tu(preA, 0, n_tuy, li0);
+        if (li >= (chroma ? nAc : nAy)) continue;
         const TuDesc d = s_tu[b];
-        const int r = li - (int)(chroma ? s_pre1[b + 1] : s_pre1[b]);
-        const int lw = d.lw_lh & 15, pl = d.plane_wide & 3;
-        const int16_t *src = s_coef + d.coef_off + (r << d.cstride_log2);
-        int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off +
-                   r * (pl ? kTmpCStride : kTmpLStride);
-        const int off = d.shift ? (1 << (d.shift - 1)) : 0;
+        const int q = li - (int)(chroma ? preA[b + 1] : preA[b]);           // row (Baseline) / column (IQT) of the block
+        const int ln = IQT ? d.lw_lh >> 4 : d.lw_lh & 15, pl = d.plane_wide & 3;
+        const int ts = pl ? kTmpCStride : kTmpLStride;
+        const int16_t *src = s_coef + d.coef_off + (IQT ? q : q << d.cstride_log2);
+        int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + (IQT ? q : q * ts);
+        const int off = d.shift ? (1 << (d.shift - 1)) : 0, cs = 1 << d.cstride_log2;
         const bool wide = (d.plane_wide & 4) != 0;
-        switch (lw) {
-        case 1: row_pass<2>(src, dst, d.mul, off, d.shift, wide); break;
-        case 2: row_pass<4>(src, dst, d.mul, off, d.shift, wide); break;
-        case 3: row_pass<8>(src, dst, d.mul, off, d.shift, wide); break;
-        case 4: row_pass<16>(src, dst, d.mul, off, d.shift, wide); break;
-        case 5: row_pass<32>(src, dst, d.mul, off, d.shift, wide); break;
-        default: row_pass<64>(src, dst, d.mul, off, d.shift, wide); break;
+        switch (ln) {
+        case 1: row_pass<2, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        case 2: row_pass<4, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        case 3: row_pass<8, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        case 4: row_pass<16, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        case 5: row_pass<32, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        default: row_pass<64, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
         }
     }
     __syncthreads();
@@ -490,28 +503,29 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
     }
-    // ---- residual pass 2 (columns, IMAD) --------------------------------------------------------------------------------------
+    // ---- residual pass 2 (IMAD): the other direction ---------------------------------------------------------------------------
     {
-        const int sh2 = 19 - (a.bd_l - 8);
-        const int n_l2y_w = (n_l2y + 31) & ~31, n_l2c_w = (n_l2c + 31) & ~31;
-        for (int i0 = warp * 32; i0 < n_l2y_w + n_l2c_w; i0 += kR2Threads) {
-            const bool chroma = i0 >= n_l2y_w;
-            const int li0 = chroma ? i0 - n_l2y_w : i0, li = li0 + lane;
-            const int b = chroma ? find_tu(s_pre2 + 1, n_tuy, n_tu, li0) : find_tu(s_pre2, 0, n_tuy, li0);
-            if (li >= (chroma ? n_l2c : n_l2y)) continue;
+        const int sh2 = (IQT ? 12 : 19) - (a.bd_l - 8);
+        const int nBy_w = (nBy + 31) & ~31, nBc_w = (nBc + 31) & ~31;
+        for (int i0 = warp * 32; i0 < nBy_w + nBc_w; i0 += kR2Threads) {
+            const bool chroma = i0 >= nBy_w;
+            const int li0 = chroma ? i0 - nBy_w : i0, li = li0 + lane;
+            const int b = chroma ? find_tu(preB + 1, n_tuy, n_tu, li0) : find_tu(preB, 0, n_tuy, li0);
+            if (li >= (chroma ? nBc : nBy)) continue;
             const TuDesc d = s_tu[b];
-            const int c = li - (int)(chroma ? s_pre2[b + 1] : s_pre2[b]);
-            const int lh = d.lw_lh >> 4, pl = d.plane_wide & 3;
-            const int *src = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + c;
-            int16_t *dst = s_res + (pl == 0 ? 0 : (pl == 1 ? 64 * kResLStride : 64 * kResLStride + 32 * kResCStride)) + d.res_off + c;
+            const int q = li - (int)(chroma ? preB[b + 1] : preB[b]);       // column (Baseline) / row (IQT)
+            const int ln = IQT ? d.lw_lh & 15 : d.lw_lh >> 4, pl = d.plane_wide & 3;
             const int ss = pl ? kTmpCStride : kTmpLStride, ds = pl ? kResCStride : kResLStride;
-            switch (lh) {
-            case 1: col_pass<2>(src, ss, dst, ds, sh2); break;
-            case 2: col_pass<4>(src, ss, dst, ds, sh2); break;
-            case 3: col_pass<8>(src, ss, dst, ds, sh2); break;
-            case 4: col_pass<16>(src, ss, dst, ds, sh2); break;
-            case 5: col_pass<32>(src, ss, dst, ds, sh2); break;
-            default: col_pass<64>(src, ss, dst, ds, sh2); break;
+            const int *src = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + (IQT ? q * ss : q);
+            int16_t *dst = s_res + (pl == 0 ? 0 : (pl == 1 ? 64 * kResLStride : 64 * kResLStride + 32 * kResCStride)) + d.res_off + (IQT ? q * ds : q);
+            const int s1 = IQT ? 1 : ss, d1 = IQT ? 1 : ds;
+            switch (ln) {
+            case 1: col_pass<2>(src, s1, dst, d1, sh2); break;
+            case 2: col_pass<4>(src, s1, dst, d1, sh2); break;
+            case 3: col_pass<8>(src, s1, dst, d1, sh2); break;
+            case 4: col_pass<16>(src, s1, dst, d1, sh2); break;
+            case 5: col_pass<32>(src, s1, dst, d1, sh2); break;
+            default: col_pass<64>(src, s1, dst, d1, sh2); break;
             }
         }
     }
