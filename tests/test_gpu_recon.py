@@ -301,6 +301,43 @@ def test_intra_1080p_wavefront(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("variant,iqt,aff,ats,dmvr", [("C", 1, 0.03, 0.02, 0), ("B", 1, 0.05, 0.0, 0), ("C", 0, 0.0, 0.03, 0), ("C", 1, 0.02, 0.02, 1)])
+def test_main_picture_per_ctu_dispatch(oracle, monkeypatch, variant, iqt, aff, ats, dmvr):
+    """Main pictures with only a few ATS / affine / DMVR CUs: the throughput kernel reconstructs the CTUs without them, the generic kernel
+    the others.  Planes and every per-SCU map must equal the oracle's, and the all-generic route must agree too."""
+    from xevd_b200.device import Context
+    w, h, bd = 960, 520, 10
+    if dmvr:
+        # DMVR on a minority of the CUs so that some CTUs stay with the throughput kernel
+        prm, cl, refs = synth.make_dmvr_case(w, h, bit_depth=bd, variant=variant, seed=33, flag_frac=0.03, coded_frac=0.6, main_mv=True, ats_inter_frac=ats,
+                                             iqt=bool(iqt))
+    else:
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=33, n_refs=2, coded_frac=0.6, main_mv=True, ats_inter_frac=ats, iqt=bool(iqt))
+        refs = synth.make_refs(w, h, bd, 2, seed=34)
+    if aff:
+        prm.tool_affine = 1
+        synth.add_affine_cus(cl, np.random.default_rng(5), aff)
+    cl.validate()
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    got = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("XB200_FORCE_GENERIC", force)
+        c = Context(0)
+        drefs = [c.pic_alloc(w, h).upload(r) for r in refs]
+        cur = c.pic_alloc(w, h)
+        c.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        got[force] = (cur.download(maps=True), c.launches)
+        c.close()
+    assert got["0"][1] == got["1"][1] + 1, "per-CTU dispatch is two inter launches, the forced generic route one"
+    for force in ("0", "1"):
+        g = got[force][0]
+        for a, b, n in zip(g.planes(), want.planes(), "YUV"):
+            assert np.array_equal(a, b), f"force={force} plane {n}: {int((a != b).sum())} samples differ"
+        assert np.array_equal(g.map_scu, want.map_scu) and np.array_equal(g.map_mv, want.map_mv) and np.array_equal(g.map_refi, want.map_refi)
+        assert np.array_equal(g.map_unrefined_mv, want.map_unrefined_mv)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("frac,eipd,kw", [(0.05, 0, {}), (0.2, 0, {}), (0.5, 0, {}), (0.2, 1, {}), (0.2, 1, dict(log2_ctu=7)), (0.3, 0, dict(log2_ctu=5))])
 def test_mixed_picture_sparse_wavefront(ctx, oracle, frac, eipd, kw):
     """P/B pictures with scattered intra CUs: without HTDF and IBC a CTU waits only for the neighbour CTUs whose intra CUs lie under the

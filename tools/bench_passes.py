@@ -95,7 +95,14 @@ def main():
     dm = [ctx.pic_alloc(w, h).upload(r) for r in refs_m]
     wk_m = upload_work(cl_m)
     timed("recon Main picture: BTT, ATS, DMVR, affine (v2 + generic, per-CTU dispatch)", lambda i: recon(prm_m, curs[i], dm, dm[::-1], wk_m, False), alg_recon(cl_m))
-    # the same two pictures through the generic kernel alone
+    # the same tools on a few per cent of the CUs: most CTUs stay with the throughput kernel
+    prm_s, cl_s, refs_s = synth.make_dmvr_case(w, h, bit_depth=bd, variant="C", seed=6, flag_frac=0.03, coded_frac=0.6, main_mv=True, ats_inter_frac=0.01, iqt=True)
+    prm_s.tool_affine = 1
+    synth.add_affine_cus(cl_s, np.random.default_rng(4), 0.01)
+    ds_ = [ctx.pic_alloc(w, h).upload(r) for r in refs_s]
+    wk_s = upload_work(cl_s)
+    timed("recon Main picture: BTT, 1 % ATS, 1 % affine, 3 % DMVR flags (v2 + generic, per-CTU dispatch)", lambda i: recon(prm_s, curs[i], ds_, ds_[::-1], wk_s, False), alg_recon(cl_s))
+    # the same three pictures through the generic kernel alone
     import os
     os.environ["XB200_FORCE_GENERIC"] = "1"
     ctx_g = Context(0)
@@ -108,6 +115,7 @@ def main():
                               wk["coef"].data_ptr(), cl.coef.size, has_intra=False, max_cu_per_ctu=wk["max_cu"])
     timed("recon_inter generic alone (IQT, 1/16-pel, quadtree)", lambda i: recon_g(prm, curs[i], drefs, drefs[::-1], wk), alg_recon(cl))
     timed("recon_inter generic alone (Main: BTT, ATS, DMVR, affine)", lambda i: recon_g(prm_m, curs[i], dm, dm[::-1], wk_m), alg_recon(cl_m))
+    timed("recon_inter generic alone (Main: BTT, 1 % ATS, 1 % affine, 3 % DMVR flags)", lambda i: recon_g(prm_s, curs[i], ds_, ds_[::-1], wk_s), alg_recon(cl_s))
     # I picture: Baseline modes and EIPD + HTDF, through the wavefront kernel
     for eipd in (0, 1):
         prm_i, cl_i = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=9, n_refs=1, coded_frac=0.7, iqt=bool(eipd))
