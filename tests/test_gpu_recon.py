@@ -301,6 +301,34 @@ def test_intra_1080p_wavefront(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("coded,intra,kw,qp", [(0.1, 0.02, {}, 32), (0.3, 0.05, {}, 40), (0.6, 0.1, {}, 27), (0.15, 0.03, dict(log2_ctu=7), 35), (0.2, 0.0, dict(log2_ctu=5), 30)])
+def test_htdf_sparse_wavefront(ctx, oracle, coded, intra, kw, qp):
+    """HTDF without IBC: CTUs wait only for neighbours whose filtered / intra CUs lie under the samples their own border CUs read; uncoded
+    CUs break the chain.  Decoded several times: a missed dependency is a race."""
+    w, h, bd = 1280, 712, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="C", seed=71, n_refs=2, coded_frac=coded, **kw)
+    prm.tool_eipd = prm.tool_htdf = 1
+    prm.slice_qp = qp
+    if intra:
+        synth.add_intra_cus(cl, np.random.default_rng(4), intra, eipd=True)
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    refs = synth.make_refs(w, h, bd, 2, seed=72)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    try:
+        for rep in range(4):
+            ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+            got = cur.download()
+            for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+                assert np.array_equal(a, b), f"repetition {rep}, plane {n}: {int((a != b).sum())} samples differ"
+    finally:
+        for p in drefs + [cur]:
+            p.free()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("variant,iqt,aff,ats,dmvr", [("C", 1, 0.03, 0.02, 0), ("B", 1, 0.05, 0.0, 0), ("C", 0, 0.0, 0.03, 0), ("C", 1, 0.02, 0.02, 1)])
 def test_main_picture_per_ctu_dispatch(oracle, monkeypatch, variant, iqt, aff, ats, dmvr):
     """Main pictures with only a few ATS / affine / DMVR CUs: the throughput kernel reconstructs the CTUs without them, the generic kernel

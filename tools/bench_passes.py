@@ -134,6 +134,17 @@ def main():
         synth.derive_avail_cu(cl_x)
         wk_x = upload_work(cl_x)
         timed(f"recon P picture, {int(frac * 100)} % intra CUs (inter v2 + wavefront)", lambda i: recon(prm_x, curs[i], drefs, drefs[::-1], wk_x, True), alg_recon(cl_x))
+    # Main P picture with HTDF: every CU with a luma residual goes through the in-order filter of the wavefront kernel; uncoded CUs break
+    # the dependency chains
+    for cf in (0.15, 0.6):
+        prm_h, cl_h = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=23, n_refs=2, coded_frac=cf, iqt=True, main_mv=True)
+        prm_h.tool_eipd = prm_h.tool_htdf = 1
+        prm_h.slice_qp = 34
+        synth.add_intra_cus(cl_h, np.random.default_rng(7), 0.02, eipd=True)
+        synth.derive_avail_cu(cl_h)
+        wk_h = upload_work(cl_h)
+        timed(f"recon Main P picture with HTDF, {int(cf * 100)} % of the CUs coded, 2 % intra (v2 + wavefront)", lambda i: recon(prm_h, curs[i], drefs, drefs[::-1], wk_h, True),
+              alg_recon(cl_h))
     # picture-wide passes on reconstructed pictures (maps left by the Main inter reconstruction above)
     for i in range(args.npic):
         recon(prm_m, curs[i], dm, dm[::-1], wk_m, False)

@@ -431,12 +431,15 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         }
         //      intra / IBC areas hold the RESIDUAL there (parked by the inter kernel), which is why the preload fills both arrays
         // ---- which of the left, upper-left, upper and upper-right CTU this one really depends on -----------------------------------
-        // Without HTDF and IBC the wavefront kernel changes nothing but the samples of intra CUs, and an intra CU reads the row above
+        // Without HTDF the wavefront kernel changes nothing but the samples of intra CUs, and an intra CU reads the row above
         // it (up[-1 .. w+h)) and the column left of it (left[-1 .. h+w)) only.  Inter CUs are final when this kernel starts, so a
         // neighbour CTU matters only where one of ITS intra CUs lies under those samples: per 4-sample unit, the columns of the
         // neighbour's bottom row / rows of its right column covered by intra CUs against the units this CTU's border CUs read.
         // In P/B pictures with scattered intra CUs most CTUs then start at once instead of queueing on a 128-step wavefront.
-        const bool prune = !a.htdf && !a.ibc;
+        // With HTDF the same holds for the CUs it filters: they read a one-sample ring around the CU (inside the extents above) and
+        // are the only other samples this kernel changes - uncoded CUs break the chain.  IBC reaches arbitrarily far: full wavefront.
+        const bool prune = !a.ibc;
+        auto touched = [&](const XB200_CU &cu) { int q; return cu.mode == XB200_MODE_INTRA || htdf_applies(a, cu, q); };
         if (tid < 4) { s_req[tid] = 0; s_has[tid] = 0; }
         __syncthreads();
         if (prune) {
@@ -444,7 +447,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             auto bits = [](int lo, int hi) -> unsigned { return hi <= lo ? 0u : ((hi - lo >= 32 ? 0u : (1u << (hi - lo))) - 1u) << lo; };   // [lo, hi)
             for (int i = cu0 + tid; i < cu1; i += kIntraThreads) {
                 const XB200_CU cu = get_cu(i);
-                if (cu.mode != XB200_MODE_INTRA) continue;
+                if (!touched(cu)) continue;
                 const int X = (cu.x - ctu_x) >> 2, Y = (cu.y - ctu_y) >> 2, W = 1 << (cu.log2w - 2), H = 1 << (cu.log2h - 2);
                 if (Y == 0) {                       // columns X-1 .. X+W+H of the row above
                     if (X == 0) atomicOr(&s_req[1], 1u);
@@ -462,7 +465,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 const int nc = ny * a.w_ctu + nx, ox = nx << a.log2_ctu, oy = ny << a.log2_ctu;
                 for (int i = a.ctu_first[nc] + tid; i < a.ctu_first[nc + 1]; i += kIntraThreads) {
                     const XB200_CU cu = a.cus[i];
-                    if (cu.mode != XB200_MODE_INTRA) continue;
+                    if (!touched(cu)) continue;
                     const int X = (cu.x - ox) >> 2, Y = (cu.y - oy) >> 2, W = 1 << (cu.log2w - 2), H = 1 << (cu.log2h - 2);
                     const bool at_right = X + W == n, at_bottom = Y + H == n;
                     if (k == 0) { if (at_right) atomicOr(&s_has[0], bits(Y, Y + H)); }
