@@ -85,7 +85,7 @@ def main():
         r0 = drefs[:1] if variant == "A" else drefs
         timed(f"recon_inter_v2 (config 2{variant})", lambda i: recon(works[i % 2][0], curs[i], r0, r1, works[i % 2][1], False), alg_recon(works[0][1]["cl"]))
     # Main-profile inter pictures: IQT + 1/16-pel tables go through the throughput kernel as well; with ATS / DMVR / affine enabled the CTUs
-    # that hold such CUs go through the generic kernel (per-CTU dispatch, two launches)
+    # that hold such CUs go through the generic kernel (per-CU dispatch, two launches)
     prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=1, n_refs=2, iqt=True, main_mv=True)
     wk = upload_work(cl)
     timed("recon_inter_v2 (IQT, 1/16-pel, quadtree)", lambda i: recon(prm, curs[i], drefs, drefs[::-1], wk, False), alg_recon(cl))
@@ -94,14 +94,14 @@ def main():
     synth.add_affine_cus(cl_m, np.random.default_rng(3), 0.3)
     dm = [ctx.pic_alloc(w, h).upload(r) for r in refs_m]
     wk_m = upload_work(cl_m)
-    timed("recon Main picture: BTT, ATS, DMVR, affine (v2 + generic, per-CTU dispatch)", lambda i: recon(prm_m, curs[i], dm, dm[::-1], wk_m, False), alg_recon(cl_m))
+    timed("recon Main picture: BTT, ATS, DMVR, affine (v2 + generic, per-CU dispatch)", lambda i: recon(prm_m, curs[i], dm, dm[::-1], wk_m, False), alg_recon(cl_m))
     # the same tools on a few per cent of the CUs: most CTUs stay with the throughput kernel
     prm_s, cl_s, refs_s = synth.make_dmvr_case(w, h, bit_depth=bd, variant="C", seed=6, flag_frac=0.03, coded_frac=0.6, main_mv=True, ats_inter_frac=0.01, iqt=True)
     prm_s.tool_affine = 1
     synth.add_affine_cus(cl_s, np.random.default_rng(4), 0.01)
     ds_ = [ctx.pic_alloc(w, h).upload(r) for r in refs_s]
     wk_s = upload_work(cl_s)
-    timed("recon Main picture: BTT, 1 % ATS, 1 % affine, 3 % DMVR flags (v2 + generic, per-CTU dispatch)", lambda i: recon(prm_s, curs[i], ds_, ds_[::-1], wk_s, False), alg_recon(cl_s))
+    timed("recon Main picture: BTT, 1 % ATS, 1 % affine, 3 % DMVR flags (v2 + generic, per-CU dispatch)", lambda i: recon(prm_s, curs[i], ds_, ds_[::-1], wk_s, False), alg_recon(cl_s))
     # the same three pictures through the generic kernel alone
     import os
     os.environ["XB200_FORCE_GENERIC"] = "1"

@@ -124,6 +124,10 @@ xb200_ctx *xb200_create(int device, int *err)
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256, true).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
     cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
+    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
     {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
         static const int8_t base[58] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                         29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41};
@@ -475,9 +479,13 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         if (peer) {
             if (bi) xb::k_recon_inter_v2<true, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
             else    xb::k_recon_inter_v2<false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-        } else if (a.iqt) {
-            if (bi) xb::k_recon_inter_v2<true, false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-            else    xb::k_recon_inter_v2<false, false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
+        } else if (a.iqt || mixed) {
+            // Main variants: IQT transform and / or per-CU dispatch
+#define XB_V2(BI_, IQT_, DISP_) xb::k_recon_inter_v2<BI_, false, IQT_, DISP_><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu)
+            if (a.iqt && mixed) { if (bi) XB_V2(true, true, true); else XB_V2(false, true, true); }
+            else if (a.iqt)     { if (bi) XB_V2(true, true, false); else XB_V2(false, true, false); }
+            else                { if (bi) XB_V2(true, false, true); else XB_V2(false, false, true); }
+#undef XB_V2
         } else if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
         else           xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
         if (mixed) { c->launches++; CK(c, cudaGetLastError()); }

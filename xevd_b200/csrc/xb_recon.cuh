@@ -220,7 +220,7 @@ __device__ __forceinline__ bool dmvr_applies(const XbFrameArgs &a, const XB200_C
     return !(p0 == p1 && start[0][0] == start[1][0] && start[0][1] == start[1][1]);
 }
 
-// Per-CTU dispatch between the two inter kernels: a CU the throughput kernel (xb_recon2.cuh) has no code for
+// Per-CU dispatch between the two inter kernels: a CU the throughput kernel (xb_recon2.cuh) has no code for
 __device__ __forceinline__ bool cu_needs_generic(const XbFrameArgs &a, const XB200_CU &cu)
 {
     if (a.ats && (cu.ats || (cu.flags & XB200_CUF_ATS_INTRA))) return true;        // DST-7 / DCT-8 lines, sub-block transform units
@@ -664,7 +664,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
     const XB200_CU *cus = a.cus + cu0;
     const int ncu = cu1 - cu0;
-    if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) return;      // the throughput kernel has done this CTU
+    if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) return;      // no ATS / DMVR / affine CU here: the throughput kernel does it all
 
     // ---- SCU -> CU map, zero residual -------------------------------------------------------------------
     for (int i = tid; i < nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;
@@ -673,6 +673,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     __syncthreads();
     for (int i = tid; i < ncu; i += kReconThreads) {
         const XB200_CU cu = cus[i];
+        if (a.dispatch && !cu_needs_generic(a, cu)) continue;        // per-CU dispatch: the throughput kernel reconstructs this CU (and publishes its maps)
         const int sx = (cu.x - ctu_x) >> 2, sy = (cu.y - ctu_y) >> 2;
         const int nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
         for (int y = 0; y < nh; y++)
@@ -795,7 +796,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     // ---- phase B1: intra / IBC CUs are predicted by the wavefront kernel; their residual (neighbour-independent, transformed above with
     //      everything else) is parked in the picture, where that kernel picks it up with its CTU preload
     bool any_wf = false;
-    for (int i = tid; i < ncu; i += kReconThreads) any_wf |= xb_wavefront_mode(cus[i].mode);
+    for (int i = tid; i < ncu; i += kReconThreads) any_wf |= xb_wavefront_mode(cus[i].mode) && (!a.dispatch || cu_needs_generic(a, cus[i]));
     any_wf = __syncthreads_or(any_wf);
     for (int i = tid; any_wf && i < S * S + 2 * Sc * Sc; i += kReconThreads) {
         int pl, x, y;

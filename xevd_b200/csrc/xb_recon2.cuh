@@ -44,6 +44,7 @@ constexpr int kResLStride = 72;              // residual row stride, int16 (64 +
 constexpr int kResCStride = 40;
 
 constexpr int kCoefStageBytes = 2 * 2 * 64 * 64;
+constexpr uint8_t kCuOtherKernel = 0x80;     // private bit in the staged copy of XB200_CU.flags: this CU belongs to the generic kernel
 
 struct TuDesc {                              // one transform block (16 bytes)
     uint32_t coef_off;                       // first coefficient, int16 units
@@ -248,7 +249,7 @@ __device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstrid
 
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
 // local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
-template <bool BI, bool PEER = false, bool IQT = false>
+template <bool BI, bool PEER = false, bool IQT = false, bool DISP = false>
 __global__ void __launch_bounds__(kR2Threads, 2)
 k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 {
@@ -286,7 +287,13 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     auto ld_taps5 = [&](int ph, int set) { Taps5 t; const int *q = s_t8 + (ph & 15) * 9 + set * 3; t.r0 = q[0]; t.r1 = q[1]; t.r2 = q[2]; return t; };
     auto ld_taps3 = [&](int ph, int set) { Taps3 t; const int *q = s_t4 + (ph & 31) * 6 + set * 2; t.r0 = q[0]; t.r1 = q[1]; return t; };
     __syncthreads();
-    if (a.dispatch && ctu_needs_generic(a, s_cu, ncu, tid, kR2Threads)) return;      // CTUs with ATS / DMVR / affine CUs are left to the generic kernel
+    // Per-CU dispatch (Main tools): CUs with ATS / DMVR / affine are reconstructed by the generic kernel, which is launched next and takes
+    // exactly those; here they are marked and then treated as absent (no transform blocks, no tiles, no map entries)
+    if (DISP) {
+        for (int i = tid; i < ncu; i += kR2Threads)
+            if (cu_needs_generic(a, s_cu[i])) s_cu[i].flags |= kCuOtherKernel;
+        __syncthreads();
+    }
 
     // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the stream.  One bulk
     //      copy brings it on chip while the descriptors are built; the row pass, two barriers later, reads shared memory instead of
@@ -311,7 +318,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     // q: 0 luma blocks, 1 chroma blocks, 2 pass-1 luma lines, 3 pass-1 chroma lines, 4 pass-2 luma lines, 5 pass-2 chroma, 6 tiles
     if (warp == 7) {            // number of intra / IBC CUs (their residual is parked in the picture below)
         int n = 0;
-        for (int i = lane; i < ncu; i += 32) n += xb_wavefront_mode(s_cu[i].mode) ? 1 : 0;
+        for (int i = lane; i < ncu; i += 32) n += (xb_wavefront_mode(s_cu[i].mode) && !(DISP && (s_cu[i].flags & kCuOtherKernel))) ? 1 : 0;
         n = __reduce_add_sync(0xffffffffu, n);
         if (lane == 0) cnt[7] = n;
     }
@@ -325,8 +332,9 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 const int w = 1 << cu.log2w, h = 1 << cu.log2h;
                 // intra / IBC CUs are predicted by the wavefront kernel, but their residual does not depend on neighbours: it is
                 // transformed here with everything else and parked in the picture for that kernel to pick up
-                const bool inter = !xb_wavefront_mode(cu.mode);
-                const int ny = (cu.cbf & 15) ? 1 : 0, nc = ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0);
+                const bool mine = !(DISP && (cu.flags & kCuOtherKernel));
+                const bool inter = mine && !xb_wavefront_mode(cu.mode);
+                const int ny = (mine && (cu.cbf & 15)) ? 1 : 0, nc = mine ? ((cu.cbf & 0x0f0) ? 1 : 0) + ((cu.cbf & 0xf00) ? 1 : 0) : 0;
                 switch (warp) {
                 case 0: c = ny; break;
                 case 1: c = nc; break;
@@ -350,7 +358,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int n_tu = n_tuy + n_tuc;
 
     // ---- one thread per CU: transform-block and tile descriptors ------------------------------------------------------------------
-    if (tid < ncu) {
+    if (tid < ncu && !(DISP && (s_cu[tid].flags & kCuOtherKernel))) {
         const XB200_CU cu = s_cu[tid];
         const bool inter_cu = !xb_wavefront_mode(cu.mode);
         const int *of = s_offs + tid * 8;
@@ -534,7 +542,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     // ---- park the residual of intra / IBC CUs in the picture (s16 fits a pel; the wavefront kernel replaces it by the reconstruction)
     for (int i = 0; i < ncu && cnt[7]; i++) {
         const XB200_CU cu = s_cu[i];
-        if (!xb_wavefront_mode(cu.mode)) continue;                  // uniform
+        if (!xb_wavefront_mode(cu.mode) || (DISP && (cu.flags & kCuOtherKernel))) continue;                  // uniform
         const int w = 1 << cu.log2w, h = 1 << cu.log2h, lx = cu.x - ctu_x, ly = cu.y - ctu_y;
         for (int k = tid; k < (w * h) >> 1; k += kR2Threads) {      // luma, two samples per thread
             const int y = k >> (cu.log2w - 1), x = (k & ((w >> 1) - 1)) << 1;
@@ -763,6 +771,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const bool wide_maps = PEER && (a.w_scu & 15) == 0;
     for (int i = tid; i < ncu; i += kR2Threads) {
         const XB200_CU cu = s_cu[i];
+        if (DISP && (cu.flags & kCuOtherKernel)) continue;
         const int sx = cu.x >> 2, sy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
         const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
         uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);
