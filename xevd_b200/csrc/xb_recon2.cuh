@@ -357,23 +357,26 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int n_tuy = cnt[0], n_tuc = cnt[1], n_l1y = cnt[2], n_l1c = cnt[3], n_l2y = cnt[4], n_l2c = cnt[5], n_tiles = cnt[6];
     const int n_tu = n_tuy + n_tuc;
 
-    // ---- one thread per CU: transform-block and tile descriptors ------------------------------------------------------------------
-    if (tid < ncu && !(DISP && (s_cu[tid].flags & kCuOtherKernel))) {
-        const XB200_CU cu = s_cu[tid];
+    // ---- descriptors: warp role = (luma block, Cb block, Cr block, tiles) x CU chunk, one CU per lane.  (One thread per CU doing all
+    //      four in a row left seven warps waiting at the barrier below for ~6 % of the kernel's time.)
+    const int role = warp & 3;
+    for (int ci = (warp >> 2) * 32 + lane; ci < ncu; ci += 64) {
+        const XB200_CU cu = s_cu[ci];
+        if (DISP && (cu.flags & kCuOtherKernel)) continue;
         const bool inter_cu = !xb_wavefront_mode(cu.mode);
-        const int *of = s_offs + tid * 8;
+        const int *of = s_offs + ci * 8;
         const int w = 1 << cu.log2w, h = 1 << cu.log2h;
         const int lx = cu.x - ctu_x, ly = cu.y - ctu_y;
-        int coef = cu.coef_off;
-        int tuc = n_tuy + of[1], l1c = of[3], l2c = of[5];
-#pragma unroll
-        for (int pl = 0; pl < 3; pl++) {
+        if (role < 3) {
+            const int pl = role;
             if (!((cu.cbf >> (4 * pl)) & 15)) continue;
             const int sh = pl ? 1 : 0;
             const int lw = cu.log2w - sh, lh = cu.log2h - sh;
+            const int n_y = ((1 << (cu.log2w + cu.log2h)) + 7) & ~7, n_c = ((1 << (cu.log2w + cu.log2h - 2)) + 7) & ~7;
+            const bool has_y = (cu.cbf & 0x00f) != 0, has_u = (cu.cbf & 0x0f0) != 0;
+            const int coef = cu.coef_off + (pl >= 1 && has_y ? n_y : 0) + (pl == 2 && has_u ? n_c : 0);
             TuDesc d;
             d.coef_off = coef - coef_base;      // relative to the staged slice
-            coef += ((1 << (lw + lh)) + 7) & ~7;
             d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
             d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
             d.lw_lh = (uint8_t)(lw | (lh << 4));
@@ -388,9 +391,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             if (pl == 0) {
                 s_tu[of[0]] = d; s_pre1[of[0]] = (uint16_t)of[2]; s_pre2[of[0]] = (uint16_t)of[4];
             } else {
-                s_tu[tuc] = d; s_pre1[tuc + 1] = (uint16_t)l1c; s_pre2[tuc + 1] = (uint16_t)l2c;   // chroma tables sit after a luma end marker
-                tuc++; l1c += 1 << lh; l2c += 1 << lw;
+                const int second = pl == 2 && has_u ? 1 : 0;          // Cr follows Cb in the chroma tables
+                const int tuc = n_tuy + of[1] + second;
+                s_tu[tuc] = d;                                          // chroma tables sit after a luma end marker
+                s_pre1[tuc + 1] = (uint16_t)(of[3] + (second << lh)); s_pre2[tuc + 1] = (uint16_t)(of[5] + (second << lw));
             }
+            continue;
         }
         // prediction tiles (inter CUs only)
         if (inter_cu) {
@@ -405,7 +411,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         for (int ty = 0; ty < h; ty += 16)
             for (int tx = 0; tx < w; tx += 16, t++) {
                 TileDesc td;
-                td.cu = (uint16_t)tid; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
+                td.cu = (uint16_t)ci; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
                 td.tw = (uint8_t)tw; td.th = (uint8_t)th; td.nl = (uint8_t)((use0 ? 1 : 0) + (use1 ? 1 : 0)); td.pad = 0;
                 s_tile[t] = td;
                 int k = 0;
