@@ -333,7 +333,7 @@ def run_ours(args):
     achieved = alg / (kern_ms * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------------------------------------
-    n_ctx = 1 if band else 3          # band mode: the exchange orders every picture on one stream
+    n_ctx = 1 if band else int(os.environ.get("XB200_BENCH_CONTEXTS", "3"))          # band mode: the exchange orders every picture on one stream
     ctxs, streams = [], []
     for i in range(n_ctx):
         st = stream if band else torch.cuda.Stream(device=dev)

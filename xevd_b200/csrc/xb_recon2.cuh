@@ -44,6 +44,7 @@ constexpr int kResLStride = 72;              // residual row stride, int16 (64 +
 constexpr int kResCStride = 40;
 
 constexpr int kCoefStageBytes = 2 * 2 * 64 * 64;
+constexpr int kBatchCap = 34;                // a CTU has at most 1024 luma and 1024 chroma lines per pass
 constexpr uint8_t kCuOtherKernel = 0x80;     // private bit in the staged copy of XB200_CU.flags: this CU belongs to the generic kernel
 
 struct TuDesc {                              // one transform block (16 bytes)
@@ -77,7 +78,7 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
 // 32 consecutive line tasks run the same butterfly size; line -> block lookup is a binary search over the
 // per-block line prefix sums (no per-line lists).
 struct R2Layout {
-    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, tiles, preds, offs, taps, out, total;
+    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, batch, tiles, preds, offs, taps, out, total;
     __host__ __device__ static R2Layout make(int nl, int max_cu, bool peer = false)
     {
         R2Layout L;
@@ -98,6 +99,7 @@ struct R2Layout {
         L.tus = o; o += 16 * 3 * max_cu;
         L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
         L.pre2 = o; o += 2 * (3 * max_cu + 2);
+        L.batch = o; o += 2 * 4 * kBatchCap;            // block holding the first line of every 32-line batch: [pass][luma / chroma][batch]
         o = (o + 15) & ~15;
         const int max_tiles = max_cu + 16;              // a CU larger than 16x16 is several tiles: at most 15 extra per CTU
         L.tiles = o; o += 8 * max_tiles;
@@ -262,6 +264,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
     TuDesc *s_tu = (TuDesc *)(smem + L.tus);
     uint16_t *s_pre1 = (uint16_t *)(smem + L.pre1), *s_pre2 = (uint16_t *)(smem + L.pre2);
+    uint16_t *s_bat1 = (uint16_t *)(smem + L.batch), *s_bat2 = s_bat1 + 2 * kBatchCap;
     TileDesc *s_tile = (TileDesc *)(smem + L.tiles);
     TilePred *s_pred = (TilePred *)(smem + L.preds);
     int *s_offs = (int *)(smem + L.offs);
@@ -388,14 +391,19 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             d.shift = (uint8_t)shift;
             d.mul = (int)mul;
             d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
+            int b, p1, p2;
             if (pl == 0) {
-                s_tu[of[0]] = d; s_pre1[of[0]] = (uint16_t)of[2]; s_pre2[of[0]] = (uint16_t)of[4];
+                b = of[0]; p1 = of[2]; p2 = of[4];
+                s_tu[b] = d; s_pre1[b] = (uint16_t)p1; s_pre2[b] = (uint16_t)p2;
             } else {
                 const int second = pl == 2 && has_u ? 1 : 0;          // Cr follows Cb in the chroma tables
-                const int tuc = n_tuy + of[1] + second;
-                s_tu[tuc] = d;                                          // chroma tables sit after a luma end marker
-                s_pre1[tuc + 1] = (uint16_t)(of[3] + (second << lh)); s_pre2[tuc + 1] = (uint16_t)(of[5] + (second << lw));
+                b = n_tuy + of[1] + second; p1 = of[3] + (second << lh); p2 = of[5] + (second << lw);
+                s_tu[b] = d;                                            // chroma tables sit after a luma end marker
+                s_pre1[b + 1] = (uint16_t)p1; s_pre2[b + 1] = (uint16_t)p2;
             }
+            // the block that holds the first line of a 32-line batch is where the passes start their lookup
+            for (int k = (p1 + 31) >> 5; (k << 5) < p1 + (1 << lh); k++) s_bat1[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
+            for (int k = (p2 + 31) >> 5; (k << 5) < p2 + (1 << lw); k++) s_bat2[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
             continue;
         }
         // prediction tiles (inter CUs only)
@@ -467,25 +475,18 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     };
     issue(0, 0);
 
-    // Block lookup for a warp's 32 consecutive lines li0 .. li0+31 (all lanes participate): blocks are sorted by first
-    // line, so block(li0 + lane) = #{starts <= li0} - 1 + #{starts in (li0, li0 + lane]}.  One coalesced load of the
-    // prefix table, one ballot and one warp OR-reduction per 32 blocks instead of a per-lane binary search.
-    auto find_tu = [&](const uint16_t *pre, int lo, int hi, int li0) {
-        int c0 = 0;
-        unsigned m = 0;
-        for (int k0 = lo; k0 < hi; k0 += 32) {
-            const int k = k0 + lane;
-            const int p = k < hi ? (int)pre[k] : 0x7fffffff;
-            c0 += __popc(__ballot_sync(0xffffffffu, p <= li0));
-            const int dd = p - li0;
-            m |= __reduce_or_sync(0xffffffffu, (dd > 0 && dd < 32) ? (1u << dd) : 0u);
-            if (__shfl_sync(0xffffffffu, p, 31) > li0 + 31) break;
-        }
-        return lo + c0 - 1 + __popc(m & (0xffffffffu >> (31 - lane)));
+    // Block lookup for line li of a pass: start at the block that holds the first line of the warp's 32-line batch (table written with the
+    // descriptors) and step over the block starts up to li - one step per block boundary inside the batch, none for blocks of 32+ lines.
+    // (The previous warp-wide search over the prefix table cost 6 % of the kernel.)
+    auto find_tu = [&](const uint16_t *pre, const uint16_t *bat, int li) {
+        int b = bat[li >> 5];
+        while (li >= (int)pre[b + 1]) b++;
+        return b;
     };
 
     // ---- residual pass 1 (IDP.2A): luma lines first, then chroma lines (each padded to whole warps).  Baseline: rows; IQT: columns
     const uint16_t *preA = IQT ? s_pre2 : s_pre1, *preB = IQT ? s_pre1 : s_pre2;
+    const uint16_t *batA = IQT ? s_bat2 : s_bat1, *batB = IQT ? s_bat1 : s_bat2;
     const int nAy = IQT ? n_l2y : n_l1y, nAc = IQT ? n_l2c : n_l1c, nBy = IQT ? n_l1y : n_l2y, nBc = IQT ? n_l1c : n_l2c;
     const int nAy_w = (nAy + 31) & ~31, nAc_w = (nAc + 31) & ~31;
     const int16_t *s_coef = (const int16_t *)(smem + L.coef);
@@ -493,8 +494,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     for (int i0 = warp * 32; i0 < nAy_w + nAc_w; i0 += kR2Threads) {
         const bool chroma = i0 >= nAy_w;
         const int li0 = chroma ? i0 - nAy_w : i0, li = li0 + lane;
-        const int b = chroma ? find_tu(preA + 1, n_tuy, n_tu, li0) : find_tu(preA, 0, n_tuy, li0);
         if (li >= (chroma ? nAc : nAy)) continue;
+        const int b = chroma ? find_tu(preA + 1, batA + kBatchCap, li) : find_tu(preA, batA, li);
         const TuDesc d = s_tu[b];
         const int q = li - (int)(chroma ? preA[b + 1] : preA[b]);           // row (Baseline) / column (IQT) of the block
         const int ln = IQT ? d.lw_lh >> 4 : d.lw_lh & 15, pl = d.plane_wide & 3;
@@ -526,8 +527,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         for (int i0 = warp * 32; i0 < nBy_w + nBc_w; i0 += kR2Threads) {
             const bool chroma = i0 >= nBy_w;
             const int li0 = chroma ? i0 - nBy_w : i0, li = li0 + lane;
-            const int b = chroma ? find_tu(preB + 1, n_tuy, n_tu, li0) : find_tu(preB, 0, n_tuy, li0);
             if (li >= (chroma ? nBc : nBy)) continue;
+            const int b = chroma ? find_tu(preB + 1, batB + kBatchCap, li) : find_tu(preB, batB, li);
             const TuDesc d = s_tu[b];
             const int q = li - (int)(chroma ? preB[b + 1] : preB[b]);       // column (Baseline) / row (IQT)
             const int ln = IQT ? d.lw_lh & 15 : d.lw_lh >> 4, pl = d.plane_wide & 3;
