@@ -6,10 +6,12 @@
 //
 // Intra CUs read reconstructed samples of their left / upper neighbours, so they cannot run in the fully parallel inter
 // kernel.  The reference serialises them with a CTU-row wavefront (sync_flag, src_base/xevd.c:1497-1501); the same
-// dependency structure is used here: one CTA per CTU, CTUs are handed out in raster order by an atomic ticket (so every
-// CTA a waiter depends on has already started), a CTA spins on the `done` flags of its left, upper-left, upper and
-// upper-right CTU, then reconstructs its intra CUs one after the other in decoding order, all threads cooperating on each
-// CU.  Inter CUs of the picture have been reconstructed by the inter kernel before this one starts.
+// dependency structure is used here: one CTA per CTU, CTUs are handed out in wavefront order (x + 2y) by an atomic ticket (so
+// every CTA a waiter depends on has already started), a CTA spins on the `done` flags of those of its left, upper-left, upper
+// and upper-right CTUs it really depends on (without IBC: only where a neighbour's intra / HTDF-filtered CUs lie under the
+// samples its own border CUs read), then reconstructs its intra CUs one after the other in decoding order, all threads
+// cooperating on each CU.  Inter CUs of the picture - and the residual of the intra CUs - have been done by the inter kernel
+// before this one starts.
 // Neighbour availability is order-derived in the reference (COD bits); it arrives precomputed as the per-SCU masks of
 // XB200_CU_EXT.
 #pragma once

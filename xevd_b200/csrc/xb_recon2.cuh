@@ -1,16 +1,21 @@
-// xb_recon2.cuh -- throughput-oriented inter reconstruction kernel (Baseline transform path, 64x64 CTUs).
+// xb_recon2.cuh -- throughput-oriented inter reconstruction kernel (64x64 CTUs; Baseline or Main IQT transform, Baseline or Main taps).
 //
 // Same contract as k_recon_inter (xb_recon.cuh): one CTA reconstructs one CTU from the flat CU work items.
 // What is different is how the work is laid onto the SM:
 //
 //   * reference windows arrive by TMA (cp.async.bulk.tensor.2d): one 40x23 (luma) / 24x11 (chroma) box per
-//     16x16 tile, issued up front so the HBM latency hides behind the residual phase; completion by mbarrier.
+//     16x16 tile, issued up front (every warp issues the boxes of its own two tile slots) so the HBM latency hides behind the
+//     residual phase; completion by mbarrier.  The two lists of a B picture go through the same windows one after the other.
 //     The hardware wants the box to start on a 16-byte boundary (measured: profiles/microbench/tma_probe*.cu), so
 //     the box is the 8-sample-aligned superset of the window and the horizontal stage absorbs the 0..7 sample
 //     offset (word offset by addressing, odd offsets by swapping the tap sets of even and odd outputs).
+//   * the CTU's slice of the coefficient stream arrives by one cp.async.bulk into the bytes of the residual planes.
 //   * residual: thread-per-line butterflies in registers.  The Baseline 2-D inverse DCT is an exact integer
 //     matrix product modulo 2^32, so the row pass is done first on the s16 inputs with IDP.2A
-//     (packed s16x2 . s8x2) and the column pass second with IMAD on the s32 intermediate.
+//     (packed s16x2 . s8x2) and the column pass second with IMAD on the s32 intermediate.  IQT rounds the first pass to s16,
+//     so the IQT variant runs the reference's order: columns first (strided reads of the staged coefficients), rows second.
+//   * Main tools it has no code for (ATS, DMVR, affine): per-CU dispatch - those CUs are marked and treated as absent; the
+//     generic kernel, launched next, reconstructs exactly them (cu_needs_generic, xb_recon.cuh).
 //   * interpolation: IDP.2A on packed pixel pairs; the horizontal stage emits vertical pairs so the vertical
 //     stage needs no repacking; variants 00/n0/0n/nn are one code path (phase-0 taps are an exact copy).
 //   * reconstruction: VIADDMNMX.S16x2.RELU = clip3(0, max, (s16)(pred + resid)) for two samples per instruction.
