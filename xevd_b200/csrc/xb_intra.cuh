@@ -31,7 +31,7 @@ struct IntraSmem {
     static constexpr int kPlaneElems = 128 * 128 + 2 * 64 * 64;     // CTU-raster, luma then Cb, Cr (plane stride = plane CTU size)
     static constexpr int kTopElems = 2 * 128 + 8;                   // per plane: x = -1 .. 2 * S - 1 of the row above
     static constexpr int kLeftElems = 128;                          // per plane: the column left of the CTU
-    static constexpr int kTmpElems = 64 * 65;                       // pass-1 buffer of one transform block / HTDF ring block
+    static constexpr int kTmpElems = 66 * 66 / 2 + 65 * 65 * 2 + 16; // HTDF: ring-extended copy of the CU (int16) + four outputs per 2x2 window (4 x int16)
     static constexpr int kNbElems = 3 * (2 * 128 + 8);              // up[-1..w+h), left[-1..w+h), right[-1..w+h)
     static constexpr int kCuStage = 256;                            // CU descriptors + extension records staged on chip (the rest stay in L2)
     static size_t bytes()
@@ -298,17 +298,6 @@ __device__ __forceinline__ int htdf_shrink(int z, const HtdfTbl &tbl, int thr, i
     const int v = (int)((idx < 8 ? __byte_perm(tbl.t0, tbl.t1, idx & 7) : __byte_perm(tbl.t2, tbl.t3, idx & 7)) & 0xff);
     return z < 0 ? -v : v;
 }
-// output `which` (0..3 = (0,0) (0,1) (1,0) (1,1)) of the window whose top-left sample is t[0]
-__device__ __forceinline__ int htdf_window(const int16_t *t, int s, int which, const HtdfTbl &tbl, int thr, int shift, int round)
-{
-    const int x0 = t[0], x1 = t[1], x2 = t[s], x3 = t[s + 1];
-    const int y0 = x0 + x2, y1 = x1 + x3, y2 = x0 - x2, y3 = x1 - x3;
-    const int z0 = y0 + y1;
-    const int z1 = htdf_shrink(y0 - y1, tbl, thr, shift, round), z2 = htdf_shrink(y2 + y3, tbl, thr, shift, round), z3 = htdf_shrink(y2 - y3, tbl, thr, shift, round);
-    const int i0 = z0 + z2, i1 = z1 + z3, i2 = z0 - z2, i3 = z1 - z3;
-    return (which == 0 ? i0 + i1 : (which == 1 ? i0 - i1 : (which == 2 ? i2 + i3 : i2 - i3))) >> 2;
-}
-
 // true when the CU is filtered (xevdm.c:1383 + xevdm_htdf_skip_condition, xevdm_recon.c:271-297); qp receives the table QP
 __device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_CU &cu, int &qp)
 {
@@ -325,10 +314,19 @@ __device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_C
 
 __device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log2h, int av, const PlaneCtx pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads)
 {
-    const int w = 1 << log2w, h = 1 << log2h, we = w + 2, he = h + 2;
+    const int w = 1 << log2w, h = 1 << log2h, we = w + 2;
     const bool up = av & 1, le = (av >> 1) & 1, ri = (av >> 3) & 1;
-    for (int idx = tid; idx < we * he; idx += nthreads) {
-        const int r = idx / we, c = idx - r * we, i = r - 1, j = c - 1;
+    // (1) the CU itself, straight from the on-chip CTU
+    for (int idx = tid; idx < w * h; idx += nthreads) {
+        const int y = idx >> log2w, x = idx & (w - 1);
+        t[(y + 1) * we + x + 1] = pc.rec[(cy + y) * pc.Sp + cx + x];
+    }
+    //     and the one-sample ring: row above, row below, left and right columns
+    for (int idx = tid; idx < 2 * we + 2 * h; idx += nthreads) {
+        int i, j;
+        if (idx < we) { i = -1; j = idx - 1; }
+        else if (idx < 2 * we) { i = h; j = idx - we - 1; }
+        else { const int k = idx - 2 * we; i = k >> 1; j = (k & 1) ? w : -1; }
         int si = min(max(i, 0), h - 1), sj = min(max(j, 0), w - 1);          // replicated by default
         if (i >= 0 && i < h) { if (j < 0 && le) sj = -1; else if (j >= w && ri) sj = w; }
         else if (i < 0) {
@@ -337,22 +335,38 @@ __device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log
             else if ((av >> 6) & 1) { si = -1; sj = w; }
         } else if (j < 0) { if ((av >> 7) & 1) { si = h; sj = -1; } }
         else if (j >= w) { if ((av >> 8) & 1) { si = h; sj = w; } }
-        t[idx] = (int16_t)pc.get(cx + sj, cy + si);
+        t[(i + 1) * we + j + 1] = (int16_t)pc.get(cx + sj, cy + si);
     }
     __syncthreads();
+    // (2) every 2x2 window once: Hadamard, shrink, inverse; its four outputs go to the four samples it covers
     int k = (qp - 20 + 4) >> 3;
     k = min(max(k, 0), 4);
     const int lg = c_htdf_thr_log2[k], shift = lg - 4, round = (1 << shift) >> 1, thr = (1 << lg) - (1 << shift);
     const uint4 tw = *(const uint4 *)c_htdf_tbl[k];
     const HtdfTbl tbl = {tw.x, tw.y, tw.z, tw.w};
     const int maxv = (1 << a.bd_l) - 1;
+    const int ww = w + 1, nwin = ww * (h + 1);
+    uint2 *win = (uint2 *)(t + ((we * (h + 2) + 3) & ~3));
+    const float inv_ww = 1.0f / (float)ww;
+    for (int idx = tid; idx < nwin; idx += nthreads) {
+        const int i = __float2int_rd(((float)idx + 0.5f) * inv_ww), j = idx - i * ww;      // exact: idx < 4225, ww <= 65
+        const int16_t *q = t + i * we + j;
+        const int x0 = q[0], x1 = q[1], x2 = q[we], x3 = q[we + 1];
+        const int y0 = x0 + x2, y1 = x1 + x3, y2 = x0 - x2, y3 = x1 - x3;
+        const int z0 = y0 + y1;
+        const int z1 = htdf_shrink(y0 - y1, tbl, thr, shift, round), z2 = htdf_shrink(y2 + y3, tbl, thr, shift, round), z3 = htdf_shrink(y2 - y3, tbl, thr, shift, round);
+        const int i0 = z0 + z2, i1 = z1 + z3, i2 = z0 - z2, i3 = z1 - z3;
+        const unsigned o0 = (unsigned)((i0 + i1) >> 2) & 0xffffu, o1 = (unsigned)((i0 - i1) >> 2) & 0xffffu;
+        const unsigned o2 = (unsigned)((i2 + i3) >> 2) & 0xffffu, o3 = (unsigned)((i2 - i3) >> 2) & 0xffffu;
+        win[idx] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+    }
+    __syncthreads();
+    // (3) a sample is the rounded average of the four windows that cover it (the reference accumulates in s16: sums are mod 2^16)
     for (int idx = tid; idx < w * h; idx += nthreads) {
-        const int i = (idx >> log2w) + 1, j = (idx & (w - 1)) + 1;
-        int acc = htdf_window(t + (i - 1) * we + (j - 1), we, 3, tbl, thr, shift, round);
-        acc = (int16_t)(acc + htdf_window(t + (i - 1) * we + j, we, 2, tbl, thr, shift, round));
-        acc = (int16_t)(acc + htdf_window(t + i * we + (j - 1), we, 1, tbl, thr, shift, round));
-        acc = (int16_t)(acc + htdf_window(t + i * we + j, we, 0, tbl, thr, shift, round));
-        pc.put(cx + j - 1, cy + i - 1, xb_clip3(0, maxv, (acc + 2) >> 2));
+        const int y = idx >> log2w, x = idx & (w - 1);
+        const uint2 a00 = win[y * ww + x], a01 = win[y * ww + x + 1], a10 = win[(y + 1) * ww + x], a11 = win[(y + 1) * ww + x + 1];
+        const int acc = (int16_t)((a00.y >> 16) + (a01.y & 0xffffu) + (a10.x >> 16) + (a11.x & 0xffffu));
+        pc.put(cx + x, cy + y, xb_clip3(0, maxv, (acc + 2) >> 2));
     }
     __syncthreads();
 }
