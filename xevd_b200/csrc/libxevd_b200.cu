@@ -247,15 +247,17 @@ static int make_tensor_maps(xb200_ctx *c, xb200_pic *p)
         }
         encode = (PFN_encodeTiled)fn;
     }
+    // maps[0]: luma plane (2-D).  maps[1]: Cb and Cr as one 3-D tensor (x, y, plane) - the planes have the same geometry and lie
+    // chroma_elems apart, so one TMA instruction fetches a tile's two chroma windows.  maps[2]: Cr alone (2-D, kept for tools).
     alignas(64) CUtensorMap maps[3];
     for (int pl = 0; pl < 3; pl++) {
-        const bool luma = pl == 0;
+        const bool luma = pl == 0, both = pl == 1;
         void *base = luma ? (void *)p->buf : (void *)(p->buf + p->luma_elems + (pl == 2 ? p->chroma_elems : 0));
-        const cuuint64_t dims[2] = {(cuuint64_t)(luma ? p->s_l : p->s_c), (cuuint64_t)(luma ? p->h + 2 * p->pad_l : p->h_c + 2 * p->pad_c)};
-        const cuuint64_t strides[1] = {(cuuint64_t)(luma ? p->s_l : p->s_c) * 2};
-        const cuuint32_t box[2] = {luma ? (cuuint32_t)xb::kBoxLW : (cuuint32_t)xb::kBoxCW, luma ? (cuuint32_t)xb::kBoxLH : (cuuint32_t)xb::kBoxCH};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const cuuint64_t dims[3] = {(cuuint64_t)(luma ? p->s_l : p->s_c), (cuuint64_t)(luma ? p->h + 2 * p->pad_l : p->h_c + 2 * p->pad_c), 2};
+        const cuuint64_t strides[2] = {(cuuint64_t)(luma ? p->s_l : p->s_c) * 2, (cuuint64_t)p->chroma_elems * 2};
+        const cuuint32_t box[3] = {luma ? (cuuint32_t)xb::kBoxLW : (cuuint32_t)xb::kBoxCW, luma ? (cuuint32_t)xb::kBoxLH : (cuuint32_t)xb::kBoxCH, 2};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&maps[pl], CU_TENSOR_MAP_DATA_TYPE_UINT16, both ? 3 : 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled failed (%d) plane %d", (int)r, pl);

@@ -36,7 +36,8 @@ constexpr int kTileCap = 16;                 // 16x16 luma tiles staged per roun
 constexpr int kBoxLW = 40, kBoxLH = 23;      // luma TMA box: (offset <= 7) + 16 + 7 = 30 -> 40 samples keeps the row stride
 constexpr int kBoxCW = 24, kBoxCH = 11;      //   at 20 words (8 rows = 8 distinct bank quads); chroma: 7 + 8 + 3 = 18 -> 24
 constexpr int kWinLBytes = 1920;             // 40 x 23 x 2 = 1840, rounded to a multiple of 128
-constexpr int kWinCBytes = 640;              // 24 x 11 x 2 = 528
+constexpr int kWinCPlane = kBoxCW * kBoxCH * 2;   // 528 bytes: one chroma plane of a window; Cb and Cr arrive as ONE 3-D box, back to back
+constexpr int kWinCBytes = 1152;             // 2 x 528 = 1056, rounded to a multiple of 128
 constexpr int kWinLStrideW = kBoxLW / 2;     // window row stride in 32-bit words
 constexpr int kWinCStrideW = kBoxCW / 2;
 constexpr int kM2LStrideW = 20;              // vertical-pair buffer row stride (16 columns + 4 pad), words
@@ -92,7 +93,7 @@ struct R2Layout {
         // after the other (the running prediction lives in registers), so B pictures keep two CTAs per SM like P pictures
         (void)nl;
         L.win_l = o; o += kTileCap * kWinLBytes;
-        L.win_c = o; o += kTileCap * 2 * kWinCBytes;
+        L.win_c = o; o += kTileCap * kWinCBytes;
         const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
         const int m2_bytes = 4 * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
@@ -135,6 +136,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n\t.reg .pred p;\n\t"
         "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra W;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -474,8 +480,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             const TilePred p = s_pred[(t0 + slot) * NL + l];
             const CUtensorMap *tm = a.ref_tmap[p.ref];
             tma_load_2d(smem + L.win_l + slot * kWinLBytes, tm + 0, p.wx & ~7, p.wy, mbar);
-            tma_load_2d(smem + L.win_c + (slot * 2 + 0) * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, mbar);
-            tma_load_2d(smem + L.win_c + (slot * 2 + 1) * kWinCBytes, tm + 2, p.cwx & ~7, p.cwy, mbar);
+            tma_load_3d(smem + L.win_c + slot * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, 0, mbar);        // Cb and Cr: one box over the plane dimension
         }
     };
     issue(0, 0);
@@ -627,7 +632,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     if (l < td.nl && 2 * rp < (td.th >> 1) + 3) {
                         const TilePred p = s_pred[(t0 + slot) * NL + l];
                         const int offx = p.offs >> 4, par = offx & 1;
-                        const int *win = (const int *)(smem + L.win_c + (slot * 2 + pl) * kWinCBytes) + (offx >> 1);
+                        const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1);
                         const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
                         const int sh = p.ctwo_d ? s1c : 6;
                         int hv[2][8];
