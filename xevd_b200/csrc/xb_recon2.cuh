@@ -788,22 +788,23 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     int16_t *sm_refi = (int16_t *)(sm_scu + 256);
     uint8_t *sm_edge = (uint8_t *)(sm_refi + 256);
     const bool wide_maps = PEER && (a.w_scu & 15) == 0;
-    for (int i = tid; i < ncu; i += kR2Threads) {
+    // sixteen lanes per CU, one SCU per lane and step (a thread per CU wrote up to 256 entries x 5 maps on its own at the kernel's tail)
+    for (int i = tid >> 4; i < ncu; i += kR2Threads / 16) {
         const XB200_CU cu = s_cu[i];
         if (DISP && (cu.flags & kCuOtherKernel)) continue;
-        const int sx = cu.x >> 2, sy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
+        const int sx = cu.x >> 2, sy = cu.y >> 2, lnw = cu.log2w - 2, nw = 1 << lnw, nscu_cu = 1 << (cu.log2w + cu.log2h - 4);
         const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
         uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);
         if (cu.cbf & 1) m |= 1u << 24;
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         const int2 mv = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
         const int16_t rf = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
-        for (int y = 0; y < nh; y++)
-            for (int x = 0; x < nw; x++) {
+        for (int q = tid & 15; q < nscu_cu; q += 16) {
+                const int y = q >> lnw, x = q & (nw - 1);
                 const uint8_t e = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
                 if (wide_maps) {
-                    const int q = ((sy + y) & 15) * 16 + ((sx + x) & 15);
-                    sm_mv[q] = mv; sm_scu[q] = m; sm_refi[q] = rf; sm_edge[q] = e;
+                    const int qq = ((sy + y) & 15) * 16 + ((sx + x) & 15);
+                    sm_mv[qq] = mv; sm_scu[qq] = m; sm_refi[qq] = rf; sm_edge[qq] = e;
                     continue;
                 }
                 const int p = (sy + y) * a.w_scu + sx + x;
