@@ -84,7 +84,7 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
 // 32 consecutive line tasks run the same butterfly size; line -> block lookup is a binary search over the
 // per-block line prefix sums (no per-line lists).
 struct R2Layout {
-    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, batch, own, tiles, preds, offs, taps, out, total;
+    int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, batch, tiles, preds, offs, taps, out, total;
     __host__ __device__ static R2Layout make(int nl, int max_cu, bool peer = false)
     {
         R2Layout L;
@@ -105,7 +105,6 @@ struct R2Layout {
         L.tus = o; o += 16 * 3 * max_cu;
         L.pre1 = o; o += 2 * (3 * max_cu + 2);          // uint16 prefix of pass-1 lines per block (+ end markers)
         L.pre2 = o; o += 2 * (3 * max_cu + 2);
-        L.own = o; o += 2 * 256;                        // CU that owns each of the CTU's 16 x 16 SCUs (0xffff: none)
         L.batch = o; o += 2 * 4 * kBatchCap;            // block holding the first line of every 32-line batch: [pass][luma / chroma][batch]
         o = (o + 15) & ~15;
         const int max_tiles = max_cu + 16;              // a CU larger than 16x16 is several tiles: at most 15 extra per CTU
@@ -294,7 +293,6 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         int4 *s = (int4 *)s_cu;
         for (int i = tid; i < ncu * 2; i += kR2Threads) s[i] = __ldg(g + i);
         if (tid == 0) { mbar_init(mbar, 1); mbar_init(mbar_coef, 1); }
-        ((uint16_t *)(smem + L.own))[tid] = 0xffff;
         int *t8 = (int *)(smem + L.taps), *t4 = t8 + 16 * 9;
         if (tid < 16 * 9) t8[tid] = c_taps5[a.main_tables][tid];
         if (tid < 32 * 6) t4[tid] = c_taps3[a.main_tables][tid];
@@ -309,16 +307,6 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         for (int i = tid; i < ncu; i += kR2Threads)
             if (cu_needs_generic(a, s_cu[i])) s_cu[i].flags |= kCuOtherKernel;
         __syncthreads();
-    }
-    // SCU -> CU table for the map publication at the end (sixteen lanes per CU; every later barrier orders it before its readers)
-    {
-        uint16_t *s_own = (uint16_t *)(smem + L.own);
-        for (int i = tid >> 4; i < ncu; i += kR2Threads / 16) {
-            const XB200_CU cu = s_cu[i];
-            if (DISP && (cu.flags & kCuOtherKernel)) continue;
-            const int sx = (cu.x - ctu_x) >> 2, sy = (cu.y - ctu_y) >> 2, lnw = cu.log2w - 2, nw = 1 << lnw, n = 1 << (cu.log2w + cu.log2h - 4);
-            for (int q = tid & 15; q < n; q += 16) s_own[(sy + (q >> lnw)) * 16 + sx + (q & (nw - 1))] = (uint16_t)i;
-        }
     }
 
     // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the stream.  One bulk
@@ -800,36 +788,13 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     int16_t *sm_refi = (int16_t *)(sm_scu + 256);
     uint8_t *sm_edge = (uint8_t *)(sm_refi + 256);
     const bool wide_maps = PEER && (a.w_scu & 15) == 0;
-    if (!wide_maps) {
-        // one SCU per thread, five coalesced stores each; the SCU -> CU table was filled at the start.  (A thread per CU wrote up to
-        // 256 entries x 5 maps on its own at the kernel's tail: 64x64 CUs took 316 us per 4K picture instead of 136.)
-        const uint16_t *s_own = (const uint16_t *)(smem + L.own);
-        const int i = s_own[tid];
-        if (i != 0xffff) {
-            const XB200_CU cu = s_cu[i];
-            const int gx = (ctu_x >> 2) + (tid & 15), gy = (ctu_y >> 2) + (tid >> 4);
-            const int x = gx - (cu.x >> 2), y = gy - (cu.y >> 2);
-            const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
-            uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);
-            if (cu.cbf & 1) m |= 1u << 24;
-            if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
-            const int2 mv = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
-            const int16_t rf = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
-            const uint8_t e = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
-            const int p = gy * a.w_scu + gx;
-            const bool fo = a.peer_maps != 0;
-            xb_store_all(a, a.map_scu + p, m, fo);
-            xb_store_all(a, (int2 *)a.map_mv + p, mv, fo);
-            xb_store_all(a, (int2 *)a.map_unrefined_mv + p, mv, fo);
-            xb_store_all(a, (int16_t *)a.map_refi + p, rf, fo);
-            xb_store_all(a, a.map_edge + p, e, fo);
-        }
-        return;
-    }
-    // PEER with whole 16-SCU rows: sixteen lanes per CU stage the entries, whole rows go out below
-    if (PEER) {
-    for (int i = tid >> 4; i < ncu; i += kR2Threads / 16) {
+    // A group of lanes per CU, one SCU per lane and step: 16 groups of 16 lanes, or fewer and wider groups when the CTU has few (hence
+    // large) CUs - a 64x64 CU is written by all 256 threads at once.  (A thread per CU wrote up to 256 entries x 5 maps on its own at the
+    // kernel's tail: 4K pictures of 64x64 CUs took 316 us instead of ~125, of 16x16 CUs 86 instead of 76.)
+    const int lgg = ncu > 8 ? 4 : (ncu > 4 ? 3 : (ncu > 2 ? 2 : (ncu > 1 ? 1 : 0))), glanes = kR2Threads >> lgg;
+    for (int i = tid >> (8 - lgg); i < ncu; i += 1 << lgg) {
         const XB200_CU cu = s_cu[i];
+        if (DISP && (cu.flags & kCuOtherKernel)) continue;
         const int sx = cu.x >> 2, sy = cu.y >> 2, lnw = cu.log2w - 2, nw = 1 << lnw, nscu_cu = 1 << (cu.log2w + cu.log2h - 4);
         const bool intra = cu.mode == XB200_MODE_INTRA, ibc = cu.mode == XB200_MODE_IBC;
         uint32_t m = ((uint32_t)(cu.qp_map & 0x7f) << 16) | (1u << 31) | (intra ? 1u << 15 : 0u) | (ibc ? 1u << 26 : 0u);
@@ -837,14 +802,24 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (cu.flags & XB200_CUF_SKIP) m |= 1u << 23;
         const int2 mv = intra ? make_int2(0, 0) : make_int2(((const int *)cu.mv)[0], ((const int *)cu.mv)[1]);
         const int16_t rf = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
-        for (int q = tid & 15; q < nscu_cu; q += 16) {
-            const int y = q >> lnw, x = q & (nw - 1);
-            const uint8_t e = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
-            const int qq = ((sy + y) & 15) * 16 + ((sx + x) & 15);
-            sm_mv[qq] = mv; sm_scu[qq] = m; sm_refi[qq] = rf; sm_edge[qq] = e;
-        }
+        for (int q = tid & (glanes - 1); q < nscu_cu; q += glanes) {
+                const int y = q >> lnw, x = q & (nw - 1);
+                const uint8_t e = (uint8_t)(((x & 15) == 0 ? XB200_EDGE_LEFT : 0) | ((y & 15) == 0 ? XB200_EDGE_TOP : 0));
+                if (wide_maps) {
+                    const int qq = ((sy + y) & 15) * 16 + ((sx + x) & 15);
+                    sm_mv[qq] = mv; sm_scu[qq] = m; sm_refi[qq] = rf; sm_edge[qq] = e;
+                    continue;
+                }
+                const int p = (sy + y) * a.w_scu + sx + x;
+                const bool fo = a.peer_maps != 0;
+                xb_store_all(a, a.map_scu + p, m, fo);
+                xb_store_all(a, (int2 *)a.map_mv + p, mv, fo);
+                xb_store_all(a, (int2 *)a.map_unrefined_mv + p, mv, fo);
+                xb_store_all(a, (int16_t *)a.map_refi + p, rf, fo);
+                xb_store_all(a, a.map_edge + p, e, fo);
+            }
     }
-    {
+    if (wide_maps) {
         __syncthreads();
         const int rows = min(16, a.h_scu - (ctu_y >> 2));
         const int p0 = (ctu_y >> 2) * a.w_scu + (ctu_x >> 2);              // the CTU's 16 SCU columns all exist when w_scu % 16 == 0
@@ -858,7 +833,6 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             else if (k < 22) xb_store_all(a, (int4 *)((int16_t *)a.map_refi + p) + (k - 20), ((const int4 *)(sm_refi + r * 16))[k - 20]);
             else xb_store_all(a, (int4 *)(a.map_edge + p), *(const int4 *)(sm_edge + r * 16));
         }
-    }
     }
 }
 
