@@ -374,7 +374,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     // ---- descriptors: warp role = (luma block, Cb block, Cr block, tiles) x CU chunk, one CU per lane.  (One thread per CU doing all
     //      four in a row left seven warps waiting at the barrier below for ~6 % of the kernel's time.)
     const int role = warp & 3;
-    for (int ci = (warp >> 2) * 32 + lane; ci < ncu; ci += 64) {
+    // the 64 lanes of a role take one CU each, except the tile role when the CTU has few (hence large) CUs: then a group of lanes shares a
+    // CU and every lane builds one of its 16x16 tiles (the 16 tiles of a 64x64 CU were built by one thread, one after the other)
+    const int r_id = (warp >> 2) * 32 + lane;
+    const int lgt = role < 3 || ncu > 8 ? 6 : (ncu > 4 ? 3 : (ncu > 2 ? 2 : (ncu > 1 ? 1 : 0)));      // (with more CUs, spreading them over both warps of the role only costs issue slots)
+    const int t_lanes = 64 >> lgt, t_q = r_id & (t_lanes - 1);
+    for (int ci = r_id >> (6 - lgt); ci < ncu; ci += 1 << lgt) {
         const XB200_CU cu = s_cu[ci];
         if (DISP && (cu.flags & kCuOtherKernel)) continue;
         const bool inter_cu = !xb_wavefront_mode(cu.mode);
@@ -426,9 +431,10 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (use0 && use1 && a.ref_poc[0][cu.refi[0]] == a.ref_poc[1][cu.refi[1]] && mvc[0][0] == mvc[1][0] && mvc[0][1] == mvc[1][1])
             use1 = false;                 // identical motion -> list 0 only (xevd_mc.c:513-519)
         const int tw = min(w, 16), th = min(h, 16);
-        int t = of[6];
-        for (int ty = 0; ty < h; ty += 16)
-            for (int tx = 0; tx < w; tx += 16, t++) {
+        const int ltx = max(0, cu.log2w - 4), n_t = 1 << (ltx + max(0, cu.log2h - 4));
+        for (int kt = t_q; kt < n_t; kt += t_lanes) {
+            {
+                const int tx = (kt & ((1 << ltx) - 1)) << 4, ty = (kt >> ltx) << 4, t = of[6] + kt;
                 TileDesc td;
                 td.cu = (uint16_t)ci; td.px = (uint8_t)(lx + tx); td.py = (uint8_t)(ly + ty);
                 td.tw = (uint8_t)tw; td.th = (uint8_t)th; td.nl = (uint8_t)((use0 ? 1 : 0) + (use1 ? 1 : 0)); td.pad = 0;
@@ -455,6 +461,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     k++;
                 }
             }
+        }
         }
     }
     if (tid == 0) {         // end markers of the two prefix tables: [0..n_tuy) luma, [n_tuy] end, [n_tuy+1 .. n_tu+1) chroma, [n_tu+1] end
