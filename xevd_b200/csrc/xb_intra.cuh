@@ -91,46 +91,6 @@ __device__ void cu_plane_residual(const int16_t *__restrict__ coef, int lw, int 
 
 // xevd_get_nbr_b for one plane: up[-1 .. w+h), left[-1 .. h+w); unit = samples per SCU (4 luma, 2 chroma)
 // (cx, cy): position of the CU inside the CTU plane
-// element i of the 2 * (w + h) + 1 neighbour samples of one plane (the three planes of a CU are gathered by one joint loop, so that a
-// small CU keeps three warps busy for one pass instead of one warp for three)
-__device__ __forceinline__ void intra_gather_elem(const PlaneCtx &pc, int cx, int cy, int n, int ush, unsigned long long up_mask, unsigned long long left_mask,
-                                                  bool up_left, int dflt, int16_t *up, int16_t *left, int i)
-{
-    if (i == 2 * n) {
-        const int v = up_left ? pc.get(cx - 1, cy - 1) : dflt;
-        up[-1] = (int16_t)v; left[-1] = (int16_t)v;
-    } else if (i < n) {
-        up[i] = (int16_t)(((up_mask >> (i >> ush)) & 1) ? pc.get(cx + i, cy - 1) : dflt);
-    } else {
-        const int k = i - n;
-        left[k] = (int16_t)(((left_mask >> (k >> ush)) & 1) ? pc.get(cx - 1, cy + k) : dflt);
-    }
-}
-
-// xevd_ipred_b for one plane; modes IPD_DC_B 0, HOR 1, VER 2, UL 3, UR 4.  Split in two so that the three planes of a CU share
-// their barriers: the scalar of the mode (DC) by one warp per plane, then one joint sample loop over all planes.
-__device__ __forceinline__ void intra_scalars(int w, int h, int lw, int mode, const int16_t *up, const int16_t *left, int *scr, int lane)
-{
-    if (mode != 0) return;
-    // DC = (sum(left[0..h)) + sum(up[0..w)) + w) >> (log2 w + 1)
-    int acc = 0;
-    for (int i = lane; i < h; i += 32) acc += left[i];
-    for (int i = lane; i < w; i += 32) acc += up[i];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0) scr[0] = (acc + w) >> (lw + 1);
-}
-__device__ __forceinline__ int intra_px(int mode, int x, int y, const int16_t *up, const int16_t *left, const int *scr)
-{
-    switch (mode) {
-    case 0: return scr[0];
-    case 1: return left[y];
-    case 2: return up[x];
-    case 3: return y > x ? left[y - x - 1] : (y == x ? up[-1] : up[x - y - 1]);
-    default: return (up[x + y + 1] + left[x + y + 1]) >> 1;
-    }
-}
-
 // ---- Main profile (tool_eipd) ------------------------------------------------------------------------------------------
 // xevdm_get_nbr (src_main/xevdm_ipred.c:39-150): unavailable units repeat the last filled sample, scanning away from the
 // corner.  In closed form: the value at unit k is the sample itself when the unit is available, else the last sample of the
@@ -586,28 +546,43 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 break;
             }
             {
-                const int n0 = 2 * (w + h) + 1, n1 = 2 * (cw + ch) + 1;
-                for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
-                    const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2), sh = pl ? 1 : 0;
-                    intra_gather_elem(pc(pl), lx >> sh, ly >> sh, (w + h) >> sh, 2 - sh, ex.u.intra.up, ex.u.intra.left, ul, dflt, up(pl), le(pl),
-                                      k - (pl == 0 ? 0 : (pl == 1 ? n0 : n0 + n1)));
+                // Baseline modes (xevd_get_nbr_b + xevd_ipred_b): every sample is predicted straight from the on-chip neighbours - no
+                // gathered copy, no barrier before the samples are written (neighbours lie outside the CU, writes inside it).  The DC
+                // value is a warp-local reduction that every warp does for itself.  One barrier per CU instead of three.
+                const unsigned long long um = ex.u.intra.up, lm = ex.u.intra.left;
+                const int lane = tid & 31;
+                int dc0 = 0, dc1 = 0, dc2 = 0;
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++) {
+                    if ((pl ? cu.refi[1] : cu.refi[0]) != 0) continue;            // uniform
+                    const int sh = pl ? 1 : 0, wp = w >> sh, hp = h >> sh, cxp = lx >> sh, cyp = ly >> sh, ush = 2 - sh;
+                    const PlaneCtx c = pc(pl);
+                    int acc = 0;
+                    for (int i = lane; i < hp; i += 32) acc += ((lm >> (i >> ush)) & 1) ? c.get(cxp - 1, cyp + i) : dflt;
+                    for (int i = lane; i < wp; i += 32) acc += ((um >> (i >> ush)) & 1) ? c.get(cxp + i, cyp - 1) : dflt;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+                    const int v = (acc + wp) >> (cu.log2w - sh + 1);
+                    if (pl == 0) dc0 = v; else if (pl == 1) dc1 = v; else dc2 = v;
                 }
-            }
-            __syncthreads();
-            if (cu.refi[0] == 0 || cu.refi[1] == 0) {         // DC value of the planes that use it
-                if ((tid >> 5) < 3) {
-                    const int pl = tid >> 5;
-                    intra_scalars(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), (pl ? cu.refi[1] : cu.refi[0]), up(pl), le(pl), s_scr12 + 4 * pl, tid & 31);
+                for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
+                    const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
+                    const int sh = pl ? 1 : 0, lwp = cu.log2w - sh, wp = 1 << lwp, ush = 2 - sh;
+                    const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> sh, oy = ly >> sh;
+                    const PlaneCtx c = pc(pl);
+                    auto nb_up = [&](int i) -> int { return ((um >> (i >> ush)) & 1) ? c.get(ox + i, oy - 1) : dflt; };
+                    auto nb_le = [&](int i) -> int { return ((lm >> (i >> ush)) & 1) ? c.get(ox - 1, oy + i) : dflt; };
+                    int p;
+                    switch (pl ? cu.refi[1] : cu.refi[0]) {
+                    case 0: p = pl == 0 ? dc0 : (pl == 1 ? dc1 : dc2); break;
+                    case 1: p = nb_le(y); break;
+                    case 2: p = nb_up(x); break;
+                    case 3: p = y > x ? nb_le(y - x - 1) : (y == x ? (ul ? c.get(ox - 1, oy - 1) : dflt) : nb_up(x - y - 1)); break;
+                    default: p = (nb_up(x + y + 1) + nb_le(x + y + 1)) >> 1; break;
+                    }
+                    const int r = ((cu.cbf >> (4 * pl)) & 15) ? c.res[(oy + y) * c.Sp + ox + x] : 0;
+                    c.put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));          // xevd_recon: s16 wrap, then clip
                 }
-                __syncthreads();
-            }
-            for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
-                const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
-                const int lwp = cu.log2w - (pl ? 1 : 0), wp = 1 << lwp;
-                const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
-                const int p = intra_px((pl ? cu.refi[1] : cu.refi[0]), x, y, up(pl), le(pl), s_scr12 + 4 * pl);
-                const int r = ((cu.cbf >> (4 * pl)) & 15) ? pc(pl).res[(oy + y) * pc(pl).Sp + ox + x] : 0;
-                pc(pl).put(ox + x, oy + y, xb_clip3(0, maxv, (int16_t)(p + r)));          // xevd_recon: s16 wrap, then clip
             }
             __syncthreads();         // the next CU reads these samples from shared memory
             } while (0);
