@@ -86,6 +86,7 @@ typedef struct {
     ORC_PIC *pic;
     const int *cq[2];        /* chroma QP mapping for qp >= 0 (58 entries each); identity below 0 */
     uint8_t *cod;
+    int planes;              /* XB200_CUF_LUMA | XB200_CUF_CHROMA of the CU being visited (tree_cons, xevdm_df.c:155-160,245-250) */
 } DfCtx;
 
 static int chroma_map(const DfCtx *c, int k, int q) { return q < 0 ? q : c->cq[k][q]; }
@@ -99,10 +100,11 @@ static void edge_segment(DfCtx *c, int cur, int nb, int x, int y, int vertical)
                                    DF_MV(p) + 4 * cur, DF_MV(p) + 4 * nb);
     const int qp = (p->map_scu[cur] >> 16) & 0x7f;                       /* QP of the CURRENT side only (T7) */
     const int st = st_lookup(cls, qp) << (bdl - 8);
-    if (st) {
+    if (st && (c->planes & XB200_CUF_LUMA)) {
         pel *q = p->y + y * p->s_l + x;
         for (int i = 0; i < 4; i++) vertical ? filt_luma(q + i * p->s_l, 1, st, (1 << bdl) - 1) : filt_luma(q + i, p->s_l, st, (1 << bdl) - 1);
     }
+    if (!(c->planes & XB200_CUF_CHROMA)) return;
     const int qu = orc_clip3(-6 * (bdc - 8), 57, qp + c->prm->qp_u_offset), qv = orc_clip3(-6 * (bdc - 8), 57, qp + c->prm->qp_v_offset);
     const int st_u = st_lookup(cls, chroma_map(c, 0, qu)) << (bdc - 8), st_v = st_lookup(cls, chroma_map(c, 1, qv)) << (bdc - 8);
     for (int k = 0; k < 2; k++) {
@@ -138,6 +140,7 @@ int orc_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
         memset(c.cod, 0, (size_t)pic->w_scu * pic->h_scu);
         for (int n = 0; n < n_cu; n++) {
             const int w = 1 << cus[n].log2w, h = 1 << cus[n].log2h;
+            c.planes = cus[n].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA);
             if (pass == 0 && w > 64) { visit(&c, cus[n].x, cus[n].y, w >> 1, h, pass); visit(&c, cus[n].x + 64, cus[n].y, w >> 1, h, pass); }
             else if (pass == 1 && h > 64) { visit(&c, cus[n].x, cus[n].y, w, h >> 1, pass); visit(&c, cus[n].x, cus[n].y + 64, w, h >> 1, pass); }
             else visit(&c, cus[n].x, cus[n].y, w, h, pass);
@@ -178,6 +181,7 @@ typedef struct {
     const int *ref_id[2];        /* identity of the picture behind (list, refi) */
     uint8_t *cod;
     uint8_t *ats;                /* mctx->map_ats_inter: non-zero on the SCUs of ats_inter CUs (tool_ats) */
+    int planes;                  /* XB200_CUF_LUMA | XB200_CUF_CHROMA of the CU being visited (tree_cons, xevdm_df.c:916-920,986-997) */
 } AddbCtx;
 
 static int addb_index(int qp, int offset) { return orc_clip3(0, 51, (int)(uint8_t)qp + (int)(uint8_t)offset); }
@@ -267,8 +271,9 @@ static void addb_segment(AddbCtx *c, int cur, int nb, int x, int y, int vertical
     int alpha = (uint16_t)(k_alpha[ia] << scale), beta = (uint8_t)(k_beta[ib] << scale);
     int c1 = (uint8_t)(k_clip[ia][bs] << orc_max(0, bdl - 9));
     pel *q = p->y + y * p->s_l + x;
-    for (int i = 0; i < 4; i++) vertical ? addb_line_luma(q + i * p->s_l, 1, bs, alpha, beta, c1, bdl) : addb_line_luma(q + i, p->s_l, bs, alpha, beta, c1, bdl);
-    for (int k = 0; k < 2; k++) {
+    for (int i = 0; i < 4 && (c->planes & XB200_CUF_LUMA); i++)
+        vertical ? addb_line_luma(q + i * p->s_l, 1, bs, alpha, beta, c1, bdl) : addb_line_luma(q + i, p->s_l, bs, alpha, beta, c1, bdl);
+    for (int k = 0; k < 2 && (c->planes & XB200_CUF_CHROMA); k++) {
         const int qc = orc_clip3(-6 * (bdc - 8), 57, qp + (k ? prm->qp_v_offset : prm->qp_u_offset));
         const int qm = qc < 0 ? qc : c->cq[k][qc];
         ia = addb_index(qm, prm->deblock_alpha_offset); ib = addb_index(qm, prm->deblock_beta_offset);
@@ -311,6 +316,7 @@ int orc_deblock_frame_addb(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU
         memset(c.cod, 0, (size_t)pic->w_scu * pic->h_scu);
         for (int n = 0; n < n_cu; n++) {
             const int w = 1 << cus[n].log2w, h = 1 << cus[n].log2h;
+            c.planes = cus[n].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA);
             if (pass == 0 && w > 64) { addb_visit(&c, cus[n].x, cus[n].y, w >> 1, h, pass); addb_visit(&c, cus[n].x + 64, cus[n].y, w >> 1, h, pass); }
             else if (pass == 1 && h > 64) { addb_visit(&c, cus[n].x, cus[n].y, w, h >> 1, pass); addb_visit(&c, cus[n].x, cus[n].y + 64, w, h >> 1, pass); }
             else addb_visit(&c, cus[n].x, cus[n].y, w, h, pass);

@@ -87,7 +87,16 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         pel *py = pred, *pu = pred + w * h, *pv = pu + cw * ch;
         int16_t *ry = res, *ru = res + w * h, *rv = ru + cw * ch;
         const int16_t *c = coef + cu->coef_off;
-        const int has_y = (cu->cbf & 0x00f) != 0, has_u = (cu->cbf & 0x0f0) != 0, has_v = (cu->cbf & 0xf00) != 0;
+        /* local dual tree (src_main/xevdm.c:1828-1846): a TREE_L CU carries luma only, the TREE_C CU that follows its siblings chroma only;
+         * every per-plane step of xevd_recon_unit is gated by xevd_check_luma / xevd_check_chroma (:611-640,1344-1391, xevdm_recon.c:135-150).
+         * The coefficient stream of such a CU holds the blocks of its own planes only. */
+        const int do_l = (cu->flags & XB200_CUF_LUMA) != 0, do_c = (cu->flags & XB200_CUF_CHROMA) != 0;
+        const int has_y = do_l && (cu->cbf & 0x00f) != 0, has_u = do_c && (cu->cbf & 0x0f0) != 0, has_v = do_c && (cu->cbf & 0xf00) != 0;
+        if ((!do_l && !do_c) || (!(do_l && do_c) && cu->mode != XB200_MODE_INTRA && cu->mode != XB200_MODE_IBC) || (!do_l && cu->mode == XB200_MODE_IBC) ||
+            (!do_l && (cu->cbf & 0x00f)) || (!do_c && (cu->cbf & 0xff0))) {      /* cbf bits of planes the CU does not carry must be clear */
+            free(pred); free(res); free(dmvr_mv);
+            return XB200_ERR_INVALID_ARGUMENT;           /* inter CUs are always TREE_LC, IBC needs luma (xevdm.c:1113-1122) */
+        }
 
         /* plane blocks are padded to multiples of 8 coefficients (include/xevd_b200.h); an ats_inter CU carries only its TU */
         int tlw = cu->log2w, tlh = cu->log2h, txo = 0, tyo = 0;
@@ -123,7 +132,7 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             /* xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the current picture; chroma vector = luma >> 1 */
             const int bx = cu->mv[0][0], by = cu->mv[0][1];
             for (int i = 0; i < h; i++) memcpy(py + i * w, cur->y + (cu->y + by + i) * cur->s_l + cu->x + bx, sizeof(pel) * w);
-            for (int i = 0; i < ch; i++) {
+            for (int i = 0; i < ch && do_c; i++) {
                 memcpy(pu + i * cw, cur->u + ((cu->y >> 1) + (by >> 1) + i) * cur->s_c + (cu->x >> 1) + (bx >> 1), sizeof(pel) * cw);
                 memcpy(pv + i * cw, cur->v + ((cu->y >> 1) + (by >> 1) + i) * cur->s_c + (cu->x >> 1) + (bx >> 1), sizeof(pel) * cw);
             }
@@ -135,10 +144,12 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             memcpy(&ei, cu->mv[1], 4);
             const XB200_CU_EXT *e = &ext[ei];
             const int ul = (cu->avail >> 2) & 1;
-            orc_intra_neighbours(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, ul,
-                                 prm->bit_depth_luma, nb_up + 1, nb_le + 1);
-            orc_ipred_base(nb_le + 1, nb_up + 1, py, cu->refi[0], w, h);
-            for (int k = 0; k < 2; k++) {
+            if (do_l) {
+                orc_intra_neighbours(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, ul,
+                                     prm->bit_depth_luma, nb_up + 1, nb_le + 1);
+                orc_ipred_base(nb_le + 1, nb_up + 1, py, cu->refi[0], w, h);
+            }
+            for (int k = 0; k < 2 && do_c; k++) {
                 pel *pl = k ? cur->v : cur->u;
                 orc_intra_neighbours(pl + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, cw, ch, 2, e->u.intra.up, e->u.intra.left, ul,
                                      prm->bit_depth_luma, nb_up + 1, nb_le + 1);
@@ -152,10 +163,14 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             memcpy(&ei, cu->mv[1], 4);
             const XB200_CU_EXT *e = &ext[ei];
             const int ul = (cu->avail >> 2) & 1, lr = cu->avail & 3;
-            orc_intra_neighbours_main(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, e->u.intra.right, ul,
-                                      prm->bit_depth_luma, nb_up + 1, nb_le + 1, nb_ri + 1);
-            orc_ipred_main(nb_le + 1, nb_up + 1, nb_ri + 1, lr, py, cu->refi[0], w, h, prm->bit_depth_luma);
-            for (int k = 0; k < 2; k++) {
+            if (do_l) {
+                orc_intra_neighbours_main(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, 4, e->u.intra.up, e->u.intra.left, e->u.intra.right, ul,
+                                          prm->bit_depth_luma, nb_up + 1, nb_le + 1, nb_ri + 1);
+                orc_ipred_main(nb_le + 1, nb_up + 1, nb_ri + 1, lr, py, cu->refi[0], w, h, prm->bit_depth_luma);
+            }
+            /* a TREE_C CU takes ipm[0] (the DM mode) from map_ipm at its luma position, IPD_DC when that SCU is not intra
+             * (src_main/xevdm.c:1081-1092): host derivation, delivered in refi[0] like any other CU's */
+            for (int k = 0; k < 2 && do_c; k++) {
                 pel *pl = k ? cur->v : cur->u;
                 orc_intra_neighbours_main(pl + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, cw, ch, 2, e->u.intra.up, e->u.intra.left,
                                           e->u.intra.right, ul, prm->bit_depth_luma, nb_up + 1, nb_le + 1, nb_ri + 1);
@@ -165,14 +180,16 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             free(pred); free(res); free(dmvr_mv);
             return XB200_ERR_UNSUPPORTED;
         }
-        put_block_tu(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma, txo, tyo, tw, th);
+        if (do_l) put_block_tu(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, py, has_y ? ry : NULL, w, h, prm->bit_depth_luma, txo, tyo, tw, th);
         /* the reference passes the LUMA bit depth to all three planes (xevd_recon.c:70-91) */
-        put_block_tu(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
-        put_block_tu(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
+        if (do_c) put_block_tu(cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pu, has_u ? ru : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
+        if (do_c) put_block_tu(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
         /* Main tool_htdf (src_main/xevdm.c:1381-1391): luma post-filter of CUs with a luma residual and of every intra CU, slice QP */
         if (prm->tool_htdf && cu->mode != XB200_MODE_IBC && (has_y || cu->mode == XB200_MODE_INTRA) && (cu->flags & XB200_CUF_LUMA))
             orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma);
-        publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL, aff);
+        /* xevdm_set_dec_info writes the maps of luma-carrying CUs only (src_main/xevdm_util.c:4241); a TREE_C CU leaves what its luma
+         * siblings published (its COD bits are already set) */
+        if (do_l) publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL, aff);
     }
     free(pred); free(res); free(dmvr_mv);
     return XB200_OK;

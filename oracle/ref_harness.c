@@ -214,38 +214,42 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             xevdm_sub_block_itdq(g_ctx, s->coef, cu->log2w, cu->log2h, cu->qp_y, cu->qp_u, cu->qp_v, is_coef, nnz_sub,
                                  prm->tool_iqt, ats_intra_cu, ats_mode, ats_inter_info, prm->bit_depth_luma, prm->chroma_format_idc);
         const int scup = (cu->y >> 2) * cur->w_scu + (cu->x >> 2);
+        /* local dual tree (src_main/xevdm.c:1828-1846,1908-1927): TREE_L CUs carry luma only, the TREE_C CU that follows them chroma only */
+        const int do_l = (cu->flags & XB200_CUF_LUMA) != 0, do_c = (cu->flags & XB200_CUF_CHROMA) != 0;
+        const TREE_CONS tcu = { FALSE, do_l && do_c ? TREE_LC : (do_l ? TREE_L : TREE_C), do_l && do_c ? eAll : eOnlyIntra };
+        if (!do_l && !do_c) { free(s); free(map_scu); free(map_tidx); return XB200_ERR_INVALID_ARGUMENT; }
         if (cu->mode == XB200_MODE_INTRA && !prm->tool_eipd) {
             /* xevd_recon_unit intra branch (src_base/xevd.c:732-741) with the reference's own availability logic */
             const u16 avail_cu = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
             const int bdl = prm->bit_depth_luma;
-            xevd_get_nbr_b(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
+            /* get_nbr_yuv and the prediction calls are gated by xevd_check_luma / xevd_check_chroma (src_main/xevdm.c:611-640,1362-1376) */
+            if (do_l) xevd_get_nbr_b(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
                            Y_C, 0, map_tidx, bdl, 1);
-            xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+            if (do_c) xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
                            cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
-            xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+            if (do_c) xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
                            cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
-            xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
-            xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
-            xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
+            if (do_l) xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
+            if (do_c) xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
+            if (do_c) xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
         } else if (cu->mode == XB200_MODE_IBC) {
             XEVD_PIC cp;
-            TREE_CONS tc = { FALSE, TREE_LC, eAll };
             wrap_pic(cur, &cp);
-            xevdm_IBC_mc(cu->x, cu->y, cu->log2w, cu->log2h, mv[0], &cp, s->pred[0], tc, prm->chroma_format_idc);
+            xevdm_IBC_mc(cu->x, cu->y, cu->log2w, cu->log2h, mv[0], &cp, s->pred[0], tcu, prm->chroma_format_idc);
         } else if (cu->mode == XB200_MODE_INTRA) {
             /* Main-profile intra branch of xevd_recon_unit (src_main/xevdm.c:1344-1361) with the reference's own availability logic */
             const u16 avail_cu = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
             const u16 avail_lr = xevd_check_nev_avail(cu->x >> 2, cu->y >> 2, w, h, cur->w_scu, cur->h_scu, map_scu, map_tidx);
             const int bdl = prm->bit_depth_luma, bdc = prm->bit_depth_chroma;
-            xevdm_get_nbr(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
+            if (do_l) xevdm_get_nbr(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
                           Y_C, 0, map_tidx, bdl, 1);
-            xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+            if (do_c) xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
                           cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
-            xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
+            if (do_c) xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
                           cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
-            xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
-            xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
-            xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
+            if (do_l) xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
+            if (do_c) xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
+            if (do_c) xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
         } else if (cu->mode == XB200_MODE_AFFINE) {
             /* xevdm_affine_mc (src_main/xevdm_mc.c:2606) + the per-SCU vectors of xevdm_set_affine_mvf (src_main/xevdm_util.c:4095) */
             static pel eif_tmp[(MAX_CU_SIZE + 2) * (MAX_CU_SIZE + 2)];
@@ -303,10 +307,10 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
         if (prm->tool_ats || prm->tool_htdf) {
             /* Main profile: xevdm_recon_yuv (src_main/xevdm_recon.c:128-151), which places the ats_inter TU */
-            xevdm_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, ats_inter_info, prm->bit_depth_luma);
-            xevdm_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
-            xevdm_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
-            if (cu->mode != XB200_MODE_IBC && prm->tool_htdf && (is_coef[Y_C] || cu->mode == XB200_MODE_INTRA)) {
+            if (do_l) xevdm_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, ats_inter_info, prm->bit_depth_luma);
+            if (do_c) xevdm_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
+            if (do_c) xevdm_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), ats_inter_info, prm->bit_depth_luma);
+            if (cu->mode != XB200_MODE_IBC && prm->tool_htdf && (is_coef[Y_C] || cu->mode == XB200_MODE_INTRA) && do_l) {
                 /* src_main/xevdm.c:1381-1391; the COD bits of this CU are cleared around the call as they are in the decoder */
                 u16 av;
                 for (l = 0; l < (h >> 2); l++) for (i = 0; i < (w >> 2); i++) MCU_CLR_COD(map_scu[scup + l * cur->w_scu + i]);
@@ -318,9 +322,9 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             continue;
         }
         /* xevd_recon_yuv (src_base/xevd_recon.c:70-91) */
-        g_ctx->fn_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, prm->bit_depth_luma);
-        g_ctx->fn_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
-        g_ctx->fn_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
+        if (do_l) g_ctx->fn_recon(s->coef[Y_C], s->pred[0][Y_C], is_coef[Y_C], w, h, cur->s_l, cur->y + cu->y * cur->s_l + cu->x, prm->bit_depth_luma);
+        if (do_c) g_ctx->fn_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
+        if (do_c) g_ctx->fn_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
     }
     free(s); free(map_scu); free(map_tidx);
     return XB200_OK;
@@ -390,6 +394,10 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
         for (i = 0; i < f_scu; i++) MCU_CLR_COD(map_scu[i]);
         for (n = 0; n < n_cu; n++) {
             const int x = cus[n].x, y = cus[n].y, w = 1 << cus[n].log2w, h = 1 << cus[n].log2h;
+            /* deblock_tree visits the TREE_L leaves, then the parent block once more as TREE_C (src_main/xevdm.c:1991-1998) */
+            const int do_l = (cus[n].flags & XB200_CUF_LUMA) != 0, do_c = (cus[n].flags & XB200_CUF_CHROMA) != 0;
+            tc.tree_type = do_l && do_c ? TREE_LC : (do_l ? TREE_L : TREE_C);
+            tc.mode_cons = do_l && do_c ? eAll : eOnlyIntra;
             if (pass == 0) {
                 const int parts = w > MAX_TR_SIZE ? 2 : 1;
                 for (i = 0; i < parts; i++)

@@ -136,6 +136,25 @@ def test_reference_index_outside_lists_is_rejected(ctx):
         p.free()
 
 
+@pytest.mark.parametrize("keep", [1, 2])
+def test_dual_tree_cu_is_refused(ctx, keep):
+    """a luma-only (TREE_L) or chroma-only (TREE_C) CU, src_main/xevdm.c:1828-1846: the kernels have no per-plane path yet, so the
+    host entry point says XB200_ERR_UNSUPPORTED instead of reconstructing three planes"""
+    from xevd_b200.device import XevdB200Error
+    from xevd_b200 import abi
+    w, h, bd = 128, 64, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="A", seed=73, n_refs=1)
+    cl.cus["flags"][3] = (int(cl.cus["flags"][3]) & ~3) | keep
+    refs = synth.make_refs(w, h, bd, 1, seed=74)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    with pytest.raises(XevdB200Error) as e:
+        ctx.recon_frame(prm, cur, drefs, drefs, cl)
+    assert e.value.code == abi.XB200_ERR_UNSUPPORTED
+    for p in drefs + [cur]:
+        p.free()
+
+
 @pytest.mark.parametrize("variant,log2_cu,bd,intra_frac", [("B", 4, 10, 1.0), ("A", 2, 10, 1.0), ("B", 4, 8, 0.4), ("A", 6, 10, 1.0), ("A", 3, 10, 0.5)])
 @pytest.mark.parametrize("force", ["0", "1"])
 def test_intra_baseline(oracle, monkeypatch, variant, log2_cu, bd, intra_frac, force):

@@ -279,6 +279,58 @@ def test_deblock_main_partitions(oracle, reference, kw, bd, addb):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
+def dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac=1.0):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.7, **kw)
+    prm.tool_eipd, prm.tool_htdf, prm.slice_qp = eipd, htdf, 37
+    synth.split_local_dual_tree(cl, np.random.default_rng(5), 0.6)
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=bool(eipd))
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    fl = cl.cus["flags"] & 3
+    assert (fl == 1).sum() > 8 and (fl == 2).sum() > 3, "test picture has no dual-tree groups"
+    return w, h, prm, cl, synth.make_refs(w, h, bd, 2, seed=9)
+
+
+DUAL_TREE_CASES = [("C", {}, 10, 0, 0, 1.0), ("C", {}, 10, 1, 0, 1.0), ("C", dict(log2_ctu=5), 8, 1, 1, 1.0), ("A", dict(log2_cu=3), 10, 1, 1, 1.0),
+                   ("C", dict(suco=False), 12, 0, 0, 0.5), ("C", dict(log2_ctu=7), 10, 1, 1, 0.4)]
+
+
+@pytest.mark.parametrize("variant,kw,bd,eipd,htdf,intra_frac", DUAL_TREE_CASES)
+def test_recon_frame_dual_tree(oracle, reference, variant, kw, bd, eipd, htdf, intra_frac):
+    """local dual tree (src_main/xevdm.c:1828-1846,1908-1927): luma-only leaves followed by one chroma-only CU over the node; every
+    per-plane step gated by xevd_check_luma / xevd_check_chroma, maps written by the luma leaves only, HTDF on luma CUs only"""
+    w, h, prm, cl, refs = dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    # the planes a dual-tree CU does not carry are untouched by it: dropping the chroma-only CUs changes chroma only
+    keep = (cl.cus["flags"] & 3) != 2
+    assert keep.sum() < len(cl.cus)
+
+
+@pytest.mark.parametrize("bd,addb", [(10, 0), (10, 1), (8, 0), (12, 1)])
+def test_deblock_dual_tree(oracle, reference, bd, addb):
+    """deblock_tree visits the luma leaves as TREE_L and then the node as TREE_C (src_main/xevdm.c:1991-1998): inner leaf edges are
+    filtered in luma only, the node's outline in chroma once (xevdm_df.c:155-160,245-250,916-920,986-997)"""
+    w, h, prm, cl, refs = dual_tree_inputs("C", {}, bd, 1, 0, 0.6)
+    rng = np.random.default_rng(300 + bd + addb)
+    prm.tool_addb = addb
+    prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
+    base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl in base.planes():
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
+    synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)
+    tbl, ids = synth.chroma_qp_table(True), ((0, 1), (1, 0))
+    a = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    b = reference.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    changed = sum(int((x != y).sum()) for x, y in zip(a.planes(), base.planes()))
+    assert changed > 300, "test picture does not exercise the filter"
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
 IBC_CASES = [("C", {}, 10, 0.3), ("C", dict(log2_ctu=7), 10, 0.3), ("C", dict(log2_ctu=5), 8, 0.5), ("B", {}, 10, 0.0), ("A", dict(log2_cu=3), 10, 0.2)]
 
 

@@ -576,6 +576,9 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     };
     int has_intra = 0, max_cu = 0, any_l1 = 0;
     for (int i = 0; i < n_cu; i++) {
+        // local dual tree (TREE_L / TREE_C CUs, src_main/xevdm.c:1828-1846): the kernels reconstruct all three planes of every CU, so a
+        // luma-only or chroma-only CU would come out wrong; refuse it instead
+        if ((cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA)) != (XB200_CUF_LUMA | XB200_CUF_CHROMA)) return XB200_ERR_UNSUPPORTED;
         const bool intra = xb_wavefront_mode(cus[i].mode);
         has_intra |= intra || (prm->tool_htdf && (cus[i].cbf & 15));       // HTDF-filtered inter CUs are finished by the wavefront kernel too
         if (intra) continue;

@@ -306,6 +306,77 @@ def randomize_deblock_maps(pic: HostPicture, cl: CuList, rng, intra_frac=0.1, qp
     return pic
 
 
+def split_local_dual_tree(cl: CuList, rng, frac: float = 0.5):
+    """Local dual tree (Main, 4:2:0): where a split would leave chroma blocks narrower than 4 samples the decoder switches the
+    node to intra-only, codes the split's leaves as luma-only CUs (TREE_L) and then the whole node once more as ONE chroma-only
+    CU (TREE_C) (xevd_entropy_dec_tree / xevd_recon_tree, src_main/xevdm.c:1775-1846,1872-1927).  Turns a fraction of the CUs whose
+    short side is 8 into such groups: luma leaves of 4 x N / N x 4 (halves; an 8x8 node may also quarter), flags = CUF_LUMA, then
+    the node itself with flags = CUF_CHROMA.  Call BEFORE add_intra_cus (which makes every such CU intra and derives the
+    chroma CU's DM mode from the luma leaf at the node's centre).  Coefficient blocks of a dual-tree CU hold its own planes only."""
+    a8 = lambda v: (v + 7) & ~7
+    old, coef_old = cl.cus, cl.coef
+    rows, blocks, off = [], [], 0
+    remap = {}
+
+    def levels(n):
+        v = rng.integers(-6, 7, n) * (rng.random(n) < 0.15)
+        v[0] = int(rng.integers(-60, 61))
+        out = np.zeros(a8(n), np.int16)
+        out[:n] = v
+        return out
+
+    def emit(cu, block):
+        nonlocal off
+        cu = cu.copy()
+        cu["coef_off"] = off
+        rows.append(cu)
+        blocks.append(block)
+        off += len(block)
+
+    for i in range(len(old)):
+        remap[i] = len(rows)
+        cu = old[i]
+        lw, lh = int(cu["log2w"]), int(cu["log2h"])
+        n = 1 << (lw + lh)
+        coded = int(cu["cbf"]) != 0
+        own = coef_old[int(cu["coef_off"]):int(cu["coef_off"]) + (a8(n) + 2 * a8(n // 4) if coded else 0)]
+        ats_inter = (int(cu["ats"]) >> 2) & 7
+        if min(lw, lh) != 3 or max(lw, lh) > 4 or ats_inter or rng.random() >= frac:
+            emit(cu, own)
+            continue
+        x, y = int(cu["x"]), int(cu["y"])
+        if lw == 3 and lh == 3:
+            kind = ("bv", "bh", "q")[int(rng.integers(0, 3))]
+        else:
+            kind = "bv" if lw == 3 else "bh"
+        if kind == "bv":
+            leaves = [(x, y, 2, lh), (x + 4, y, 2, lh)]
+            if rng.random() < 0.5:
+                leaves = leaves[::-1]                  # SUCO: right child first
+        elif kind == "bh":
+            leaves = [(x, y, lw, 2), (x, y + 4, lw, 2)]
+        else:
+            leaves = [(x, y, 2, 2), (x + 4, y, 2, 2), (x, y + 4, 2, 2), (x + 4, y + 4, 2, 2)]
+        for (lx, ly, llw, llh) in leaves:
+            c = cu.copy()
+            c["x"], c["y"], c["log2w"], c["log2h"] = lx, ly, llw, llh
+            c["flags"] = (int(cu["flags"]) & ~CUF_CHROMA) | CUF_LUMA
+            c["ats"] = 0
+            has = rng.random() < 0.7
+            c["cbf"] = 1 if has else 0
+            emit(c, levels(1 << (llw + llh)) if has else np.zeros(0, np.int16))
+        c = cu.copy()
+        c["flags"] = (int(cu["flags"]) & ~CUF_LUMA) | CUF_CHROMA
+        c["ats"] = 0
+        c["cbf"] = int(cu["cbf"]) & 0xff0
+        emit(c, own[a8(n):] if coded else np.zeros(0, np.int16))
+    remap[len(old)] = len(rows)
+    cl.cus = np.array(rows, CU_DTYPE)
+    cl.coef = np.concatenate(blocks).astype(np.int16) if blocks else np.zeros(0, np.int16)
+    cl.ctu_first = np.array([remap[int(v)] for v in cl.ctu_first], np.uint32)
+    return cl
+
+
 def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, constrained: bool = False, eipd: bool = False,
                   ats_intra_frac: float = 0.0, ibc_frac: float = 0.0):
     """Turn a fraction of the CUs of a picture into intra CUs (Baseline modes 0..4 for luma and chroma) and derive their
@@ -320,6 +391,8 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     n = len(cus)
     w_scu, h_scu = (cl.w + 3) >> 2, (cl.h + 3) >> 2
     is_intra = (rng.random(n) < intra_frac) & (((cus["ats"] >> 2) & 7) == 0)       # ats_inter CUs stay inter
+    dual = (cus["flags"] & (CUF_LUMA | CUF_CHROMA)) != (CUF_LUMA | CUF_CHROMA)       # local dual tree: intra only (split_local_dual_tree)
+    is_intra |= dual
     if ats_intra_frac > 0:
         # ats_intra_cu (Main tool_ats): intra CUs of at most 32x32 with coded luma; ats mode = h << 1 | v (0 DST-7, 1 DCT-8)
         from .abi import CUF_ATS_INTRA
@@ -336,6 +409,7 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     ext = [np.zeros(1, EXT_DTYPE)[0]]
     cod = np.zeros((h_scu, w_scu), bool)
     intra_map = np.zeros((h_scu, w_scu), bool)
+    ipm_map = np.zeros((h_scu, w_scu), np.int8)
     from .abi import MODE_IBC
     ctu_scu = (1 << cl.log2_ctu) >> 2
     want_ibc = (~is_intra) & (((cus["ats"] >> 2) & 7) == 0) & (rng.random(n) < ibc_frac) if ibc_frac > 0 else np.zeros(n, bool)
@@ -360,6 +434,10 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
                     cu["mv"] = 0
                     cu["mv"][0] = (sx - x0, sy - y0)
                     break
+        if is_intra[i] and not (int(cu["flags"]) & CUF_LUMA):
+            # TREE_C CU: ipm[0] comes from map_ipm at the node's centre SCU, IPD_DC if that SCU is not intra (src_main/xevdm.c:1081-1092)
+            yc, xc = ys + (nh >> 1), xs + (nw >> 1)
+            cu["refi"][0] = ipm_map[yc, xc] if intra_map[yc, xc] else 0
         if is_intra[i]:
             ok = (lambda yy, xx: cod[yy, xx] and (not constrained or intra_map[yy, xx]))
             up = left = right = 0
@@ -379,7 +457,9 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
             cu["mv"][1] = np.frombuffer(np.uint32(len(ext)).tobytes(), np.int16)
             ext.append(e)
         cod[ys:ys + nh, xs:xs + nw] = True
-        intra_map[ys:ys + nh, xs:xs + nw] = is_intra[i]
+        if int(cu["flags"]) & CUF_LUMA:               # xevdm_set_dec_info publishes for luma-carrying CUs only (xevdm_util.c:4241)
+            intra_map[ys:ys + nh, xs:xs + nw] = is_intra[i]
+            ipm_map[ys:ys + nh, xs:xs + nw] = int(cu["refi"][0]) if is_intra[i] else 0
     cl.ext = np.array(ext, EXT_DTYPE)
     return cl
 
