@@ -62,6 +62,10 @@ typedef int16_t xb200_pel;           /* pel == s16 always (src_base/xevd_port.h:
 /* XB200_CU.flags */
 #define XB200_CUF_LUMA     0x01      /* CU carries luma   (tree_cons != TREE_C) */
 #define XB200_CUF_CHROMA   0x02      /* CU carries chroma (tree_cons != TREE_L) */
+/* Local dual tree (src_main/xevdm.c:1828-1846,1908-1927): the luma-only leaves of a node come first, then ONE chroma-only CU with the
+ * node's position and size, all in the decoding order of the list and all intra (leaves may be IBC).  Such a CU's coefficient blocks
+ * hold the planes it carries only, the cbf bits of the other planes are 0; a chroma-only CU delivers its DM luma mode (map_ipm at the
+ * node's centre, xevdm.c:1081-1092) in refi[0].  Per-SCU maps are published by the luma-carrying CUs (xevdm_util.c:4241).            */
 #define XB200_CUF_SKIP     0x04      /* MODE_SKIP: published to map_scu (MCU_SET_SF) */
 #define XB200_CUF_DMVR     0x08      /* DMVR enabled for this CU (Main) */
 #define XB200_CUF_ATS_INTRA 0x10     /* ats_intra_cu */
@@ -227,13 +231,17 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
                        const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,
                        const void *d_ext, int n_ext,
                        const void *d_coef, size_t n_coef, int has_intra, int max_cu_per_ctu);
-/* has_intra: non-zero when the wavefront pass is needed: the picture has intra or IBC CUs, or tool_htdf is on and some CU has a
+#define XB200_HAS_INTRA      1
+#define XB200_HAS_DUAL_TREE  2        /* some CU is luma-only / chroma-only: selects the per-plane owner path (with XB200_HAS_INTRA) */
+/* has_intra: XB200_HAS_* bits.  XB200_HAS_INTRA when the wavefront pass is needed: the picture has intra or IBC CUs, or tool_htdf is on and some CU has a
  * luma residual.  max_cu_per_ctu: upper bound of ctu_first[k+1]-ctu_first[k] (sizes on-chip work lists); 0 = unknown (worst case) */
 
 /* ---- picture-wide in-loop filters ------------------------------------------------------------------ */
 /* edge flags, one byte per SCU */
 #define XB200_EDGE_LEFT   0x01    /* a CU/TU boundary runs along the left side of this SCU           */
 #define XB200_EDGE_TOP    0x02    /* ... along the top side                                          */
+#define XB200_EDGE_LEFT_NOC 0x08  /* the left-side boundary is a luma edge only (inner leaf boundary of a local dual tree node) */
+#define XB200_EDGE_TOP_NOC  0x10  /* ... the top-side boundary                                                                   */
 #define XB200_EDGE_ATS    0x04    /* the SCU belongs to an ats_inter CU (mctx->map_ats_inter != 0): raises the Main
                                      deblocking strength to "coded" (xevdm_df.c:902-906,977-981)            */
 /* Both passes (vertical edges, then horizontal edges) over the whole picture, in place.  The per-SCU maps

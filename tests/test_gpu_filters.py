@@ -163,6 +163,33 @@ def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
 
 
+@pytest.mark.parametrize("bd,addb,kw", [(10, 0, {}), (10, 1, {}), (8, 0, dict(log2_ctu=5)), (12, 1, dict(log2_ctu=7))])
+def test_dual_tree_pipeline(ctx, oracle, bd, addb, kw):
+    """recon -> deblock -> pad of a picture with local dual tree nodes: the deblocking pass runs on the maps and the edge map the recon
+    kernels left on the device (inner leaf edges filtered in luma only, the node's outline in chroma; xevdm_df.c:155-160,245-250)"""
+    from tests.test_oracle_vs_ref import dual_tree_inputs
+    w, h, prm, cl, refs = dual_tree_inputs("C", kw, bd, 1, 0, 0.6)
+    prm.tool_addb = addb
+    prm.qp_u_offset, prm.qp_v_offset = 2, -3
+    tbl, ids = synth.chroma_qp_table(True), ((0, 1), (1, 0))
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    pre = want.copy()
+    oracle.deblock_frame(prm, want, cl, tbl, bool(addb), ids)
+    oracle.pad(want)
+    assert sum(int((x != y).sum()) for x, y in zip(want.planes(), pre.planes())) > 300
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.set_chroma_qp_table(tbl)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    ctx.deblock(prm, cur, drefs, drefs[::-1])
+    ctx.pad(cur)
+    got = cur.download_padded()
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+    for p in drefs + [cur]:
+        p.free()
+    assert np.array_equal(got.buf_y, want.buf_y) and np.array_equal(got.buf_u, want.buf_u) and np.array_equal(got.buf_v, want.buf_v)
+
+
 @pytest.mark.parametrize("use_dra,out_bits,crop", [(0, 16, (0, 0, 0, 0)), (1, 16, (0, 0, 0, 0)), (0, 8, (8, 16, 2, 6)), (1, 8, (4, 0, 0, 10)), (1, 16, (2, 2, 2, 2))])
 def test_output_path(ctx, oracle, use_dra, out_bits, crop):
     """SURVEY 8f N2 + N4: what xevd_pull hands out - DRA on a copy, SPS cropping window, optional 16 -> 8-bit conversion - in one kernel"""

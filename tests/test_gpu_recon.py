@@ -136,21 +136,45 @@ def test_reference_index_outside_lists_is_rejected(ctx):
         p.free()
 
 
-@pytest.mark.parametrize("keep", [1, 2])
-def test_dual_tree_cu_is_refused(ctx, keep):
-    """a luma-only (TREE_L) or chroma-only (TREE_C) CU, src_main/xevdm.c:1828-1846: the kernels have no per-plane path yet, so the
-    host entry point says XB200_ERR_UNSUPPORTED instead of reconstructing three planes"""
+@pytest.mark.parametrize("variant,kw,bd,eipd,htdf,intra_frac", [("C", {}, 10, 0, 0, 1.0), ("C", {}, 10, 1, 0, 1.0), ("C", dict(log2_ctu=5), 8, 1, 1, 1.0),
+                                                                ("A", dict(log2_cu=3), 10, 1, 1, 1.0), ("C", dict(suco=False), 12, 0, 0, 0.5),
+                                                                ("C", dict(log2_ctu=7), 10, 1, 1, 0.4), ("C", dict(iqt=True), 10, 1, 0, 0.3)])
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_dual_tree(oracle, monkeypatch, variant, kw, bd, eipd, htdf, intra_frac, force):
+    """local dual tree (src_main/xevdm.c:1828-1846): luma-only leaves + one chroma-only CU per node.  Planes, per-SCU maps (published by
+    the luma leaves only) and the edge map (inner leaf edges luma-only) against the oracle, through the per-CU dispatch (64x64 CTUs:
+    dual-tree CUs in the generic kernel, the rest in the throughput kernel) and through the generic kernel alone"""
+    from xevd_b200.device import Context
+    from tests.test_oracle_vs_ref import dual_tree_inputs
+    monkeypatch.setenv("XB200_FORCE_GENERIC", force)
+    c = Context(0)
+    w, h, prm, cl, refs = dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [c.pic_alloc(w, h).upload(r) for r in refs]
+    cur = c.pic_alloc(w, h)
+    c.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    edge = cur.download_edge_map()
+    c.close()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+    assert np.array_equal(edge, cl.edge_flags())
+
+
+def test_dual_tree_inter_cu_is_refused(ctx):
+    """an inter CU is always TREE_LC (xevdm.c:1122): one flagged luma-only is a caller error, not something to reconstruct"""
     from xevd_b200.device import XevdB200Error
     from xevd_b200 import abi
     w, h, bd = 128, 64, 10
     prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="A", seed=73, n_refs=1)
-    cl.cus["flags"][3] = (int(cl.cus["flags"][3]) & ~3) | keep
+    cl.cus["flags"][3] = (int(cl.cus["flags"][3]) & ~3) | 1
     refs = synth.make_refs(w, h, bd, 1, seed=74)
     drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
     cur = ctx.pic_alloc(w, h)
     with pytest.raises(XevdB200Error) as e:
         ctx.recon_frame(prm, cur, drefs, drefs, cl)
-    assert e.value.code == abi.XB200_ERR_UNSUPPORTED
+    assert e.value.code == abi.XB200_ERR_INVALID_ARGUMENT
     for p in drefs + [cur]:
         p.free()
 

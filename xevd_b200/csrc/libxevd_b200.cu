@@ -461,7 +461,7 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     // throughput kernel (xb_recon2.cuh): 64x64 CTUs, Baseline or IQT transform; with ATS / DMVR / affine enabled it takes the CTUs that hold
     // no such CU and the generic kernel (xb_recon.cuh) the others
     const bool fast = a.log2_ctu == 6 && !c->force_generic;
-    const bool mixed = fast && (a.ats || a.dmvr || a.affine);
+    const bool mixed = fast && (a.ats || a.dmvr || a.affine || (has_intra & XB200_HAS_DUAL_TREE));     // dual-tree CUs need per-plane owners
     a.dispatch = mixed ? 1 : 0;
     if (a.n_peer > 0 && (!fast || mixed || a.iqt)) return XB200_ERR_UNSUPPORTED;        // peer stores exist in the throughput kernel only; use the all-gather exchange
     if (((uintptr_t)d_coef & 15) || ((uintptr_t)d_cus & 15)) return XB200_ERR_INVALID_ARGUMENT;   // 16-byte vector / bulk-copy access
@@ -576,11 +576,16 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     };
     int has_intra = 0, max_cu = 0, any_l1 = 0;
     for (int i = 0; i < n_cu; i++) {
-        // local dual tree (TREE_L / TREE_C CUs, src_main/xevdm.c:1828-1846): the kernels reconstruct all three planes of every CU, so a
-        // luma-only or chroma-only CU would come out wrong; refuse it instead
-        if ((cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA)) != (XB200_CUF_LUMA | XB200_CUF_CHROMA)) return XB200_ERR_UNSUPPORTED;
         const bool intra = xb_wavefront_mode(cus[i].mode);
-        has_intra |= intra || (prm->tool_htdf && (cus[i].cbf & 15));       // HTDF-filtered inter CUs are finished by the wavefront kernel too
+        // local dual tree (TREE_L / TREE_C CUs, src_main/xevdm.c:1828-1846): intra-only nodes; inter CUs always carry all three planes and
+        // IBC needs luma (xevdm.c:1113-1122); the cbf bits of a plane the CU does not carry must be clear (its coefficient block is absent)
+        const int pl = cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA);
+        if (pl != (XB200_CUF_LUMA | XB200_CUF_CHROMA)) {
+            if (!pl || !intra || (cus[i].mode == XB200_MODE_IBC && !(pl & XB200_CUF_LUMA))) return XB200_ERR_INVALID_ARGUMENT;
+            if ((!(pl & XB200_CUF_LUMA) && (cus[i].cbf & 0x00f)) || (!(pl & XB200_CUF_CHROMA) && (cus[i].cbf & 0xff0))) return XB200_ERR_INVALID_ARGUMENT;
+            has_intra |= XB200_HAS_DUAL_TREE;
+        }
+        has_intra |= (intra || (prm->tool_htdf && (cus[i].cbf & 15))) ? XB200_HAS_INTRA : 0;       // HTDF-filtered inter CUs are finished by the wavefront kernel too
         if (intra) continue;
         any_l1 |= cus[i].refi[1] >= 0;
         // a reference index outside the lists the caller supplied would dereference a missing picture on the device

@@ -137,6 +137,13 @@ __device__ __forceinline__ bool dbk_has_edge(const DbkArgs &a, int sx, int sy, b
     return sy > 0 && (a.map_edge[sy * a.w_scu + sx] & XB200_EDGE_TOP);
 }
 
+// chroma edges: the inner leaf boundaries of a local dual tree node are luma edges only (XB200_EDGE_*_NOC; xevdm_df.c:155-160,245-250)
+__device__ __forceinline__ bool dbk_has_edge_c(const DbkArgs &a, int sx, int sy, bool vertical)
+{
+    if (vertical) return sx > 0 && (a.map_edge[sy * a.w_scu + sx] & (XB200_EDGE_LEFT | XB200_EDGE_LEFT_NOC)) == XB200_EDGE_LEFT;
+    return sy > 0 && (a.map_edge[sy * a.w_scu + sx] & (XB200_EDGE_TOP | XB200_EDGE_TOP_NOC)) == XB200_EDGE_TOP;
+}
+
 // strengths of one segment: luma, Cb, Cr.  QP is the one of the CURRENT (right / lower) SCU only (xevd_df.c:347,446; T7)
 __device__ __forceinline__ void dbk_strengths(const DbkArgs &a, int cur, int nb, int &st, int &st_u, int &st_v)
 {
@@ -185,8 +192,9 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
         }
     }
     // chroma: only the head of a run of consecutive segments works; it walks the run in the reference's order
+    if (!dbk_has_edge_c(a, sx, sy, VERTICAL)) return;
     const int psx = VERTICAL ? sx - 1 : sx, psy = VERTICAL ? sy : sy - 1;
-    if (dbk_has_edge(a, psx, psy, VERTICAL)) return;
+    if (dbk_has_edge_c(a, psx, psy, VERTICAL)) return;
     int cx = sx, cy = sy;
     while (true) {
         const int c2 = cy * a.w_scu + cx, n2 = VERTICAL ? c2 - 1 : c2 - a.w_scu;
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
             }
         }
         if (VERTICAL) { cx++; if (cx >= a.w_scu) break; } else { cy++; if (cy >= a.h_scu) break; }
-        if (!dbk_has_edge(a, cx, cy, VERTICAL)) break;
+        if (!dbk_has_edge_c(a, cx, cy, VERTICAL)) break;
     }
 }
 

@@ -485,12 +485,15 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             // inter CUs are reconstructed by the inter kernel; only the in-order HTDF pass below is left for them
             if (xb_wavefront_mode(cu.mode)) do {
             const int w = 1 << cu.log2w, h = 1 << cu.log2h, cw = w >> 1, ch = h >> 1;
+            // local dual tree: a TREE_L leaf carries luma only, the TREE_C CU after its siblings the chroma of the whole node; every
+            // per-plane step of xevd_recon_unit is gated by xevd_check_luma / xevd_check_chroma (xevdm.c:611-640,1344-1391)
+            const bool do_l = cu.flags & XB200_CUF_LUMA, do_c = cu.flags & XB200_CUF_CHROMA;          // uniform
             if (cu.mode == XB200_MODE_IBC) {
                 // xevdm_IBC_mc (src_main/xevdm_mc.c:2040-2106): whole-sample copy from the already reconstructed part of the CURRENT
                 // picture (block vector mv[0], chroma vector = luma >> 1), then xevdm_recon.  Conforming vectors stay inside the
                 // current CTU row at or left of this CTU: samples of this CTU come from shared memory, older ones from the picture.
                 const int bx = cu.mv[0][0], by = cu.mv[0][1];
-                for (int pl = 0; pl < 3; pl++) {
+                for (int pl = do_l ? 0 : 1; pl < (do_c ? 3 : 1); pl++) {
                     const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, lwp = cu.log2w - sh, Sp = pc(pl).Sp;
                     const int ox = lx >> sh, oy = ly >> sh, vx = bx >> sh, vy = by >> sh;
                     const bool coded = ((cu.cbf >> (4 * pl)) & 15) != 0;
@@ -516,7 +519,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 const int ipm_c = cu.refi[1] == 0 ? cu.refi[0] : kChromaToLuma[cu.refi[1]];
                 {
                     const int n0 = 3 * (w + h) + 3, n1 = 3 * (cw + ch) + 3;
-                    for (int k = tid; k < n0 + 2 * n1; k += kIntraThreads) {
+                    for (int k = (do_l ? 0 : n0) + tid; k < (do_c ? n0 + 2 * n1 : n0); k += kIntraThreads) {
                         const int pl = k < n0 ? 0 : (k < n0 + n1 ? 1 : 2);
                         NbSrc nb;
                         nb.pc = pc(pl); nb.cx = lx >> (pl ? 1 : 0); nb.cy = ly >> (pl ? 1 : 0);
@@ -527,14 +530,14 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 }
                 __syncthreads();
                 if (cu.refi[0] <= 2 || ipm_c <= 2) {          // DC / plane / bilinear: per-plane scalars first (angular modes need none)
-                    if ((tid >> 5) < 3) {
+                    if ((tid >> 5) < 3 && ((tid >> 5) ? do_c : do_l)) {
                         const int pl = tid >> 5;
                         intra_scalars_main(pl ? cw : w, pl ? ch : h, cu.log2w - (pl ? 1 : 0), cu.log2h - (pl ? 1 : 0), pl ? ipm_c : cu.refi[0], lr, up(pl), le(pl), ri(pl),
                                            s_scr12 + 4 * pl, tid & 31);
                     }
                     __syncthreads();
                 }
-                for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
+                for (int k = (do_l ? 0 : w * h) + tid; k < (do_c ? w * h + 2 * cw * ch : w * h); k += kIntraThreads) {
                     const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                     const int lwp = cu.log2w - (pl ? 1 : 0), lhp = cu.log2h - (pl ? 1 : 0), wp = 1 << lwp, hp = 1 << lhp;
                     const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> (pl ? 1 : 0), oy = ly >> (pl ? 1 : 0);
@@ -554,7 +557,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 int dc0 = 0, dc1 = 0, dc2 = 0;
 #pragma unroll
                 for (int pl = 0; pl < 3; pl++) {
-                    if ((pl ? cu.refi[1] : cu.refi[0]) != 0) continue;            // uniform
+                    if ((pl ? cu.refi[1] : cu.refi[0]) != 0 || !(pl ? do_c : do_l)) continue;            // uniform
                     const int sh = pl ? 1 : 0, wp = w >> sh, hp = h >> sh, cxp = lx >> sh, cyp = ly >> sh, ush = 2 - sh;
                     const PlaneCtx c = pc(pl);
                     int acc = 0;
@@ -565,7 +568,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                     const int v = (acc + wp) >> (cu.log2w - sh + 1);
                     if (pl == 0) dc0 = v; else if (pl == 1) dc1 = v; else dc2 = v;
                 }
-                for (int k = tid; k < w * h + 2 * cw * ch; k += kIntraThreads) {
+                for (int k = (do_l ? 0 : w * h) + tid; k < (do_c ? w * h + 2 * cw * ch : w * h); k += kIntraThreads) {
                     const int pl = k < w * h ? 0 : (k < w * h + cw * ch ? 1 : 2), kk = k - (pl == 0 ? 0 : (pl == 1 ? w * h : w * h + cw * ch));
                     const int sh = pl ? 1 : 0, lwp = cu.log2w - sh, wp = 1 << lwp, ush = 2 - sh;
                     const int y = kk >> lwp, x = kk & (wp - 1), ox = lx >> sh, oy = ly >> sh;

@@ -23,7 +23,8 @@ struct ReconSmem {
     int S, Sc;
     int *tmp_y, *tmp_u, *tmp_v;            // pass-1 results, row stride S+1 / Sc+1 (bank-conflict free)
     int16_t *res_y, *res_u, *res_v;        // residual, row stride S+2 / Sc+2
-    uint16_t *cu_of_scu;                   // CU index (relative to the CTU's first CU) covering each SCU
+    uint16_t *cu_of_scu;                   // CU index (relative to the CTU's first CU) covering each SCU: owner of its luma samples and maps
+    uint16_t *cu_of_scu_c;                 // owner of its chroma samples: differs inside a local dual tree node (luma leaves + one chroma-only CU)
     int16_t *mc;                           // per-warp interpolation scratch (aliases tmp_*)
     __device__ __forceinline__ void carve(unsigned char *base, int log2_ctu)
     {
@@ -40,6 +41,7 @@ struct ReconSmem {
         res_u = res_y + S * (S + 2);
         res_v = res_u + Sc * (Sc + 2);
         cu_of_scu = (uint16_t *)(res_v + Sc * (Sc + 2));
+        cu_of_scu_c = cu_of_scu + (S / 4) * (S / 4);
     }
     static size_t bytes(int log2_ctu)
     {
@@ -48,7 +50,7 @@ struct ReconSmem {
         size_t mc_bytes = sizeof(int16_t) * kMcScratchPerWarp * kReconWarps;
         size_t a = tmp_bytes > mc_bytes ? tmp_bytes : mc_bytes;
         a = (a + 15) & ~(size_t)15;
-        return a + sizeof(int16_t) * (S * (S + 2) + 2 * Sc * (Sc + 2)) + sizeof(uint16_t) * (S / 4) * (S / 4) + 16;
+        return a + sizeof(int16_t) * (S * (S + 2) + 2 * Sc * (Sc + 2)) + 2 * sizeof(uint16_t) * (S / 4) * (S / 4) + 16;
     }
 };
 
@@ -224,6 +226,7 @@ __device__ __forceinline__ bool dmvr_applies(const XbFrameArgs &a, const XB200_C
 __device__ __forceinline__ bool cu_needs_generic(const XbFrameArgs &a, const XB200_CU &cu)
 {
     if (a.ats && (cu.ats || (cu.flags & XB200_CUF_ATS_INTRA))) return true;        // DST-7 / DCT-8 lines, sub-block transform units
+    if ((cu.flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA)) != (XB200_CUF_LUMA | XB200_CUF_CHROMA)) return true;      // local dual tree: per-plane owners
     if (cu.mode == XB200_MODE_AFFINE) return true;
     int st[2][2];
     return dmvr_applies(a, cu, st);
@@ -667,7 +670,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) return;      // no ATS / DMVR / affine CU here: the throughput kernel does it all
 
     // ---- SCU -> CU map, zero residual -------------------------------------------------------------------
-    for (int i = tid; i < nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;
+    for (int i = tid; i < 2 * nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;          // both owner tables (contiguous)
     for (int i = tid; i < S * (S + 2) / 2; i += kReconThreads) ((int *)sm.res_y)[i] = 0;
     for (int i = tid; i < Sc * (Sc + 2); i += kReconThreads) ((int *)sm.res_u)[i] = 0;     // res_u and res_v are contiguous
     __syncthreads();
@@ -677,7 +680,11 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const int sx = (cu.x - ctu_x) >> 2, sy = (cu.y - ctu_y) >> 2;
         const int nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
         for (int y = 0; y < nh; y++)
-            for (int x = 0; x < nw; x++) sm.cu_of_scu[(sy + y) * nscu + sx + x] = (uint16_t)i;
+            for (int x = 0; x < nw; x++) {
+                // TREE_L leaves own luma and the maps, the TREE_C CU that follows them the chroma of the whole node (xevdm.c:1828-1846)
+                if (cu.flags & XB200_CUF_LUMA) sm.cu_of_scu[(sy + y) * nscu + sx + x] = (uint16_t)i;
+                if (cu.flags & XB200_CUF_CHROMA) sm.cu_of_scu_c[(sy + y) * nscu + sx + x] = (uint16_t)i;
+            }
     }
     __syncthreads();
 
@@ -691,7 +698,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             if (s < luma_slots) { pl = 0; ys = s >> a.log2_ctu; x = s - ys * S; }
             else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; ys = t >> (a.log2_ctu - 1); x = t - ys * Sc; }
             const int xs = pl == 0 ? (x >> 2) : (x >> 1);
-            const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
+            const unsigned ci = (pl ? sm.cu_of_scu_c : sm.cu_of_scu)[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
             TbInfo t;
@@ -716,7 +723,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             if (s < luma_slots) { pl = 0; xs = s >> a.log2_ctu; y = s - xs * S; }
             else { int t = s - luma_slots; pl = 1 + (t >= chroma_slots); t -= (pl - 1) * chroma_slots; xs = t >> (a.log2_ctu - 1); y = t - xs * Sc; }
             const int ys = pl == 0 ? (y >> 2) : (y >> 1);
-            const unsigned ci = sm.cu_of_scu[ys * nscu + xs];
+            const unsigned ci = (pl ? sm.cu_of_scu_c : sm.cu_of_scu)[ys * nscu + xs];
             if (ci == 0xffff) continue;
             const XB200_CU cu = cus[ci];
             TbInfo t;
@@ -803,7 +810,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         if (i < S * S) { pl = 0; y = i >> a.log2_ctu; x = i - y * S; }
         else { int t = i - S * S; pl = 1 + (t >= Sc * Sc); t -= (pl - 1) * Sc * Sc; y = t >> (a.log2_ctu - 1); x = t - y * Sc; }
         const int sh = pl ? 1 : 0;
-        const unsigned ci = sm.cu_of_scu[((y << sh) >> 2) * nscu + ((x << sh) >> 2)];
+        const unsigned ci = (pl ? sm.cu_of_scu_c : sm.cu_of_scu)[((y << sh) >> 2) * nscu + ((x << sh) >> 2)];
         if (ci == 0xffff || !xb_wavefront_mode(cus[ci].mode)) continue;
         const int16_t *res = pl == 0 ? sm.res_y : (pl == 1 ? sm.res_u : sm.res_v);
         pel *dst = (pl == 0 ? a.cur.y : (pl == 1 ? a.cur.u : a.cur.v)) + (size_t)((ctu_y >> sh) + y) * (pl ? a.s_c : a.s_l) + (ctu_x >> sh) + x;
@@ -887,8 +894,22 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         if (!refined) ((int2 *)a.map_mv)[p] = mvm;
         ((int2 *)a.map_unrefined_mv)[p] = mvw;
         ((int16_t *)a.map_refi)[p] = (intra || ibc) ? (int16_t)-1 : *(const int16_t *)cu.refi;
-        a.map_edge[p] = (uint8_t)(((((gx << 2) - cu.x) & 63) == 0 ? XB200_EDGE_LEFT : 0) | ((((gy << 2) - cu.y) & 63) == 0 ? XB200_EDGE_TOP : 0) |
+        // a TREE_L leaf: its edges are luma edges; the chroma outline of the node is restored below by the TREE_C CU
+        const bool e_l = (((gx << 2) - cu.x) & 63) == 0, e_t = (((gy << 2) - cu.y) & 63) == 0, lonly = !(cu.flags & XB200_CUF_CHROMA);
+        a.map_edge[p] = (uint8_t)((e_l ? XB200_EDGE_LEFT | (lonly ? XB200_EDGE_LEFT_NOC : 0) : 0) | (e_t ? XB200_EDGE_TOP | (lonly ? XB200_EDGE_TOP_NOC : 0) : 0) |
                                   (aidx ? XB200_EDGE_ATS : 0));
+    }
+    // chroma-only CUs (deblock_tree visits the node once more as TREE_C, xevdm.c:1991-1998): chroma edges along their left column / top row
+    bool any_c = false;
+    for (int i = tid; i < ncu; i += kReconThreads) any_c |= (cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA)) == XB200_CUF_CHROMA;
+    if (__syncthreads_or(any_c)) {          // the barrier also orders the map_edge stores above before the updates below
+        for (int i = tid; i < ncu; i += kReconThreads) {
+            const XB200_CU cu = cus[i];
+            if ((cu.flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA)) != XB200_CUF_CHROMA) continue;
+            const int gx = cu.x >> 2, gy = cu.y >> 2, nw = 1 << (cu.log2w - 2), nh = 1 << (cu.log2h - 2);
+            for (int y = 0; y < nh; y++) a.map_edge[(gy + y) * a.w_scu + gx] &= (uint8_t)~XB200_EDGE_LEFT_NOC;
+            for (int x = 0; x < nw; x++) a.map_edge[gy * a.w_scu + gx + x] &= (uint8_t)~XB200_EDGE_TOP_NOC;
+        }
     }
 }
 

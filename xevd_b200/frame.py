@@ -176,7 +176,8 @@ class CuList:
         return CuList(w=self.w, h=self.h, log2_ctu=self.log2_ctu, cus=cus, ctu_first=first, coef=self.coef[k0:k1].copy(), ext=self.ext)
 
     def edge_flags(self) -> np.ndarray:
-        """one byte per SCU: bit0 = CU/TU boundary on the left side, bit1 = on the top side, bit2 = ats_inter CU
+        """one byte per SCU: bit0 = CU/TU boundary on the left side, bit1 = on the top side, bit2 = ats_inter CU, bits 3/4 = the
+        left / top boundary is a luma edge only (inner leaf boundaries of a local dual tree node)
         (what deblock_tree derives from map_split, src_base/xevd.c:1057-1114: CU boundaries plus the
         64-sample transform split of larger CUs)"""
         w_scu, h_scu = (self.w + 3) >> 2, (self.h + 3) >> 2
@@ -184,10 +185,17 @@ class CuList:
         for cu in self.cus:
             x0, y0 = int(cu["x"]) >> 2, int(cu["y"]) >> 2
             nw, nh = 1 << (int(cu["log2w"]) - 2), 1 << (int(cu["log2h"]) - 2)
+            fl = int(cu["flags"]) & 3
+            if fl == 2:
+                # chroma-only CU of a local dual tree node (visited after its luma leaves): its outline carries chroma again
+                f[y0:y0 + nh, x0] &= ~np.uint8(0x08)
+                f[y0, x0:x0 + nw] &= ~np.uint8(0x10)
+                continue
+            # luma-only leaves: XB200_EDGE_LEFT_NOC / XB200_EDGE_TOP_NOC = luma edge only
             for xs in range(x0, x0 + nw, 16):
-                f[y0:y0 + nh, xs] |= 1
+                f[y0:y0 + nh, xs] |= 1 | (0x08 if fl == 1 else 0)
             for ys in range(y0, y0 + nh, 16):
-                f[ys, x0:x0 + nw] |= 2
+                f[ys, x0:x0 + nw] |= 2 | (0x10 if fl == 1 else 0)
             if int(cu["mode"]) not in (0, 4) and (int(cu["ats"]) >> 2) & 7:
                 f[y0:y0 + nh, x0:x0 + nw] |= 4          # XB200_EDGE_ATS: SCUs of ats_inter CUs (map_ats_inter != 0)
         return f.reshape(-1)
