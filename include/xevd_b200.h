@@ -156,7 +156,10 @@ typedef struct XB200_PARAMS {
                                      [ctu_row0, ctu_row0 + ctu_rows) are reconstructed; cus / ctu_first / n_ctu describe just
                                      those CTUs (n_ctu = ctu_rows * CTUs per row).  Inter CUs only: intra / IBC / HTDF need the
                                      bands above, which live on other GPUs (bands that are tiles would lift this)            */
-    int32_t reserved[8];
+    int32_t constrained_intra_pred;   /* pps.constrained_intra_pred_flag: the HTDF ring of an intra CU takes left / right / upper samples
+                                         from intra neighbours only (xevdm_recon.c:317,338,359); the intra neighbour masks of
+                                         XB200_CU_EXT already carry the same test                                  */
+    int32_t reserved[7];
 } XB200_PARAMS;
 
 typedef struct xb200_ctx xb200_ctx;   /* device context: stream, uploaded tables, scratch              */

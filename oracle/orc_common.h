@@ -98,7 +98,7 @@ void orc_ipred_main(const pel *left, const pel *up, const pel *right, int avail_
 void orc_ipred_uv_main(const pel *left, const pel *up, const pel *right, int avail_lr, pel *dst, int ipm_c, int ipm, int w, int h, int bit_depth);
 
 /* orc_htdf.c */
-void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth);
+void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth, const uint32_t *map_scu, int w_scu, int constrained);
 const uint8_t *orc_htdf_table(int idx);
 
 /* orc_output.c */

@@ -43,7 +43,10 @@ static void window(const pel *t, int s, const uint8_t *tbl, int thr, int shift, 
 }
 
 /* avail: the AVAIL_* bits of xevd_get_avail_intra (src_base/xevd_util.c:689-745; bit numbers xevd_def.h:237-247) */
-void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth)
+/* map_scu: the picture's map at the CU's first SCU, consulted when `constrained` (intra CU under pps.constrained_intra_pred_flag,
+ * xevdm.c:1387): a left / right / upper ring sample comes from the picture only if that neighbour SCU is intra (MCU_GET_IF), else it
+ * is replicated from the CU (xevdm_recon.c:313-368); the four corners do not take the test */
+void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int bit_depth, const uint32_t *map_scu, int w_scu, int constrained)
 {
     /* xevdm_htdf_skip_condition (:271-297) */
     if (qp <= 17 || w * h < 64) return;
@@ -57,11 +60,13 @@ void orc_htdf(pel *rec, int s, int w, int h, int qp, int intra, int avail, int b
     const int le = (avail >> 1) & 1, up = avail & 1, ri = (avail >> 3) & 1;
     for (int i = 0; i < h; i++) {
         memcpy(t + (i + 1) * we + 1, rec + i * s, sizeof(pel) * w);
-        t[(i + 1) * we] = le ? rec[i * s - 1] : rec[i * s];
-        t[(i + 1) * we + we - 1] = ri ? rec[i * s + w] : rec[i * s + w - 1];
+#define NB_INTRA(off) (!constrained || ((map_scu[off] >> 15) & 1))                 /* MCU_GET_IF */
+        t[(i + 1) * we] = (le && NB_INTRA(-1 + (i >> 2) * w_scu)) ? rec[i * s - 1] : rec[i * s];
+        t[(i + 1) * we + we - 1] = (ri && NB_INTRA((w >> 2) + (i >> 2) * w_scu)) ? rec[i * s + w] : rec[i * s + w - 1];
     }
     for (int j = 0; j < w; j++) {
-        t[j + 1] = up ? rec[j - s] : rec[j];
+        t[j + 1] = (up && NB_INTRA(-w_scu + (j >> 2))) ? rec[j - s] : rec[j];
+#undef NB_INTRA
         t[(he - 1) * we + j + 1] = rec[(h - 1) * s + j];              /* the row below is never available */
     }
     t[0] = ((avail >> 5) & 1) ? rec[-1 - s] : rec[0];

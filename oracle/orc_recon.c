@@ -186,7 +186,8 @@ int orc_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         if (do_c) put_block_tu(cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, pv, has_v ? rv : NULL, cw, ch, prm->bit_depth_luma, txo >> 1, tyo >> 1, tw >> 1, th >> 1);
         /* Main tool_htdf (src_main/xevdm.c:1381-1391): luma post-filter of CUs with a luma residual and of every intra CU, slice QP */
         if (prm->tool_htdf && cu->mode != XB200_MODE_IBC && (has_y || cu->mode == XB200_MODE_INTRA) && (cu->flags & XB200_CUF_LUMA))
-            orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma);
+            orc_htdf(cur->y + cu->y * cur->s_l + cu->x, cur->s_l, w, h, prm->slice_qp, cu->mode == XB200_MODE_INTRA, cu->avail_cu, prm->bit_depth_luma,
+                     cur->map_scu + (cu->y >> 2) * cur->w_scu + (cu->x >> 2), cur->w_scu, cu->mode == XB200_MODE_INTRA && prm->constrained_intra_pred);
         /* xevdm_set_dec_info writes the maps of luma-carrying CUs only (src_main/xevdm_util.c:4241); a TREE_C CU leaves what its luma
          * siblings published (its COD bits are already set) */
         if (do_l) publish_maps(prm, cur, cu, dmvr ? dmvr_mv : NULL, aff);

@@ -187,10 +187,17 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
     u32 *map_scu = (u32 *)calloc(f_scu, sizeof(u32));
     u8 *map_tidx = (u8 *)calloc(f_scu, 1);
 
+    /* the intra flags are in map_scu from the parsing pass of the CTU (xevdm_set_dec_info in xevd_entropy_dec_unit), i.e. before any CU
+     * of it is reconstructed; only luma-carrying CUs publish (xevdm_util.c:4241).  Read under pps.constrained_intra_pred_flag. */
+    for (n = 0; n < n_cu; n++)
+        if (cus[n].mode == XB200_MODE_INTRA && (cus[n].flags & XB200_CUF_LUMA))
+            for (l = 0; l < (1 << (cus[n].log2h - 2)); l++)
+                for (i = 0; i < (1 << (cus[n].log2w - 2)); i++) MCU_SET_IF(map_scu[((cus[n].y >> 2) + l) * cur->w_scu + (cus[n].x >> 2) + i]);
     for (n = 0; n < n_cu; n++) {
         const XB200_CU *cu = &cus[n];
         const int w = 1 << cu->log2w, h = 1 << cu->log2h, cw = w >> 1, ch = h >> 1;
         const int16_t *c = coef + cu->coef_off;
+        const int cip = cu->mode == XB200_MODE_INTRA && prm->constrained_intra_pred;       /* constrained_intra_flag (xevdm.c:609,1387) */
         int is_coef[N_C], nnz_sub[N_C][MAX_SUB_TB_NUM];
         s8  refi[REFP_NUM] = { cu->refi[0], cu->refi[1] };
         s16 mv[REFP_NUM][MV_D] = { { cu->mv[0][0], cu->mv[0][1] }, { cu->mv[1][0], cu->mv[1][1] } };
@@ -224,11 +231,11 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             const int bdl = prm->bit_depth_luma;
             /* get_nbr_yuv and the prediction calls are gated by xevd_check_luma / xevd_check_chroma (src_main/xevdm.c:611-640,1362-1376) */
             if (do_l) xevd_get_nbr_b(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
-                           Y_C, 0, map_tidx, bdl, 1);
+                           Y_C, cip, map_tidx, bdl, 1);
             if (do_c) xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
-                           cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
+                           cur->w_scu, cur->h_scu, U_C, cip, map_tidx, bdl, 1);
             if (do_c) xevd_get_nbr_b(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
-                           cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
+                           cur->w_scu, cur->h_scu, V_C, cip, map_tidx, bdl, 1);
             if (do_l) xevd_ipred_b(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, 0, s->pred[0][Y_C], cu->refi[0], w, h);
             if (do_c) xevd_ipred_uv_b(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, 0, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch);
             if (do_c) xevd_ipred_uv_b(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, 0, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch);
@@ -242,11 +249,11 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             const u16 avail_lr = xevd_check_nev_avail(cu->x >> 2, cu->y >> 2, w, h, cur->w_scu, cur->h_scu, map_scu, map_tidx);
             const int bdl = prm->bit_depth_luma, bdc = prm->bit_depth_chroma;
             if (do_l) xevdm_get_nbr(cu->x, cu->y, w, h, cur->y + cu->y * cur->s_l + cu->x, cur->s_l, avail_cu, s->nb, scup, map_scu, cur->w_scu, cur->h_scu,
-                          Y_C, 0, map_tidx, bdl, 1);
+                          Y_C, cip, map_tidx, bdl, 1);
             if (do_c) xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
-                          cur->w_scu, cur->h_scu, U_C, 0, map_tidx, bdl, 1);
+                          cur->w_scu, cur->h_scu, U_C, cip, map_tidx, bdl, 1);
             if (do_c) xevdm_get_nbr(cu->x >> 1, cu->y >> 1, cw, ch, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), cur->s_c, avail_cu, s->nb, scup, map_scu,
-                          cur->w_scu, cur->h_scu, V_C, 0, map_tidx, bdl, 1);
+                          cur->w_scu, cur->h_scu, V_C, cip, map_tidx, bdl, 1);
             if (do_l) xevdm_ipred(s->nb[0][0] + 2, s->nb[0][1] + h, s->nb[0][2] + 2, avail_lr, s->pred[0][Y_C], cu->refi[0], w, h, bdl);
             if (do_c) xevdm_ipred_uv(s->nb[1][0] + 2, s->nb[1][1] + ch, s->nb[1][2] + 2, avail_lr, s->pred[0][U_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
             if (do_c) xevdm_ipred_uv(s->nb[2][0] + 2, s->nb[2][1] + ch, s->nb[2][2] + 2, avail_lr, s->pred[0][V_C], cu->refi[1], cu->refi[0], cw, ch, bdc);
@@ -316,7 +323,7 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                 for (l = 0; l < (h >> 2); l++) for (i = 0; i < (w >> 2); i++) MCU_CLR_COD(map_scu[scup + l * cur->w_scu + i]);
                 av = xevd_get_avail_intra(cu->x >> 2, cu->y >> 2, cur->w_scu, cur->h_scu, scup, cu->log2w, cu->log2h, map_scu, map_tidx);
                 xevdm_htdf(cur->y + cu->y * cur->s_l + cu->x, prm->slice_qp, w, h, cur->s_l, cu->mode == XB200_MODE_INTRA,
-                           cur->y + cu->y * cur->s_l + cu->x, cur->s_l, av, scup, cur->w_scu, cur->h_scu, map_scu, 0, prm->bit_depth_luma);
+                           cur->y + cu->y * cur->s_l + cu->x, cur->s_l, av, scup, cur->w_scu, cur->h_scu, map_scu, cip, prm->bit_depth_luma);
                 for (l = 0; l < (h >> 2); l++) for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
             }
             continue;

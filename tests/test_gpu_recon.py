@@ -162,6 +162,26 @@ def test_dual_tree(oracle, monkeypatch, variant, kw, bd, eipd, htdf, intra_frac,
     assert np.array_equal(edge, cl.edge_flags())
 
 
+@pytest.mark.parametrize("variant,kw,bd,eipd,htdf,intra_frac,dual", [("C", {}, 10, 0, 0, 0.5, 0), ("C", {}, 10, 1, 1, 0.5, 0), ("C", dict(log2_ctu=5), 8, 1, 1, 0.3, 1),
+                                                                     ("A", dict(log2_cu=3), 10, 1, 1, 0.6, 0), ("C", dict(log2_ctu=7), 12, 1, 1, 0.5, 1),
+                                                                     ("B", {}, 10, 0, 0, 0.4, 0)])
+def test_constrained_intra(ctx, oracle, variant, kw, bd, eipd, htdf, intra_frac, dual):
+    """pps.constrained_intra_pred_flag in mixed pictures: neighbour masks with the intra test and the HTDF ring of intra CUs taking left /
+    right / upper samples from intra neighbours only (xevdm_recon.c:317,338,359; read from the published map_scu on the device)"""
+    from tests.test_oracle_vs_ref import constrained_inputs
+    w, h, prm, cl, refs = constrained_inputs(variant, kw, bd, eipd, htdf, intra_frac, dual)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+
+
 def test_dual_tree_inter_cu_is_refused(ctx):
     """an inter CU is always TREE_LC (xevdm.c:1122): one flagged luma-only is a caller error, not something to reconstruct"""
     from xevd_b200.device import XevdB200Error

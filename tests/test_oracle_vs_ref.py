@@ -331,6 +331,39 @@ def test_deblock_dual_tree(oracle, reference, bd, addb):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
+def constrained_inputs(variant, kw, bd, eipd, htdf, intra_frac, dual):
+    w, h = 256, 136
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=91, n_refs=2, coded_frac=0.7, **kw)
+    prm.tool_eipd, prm.tool_htdf, prm.slice_qp, prm.constrained_intra_pred = eipd, htdf, 37, 1
+    if dual:
+        synth.split_local_dual_tree(cl, np.random.default_rng(5), 0.5)
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=bool(eipd), constrained=True)
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    return w, h, prm, cl, synth.make_refs(w, h, bd, 2, seed=9)
+
+
+CONSTRAINED_CASES = [("C", {}, 10, 0, 0, 0.5, 0), ("C", {}, 10, 1, 1, 0.5, 0), ("C", dict(log2_ctu=5), 8, 1, 1, 0.3, 1), ("A", dict(log2_cu=3), 10, 1, 1, 0.6, 0),
+                     ("C", dict(log2_ctu=7), 12, 1, 1, 0.5, 1), ("B", {}, 10, 0, 0, 0.4, 0)]
+
+
+@pytest.mark.parametrize("variant,kw,bd,eipd,htdf,intra_frac,dual", CONSTRAINED_CASES)
+def test_recon_frame_constrained_intra(oracle, reference, variant, kw, bd, eipd, htdf, intra_frac, dual):
+    """pps.constrained_intra_pred_flag in pictures that mix intra and inter CUs: intra prediction takes neighbours from intra CUs only
+    (xevd_get_nbr_b / xevdm_get_nbr with constrained_intra_flag, src_main/xevdm.c:609-652; the oracle gets that as the masks of
+    synth.add_intra_cus) and so does the HTDF ring of an intra CU (xevdm_recon.c:317,338,359).  The reference applies its own tests
+    on its own map_scu."""
+    w, h, prm, cl, refs = constrained_inputs(variant, kw, bd, eipd, htdf, intra_frac, dual)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    prm.constrained_intra_pred = 0
+    if htdf:
+        c = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        assert (a.y != c.y).sum() > 50, "test picture does not exercise the constrained HTDF ring"
+
+
 IBC_CASES = [("C", {}, 10, 0.3), ("C", dict(log2_ctu=7), 10, 0.3), ("C", dict(log2_ctu=5), 8, 0.5), ("B", {}, 10, 0.0), ("A", dict(log2_cu=3), 10, 0.2)]
 
 

@@ -60,7 +60,8 @@ class Params(C.Structure):
         ("deblock_alpha_offset", C.c_int32), ("deblock_beta_offset", C.c_int32),
         ("poc", C.c_int32),
         ("ctu_row0", C.c_int32), ("ctu_rows", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("constrained_intra_pred", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 

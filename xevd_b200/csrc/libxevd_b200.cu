@@ -438,6 +438,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.ats = prm->tool_ats ? 1 : 0;
     a.htdf = prm->tool_htdf ? 1 : 0;
     a.ibc = prm->tool_ibc ? 1 : 0;
+    a.constrained = prm->constrained_intra_pred ? 1 : 0;
     a.dmvr = prm->tool_dmvr ? 1 : 0;
     a.poc = prm->poc;
     a.affine = prm->tool_affine ? 1 : 0;

@@ -35,6 +35,7 @@ struct XbFrameArgs {
     long long peer_delta[7];    //   byte distance from this GPU's picture allocation to the peer's mapping of its twin (same layout)
     int ctu_row0;               // band mode: first CTU row of this launch (the CU arrays / ctu_first index CTUs relative to it)
     int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine, ibc;
+    int constrained;              // pps.constrained_intra_pred_flag (HTDF ring of intra CUs)
     int dispatch;                 // 1: the throughput kernel reconstructs the CUs it has code for, the generic kernel the ATS / DMVR / affine CUs
     const XB200_CU *cus;
     const uint32_t *ctu_first;

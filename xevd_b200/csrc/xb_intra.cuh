@@ -272,7 +272,11 @@ __device__ __forceinline__ bool htdf_applies(const XbFrameArgs &a, const XB200_C
     return true;
 }
 
-__device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log2h, int av, const PlaneCtx pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads)
+// ms: map_scu at the CU's first SCU when the ring takes the constrained-intra test (intra CU under pps.constrained_intra_pred_flag: left /
+// right / upper samples only from intra neighbours, xevdm_recon.c:317,338,359), else null.  The maps of the whole picture are final here:
+// the inter kernels publish them for every CU before this kernel starts.
+__device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log2h, int av, const PlaneCtx pc, int cx, int cy, int qp, int16_t *t, int tid, int nthreads,
+                                        const uint32_t *__restrict__ ms)
 {
     const int w = 1 << log2w, h = 1 << log2h, we = w + 2;
     const bool up = av & 1, le = (av >> 1) & 1, ri = (av >> 3) & 1;
@@ -288,9 +292,13 @@ __device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log
         else if (idx < 2 * we) { i = h; j = idx - we - 1; }
         else { const int k = idx - 2 * we; i = k >> 1; j = (k & 1) ? w : -1; }
         int si = min(max(i, 0), h - 1), sj = min(max(j, 0), w - 1);          // replicated by default
-        if (i >= 0 && i < h) { if (j < 0 && le) sj = -1; else if (j >= w && ri) sj = w; }
+        auto nb_intra = [&](int off) -> bool { return !ms || ((__ldg(ms + off) >> 15) & 1); };          // MCU_GET_IF
+        if (i >= 0 && i < h) {
+            if (j < 0 && le) { if (nb_intra(-1 + (i >> 2) * a.w_scu)) sj = -1; }
+            else if (j >= w && ri) { if (nb_intra((w >> 2) + (i >> 2) * a.w_scu)) sj = w; }
+        }
         else if (i < 0) {
-            if (j >= 0 && j < w) { if (up) si = -1; }
+            if (j >= 0 && j < w) { if (up && nb_intra(-a.w_scu + (j >> 2))) si = -1; }
             else if (j < 0) { if ((av >> 5) & 1) { si = -1; sj = -1; } }
             else if ((av >> 6) & 1) { si = -1; sj = w; }
         } else if (j < 0) { if ((av >> 7) & 1) { si = h; sj = -1; } }
@@ -590,7 +598,8 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             __syncthreads();         // the next CU reads these samples from shared memory
             } while (0);
             // one call site: the routine is not inlined, and a second copy of its operands would live in local memory
-            if (do_htdf && cu.mode != XB200_MODE_IBC) cu_htdf(a, cu.log2w, cu.log2h, cu.avail_cu, pc(0), lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads);
+            if (do_htdf && cu.mode != XB200_MODE_IBC) cu_htdf(a, cu.log2w, cu.log2h, cu.avail_cu, pc(0), lx, ly, hq, (int16_t *)s_tmp, tid, kIntraThreads,
+                                                               (a.constrained && cu.mode == XB200_MODE_INTRA) ? a.map_scu + (cu.y >> 2) * a.w_scu + (cu.x >> 2) : nullptr);
         }
     }
     __threadfence();
