@@ -113,11 +113,33 @@ def golden_main(ref):
     np.savez_compressed(OUT / "main_frames.npz", **out)
 
 
+def golden_tree(ref):
+    """local dual tree nodes and constrained intra prediction: the reference's per-CU calls with its own tree_cons / constrained_intra_flag
+    arguments, then its deblocking (Baseline filter or ADDB, per-CU tree_cons) and border padding.  Maps between the stages are the
+    oracle's, as in golden_main."""
+    from oracle.pyoracle import Oracle
+    from tests.test_golden import TREE_CFGS, golden_tree_inputs
+    orc = Oracle()
+    out = {}
+    for name, kw, o in TREE_CFGS:
+        w, h, prm, cl, refs = golden_tree_inputs(kw, o)
+        pic = ref.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        m = orc.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+        out[f"{name}_rec_y"], out[f"{name}_rec_u"], out[f"{name}_rec_v"] = pic.y.copy(), pic.u.copy(), pic.v.copy()
+        out[f"{name}_map_scu"] = m.map_scu.copy()
+        for k in ("map_mv", "map_refi", "map_scu", "map_unrefined_mv"):
+            getattr(pic, k)[...] = getattr(m, k)
+        ref.deblock_frame(prm, pic, cl, synth.chroma_qp_table(True), bool(o["addb"]), ((0, 1), (1, 0)))
+        ref.pad(pic)
+        out[f"{name}_fin_y"], out[f"{name}_fin_u"], out[f"{name}_fin_v"] = pic.buf_y.copy(), pic.buf_u.copy(), pic.buf_v.copy()
+    np.savez_compressed(OUT / "tree_frames.npz", **out)
+
+
 if __name__ == "__main__":
     r = Reference(2)
-    golden_itdq(r)
-    golden_mc(r)
-    golden_frames(r)
-    golden_main(r)
+    only = sys.argv[1:] or ["itdq", "mc", "frames", "main", "tree"]
+    for k, fn in (("itdq", golden_itdq), ("mc", golden_mc), ("frames", golden_frames), ("main", golden_main), ("tree", golden_tree)):
+        if k in only:
+            fn(r)
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size, "bytes")

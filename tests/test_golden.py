@@ -83,3 +83,41 @@ def test_golden_main_pipeline(oracle, name, kw):
     oracle.alf_frame(prm, pic, alf, flags)
     oracle.pad(pic)
     assert np.array_equal(pic.buf_y, z[f"{name}_fin_y"]) and np.array_equal(pic.buf_u, z[f"{name}_fin_u"]) and np.array_equal(pic.buf_v, z[f"{name}_fin_v"])
+
+
+TREE_CFGS = [("dual_eipd_htdf_10", dict(bit_depth=10, seed=11, log2_ctu=6), dict(eipd=1, htdf=1, constrained=0, intra=1.0, addb=0)),
+             ("dual_base_8", dict(bit_depth=8, seed=12, log2_ctu=5), dict(eipd=0, htdf=0, constrained=0, intra=0.6, addb=0)),
+             ("dual_constrained_iqt_10", dict(bit_depth=10, seed=13, log2_ctu=7, iqt=True), dict(eipd=1, htdf=1, constrained=1, intra=0.5, addb=1)),
+             ("constrained_12", dict(bit_depth=12, seed=14, log2_ctu=6), dict(eipd=1, htdf=1, constrained=1, intra=0.4, addb=1, dual=0))]
+
+
+def golden_tree_inputs(kw, o):
+    """the seeded inputs make_golden.py used for tree_frames.npz: BTT partitions with local dual tree nodes (luma-only leaves + one
+    chroma-only CU, src_main/xevdm.c:1828-1846) and / or pps.constrained_intra_pred_flag in mixed intra / inter pictures"""
+    w, h = 256, 136
+    kw = dict(kw)
+    seed = kw.pop("seed")
+    prm, cl = synth.make_inter_frame(w, h, variant="C", seed=seed, n_refs=2, coded_frac=0.7, **kw)
+    prm.tool_eipd, prm.tool_htdf, prm.slice_qp, prm.constrained_intra_pred, prm.tool_addb = o["eipd"], o["htdf"], 37, o["constrained"], o["addb"]
+    prm.qp_u_offset, prm.qp_v_offset = 1, -2
+    if o.get("dual", 1):
+        synth.split_local_dual_tree(cl, np.random.default_rng(seed + 1), 0.6)
+    synth.add_intra_cus(cl, np.random.default_rng(seed + 2), o["intra"], eipd=bool(o["eipd"]), constrained=bool(o["constrained"]))
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    return w, h, prm, cl, synth.make_refs(w, h, kw["bit_depth"], 2, seed=seed + 3)
+
+
+@pytest.mark.parametrize("name,kw,o", TREE_CFGS)
+def test_golden_tree_pipeline(oracle, name, kw, o):
+    """recon -> deblock -> pad of pictures with local dual tree nodes / constrained intra prediction against the recorded output of the
+    unmodified reference (its own tree_cons and constrained_intra_flag arguments)"""
+    z = np.load(G / "tree_frames.npz")
+    w, h, prm, cl, refs = golden_tree_inputs(kw, o)
+    pic = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pl, k in zip(pic.planes(), "yuv"):
+        assert np.array_equal(pl, z[f"{name}_rec_{k}"]), (name, k)
+    assert np.array_equal(pic.map_scu, z[f"{name}_map_scu"])
+    oracle.deblock_frame(prm, pic, cl, synth.chroma_qp_table(True), bool(o["addb"]), ((0, 1), (1, 0)))
+    oracle.pad(pic)
+    assert np.array_equal(pic.buf_y, z[f"{name}_fin_y"]) and np.array_equal(pic.buf_u, z[f"{name}_fin_u"]) and np.array_equal(pic.buf_v, z[f"{name}_fin_v"])

@@ -24,8 +24,11 @@ def oracle():
     return Oracle()
 
 
-def draw_case(seed):
+def draw_case(seed, tree=False):
+    """tree: additionally local dual tree nodes (luma-only leaves + chroma-only CU) and / or pps.constrained_intra_pred_flag, drawn from a
+    second generator so that the cases of the plain sweep stay what they were"""
     rng = np.random.default_rng(4000 + seed)
+    rng2 = np.random.default_rng(9000 + seed)
     w, h = 8 * int(rng.integers(20, 72)), 8 * int(rng.integers(12, 44))
     bd = int(rng.choice([8, 10, 10, 12]))
     main = bool(rng.random() < 0.7)
@@ -57,8 +60,14 @@ def draw_case(seed):
     prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-3, 4)), int(rng.integers(-3, 4))
     cl.cus["qp_map"] = rng.integers(20, 48, cl.n_cu)
     intra = float(rng.choice([0.0, 0.03, 0.25, 1.0]))
-    if intra or prm.tool_ibc:
-        synth.add_intra_cus(cl, rng, max(intra, 0.05), eipd=True, ats_intra_frac=0.5 if ats else 0.0, ibc_frac=0.2 if prm.tool_ibc else 0.0)
+    constrained = False
+    if tree:
+        constrained = bool(rng2.random() < 0.5)
+        prm.constrained_intra_pred = int(constrained)
+        if rng2.random() < 0.8:
+            synth.split_local_dual_tree(cl, rng2, float(rng2.choice([0.05, 0.5, 1.0])))
+    if intra or prm.tool_ibc or tree:
+        synth.add_intra_cus(cl, rng, max(intra, 0.05), eipd=True, ats_intra_frac=0.5 if ats else 0.0, ibc_frac=0.2 if prm.tool_ibc else 0.0, constrained=constrained)
     if rng.random() < 0.5:
         prm.tool_affine = 1
         synth.add_affine_cus(cl, rng, float(rng.choice([0.02, 0.3])))
@@ -70,9 +79,21 @@ def draw_case(seed):
                 flags=(rng.random(n_ctu) < 0.7).astype(np.uint8), main=True)
 
 
+@pytest.mark.parametrize("seed", range(32))
+def test_random_pipeline_tree(ctx, oracle, seed):
+    """the same sweep over Main pictures with local dual tree nodes and constrained intra prediction mixed into the tool set"""
+    k = draw_case(seed, tree=True)
+    if not k["main"]:
+        pytest.skip("Baseline draw: no BTT, no dual tree")
+    run_case(ctx, oracle, k, seed)
+
+
 @pytest.mark.parametrize("seed", range(64))
 def test_random_pipeline(ctx, oracle, seed):
-    k = draw_case(seed)
+    run_case(ctx, oracle, draw_case(seed), seed)
+
+
+def run_case(ctx, oracle, k, seed):
     w, h, prm, cl, refs = k["w"], k["h"], k["prm"], k["cl"], k["refs"]
     tbl = synth.chroma_qp_table(k["main"])
     want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)

@@ -509,6 +509,31 @@ def test_golden_main_pipeline_gpu(ctx):
         assert np.array_equal(out.buf_y, z[f"{name}_fin_y"]) and np.array_equal(out.buf_u, z[f"{name}_fin_u"]) and np.array_equal(out.buf_v, z[f"{name}_fin_v"]), name
 
 
+def test_golden_tree_pipeline_gpu(ctx):
+    """local dual tree nodes / constrained intra prediction through the C ABI - xb200_recon_frame -> xb200_deblock (maps and edge map as
+    the reconstruction published them) -> xb200_pad - against the recorded output of the unmodified reference (tests/golden/tree_frames.npz)"""
+    from pathlib import Path
+    from tests.test_golden import TREE_CFGS, golden_tree_inputs
+    z = np.load(Path(__file__).resolve().parent / "golden" / "tree_frames.npz")
+    for name, kw, o in TREE_CFGS:
+        w, h, prm, cl, refs = golden_tree_inputs(kw, o)
+        drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+        cur = ctx.pic_alloc(w, h)
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(True))
+        ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        got = cur.download(maps=True)
+        for pl, k in zip(got.planes(), "yuv"):
+            assert np.array_equal(pl, z[f"{name}_rec_{k}"]), (name, k)
+        assert np.array_equal(got.map_scu, z[f"{name}_map_scu"]), name
+        ctx.deblock(prm, cur, drefs, drefs[::-1])
+        ctx.pad(cur)
+        out = cur.download_padded()
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+        for p in drefs + [cur]:
+            p.free()
+        assert np.array_equal(out.buf_y, z[f"{name}_fin_y"]) and np.array_equal(out.buf_u, z[f"{name}_fin_u"]) and np.array_equal(out.buf_v, z[f"{name}_fin_v"]), name
+
+
 @pytest.mark.parametrize("variant,lg", [("B", 6), ("C", 6), ("C", 7), ("C", 5)])
 def test_band_mode_single_gpu(ctx, oracle, variant, lg):
     """band mode of xb200_recon_frame (BASELINE config 4): the picture reconstructed as three separate CTU-row bands into a second

@@ -339,7 +339,7 @@ def split_local_dual_tree(cl: CuList, rng, frac: float = 0.5):
         lw, lh = int(cu["log2w"]), int(cu["log2h"])
         n = 1 << (lw + lh)
         coded = int(cu["cbf"]) != 0
-        own = coef_old[int(cu["coef_off"]):int(cu["coef_off"]) + (a8(n) + 2 * a8(n // 4) if coded else 0)]
+        own = coef_old[int(cu["coef_off"]):int(old[i + 1]["coef_off"]) if i + 1 < len(old) else len(coef_old)]       # ats_inter CUs carry their TU only
         ats_inter = (int(cu["ats"]) >> 2) & 7
         if min(lw, lh) != 3 or max(lw, lh) > 4 or ats_inter or rng.random() >= frac:
             emit(cu, own)
