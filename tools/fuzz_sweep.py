@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Long randomised parity sweep on one GPU: the cases of tests/test_gpu_fuzz.py for seeds [--first, --first + --count) through
 recon -> deblock -> ALF -> pad, final padded pictures against the oracle.  Prints the mismatching seeds (none expected).
-    python tools/fuzz_sweep.py --first 64 --count 400"""
+    python tools/fuzz_sweep.py --first 64 --count 400 [--tree]"""
 import argparse
 import sys
 from pathlib import Path
@@ -20,10 +20,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--first", type=int, default=64)
     ap.add_argument("--count", type=int, default=200)
+    ap.add_argument("--tree", action="store_true", help="Main pictures with local dual tree nodes / constrained intra mixed in (draw_case(seed, tree=True))")
     args = ap.parse_args()
-    o, c, bad = Oracle(), Context(0), []
+    o, c, bad, skipped = Oracle(), Context(0), [], 0
     for seed in range(args.first, args.first + args.count):
-        k = draw_case(seed)
+        k = draw_case(seed, tree=args.tree)
+        if args.tree and not k["main"]:
+            skipped += 1
+            continue
         prm, w, h = k["prm"], k["w"], k["h"]
         want = o.recon_frame(prm, HostPicture(w, h, prm.poc), k["refs"], k["refs"][::-1], k["cl"])
         dr = [c.pic_alloc(w, h).upload(r) for r in k["refs"]]
@@ -43,7 +47,8 @@ def main():
             bad.append(seed)
         for p in dr + [cur]:
             p.free()
-    print(f"fuzz sweep seeds {args.first}..{args.first + args.count - 1}: {args.count - len(bad)} bit-exact, mismatching seeds: {bad}")
+    print(f"fuzz sweep{' (tree)' if args.tree else ''} seeds {args.first}..{args.first + args.count - 1}: {args.count - skipped - len(bad)} bit-exact, "
+          f"{skipped} Baseline draws skipped, mismatching seeds: {bad}")
     return 1 if bad else 0
 
 
