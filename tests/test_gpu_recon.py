@@ -182,6 +182,25 @@ def test_constrained_intra(ctx, oracle, variant, kw, bd, eipd, htdf, intra_frac,
     assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
 
 
+@pytest.mark.parametrize("kw,bd,intra_frac", [({}, 10, 1.0), (dict(log2_ctu=7), 8, 0.5), (dict(log2_ctu=5, suco=False), 10, 0.7)])
+def test_dual_tree_ibc(ctx, oracle, kw, bd, intra_frac):
+    """luma-only leaves that are IBC CUs (luma copy only), next to intra leaves and the chroma-only CU of the node"""
+    from tests.test_oracle_vs_ref import dual_tree_inputs
+    w, h, prm, cl, refs = dual_tree_inputs("C", kw, bd, 1, 1, intra_frac, ibc=0.5)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    got = cur.download(maps=True)
+    edge = cur.download_edge_map()
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi)
+    assert np.array_equal(edge, cl.edge_flags())
+
+
 def test_dual_tree_inter_cu_is_refused(ctx):
     """an inter CU is always TREE_LC (xevdm.c:1122): one flagged luma-only is a caller error, not something to reconstruct"""
     from xevd_b200.device import XevdB200Error

@@ -279,12 +279,12 @@ def test_deblock_main_partitions(oracle, reference, kw, bd, addb):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
-def dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac=1.0):
+def dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac=1.0, ibc=0.0):
     w, h = 256, 136
     prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.7, **kw)
-    prm.tool_eipd, prm.tool_htdf, prm.slice_qp = eipd, htdf, 37
+    prm.tool_eipd, prm.tool_htdf, prm.slice_qp, prm.tool_ibc = eipd, htdf, 37, int(ibc > 0)
     synth.split_local_dual_tree(cl, np.random.default_rng(5), 0.6)
-    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=bool(eipd))
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=bool(eipd), ibc_frac=ibc)
     synth.derive_avail_cu(cl)
     cl.validate()
     fl = cl.cus["flags"] & 3
@@ -308,6 +308,19 @@ def test_recon_frame_dual_tree(oracle, reference, variant, kw, bd, eipd, htdf, i
     # the planes a dual-tree CU does not carry are untouched by it: dropping the chroma-only CUs changes chroma only
     keep = (cl.cus["flags"] & 3) != 2
     assert keep.sum() < len(cl.cus)
+
+
+@pytest.mark.parametrize("kw,bd,intra_frac", [({}, 10, 1.0), (dict(log2_ctu=7), 8, 0.5), (dict(log2_ctu=5, suco=False), 10, 0.7)])
+def test_recon_frame_dual_tree_ibc(oracle, reference, kw, bd, intra_frac):
+    """luma-only leaves that are IBC CUs: xevdm_IBC_mc copies luma only under TREE_L (src_main/xevdm_mc.c:2059-2073), the chroma-only CU of
+    the node then finds a non-intra SCU at the node's centre and falls back to IPD_DC as its DM mode (src_main/xevdm.c:1084-1091)"""
+    w, h, prm, cl, refs = dual_tree_inputs("C", kw, bd, 1, 1, intra_frac, ibc=0.5)
+    leaf_ibc = (cl.cus["mode"] == 4) & ((cl.cus["flags"] & 3) == 1)
+    assert leaf_ibc.sum() >= 3, "test picture has no IBC leaves"
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
 @pytest.mark.parametrize("bd,addb", [(10, 0), (10, 1), (8, 0), (12, 1)])

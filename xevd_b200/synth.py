@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .abi import CU_DTYPE, EXT_DTYPE, CUF_CHROMA, CUF_LUMA, MODE_INTER, MODE_INTRA, make_params
+from .abi import CU_DTYPE, EXT_DTYPE, CUF_ATS_INTRA, CUF_CHROMA, CUF_LUMA, MODE_INTER, MODE_INTRA, make_params
 from .frame import CuList, HostPicture
 
 _DQ_BASE = (40, 45, 51, 57, 64, 71)
@@ -395,7 +395,6 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     is_intra |= dual
     if ats_intra_frac > 0:
         # ats_intra_cu (Main tool_ats): intra CUs of at most 32x32 with coded luma; ats mode = h << 1 | v (0 DST-7, 1 DCT-8)
-        from .abi import CUF_ATS_INTRA
         ok = is_intra & (cus["log2w"] <= 5) & (cus["log2h"] <= 5) & ((cus["cbf"] & 15) != 0) & (rng.random(n) < ats_intra_frac)
         cus["flags"] = np.where(ok, cus["flags"] | CUF_ATS_INTRA, cus["flags"])
         cus["ats"] = np.where(ok, rng.integers(0, 4, n), cus["ats"]).astype(np.uint8)
@@ -413,6 +412,10 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
     from .abi import MODE_IBC
     ctu_scu = (1 << cl.log2_ctu) >> 2
     want_ibc = (~is_intra) & (((cus["ats"] >> 2) & 7) == 0) & (rng.random(n) < ibc_frac) if ibc_frac > 0 else np.zeros(n, bool)
+    if ibc_frac > 0 and dual.any():
+        # luma-only leaves of a dual tree node may be IBC CUs (intra-only nodes allow it; xevdm_IBC_mc copies luma only for TREE_L,
+        # src_main/xevdm_mc.c:2059-2073); drawn separately so that pictures without dual tree nodes stay what they were
+        want_ibc |= ((cus["flags"] & (CUF_LUMA | CUF_CHROMA)) == CUF_LUMA) & (rng.random(n) < ibc_frac)
     for i in range(n):
         cu = cus[i]
         xs, ys = int(cu["x"]) >> 2, int(cu["y"]) >> 2
@@ -433,6 +436,9 @@ def add_intra_cus(cl: CuList, rng, intra_frac: float = 1.0, n_modes: int = 5, co
                     cu["refi"] = -1
                     cu["mv"] = 0
                     cu["mv"][0] = (sx - x0, sy - y0)
+                    cu["flags"] = int(cu["flags"]) & ~CUF_ATS_INTRA
+                    cu["ats"] = 0
+                    is_intra[i] = False
                     break
         if is_intra[i] and not (int(cu["flags"]) & CUF_LUMA):
             # TREE_C CU: ipm[0] comes from map_ipm at the node's centre SCU, IPD_DC if that SCU is not intra (src_main/xevdm.c:1081-1092)
