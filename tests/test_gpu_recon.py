@@ -201,6 +201,46 @@ def test_dual_tree_ibc(ctx, oracle, kw, bd, intra_frac):
     assert np.array_equal(edge, cl.edge_flags())
 
 
+@pytest.mark.parametrize("intra_frac,lg", [(0.08, 6), (1.0, 6), (0.3, 7)])
+def test_dual_tree_1080p_pipeline(ctx, oracle, intra_frac, lg):
+    """a full-size Main picture (IQT, 1/16-pel motion, EIPD, HTDF, constrained intra, ADDB) with local dual tree nodes scattered over
+    500+ CTUs: sparse wavefront dependencies, per-CU dispatch between the kernels, recon -> deblock -> pad.  Decoded three times into
+    the same picture: a missed dependency is a race."""
+    w, h, bd = 1920, 1080, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="C", seed=101, n_refs=2, coded_frac=0.4, main_mv=True, iqt=True, log2_ctu=lg)
+    prm.tool_eipd = prm.tool_htdf = prm.tool_addb = prm.constrained_intra_pred = 1
+    prm.slice_qp = 35
+    synth.split_local_dual_tree(cl, np.random.default_rng(5), 0.7)
+    synth.add_intra_cus(cl, np.random.default_rng(4), intra_frac, eipd=True, constrained=True)
+    synth.derive_avail_cu(cl)
+    cl.validate()
+    assert ((cl.cus["flags"] & 3) != 3).sum() > 200
+    refs = synth.make_refs(w, h, bd, 2, seed=9)
+    tbl = synth.chroma_qp_table(True)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    rec = want.copy()
+    oracle.deblock_frame(prm, want, cl, tbl, True, ((0, 1), (1, 0)))
+    oracle.pad(want)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.set_chroma_qp_table(tbl)
+    try:
+        for it in range(3):
+            ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+            got = cur.download(maps=True)
+            for a, b, n in zip(got.planes(), rec.planes(), "YUV"):
+                assert np.array_equal(a, b), f"pass {it} recon plane {n}: {int((a != b).sum())} samples differ"
+            assert np.array_equal(got.map_scu, rec.map_scu)
+            ctx.deblock(prm, cur, drefs, drefs[::-1])
+            ctx.pad(cur)
+            out = cur.download_padded()
+            assert np.array_equal(out.buf_y, want.buf_y) and np.array_equal(out.buf_u, want.buf_u) and np.array_equal(out.buf_v, want.buf_v), f"pass {it}"
+    finally:
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+        for p in drefs + [cur]:
+            p.free()
+
+
 def test_dual_tree_inter_cu_is_refused(ctx):
     """an inter CU is always TREE_LC (xevdm.c:1122): one flagged luma-only is a caller error, not something to reconstruct"""
     from xevd_b200.device import XevdB200Error
