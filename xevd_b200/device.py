@@ -201,7 +201,7 @@ class Context:
 
     # -- device-resident entry point (inputs already in HBM; pointers are raw device addresses) --------------
     def recon_frame_dev(self, prm: abi.Params, cur: DevicePicture, refs_l0, refs_l1, d_cus: int, n_cu: int,
-                        d_first: int, n_ctu: int, d_ext: int, n_ext: int, d_coef: int, n_coef: int, has_intra: bool = False,
+                        d_first: int, n_ctu: int, d_ext: int, n_ext: int, d_coef: int, n_coef: int, has_intra: int = 0,
                         max_cu_per_ctu: int = 0):
         cur.set_poc(prm.poc)
         self._chk(self.lib.xb200_recon_frame_dev(self.handle, C.byref(prm), cur.handle,
