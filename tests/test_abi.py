@@ -49,6 +49,20 @@ def test_struct_layouts_match_header():
     assert vals[4:] == [f["refi"][1], f["cbf"][1], f["mv"][1], f["ats"][1], f["coef_off"][1]]
 
 
+def test_constants_match_header():
+    """the Python mirror of the header's #defines (modes, CU flags, edge flags, has_intra bits, error codes)"""
+    text = (ROOT / "include" / "xevd_b200.h").read_text()
+    d = {k: int(v, 0) for k, v in re.findall(r"#define\s+(XB200_[A-Z0-9_]+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))\)?", text)}
+    want = {"XB200_MODE_INTRA": abi.MODE_INTRA, "XB200_MODE_INTER": abi.MODE_INTER, "XB200_MODE_IBC": abi.MODE_IBC, "XB200_MODE_AFFINE": abi.MODE_AFFINE,
+            "XB200_CUF_LUMA": abi.CUF_LUMA, "XB200_CUF_CHROMA": abi.CUF_CHROMA, "XB200_CUF_SKIP": abi.CUF_SKIP, "XB200_CUF_DMVR": abi.CUF_DMVR,
+            "XB200_CUF_ATS_INTRA": abi.CUF_ATS_INTRA, "XB200_CUF_AFF6": abi.CUF_AFF6,
+            "XB200_EDGE_LEFT": abi.EDGE_LEFT, "XB200_EDGE_TOP": abi.EDGE_TOP, "XB200_EDGE_ATS": abi.EDGE_ATS,
+            "XB200_EDGE_LEFT_NOC": abi.EDGE_LEFT_NOC, "XB200_EDGE_TOP_NOC": abi.EDGE_TOP_NOC,
+            "XB200_HAS_INTRA": abi.HAS_INTRA, "XB200_HAS_DUAL_TREE": abi.HAS_DUAL_TREE}
+    for k, v in want.items():
+        assert d.get(k) == v, (k, d.get(k), v)
+
+
 def test_no_cpu_fallback_without_device():
     lib = abi.load_library()
     if lib.xb200_device_count() > 0:
