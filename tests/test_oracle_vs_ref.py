@@ -323,18 +323,20 @@ def test_recon_frame_dual_tree_ibc(oracle, reference, kw, bd, intra_frac):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
+@pytest.mark.parametrize("ibc", [0.0, 0.5])
 @pytest.mark.parametrize("bd,addb", [(10, 0), (10, 1), (8, 0), (12, 1)])
-def test_deblock_dual_tree(oracle, reference, bd, addb):
+def test_deblock_dual_tree(oracle, reference, bd, addb, ibc):
     """deblock_tree visits the luma leaves as TREE_L and then the node as TREE_C (src_main/xevdm.c:1991-1998): inner leaf edges are
     filtered in luma only, the node's outline in chroma once (xevdm_df.c:155-160,245-250,916-920,986-997)"""
-    w, h, prm, cl, refs = dual_tree_inputs("C", {}, bd, 1, 0, 0.6)
+    w, h, prm, cl, refs = dual_tree_inputs("C", {}, bd, 1, 0, 0.6, ibc=ibc)
     rng = np.random.default_rng(300 + bd + addb)
     prm.tool_addb = addb
     prm.qp_u_offset, prm.qp_v_offset = int(rng.integers(-6, 7)), int(rng.integers(-6, 7))
     base = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
     for pl in base.planes():
         pl[...] = (pl.astype(np.int32) // 8 + (1 << (bd - 1))).astype(np.int16)
-    synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)
+    if not ibc:
+        synth.randomize_deblock_maps(base, cl, rng, intra_frac=0.15)       # else: the maps the reconstruction published (IBC / intra / cbf bits of the leaves)
     tbl, ids = synth.chroma_qp_table(True), ((0, 1), (1, 0))
     a = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
     b = reference.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
