@@ -15,7 +15,10 @@
 #include <stdlib.h>
 #include "orc_common.h"
 
-/* deblocking compares the vectors BEFORE DMVR refinement (map_unrefined_mv, src_main/xevdm.c:2009-2041) */
+/* The ADDB walkers compare the vectors BEFORE DMVR refinement: deblock_tree hands mctx->map_unrefined_mv to xevdm_deblock_cu_hor/ver
+ * (src_main/xevdm.c:2009-2041) and deblock_addb_cu_* use that argument.  The Baseline-filter walkers do not: xevdm_deblock_cu_*
+ * drops the argument when !tool_addb (src_main/xevdm_df.c:1143-1166) and deblock_cu_hor/ver read ctx->map_mv (:111-124,207-208), i.e. the
+ * vectors AFTER refinement - DMVR sub-PU vectors, affine sub-block vectors.  Both reproduced. */
 #define DF_MV(p) ((p)->map_unrefined_mv ? (p)->map_unrefined_mv : (p)->map_mv)
 
 /* xevd_tbl_df_st (src_base/xevd_tbl.c:306-324) */
@@ -97,7 +100,7 @@ static void edge_segment(DfCtx *c, int cur, int nb, int x, int y, int vertical)
     ORC_PIC *p = c->pic;
     const int bdl = c->prm->bit_depth_luma, bdc = c->prm->bit_depth_chroma;
     const int cls = strength_class(p->map_scu[cur], p->map_scu[nb], p->map_refi + 2 * cur, p->map_refi + 2 * nb,
-                                   DF_MV(p) + 4 * cur, DF_MV(p) + 4 * nb);
+                                   p->map_mv + 4 * cur, p->map_mv + 4 * nb);          /* ctx->map_mv: see DF_MV */
     const int qp = (p->map_scu[cur] >> 16) & 0x7f;                       /* QP of the CURRENT side only (T7) */
     const int st = st_lookup(cls, qp) << (bdl - 8);
     if (st && (c->planes & XB200_CUF_LUMA)) {

@@ -379,6 +379,30 @@ def test_recon_frame_constrained_intra(oracle, reference, variant, kw, bd, eipd,
         assert (a.y != c.y).sum() > 50, "test picture does not exercise the constrained HTDF ring"
 
 
+@pytest.mark.parametrize("seed,lg,addb", [(3, 6, 0), (4, 7, 0), (5, 5, 0), (3, 6, 1)])
+def test_deblock_after_dmvr_and_affine(oracle, reference, seed, lg, addb):
+    """which vectors the boundary strength compares once DMVR / affine have run: the ADDB walkers get mctx->map_unrefined_mv
+    (src_main/xevdm.c:2009-2041), the Baseline-filter walkers read ctx->map_mv - refined sub-PU and affine sub-block vectors
+    (src_main/xevdm_df.c:111-124,207-208,1143-1166).  Maps as the reconstruction published them."""
+    w, h = 256, 136
+    prm, cl, refs, alf, flags = synth.make_main_frame(w, h, bit_depth=10, seed=seed, log2_ctu=lg, iqt=bool(seed & 1))
+    prm.tool_addb = addb
+    pic = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    assert (pic.map_mv != pic.map_unrefined_mv).sum() > 50, "test picture has no refined / affine vectors"
+    for pl in pic.planes():                      # small edge steps, so that the strength decides what the filter does
+        pl[...] = (pl.astype(np.int32) // 8 + (1 << 9)).astype(np.int16)
+    tbl, ids = synth.chroma_qp_table(True), ((0, 1), (1, 0))
+    a = oracle.deblock_frame(prm, pic.copy(), cl, tbl, bool(addb), ids)
+    b = reference.deblock_frame(prm, pic.copy(), cl, tbl, bool(addb), ids)
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    if not addb and lg == 7:        # the choice is visible where an edge runs INSIDE a refined CU: the 64-sample transform edge of 128-sample CUs
+        swapped = pic.copy()
+        swapped.map_mv[...] = pic.map_unrefined_mv
+        c = oracle.deblock_frame(prm, swapped, cl, tbl, False, ids)
+        assert any((x != y).any() for x, y in zip(a.planes(), c.planes())), "the two vector maps give the same picture: the case pins nothing"
+
+
 IBC_CASES = [("C", {}, 10, 0.3), ("C", dict(log2_ctu=7), 10, 0.3), ("C", dict(log2_ctu=5), 8, 0.5), ("B", {}, 10, 0.0), ("A", dict(log2_cu=3), 10, 0.2)]
 
 

@@ -711,7 +711,9 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     a.y = cur->y; a.u = cur->u; a.v = cur->v; a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma; a.qp_u_offset = prm->qp_u_offset; a.qp_v_offset = prm->qp_v_offset;
-    a.map_scu = cur->map_scu; a.map_mv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;   // bS compares the vectors before DMVR (T7)
+    // ADDB compares the vectors before DMVR refinement (mctx->map_unrefined_mv, xevdm.c:2009-2041, T7); the Baseline-filter walkers read
+    // ctx->map_mv, the refined / affine sub-block vectors (xevdm_df.c:111-124,1143-1166)
+    a.map_scu = cur->map_scu; a.map_mv = prm->tool_addb ? cur->map_unrefined_mv : cur->map_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
     memcpy(a.cq, c->chroma_qp, sizeof(a.cq));
     a.alpha_offset = prm->deblock_alpha_offset; a.beta_offset = prm->deblock_beta_offset; a.log2_ctu = prm->log2_ctu;
     {   // picture identity of every reference index: first position of the same picture in (list 0 ++ list 1)
