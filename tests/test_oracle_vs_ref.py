@@ -535,3 +535,12 @@ def test_dra_apply(oracle, reference):
     assert (a.y != pic.y).sum() > 1000 and (a.u != pic.u).sum() > 1000
     for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+
+
+@pytest.mark.parametrize("tree,first", [(False, 0), (False, 2000), (True, 0), (True, 2000)])
+def test_random_pipeline_vs_reference(reference, tree, first):
+    """the randomised whole-pipeline cases the GPU is checked on (tests/test_gpu_fuzz.py: random size, bit depth, CTU size, partition,
+    tool mix; with `tree` also local dual tree nodes and constrained intra prediction) - here the oracle against the reference itself:
+    recon, deblocking, ALF, padding.  tools/ref_sweep.py runs the same over any seed range (2500 cases identical at the end of round 1)."""
+    from tools.ref_sweep import sweep
+    assert sweep(first, 40, tree) == []
