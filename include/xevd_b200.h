@@ -179,8 +179,9 @@ typedef struct XB200_PIC_INFO {
     int32_t poc;
     void   *dev_map_edge;         /* uint8[w_scu*h_scu], XB200_EDGE_* flags written by xb200_recon_frame      */
     void   *dev_map_unrefined_mv; /* int16[w_scu*h_scu][2][2]: vectors before DMVR refinement (mctx->map_unrefined_mv,
-                                     read by spatial MV prediction and by deblocking); dev_map_mv holds the refined ones
-                                     (read by temporal MV prediction)                                */
+                                     read by spatial MV prediction and by ADDB deblocking); dev_map_mv holds the refined ones
+                                     (read by temporal MV prediction, SURVEY T12, and by the Baseline deblocking filter,
+                                     src_main/xevdm_df.c:111-124,1143-1166)                                      */
 } XB200_PIC_INFO;
 
 /* ---- context ------------------------------------------------------------------------------------- */
