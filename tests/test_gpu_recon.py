@@ -709,3 +709,41 @@ def test_empty_and_ragged_inputs(ctx, oracle):
     assert not cur2.download().y.any()
     for p in drefs + [cur, cur2]:
         p.free()
+
+
+@pytest.mark.parametrize("lg,iqt,seed", [(6, True, 31), (7, False, 32)])
+def test_4k_main_full_pipeline(ctx, oracle, lg, iqt, seed):
+    """BASELINE config 3 at its full size: a 3840x2160 10-bit Main-profile picture with every hot-path tool on (BTT + SUCO partition,
+    1/16-pel taps, IQT, ATS, EIPD, IBC, HTDF, DMVR, affine) through xb200_recon_frame -> xb200_deblock (ADDB) -> xb200_alf -> xb200_pad,
+    planes (with borders) and per-SCU maps bit-exact against the oracle"""
+    w, h = 3840, 2160
+    prm, cl, refs, alf, flags = synth.make_main_frame(w, h, bit_depth=10, seed=seed, log2_ctu=lg, iqt=iqt)
+    cl.validate()
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(True))
+    try:
+        ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+        got = cur.download(maps=True)
+        for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+            assert np.array_equal(a, b), f"recon plane {n}: {int((a != b).sum())} samples differ"
+        assert np.array_equal(got.map_mv, want.map_mv) and np.array_equal(got.map_refi, want.map_refi) and np.array_equal(got.map_scu, want.map_scu)
+        assert np.array_equal(got.map_unrefined_mv, want.map_unrefined_mv)
+        oracle.deblock_frame(prm, want, cl, synth.chroma_qp_table(True), True, ((0, 1), (1, 0)))
+        oracle.alf_frame(prm, want, alf, flags)
+        oracle.pad(want)
+        ctx.deblock(prm, cur, drefs, drefs[::-1])
+        ctx.alf(prm, cur, alf, flags)
+        ctx.pad(cur)
+        out = cur.download_padded()
+        assert np.array_equal(out.buf_y, want.buf_y) and np.array_equal(out.buf_u, want.buf_u) and np.array_equal(out.buf_v, want.buf_v)
+    finally:
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+        for p in drefs + [cur]:
+            p.free()
+
+
+def test_8k_parity_vs_oracle(ctx, oracle):
+    """BASELINE config 4's picture size on one GPU: 7680x4320 10-bit config 2A bit-exact against the oracle (planes and maps)"""
+    _run(ctx, oracle, 7680, 4320, 10, "A", seed=12, n_refs=1)
