@@ -200,6 +200,10 @@ long long xb200_launch_count(xb200_ctx *ctx);             /* kernels launched by
  * src_base/xevd.c:1685-1738; an integration allocates it with xb200_host_alloc instead) */
 void *xb200_host_alloc(size_t bytes);
 void  xb200_host_free(void *p);
+/* page-lock memory the caller already owns (the XEVD_IMGB planes xevd_picbuf_alloc allocates, src_base/xevd_util.c:153-230), so that
+ * xb200_pic_download into it is a true asynchronous DMA; returns XB200_OK or XB200_ERR_CUDA */
+int   xb200_host_register(void *p, size_t bytes);
+int   xb200_host_unregister(void *p);
 
 /* ---- pictures (PICBUF_ALLOCATOR) ------------------------------------------------------------------ */
 xb200_pic *xb200_pic_alloc(xb200_ctx *ctx, int w, int h, int *err);

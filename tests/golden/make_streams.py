@@ -1,0 +1,72 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/streams/*.evc (+ .md5 of every decoded picture as the UNMODIFIED reference produces it).
+
+The reference ships no streams and the box has no encoder: the streams come from tools/evcgen (the reference's own
+syntax parser run as a generator).  Every stream is kept only if (1) the unmodified reference decodes it to the generator's own
+pictures, and (2) the reference's application built with AddressSanitizer (tools/evcgen `make asan`) decodes it without touching
+memory out of bounds - i.e. it is a stream the reference decoder is well defined on.
+Run (needs /root/reference):  make -C tools/evcgen all asan && python tests/golden/make_streams.py"""
+import hashlib
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tools" / "evcgen"))
+import evcgen as G  # noqa: E402
+from xevd_b200 import xevd_api as X  # noqa: E402
+
+OUT = Path(__file__).resolve().parent / "streams"
+ASAN = ROOT / "tools" / "evcgen" / "_build" / "xevd_app_asan"
+
+# name: (tool set, tool overrides, generator arguments)
+STREAMS = {
+    "base_i_64x64_8b": ("baseline", {}, dict(w=64, h=64, bd=8, frames=4, seed=1, types="I")),
+    "base_ipb_128x64_8b": ("baseline", {}, dict(w=128, h=64, bd=8, frames=8, seed=3, types="IPB")),
+    "base_ipbb_320x192_10b": ("baseline", {}, dict(w=320, h=192, bd=10, frames=8, seed=5, types="IPBB")),
+    "base_ibp_256x128_8b_qp38": ("baseline", {}, dict(w=256, h=128, bd=8, frames=6, seed=9, types="IBP", qp=38)),
+    "base_ipp_200x120_10b_nodbk": ("baseline", {}, dict(w=200, h=120, bd=10, frames=5, seed=11, types="IPP", deblock=0)),
+    "base_ipb_416x240_8b_cip": ("baseline", {}, dict(w=416, h=240, bd=8, frames=6, seed=13, types="IPB", constrained_intra=1)),
+}
+
+
+def pic_md5(p):
+    return hashlib.md5(p[0].tobytes() + p[1].tobytes() + p[2].tobytes()).hexdigest()
+
+
+def main():
+    only = set(sys.argv[1:])
+    g = G.Generator()
+    ref = X.XevdLibrary(X.REF_SO)
+    OUT.mkdir(exist_ok=True)
+    for name, (profile, over, kw) in STREAMS.items():
+        if only and name not in only:
+            continue
+        tools = dict(G.BASELINE if profile == "baseline" else G.MAIN)
+        tools.update(over)
+        kw = dict(kw)
+        for attempt in range(20):
+            nals, own = g.make(tools, **kw)
+            path = OUT / f"{name}.evc"
+            X.write_stream(path, nals)
+            pics = X.decode_stream(ref, nals)
+            ok = G.same_pictures(own, pics)
+            why = "" if ok else "reference != generator"
+            if ok and ASAN.exists():
+                r = subprocess.run([str(ASAN), "-i", str(path), "-o", "/dev/null", "--output-bit-depth", "10"], capture_output=True, text=True)
+                if "ERROR: AddressSanitizer" in r.stderr or r.returncode != 0:
+                    ok, why = False, "AddressSanitizer: " + next((l for l in r.stderr.splitlines() if "SUMMARY" in l), f"rc {r.returncode}")
+            if ok:
+                (OUT / f"{name}.md5").write_text("".join(pic_md5(p) + "\n" for p in pics))
+                print(f"{name}: {len(nals)} NAL units, {path.stat().st_size} bytes, {len(pics)} pictures (seed {kw['seed']})")
+                break
+            print(f"{name}: seed {kw['seed']} rejected ({why})")
+            kw["seed"] += 1000
+        else:
+            path.unlink(missing_ok=True)
+            print(f"{name}: no conforming stream found")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,238 @@
+#!/usr/bin/env python3
+"""evcgen -- random but syntactically valid MPEG-5 EVC elementary streams for decoder parity tests (test tooling).
+
+There is no EVC encoder and no conformance stream on the build box.  This tool writes the parameter sets and
+slice headers bit by bit (field order: xevdm_eco_sps / xevdm_eco_pps / xevdm_eco_sh, src_main/xevdm_eco.c:1847,2006,2510) and lets the
+reference's OWN slice-data parser generate the slice data: tools/evcgen/_build/libxevd_gen.so is the unmodified decoder whose CABAC
+decoding primitives choose-and-encode instead of decode (gen_engine.c).  Every stream is then decoded by the unmodified reference
+(oracle/_ref/libxevd_ref.so) as a self-check: it must parse without error and reproduce the generator's own pictures.
+
+    python tools/evcgen/evcgen.py --out tests/golden/streams/base_64x64.evc --profile baseline --w 64 --h 64 --frames 6
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+from xevd_b200 import xevd_api as X  # noqa: E402
+
+GEN_SO = Path(__file__).resolve().parent / "_build" / "libxevd_gen.so"
+
+
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def u(self, v, n):
+        for i in range(n - 1, -1, -1):
+            self.bits.append((v >> i) & 1)
+
+    def ue(self, v):
+        v += 1
+        n = v.bit_length()
+        self.u(0, n - 1)
+        self.u(v, n)
+
+    def se(self, v):
+        self.ue(2 * v - 1 if v > 0 else -2 * v)
+
+    def align(self):
+        while len(self.bits) % 8:
+            self.bits.append(0)
+
+    def bytes(self):
+        self.align()
+        return bytes(int("".join(map(str, self.bits[i:i + 8])), 2) for i in range(0, len(self.bits), 8))
+
+
+def nal_header(nut, tid=0):
+    b = BitWriter()
+    b.u(0, 1); b.u(nut + 1, 6); b.u(tid, 3); b.u(0, 5); b.u(0, 1)
+    return b
+
+
+# tool sets -------------------------------------------------------------------------------------------------------------------
+BASELINE = dict(btt=0, suco=0, admvp=0, affine=0, amvr=0, dmvr=0, mmvd=0, hmvp=0, eipd=0, ibc=0, cm_init=0, adcc=0, iqt=0, ats=0,
+                addb=0, alf=0, htdf=0, rpl=0, pocs=0, dquant=0, dra=0)
+MAIN = dict(btt=1, suco=1, admvp=1, affine=1, amvr=1, dmvr=1, mmvd=1, hmvp=1, eipd=1, ibc=0, cm_init=1, adcc=1, iqt=1, ats=1,
+            addb=1, alf=0, htdf=1, rpl=0, pocs=0, dquant=0, dra=0)
+
+
+def write_sps(t, w, h, bd, max_refs=2, log2_ctu=6):
+    b = nal_header(X.NUT_SPS)
+    b.ue(0)                                # sps_seq_parameter_set_id
+    b.u(1 if t["btt"] or t["admvp"] or t["eipd"] or t["iqt"] else 0, 8)          # profile_idc (0 baseline, 1 main)
+    b.u(51, 8)                             # level_idc
+    b.u(0, 32); b.u(0, 32)                 # toolset_idc_h / _l (not interpreted by the decoder)
+    b.ue(1)                                # chroma_format_idc 4:2:0
+    b.ue(w); b.ue(h)
+    b.ue(bd - 8); b.ue(bd - 8)
+    b.u(t["btt"], 1)
+    if t["btt"]:
+        b.ue(log2_ctu - 5)                 # log2_ctu_size_minus5
+        b.ue(0)                            # log2_min_cb_size_minus2
+        b.ue(0)                            # log2_diff_ctu_max_14_cb_size
+        b.ue(0)                            # log2_diff_ctu_max_tt_cb_size
+        b.ue(0)                            # log2_diff_min_cb_min_tt_cb_size_minus2
+    b.u(t["suco"], 1)
+    if t["suco"]:
+        b.ue(0); b.ue(2 if log2_ctu > 5 else 1)      # log2_diff_ctu_size_max_suco_cb_size, log2_diff_max_suco_min_suco_cb_size
+    b.u(t["admvp"], 1)
+    if t["admvp"]:
+        for k in ("affine", "amvr", "dmvr", "mmvd", "hmvp"):
+            b.u(t[k], 1)
+    b.u(t["eipd"], 1)
+    if t["eipd"]:
+        b.u(t["ibc"], 1)
+        if t["ibc"]:
+            b.ue(2)
+    b.u(t["cm_init"], 1)
+    if t["cm_init"]:
+        b.u(t["adcc"], 1)
+    b.u(t["iqt"], 1)
+    if t["iqt"]:
+        b.u(t["ats"], 1)
+    b.u(t["addb"], 1); b.u(t["alf"], 1); b.u(t["htdf"], 1); b.u(t["rpl"], 1); b.u(t["pocs"], 1); b.u(t["dquant"], 1); b.u(t["dra"], 1)
+    if t["pocs"]:
+        b.ue(4)
+    if not t["rpl"] or not t["pocs"]:
+        b.ue(0)                            # log2_sub_gop_length = 0: low delay
+        b.ue(0)                            # log2_ref_pic_gap_length
+    assert not t["rpl"]
+    b.ue(max_refs)                         # max_num_ref_pics
+    b.u(0, 1)                              # picture_cropping_flag
+    b.u(0, 1)                              # chroma_qp_table_present_flag
+    b.u(0, 1)                              # vui_parameters_present_flag
+    return b.bytes()
+
+
+def write_pps(constrained_intra=0, cu_qp_delta=0):
+    b = nal_header(X.NUT_PPS)
+    b.ue(0); b.ue(0)                       # pps id, sps id
+    b.ue(0); b.ue(0)                       # num_ref_idx_default_active_minus1[0..1]
+    b.ue(0)                                # additional_lt_poc_lsb_len
+    b.u(0, 1)                              # rpl1_idx_present_flag
+    b.u(1, 1)                              # single_tile_in_pic_flag
+    b.ue(0)                                # tile_id_len_minus1
+    b.u(0, 1)                              # explicit_tile_id_flag
+    b.u(0, 1)                              # pic_dra_enabled_flag
+    b.u(0, 1)                              # arbitrary_slice_present_flag
+    b.u(constrained_intra, 1)
+    b.u(cu_qp_delta, 1)
+    if cu_qp_delta:
+        b.ue(0)                            # cu_qp_delta_area - 6
+    return b.bytes()
+
+
+def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_v_off=0, tid=0):
+    b = nal_header(nut, tid)
+    b.ue(0)                                # slice_pic_parameter_set_id
+    b.ue(slice_type)
+    if nut == X.NUT_IDR:
+        b.u(0, 1)                          # no_output_of_prior_pics_flag
+    if t["mmvd"] and slice_type in (X.ST_B, X.ST_P):
+        b.u(1, 1)                          # mmvd_group_enable_flag
+    if t["alf"]:
+        b.u(0, 1)                          # alf_on (no APS in these streams)
+    if slice_type != X.ST_I:
+        b.u(0, 1)                          # num_ref_idx_active_override_flag
+        if t["admvp"]:
+            b.u(0, 1)                      # temporal_mvp_asigned_flag
+    b.u(deblock, 1)
+    if deblock and t["addb"]:
+        b.se(alpha); b.se(beta)
+    b.u(qp, 6)
+    b.se(qp_u_off); b.se(qp_v_off)
+    return b.bytes()
+
+
+class Generator:
+    def __init__(self):
+        if not GEN_SO.exists():
+            raise RuntimeError(f"{GEN_SO} missing: make -C tools/evcgen (needs /root/reference)")
+        self.lib = X.XevdLibrary(GEN_SO)
+        L = self.lib.lib
+        L.gen_reset.argtypes = [C.c_uint64, C.c_int, C.c_int]
+        L.gen_reset.restype = None
+        L.gen_take.argtypes = [C.c_void_p, C.c_size_t]
+        L.gen_take.restype = C.c_size_t
+        L.gen_selfcheck.restype = C.c_longlong
+
+    def make(self, tools, w, h, bd, frames, seed, types="IPB", qp=30, lps_scale=256, ep_one=128, log2_ctu=6, deblock=1, gop=0, **pps_kw):
+        """returns (list of NAL units, pictures the generator's own decode produced in output order)"""
+        rng = np.random.default_rng(seed)
+        L = self.lib.lib
+        nals, pics = [], []
+        tail = bytes(max(1 << 17, w * h * 8))
+        with X.Decoder(self.lib) as d:
+            for n in (write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(**pps_kw)):
+                ret, _ = d.decode(n)
+                assert ret >= 0, ("parameter set rejected", ret)
+                nals.append(n)
+            for f in range(frames):
+                idr = f == 0 or (gop and f % gop == 0)
+                st = X.ST_I if idr else {"I": X.ST_I, "P": X.ST_P, "B": X.ST_B}[types[1 + (f - 1) % (len(types) - 1)]] if len(types) > 1 else X.ST_I
+                hdr = write_sh(tools, X.NUT_IDR if idr else X.NUT_NONIDR, st, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), deblock=deblock,
+                               alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)), qp_u_off=int(rng.integers(-3, 4)),
+                               qp_v_off=int(rng.integers(-3, 4)))
+                L.gen_reset(int(seed) * 1000003 + f, lps_scale, ep_one)
+                ret, stat = d.decode(hdr + tail)
+                assert ret >= 0, ("generator decode failed", f, ret)
+                buf = (C.c_ubyte * len(tail))()
+                n = L.gen_take(buf, len(tail))
+                assert n > 0, "slice data not terminated"
+                bad = L.gen_selfcheck()
+                assert bad < 0, f"arithmetic encoder self-check: bin {bad} of picture {f} does not decode as chosen"
+                nals.append(hdr + bytes(buf[:n]))
+                while True:
+                    p = d.pull()
+                    if p is None:
+                        break
+                    pics.append(p)
+            while True:
+                p = d.pull()
+                if p is None:
+                    break
+                pics.append(p)
+        return nals, pics
+
+
+def same_pictures(a, b):
+    return len(a) == len(b) and all(np.array_equal(x, y) for pa, pb in zip(a, b) for x, y in zip(pa, pb))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--profile", default="baseline", choices=["baseline", "main"])
+    ap.add_argument("--w", type=int, default=64)
+    ap.add_argument("--h", type=int, default=64)
+    ap.add_argument("--bd", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=4)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--types", default="IPB")
+    ap.add_argument("--qp", type=int, default=30)
+    ap.add_argument("--lps-scale", type=int, default=256)
+    ap.add_argument("--set", action="append", default=[], help="tool=0/1 overrides, e.g. --set dmvr=0")
+    args = ap.parse_args()
+    tools = dict(BASELINE if args.profile == "baseline" else MAIN)
+    for kv in args.set:
+        k, v = kv.split("=")
+        tools[k] = int(v)
+    g = Generator()
+    nals, own = g.make(tools, args.w, args.h, args.bd, args.frames, args.seed, args.types, args.qp, args.lps_scale)
+    ref = X.decode_stream(X.XevdLibrary(X.REF_SO), nals)
+    ok = same_pictures(own, ref)
+    X.write_stream(args.out, nals)
+    print(f"{args.out}: {len(nals)} NAL units, {sum(map(len, nals))} bytes, {len(ref)} pictures; unmodified reference reproduces the generator's pictures: {ok}")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

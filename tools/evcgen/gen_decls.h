@@ -1,0 +1,7 @@
+/* force-included when tools/evcgen/Makefile compiles the reference's xevd_eco.c / xevdm_eco.c with the DEFINITIONS of the CABAC
+ * decoding primitives renamed away: their uses then bind to the generator's versions (gen_engine.c) */
+#include "xevd_def.h"
+u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model);
+u32 sbac_decode_bin_ep(XEVD_BSR *bs, XEVD_SBAC *sbac);
+u32 xevd_sbac_decode_bin_trm(XEVD_BSR *bs, XEVD_SBAC *sbac);
+u32 gen_run(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, int max_run);

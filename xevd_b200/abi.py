@@ -121,6 +121,8 @@ _SIGS = {
     "xb200_launch_count": (C.c_longlong, [C.c_void_p]),
     "xb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "xb200_host_free": (None, [C.c_void_p]),
+    "xb200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "xb200_host_unregister": (C.c_int, [C.c_void_p]),
     "xb200_pic_alloc": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "xb200_pic_free": (None, [C.c_void_p, C.c_void_p]),
     "xb200_pic_info": (C.c_int, [C.c_void_p, C.POINTER(PicInfo)]),

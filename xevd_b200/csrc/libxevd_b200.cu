@@ -227,6 +227,18 @@ void *xb200_host_alloc(size_t bytes)
     return p;
 }
 void xb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+int xb200_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return XB200_ERR_INVALID_ARGUMENT;
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return XB200_ERR_CUDA; }
+    return XB200_OK;
+}
+int xb200_host_unregister(void *p)
+{
+    if (!p) return XB200_ERR_INVALID_ARGUMENT;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return XB200_ERR_CUDA; }
+    return XB200_OK;
+}
 
 // ---- pictures ---------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -461,7 +473,10 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     if (has_intra && prm->ctu_rows > 0) return XB200_ERR_UNSUPPORTED;          // the wavefront crosses band boundaries
     // throughput kernel (xb_recon2.cuh): 64x64 CTUs, Baseline or IQT transform; with ATS / DMVR / affine enabled it takes the CTUs that hold
     // no such CU and the generic kernel (xb_recon.cuh) the others
-    const bool fast = a.log2_ctu == 6 && !c->force_generic;
+    // The throughput kernel sizes its on-chip work lists for at most 256 CUs per CTU (a 64x64 CTU of 4x4 CUs).  Local dual tree nodes
+    // can exceed that (four 4x4 luma leaves + one chroma CU per 8x8 node: up to 320): such pictures go through the generic kernel.
+    const bool many_cus = max_cu_per_ctu > 256 || (max_cu_per_ctu <= 0 && (has_intra & XB200_HAS_DUAL_TREE));
+    const bool fast = a.log2_ctu == 6 && !c->force_generic && !many_cus;
     const bool mixed = fast && (a.ats || a.dmvr || a.affine || (has_intra & XB200_HAS_DUAL_TREE));     // dual-tree CUs need per-plane owners
     a.dispatch = mixed ? 1 : 0;
     if (a.n_peer > 0 && (!fast || mixed || a.iqt)) return XB200_ERR_UNSUPPORTED;        // peer stores exist in the throughput kernel only; use the all-gather exchange

@@ -31,6 +31,9 @@
 
 namespace xb {
 
+#ifndef XB_R2_MINB
+#define XB_R2_MINB 2
+#endif
 constexpr int kR2Threads = 256;
 constexpr int kTileCap = 16;                 // 16x16 luma tiles staged per round (a whole 64x64 CTU)
 constexpr int kBoxLW = 40, kBoxLH = 23;      // luma TMA box: (offset <= 7) + 16 + 7 = 30 -> 40 samples keeps the row stride
@@ -263,7 +266,7 @@ __device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstrid
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
 // local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
 template <bool BI, bool PEER = false, bool IQT = false, bool DISP = false>
-__global__ void __launch_bounds__(kR2Threads, 2)
+__global__ void __launch_bounds__(kR2Threads, XB_R2_MINB)
 k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -285,7 +288,9 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctu = blockIdx.y * a.w_ctu + blockIdx.x;
     const int ctu_x = blockIdx.x << 6, ctu_y = (blockIdx.y + a.ctu_row0) << 6;
-    const int cu0 = a.ctu_first[ctu], ncu = a.ctu_first[ctu + 1] - cu0;
+    // the host entry points route pictures with more CUs per CTU than the lists hold to the generic kernel; the clamp keeps a wrong
+    // max_cu_per_ctu handed to the _dev entry from overrunning shared memory
+    const int cu0 = a.ctu_first[ctu], ncu = min((int)(a.ctu_first[ctu + 1] - cu0), max_cu);
 
     // ---- stage CU descriptors, init barriers, build tap tables ----------------------------------------------------------------
     {
