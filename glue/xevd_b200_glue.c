@@ -482,6 +482,25 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
         free(of_ctu);
         cus = g->cus2; coef = g->coef2;
     }
+    {   /* debugging aid: XEVD_B200_DUMP=<directory> writes the work lists of every slice (tools/glue_dump.py reads them back) */
+        const char *dir = getenv("XEVD_B200_DUMP");
+        if (dir) {
+            static int serial;
+            char fn[512];
+            snprintf(fn, sizeof(fn), "%s/slice_%04d.bin", dir, serial++);
+            FILE *fp = fopen(fn, "wb");
+            if (fp) {
+                int32_t hdr[8] = { g->n_cu, n_ctu, g->n_ext, (int32_t)g->n_coef, g->n0, g->n1, ctx->sh.slice_type, ctx->sh.deblocking_filter_on };
+                int32_t pocs[2 * XEVD_MAX_NUM_REF_PICS] = {0};
+                for (int i = 0; i < g->n0; i++) pocs[i] = ctx->refp[i][REFP_0].poc;
+                for (int i = 0; i < g->n1; i++) pocs[XEVD_MAX_NUM_REF_PICS + i] = ctx->refp[i][REFP_1].poc;
+                fwrite(hdr, sizeof(hdr), 1, fp); fwrite(&g->prm, sizeof(g->prm), 1, fp); fwrite(pocs, sizeof(pocs), 1, fp);
+                fwrite(cus, sizeof(XB200_CU), (size_t)g->n_cu, fp); fwrite(g->ctu_first, 4, (size_t)n_ctu + 1, fp);
+                fwrite(g->ext, sizeof(XB200_CU_EXT), (size_t)g->n_ext, fp); fwrite(coef, 2, g->n_coef, fp);
+                fclose(fp);
+            }
+        }
+    }
     if (g->n_cu > 0) {
         {   /* the sequence's chroma QP mapping (xevd_set_chroma_qp_tbl_loc / xevd_derived_chroma_qp_mapping_tables, xevdm.c:471-486) */
             int32_t tbl[2][XEVD_MAX_QP_TABLE_SIZE];
@@ -490,7 +509,7 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
         }
         int r = xb200_recon_frame(g->dev, &g->prm, cur->dev, g->l0, g->n0, g->l1, g->n1, cus, g->n_cu, g->ctu_first, n_ctu,
                                   g->ext, g->n_ext, coef, g->n_coef);
-        if (r < 0) { dev_fail(g, XEVD_ERR, "xb200_recon_frame"); return g->err; }
+        if (r < 0) { fprintf(stderr, "[xevd-b200] xb200_recon_frame: %d, slice type %d, lists %d / %d\n", r, ctx->sh.slice_type, g->n0, g->n1); dev_fail(g, XEVD_ERR, "xb200_recon_frame"); return g->err; }
         g->n_cus_total += g->n_cu;
     }
     return ret;

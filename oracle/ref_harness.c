@@ -168,6 +168,92 @@ static void wrap_pic(const ORC_PIC *o, XEVD_PIC *p)
 
 typedef struct { pel pred[REFP_NUM][N_C][MAX_CU_DIM]; s16 coef[N_C][MAX_CU_DIM]; pel nb[N_C][N_REF][MAX_CU_SIZE * 3]; } REF_SCRATCH;
 
+/* ---- per-SCU map publication through the reference's OWN xevdm_set_dec_info (src_main/xevdm_util.c:4205-4389) ---------------
+ * A zeroed XEVDM_CTX / XEVDM_CORE pair carries exactly the fields that function reads; the core is filled from the work item the way
+ * cu_init (src_main/xevdm.c:1022) and the motion derivation leave it.  Nothing here writes a map entry itself. */
+typedef struct {
+    XEVDM_CTX *m; XEVDM_CORE *k; XEVD_SPS sps;
+    s8 *map_ipm; u32 *map_affine, *map_cu_mode; u8 *map_ats_inter; s16 *own_unref;
+} REF_INFO;
+static void info_open(REF_INFO *I, const XB200_PARAMS *prm, ORC_PIC *cur, u32 *map_scu)
+{
+    const int f_scu = cur->w_scu * cur->h_scu;
+    memset(I, 0, sizeof(*I));
+    I->m = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX));
+    I->k = (XEVDM_CORE *)calloc(1, sizeof(XEVDM_CORE));
+    I->map_ipm = (s8 *)calloc(f_scu, 1); I->map_affine = (u32 *)calloc(f_scu, 4); I->map_cu_mode = (u32 *)calloc(f_scu, 4);
+    I->map_ats_inter = (u8 *)calloc(f_scu, 1);
+    I->sps.chroma_format_idc = prm->chroma_format_idc;
+    XEVD_CTX *c = &I->m->bctx;
+    c->sps = &I->sps;
+    c->w_scu = cur->w_scu; c->h_scu = cur->h_scu;
+    c->map_scu = map_scu;
+    c->map_refi = (s8(*)[REFP_NUM])cur->map_refi;
+    c->map_mv = (s16(*)[REFP_NUM][MV_D])cur->map_mv;
+    if (!cur->map_unrefined_mv) I->own_unref = (s16 *)calloc(f_scu, 8);
+    I->m->map_unrefined_mv = (s16(*)[REFP_NUM][MV_D])(cur->map_unrefined_mv ? cur->map_unrefined_mv : I->own_unref);
+    c->map_ipm = I->map_ipm; c->map_cu_mode = I->map_cu_mode;
+    I->m->map_affine = I->map_affine; I->m->map_ats_inter = I->map_ats_inter;
+    c->pps.cu_qp_delta_enabled_flag = 1;          /* map_scu takes core->qp (xevdm_util.c:4303-4306) = XB200_CU.qp_map */
+    c->slice_num = 0;
+}
+static void info_close(REF_INFO *I)
+{
+    free(I->m); free(I->k); free(I->map_ipm); free(I->map_affine); free(I->map_cu_mode); free(I->map_ats_inter); free(I->own_unref);
+}
+/* dmvr_mv / dmvr_flag: what xevdm_mc returned for this CU (NULL / 0 otherwise) */
+static void info_publish(REF_INFO *I, const XB200_PARAMS *prm, ORC_PIC *cur, const XB200_CU *cu, const XB200_CU_EXT *ext,
+                         int dmvr_flag, s16 (*dmvr_mv)[REFP_NUM][MV_D])
+{
+    XEVD_CORE *k = &I->k->core;
+    XEVDM_CORE *mk = I->k;
+    const int do_l = (cu->flags & XB200_CUF_LUMA) != 0, do_c = (cu->flags & XB200_CUF_CHROMA) != 0;
+    int l, i;
+    if (!cur->map_mv || !cur->map_refi) return;
+    mk->tree_cons = (TREE_CONS){ FALSE, do_l && do_c ? TREE_LC : (do_l ? TREE_L : TREE_C), do_l && do_c ? eAll : eOnlyIntra };
+    k->scup = (cu->y >> 2) * cur->w_scu + (cu->x >> 2);
+    k->log2_cuw = cu->log2w; k->log2_cuh = cu->log2h;
+    k->qp = cu->qp_map;
+    mk->affine_flag = 0; mk->ibc_flag = 0; mk->mmvd_flag = 0; mk->dmvr_flag = 0; mk->ats_inter_info = 0;
+    memset(k->mv, 0, sizeof(k->mv));
+    k->refi[0] = k->refi[1] = -1;
+    k->ipm[0] = k->ipm[1] = 0;
+    for (l = 0; l < N_C; l++) {
+        const int bits = (cu->cbf >> (4 * l)) & 15;
+        k->is_coef[l] = bits != 0;
+        for (i = 0; i < MAX_SUB_TB_NUM; i++) k->is_coef_sub[l][i] = (bits >> i) & 1;
+    }
+    if (cu->mode == XB200_MODE_INTRA) {
+        k->pred_mode = MODE_INTRA;
+        k->ipm[0] = cu->refi[0]; k->ipm[1] = cu->refi[1];
+    } else if (cu->mode == XB200_MODE_IBC) {
+        k->pred_mode = MODE_IBC; mk->ibc_flag = 1;
+        k->mv[0][0] = cu->mv[0][0]; k->mv[0][1] = cu->mv[0][1];
+    } else {
+        /* DMVR is only ever enabled for skip and direct-mode CUs (xevdm.c:1273-1288) */
+        k->pred_mode = (cu->flags & XB200_CUF_SKIP) ? MODE_SKIP : ((cu->flags & XB200_CUF_DMVR) ? MODE_DIR : MODE_INTER);
+        k->refi[0] = cu->refi[0]; k->refi[1] = cu->refi[1];
+        if (prm->tool_ats) mk->ats_inter_info = get_ats_inter_info(XB200_ATS_INTER_IDX(cu->ats), XB200_ATS_INTER_POS(cu->ats));
+        if (cu->mode == XB200_MODE_AFFINE) {
+            uint32_t ei; int v;
+            memcpy(&ei, cu->mv[1], 4);
+            mk->affine_flag = (cu->flags & XB200_CUF_AFF6) ? 2 : 1;
+            memset(mk->affine_mv, 0, sizeof(mk->affine_mv));
+            for (l = 0; l < 2; l++) {
+                for (v = 0; v < 3; v++) { mk->affine_mv[l][v][0] = ext[ei].u.affine.cp[l][v][0]; mk->affine_mv[l][v][1] = ext[ei].u.affine.cp[l][v][1]; }
+                k->mv[l][0] = ext[ei].u.affine.mv_unref[l][0]; k->mv[l][1] = ext[ei].u.affine.mv_unref[l][1];
+            }
+        } else {
+            for (l = 0; l < 2; l++) { k->mv[l][0] = cu->mv[l][0]; k->mv[l][1] = cu->mv[l][1]; }
+            if (dmvr_flag) {
+                mk->dmvr_flag = 1;
+                memcpy(mk->dmvr_mv, dmvr_mv, sizeof(mk->dmvr_mv));
+            }
+        }
+    }
+    xevdm_set_dec_info(&I->m->bctx, k);
+}
+
 int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
                     const ORC_PIC *const *refs_l0, int n_l0, const ORC_PIC *const *refs_l1, int n_l1,
                     const XB200_CU *cus, int n_cu, const XB200_CU_EXT *ext, const int16_t *coef)
@@ -189,10 +275,10 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
 
     /* the intra flags are in map_scu from the parsing pass of the CTU (xevdm_set_dec_info in xevd_entropy_dec_unit), i.e. before any CU
      * of it is reconstructed; only luma-carrying CUs publish (xevdm_util.c:4241).  Read under pps.constrained_intra_pred_flag. */
-    for (n = 0; n < n_cu; n++)
-        if (cus[n].mode == XB200_MODE_INTRA && (cus[n].flags & XB200_CUF_LUMA))
-            for (l = 0; l < (1 << (cus[n].log2h - 2)); l++)
-                for (i = 0; i < (1 << (cus[n].log2w - 2)); i++) MCU_SET_IF(map_scu[((cus[n].y >> 2) + l) * cur->w_scu + (cus[n].x >> 2) + i]);
+    REF_INFO info;
+    info_open(&info, prm, cur, map_scu);
+    for (n = 0; n < n_cu; n++)          /* the parsing pass: xevdm_set_dec_info of every CU (intra flags, QP, modes); inter CUs again after MC below */
+        info_publish(&info, prm, cur, &cus[n], ext, 0, NULL);
     for (n = 0; n < n_cu; n++) {
         const XB200_CU *cu = &cus[n];
         const int w = 1 << cu->log2w, h = 1 << cu->log2h, cw = w >> 1, ch = h >> 1;
@@ -260,7 +346,6 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         } else if (cu->mode == XB200_MODE_AFFINE) {
             /* xevdm_affine_mc (src_main/xevdm_mc.c:2606) + the per-SCU vectors of xevdm_set_affine_mvf (src_main/xevdm_util.c:4095) */
             static pel eif_tmp[(MAX_CU_SIZE + 2) * (MAX_CU_SIZE + 2)];
-            static XEVDM_CTX *fctx; static XEVDM_CORE *fcore;
             uint32_t ei;
             s16 amv[REFP_NUM][VER_NUM][MV_D];
             int v;
@@ -270,21 +355,7 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             select_mc_tables(prm->tool_admvp ? 1 : 0);
             xevdm_affine_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, amv, refp, s->pred, (cu->flags & XB200_CUF_AFF6) ? 3 : 2, eif_tmp,
                             prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
-            if (cur->map_mv) {
-                if (!fctx) { fctx = (XEVDM_CTX *)calloc(1, sizeof(XEVDM_CTX)); fcore = (XEVDM_CORE *)calloc(1, sizeof(XEVDM_CORE)); }
-                for (l = 0; l < (h >> 2); l++)
-                    for (i = 0; i < (w >> 2); i++) {          /* xevdm_set_dec_info first stores core->mv everywhere */
-                        s16 *o = cur->map_mv + (scup + l * cur->w_scu + i) * 4;
-                        o[0] = ext[ei].u.affine.mv_unref[0][0]; o[1] = ext[ei].u.affine.mv_unref[0][1];
-                        o[2] = ext[ei].u.affine.mv_unref[1][0]; o[3] = ext[ei].u.affine.mv_unref[1][1];
-                    }
-                fctx->bctx.map_mv = (s16(*)[REFP_NUM][MV_D])cur->map_mv; fctx->bctx.w_scu = cur->w_scu;
-                fcore->core.scup = scup; fcore->core.log2_cuw = cu->log2w; fcore->core.log2_cuh = cu->log2h;
-                fcore->core.refi[0] = refi[0]; fcore->core.refi[1] = refi[1];
-                fcore->affine_flag = (cu->flags & XB200_CUF_AFF6) ? 2 : 1;
-                memcpy(fcore->affine_mv, amv, sizeof(amv));
-                xevdm_set_affine_mvf(&fctx->bctx, &fcore->core);
-            }
+            info_publish(&info, prm, cur, cu, ext, 0, NULL);          /* xevdm_set_dec_info incl. xevdm_set_affine_mvf (src_main/xevdm.c:1333) */
         } else if (cu->mode == XB200_MODE_INTER && prm->tool_dmvr) {
             /* Main xevdm_mc with the DMVR scratch buffers of XEVDM_CORE (src_main/xevdm_def.h:505-530); it leaves the averaged
              * prediction in pred[0], the refined vectors per SCU in dmvr_mv and restores mv[] */
@@ -296,19 +367,13 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
             u8 dmvr_flag = 0;
             xevdm_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, mv, refp, s->pred, prm->poc, tmpl, interp, halfp, (cu->flags & XB200_CUF_DMVR) ? 1 : 0,
                      padbuf, &dmvr_flag, dmvr_mv, prm->tool_admvp, prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
-            if (cur->map_mv)          /* what xevdm_set_dec_info would publish: refined vectors for DMVR CUs */
-                for (l = 0; l < (h >> 2); l++)
-                    for (i = 0; i < (w >> 2); i++) {
-                        s16 *o = cur->map_mv + (scup + l * cur->w_scu + i) * 4;
-                        const int k = l * (w >> 2) + i;
-                        o[0] = dmvr_flag ? dmvr_mv[k][0][0] : mv[0][0]; o[1] = dmvr_flag ? dmvr_mv[k][0][1] : mv[0][1];
-                        o[2] = dmvr_flag ? dmvr_mv[k][1][0] : mv[1][0]; o[3] = dmvr_flag ? dmvr_mv[k][1][1] : mv[1][1];
-                    }
+            info_publish(&info, prm, cur, cu, ext, dmvr_flag, dmvr_mv);
         } else if (cu->mode == XB200_MODE_INTER) {
             select_mc_tables(prm->tool_admvp ? 1 : 0);
             /* Baseline xevd_mc (src_base/xevd_mc.c:469); identical to xevdm_mc with DMVR off apart from the table switch */
             xevd_mc(cu->x, cu->y, prm->w, prm->h, w, h, refi, mv, refp, s->pred, prm->poc,
                     prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
+            info_publish(&info, prm, cur, cu, ext, 0, NULL);
         } else { free(s); free(map_scu); free(map_tidx); return XB200_ERR_UNSUPPORTED; }
         for (l = 0; l < (h >> 2); l++)
             for (i = 0; i < (w >> 2); i++) MCU_SET_COD(map_scu[scup + l * cur->w_scu + i]);
@@ -333,6 +398,8 @@ int ref_recon_frame(const XB200_PARAMS *prm, ORC_PIC *cur,
         if (do_c) g_ctx->fn_recon(s->coef[U_C], s->pred[0][U_C], is_coef[U_C], cw, ch, cur->s_c, cur->u + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
         if (do_c) g_ctx->fn_recon(s->coef[V_C], s->pred[0][V_C], is_coef[V_C], cw, ch, cur->s_c, cur->v + (cu->y >> 1) * cur->s_c + (cu->x >> 1), prm->bit_depth_luma);
     }
+    if (cur->map_scu) memcpy(cur->map_scu, map_scu, sizeof(u32) * f_scu);
+    info_close(&info);
     free(s); free(map_scu); free(map_tidx);
     return XB200_OK;
 }

@@ -28,6 +28,14 @@ STREAMS = {
     "base_ibp_256x128_8b_qp38": ("baseline", {}, dict(w=256, h=128, bd=8, frames=6, seed=9, types="IBP", qp=38)),
     "base_ipp_200x120_10b_nodbk": ("baseline", {}, dict(w=200, h=120, bd=10, frames=5, seed=11, types="IPP", deblock=0)),
     "base_ipb_416x240_8b_cip": ("baseline", {}, dict(w=416, h=240, bd=8, frames=6, seed=13, types="IPB", constrained_intra=1)),
+    # Main profile: BTT + SUCO partitions, ADMVP (1/16-pel), affine, AMVR, DMVR, MMVD, HMVP, EIPD, CM_INIT + ADCC, IQT, ATS, ADDB, HTDF
+    "main_all_256x128_10b": ("main", {}, dict(w=256, h=128, bd=10, frames=6, seed=21, types="IPP")),
+    "main_all_320x192_8b_lps": ("main", {}, dict(w=320, h=192, bd=8, frames=6, seed=22, types="IBB", lps_scale=420)),
+    "main_ctu128_384x256_10b": ("main", {}, dict(w=384, h=256, bd=10, frames=5, seed=23, types="IBB", log2_ctu=7, lps_scale=350)),
+    "main_ctu32_200x120_8b": ("main", {}, dict(w=200, h=120, bd=8, frames=5, seed=24, types="IBB", log2_ctu=5, lps_scale=350)),
+    "main_noaddb_nohtdf_256x144_10b": ("main", dict(addb=0, htdf=0), dict(w=256, h=144, bd=10, frames=5, seed=25, types="IBB", lps_scale=350)),
+    "main_intra_eipd_ats_192x128_10b": ("main", {}, dict(w=192, h=128, bd=10, frames=4, seed=26, types="I", lps_scale=400)),
+    "main_nodmvr_noaffine_256x128_8b_cip": ("main", dict(dmvr=0, affine=0), dict(w=256, h=128, bd=8, frames=5, seed=27, types="IPP", lps_scale=350, constrained_intra=1)),
 }
 
 
@@ -54,7 +62,7 @@ def main():
             ok = G.same_pictures(own, pics)
             why = "" if ok else "reference != generator"
             if ok and ASAN.exists():
-                r = subprocess.run([str(ASAN), "-i", str(path), "-o", "/dev/null", "--output-bit-depth", "10"], capture_output=True, text=True)
+                r = subprocess.run([str(ASAN), "-i", str(path)], capture_output=True, text=True)
                 if "ERROR: AddressSanitizer" in r.stderr or r.returncode != 0:
                     ok, why = False, "AddressSanitizer: " + next((l for l in r.stderr.splitlines() if "SUMMARY" in l), f"rc {r.returncode}")
             if ok:

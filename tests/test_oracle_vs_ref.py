@@ -544,3 +544,47 @@ def test_random_pipeline_vs_reference(reference, tree, first):
     recon, deblocking, ALF, padding.  tools/ref_sweep.py runs the same over any seed range (2500 cases identical at the end of round 1)."""
     from tools.ref_sweep import sweep
     assert sweep(first, 40, tree) == []
+
+
+def assert_maps_equal(a, b, what=""):
+    """per-SCU maps of the oracle (a) against what the reference's own xevdm_set_dec_info published (b, oracle/ref_harness.c info_publish)"""
+    for name in ("map_scu", "map_refi", "map_mv", "map_unrefined_mv"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert np.array_equal(x, y), f"{what}{name}: {int((x != y).sum())} entries differ, first SCU {int(np.argwhere((x != y).reshape(len(x), -1).any(axis=1))[0][0])}"
+
+
+@pytest.mark.parametrize("case", ["inter_B", "inter_iqt_skipflags", "main_all_64", "main_all_128", "main_all_32", "dual_tree", "constrained_dual", "ibc", "ats"])
+def test_set_dec_info_maps(oracle, reference, case):
+    """xevd_set_dec_info / xevdm_set_dec_info (src_base/xevd_util.c:1574-1691, src_main/xevdm_util.c:4205-4389) pinned directly: the harness
+    fills a zeroed XEVDM_CTX / XEVDM_CORE from every work item and calls the reference's function (also xevdm_set_affine_mvf and
+    xevdm_set_cu_cbf_flags through it); map_scu (QP, intra / skip / cbf / DMVR / affine / IBC / COD bits), map_refi, map_mv (refined and
+    affine sub-block vectors) and map_unrefined_mv must equal what the oracle - and therefore the GPU kernels - publish."""
+    w, h = 256, 136
+    if case == "inter_B":
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=10, variant="B", seed=41, n_refs=2, coded_frac=0.6)
+        refs = synth.make_refs(w, h, 10, 2, seed=42)
+    elif case == "inter_iqt_skipflags":
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=8, variant="C", seed=43, n_refs=2, coded_frac=0.5, iqt=True, main_mv=True)
+        rng = np.random.default_rng(44)
+        skip = (rng.random(cl.n_cu) < 0.3) & (cl.cus["cbf"] == 0)
+        cl.cus["flags"] = np.where(skip, cl.cus["flags"] | 4, cl.cus["flags"])           # XB200_CUF_SKIP -> MCU_SET_SF
+        cl.cus["qp_map"] = rng.integers(10, 50, cl.n_cu)
+        refs = synth.make_refs(w, h, 8, 2, seed=45)
+    elif case.startswith("main_all"):
+        lg = {"64": 6, "128": 7, "32": 5}[case.split("_")[-1]]
+        prm, cl, refs, _, _ = synth.make_main_frame(w, h, bit_depth=10, seed=46 + lg, log2_ctu=lg, iqt=lg != 7)
+    elif case == "dual_tree":
+        w, h, prm, cl, refs = dual_tree_inputs("C", dict(log2_ctu=6), 10, 1, 1, 0.7)
+    elif case == "constrained_dual":
+        w, h, prm, cl, refs = constrained_inputs("C", dict(log2_ctu=6), 10, 1, 1, 0.5, 1)
+    elif case == "ibc":
+        w, h, prm, cl, refs = ibc_inputs("C", dict(log2_ctu=6), 10, 0.3)
+    else:
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=10, variant="C", seed=51, n_refs=2, coded_frac=0.8, iqt=True, ats_inter_frac=0.5)
+        prm.tool_ats = 1
+        refs = synth.make_refs(w, h, 10, 2, seed=52)
+    a = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    b = reference.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    for pa, pb, n in zip(a.planes(), b.planes(), "YUV"):
+        assert np.array_equal(pa, pb), n
+    assert_maps_equal(a, b, case + ": ")

@@ -152,6 +152,10 @@ def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_
     return b.bytes()
 
 
+class NonConforming(Exception):
+    """the random syntax described something no encoder emits (see gen_engine.c, conformance watch): discard the stream"""
+
+
 class Generator:
     def __init__(self):
         if not GEN_SO.exists():
@@ -163,44 +167,81 @@ class Generator:
         L.gen_take.argtypes = [C.c_void_p, C.c_size_t]
         L.gen_take.restype = C.c_size_t
         L.gen_selfcheck.restype = C.c_longlong
+        L.gen_invalid.argtypes = [C.c_char_p, C.c_int]
+        L.gen_replay.argtypes = [C.c_void_p, C.c_size_t]
+        L.gen_replay.restype = None
+        L.gen_log.argtypes = [C.c_void_p, C.c_size_t]
+        L.gen_log.restype = C.c_size_t
 
-    def make(self, tools, w, h, bd, frames, seed, types="IPB", qp=30, lps_scale=256, ep_one=128, log2_ctu=6, deblock=1, gop=0, **pps_kw):
-        """returns (list of NAL units, pictures the generator's own decode produced in output order)"""
+    def make(self, tools, w, h, bd, frames, seed, types="IPB", qp=30, lps_scale=256, ep_one=128, log2_ctu=6, deblock=1, gop=0, tries=40, **pps_kw):
+        """returns (list of NAL units, pictures the generator's own decode produced in output order).
+        Picture by picture: draw a random slice; if the conformance watch of gen_engine.c objects, a FRESH decoder instance is brought to
+        the same state by replaying the recorded bins of the pictures accepted so far, and the picture is drawn again with another seed."""
         rng = np.random.default_rng(seed)
         L = self.lib.lib
-        nals, pics = [], []
         tail = bytes(max(1 << 17, w * h * 8))
-        with X.Decoder(self.lib) as d:
-            for n in (write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(**pps_kw)):
-                ret, _ = d.decode(n)
-                assert ret >= 0, ("parameter set rejected", ret)
-                nals.append(n)
-            for f in range(frames):
-                idr = f == 0 or (gop and f % gop == 0)
-                st = X.ST_I if idr else {"I": X.ST_I, "P": X.ST_P, "B": X.ST_B}[types[1 + (f - 1) % (len(types) - 1)]] if len(types) > 1 else X.ST_I
-                hdr = write_sh(tools, X.NUT_IDR if idr else X.NUT_NONIDR, st, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), deblock=deblock,
-                               alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)), qp_u_off=int(rng.integers(-3, 4)),
-                               qp_v_off=int(rng.integers(-3, 4)))
-                L.gen_reset(int(seed) * 1000003 + f, lps_scale, ep_one)
-                ret, stat = d.decode(hdr + tail)
-                assert ret >= 0, ("generator decode failed", f, ret)
-                buf = (C.c_ubyte * len(tail))()
-                n = L.gen_take(buf, len(tail))
-                assert n > 0, "slice data not terminated"
-                bad = L.gen_selfcheck()
-                assert bad < 0, f"arithmetic encoder self-check: bin {bad} of picture {f} does not decode as chosen"
-                nals.append(hdr + bytes(buf[:n]))
+        params = [write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(**pps_kw)]
+        hdrs = []
+        for f in range(frames):
+            idr = f == 0 or (gop and f % gop == 0)
+            st = X.ST_I if (idr or len(types) == 1) else {"I": X.ST_I, "P": X.ST_P, "B": X.ST_B}[types[1 + (f - 1) % (len(types) - 1)]]
+            hdrs.append(write_sh(tools, X.NUT_IDR if idr else X.NUT_NONIDR, st, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), deblock=deblock,
+                                 alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)), qp_u_off=int(rng.integers(-3, 4)),
+                                 qp_v_off=int(rng.integers(-3, 4))))
+        accepted = []                      # per picture: (slice data bytes, bins)
+
+        def run(upto, attempt):
+            """fresh decoder: replay pictures [0, upto), then draw picture `upto` (None: replay only).  Returns (pictures, result)"""
+            pics, result = [], None
+            with X.Decoder(self.lib) as d:
+                for n in params:
+                    ret, _ = d.decode(n)
+                    assert ret >= 0, ("parameter set rejected", ret)
+                for f in range(upto + (0 if attempt is None else 1)):
+                    replay = f < len(accepted) and (attempt is None or f < upto)
+                    L.gen_reset(int(seed) * 1000003 + f * 101 + (attempt or 0), lps_scale, ep_one)
+                    if replay:
+                        bins = accepted[f][1]
+                        L.gen_replay(bins.ctypes.data, bins.size)
+                    ret, stat = d.decode(hdrs[f] + tail)
+                    assert ret >= 0, ("generator decode failed", f, ret)
+                    why = C.create_string_buffer(200)
+                    invalid = L.gen_invalid(why, 200)
+                    if replay:
+                        assert L.gen_replay_done() and not invalid, "replay diverged"
+                    else:
+                        buf = (C.c_ubyte * len(tail))()
+                        n = L.gen_take(buf, len(tail))
+                        assert n > 0, "slice data not terminated"
+                        bad = L.gen_selfcheck()
+                        assert bad < 0, f"arithmetic encoder self-check: bin {bad} of picture {f} does not decode as chosen"
+                        lb = (C.c_int32 * (2 * 4000000))()
+                        k = L.gen_log(lb, 2 * 4000000)
+                        assert k <= 4000000
+                        bins = np.frombuffer(lb, np.int32, 2 * k)[1::2].astype(np.uint8)
+                        result = (bytes(buf[:n]), bins, why.value.decode() if invalid else None)
+                    while True:
+                        p = d.pull()
+                        if p is None:
+                            break
+                        pics.append(p)
                 while True:
                     p = d.pull()
                     if p is None:
                         break
                     pics.append(p)
-            while True:
-                p = d.pull()
-                if p is None:
+            return pics, result
+
+        for f in range(frames):
+            for attempt in range(tries):
+                _, (data, bins, why) = run(f, attempt)
+                if why is None:
+                    accepted.append((data, bins))
                     break
-                pics.append(p)
-        return nals, pics
+            else:
+                raise NonConforming(f"picture {f}: no conforming slice in {tries} draws (last: {why})")
+        pics, _ = run(frames, None)
+        return params + [hdrs[f] + accepted[f][0] for f in range(frames)], pics
 
 
 def same_pictures(a, b):

@@ -5,3 +5,6 @@ u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model);
 u32 sbac_decode_bin_ep(XEVD_BSR *bs, XEVD_SBAC *sbac);
 u32 xevd_sbac_decode_bin_trm(XEVD_BSR *bs, XEVD_SBAC *sbac);
 u32 gen_run(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, int max_run);
+int gen_force_next(int bin);
+u32 gen_merge_idx(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, u32 max_num, u32 limit);
+u32 gen_unary_ep(XEVD_BSR *bs, XEVD_SBAC *sbac, u32 max_val, u32 max_symbol);

@@ -14,7 +14,9 @@
  * lower part, LPS width = max(437, state * range >> 9), state update +/- ((x + 16) >> 5); bypass halves the range with floor
  * (an odd range loses one unit); the terminating bin takes one unit off the top.
  */
+#include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "xevd_def.h"
@@ -31,6 +33,13 @@ static struct {
     uint32_t *log; int32_t *log_off; size_t n_log, cap_log;     /* every bin: kind << 30 | model-before << 1 | bin, for the self-check */
 } E;
 
+static const uint8_t *g_replay; static size_t g_replay_n, g_replay_pos; static int g_replay_err;
+/* replay: the next slice takes its bins from a recorded sequence instead of drawing them (used to bring a fresh decoder instance to
+ * the state after the pictures accepted so far, before another attempt at the next picture) */
+void gen_replay(const uint8_t *bins, size_t n) { g_replay = bins; g_replay_n = n; g_replay_pos = 0; g_replay_err = 0; }
+int gen_replay_done(void) { int ok = g_replay && !g_replay_err && g_replay_pos == g_replay_n; g_replay = 0; return ok; }
+static int replay_bin(void) { if (g_replay_pos >= g_replay_n) { g_replay_err = 1; return 0; } return g_replay[g_replay_pos++]; }
+static int g_force_ep = -1;
 static int g_force = -1;             /* -1 free choice, else the bin the next context-coded call must take (gen_run) */
 static int32_t g_off;                 /* which context model (offset inside XEVD_SBAC_CTX): lets a trace of the real decoder be compared */
 static void log_bin(uint32_t kind, uint32_t model, uint32_t bin)
@@ -107,7 +116,8 @@ u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model)
     uint32_t p = (state * (uint32_t)E.lps_scale_q8) >> 8;
     if (p > 480) p = 480;
     int is_lps = (rnd32() & 511) < p;
-    if (g_force >= 0) is_lps = ((uint32_t)g_force != mps);
+    if (g_force >= 0) { is_lps = ((uint32_t)g_force != mps); g_force = -1; }      /* a forced value applies to one bin */
+    if (g_replay) is_lps = ((uint32_t)replay_bin() != mps);
     log_bin(0, *model, is_lps ? 1 - mps : mps);
     E.range -= lps;
     uint32_t bin;
@@ -129,6 +139,10 @@ u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model)
 
 /* sbac_read_unary_sym (xevd_eco.c:207) for the zero run of the run-length coefficient code, with the one constraint the syntax
  * leaves to the encoder: the run must end inside the block.  g_force: -1 free choice, else the bin the next context-coded call must take. */
+/* the next context-coded bin must take this value (syntax the decoder parses but a conforming encoder has no choice about,
+ * e.g. the split flag of a Baseline coding block that crosses the picture boundary, src_main/xevdm.c:1713) */
+int gen_force_next(int bin) { g_force = bin; return 0; }
+
 u32 gen_run(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, int max_run)
 {
     u32 ctx_idx = 0, symbol = 0, t;
@@ -147,10 +161,44 @@ u32 gen_run(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, i
     return symbol;
 }
 
+/* sbac_read_truncate_unary_sym (xevdm_eco.c:113) with the value kept below `limit` (<= max_num): the merge index of a small block */
+u32 gen_merge_idx(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, u32 max_num, u32 limit)
+{
+    u32 ctx_idx = 0;
+    if (max_num > 1)
+        for (; ctx_idx < max_num - 1; ++ctx_idx) {
+            if (ctx_idx + 1 >= limit) g_force = 0;
+            const u32 symbol = xevd_sbac_decode_bin(bs, sbac, model + (ctx_idx > num_ctx - 1 ? num_ctx - 1 : ctx_idx));
+            g_force = -1;
+            if (symbol == 0) break;
+        }
+    return ctx_idx;
+}
+
+u32 sbac_decode_bin_ep(XEVD_BSR *bs, XEVD_SBAC *sbac);
+/* sbac_read_unary_sym_ep (xevd_eco.c:166) with the value kept at or below max_symbol */
+u32 gen_unary_ep(XEVD_BSR *bs, XEVD_SBAC *sbac, u32 max_val, u32 max_symbol)
+{
+    u32 t, symbol;
+    int counter = 0;
+    if (max_symbol == 0) g_force_ep = 0;
+    symbol = sbac_decode_bin_ep(bs, sbac); counter++;
+    if (symbol == 0) return 0;
+    symbol = 0;
+    do {
+        if (counter == (int)max_val) t = 0;
+        else { if (symbol + 1 >= max_symbol) g_force_ep = 0; t = sbac_decode_bin_ep(bs, sbac); }
+        counter++; symbol++;
+    } while (t);
+    return symbol;
+}
+
 u32 sbac_decode_bin_ep(XEVD_BSR *bs, XEVD_SBAC *sbac)
 {
     (void)bs; (void)sbac;
-    const uint32_t bin = (rnd32() & 255) < (uint32_t)E.ep_one_q8;
+    uint32_t bin = (rnd32() & 255) < (uint32_t)E.ep_one_q8;
+    if (g_force_ep >= 0) { bin = (uint32_t)g_force_ep; g_force_ep = -1; }
+    if (g_replay) bin = (uint32_t)replay_bin();
     const uint32_t r2 = E.range >> 1;
     log_bin(1, 0, bin);
     shift1();
@@ -169,6 +217,7 @@ u32 xevd_sbac_decode_bin_trm(XEVD_BSR *bs, XEVD_SBAC *sbac)
         u32 t0;
         while (!XEVD_BSR_IS_BYTE_ALIGN(bs)) xevd_bsr_read1(bs, &t0);
     }
+    if (g_replay) (void)replay_bin();
     log_bin(2, 0, 1);
     E.range--;
     add_low(E.range);
@@ -210,4 +259,65 @@ long long gen_selfcheck(void)
         if (bin != want) return (long long)k;
     }
     return -1;
+}
+
+/* ---- conformance watch ------------------------------------------------------------------------------------------------------
+ * Random syntax can describe a coding unit no encoder would emit although every element parses: an inter CU whose derived motion
+ * has no valid reference picture in either list (a merge / MMVD index pointing at a candidate that does not exist; the reference then
+ * "predicts" from whatever its scratch buffer holds).  tools/evcgen/Makefile routes the generator's xevdm_mc / xevdm_affine_mc calls
+ * through these wrappers; a slice that trips one is reported by gen_invalid() and the stream is discarded. */
+#include "xevdm_def.h"
+#include "xevdm_ipred.h"
+static int g_invalid;
+static char g_why[160];
+int gen_invalid(char *why, int cap) { if (why && cap > 0) { strncpy(why, g_why, (size_t)cap - 1); why[cap - 1] = 0; } int v = g_invalid; g_invalid = 0; return v; }
+typedef void (*MC_FN)(int, int, int, int, int, int, s8 *, s16 (*)[MV_D], XEVD_REFP (*)[REFP_NUM], void *, int, pel *, void *, void *, BOOL, void *, u8 *, void *,
+                      int, int, int, int);
+typedef void (*AFF_FN)(int, int, int, int, int, int, s8 *, void *, XEVD_REFP (*)[REFP_NUM], void *, int, pel *, int, int, int);
+static void watch(const char *what, int x, int y, int w, int h, s8 refi[REFP_NUM], XEVD_REFP (*refp)[REFP_NUM], void *pred)
+{
+    XEVD_CORE *core = (XEVD_CORE *)((char *)pred - offsetof(XEVD_CORE, pred));
+    XEVDM_CORE *m = (XEVDM_CORE *)core;
+    int bad = !REFI_IS_VALID(refi[REFP_0]) && !REFI_IS_VALID(refi[REFP_1]);
+    for (int l = 0; l < REFP_NUM && !bad; l++)
+        if (REFI_IS_VALID(refi[l]) && (refi[l] >= XEVD_MAX_NUM_REF_PICS || !refp[refi[l]][l].pic)) bad = 1;
+    if (bad && !g_invalid) {
+        g_invalid = 1;
+        snprintf(g_why, sizeof(g_why), "%s CU %dx%d at (%d,%d): refi %d/%d, pred_mode %d, inter_dir %d, mmvd %d, affine %d, mvp_idx %d/%d", what, w, h, x, y,
+                 refi[0], refi[1], core->pred_mode, core->inter_dir, m->mmvd_flag, m->affine_flag, core->mvp_idx[0], core->mvp_idx[1]);
+    }
+}
+void gen_watch_mc(int x, int y, int pic_w, int pic_h, int w, int h, s8 refi[REFP_NUM], s16 (*mv)[MV_D], XEVD_REFP (*refp)[REFP_NUM],
+                  void *pred, int poc_c, pel *dmvr_current_template, void *a, void *b, BOOL apply_DMVR, void *c, u8 *cu_dmvr_flag,
+                  void *d, int sps_admvp_flag, int bit_depth_luma, int bit_depth_chroma, int chroma_format_idc)
+{
+    s8 r0[REFP_NUM] = {0, -1};
+    watch("inter", x, y, w, h, refi, refp, pred);
+    if (g_invalid) { if (!refp[0][0].pic) return; refi = r0; }       /* keep the generator itself on defined ground */
+    ((MC_FN)xevdm_mc)(x, y, pic_w, pic_h, w, h, refi, mv, refp, pred, poc_c, dmvr_current_template, a, b, apply_DMVR, c, cu_dmvr_flag, d, sps_admvp_flag,
+                      bit_depth_luma, bit_depth_chroma, chroma_format_idc);
+}
+void gen_watch_affine_mc(int x, int y, int pic_w, int pic_h, int w, int h, s8 refi[REFP_NUM], void *mv, XEVD_REFP (*refp)[REFP_NUM],
+                         void *pred, int vertex_num, pel *tmp_buffer, int bit_depth_luma, int bit_depth_chroma, int chroma_format_idc)
+{
+    watch("affine", x, y, w, h, refi, refp, pred);
+    if (g_invalid) return;
+    ((AFF_FN)xevdm_affine_mc)(x, y, pic_w, pic_h, w, h, refi, mv, refp, pred, vertex_num, tmp_buffer, bit_depth_luma, bit_depth_chroma, chroma_format_idc);
+}
+
+/* intra modes outside the defined sets (chroma: IPD_CHROMA_CNT, luma: IPD_CNT) */
+typedef void (*IPUV_FN)(pel *, pel *, pel *, u16, pel *, int, int, int, int, int);
+typedef void (*IP_FN)(pel *, pel *, pel *, u16, pel *, int, int, int, int);
+void gen_watch_ipred_uv(pel *src_le, pel *src_up, pel *src_ri, u16 avail_lr, pel *dst, int ipm_c, int ipm, int w, int h, int bit_depth)
+{
+    if ((ipm_c < 0 || ipm_c >= IPD_CHROMA_CNT || ipm < 0 || ipm >= IPD_CNT) && !g_invalid) {
+        g_invalid = 1;
+        snprintf(g_why, sizeof(g_why), "intra chroma mode %d (luma %d) in a %dx%d block", ipm_c, ipm, w, h);
+    }
+    ((IPUV_FN)xevdm_ipred_uv)(src_le, src_up, src_ri, avail_lr, dst, ipm_c, ipm, w, h, bit_depth);
+}
+void gen_watch_ipred(pel *src_le, pel *src_up, pel *src_ri, u16 avail_lr, pel *dst, int ipm, int w, int h, int bit_depth)
+{
+    if ((ipm < 0 || ipm >= IPD_CNT) && !g_invalid) { g_invalid = 1; snprintf(g_why, sizeof(g_why), "intra luma mode %d in a %dx%d block", ipm, w, h); }
+    ((IP_FN)xevdm_ipred)(src_le, src_up, src_ri, avail_lr, dst, ipm, w, h, bit_depth);
 }

@@ -597,15 +597,25 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         // IBC needs luma (xevdm.c:1113-1122); the cbf bits of a plane the CU does not carry must be clear (its coefficient block is absent)
         const int pl = cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA);
         if (pl != (XB200_CUF_LUMA | XB200_CUF_CHROMA)) {
-            if (!pl || !intra || (cus[i].mode == XB200_MODE_IBC && !(pl & XB200_CUF_LUMA))) return XB200_ERR_INVALID_ARGUMENT;
-            if ((!(pl & XB200_CUF_LUMA) && (cus[i].cbf & 0x00f)) || (!(pl & XB200_CUF_CHROMA) && (cus[i].cbf & 0xff0))) return XB200_ERR_INVALID_ARGUMENT;
+            if (!pl || !intra || (cus[i].mode == XB200_MODE_IBC && !(pl & XB200_CUF_LUMA))) {
+                snprintf(c->err, sizeof(c->err), "CU %d: planes 0x%x with mode %d (single-plane CUs are intra / luma IBC only)", i, pl, cus[i].mode);
+                return XB200_ERR_INVALID_ARGUMENT;
+            }
+            if ((!(pl & XB200_CUF_LUMA) && (cus[i].cbf & 0x00f)) || (!(pl & XB200_CUF_CHROMA) && (cus[i].cbf & 0xff0))) {
+                snprintf(c->err, sizeof(c->err), "CU %d: cbf 0x%x names a plane the CU does not carry (flags 0x%x)", i, cus[i].cbf, cus[i].flags);
+                return XB200_ERR_INVALID_ARGUMENT;
+            }
             has_intra |= XB200_HAS_DUAL_TREE;
         }
         has_intra |= (intra || (prm->tool_htdf && (cus[i].cbf & 15))) ? XB200_HAS_INTRA : 0;       // HTDF-filtered inter CUs are finished by the wavefront kernel too
         if (intra) continue;
         any_l1 |= cus[i].refi[1] >= 0;
         // a reference index outside the lists the caller supplied would dereference a missing picture on the device
-        if (cus[i].refi[0] >= n0 || cus[i].refi[1] >= n1 || (cus[i].refi[0] < 0 && cus[i].refi[1] < 0)) return XB200_ERR_INVALID_ARGUMENT;
+        if (cus[i].refi[0] >= n0 || cus[i].refi[1] >= n1 || (cus[i].refi[0] < 0 && cus[i].refi[1] < 0)) {
+            snprintf(c->err, sizeof(c->err), "CU %d (mode %d at %d,%d): reference indices %d / %d outside the lists (%d / %d pictures)", i, cus[i].mode, cus[i].x, cus[i].y,
+                     cus[i].refi[0], cus[i].refi[1], n0, n1);
+            return XB200_ERR_INVALID_ARGUMENT;
+        }
     }
     if (!any_l1) n1 = 0;          // P picture: no CU predicts from list 1 (selects the single-list kernel)
     for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
