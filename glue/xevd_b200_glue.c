@@ -41,6 +41,7 @@
 #include "xevdm_def.h"
 #include "xevdm_alf.h"
 #include "xevd_b200.h"
+#include "cu_trace.h"
 
 /* the reference's entry points, as src_main/xevdm.c defines them under the names glue/Makefile gives them */
 XEVD xevdref_create(XEVD_CDSC *cdsc, int *err);
@@ -126,6 +127,41 @@ static int grow(void **p, int *cap, int need, size_t elem)
     if (!q) return -1;
     *p = q; *cap = n;
     return 0;
+}
+
+/* debugging aid (XEVD_B200_DUMP=<directory>): the device picture after a stage, compact planes, for tools/gpu_replay.py */
+static int g_dump_serial;
+static void dump_stage(GLUE *g, GLUE_PIC *p, const char *stage)
+{
+    const char *dir = getenv("XEVD_B200_DUMP");
+    if (!dir || !p) return;
+    const int w = g->ctx->w, h = g->ctx->h;
+    int16_t *buf = (int16_t *)malloc((size_t)w * h * 3 / 2 * sizeof(int16_t) + 64);
+    if (!buf) return;
+    int16_t *y = buf, *u = buf + (size_t)w * h, *v = u + (size_t)(w / 2) * (h / 2);
+    if (xb200_pic_download(g->dev, p->dev, y, w, u, w / 2, v, w / 2) >= 0 && xb200_sync(g->dev) >= 0) {
+        char fn[512];
+        snprintf(fn, sizeof(fn), "%s/pic_%04d_%s.bin", dir, g_dump_serial - 1, stage);
+        FILE *fp = fopen(fn, "wb");
+        if (fp) { int32_t hdr[2] = { w, h }; fwrite(hdr, sizeof(hdr), 1, fp); fwrite(buf, 2, (size_t)w * h * 3 / 2, fp); fclose(fp); }
+    }
+    free(buf);
+    if (!strcmp(stage, "recon")) {          /* what deblocking is about to read: per-SCU maps, edge map, parameters */
+        const size_t n = (size_t)g->ctx->f_scu;
+        uint8_t *m = (uint8_t *)calloc(n, 8 + 2 + 4 + 8 + 1);
+        if (!m) return;
+        int16_t *mv = (int16_t *)m; int8_t *refi = (int8_t *)(m + n * 8); uint32_t *scu = (uint32_t *)(m + n * 10);
+        int16_t *umv = (int16_t *)(m + n * 14); uint8_t *edge = m + n * 22;
+        xb200_pic_download_maps(g->dev, p->dev, mv, refi, scu);
+        xb200_pic_download_unrefined_mv(g->dev, p->dev, umv);
+        xb200_pic_download_edge_map(g->dev, p->dev, edge);
+        xb200_sync(g->dev);
+        char fn[512];
+        snprintf(fn, sizeof(fn), "%s/pic_%04d_maps.bin", dir, g_dump_serial - 1);
+        FILE *fp = fopen(fn, "wb");
+        if (fp) { int32_t hdr[2] = { (int32_t)n, 0 }; fwrite(hdr, sizeof(hdr), 1, fp); fwrite(m, 23, n, fp); fclose(fp); }
+        free(m);
+    }
 }
 
 /* ---- hooks: the pixel functions of xevd_recon_unit --------------------------------------------------------------------- */
@@ -236,6 +272,7 @@ void glue_recon_yuv(int x, int y, int cuw, int cuh, s16 coef[N_C][MAX_CU_DIM], p
     GLUE *g = glue_of(ctx);
     (void)pred; (void)nnz; (void)pic; (void)bit_depth; (void)chroma_format_idc;
     if (!g || g->err) return;
+    cu_trace(ctx, core, x, y, cuw, cuh, tree_cons.tree_type, ats_inter_info);
     const int log2_ctu = ctx->log2_max_cuwh;
     const int ctu = (y >> log2_ctu) * ctx->w_lcu + (x >> log2_ctu);
     if (grow((void **)&g->cus, &g->cap_cu, g->n_cu + 1, sizeof(XB200_CU)) || grow((void **)&g->ext, &g->cap_ext, g->n_ext + 2, sizeof(XB200_CU_EXT))) {
@@ -408,6 +445,7 @@ static void fill_params(GLUE *g)
     p->deblock_alpha_offset = ctx->sh.sh_deblock_alpha_offset; p->deblock_beta_offset = ctx->sh.sh_deblock_beta_offset;
     p->poc = ctx->poc.poc_val;
     p->constrained_intra_pred = ctx->pps.constrained_intra_pred_flag;
+    p->tool_suco = sps->sps_suco_flag;
     g->n0 = g->n1 = 0;
     if (ctx->sh.slice_type != SLICE_I) {
         for (int i = 0; i < mctx->dpm.num_refp[REFP_0] && i < XEVD_MAX_NUM_REF_PICS; i++) {
@@ -485,9 +523,8 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
     {   /* debugging aid: XEVD_B200_DUMP=<directory> writes the work lists of every slice (tools/glue_dump.py reads them back) */
         const char *dir = getenv("XEVD_B200_DUMP");
         if (dir) {
-            static int serial;
             char fn[512];
-            snprintf(fn, sizeof(fn), "%s/slice_%04d.bin", dir, serial++);
+            snprintf(fn, sizeof(fn), "%s/slice_%04d.bin", dir, g_dump_serial++);
             FILE *fp = fopen(fn, "wb");
             if (fp) {
                 int32_t hdr[8] = { g->n_cu, n_ctu, g->n_ext, (int32_t)g->n_coef, g->n0, g->n1, ctx->sh.slice_type, ctx->sh.deblocking_filter_on };
@@ -511,6 +548,7 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
                                   g->ext, g->n_ext, coef, g->n_coef);
         if (r < 0) { fprintf(stderr, "[xevd-b200] xb200_recon_frame: %d, slice type %d, lists %d / %d\n", r, ctx->sh.slice_type, g->n0, g->n1); dev_fail(g, XEVD_ERR, "xb200_recon_frame"); return g->err; }
         g->n_cus_total += g->n_cu;
+        dump_stage(g, cur, "recon");
     }
     return ret;
 }
@@ -528,6 +566,13 @@ int glue_deblock(void *arg)
     if (!cur) return XEVD_ERR_UNEXPECTED;
     fill_params(g);
     if (xb200_deblock(g->dev, &g->prm, cur->dev, g->l0, g->n0, g->l1, g->n1, NULL) < 0) { dev_fail(g, XEVD_ERR, "xb200_deblock"); return g->err; }
+    if (getenv("XEVD_B200_DUMP")) {
+        char fn[512];
+        snprintf(fn, sizeof(fn), "%s/pic_%04d_dbkprm.bin", getenv("XEVD_B200_DUMP"), g_dump_serial - 1);
+        FILE *fp = fopen(fn, "wb");
+        if (fp) { fwrite(&g->prm, sizeof(g->prm), 1, fp); fclose(fp); }
+    }
+    dump_stage(g, cur, "dbk");
     return XEVD_OK;
 }
 
@@ -556,18 +601,17 @@ int alf_process_tile(void *arg)
 
 /* ctx->fn_picbuf_expand: border replication on the device, then the picture starts its way to the host XEVD_IMGB that xevd_pull
  * will hand out; with DMVR the refined vectors come back too (temporal candidates of later pictures) */
-int glue_picbuf_expand(XEVD_CTX *ctx, XEVD_PIC *pic)
+void glue_picbuf_expand(XEVD_CTX *ctx, XEVD_PIC *pic)
 {
     GLUE *g = glue_of(ctx);
     GLUE_PIC *s = g ? pic_of(g, pic) : NULL;
-    if (!s) return XEVD_ERR_UNEXPECTED;
-    if (xb200_pad(g->dev, s->dev) < 0) { dev_fail(g, XEVD_ERR, "xb200_pad"); return g->err; }
-    if (xb200_pic_download(g->dev, s->dev, pic->y, pic->s_l, pic->u, pic->s_c, pic->v, pic->s_c) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download"); return g->err; }
+    if (!s) { if (g) dev_fail(g, XEVD_ERR_UNEXPECTED, "picture lookup"); return; }
+    if (xb200_pad(g->dev, s->dev) < 0) { dev_fail(g, XEVD_ERR, "xb200_pad"); return; }
+    if (xb200_pic_download(g->dev, s->dev, pic->y, pic->s_l, pic->u, pic->s_c, pic->v, pic->s_c) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download"); return; }
     if (ctx->sps->tool_dmvr && ctx->sh.slice_type == SLICE_B) {
-        if (xb200_pic_download_maps(g->dev, s->dev, (int16_t *)pic->map_mv, NULL, NULL) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download_maps"); return g->err; }
+        if (xb200_pic_download_maps(g->dev, s->dev, (int16_t *)pic->map_mv, NULL, NULL) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download_maps"); return; }
     } else g->maps_pending = 1;
     g->n_pictures++;
-    return XEVD_OK;
 }
 
 /* xevd_imgb_generate is what the reference calls right before it reads a decoded picture on the host (MD5 check, src_main/xevdm.c:3269;

@@ -159,7 +159,12 @@ typedef struct XB200_PARAMS {
     int32_t constrained_intra_pred;   /* pps.constrained_intra_pred_flag: the HTDF ring of an intra CU takes left / right / upper samples
                                          from intra neighbours only (xevdm_recon.c:317,338,359); the intra neighbour masks of
                                          XB200_CU_EXT already carry the same test                                  */
-    int32_t reserved[7];
+    int32_t tool_suco;                /* sps.sps_suco_flag: CUs of one row may be decoded right-to-left.  Matters to the Baseline deblocking
+                                         filter only (tool_addb == 0): chroma edges of 4-wide CUs are 2 samples apart and read what the
+                                         neighbouring edge wrote, and the reference filters an edge when the LATER of its two CUs is
+                                         visited (src_main/xevdm_df.c:272-300) - with the flag set xb200_recon_frame also publishes the
+                                         decoding order per SCU and xb200_deblock walks such runs in that order                       */
+    int32_t reserved[6];
 } XB200_PARAMS;
 
 typedef struct xb200_ctx xb200_ctx;   /* device context: stream, uploaded tables, scratch              */

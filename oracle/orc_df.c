@@ -16,10 +16,12 @@
 #include "orc_common.h"
 
 /* The ADDB walkers compare the vectors BEFORE DMVR refinement: deblock_tree hands mctx->map_unrefined_mv to xevdm_deblock_cu_hor/ver
- * (src_main/xevdm.c:2009-2041) and deblock_addb_cu_* use that argument.  The Baseline-filter walkers do not: xevdm_deblock_cu_*
- * drops the argument when !tool_addb (src_main/xevdm_df.c:1143-1166) and deblock_cu_hor/ver read ctx->map_mv (:111-124,207-208), i.e. the
- * vectors AFTER refinement - DMVR sub-PU vectors, affine sub-block vectors.  Both reproduced. */
-#define DF_MV(p) ((p)->map_unrefined_mv ? (p)->map_unrefined_mv : (p)->map_mv)
+ * (src_main/xevdm.c:2009-2041) and deblock_addb_cu_* use that argument - but xevdm_deblock first copies map_mv over
+ * map_unrefined_mv for every SCU WITHOUT the DMVR flag (src_main/xevdm.c:2077-2090), so what ADDB sees is: the unrefined vector of a
+ * DMVR-refined CU, and map_mv - i.e. the affine SUB-BLOCK vectors xevdm_set_affine_mvf wrote - everywhere else (found on generated
+ * Main streams: an edge along an affine CU changes strength from sub-block to sub-block).  The Baseline-filter walkers ignore the
+ * argument (src_main/xevdm_df.c:1143-1166) and read ctx->map_mv (:111-124,207-208), the vectors AFTER refinement.  Both reproduced. */
+#define DF_MV_AT(p, scu) (((p)->map_unrefined_mv && (((p)->map_scu[scu] >> 25) & 1)) ? (p)->map_unrefined_mv + 4 * (scu) : (p)->map_mv + 4 * (scu))
 
 /* xevd_tbl_df_st (src_base/xevd_tbl.c:306-324) */
 static const uint8_t k_df_st[4][52] = {
@@ -201,7 +203,7 @@ static int addb_bs(const AddbCtx *c, int cur, int nb, int x0, int y0, int x1, in
     if (((m0 >> 26) & 1) || ((m1 >> 26) & 1)) return 3;
     if (((m0 >> 24) & 1) || ((m1 >> 24) & 1) || c->ats[cur] || c->ats[nb]) return 2;       /* ats_present, xevdm_df.c:415,902-906 */
     const int8_t *r0 = p->map_refi + 2 * cur, *r1 = p->map_refi + 2 * nb;
-    const int16_t *v0 = DF_MV(p) + 4 * cur, *v1 = DF_MV(p) + 4 * nb;
+    const int16_t *v0 = DF_MV_AT(p, cur), *v1 = DF_MV_AT(p, nb);
     int pa[2], pb[2], a[2][2], b[2][2];
     for (int l = 0; l < 2; l++) {
         pa[l] = r0[l] >= 0 ? c->ref_id[l][r0[l]] : -1;          /* NULL picture */

@@ -439,7 +439,13 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     ctx->map_scu = map_scu;
     ctx->map_refi = (s8(*)[REFP_NUM])pic->map_refi;
     ctx->map_mv = (s16(*)[REFP_NUM][MV_D])pic->map_mv;
-    m->map_unrefined_mv = pic->map_unrefined_mv ? (s16(*)[REFP_NUM][MV_D])pic->map_unrefined_mv : ctx->map_mv;
+    /* xevdm_deblock's first loop (src_main/xevdm.c:2077-2090): map_mv replaces map_unrefined_mv wherever the DMVR flag is not set.  Done on
+     * a copy: the caller's maps are inputs here */
+    s16 (*umv)[REFP_NUM][MV_D] = (s16(*)[REFP_NUM][MV_D])malloc(sizeof(s16) * REFP_NUM * MV_D * f_scu);
+    memcpy(umv, pic->map_unrefined_mv ? pic->map_unrefined_mv : pic->map_mv, sizeof(s16) * REFP_NUM * MV_D * f_scu);
+    for (i = 0; i < f_scu; i++)
+        if (!MCU_GET_DMVRF(pic->map_scu[i])) memcpy(umv[i], ctx->map_mv[i], sizeof(umv[i]));
+    m->map_unrefined_mv = umv;
     ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu; ctx->w = pic->w_l; ctx->h = pic->h_l;
     ctx->log2_max_cuwh = prm->log2_ctu;
     ctx->map_tidx = (u8 *)calloc(f_scu, 1);
@@ -487,7 +493,7 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
             }
         }
     }
-    free(ctx->map_tidx); free(ctx->map_cu_mode); free(m->map_ats_inter); free(map_scu); free(m);
+    free(ctx->map_tidx); free(ctx->map_cu_mode); free(m->map_ats_inter); free(map_scu); free(umv); free(m);
     return XB200_OK;
 }
 

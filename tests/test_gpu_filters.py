@@ -163,6 +163,35 @@ def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
 
 
+@pytest.mark.parametrize("bd,addb,kw", [(10, 0, {}), (8, 0, dict(log2_ctu=5)), (10, 0, dict(log2_ctu=7)), (10, 1, {}), (10, 0, dict(suco=False))])
+def test_deblock_suco_order_4wide(ctx, oracle, bd, addb, kw):
+    """recon -> deblock on binary/ternary partitions down to 4-wide CUs in SUCO order: neighbouring chroma edges are 2 samples apart, each
+    reads a sample the other writes, and the reference filters an edge when the LATER of its two CUs is visited (xevdm_df.c:272-300), so the
+    run is not walked left to right (found on generated Main streams).  The recon kernels publish the order (tool_suco)."""
+    w, h = 320, 192
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="C", seed=77, n_refs=2, coded_frac=0.5, bi_frac=0.3, min_log2=2, **kw)
+    prm.tool_addb = addb
+    prm.qp_u_offset, prm.qp_v_offset = 3, -2
+    cl.cus["qp_map"] = 44
+    tbl, ids = synth.chroma_qp_table(True), ((0, 1), (1, 0))
+    refs = synth.make_refs(w, h, bd, 2, seed=78)
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), refs, refs[::-1], cl)
+    rec = want.copy()
+    oracle.deblock_frame(prm, want, cl, tbl, bool(addb), ids)
+    assert sum(int((a != b).sum()) for a, b in zip(want.planes()[1:], rec.planes()[1:])) > (20 if addb else 500), "chroma deblocking does nothing here"
+    ctx.set_chroma_qp_table(tbl)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, drefs[::-1], cl)
+    ctx.deblock(prm, cur, drefs, drefs[::-1])
+    got = cur.download()
+    ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+    for p in drefs + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
 @pytest.mark.parametrize("bd,addb,kw", [(10, 0, {}), (10, 1, {}), (8, 0, dict(log2_ctu=5)), (12, 1, dict(log2_ctu=7))])
 def test_dual_tree_pipeline(ctx, oracle, bd, addb, kw):
     """recon -> deblock -> pad of a picture with local dual tree nodes: the deblocking pass runs on the maps and the edge map the recon

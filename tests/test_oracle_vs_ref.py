@@ -248,7 +248,9 @@ def test_recon_frame_ats(oracle, reference, variant, kw, bd, intra_frac, iqt):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
-DBK_MAIN_CASES = [({}, 10, 1), (dict(log2_ctu=7), 10, 1), (dict(log2_ctu=5), 8, 1), ({}, 10, 0), (dict(log2_ctu=7), 8, 0)]
+# min_log2=2: 4-wide / 4-high CUs in SUCO order - chroma edges 2 samples apart whose filtering order is the CUs' decoding order
+DBK_MAIN_CASES = [({}, 10, 1), (dict(log2_ctu=7), 10, 1), (dict(log2_ctu=5), 8, 1), ({}, 10, 0), (dict(log2_ctu=7), 8, 0),
+                  (dict(min_log2=2), 10, 0), (dict(min_log2=2, log2_ctu=5), 8, 0), (dict(min_log2=2, log2_ctu=7), 10, 0), (dict(min_log2=2), 8, 1)]
 
 
 def deblock_main_inputs(oracle, kw, bd, addb):

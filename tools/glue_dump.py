@@ -31,6 +31,26 @@ def read_slice(path):
     return prm, cl, pocs[:n0].tolist(), pocs[21:21 + n1].tolist(), stype, dbk
 
 
+def stage_cmp(slice_path, stage, pic, cl):
+    """the device picture the glue dumped after `stage` against the oracle's picture at the same point"""
+    f = slice_path.with_name(slice_path.name.replace("slice_", "pic_").replace(".bin", f"_{stage}.bin"))
+    if not f.exists():
+        return
+    b = f.read_bytes()
+    w, h = np.frombuffer(b, np.int32, 2)
+    a = np.frombuffer(b, np.int16, offset=8)
+    planes = [a[:w * h].reshape(h, w), a[w * h:w * h * 5 // 4].reshape(h // 2, w // 2), a[w * h * 5 // 4:].reshape(h // 2, w // 2)]
+    for pl, (g, want) in enumerate(zip(planes, pic.planes())):
+        d = g != want
+        if d.any():
+            ys, xs = np.nonzero(d)
+            s = 1 if pl == 0 else 2
+            y, x = int(ys[0]), int(xs[0])
+            own = [i for i, c in enumerate(cl.cus) if c["x"] <= x * s < c["x"] + (1 << c["log2w"]) and c["y"] <= y * s < c["y"] + (1 << c["log2h"])]
+            print(f"\n   [{stage}] device != oracle, plane {pl}: {int(d.sum())} samples, first y={y} x={x} dev {int(g[y, x])} oracle {int(want[y, x])}, "
+                  f"rows {ys.min()}..{ys.max()} cols {xs.min()}..{xs.max()}; CUs {[(i, cl.cus[i]) for i in own]}", end="")
+
+
 def main():
     dump, stream = Path(sys.argv[1]), sys.argv[2]
     ref_pics = X.decode_stream(X.XevdLibrary(X.REF_SO), X.read_stream(stream))
@@ -43,10 +63,12 @@ def main():
         refs1 = [done[p] for p in p1]
         pic = o.recon_frame(prm, HostPicture(prm.w, prm.h, prm.poc), refs0, refs1, cl)
         rec = pic.copy()
+        stage_cmp(f, "recon", rec, cl)
         ids = {}
         rid = lambda lst: tuple(ids.setdefault(p, len(ids)) for p in lst)
         if dbk and not __import__('os').environ.get('NO_DBK'):
             o.deblock_frame(prm, pic, cl, synth.chroma_qp_table(bool(prm.tool_iqt)), bool(prm.tool_addb), (rid(p0) or (0,), rid(p1) or (0,)))
+        stage_cmp(f, "dbk", pic, cl)
         o.pad(pic)
         done[prm.poc] = pic
         want = ref_pics[k] if k < len(ref_pics) else None

@@ -62,7 +62,8 @@ class Params(C.Structure):
         ("poc", C.c_int32),
         ("ctu_row0", C.c_int32), ("ctu_rows", C.c_int32),
         ("constrained_intra_pred", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("tool_suco", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 

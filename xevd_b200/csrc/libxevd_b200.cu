@@ -30,6 +30,7 @@ struct xb200_pic {
     int8_t *map_refi;
     uint32_t *map_scu;
     uint8_t *map_edge;
+    uint16_t *map_order;
     size_t alloc_bytes;
     int n_peer;                  // twins of this picture on other GPUs, opened over CUDA IPC (band mode with P2P stores)
     void *peer_base[7];
@@ -298,7 +299,7 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     const size_t nscu = (size_t)p->w_scu * p->h_scu;
     const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
     const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
-    const size_t total = pix_al + ((nscu * 24 + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
+    const size_t total = pix_al + ((nscu * 26 + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
     if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
         delete p;
@@ -317,7 +318,8 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     p->map_refi = (int8_t *)(m + nscu * 12);
     p->map_edge = (uint8_t *)(m + nscu * 14);
     p->map_unrefined_mv = (int16_t *)(m + nscu * 16);
-    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 24 + 255) & ~(size_t)255));
+    p->map_order = (uint16_t *)(m + nscu * 24);
+    p->d_tmaps = (CUtensorMap *)(m + ((nscu * 26 + 255) & ~(size_t)255));
     if (make_tensor_maps(c, p) != XB200_OK) {
         cudaFree(p->buf);
         delete p;
@@ -456,6 +458,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     a.affine = prm->tool_affine ? 1 : 0;
     a.slice_qp = prm->slice_qp;
     a.map_mv = cur->map_mv; a.map_unrefined_mv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_scu = cur->map_scu; a.map_edge = cur->map_edge;
+    a.map_order = prm->tool_suco ? cur->map_order : nullptr;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     return XB200_OK;
 }
@@ -736,9 +739,10 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
     a.y = cur->y; a.u = cur->u; a.v = cur->v; a.s_l = cur->s_l; a.s_c = cur->s_c; a.w = cur->w; a.h = cur->h;
     a.w_scu = cur->w_scu; a.h_scu = cur->h_scu;
     a.bd_l = prm->bit_depth_luma; a.bd_c = prm->bit_depth_chroma; a.qp_u_offset = prm->qp_u_offset; a.qp_v_offset = prm->qp_v_offset;
-    // ADDB compares the vectors before DMVR refinement (mctx->map_unrefined_mv, xevdm.c:2009-2041, T7); the Baseline-filter walkers read
-    // ctx->map_mv, the refined / affine sub-block vectors (xevdm_df.c:111-124,1143-1166)
-    a.map_scu = cur->map_scu; a.map_mv = prm->tool_addb ? cur->map_unrefined_mv : cur->map_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
+    // ADDB compares the vectors before DMVR refinement where the DMVR flag is set and map_mv (affine sub-block vectors) elsewhere
+    // (xevdm.c:2009-2041,2077-2090, T7); the Baseline-filter walkers read ctx->map_mv throughout (xevdm_df.c:111-124,1143-1166)
+    a.map_scu = cur->map_scu; a.map_mv = cur->map_mv; a.map_umv = cur->map_unrefined_mv; a.map_refi = cur->map_refi; a.map_edge = cur->map_edge;
+    a.map_order = (prm->tool_suco && !prm->tool_addb) ? cur->map_order : nullptr;
     memcpy(a.cq, c->chroma_qp, sizeof(a.cq));
     a.alpha_offset = prm->deblock_alpha_offset; a.beta_offset = prm->deblock_beta_offset; a.log2_ctu = prm->log2_ctu;
     {   // picture identity of every reference index: first position of the same picture in (list 0 ++ list 1)

@@ -46,6 +46,7 @@ struct XbFrameArgs {
     int8_t *map_refi;           // [scu][2]
     uint32_t *map_scu;
     uint8_t *map_edge;          // XB200_EDGE_* per SCU: CU boundaries + the 64-sample transform split of larger CUs
+    uint16_t *map_order;        // index (inside its CTU, decoding order) of the CU that owns the SCU's CHROMA samples; null unless tool_suco
     int w_scu, h_scu;
 };
 

@@ -67,9 +67,11 @@ struct DbkArgs {
     int s_l, s_c, w, h, w_scu, h_scu;
     int bd_l, bd_c, qp_u_offset, qp_v_offset;
     const uint32_t *map_scu;
-    const int16_t *map_mv;
+    const int16_t *map_mv;           // Baseline filter: ctx->map_mv (refined / affine sub-block vectors)
+    const int16_t *map_umv;          // ADDB: vectors before DMVR refinement, read where map_scu carries the DMVR flag; map_mv elsewhere
     const int8_t *map_refi;
     const uint8_t *map_edge;
+    const uint16_t *map_order;   // decoding order of the chroma-owning CU inside its CTU (tool_suco && !tool_addb), else null
     int8_t cq[2][58];            // chroma QP mapping for qp >= 0 (xevd_qp_chroma_dynamic); identity below 0
     // Main-profile filter (tool_addb)
     int alpha_offset, beta_offset, log2_ctu;
@@ -155,6 +157,44 @@ __device__ __forceinline__ void dbk_strengths(const DbkArgs &a, int cur, int nb,
     st_v = dbk_st(cls, qv < 0 ? qv : a.cq[1][qv]) << (a.bd_c - 8);
 }
 
+// both chroma planes of the 4-sample (2 chroma samples) segment whose right / lower SCU is (cx, cy)
+template <bool VERTICAL>
+__device__ __forceinline__ void dbk_chroma_segment(const DbkArgs &a, int cx, int cy, int maxc)
+{
+    const int c2 = cy * a.w_scu + cx, n2 = VERTICAL ? c2 - 1 : c2 - a.w_scu;
+    int st, st_u, st_v;
+    dbk_strengths(a, c2, n2, st, st_u, st_v);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int s = k ? st_v : st_u;
+        if (!s) continue;
+        pel *p = (k ? a.v : a.u) + (size_t)(cy * 2) * a.s_c + cx * 2;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            if (VERTICAL) {
+                pel *q = p + (size_t)i * a.s_c;
+                int A = q[-2], B = q[-1], C = q[0], D = q[1];
+                dbk_chroma(A, B, C, D, s, maxc);
+                q[-1] = (pel)B; q[0] = (pel)C;
+            } else {
+                pel *q = p + i;
+                int A = q[-2 * a.s_c], B = q[-a.s_c], C = q[0], D = q[a.s_c];
+                dbk_chroma(A, B, C, D, s, maxc);
+                q[-a.s_c] = (pel)B; q[0] = (pel)C;
+            }
+        }
+    }
+}
+
+// when the reference filters the vertical edge left of SCU (sx, sy): at the visit of the later of the two chroma-owning CUs.  CTUs are
+// visited in raster order, CUs inside a CTU in decoding order (map_order)
+__device__ __forceinline__ int dbk_visit_time(const DbkArgs &a, int sx, int sy)
+{
+    const int p = sy * a.w_scu + sx, sh = a.log2_ctu - 2;
+    const int t1 = ((sx >> sh) << 16) | a.map_order[p], t0 = (((sx - 1) >> sh) << 16) | a.map_order[p - 1];
+    return max(t0, t1);
+}
+
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs a)
 {
@@ -195,30 +235,23 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
     if (!dbk_has_edge_c(a, sx, sy, VERTICAL)) return;
     const int psx = VERTICAL ? sx - 1 : sx, psy = VERTICAL ? sy : sy - 1;
     if (dbk_has_edge_c(a, psx, psy, VERTICAL)) return;
+    if (VERTICAL && a.map_order) {
+        // SUCO: the reference filters an edge when the LATER of its two CUs is visited (its left edge, then its right edge; xevdm_df.c:272-300),
+        // so inside a run the order is not left-to-right.  Only neighbouring edges interact: walk every maximal stretch of decreasing visit
+        // times from its right end back to its left end, the stretches themselves left to right.
+        int cx = sx;
+        while (true) {
+            int last = cx;
+            while (last + 1 < a.w_scu && dbk_has_edge_c(a, last + 1, sy, true) && dbk_visit_time(a, last, sy) > dbk_visit_time(a, last + 1, sy)) last++;
+            for (int x = last; x >= cx; x--) dbk_chroma_segment<true>(a, x, sy, maxc);
+            cx = last + 1;
+            if (cx >= a.w_scu || !dbk_has_edge_c(a, cx, sy, true)) break;
+        }
+        return;
+    }
     int cx = sx, cy = sy;
     while (true) {
-        const int c2 = cy * a.w_scu + cx, n2 = VERTICAL ? c2 - 1 : c2 - a.w_scu;
-        if (c2 != cur) dbk_strengths(a, c2, n2, st, st_u, st_v);
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int s = k ? st_v : st_u;
-            if (!s) continue;
-            pel *p = (k ? a.v : a.u) + (size_t)(cy * 2) * a.s_c + cx * 2;
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                if (VERTICAL) {
-                    pel *q = p + (size_t)i * a.s_c;
-                    int A = q[-2], B = q[-1], C = q[0], D = q[1];
-                    dbk_chroma(A, B, C, D, s, maxc);
-                    q[-1] = (pel)B; q[0] = (pel)C;
-                } else {
-                    pel *q = p + i;
-                    int A = q[-2 * a.s_c], B = q[-a.s_c], C = q[0], D = q[a.s_c];
-                    dbk_chroma(A, B, C, D, s, maxc);
-                    q[-a.s_c] = (pel)B; q[0] = (pel)C;
-                }
-            }
-        }
+        dbk_chroma_segment<VERTICAL>(a, cx, cy, maxc);
         if (VERTICAL) { cx++; if (cx >= a.w_scu) break; } else { cy++; if (cy >= a.h_scu) break; }
         if (!dbk_has_edge_c(a, cx, cy, VERTICAL)) break;
     }
@@ -255,7 +288,8 @@ __device__ __forceinline__ int addb_bs(const DbkArgs &a, int cur, int nb, int x0
     const int8_t r00 = (int8_t)(r0 & 0xff), r01 = (int8_t)(r0 >> 8), r10 = (int8_t)(r1 & 0xff), r11 = (int8_t)(r1 >> 8);
     const int pa0 = r00 >= 0 ? a.ref_id[0][r00] : -1, pa1 = r01 >= 0 ? a.ref_id[1][r01] : -1;
     const int pb0 = r10 >= 0 ? a.ref_id[0][r10] : -1, pb1 = r11 >= 0 ? a.ref_id[1][r11] : -1;
-    const int2 v0 = ((const int2 *)a.map_mv)[cur], v1 = ((const int2 *)a.map_mv)[nb];
+    // xevdm_deblock copies map_mv over map_unrefined_mv wherever the DMVR flag is not set before it walks the tree (xevdm.c:2077-2090)
+    const int2 v0 = ((const int2 *)(((m0 >> 25) & 1) ? a.map_umv : a.map_mv))[cur], v1 = ((const int2 *)(((m1 >> 25) & 1) ? a.map_umv : a.map_mv))[nb];
     int a0x = (int16_t)(v0.x & 0xffff), a0y = v0.x >> 16, a1x = (int16_t)(v0.y & 0xffff), a1y = v0.y >> 16;
     int b0x = (int16_t)(v1.x & 0xffff), b0y = v1.x >> 16, b1x = (int16_t)(v1.y & 0xffff), b1y = v1.y >> 16;
     if (r00 < 0) a0x = a0y = 0;
@@ -355,6 +389,7 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
             }
         }
     }
+    if (!dbk_has_edge_c(a, sx, sy, VERTICAL)) return;      // inner leaf boundary of a local dual tree node: a luma edge only (xevdm_df.c:916-920,986-997)
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int qc = xb_clip3(-6 * (a.bd_c - 8), 57, qp + (k ? a.qp_v_offset : a.qp_u_offset));

@@ -898,6 +898,7 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
         const bool e_l = (((gx << 2) - cu.x) & 63) == 0, e_t = (((gy << 2) - cu.y) & 63) == 0, lonly = !(cu.flags & XB200_CUF_CHROMA);
         a.map_edge[p] = (uint8_t)((e_l ? XB200_EDGE_LEFT | (lonly ? XB200_EDGE_LEFT_NOC : 0) : 0) | (e_t ? XB200_EDGE_TOP | (lonly ? XB200_EDGE_TOP_NOC : 0) : 0) |
                                   (aidx ? XB200_EDGE_ATS : 0));
+        if (a.map_order) a.map_order[p] = sm.cu_of_scu_c[i];        // decoding order of the CU whose visit filters the chroma edges here
     }
     // chroma-only CUs (deblock_tree visits the node once more as TREE_C, xevdm.c:1991-1998): chroma edges along their left column / top row
     bool any_c = false;

@@ -829,6 +829,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 xb_store_all(a, (int2 *)a.map_unrefined_mv + p, mv, fo);
                 xb_store_all(a, (int16_t *)a.map_refi + p, rf, fo);
                 xb_store_all(a, a.map_edge + p, e, fo);
+                if (a.map_order) a.map_order[p] = (uint16_t)i;
             }
     }
     if (wide_maps) {

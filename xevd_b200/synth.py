@@ -155,7 +155,8 @@ def partition_btt(w: int, h: int, log2_ctu: int, rng, suco: bool = True, min_log
 def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A", seed: int = 1,
                      n_refs: int = 1, bi_frac: float | None = None, coded_frac: float = 1.0,
                      mv_range_px: int = 32, resid_scale: float | None = None, iqt: bool = False,
-                     log2_cu: int = 4, main_mv: bool = False, log2_ctu: int = 6, suco: bool = True, ats_inter_frac: float = 0.0):
+                     log2_cu: int = 4, main_mv: bool = False, log2_ctu: int = 6, suco: bool = True, ats_inter_frac: float = 0.0,
+                     min_log2: int = 3):
     """Config-2 style inter picture.
 
     variant "A": uniform 16x16 CUs, uni-prediction, every CU coded in all three planes.
@@ -169,7 +170,7 @@ def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A",
         parts, first = partition_uniform(w, h, log2_ctu, log2_cu)
         bi = 0.0 if bi_frac is None else bi_frac
     elif variant == "C":
-        parts, first = partition_btt(w, h, log2_ctu, rng, suco=suco)
+        parts, first = partition_btt(w, h, log2_ctu, rng, suco=suco, min_log2=min_log2)
         bi = 0.5 if bi_frac is None else bi_frac
     else:
         parts, first = partition_quadtree(w, h, log2_ctu, rng)
@@ -261,7 +262,7 @@ def make_inter_frame(w: int, h: int, *, bit_depth: int = 10, variant: str = "A",
         idx = off[sel][:, None] + np.arange(blk.shape[1])[None, :]
         coef[idx] = blk
     prm = make_params(w, h, bit_depth=bit_depth, log2_ctu=log2_ctu, poc=8, tool_iqt=int(iqt), tool_admvp=int(main_mv),
-                      tool_ats=int(ats_inter_frac > 0))
+                      tool_ats=int(ats_inter_frac > 0), tool_suco=int(variant == "C" and suco))
     cl = CuList(w=w, h=h, log2_ctu=log2_ctu, cus=cus, ctu_first=np.array(first, np.uint32), coef=coef)
     return prm, cl
 
