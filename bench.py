@@ -41,6 +41,7 @@ WORKLOADS = {
     "1080p-2B": (1920, 1080, 10, "B"),
     "8k-2A": (7680, 4320, 10, "A"),
 }
+REF_SO_PATH = ROOT / "oracle" / "_ref" / "libxevd_ref.so"
 METRIC = "4k_10bit_frames_per_sec"
 UNIT = "frames/s"
 
@@ -119,6 +120,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def common_config(args, world):
+    """the `config` object: identical in both arms (--impl ours / reference), so that the driver's same-config check sees one workload"""
+    w, h, bd, variant = WORKLOADS[args.workload]
+    return {"workload": args.workload, "picture": f"{w}x{h} 4:2:0 {bd}-bit",
+            "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
+            "per_picture": "MC + dequant / inverse transform + reconstruction of every CU (xevd_ctu_row_rec_mt), then border padding (xevd_picbuf_expand)",
+            "sharding": args.sharding, "n_gpus": world, "l2": "every step streams more than the 126 MB L2 (distinct pictures in rotation)"}
+
+
 def make_workload(name, n_distinct, seed0=1):
     from xevd_b200 import synth
     w, h, bd, variant = WORKLOADS[name]
@@ -141,6 +151,8 @@ def run_reference(args):
     import multiprocessing as mp
     from oracle.pyoracle import have_reference
     kind = "reference" if have_reference() else "port"
+    if kind == "reference":
+        C.CDLL(str(REF_SO_PATH))          # also in the parent, so that the driver's loaded-library record shows the reference (the workers are forks)
     cores = len(os.sched_getaffinity(0))
     w, h, bd, variant, frames = make_workload(args.workload, 1)
     prm, cl = frames[0]
@@ -175,7 +187,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "s16", "data": "synthetic",
-        "config": {"workload": args.workload, "frames_per_step": cores, "inputs": "larger than L2 (host arm)"},
+        "config": common_config(args, args.gpus),
+        "detail": {"frames_per_step": cores, "native_library": str(REF_SO_PATH)},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{cores} single-threaded decoder instances x {args.steps} pictures of {args.workload} each (recon + pad)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,7 +234,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    F = args.frames_per_step
+    F = args.slots                                         # distinct picture slots (> L2 per rotation)
+    P = max(1, args.frames_per_step // F)                  # rotations per step: frames per step = P * F
     band = args.sharding in ("band", "band-p2p")
     p2p = args.sharding == "band-p2p"
     # GOP sharding: every rank has its own pictures.  Band sharding: every rank works on the SAME pictures, one CTU-row band each.
@@ -272,18 +286,19 @@ def run_ours(args):
                 dist.all_reduce(flag)                     # tiny collective in stream order: all peer stores of this picture have landed
 
     def step_resident():
-        for s in slots:
-            cl = s["cl"]
-            if cl.n_cu:
-                ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
-                                    s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
-                                    max_cu_per_ctu=s["max_cu"])
-            if exch is not None:
-                with torch.cuda.stream(stream):
-                    exch.exchange(s["cur"])              # one in-place NCCL all-gather of the packed bands per picture
-            elif p2p:
-                stream_barrier()
-            ctx.pad(s["cur"])
+        for _ in range(P):                                 # a step = P rotations over the F distinct picture slots
+            for s in slots:
+                cl = s["cl"]
+                if cl.n_cu:
+                    ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
+                                        s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
+                                        max_cu_per_ctu=s["max_cu"])
+                if exch is not None:
+                    with torch.cuda.stream(stream):
+                        exch.exchange(s["cur"])              # one in-place NCCL all-gather of the packed bands per picture
+                elif p2p:
+                    stream_barrier()
+                ctx.pad(s["cur"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -310,7 +325,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     ms = xdist.max_over_ranks(ms, dev)
-    fps = (1 if band else world) * F * args.steps / (ms * 1e-3)
+    fps = (1 if band else world) * P * F * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_recon_inter): per-launch CUDA-event timing on the launching stream --------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * min(args.steps, 4))]
@@ -361,36 +376,36 @@ def run_ours(args):
         refs = [c.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
         e2e_slots.append(dict(ctx=c, refs=refs, cur=c.pic_alloc(w, h)))
     torch.cuda.synchronize()
-    h2d = int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
-    d2h = F * (w * h * 3 // 2) * 2 if (not band or rank == 0) else 0       # band mode: rank 0 hands the assembled pictures to the consumer
+    h2d = P * int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
+    d2h = P * F * (w * h * 3 // 2) * 2 if (not band or rank == 0) else 0       # band mode: rank 0 hands the assembled pictures to the consumer
 
     def step_e2e():
-        for i in range(F):
-            prm, cl = frames[i % len(frames)]
-            s, p = e2e_slots[i], pinned[i]
-            c = s["ctx"]
-            if cl.n_cu:
-                c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
-                                               (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
-                                               (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
-                                               p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
-                                               p["ext"].data_ptr(), len(cl.ext), p["coef"].data_ptr(), cl.coef.size), "xb200_recon_frame")
-            if exch is not None:
-                with torch.cuda.stream(stream):
-                    exch.exchange(s["cur"])
-            elif p2p:
-                stream_barrier()
-            c.pad(s["cur"])
-            if band and rank != 0:
-                continue
-            c._chk(c.lib.xb200_pic_download(c.handle, s["cur"].handle, p["out_y"].data_ptr(), w, p["out_u"].data_ptr(), w // 2,
-                                            p["out_v"].data_ptr(), w // 2), "xb200_pic_download")
+        for _ in range(P):
+            for i in range(F):
+                prm, cl = frames[i % len(frames)]
+                s, p = e2e_slots[i], pinned[i]
+                c = s["ctx"]
+                if cl.n_cu:
+                    c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
+                                                   (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
+                                                   (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
+                                                   p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
+                                                   p["ext"].data_ptr(), len(cl.ext), p["coef"].data_ptr(), cl.coef.size), "xb200_recon_frame")
+                if exch is not None:
+                    with torch.cuda.stream(stream):
+                        exch.exchange(s["cur"])
+                elif p2p:
+                    stream_barrier()
+                c.pad(s["cur"])
+                if band and rank != 0:
+                    continue
+                c._chk(c.lib.xb200_pic_download(c.handle, s["cur"].handle, p["out_y"].data_ptr(), w, p["out_u"].data_ptr(), w // 2,
+                                                p["out_v"].data_ptr(), w // 2), "xb200_pic_download")
         for c in ctxs:
             c.sync()
 
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(2):
-        step_e2e()
+    e2e_steps = max(1, min(args.steps, 6))
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -398,7 +413,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     t_e2e = xdist.max_over_ranks(t_e2e, dev)
-    e2e_fps = (1 if band else world) * F * e2e_steps / t_e2e
+    e2e_fps = (1 if band else world) * P * F * e2e_steps / t_e2e
     # a decoded sample read back on the host proves the D2H happened
     checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())
 
@@ -406,17 +421,37 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(args.workload)
 
+    extra = None
+    if rank == 0 and world == 1 and not band and not args.no_extra:
+        # every other workload DESIGN.md quotes, measured in this same run (tools/bench_extra.py): per-picture device time, roofline fraction,
+        # and the same pass through the reference's CPU code
+        for s in slots:
+            for p in s["refs"] + [s["cur"]]:
+                p.free()
+        for s in e2e_slots:
+            for p in s["refs"] + [s["cur"]]:
+                p.free()
+        del pinned
+        from tools import bench_extra
+        try:
+            extra = bench_extra.run(torch, ctx, stream, dev, peak, log=lambda m: print(m, file=sys.stderr, flush=True))
+        except Exception as e:      # the headline line must not be lost to a failure in an auxiliary workload
+            import traceback
+            traceback.print_exc()
+            extra = [{"error": repr(e)}]
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if band else "weak", "vs_baseline": None,
             "dtype": "s16", "data": "synthetic",
-            "config": {"workload": args.workload, "frames_per_step": F * (1 if band else world), "picture": f"{w}x{h} 4:2:0 {bd}-bit",
-                       "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
-                       "per_picture": ("xb200_recon_frame_dev (band, stores fanned out to the peer GPUs over NVLink) + stream barrier + xb200_pad" if p2p else
-                                       "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad") if band else "xb200_recon_frame_dev + xb200_pad",
+            "config": common_config(args, world),
+            "detail": {"frames_per_step": P * F * (1 if band else world), "distinct_picture_slots": F,
+                       "calls_per_picture": ("xb200_recon_frame_dev (band, stores fanned out to the peer GPUs over NVLink) + stream barrier + xb200_pad" if p2p else
+                                             "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad") if band else "xb200_recon_frame_dev + xb200_pad",
                        "parallelism": (f"ctu-row bands x{world} (peer stores fused into the kernel)" if p2p else f"ctu-row bands x{world} (one all-gather per picture)") if band else f"gop-sharded x{world}",
-                       "l2": f"inputs larger than L2 ({F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per step per GPU)"},
+                       "l2": f"{F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per rotation per GPU, {P} rotations per step; the slots share "
+                             f"{len(frames)} distinct CU arrays / coefficient streams, every slot holds its own device copy"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -426,6 +461,8 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -435,12 +472,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="4k-2A", choices=sorted(WORKLOADS))
-    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--frames-per-step", type=int, default=128, help="pictures per step and GPU (rounded down to a multiple of --slots)")
+    ap.add_argument("--slots", type=int, default=16, help="distinct picture slots a step rotates through (inputs + outputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the non-headline workloads (tools/bench_extra.py)")
     ap.add_argument("--sharding", default="gop", choices=["gop", "band", "band-p2p"],
                     help="gop: independent pictures per GPU (weak scaling, default); band: every picture split into CTU-row bands across the GPUs, "
                          "one NCCL all-gather per picture (strong scaling, BASELINE config 4)")

@@ -155,6 +155,35 @@ void ref_itdq_block(int16_t *coef, int log2w, int log2h, int qp, int bit_depth, 
     free(buf);
 }
 
+/* batched forms of the two leaf calls: the CPU baseline of BASELINE config 5 (bench.py), no per-block allocation or Python overhead inside
+ * the timed loop.  coef: n contiguous blocks, transformed in place.  mv: int32[n][4] = {gmv_x, gmv_y, ori_mv_x, ori_mv_y} as xb200_mc_blocks */
+void ref_itdq_blocks(int16_t *coef, int n, int log2w, int log2h, int qp, int bit_depth, int iqt)
+{
+    const int sz = 1 << (log2w + log2h);
+    int i, scale;
+    s16 *buf;
+    ensure_init();
+    buf = (s16 *)aligned_alloc(64, sizeof(s16) * (sz < 32 ? 32 : sz));
+    scale = (iqt ? xevd_tbl_dq_scale : xevd_tbl_dq_scale_b)[qp % 6] << (qp / 6);
+    for (i = 0; i < n; i++) {
+        memcpy(buf, coef + (size_t)i * sz, sizeof(s16) * sz);
+        xevdm_itdq(g_ctx, buf, log2w, log2h, scale, iqt, 0, 0, bit_depth);
+        memcpy(coef + (size_t)i * sz, buf, sizeof(s16) * sz);
+    }
+    free(buf);
+}
+void ref_mc_blocks(const pel *ref, int s_ref, int chroma, const int *mv, pel *out, int n, int w, int h, int bit_depth, int main_tables)
+{
+    int i;
+    ensure_init();
+    select_mc_tables(main_tables);
+    for (i = 0; i < n; i++) {
+        const int *m = mv + 4 * i;
+        if (chroma) xevd_mc_c(m[2], m[3], (pel *)ref, m[0], m[1], s_ref, w, out + (size_t)i * w * h, w, h, bit_depth);
+        else        xevd_mc_l(m[2], m[3], (pel *)ref, m[0], m[1], s_ref, w, out + (size_t)i * w * h, w, h, bit_depth);
+    }
+}
+
 /* ---- CU-level picture reconstruction: the reference's own per-CU calls --------- */
 static void wrap_pic(const ORC_PIC *o, XEVD_PIC *p)
 {

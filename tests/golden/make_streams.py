@@ -28,6 +28,9 @@ STREAMS = {
     "base_ibp_256x128_8b_qp38": ("baseline", {}, dict(w=256, h=128, bd=8, frames=6, seed=9, types="IBP", qp=38)),
     "base_ipp_200x120_10b_nodbk": ("baseline", {}, dict(w=200, h=120, bd=10, frames=5, seed=11, types="IPP", deblock=0)),
     "base_ipb_416x240_8b_cip": ("baseline", {}, dict(w=416, h=240, bd=8, frames=6, seed=13, types="IPB", constrained_intra=1)),
+    # BASELINE.json config 1: a Baseline-profile 1080p 8-bit stream (also the drop-in timing case of bench.py)
+    "base_1080p_8b": ("baseline", {}, dict(w=1920, h=1080, bd=8, frames=8, seed=31, types="IPBB")),
+    "main_1080p_10b": ("main", {}, dict(w=1920, h=1080, bd=10, frames=6, seed=32, types="IBB", lps_scale=350)),
     # Main profile: BTT + SUCO partitions, ADMVP (1/16-pel), affine, AMVR, DMVR, MMVD, HMVP, EIPD, CM_INIT + ADCC, IQT, ATS, ADDB, HTDF
     "main_all_256x128_10b": ("main", {}, dict(w=256, h=128, bd=10, frames=6, seed=21, types="IPP")),
     "main_all_320x192_8b_lps": ("main", {}, dict(w=320, h=192, bd=8, frames=6, seed=22, types="IBB", lps_scale=420)),

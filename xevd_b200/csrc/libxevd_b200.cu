@@ -65,6 +65,7 @@ struct xb200_ctx {
     unsigned char *out_buf;      // output path: packed planes produced by k_output, then copied to the caller
     size_t out_cap;
     int *d_dra;                  // DRA LUTs on the device (3 x 1024 ints)
+    bool peer_maps;              // XB200_PEER_NOMAPS=1 (read once at creation) keeps the per-SCU maps local in band mode (debug)
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
 };
 
@@ -112,29 +113,41 @@ xb200_ctx *xb200_create(int device, int *err)
         return nullptr;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB)
-    cudaFuncSetAttribute(xb::k_recon_inter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
-    cudaFuncSetAttribute(xb::k_recon_inter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::ReconSmem::bytes(7));
-    cudaFuncSetAttribute(xb::k_recon_intra<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
-    cudaFuncSetAttribute(xb::k_recon_intra<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xb::IntraSmem::bytes());
-    cudaFuncSetAttribute(xb::k_itdq_blocks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 65 * (int)sizeof(int));
-    cudaFuncSetAttribute(xb::k_itdq_blocks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 65 * (int)sizeof(int));
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256, true).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256, true).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(1, 256).total);
-    cudaFuncSetAttribute(xb::k_recon_inter_v2<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xb::R2Layout::make(2, 256).total);
+    // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB); a kernel that cannot get its shared memory would
+    // fail at its first launch with a less readable error, so creation fails instead
+    cudaError_t fe = cudaSuccess;
+#define XB_SMEM(fn, bytes) do { if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); } while (0)
+    XB_SMEM((xb::k_recon_inter<false>), (int)xb::ReconSmem::bytes(7));
+    XB_SMEM((xb::k_recon_inter<true>), (int)xb::ReconSmem::bytes(7));
+    XB_SMEM((xb::k_recon_intra<false>), (int)xb::IntraSmem::bytes());
+    XB_SMEM((xb::k_recon_intra<true>), (int)xb::IntraSmem::bytes());
+    XB_SMEM((xb::k_itdq_blocks<false>), 4 * 64 * 65 * (int)sizeof(int));
+    XB_SMEM((xb::k_itdq_blocks<true>), 4 * 64 * 65 * (int)sizeof(int));
+    XB_SMEM((xb::k_recon_inter_v2<false>), xb::R2Layout::make(1, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<true>), xb::R2Layout::make(2, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, true>), xb::R2Layout::make(1, 256, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, true>), xb::R2Layout::make(2, 256, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, true>), xb::R2Layout::make(1, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, true>), xb::R2Layout::make(2, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, true, true>), xb::R2Layout::make(1, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, true, true>), xb::R2Layout::make(2, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, false, true>), xb::R2Layout::make(1, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, false, true>), xb::R2Layout::make(2, 256).total);
+#undef XB_SMEM
+    if (fe != cudaSuccess) {
+        fprintf(stderr, "[xb200] cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s\n", cudaGetErrorString(fe));
+        cudaStreamDestroy(c->stream);
+        delete c;
+        if (err) *err = XB200_ERR_CUDA;
+        return nullptr;
+    }
     {   // xevd_tbl_qp_chroma_adjust_base (src_base/xevd_tbl.c:345-355): the default when the SPS carries no table
         static const int8_t base[58] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                         29, 29, 30, 31, 32, 32, 33, 33, 34, 34, 35, 35, 36, 36, 36, 37, 37, 37, 38, 38, 39, 39, 40, 40, 40, 41, 41, 41};
         memcpy(c->chroma_qp[0], base, 58); memcpy(c->chroma_qp[1], base, 58);
     }
     { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
+    { const char *e = getenv("XB200_PEER_NOMAPS"); c->peer_maps = !(e && e[0] == '1'); }
     {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
         int16_t hl[2][16][8], hc[2][32][4];
         cudaMemcpyFromSymbol(hl, c_mc_l, sizeof(hl));
@@ -443,7 +456,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
         a.ctu_row0 = prm->ctu_row0;
         a.n_ctu = prm->ctu_rows * a.w_ctu;
         a.n_peer = cur->n_peer;
-        { const char *e = getenv("XB200_PEER_NOMAPS"); a.peer_maps = !(e && e[0] == '1'); }
+        a.peer_maps = c->peer_maps ? 1 : 0;
         for (int k = 0; k < cur->n_peer; k++) a.peer_delta[k] = (long long)((char *)cur->peer_base[k] - (char *)cur->buf);
     }
     a.main_tables = prm->tool_admvp ? 1 : 0;
@@ -521,23 +534,27 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     if (has_intra) {
         // intra CUs: CTU wavefront over the picture the inter kernel just completed
         if (c->sync_cap < a.n_ctu + 1) {
+            CK(c, cudaStreamSynchronize(c->stream));
             if (c->d_sync) cudaFree(c->d_sync);
+            c->d_sync = nullptr; c->sync_cap = 0;
+            CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * (a.n_ctu + 1)));
             c->sync_cap = a.n_ctu + 1;
-            CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * c->sync_cap));
         }
         if (c->order_w != a.w_ctu || c->order_n != a.n_ctu) {
             // wavefront order: sort CTU addresses by x + 2y (a stable counting pass per index)
             const int wc = a.w_ctu, hc = a.n_ctu / a.w_ctu;
             int *h = (int *)malloc(sizeof(int) * a.n_ctu);
+            if (!h) return XB200_ERR_OUT_OF_MEMORY;
             int k = 0;
             for (int d = 0; d <= (wc - 1) + 2 * (hc - 1); d++)
                 for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
-            CK(c, cudaStreamSynchronize(c->stream));
+            cudaError_t e = cudaStreamSynchronize(c->stream);
             if (c->d_order) cudaFree(c->d_order);
-            c->d_order = nullptr;
-            CK(c, cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu));
-            CK(c, cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice));
+            c->d_order = nullptr; c->order_w = c->order_n = 0;
+            if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu);
+            if (e == cudaSuccess) e = cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice);
             free(h);
+            CK(c, e);
             c->order_w = a.w_ctu; c->order_n = a.n_ctu;
         }
         CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (a.n_ctu + 1), c->stream));
@@ -559,11 +576,18 @@ static int stage_acquire(xb200_ctx *c, size_t bytes, Staging **out)
     if (!s.done) CK(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     if (s.busy) { CK(c, cudaEventSynchronize(s.done)); s.busy = false; }
     if (s.cap < bytes) {
+        // a failed allocation must leave the slot empty, not pointing at freed memory with a larger capacity
         if (s.pinned) cudaFreeHost(s.pinned);
         if (s.dev) cudaFree(s.dev);
-        s.cap = bytes + bytes / 4 + 4096;
-        CK(c, cudaMallocHost(&s.pinned, s.cap));
-        CK(c, cudaMalloc(&s.dev, s.cap));
+        s.pinned = nullptr; s.dev = nullptr; s.cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        CK(c, cudaMallocHost(&s.pinned, want));
+        if (cudaMalloc(&s.dev, want) != cudaSuccess) {
+            cudaFreeHost(s.pinned); s.pinned = nullptr; s.dev = nullptr;
+            snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed for the staging ring", want);
+            return XB200_ERR_OUT_OF_MEMORY;
+        }
+        s.cap = want;
     }
     *out = &s;
     return XB200_OK;
@@ -574,8 +598,60 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
                       const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
                       const XB200_CU_EXT *ext, int n_ext, const int16_t *coef, size_t n_coef)
 {
-    if (!c || !cus || !ctu_first || n_cu < 0 || n_ctu <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    if (!c || !prm || !cur || !cus || !ctu_first || n_cu < 0 || n_ctu <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    if (prm->log2_ctu < 5 || prm->log2_ctu > 7) return XB200_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
+    // Everything the kernels turn into an address is checked here, where the lists are still host memory and every CU is visited anyway:
+    // a malformed work list must fail the call, not write outside the picture or overrun a CTA's shared memory.  (The _dev entry point
+    // takes device-resident lists from a producer that is trusted to have done the same.)
+    {
+        const int ctu = 1 << prm->log2_ctu, w_ctu = (prm->w + ctu - 1) >> prm->log2_ctu;
+        const int row0 = prm->ctu_rows > 0 ? prm->ctu_row0 : 0;
+        auto bad = [&](int i, const char *what) {
+            snprintf(c->err, sizeof(c->err), "CU %d (mode %d, %dx%d at %d,%d): %s", i, cus[i].mode, 1 << cus[i].log2w, 1 << cus[i].log2h, cus[i].x, cus[i].y, what);
+            return XB200_ERR_INVALID_ARGUMENT;
+        };
+        if (ctu_first[0] != 0 || ctu_first[n_ctu] != (uint32_t)n_cu) { snprintf(c->err, sizeof(c->err), "ctu_first[0] / ctu_first[n_ctu] do not span the CU list"); return XB200_ERR_INVALID_ARGUMENT; }
+        size_t run = n_cu > 0 ? cus[0].coef_off : 0;
+        for (int t = 0; t < n_ctu; t++) {
+            if (ctu_first[t + 1] < ctu_first[t] || ctu_first[t + 1] > (uint32_t)n_cu) { snprintf(c->err, sizeof(c->err), "ctu_first is not monotonic at CTU %d", t); return XB200_ERR_INVALID_ARGUMENT; }
+            const int cx = (t % w_ctu) << prm->log2_ctu, cy = (t / w_ctu + row0) << prm->log2_ctu;
+            for (int i = (int)ctu_first[t]; i < (int)ctu_first[t + 1]; i++) {
+                const XB200_CU &u = cus[i];
+                if (u.log2w < 2 || u.log2w > 7 || u.log2h < 2 || u.log2h > 7) return bad(i, "size outside 4..128");
+                const int w = 1 << u.log2w, h = 1 << u.log2h;
+                if ((u.x & 3) || (u.y & 3) || u.x < cx || u.y < cy || u.x + w > cx + ctu || u.y + h > cy + ctu) return bad(i, "not inside the CTU it is listed under");
+                if (u.x >= prm->w || u.y >= prm->h) return bad(i, "outside the picture");
+                if (u.mode != XB200_MODE_INTRA && u.mode != XB200_MODE_INTER && u.mode != XB200_MODE_IBC && u.mode != XB200_MODE_AFFINE) return bad(i, "unknown mode");
+                if (u.mode == XB200_MODE_INTRA || u.mode == XB200_MODE_AFFINE) {
+                    uint32_t ei;
+                    memcpy(&ei, u.mv[1], 4);
+                    if (!ext || ei >= (uint32_t)n_ext) return bad(i, "extension record index outside the XB200_CU_EXT array");
+                }
+                if (u.mode == XB200_MODE_IBC) {
+                    // xevdm_IBC_mc copies from the part of the picture decoded so far; the wavefront kernel orders CTUs on their left / upper neighbours
+                    const int rx = u.x + u.mv[0][0], ry = u.y + u.mv[0][1];
+                    if (rx < 0 || ry < 0 || rx + w > prm->w || ry + h > prm->h) return bad(i, "block vector leaves the picture");
+                    if (ry + h > cy + ctu || rx + w > cx + ctu) return bad(i, "block vector reaches below / right of the CU's CTU");
+                }
+                // coefficient blocks: decoding order, planes without coefficients absent, every block padded to 8 entries
+                int tlw = u.log2w, tlh = u.log2h;
+                const int ai = (u.mode == XB200_MODE_INTER || u.mode == XB200_MODE_AFFINE) && prm->tool_ats ? XB200_ATS_INTER_IDX(u.ats) : 0;
+                if (ai > 4) return bad(i, "ats_inter_idx > 4");
+                if (ai) { const int sh = ai >= 3 ? 2 : 1; if (ai == 2 || ai == 4) tlh -= sh; else tlw -= sh; if (tlw < 2 || tlh < 2) return bad(i, "ats_inter split of a CU that is too small"); }
+                const size_t n = (size_t)1 << (tlw + tlh);
+                size_t len = 0;
+                if (u.cbf & 0x00f) len += (n + 7) & ~(size_t)7;
+                if (u.cbf & 0x0f0) len += ((n >> 2) + 7) & ~(size_t)7;
+                if (u.cbf & 0xf00) len += ((n >> 2) + 7) & ~(size_t)7;
+                if (len) {
+                    if (u.coef_off != run) return bad(i, "coef_off does not continue the coefficient stream (blocks must follow the decoding order without gaps)");
+                    if (!coef || run + len > n_coef) return bad(i, "coefficient blocks run past the end of the stream");
+                    run += len;
+                } else if (u.coef_off != run && u.coef_off != 0) return bad(i, "coef_off of a CU without coefficients must continue the stream");
+            }
+        }
+    }
     // one staging blob: [cus][ctu_first][ext][coef], each 256-byte aligned
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t b_cu = al((size_t)n_cu * sizeof(XB200_CU)), b_first = al((size_t)(n_ctu + 1) * 4);
