@@ -134,7 +134,7 @@ static int g_dump_serial;
 static void dump_stage(GLUE *g, GLUE_PIC *p, const char *stage)
 {
     const char *dir = getenv("XEVD_B200_DUMP");
-    if (!dir || !p) return;
+    if (!dir || !p || getenv("XEVD_B200_DUMP_NOPICS")) return;          /* work lists only: pictures of large streams are big */
     const int w = g->ctx->w, h = g->ctx->h;
     int16_t *buf = (int16_t *)malloc((size_t)w * h * 3 / 2 * sizeof(int16_t) + 64);
     if (!buf) return;

@@ -65,9 +65,17 @@ def main():
             ok = G.same_pictures(own, pics)
             why = "" if ok else "reference != generator"
             if ok and ASAN.exists():
-                r = subprocess.run([str(ASAN), "-i", str(path)], capture_output=True, text=True)
+                # the ASan build is also the reference with its PLAIN-C kernels (X86 undefined): its pictures must be the dispatched AVX2
+                # build's pictures, or the reference is not one decoder on this stream (e.g. IQT coefficients beyond 32 of a 64-point block)
+                yuv = Path("/tmp") / f"{name}.asan.yuv"
+                r = subprocess.run([str(ASAN), "-i", str(path), "-o", str(yuv), "--output-bit-depth", "10"], capture_output=True, text=True)      # 10: the 16-bit samples as they are
                 if "ERROR: AddressSanitizer" in r.stderr or r.returncode != 0:
                     ok, why = False, "AddressSanitizer: " + next((l for l in r.stderr.splitlines() if "SUMMARY" in l), f"rc {r.returncode}")
+                else:
+                    want = b"".join(p.astype("<i2").tobytes() for pic in pics for p in pic)
+                    if yuv.read_bytes() != want:
+                        ok, why = False, "plain-C reference != dispatched (AVX2) reference"
+                yuv.unlink(missing_ok=True)
             if ok:
                 (OUT / f"{name}.md5").write_text("".join(pic_md5(p) + "\n" for p in pics))
                 print(f"{name}: {len(nals)} NAL units, {path.stat().st_size} bytes, {len(pics)} pictures (seed {kw['seed']})")

@@ -143,6 +143,9 @@ u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model)
  * e.g. the split flag of a Baseline coding block that crosses the picture boundary, src_main/xevdm.c:1713) */
 int gen_force_next(int bin) { g_force = bin; return 0; }
 
+/* ADCC last-position prefixes in a block with a 64 dimension: stop at 7 (see tools/evcgen/Makefile, LAST_BOUND) */
+int gen_last_bound(int pos, int width, int height) { if ((width == 64 || height == 64) && pos >= 7) g_force = 0; return 0; }
+
 u32 gen_run(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, int max_run)
 {
     u32 ctx_idx = 0, symbol = 0, t;

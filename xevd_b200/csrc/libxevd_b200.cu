@@ -121,8 +121,8 @@ xb200_ctx *xb200_create(int device, int *err)
     XB_SMEM((xb::k_recon_inter<true>), (int)xb::ReconSmem::bytes(7));
     XB_SMEM((xb::k_recon_intra<false>), (int)xb::IntraSmem::bytes());
     XB_SMEM((xb::k_recon_intra<true>), (int)xb::IntraSmem::bytes());
-    XB_SMEM((xb::k_itdq_blocks<false>), 4 * 64 * 65 * (int)sizeof(int));
-    XB_SMEM((xb::k_itdq_blocks<true>), 4 * 64 * 65 * (int)sizeof(int));
+    XB_SMEM((xb::k_itdq_blocks<false>), xb::itdq_blocks_smem(1, 6, 32));          // the widest case: 2-wide blocks (row stride w + 4)
+    XB_SMEM((xb::k_itdq_blocks<true>), xb::itdq_blocks_smem(1, 6, 32));
     XB_SMEM((xb::k_recon_inter_v2<false>), xb::R2Layout::make(1, 256).total);
     XB_SMEM((xb::k_recon_inter_v2<true>), xb::R2Layout::make(2, 256).total);
     XB_SMEM((xb::k_recon_inter_v2<false, true>), xb::R2Layout::make(1, 256, true).total);
@@ -950,6 +950,8 @@ int xb200_band_unpack(xb200_ctx *c, xb200_pic *p, int y0, int rows, const void *
 int xb200_itdq_blocks_dev(xb200_ctx *c, const void *d_in, void *d_out, int n, int log2w, int log2h, int qp, int bit_depth, int iqt)
 {
     if (!c || !d_in || !d_out || n <= 0 || log2w < 1 || log2w > 6 || log2h < 1 || log2h > 6) return XB200_ERR_INVALID_ARGUMENT;
+    if (qp < 0 || qp > 81 || bit_depth < 8 || bit_depth > 14) return XB200_ERR_INVALID_ARGUMENT;
+    if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return XB200_ERR_INVALID_ARGUMENT;       // 16-byte vector access
     cudaSetDevice(c->device);
     int r = xb::launch_itdq_blocks((const int16_t *)d_in, (int16_t *)d_out, n, log2w, log2h, qp, bit_depth, iqt, c->stream);
     if (r < 0) return r;

@@ -155,6 +155,8 @@ __device__ __forceinline__ int pack_sat16(int lo, int hi)
 
 // M-point inverse DCT-2 over v[S * k], k = 0..M-1; every input is used by exactly one pair, and the saturating
 // pack (I2IP.S16.S32.SAT) applies the s16 clip of xevd_dquant on the way
+// two kernel-entry pairs share one 32-bit constant (dp2a.lo takes bytes 0-1, dp2a.hi bytes 2-3): the constants travel through uniform
+// registers (one UMOV each), so this halves them
 template <int M, int S, int NV> struct InvDct2P {
     static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[M])
     {
@@ -166,10 +168,43 @@ template <int M, int S, int NV> struct InvDct2P {
 #pragma unroll
         for (int n = 0; n < M / 2; n++) {
             int o = 0;
+            if constexpr (M / 4 == 1) o = __dp2a_lo(pr[0], pk8(tm<M>(1, n), tm<M>(3, n)), o);
+            else {
 #pragma unroll
-            for (int j = 0; j < M / 4; j++) o = __dp2a_lo(pr[j], pk8(tm<M>(4 * j + 1, n), tm<M>(4 * j + 3, n)), o);
+                for (int j = 0; j < M / 4; j += 2) {
+                    const int k = pk8(tm<M>(4 * j + 1, n), tm<M>(4 * j + 3, n)) | (pk8(tm<M>(4 * j + 5, n), tm<M>(4 * j + 7, n)) << 16);
+                    o = __dp2a_lo(pr[j], k, o);
+                    o = __dp2a_hi(pr[j + 1 < M / 4 ? j + 1 : j], k, o);
+                }
+            }
             out[n] = E[n] + o;
             out[M - 1 - n] = E[n] - o;
+        }
+    }
+    // two independent lines with the same constants
+    static __device__ __forceinline__ void run2(const int (&v)[NV], const int (&w)[NV], int (&out)[M], int (&outw)[M])
+    {
+        int E[M / 2], F[M / 2];
+        InvDct2P<M / 2, 2 * S, NV>::run2(v, w, E, F);
+        int pr[M / 4], qr[M / 4];
+#pragma unroll
+        for (int j = 0; j < M / 4; j++) { pr[j] = pack_sat16(v[S * (4 * j + 1)], v[S * (4 * j + 3)]); qr[j] = pack_sat16(w[S * (4 * j + 1)], w[S * (4 * j + 3)]); }
+#pragma unroll
+        for (int n = 0; n < M / 2; n++) {
+            int o = 0, p = 0;
+            if constexpr (M / 4 == 1) {
+                const int k = pk8(tm<M>(1, n), tm<M>(3, n));
+                o = __dp2a_lo(pr[0], k, o); p = __dp2a_lo(qr[0], k, p);
+            } else {
+#pragma unroll
+                for (int j = 0; j < M / 4; j += 2) {
+                    const int k = pk8(tm<M>(4 * j + 1, n), tm<M>(4 * j + 3, n)) | (pk8(tm<M>(4 * j + 5, n), tm<M>(4 * j + 7, n)) << 16);
+                    o = __dp2a_lo(pr[j], k, o); p = __dp2a_lo(qr[j], k, p);
+                    o = __dp2a_hi(pr[j + 1 < M / 4 ? j + 1 : j], k, o); p = __dp2a_hi(qr[j + 1 < M / 4 ? j + 1 : j], k, p);
+                }
+            }
+            out[n] = E[n] + o; out[M - 1 - n] = E[n] - o;
+            outw[n] = F[n] + p; outw[M - 1 - n] = F[n] - p;
         }
     }
 };
@@ -177,8 +212,16 @@ template <int S, int NV> struct InvDct2P<2, S, NV> {
     static __device__ __forceinline__ void run(const int (&v)[NV], int (&out)[2])
     {
         const int p = pack_sat16(v[0], v[S]);
-        out[0] = __dp2a_lo(p, pk8(64, 64), 0);
-        out[1] = __dp2a_lo(p, pk8(64, -64), 0);
+        const int k = pk8(64, 64) | (pk8(64, -64) << 16);
+        out[0] = __dp2a_lo(p, k, 0);
+        out[1] = __dp2a_hi(p, k, 0);
+    }
+    static __device__ __forceinline__ void run2(const int (&v)[NV], const int (&w)[NV], int (&out)[2], int (&outw)[2])
+    {
+        const int p = pack_sat16(v[0], v[S]), q = pack_sat16(w[0], w[S]);
+        const int k = pk8(64, 64) | (pk8(64, -64) << 16);
+        out[0] = __dp2a_lo(p, k, 0); out[1] = __dp2a_hi(p, k, 0);
+        outw[0] = __dp2a_lo(q, k, 0); outw[1] = __dp2a_hi(q, k, 0);
     }
 };
 

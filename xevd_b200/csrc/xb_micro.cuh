@@ -6,45 +6,114 @@
 #include "xb_common.cuh"
 #include "xb_itdq.cuh"
 #include "xb_recon.cuh"
+#include "xb_recon2.cuh"
 
 namespace xb {
 
-// One CTA per group of blocks; a thread owns one line.  Intermediate in shared memory with +1 padding.
+// The transform passes are the ones of the picture kernel (row_pass / row_pass2 / col_pass / col_pass2, xb_recon2.cuh: IDP.2A first pass on
+// packed s16 pairs, two neighbouring lines per thread for lines of at most 16 points, packed stores), so this measures the arithmetic
+// the product runs.  A CTA handles 4096 samples' worth of blocks: coefficients staged by coalesced 16-byte loads, pass-1 results in shared
+// memory (row stride w + 4 words: 16-byte row stores of 8 consecutive rows hit 8 distinct bank quads), residual staged and written back
+// by coalesced 16-byte stores.
 template <bool IQT>
 __global__ void __launch_bounds__(256) k_itdq_blocks(const int16_t *__restrict__ in, int16_t *__restrict__ out, int n, int lw, int lh,
-                                                       int qp, int bd, int blocks_per_cta)
+                                                       int mul, int shift, int wide, int bd, int per)
 {
-    extern __shared__ int s_tmp[];
-    const int w = 1 << lw, h = 1 << lh, ts = w + 1;
-    const int first = blockIdx.x * blocks_per_cta;
-    const int nb = min(blocks_per_cta, n - first);
-    Dequant dq;
-    dq.init(lw, lh, qp, bd, IQT);
-    for (int t = threadIdx.x; t < nb * w; t += blockDim.x) {
-        const int b = t >> lw, x = t & (w - 1);
-        const int16_t *src = in + ((size_t)(first + b) << (lw + lh)) + x;
-        int *dst = s_tmp + b * h * ts + x;
-        itx_line_dyn<IQT>(lh, [&](int k) { return dq.apply(src[k * w]); }, [&](int nn, int v) { dst[nn * ts] = v; }, IQT ? 7 : 0);
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int w = 1 << lw, h = 1 << lh, bs = w * h, ts = w + 4;
+    int16_t *s_coef = (int16_t *)s_raw;
+    int16_t *s_res = s_coef + per * bs;
+    int *s_tmp = (int *)(s_res + per * bs);
+    const long long first = (long long)blockIdx.x * per;
+    const int nb = (int)min((long long)per, n - first), tot = nb * bs;
+    const int16_t *g_in = in + first * bs;
+    int16_t *g_out = out + first * bs;
+    for (int i = threadIdx.x; i < tot >> 3; i += blockDim.x) ((int4 *)s_coef)[i] = __ldg((const int4 *)g_in + i);
+    for (int i = (tot & ~7) + threadIdx.x; i < tot; i += blockDim.x) s_coef[i] = g_in[i];
+    __syncthreads();
+    const int off = shift ? 1 << (shift - 1) : 0;
+    {
+        const int nr = IQT ? w : row_tasks(lw, lh, false), lnr = 31 - __clz(nr);       // IQT: the first pass runs along columns
+        for (int t = threadIdx.x; t < nb * nr; t += blockDim.x) {
+            const int b = t >> lnr, q = t & (nr - 1);
+            if (IQT) {
+                const int16_t *src = s_coef + b * bs + q;
+                int *dst = s_tmp + b * h * ts + q;
+                switch (lh) {
+                case 1: row_pass<2, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 2: row_pass<4, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 3: row_pass<8, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 4: row_pass<16, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 5: row_pass<32, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                default: row_pass<64, true>(src, w, dst, ts, mul, off, shift, wide); break;
+                }
+            } else {
+                const int r0 = lw <= 4 ? 2 * q : q;
+                const int16_t *src = s_coef + b * bs + r0 * w;
+                int *dst = s_tmp + (b * h + r0) * ts;
+                switch (lw) {
+                case 1: row_pass2<2>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 2: row_pass2<4>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 3: row_pass2<8>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 4: row_pass2<16>(src, w, dst, ts, mul, off, shift, wide); break;
+                case 5: row_pass<32, false>(src, w, dst, ts, mul, off, shift, wide); break;
+                default: row_pass<64, false>(src, w, dst, ts, mul, off, shift, wide); break;
+                }
+            }
+        }
     }
     __syncthreads();
-    const int sh2 = IQT ? 12 - (bd - 8) : 19 - (bd - 8);
-    for (int t = threadIdx.x; t < nb * h; t += blockDim.x) {
-        const int b = t >> lh, y = t & (h - 1);
-        const int *srow = s_tmp + (b * h + y) * ts;
-        int16_t *drow = out + ((size_t)(first + b) << (lw + lh)) + y * w;
-        itx_line_dyn<false>(lw, [&](int k) { return srow[k]; }, [&](int nn, int v) { drow[nn] = (int16_t)v; }, sh2);
+    {
+        const int sh2 = (IQT ? 12 : 19) - (bd - 8);
+        const int nc = IQT ? h : col_tasks(lw, lh, false), lnc = 31 - __clz(nc);        // IQT: the second pass runs along rows
+        for (int t = threadIdx.x; t < nb * nc; t += blockDim.x) {
+            const int b = t >> lnc, q = t & (nc - 1);
+            if (IQT) {
+                const int *src = s_tmp + (b * h + q) * ts;
+                int16_t *dst = s_res + b * bs + q * w;
+                switch (lw) {
+                case 1: col_pass<2, true>(src, ts, dst, w, sh2); break;
+                case 2: col_pass<4, true>(src, ts, dst, w, sh2); break;
+                case 3: col_pass<8, true>(src, ts, dst, w, sh2); break;
+                case 4: col_pass<16, true>(src, ts, dst, w, sh2); break;
+                case 5: col_pass<32, true>(src, ts, dst, w, sh2); break;
+                default: col_pass<64, true>(src, ts, dst, w, sh2); break;
+                }
+            } else {
+                const int c0 = lh <= 4 ? 2 * q : q;
+                const int *src = s_tmp + b * h * ts + c0;
+                int16_t *dst = s_res + b * bs + c0;
+                switch (lh) {
+                case 1: col_pass2<2>(src, ts, dst, w, sh2); break;
+                case 2: col_pass2<4>(src, ts, dst, w, sh2); break;
+                case 3: col_pass2<8>(src, ts, dst, w, sh2); break;
+                case 4: col_pass2<16>(src, ts, dst, w, sh2); break;
+                case 5: col_pass<32, false>(src, ts, dst, w, sh2); break;
+                default: col_pass<64, false>(src, ts, dst, w, sh2); break;
+                }
+            }
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tot >> 3; i += blockDim.x) ((int4 *)g_out)[i] = ((const int4 *)s_res)[i];
+    for (int i = (tot & ~7) + threadIdx.x; i < tot; i += blockDim.x) g_out[i] = s_res[i];
 }
 
+inline size_t itdq_blocks_smem(int lw, int lh, int per) { return (size_t)per * (1 << (lw + lh)) * 4 + (size_t)per * (1 << lh) * ((1 << lw) + 4) * 4; }
 inline int launch_itdq_blocks(const int16_t *in, int16_t *out, int n, int lw, int lh, int qp, int bd, int iqt, cudaStream_t st)
 {
-    const int w = 1 << lw, h = 1 << lh;
-    int per = 256 / (w > h ? w : h);
+    static const int dq[2][6] = {{40, 45, 51, 57, 64, 71}, {40, 45, 51, 57, 64, 72}};       // xevd_tbl_dq_scale_b / xevd_tbl_dq_scale (xevd_tbl.c:255-256)
+    // xevd_itdq prologue (xevd_itdq.c:494-517)
+    const int odd = (lw + lh) & 1;
+    const int shift = 20 - 14 - (15 - bd - ((lw + lh) >> 1)) + (odd ? 8 : 0);
+    const long long mul = (long long)(dq[iqt ? 1 : 0][qp % 6] << (qp / 6)) * (odd ? 181 : 1);
+    if (shift < 0 || mul > 0x7fffffffLL) return XB200_ERR_INVALID_ARGUMENT;
+    int per = 4096 >> (lw + lh);
     if (per < 1) per = 1;
-    const size_t smem = (size_t)per * h * (w + 1) * sizeof(int);
+    const size_t smem = itdq_blocks_smem(lw, lh, per);
     const int grid = (n + per - 1) / per;
-    if (iqt) k_itdq_blocks<true><<<grid, 256, smem, st>>>(in, out, n, lw, lh, qp, bd, per);
-    else     k_itdq_blocks<false><<<grid, 256, smem, st>>>(in, out, n, lw, lh, qp, bd, per);
+    if (iqt) k_itdq_blocks<true><<<grid, 256, smem, st>>>(in, out, n, lw, lh, (int)mul, shift, mul >= 65536, bd, per);
+    else     k_itdq_blocks<false><<<grid, 256, smem, st>>>(in, out, n, lw, lh, (int)mul, shift, mul >= 65536, bd, per);
     return 1;
 }
 

@@ -47,10 +47,12 @@ constexpr int kM2LStrideW = 20;              // vertical-pair buffer row stride 
 constexpr int kM2LWords = 12 * kM2LStrideW;  // 12 pair-rows
 constexpr int kM2CStrideW = 12;              // 8 columns + 4 pad
 constexpr int kM2CWords = 6 * kM2CStrideW;   // 6 pair-rows
-constexpr int kTmpLStride = 68;              // pass-1 result row stride, words (64 + 4)
-constexpr int kTmpCStride = 36;
-constexpr int kResLStride = 72;              // residual row stride, int16 (64 + 8)
-constexpr int kResCStride = 40;
+// pass-1 results and the residual: rows 0..63 hold luma, rows 64..95 hold Cb (columns 0..31) and Cr (columns 32..63) side by side, so one
+// compile-time row stride serves every plane (the strided accesses of the passes become immediate offsets)
+constexpr int kTmpStride = 68;               // pass-1 result row stride, words (64 + 4: int4 stores of 8 consecutive rows hit 8 distinct bank quads)
+constexpr int kResStride = 72;               // residual row stride, int16 (64 + 8)
+constexpr int kPlaneRows = 96;
+__host__ __device__ __forceinline__ constexpr int plane_origin(int pl, int stride) { return pl == 0 ? 0 : 64 * stride + (pl == 2 ? 32 : 0); }
 
 constexpr int kCoefStageBytes = 2 * 2 * 64 * 64;
 constexpr int kBatchCap = 34;                // a CTU has at most 1024 luma and 1024 chroma lines per pass
@@ -97,12 +99,12 @@ struct R2Layout {
         (void)nl;
         L.win_l = o; o += kTileCap * kWinLBytes;
         L.win_c = o; o += kTileCap * kWinCBytes;
-        const int tmp_bytes = 4 * (64 * kTmpLStride + 2 * 32 * kTmpCStride);
+        const int tmp_bytes = 4 * kPlaneRows * kTmpStride;
         const int m2_bytes = 4 * kTileCap * (kM2LWords + 2 * kM2CWords);
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
         // residual planes; before the row pass the same bytes stage the CTU's slice of the coefficient stream, fetched by one bulk copy
         // while the descriptors are built (at most 2 int16 per luma sample: 4x4 CUs with their chroma blocks padded to 8)
-        const int res_bytes = 2 * (64 * kResLStride + 2 * 32 * kResCStride);
+        const int res_bytes = 2 * kPlaneRows * kResStride;
         L.res_y = o; L.coef = o; o += res_bytes > kCoefStageBytes ? res_bytes : kCoefStageBytes;
         L.cus = o; o += 32 * max_cu;
         L.tus = o; o += 16 * 3 * max_cu;
@@ -201,13 +203,18 @@ __host__ __device__ __forceinline__ void build_taps4(const int16_t *c, int *dst)
     dst[4] = (a0 << 16);      dst[5] = a1;
 }
 
-// ---- residual pass 1: one row of a transform block -----------------------------------------------------------------------
-// Baseline: one ROW of the block (the reference's two passes have no rounding in between, so their order is free and rows are the
-// 16-byte-load-friendly choice).  IQT: the first pass rounds to s16, so it has to be the reference's first pass - one COLUMN, strided.
+// ---- residual passes ---------------------------------------------------------------------------------------------------------------
+// A task is one line of a transform block or - Baseline transform, lines of at most 16 points - two neighbouring lines: two rows share
+// the descriptor lookup and the kernel constants, two columns are loaded as 8-byte words and stored as packed sample pairs.
+__host__ __device__ __forceinline__ int row_tasks(int lw, int lh, bool iqt) { return (!iqt && lw <= 4) ? (1 << lh) >> 1 : 1 << lh; }
+__host__ __device__ __forceinline__ int col_tasks(int lw, int lh, bool iqt) { return (!iqt && lh <= 4) ? (1 << lw) >> 1 : 1 << lw; }
+
+// N coefficients of one line -> dequantised values.  xevd_dquant: clip16((c * scale + offset) >> shift); the clip happens in the saturating
+// pack (I2IP.S16.S32.SAT) that forms the butterfly's operand pairs.  Baseline reads a ROW (16-byte loads); IQT a COLUMN (its first pass
+// rounds to s16, so it has to be the reference's first pass)
 template <int N, bool IQT>
-__device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int sstride, int *__restrict__ dst, int dstride, int mul, int off, int shift, bool wide)
+__device__ __forceinline__ void load_dequant(const int16_t *__restrict__ src, int sstride, int (&v)[N], int mul, int off, int shift, bool wide)
 {
-    int v[N];
     if (IQT) {
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] = src[k * sstride];
@@ -226,8 +233,6 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int ss
         const int w = *(const int *)src;
         v[0] = (int)(int16_t)(w & 0xffff); v[1] = w >> 16;
     }
-    // xevd_dquant: clip16((c * scale + offset) >> shift); the clip happens in the saturating pack (I2IP.S16.S32.SAT)
-    // that forms the butterfly's operand pairs
     if (!wide) {
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] = (v[k] * mul + off) >> shift;
@@ -235,11 +240,13 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int ss
 #pragma unroll
         for (int k = 0; k < N; k++) v[k] = (int)(((long long)v[k] * mul + (long long)off) >> shift);
     }
-    int out[N];
-    InvDct2P<N, 1, N>::run(v, out);
-    if (IQT) {          // Main IQT: same kernel, first pass rounded to s16 (xevdm_itdq.c:35-39,714-716)
+}
+template <int N, bool IQT>
+__device__ __forceinline__ void store_pass1(const int (&out)[N], int *__restrict__ dst, const int ts)
+{
+    if (IQT) {          // Main IQT: same kernel, first pass rounded to s16 (xevdm_itdq.c:35-39,714-716); the line is a column of the block
 #pragma unroll
-        for (int k = 0; k < N; k++) dst[k * dstride] = xb_clip16((out[k] + 64) >> 7);
+        for (int k = 0; k < N; k++) dst[k * ts] = xb_clip16((out[k] + 64) >> 7);
         return;
     }
     if (N >= 4 && ((smem_u32(dst) & 15) == 0)) {
@@ -250,17 +257,58 @@ __device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int ss
         for (int q = 0; q < N / 2; q++) ((int2 *)dst)[q] = make_int2(out[2 * q], out[2 * q + 1]);
     }
 }
-
-// ---- residual pass 2: one column of a transform block -----------------------------------------------------------------------
+template <int N, bool IQT>
+__device__ __forceinline__ void row_pass(const int16_t *__restrict__ src, int sstride, int *__restrict__ dst, const int ts, int mul, int off, int shift, bool wide)
+{
+    int v[N], out[N];
+    load_dequant<N, IQT>(src, sstride, v, mul, off, shift, wide);
+    InvDct2P<N, 1, N>::run(v, out);
+    store_pass1<N, IQT>(out, dst, ts);
+}
+// two neighbouring rows of a Baseline block (row stride of the coefficients: sstride; of the results: ts)
 template <int N>
-__device__ __forceinline__ void col_pass(const int *__restrict__ src, int sstride, int16_t *__restrict__ dst, int dstride, int sh2)
+__device__ __forceinline__ void row_pass2(const int16_t *__restrict__ src, int sstride, int *__restrict__ dst, const int ts, int mul, int off, int shift, bool wide)
+{
+    int v0[N], v1[N], o0[N], o1[N];
+    load_dequant<N, false>(src, sstride, v0, mul, off, shift, wide);
+    load_dequant<N, false>(src + sstride, sstride, v1, mul, off, shift, wide);
+    InvDct2P<N, 1, N>::run2(v0, v1, o0, o1);
+    store_pass1<N, false>(o0, dst, ts);
+    store_pass1<N, false>(o1, dst + ts, ts);
+}
+
+// second pass, one line.  Baseline: a column (stride ts in, rs out); IQT: a row, contiguous
+template <int N, bool IQT>
+__device__ __forceinline__ void col_pass(const int *__restrict__ src, const int ts, int16_t *__restrict__ dst, const int rs, int sh2)
 {
     int in[N], out[N];
+    if (IQT) {
 #pragma unroll
-    for (int k = 0; k < N; k++) in[k] = src[k * sstride];
+        for (int k = 0; k < N / 2; k++) { const int2 v = ((const int2 *)src)[k]; in[2 * k] = v.x; in[2 * k + 1] = v.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) in[k] = src[k * ts];
+    }
     InvDct2R<N>::run(in, out, 1 << (sh2 - 1));
+    if (IQT) {
 #pragma unroll
-    for (int k = 0; k < N; k++) dst[k * dstride] = (int16_t)pack_sat16(out[k] >> sh2, 0);
+        for (int k = 0; k < N / 2; k++) ((int *)dst)[k] = pack_sat16(out[2 * k] >> sh2, out[2 * k + 1] >> sh2);
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; k++) dst[k * rs] = (int16_t)pack_sat16(out[k] >> sh2, 0);
+    }
+}
+// two neighbouring columns of a Baseline block: 8-byte loads, packed 4-byte stores
+template <int N>
+__device__ __forceinline__ void col_pass2(const int *__restrict__ src, const int ts, int16_t *__restrict__ dst, const int rs, int sh2)
+{
+    int a[N], b[N], oa[N], ob[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { const int2 v = *(const int2 *)(src + k * ts); a[k] = v.x; b[k] = v.y; }
+    InvDct2R<N>::run(a, oa, 1 << (sh2 - 1));
+    InvDct2R<N>::run(b, ob, 1 << (sh2 - 1));
+#pragma unroll
+    for (int k = 0; k < N; k++) *(int *)(dst + k * rs) = pack_sat16(oa[k] >> sh2, ob[k] >> sh2);
 }
 
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
@@ -334,7 +382,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     }
 
     // ---- per-CU counts -> exclusive prefix sums: warp q scans quantity q -------------------------------------------------------
-    // q: 0 luma blocks, 1 chroma blocks, 2 pass-1 luma lines, 3 pass-1 chroma lines, 4 pass-2 luma lines, 5 pass-2 chroma, 6 tiles
+    // q: 0 luma blocks, 1 chroma blocks, 2 row-direction luma tasks, 3 row-direction chroma tasks, 4 column-direction luma tasks, 5 column-direction
+    //    chroma tasks, 6 tiles (a task = one line, or two neighbouring lines: row_tasks / col_tasks)
     if (warp == 7) {            // number of intra / IBC CUs (their residual is parked in the picture below)
         int n = 0;
         for (int i = lane; i < ncu; i += 32) n += (xb_wavefront_mode(s_cu[i].mode) && !(DISP && (s_cu[i].flags & kCuOtherKernel))) ? 1 : 0;
@@ -357,10 +406,10 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 switch (warp) {
                 case 0: c = ny; break;
                 case 1: c = nc; break;
-                case 2: c = ny * h; break;
-                case 3: c = nc * (h >> 1); break;
-                case 4: c = ny * w; break;
-                case 5: c = nc * (w >> 1); break;
+                case 2: c = ny * row_tasks(cu.log2w, cu.log2h, IQT); break;
+                case 3: c = nc * row_tasks(cu.log2w - 1, cu.log2h - 1, IQT); break;
+                case 4: c = ny * col_tasks(cu.log2w, cu.log2h, IQT); break;
+                case 5: c = nc * col_tasks(cu.log2w - 1, cu.log2h - 1, IQT); break;
                 default: c = inter ? max(1, w >> 4) * max(1, h >> 4) : 0; break;
                 }
             }
@@ -401,8 +450,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             const int coef = cu.coef_off + (pl >= 1 && has_y ? n_y : 0) + (pl == 2 && has_u ? n_c : 0);
             TuDesc d;
             d.coef_off = coef - coef_base;      // relative to the staged slice
-            d.tmp_off = (uint16_t)((ly >> sh) * (pl ? kTmpCStride : kTmpLStride) + (lx >> sh));
-            d.res_off = (uint16_t)((ly >> sh) * (pl ? kResCStride : kResLStride) + (lx >> sh));
+            d.tmp_off = (uint16_t)(plane_origin(pl, kTmpStride) + (ly >> sh) * kTmpStride + (lx >> sh));
+            d.res_off = (uint16_t)(plane_origin(pl, kResStride) + (ly >> sh) * kResStride + (lx >> sh));
             d.lw_lh = (uint8_t)(lw | (lh << 4));
             d.cstride_log2 = (uint8_t)lw;
             const int qp = pl == 0 ? cu.qp_y : (pl == 1 ? cu.qp_u : cu.qp_v);
@@ -412,19 +461,20 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             d.shift = (uint8_t)shift;
             d.mul = (int)mul;
             d.plane_wide = (uint8_t)(pl | ((mul >= 65536) ? 4 : 0));
+            const int nr = row_tasks(lw, lh, IQT), ncl = col_tasks(lw, lh, IQT);
             int b, p1, p2;
             if (pl == 0) {
                 b = of[0]; p1 = of[2]; p2 = of[4];
                 s_tu[b] = d; s_pre1[b] = (uint16_t)p1; s_pre2[b] = (uint16_t)p2;
             } else {
                 const int second = pl == 2 && has_u ? 1 : 0;          // Cr follows Cb in the chroma tables
-                b = n_tuy + of[1] + second; p1 = of[3] + (second << lh); p2 = of[5] + (second << lw);
+                b = n_tuy + of[1] + second; p1 = of[3] + second * nr; p2 = of[5] + second * ncl;
                 s_tu[b] = d;                                            // chroma tables sit after a luma end marker
                 s_pre1[b + 1] = (uint16_t)p1; s_pre2[b + 1] = (uint16_t)p2;
             }
-            // the block that holds the first line of a 32-line batch is where the passes start their lookup
-            for (int k = (p1 + 31) >> 5; (k << 5) < p1 + (1 << lh); k++) s_bat1[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
-            for (int k = (p2 + 31) >> 5; (k << 5) < p2 + (1 << lw); k++) s_bat2[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
+            // the block that holds the first task of a 32-task batch is where the passes start their lookup
+            for (int k = (p1 + 31) >> 5; (k << 5) < p1 + nr; k++) s_bat1[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
+            for (int k = (p2 + 31) >> 5; (k << 5) < p2 + ncl; k++) s_bat2[(pl ? kBatchCap : 0) + k] = (uint16_t)b;
             continue;
         }
         // prediction tiles (inter CUs only)
@@ -519,26 +569,39 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         if (li >= (chroma ? nAc : nAy)) continue;
         const int b = chroma ? find_tu(preA + 1, batA + kBatchCap, li) : find_tu(preA, batA, li);
         const TuDesc d = s_tu[b];
-        const int q = li - (int)(chroma ? preA[b + 1] : preA[b]);           // row (Baseline) / column (IQT) of the block
-        const int ln = IQT ? d.lw_lh >> 4 : d.lw_lh & 15, pl = d.plane_wide & 3;
-        const int ts = pl ? kTmpCStride : kTmpLStride;
-        const int16_t *src = s_coef + d.coef_off + (IQT ? q : q << d.cstride_log2);
-        int *dst = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + (IQT ? q : q * ts);
+        const int q = li - (int)(chroma ? preA[b + 1] : preA[b]);           // task of the block: row / row pair (Baseline), column (IQT)
+        const int ln = IQT ? d.lw_lh >> 4 : d.lw_lh & 15;
         const int off = d.shift ? (1 << (d.shift - 1)) : 0, cs = 1 << d.cstride_log2;
         const bool wide = (d.plane_wide & 4) != 0;
-        switch (ln) {
-        case 1: row_pass<2, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
-        case 2: row_pass<4, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
-        case 3: row_pass<8, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
-        case 4: row_pass<16, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
-        case 5: row_pass<32, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
-        default: row_pass<64, IQT>(src, cs, dst, ts, d.mul, off, d.shift, wide); break;
+        if (IQT) {
+            const int16_t *src = s_coef + d.coef_off + q;
+            int *dst = s_tmp + d.tmp_off + q;
+            switch (ln) {
+            case 1: row_pass<2, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 2: row_pass<4, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 3: row_pass<8, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 4: row_pass<16, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 5: row_pass<32, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            default: row_pass<64, true>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            }
+        } else {
+            const int r0 = ln <= 4 ? 2 * q : q;
+            const int16_t *src = s_coef + d.coef_off + (r0 << d.cstride_log2);
+            int *dst = s_tmp + d.tmp_off + r0 * kTmpStride;
+            switch (ln) {
+            case 1: row_pass2<2>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 2: row_pass2<4>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 3: row_pass2<8>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 4: row_pass2<16>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            case 5: row_pass<32, false>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            default: row_pass<64, false>(src, cs, dst, kTmpStride, d.mul, off, d.shift, wide); break;
+            }
         }
     }
     __syncthreads();
     if (n_tu < 3 * ncu) {         // the coefficient slice is consumed: uncoded blocks must read as zero residual
         int4 *z = (int4 *)s_res;
-        const int nz = 2 * (64 * kResLStride + 2 * 32 * kResCStride) / 16;
+        const int nz = 2 * kPlaneRows * kResStride / 16;
         for (int i = tid; i < nz; i += kR2Threads) z[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
     }
@@ -552,19 +615,31 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             if (li >= (chroma ? nBc : nBy)) continue;
             const int b = chroma ? find_tu(preB + 1, batB + kBatchCap, li) : find_tu(preB, batB, li);
             const TuDesc d = s_tu[b];
-            const int q = li - (int)(chroma ? preB[b + 1] : preB[b]);       // column (Baseline) / row (IQT)
-            const int ln = IQT ? d.lw_lh & 15 : d.lw_lh >> 4, pl = d.plane_wide & 3;
-            const int ss = pl ? kTmpCStride : kTmpLStride, ds = pl ? kResCStride : kResLStride;
-            const int *src = s_tmp + (pl == 0 ? 0 : (pl == 1 ? 64 * kTmpLStride : 64 * kTmpLStride + 32 * kTmpCStride)) + d.tmp_off + (IQT ? q * ss : q);
-            int16_t *dst = s_res + (pl == 0 ? 0 : (pl == 1 ? 64 * kResLStride : 64 * kResLStride + 32 * kResCStride)) + d.res_off + (IQT ? q * ds : q);
-            const int s1 = IQT ? 1 : ss, d1 = IQT ? 1 : ds;
-            switch (ln) {
-            case 1: col_pass<2>(src, s1, dst, d1, sh2); break;
-            case 2: col_pass<4>(src, s1, dst, d1, sh2); break;
-            case 3: col_pass<8>(src, s1, dst, d1, sh2); break;
-            case 4: col_pass<16>(src, s1, dst, d1, sh2); break;
-            case 5: col_pass<32>(src, s1, dst, d1, sh2); break;
-            default: col_pass<64>(src, s1, dst, d1, sh2); break;
+            const int q = li - (int)(chroma ? preB[b + 1] : preB[b]);       // task of the block: column / column pair (Baseline), row (IQT)
+            const int ln = IQT ? d.lw_lh & 15 : d.lw_lh >> 4;
+            if (IQT) {
+                const int *src = s_tmp + d.tmp_off + q * kTmpStride;
+                int16_t *dst = s_res + d.res_off + q * kResStride;
+                switch (ln) {
+                case 1: col_pass<2, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 2: col_pass<4, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 3: col_pass<8, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 4: col_pass<16, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 5: col_pass<32, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                default: col_pass<64, true>(src, kTmpStride, dst, kResStride, sh2); break;
+                }
+            } else {
+                const int c0 = ln <= 4 ? 2 * q : q;
+                const int *src = s_tmp + d.tmp_off + c0;
+                int16_t *dst = s_res + d.res_off + c0;
+                switch (ln) {
+                case 1: col_pass2<2>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 2: col_pass2<4>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 3: col_pass2<8>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 4: col_pass2<16>(src, kTmpStride, dst, kResStride, sh2); break;
+                case 5: col_pass<32, false>(src, kTmpStride, dst, kResStride, sh2); break;
+                default: col_pass<64, false>(src, kTmpStride, dst, kResStride, sh2); break;
+                }
             }
         }
     }
@@ -577,13 +652,13 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         const int w = 1 << cu.log2w, h = 1 << cu.log2h, lx = cu.x - ctu_x, ly = cu.y - ctu_y;
         for (int k = tid; k < (w * h) >> 1; k += kR2Threads) {      // luma, two samples per thread
             const int y = k >> (cu.log2w - 1), x = (k & ((w >> 1) - 1)) << 1;
-            *(int *)(a.cur.y + (size_t)(cu.y + y) * a.s_l + cu.x + x) = *(const int *)(s_res + (ly + y) * kResLStride + lx + x);
+            *(int *)(a.cur.y + (size_t)(cu.y + y) * a.s_l + cu.x + x) = *(const int *)(s_res + (ly + y) * kResStride + lx + x);
         }
         for (int k = tid; k < (w * h) >> 2; k += kR2Threads) {      // chroma: both planes, two samples per thread
             const int pl = k >= ((w * h) >> 3), kk = k - pl * ((w * h) >> 3);
             const int y = kk >> (cu.log2w - 2), x = (kk & ((w >> 2) - 1)) << 1;
             *(int *)((pl ? a.cur.v : a.cur.u) + (size_t)((cu.y >> 1) + y) * a.s_c + (cu.x >> 1) + x) =
-                *(const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + ((ly >> 1) + y) * kResCStride + (lx >> 1) + x);
+                *(const int *)(s_res + plane_origin(1 + pl, kResStride) + ((ly >> 1) + y) * kResStride + (lx >> 1) + x);
         }
     }
 
@@ -747,12 +822,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 const TileDesc td = s_tile[t0 + slot];
                 if (2 * cp < td.tw && 8 * rg < td.th) {
                     const int x = td.px + 2 * cp, y = td.py + 8 * rg;
-                    const int *res = (const int *)(s_res + y * kResLStride + x);
+                    const int *res = (const int *)(s_res + y * kResStride + x);
                     pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
 #pragma unroll
                     for (int r = 0; r < 8; r++)
                         if (8 * rg + r < td.th) {
-                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResLStride / 2)], maxv2);
+                            const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResStride / 2)], maxv2);
                             if (PEER) *(int *)(s_out + (y + r) * 64 + x) = v;
                             else *(int *)(dst + (size_t)r * a.s_l) = v;
                         }
@@ -761,12 +836,12 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 const int cw = td.tw >> 1, ch = td.th >> 1;
                 if (2 * ccp < cw && 4 * crg < ch) {
                     const int x = (td.px >> 1) + 2 * ccp, y = (td.py >> 1) + 4 * crg;
-                    const int *res = (const int *)(s_res + 64 * kResLStride + pl * 32 * kResCStride + y * kResCStride + x);
+                    const int *res = (const int *)(s_res + plane_origin(1 + pl, kResStride) + y * kResStride + x);
                     pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
 #pragma unroll
                     for (int r = 0; r < 4; r++)
                         if (4 * crg + r < ch) {
-                            const int v = (int)__viaddmin_s16x2_relu(outc[r], res[r * (kResCStride / 2)], maxv2);
+                            const int v = (int)__viaddmin_s16x2_relu(outc[r], res[r * (kResStride / 2)], maxv2);
                             if (PEER) *(int *)(s_out + 64 * 64 + pl * 32 * 32 + (y + r) * 32 + x) = v;
                             else *(int *)(dst + (size_t)r * a.s_c) = v;
                         }

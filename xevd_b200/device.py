@@ -114,8 +114,8 @@ def _handles(pics):
 class Context:
     """one decoder instance on one GPU (one CUDA stream)"""
 
-    def __init__(self, device: int = 0):
-        self.lib = abi.load_library()
+    def __init__(self, device: int = 0, lib_path=None):
+        self.lib = abi.load_library(lib_path)          # lib_path: another build of the library (A/B timing, tools/ab_v2.py)
         err = C.c_int(0)
         self.handle = self.lib.xb200_create(device, C.byref(err))
         if not self.handle:
