@@ -37,6 +37,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "xevdm_def.h"
 #include "xevdm_alf.h"
@@ -61,7 +62,7 @@ void      xevdm_get_tu_size(u8 ats_inter_info, int log2_cuw, int log2_cuh, int *
 typedef struct GLUE_PIC {
     XEVD_PIC  *host;
     xb200_pic *dev;
-    void      *registered;          /* page-locked imgb buffer (NULL when registration failed: copies fall back to staged DMA) */
+    void      *registered[3];       /* page-locked plane buffers of the imgb (NULL where registration failed: that copy falls back to staged DMA) */
 } GLUE_PIC;
 
 typedef struct GLUE_CHUNK {         /* the CUs of one CTU, in the order the walk reached it */
@@ -95,7 +96,10 @@ typedef struct GLUE {
     xb200_pic *l0[XEVD_MAX_NUM_REF_PICS], *l1[XEVD_MAX_NUM_REF_PICS];
     int n0, n1;
     long long n_pictures, n_cus_total;
+    double t_host, t_recon, t_dbk, t_alf, t_out, t_wait, t_alloc;       /* XEVD_B200_STATS: seconds spent per stage (host side of each call) */
 } GLUE;
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static GLUE *g_inst[8];
 
@@ -397,13 +401,20 @@ XEVD_PIC *glue_picbuf_alloc(PICBUF_ALLOCATOR *pa, int *ret, int bitdepth)
     for (int i = 0; i < 8; i++) if (g_inst[i] && (void *)g_inst[i] == pa->pdata[0]) g = g_inst[i];
     GLUE_PIC *slot = g ? pic_of(g, NULL) : NULL;
     int err = 0;
+    const double t0 = now_s();
     if (slot) {
         slot->dev = xb200_pic_alloc(g->dev, pa->w, pa->h, &err);
         if (slot->dev) {
             slot->host = pic;
-            slot->registered = NULL;
-            if (pic->imgb && pic->imgb->baddr[0] && xb200_host_register(pic->imgb->baddr[0], (size_t)pic->imgb->bsize[0]) == XB200_OK)
-                slot->registered = pic->imgb->baddr[0];
+            /* every plane buffer of the XEVD_IMGB (xevd_imgb_generate allocates them one by one): page-locked, the copy in
+             * glue_picbuf_expand is a true asynchronous DMA; a pageable plane would make that call wait for the device */
+            for (int k = 0; k < 3; k++) {
+                slot->registered[k] = NULL;
+                if (pic->imgb && pic->imgb->baddr[k] && pic->imgb->bsize[k] > 0 &&
+                    xb200_host_register(pic->imgb->baddr[k], (size_t)pic->imgb->bsize[k]) == XB200_OK)
+                    slot->registered[k] = pic->imgb->baddr[k];
+            }
+            g->t_alloc += now_s() - t0;
             return pic;
         }
     }
@@ -419,7 +430,7 @@ void glue_picbuf_free(PICBUF_ALLOCATOR *pa, XEVD_PIC *pic)
         GLUE_PIC *s = (g && pic) ? pic_of(g, pic) : NULL;
         if (!s) continue;
         xb200_sync(g->dev);
-        if (s->registered) xb200_host_unregister(s->registered);
+        for (int k = 0; k < 3; k++) if (s->registered[k]) xb200_host_unregister(s->registered[k]);
         xb200_pic_free(g->dev, s->dev);
         memset(s, 0, sizeof(*s));
     }
@@ -477,7 +488,9 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
     g->n_cu = 0; g->n_ext = 0; g->n_coef = 0; g->n_chunk = 0; g->last_cu = -1;
     memset(&g->pend, 0, sizeof(g->pend));
     g->dbk_done = g->alf_done = 0;
+    const double t_slice = now_s();
     int ret = g->ref_dec_slice(ctx, core);                 /* xevdm_dec_slice: entropy decode, then the walk through the hooks above */
+    g->t_host += now_s() - t_slice;
     if (XEVD_FAILED(ret)) return ret;
     if (g->err) return g->err;
     GLUE_PIC *cur = pic_of(g, ctx->pic);
@@ -544,8 +557,10 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
             for (int k = 0; k < 2; k++) for (int i = 0; i < XEVD_MAX_QP_TABLE_SIZE; i++) tbl[k][i] = xevd_qp_chroma_dynamic[k][i];
             xb200_set_chroma_qp_table(g->dev, &tbl[0][0]);
         }
+        const double t_r = now_s();
         int r = xb200_recon_frame(g->dev, &g->prm, cur->dev, g->l0, g->n0, g->l1, g->n1, cus, g->n_cu, g->ctu_first, n_ctu,
                                   g->ext, g->n_ext, coef, g->n_coef);
+        g->t_recon += now_s() - t_r;
         if (r < 0) { fprintf(stderr, "[xevd-b200] xb200_recon_frame: %d, slice type %d, lists %d / %d\n", r, ctx->sh.slice_type, g->n0, g->n1); dev_fail(g, XEVD_ERR, "xb200_recon_frame"); return g->err; }
         g->n_cus_total += g->n_cu;
         dump_stage(g, cur, "recon");
@@ -565,7 +580,9 @@ int glue_deblock(void *arg)
     GLUE_PIC *cur = pic_of(g, core->ctx->pic);
     if (!cur) return XEVD_ERR_UNEXPECTED;
     fill_params(g);
+    const double t_d = now_s();
     if (xb200_deblock(g->dev, &g->prm, cur->dev, g->l0, g->n0, g->l1, g->n1, NULL) < 0) { dev_fail(g, XEVD_ERR, "xb200_deblock"); return g->err; }
+    g->t_dbk += now_s() - t_d;
     if (getenv("XEVD_B200_DUMP")) {
         char fn[512];
         snprintf(fn, sizeof(fn), "%s/pic_%04d_dbkprm.bin", getenv("XEVD_B200_DUMP"), g_dump_serial - 1);
@@ -606,19 +623,21 @@ void glue_picbuf_expand(XEVD_CTX *ctx, XEVD_PIC *pic)
     GLUE *g = glue_of(ctx);
     GLUE_PIC *s = g ? pic_of(g, pic) : NULL;
     if (!s) { if (g) dev_fail(g, XEVD_ERR_UNEXPECTED, "picture lookup"); return; }
+    const double t_o = now_s();
     if (xb200_pad(g->dev, s->dev) < 0) { dev_fail(g, XEVD_ERR, "xb200_pad"); return; }
     if (xb200_pic_download(g->dev, s->dev, pic->y, pic->s_l, pic->u, pic->s_c, pic->v, pic->s_c) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download"); return; }
     if (ctx->sps->tool_dmvr && ctx->sh.slice_type == SLICE_B) {
         if (xb200_pic_download_maps(g->dev, s->dev, (int16_t *)pic->map_mv, NULL, NULL) < 0) { dev_fail(g, XEVD_ERR, "xb200_pic_download_maps"); return; }
     } else g->maps_pending = 1;
     g->n_pictures++;
+    g->t_out += now_s() - t_o;
 }
 
 /* xevd_imgb_generate is what the reference calls right before it reads a decoded picture on the host (MD5 check, src_main/xevdm.c:3269;
  * DRA copy on pull, :3378): the asynchronous copy has to have landed */
 XEVD_IMGB *glue_imgb_generate(int w, int h, int padl, int padc, int idc, int bit_depth)
 {
-    for (int i = 0; i < 8; i++) if (g_inst[i]) xb200_sync(g_inst[i]->dev);
+    for (int i = 0; i < 8; i++) if (g_inst[i]) { const double t0 = now_s(); xb200_sync(g_inst[i]->dev); g_inst[i]->t_wait += now_s() - t0; }
     return xevd_imgb_generate(w, h, padl, padc, idc, bit_depth);
 }
 
@@ -668,7 +687,9 @@ void xevd_delete(XEVD id)
     if (g) {
         for (int i = 0; i < 8; i++) if (g_inst[i] == g) g_inst[i] = NULL;
         if (getenv("XEVD_B200_STATS"))
-            fprintf(stderr, "[xevd-b200] %lld pictures, %lld CUs, %lld kernel launches\n", g->n_pictures, g->n_cus_total, xb200_launch_count(g->dev));
+            fprintf(stderr, "[xevd-b200] %lld pictures, %lld CUs, %lld kernel launches; host seconds: entropy + walk %.4f, recon call %.4f, deblock call %.4f, "
+                    "pad + download calls %.4f, waiting for the device %.4f, picture allocation %.4f\n", g->n_pictures, g->n_cus_total, xb200_launch_count(g->dev),
+                    g->t_host, g->t_recon, g->t_dbk, g->t_out, g->t_wait, g->t_alloc);
         xb200_destroy(g->dev);
         free(g->cus); free(g->ext); free(g->coef); free(g->chunk); free(g->ctu_first); free(g->cus2); free(g->coef2);
         free(g);
@@ -687,7 +708,7 @@ int xevd_decode(XEVD id, XEVD_BITB *bitb, XEVD_STAT *stat)
 int xevd_pull(XEVD id, XEVD_IMGB **imgb)
 {
     GLUE *g = glue_of((XEVD_CTX *)id);
-    if (g) xb200_sync(g->dev);                                 /* the planes handed out are complete */
+    if (g) { const double t0 = now_s(); xb200_sync(g->dev); g->t_wait += now_s() - t0; }       /* the planes handed out are complete */
     return xevdref_pull(id, imgb);
 }
 

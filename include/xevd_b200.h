@@ -246,6 +246,9 @@ int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *c
                        const void *d_coef, size_t n_coef, int has_intra, int max_cu_per_ctu);
 #define XB200_HAS_INTRA      1
 #define XB200_HAS_DUAL_TREE  2        /* some CU is luma-only / chroma-only: selects the per-plane owner path (with XB200_HAS_INTRA) */
+#define XB200_HAS_DENSE_WAVEFRONT 4   /* most CUs are intra / IBC / HTDF-filtered (an I picture): the CTU wavefront kernel is launched with about as
+                                         many persistent CTAs as the wavefront is wide instead of one per CTU, so that the waiting CTAs of
+                                         one picture do not fill the device and independent pictures of other contexts can be in flight */
 /* has_intra: XB200_HAS_* bits.  XB200_HAS_INTRA when the wavefront pass is needed: the picture has intra or IBC CUs, or tool_htdf is on and some CU has a
  * luma residual.  max_cu_per_ctu: upper bound of ctu_first[k+1]-ctu_first[k] (sizes on-chip work lists); 0 = unknown (worst case) */
 

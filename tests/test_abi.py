@@ -58,7 +58,8 @@ def test_constants_match_header():
             "XB200_CUF_ATS_INTRA": abi.CUF_ATS_INTRA, "XB200_CUF_AFF6": abi.CUF_AFF6,
             "XB200_EDGE_LEFT": abi.EDGE_LEFT, "XB200_EDGE_TOP": abi.EDGE_TOP, "XB200_EDGE_ATS": abi.EDGE_ATS,
             "XB200_EDGE_LEFT_NOC": abi.EDGE_LEFT_NOC, "XB200_EDGE_TOP_NOC": abi.EDGE_TOP_NOC,
-            "XB200_HAS_INTRA": abi.HAS_INTRA, "XB200_HAS_DUAL_TREE": abi.HAS_DUAL_TREE}
+            "XB200_HAS_INTRA": abi.HAS_INTRA, "XB200_HAS_DUAL_TREE": abi.HAS_DUAL_TREE,
+            "XB200_HAS_DENSE_WAVEFRONT": abi.HAS_DENSE_WAVEFRONT}
     for k, v in want.items():
         assert d.get(k) == v, (k, d.get(k), v)
 

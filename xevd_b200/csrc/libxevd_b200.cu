@@ -53,6 +53,8 @@ struct xb200_ctx {
     int ring_pos;
     int sm_count;
     int *d_sync;                 // wavefront state of the intra kernel: [0] ticket, [1..] per-CTU done flags
+    int *d_err;                  // sticky error word of the wavefront kernel (a wait that gave up), read by xb200_sync
+    bool wave_used;              // a wavefront kernel has been launched since the last xb200_sync
     int sync_cap;
     int *d_order;                // CTU addresses in wavefront order (x + 2y) for the current picture geometry
     int order_w, order_n;
@@ -104,7 +106,7 @@ xb200_ctx *xb200_create(int device, int *err)
     c->launches = 0;
     c->err[0] = 0;
     c->ring_pos = 0;
-    c->d_sync = nullptr; c->sync_cap = 0;
+    c->d_sync = nullptr; c->sync_cap = 0; c->d_err = nullptr; c->wave_used = false;
     c->d_order = nullptr; c->order_w = c->order_n = 0;
     c->out_buf = nullptr; c->out_cap = 0; c->d_dra = nullptr;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -204,6 +206,7 @@ void xb200_destroy(xb200_ctx *c)
         if (s.done) cudaEventDestroy(s.done);
     }
     if (c->d_sync) cudaFree(c->d_sync);
+    if (c->d_err) cudaFree(c->d_err);
     if (c->d_order) cudaFree(c->d_order);
     if (c->out_buf) cudaFree(c->out_buf);
     if (c->d_dra) cudaFree(c->d_dra);
@@ -221,6 +224,16 @@ int xb200_sync(xb200_ctx *c)
     if (!c) return XB200_ERR_INVALID_ARGUMENT;
     CK(c, cudaStreamSynchronize(c->stream));
     CK(c, cudaGetLastError());
+    if (c->wave_used && c->d_err) {       // did a CTU of the wavefront kernel give up waiting for a neighbour (malformed work list)?
+        int e = 0;
+        c->wave_used = false;
+        CK(c, cudaMemcpy(&e, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            cudaMemset(c->d_err, 0, sizeof(int));
+            snprintf(c->err, sizeof(c->err), "wavefront kernel: a CTU waited for a neighbour that never completed (inconsistent ctu_first / CU list)");
+            return XB200_ERR_INVALID_ARGUMENT;
+        }
+    }
     return XB200_OK;
 }
 void *xb200_stream(xb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
@@ -558,10 +571,16 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
             c->order_w = a.w_ctu; c->order_n = a.n_ctu;
         }
         CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (a.n_ctu + 1), c->stream));
-        xb::IntraSync sy{c->d_sync, c->d_sync + 1, c->d_order};
+        if (!c->d_err) { CK(c, cudaMalloc((void **)&c->d_err, sizeof(int))); CK(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream)); }
+        xb::IntraSync sy{c->d_sync, c->d_err, c->d_sync + 1, c->d_order};
         const size_t sm = xb::IntraSmem::bytes();
-        if (a.iqt) xb::k_recon_intra<true><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);
-        else       xb::k_recon_intra<false><<<a.n_ctu, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        // persistent CTAs (xb_intra.cuh): dense dependencies (I pictures) -> about as many CTAs as the x + 2y wavefront is wide
+        const int h_ctu = a.n_ctu / a.w_ctu;
+        int grid = a.n_ctu;
+        if (has_intra & XB200_HAS_DENSE_WAVEFRONT) { const int wide = ((a.w_ctu + 1) / 2 < h_ctu ? (a.w_ctu + 1) / 2 : h_ctu) + 8; if (wide < grid) grid = wide; }
+        if (a.iqt) xb::k_recon_intra<true><<<grid, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        else       xb::k_recon_intra<false><<<grid, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        c->wave_used = true;
         c->launches++;
         CK(c, cudaGetLastError());
     }
@@ -669,9 +688,10 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         if (!pinned) { cudaGetLastError(); memcpy(hp + off, src, bytes); src = hp + off; }
         return cudaMemcpyAsync(dp + off, src, bytes, cudaMemcpyHostToDevice, c->stream);
     };
-    int has_intra = 0, max_cu = 0, any_l1 = 0;
+    int has_intra = 0, max_cu = 0, any_l1 = 0, n_wave = 0;
     for (int i = 0; i < n_cu; i++) {
         const bool intra = xb_wavefront_mode(cus[i].mode);
+        n_wave += intra || (prm->tool_htdf && (cus[i].cbf & 15));
         // local dual tree (TREE_L / TREE_C CUs, src_main/xevdm.c:1828-1846): intra-only nodes; inter CUs always carry all three planes and
         // IBC needs luma (xevdm.c:1113-1122); the cbf bits of a plane the CU does not carry must be clear (its coefficient block is absent)
         const int pl = cus[i].flags & (XB200_CUF_LUMA | XB200_CUF_CHROMA);
@@ -696,6 +716,7 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
             return XB200_ERR_INVALID_ARGUMENT;
         }
     }
+    if (2 * n_wave > n_cu) has_intra |= XB200_HAS_DENSE_WAVEFRONT;       // I picture (or nearly): size the wavefront grid for the wavefront, not for the picture
     if (!any_l1) n1 = 0;          // P picture: no CU predicts from list 1 (selects the single-list kernel)
     for (int i = 0; i < n_ctu; i++) { const int d = (int)(ctu_first[i + 1] - ctu_first[i]); if (d > max_cu) max_cu = d; }
     CK(c, h2d(0, cus, (size_t)n_cu * sizeof(XB200_CU)));

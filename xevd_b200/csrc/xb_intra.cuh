@@ -341,6 +341,7 @@ __device__ __forceinline__ void cu_htdf(const XbFrameArgs &a, int log2w, int log
 
 struct IntraSync {
     int *ticket;        // next position of `order` to hand out
+    int *err;           // sticky: set when a wait gave up (malformed work list: a dependency that never completes); read by xb200_sync
     int *done;          // [n_ctu] 1 when every CU of the CTU is final
     const int *order;   // CTU addresses sorted by wavefront index x + 2y: CTUs of one index are independent, so the CTAs resident at
                         // any time span many CTU rows (raster order kept only ~2.5 rows busy: 148 resident CTAs / 60 CTUs per row);
@@ -364,6 +365,19 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     __shared__ unsigned s_req[4], s_has[4];
     const int tid = threadIdx.x;
 
+    // Persistent CTAs: each takes CTU after CTU in wavefront order until the tickets run out.  The host sizes the grid - one CTA per CTU
+    // when the dependencies are sparse (P / B pictures: most CTUs can start at once), about as many CTAs as the wavefront is wide when
+    // they are dense (I pictures), so that the CTAs of one picture do not fill the device with waiters and several independent pictures
+    // (other contexts / streams) can be in flight.  A dependency always has an earlier ticket, and a ticket is only ever held by a
+    // resident CTA: no deadlock for any grid size.
+    // A wait that does not end within ~2 s (a malformed work list) raises the sticky error word and lets the CTA go on: wrong pixels, no hang.
+    auto wait_done = [&](int nc) {
+        volatile int *f = sy.done + nc;
+        unsigned spins = 0;
+        while (*f == 0) { __nanosleep(64); if (++spins > (1u << 24)) { atomicExch(sy.err, 1); break; } }
+    };
+    for (;;) {
+    __syncthreads();                // every thread is done with the previous CTU's shared state
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
     __syncthreads();
     if (s_ctu >= a.n_ctu) return;
@@ -462,10 +476,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         // ---- wait for them ----------------------------------------------------------------------------------------------------------
         if (tid < 4 && (!prune || (s_req[tid] & s_has[tid]))) {
             const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
-            if (nx >= 0 && nx < a.w_ctu && ny >= 0) {
-                volatile int *f = sy.done + ny * a.w_ctu + nx;
-                while (*f == 0) __nanosleep(32);
-            }
+            if (nx >= 0 && nx < a.w_ctu && ny >= 0) wait_done(ny * a.w_ctu + nx);
             __threadfence();
         }
         __syncthreads();
@@ -602,9 +613,15 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                                                                (a.constrained && cu.mode == XB200_MODE_INTRA) ? a.map_scu + (cu.y >> 2) * a.w_scu + (cu.x >> 2) : nullptr);
         }
     }
+    else if (a.ibc && cx > 0) {
+        // a CTU without wavefront work still hands on its left neighbour's completion: an IBC vector may reach any CTU to the left in the
+        // row, and the CTUs in between must not report `done` before those are final (the waits are transitive along the row)
+        if (tid == 0) wait_done(ctu - 1);
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) atomicExch(sy.done + ctu, 1);
+    }
 }
 
 }  // namespace xb
