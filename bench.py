@@ -417,6 +417,53 @@ def run_ours(args):
     # a decoded sample read back on the host proves the D2H happened
     checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())
 
+    # ---- north_star's multi-GPU data plane: rank 0 SCATTERS the pre-parsed CU work of one picture per rank over NCCL / NVLink, every rank
+    #      reconstructs its picture, rank 0 GATHERS the decoded pictures (packed planes + per-SCU maps).  Everything stays on the devices;
+    #      rank 0's links carry (world - 1) work lists out and (world - 1) pictures in per round, so this is the hub-limited figure next
+    #      to the independent-GOP figure above (where every rank feeds itself).
+    scatter_gather = None
+    if dist is not None and not band:
+        prm0, cl0 = frames[0]
+        blob_parts = [cl0.cus.view(np.uint8).ravel(), cl0.ctu_first.view(np.uint8).ravel(), cl0.ext.view(np.uint8).ravel(), cl0.coef.view(np.uint8).ravel()]
+        offs, o = [], 0
+        for p_ in blob_parts:
+            offs.append(o)
+            o += (p_.size + 255) & ~255
+        blob = np.zeros(o, np.uint8)
+        for p_, of_ in zip(blob_parts, offs):
+            blob[of_:of_ + p_.size] = p_
+        recv = torch.empty(o, dtype=torch.uint8, device=dev)
+        # rank 0 holds every rank's work list (here: the same synthetic picture shape, its own copy per destination)
+        src = [torch.from_numpy(blob).to(dev) for _ in range(world)] if rank == 0 else None
+        cur_sg = slots[0]["cur"]
+        pic_bytes = ctx.band_bytes(cur_sg, h)
+        mine = torch.empty(pic_bytes, dtype=torch.uint8, device=dev)
+        gathered = [torch.empty(pic_bytes, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+
+        def round_sg():
+            with torch.cuda.stream(stream):
+                dist.scatter(recv, src, src=0)
+                b = recv.data_ptr()
+                ctx.recon_frame_dev(prm0, cur_sg, slots[0]["refs"], slots[0]["refs_l1"], b + offs[0], cl0.n_cu, b + offs[1], cl0.n_ctu, b + offs[2], len(cl0.ext),
+                                    b + offs[3], cl0.coef.size, max_cu_per_ctu=slots[0]["max_cu"])
+                ctx.pad(cur_sg)
+                ctx.band_pack(cur_sg, 0, h, mine.data_ptr())
+                dist.gather(mine, gathered, dst=0)
+        for _ in range(3):
+            round_sg()
+        barrier()
+        n_rounds = 40
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(n_rounds):
+            round_sg()
+        g1.record(stream)
+        barrier()
+        ms_sg = xdist.max_over_ranks(g0.elapsed_time(g1), dev)
+        scatter_gather = {"value": world * n_rounds / (ms_sg * 1e-3), "unit": UNIT, "rounds": n_rounds, "bytes_scattered_per_picture": int(o), "bytes_gathered_per_picture": int(pic_bytes),
+                          "what": "per round: NCCL scatter of one picture's CU work per rank from rank 0, xb200_recon_frame_dev + xb200_pad + pack on every rank, NCCL gather of "
+                                  "the decoded pictures (planes + maps) on rank 0; device-resident on both ends"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(args.workload)
@@ -463,6 +510,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if extra is not None:
             line["extra"] = extra
+        if scatter_gather is not None:
+            line["nccl_scatter_gather"] = scatter_gather
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

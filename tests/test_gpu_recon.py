@@ -747,3 +747,50 @@ def test_4k_main_full_pipeline(ctx, oracle, lg, iqt, seed):
 def test_8k_parity_vs_oracle(ctx, oracle):
     """BASELINE config 4's picture size on one GPU: 7680x4320 10-bit config 2A bit-exact against the oracle (planes and maps)"""
     _run(ctx, oracle, 7680, 4320, 10, "A", seed=12, n_refs=1)
+
+
+def test_host_entry_refuses_malformed_work_lists(ctx):
+    """xb200_recon_frame checks everything the kernels turn into an address: a malformed list fails the call with
+    XB200_ERR_INVALID_ARGUMENT and a message naming the CU, instead of writing outside the picture or overrunning shared memory"""
+    import copy
+    from xevd_b200 import abi
+    from xevd_b200.device import XevdB200Error
+    w, h, bd = 256, 128, 10
+    prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=5, n_refs=1, bi_frac=0.0)
+    refs = synth.make_refs(w, h, bd, 1, seed=6)
+    drefs = [ctx.pic_alloc(w, h).upload(r) for r in refs]
+    cur = ctx.pic_alloc(w, h)
+    ctx.recon_frame(prm, cur, drefs, [], cl)            # the untouched list is accepted
+
+    def refused(mutate, needle):
+        bad = copy.deepcopy(cl)
+        bad.cus = bad.cus.copy(); bad.ctu_first = bad.ctu_first.copy()
+        mutate(bad)
+        with pytest.raises(XevdB200Error) as e:
+            ctx.recon_frame(prm, cur, drefs, [], bad)
+        assert e.value.code == abi.XB200_ERR_INVALID_ARGUMENT, e.value
+        assert needle in str(e.value), str(e.value)
+
+    def m_first(b): b.ctu_first[-1] += 1
+    def m_outside(b): b.cus["x"][0] = 64                 # CU 0 is listed under CTU 0
+    def m_size(b): b.cus["log2w"][0] = 9
+    def m_coef(b): b.cus["coef_off"][3] += 8
+    def m_end(b): b.coef = b.coef[:-64]
+    def m_ext(b):
+        b.cus["mode"][0] = abi.MODE_AFFINE
+        b.cus["mv"][0, 1] = np.frombuffer(np.uint32(77).tobytes(), np.int16)
+    def m_ibc(b):
+        b.cus["mode"][0] = abi.MODE_IBC
+        b.cus["refi"][0] = -1
+        b.cus["mv"][0, 0] = (-300, 0)
+    refused(m_first, "ctu_first")
+    refused(m_outside, "not inside the CTU")
+    refused(m_size, "size outside")
+    refused(m_coef, "coef_off")
+    refused(m_end, "past the end")
+    refused(m_ext, "extension record")
+    refused(m_ibc, "block vector")
+    ctx.recon_frame(prm, cur, drefs, [], cl)            # and the context is still usable
+    ctx.sync()
+    for p in drefs + [cur]:
+        p.free()
