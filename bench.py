@@ -355,10 +355,13 @@ def run_ours(args):
         c = ctx if band else Context(local)
         c.set_stream(st.cuda_stream)
         ctxs.append(c); streams.append(st)
+    from xevd_b200.frame import sparse_coef
     pinned = []
     for i in range(F):
         prm, cl = frames[i % len(frames)]
-        pc = dict(cus=torch.from_numpy(cl.cus.view(np.uint8).copy()).pin_memory(),
+        sp_entries, sp_first = sparse_coef(cl.coef)
+        pc = dict(entries=torch.from_numpy(sp_entries.view(np.int32).copy()).pin_memory(), chunk_first=torch.from_numpy(sp_first.view(np.int32).copy()).pin_memory(),
+                  cus=torch.from_numpy(cl.cus.view(np.uint8).copy()).pin_memory(),
                   first=torch.from_numpy(cl.ctu_first.view(np.int32).copy()).pin_memory(),
                   ext=torch.from_numpy(cl.ext.view(np.uint8).copy()).pin_memory(),
                   coef=torch.from_numpy(cl.coef.copy()).pin_memory(),
@@ -376,16 +379,25 @@ def run_ours(args):
         refs = [c.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
         e2e_slots.append(dict(ctx=c, refs=refs, cur=c.pic_alloc(w, h)))
     torch.cuda.synchronize()
-    h2d = P * int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
+    h2d_dense = P * int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["coef"].numel() * 2 for p in pinned]))
+    h2d_sparse = P * int(np.sum([p["cus"].numel() + p["first"].numel() * 4 + p["ext"].numel() + p["entries"].numel() * 4 + p["chunk_first"].numel() * 4 for p in pinned]))
     d2h = P * F * (w * h * 3 // 2) * 2 if (not band or rank == 0) else 0       # band mode: rank 0 hands the assembled pictures to the consumer
 
-    def step_e2e():
+    def step_e2e(sparse=True):
         for _ in range(P):
             for i in range(F):
                 prm, cl = frames[i % len(frames)]
                 s, p = e2e_slots[i], pinned[i]
                 c = s["ctx"]
-                if cl.n_cu:
+                if cl.n_cu and sparse:
+                    # the coefficient stream crosses PCIe as (position, level) entries and is expanded on the device
+                    c._chk(c.lib.xb200_recon_frame_sparse(c.handle, C.byref(prm), s["cur"].handle,
+                                                          (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
+                                                          (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
+                                                          p["cus"].data_ptr(), cl.n_cu, p["first"].data_ptr(), cl.n_ctu,
+                                                          p["ext"].data_ptr(), len(cl.ext), p["entries"].data_ptr(), p["entries"].numel(),
+                                                          p["chunk_first"].data_ptr(), cl.coef.size), "xb200_recon_frame_sparse")
+                elif cl.n_cu:
                     c._chk(c.lib.xb200_recon_frame(c.handle, C.byref(prm), s["cur"].handle,
                                                    (C.c_void_p * n_refs)(*[r.handle for r in s["refs"]]), n_refs,
                                                    (C.c_void_p * n_refs)(*[r.handle for r in s["refs"][::-1]]), (n_refs if variant != "A" else 0),
@@ -405,15 +417,18 @@ def run_ours(args):
             c.sync()
 
     e2e_steps = max(1, min(args.steps, 6))
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    t_e2e = xdist.max_over_ranks(t_e2e, dev)
-    e2e_fps = (1 if band else world) * P * F * e2e_steps / t_e2e
+
+    def time_e2e(sparse):
+        step_e2e(sparse)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e(sparse)
+        torch.cuda.synchronize()
+        return (1 if band else world) * P * F * e2e_steps / xdist.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_dense_fps = time_e2e(False)          # the dense coefficient stream over PCIe (xb200_recon_frame): what round 1 reported
+    e2e_fps = time_e2e(True)                 # the sparse form (xb200_recon_frame_sparse): the public call a caller behind PCIe makes
+    h2d = h2d_sparse
     # a decoded sample read back on the host proves the D2H happened
     checksum = int(pinned[0]["out_y"][::64, ::64].to(torch.int64).sum().item())
 
@@ -502,7 +517,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "contexts": n_ctx, "checksum": checksum},
+                    "steps": e2e_steps, "contexts": n_ctx, "checksum": checksum,
+                    "call": "xb200_recon_frame_sparse (coefficient stream as (position, level) entries, expanded on the device) + xb200_pad + xb200_pic_download",
+                    "dense_stream": {"value": e2e_dense_fps, "h2d_bytes_per_step": h2d_dense, "call": "xb200_recon_frame (dense int16 coefficient stream)"}},
             "gpu_launches": launches,
             "clocks": clocks,
         }

@@ -239,6 +239,19 @@ int  xb200_recon_frame(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
                        const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
                        const XB200_CU_EXT *ext, int n_ext,
                        const int16_t *coef, size_t n_coef);
+/* The same call with the coefficient stream in SPARSE form, for callers that sit behind PCIe: quantised levels are mostly zero, and the
+ * dense stream is the larger half of what a picture moves to the device (25.9 MB of a 4K picture's 26.9 MB).  The dense stream of
+ * n_coef int16 is cut into chunks of XB200_SPARSE_CHUNK entries; chunk k owns entries[chunk_first[k] .. chunk_first[k + 1]), each
+ * (position inside the chunk) | (non-zero level) << 16; chunk_first has ceil(n_coef / XB200_SPARSE_CHUNK) + 1 elements.  The device
+ * expands the chunks into the dense stream (one extra kernel) and goes on exactly as xb200_recon_frame; XB200_CU.coef_off and every
+ * rule of the dense layout keep their meaning.  This is what a run-length entropy decoder produces before it scatters into a block
+ * (xevd_eco_run_length_cc, src_base/xevd_eco.c:354-400: (run, level) pairs along the scan). */
+#define XB200_SPARSE_CHUNK 4096
+int  xb200_recon_frame_sparse(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
+                              xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
+                              const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                              const XB200_CU_EXT *ext, int n_ext,
+                              const uint32_t *entries, size_t n_entries, const uint32_t *chunk_first, size_t n_coef);
 int  xb200_recon_frame_dev(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
                        xb200_pic *const *refs_l0, int n_l0, xb200_pic *const *refs_l1, int n_l1,
                        const void *d_cus, int n_cu, const void *d_ctu_first, int n_ctu,

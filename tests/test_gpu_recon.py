@@ -794,3 +794,32 @@ def test_host_entry_refuses_malformed_work_lists(ctx):
     ctx.sync()
     for p in drefs + [cur]:
         p.free()
+
+
+@pytest.mark.parametrize("kind", ["inter-B", "main-all", "empty-coef"])
+def test_sparse_coefficient_stream(ctx, oracle, kind):
+    """xb200_recon_frame_sparse: (position, level) entries per 4096-coefficient chunk, expanded on the device - same pictures and maps as
+    the dense call, against the oracle (what a caller behind PCIe sends: the dense stream is ~90 % zeros)"""
+    from xevd_b200.frame import sparse_coef
+    w, h, bd = 320, 192, 10
+    if kind == "main-all":
+        prm, cl, refs, _, _ = synth.make_main_frame(w, h, bit_depth=bd, seed=21)
+        r0, r1 = refs, refs[::-1]
+    else:
+        prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=8, n_refs=2, coded_frac=0.0 if kind == "empty-coef" else 0.7)
+        refs = synth.make_refs(w, h, bd, 2, seed=9)
+        r0, r1 = refs, refs[::-1]
+    want = oracle.recon_frame(prm, HostPicture(w, h, prm.poc), r0, r1, cl)
+    entries, chunk_first = sparse_coef(cl.coef)
+    assert entries.size <= cl.coef.size and chunk_first[-1] == entries.size
+    d0 = [ctx.pic_alloc(w, h).upload(r) for r in r0]
+    d1 = d0[::-1]
+    cur = ctx.pic_alloc(w, h)
+    for _ in range(2):                                   # twice: the staging ring reuses its slots
+        ctx.recon_frame_sparse(prm, cur, d0, d1, cl, (entries, chunk_first))
+    got = cur.download(maps=True)
+    for p in d0 + [cur]:
+        p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+    assert np.array_equal(got.map_scu, want.map_scu) and np.array_equal(got.map_mv, want.map_mv)

@@ -23,6 +23,7 @@ XB200_ERR_CUDA = -402
 MODE_INTRA, MODE_INTER, MODE_IBC, MODE_AFFINE = 0, 1, 4, 5
 CUF_LUMA, CUF_CHROMA, CUF_SKIP, CUF_DMVR, CUF_ATS_INTRA, CUF_AFF6 = 1, 2, 4, 8, 16, 32
 EDGE_LEFT, EDGE_TOP, EDGE_ATS, EDGE_LEFT_NOC, EDGE_TOP_NOC = 1, 2, 4, 8, 16
+SPARSE_CHUNK = 4096                     # XB200_SPARSE_CHUNK
 HAS_INTRA, HAS_DUAL_TREE, HAS_DENSE_WAVEFRONT = 1, 2, 4          # has_intra bits of xb200_recon_frame_dev
 
 # struct XB200_CU (32 bytes)
@@ -145,6 +146,11 @@ _SIGS = {
         C.c_int,
         [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
          C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t],
+    ),
+    "xb200_recon_frame_sparse": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+         C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t],
     ),
     "xb200_recon_frame_dev": (
         C.c_int,

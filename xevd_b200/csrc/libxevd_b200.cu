@@ -612,12 +612,39 @@ static int stage_acquire(xb200_ctx *c, size_t bytes, Staging **out)
     return XB200_OK;
 }
 
-int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
-                      xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
-                      const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
-                      const XB200_CU_EXT *ext, int n_ext, const int16_t *coef, size_t n_coef)
+// sparse -> dense coefficient stream on the device: one CTA per chunk of XB200_SPARSE_CHUNK int16 (zero it, then scatter the chunk's
+// non-zero levels).  The dense stream never crosses PCIe; writing and re-reading it in HBM costs ~10 us per 4K picture.
+__global__ void __launch_bounds__(256) k_expand_coef(const uint32_t *__restrict__ entries, const uint32_t *__restrict__ chunk_first, int16_t *__restrict__ dense, size_t n_coef)
 {
+    const size_t base = (size_t)blockIdx.x * XB200_SPARSE_CHUNK;
+    const int n = (int)min((size_t)XB200_SPARSE_CHUNK, n_coef - base);
+    int16_t *d = dense + base;
+    for (int i = threadIdx.x; i < (n >> 3); i += blockDim.x) ((int4 *)d)[i] = make_int4(0, 0, 0, 0);
+    for (int i = (n & ~7) + threadIdx.x; i < n; i += blockDim.x) d[i] = 0;
+    __syncthreads();
+    const uint32_t e0 = chunk_first[blockIdx.x], e1 = chunk_first[blockIdx.x + 1];
+    for (uint32_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
+        const uint32_t v = __ldg(entries + e);
+        const int pos = (int)(v & 0xffffu);
+        if (pos < n) d[pos] = (int16_t)(v >> 16);
+    }
+}
+
+static int recon_frame_host(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
+                            xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                            const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                            const XB200_CU_EXT *ext, int n_ext, const int16_t *coef, size_t n_coef,
+                            const uint32_t *sp_entries, size_t n_entries, const uint32_t *sp_chunk_first)
+{
+    const bool sparse = sp_entries != nullptr || sp_chunk_first != nullptr;
+    const size_t n_chunks = (n_coef + XB200_SPARSE_CHUNK - 1) / XB200_SPARSE_CHUNK;
     if (!c || !prm || !cur || !cus || !ctu_first || n_cu < 0 || n_ctu <= 0) return XB200_ERR_INVALID_ARGUMENT;
+    if (sparse) {
+        if (!sp_chunk_first || (n_entries && !sp_entries)) return XB200_ERR_INVALID_ARGUMENT;
+        if (sp_chunk_first[0] != 0 || sp_chunk_first[n_chunks] != n_entries) { snprintf(c->err, sizeof(c->err), "chunk_first does not span the entries"); return XB200_ERR_INVALID_ARGUMENT; }
+        for (size_t k = 0; k < n_chunks; k++)
+            if (sp_chunk_first[k + 1] < sp_chunk_first[k]) { snprintf(c->err, sizeof(c->err), "chunk_first is not monotonic at chunk %zu", k); return XB200_ERR_INVALID_ARGUMENT; }
+    }
     if (prm->log2_ctu < 5 || prm->log2_ctu > 7) return XB200_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
     // Everything the kernels turn into an address is checked here, where the lists are still host memory and every CU is visited anyway:
@@ -665,7 +692,7 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
                 if (u.cbf & 0xf00) len += ((n >> 2) + 7) & ~(size_t)7;
                 if (len) {
                     if (u.coef_off != run) return bad(i, "coef_off does not continue the coefficient stream (blocks must follow the decoding order without gaps)");
-                    if (!coef || run + len > n_coef) return bad(i, "coefficient blocks run past the end of the stream");
+                    if ((!coef && !sparse) || run + len > n_coef) return bad(i, "coefficient blocks run past the end of the stream");
                     run += len;
                 } else if (u.coef_off != run && u.coef_off != 0) return bad(i, "coef_off of a CU without coefficients must continue the stream");
             }
@@ -675,8 +702,10 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t b_cu = al((size_t)n_cu * sizeof(XB200_CU)), b_first = al((size_t)(n_ctu + 1) * 4);
     const size_t b_ext = al((size_t)(n_ext > 0 ? n_ext : 1) * sizeof(XB200_CU_EXT)), b_coef = al(n_coef * 2 + 2);
+    // sparse form: [chunk_first][entries] travel, the dense stream exists in the device half of the slot only
+    const size_t b_cf = sparse ? al((n_chunks + 1) * 4) : 0, b_en = sparse ? al(n_entries * 4 + 4) : 0;
     Staging *s;
-    int r = stage_acquire(c, b_cu + b_first + b_ext + b_coef, &s);
+    int r = stage_acquire(c, b_cu + b_first + b_ext + b_coef + b_cf + b_en, &s);
     if (r < 0) return r;
     unsigned char *hp = (unsigned char *)s->pinned, *dp = (unsigned char *)s->dev;
     // Page-locked caller memory (xb200_host_alloc, cudaHostRegister, ...) is DMA'd straight to the device slot; pageable
@@ -722,12 +751,37 @@ int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     CK(c, h2d(0, cus, (size_t)n_cu * sizeof(XB200_CU)));
     CK(c, h2d(b_cu, ctu_first, (size_t)(n_ctu + 1) * 4));
     if (n_ext > 0) CK(c, h2d(b_cu + b_first, ext, (size_t)n_ext * sizeof(XB200_CU_EXT)));
-    CK(c, h2d(b_cu + b_first + b_ext, coef, n_coef * 2));
+    if (!sparse) CK(c, h2d(b_cu + b_first + b_ext, coef, n_coef * 2));
+    else if (n_coef) {
+        const size_t o_cf = b_cu + b_first + b_ext + b_coef, o_en = o_cf + b_cf;
+        CK(c, h2d(o_cf, sp_chunk_first, (n_chunks + 1) * 4));
+        CK(c, h2d(o_en, sp_entries, n_entries * 4));
+        k_expand_coef<<<(unsigned)n_chunks, 256, 0, c->stream>>>((const uint32_t *)(dp + o_en), (const uint32_t *)(dp + o_cf), (int16_t *)(dp + b_cu + b_first + b_ext), n_coef);
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
     r = xb200_recon_frame_dev(c, prm, cur, l0, n0, l1, n1, dp, n_cu, dp + b_cu, n_ctu, dp + b_cu + b_first, n_ext,
                               dp + b_cu + b_first + b_ext, n_coef, has_intra, max_cu);
     CK(c, cudaEventRecord(s->done, c->stream));
     s->busy = true;
     return r;
+}
+
+int xb200_recon_frame(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
+                      xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                      const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                      const XB200_CU_EXT *ext, int n_ext, const int16_t *coef, size_t n_coef)
+{
+    return recon_frame_host(c, prm, cur, l0, n0, l1, n1, cus, n_cu, ctu_first, n_ctu, ext, n_ext, coef, n_coef, nullptr, 0, nullptr);
+}
+
+int xb200_recon_frame_sparse(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
+                             xb200_pic *const *l0, int n0, xb200_pic *const *l1, int n1,
+                             const XB200_CU *cus, int n_cu, const uint32_t *ctu_first, int n_ctu,
+                             const XB200_CU_EXT *ext, int n_ext, const uint32_t *entries, size_t n_entries, const uint32_t *chunk_first, size_t n_coef)
+{
+    if (!chunk_first) return XB200_ERR_INVALID_ARGUMENT;
+    return recon_frame_host(c, prm, cur, l0, n0, l1, n1, cus, n_cu, ctu_first, n_ctu, ext, n_ext, nullptr, n_coef, entries, n_entries, chunk_first);
 }
 
 // ---- in-loop filters / padding ----------------------------------------------------------------------------------------

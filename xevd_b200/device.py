@@ -199,6 +199,20 @@ class Context:
                                              cus.ctypes.data, len(cus), first.ctypes.data, len(first) - 1,
                                              ext.ctypes.data, len(ext), coef.ctypes.data, coef.size), "xb200_recon_frame")
 
+    def recon_frame_sparse(self, prm: abi.Params, cur: DevicePicture, refs_l0, refs_l1, cl: CuList, sparse=None):
+        """xb200_recon_frame with the coefficient stream in sparse form (entries, chunk_first) - see frame.sparse_coef"""
+        from .frame import sparse_coef
+        entries, chunk_first = sparse if sparse is not None else sparse_coef(cl.coef)
+        cus = np.ascontiguousarray(cl.cus)
+        first = np.ascontiguousarray(cl.ctu_first)
+        ext = np.ascontiguousarray(cl.ext)
+        cur.set_poc(prm.poc)
+        self._chk(self.lib.xb200_recon_frame_sparse(self.handle, C.byref(prm), cur.handle,
+                                                    _handles(refs_l0), len(refs_l0), _handles(refs_l1), len(refs_l1),
+                                                    cus.ctypes.data, len(cus), first.ctypes.data, len(first) - 1,
+                                                    ext.ctypes.data, len(ext), entries.ctypes.data, entries.size, chunk_first.ctypes.data, cl.coef.size),
+                  "xb200_recon_frame_sparse")
+
     # -- device-resident entry point (inputs already in HBM; pointers are raw device addresses) --------------
     def recon_frame_dev(self, prm: abi.Params, cur: DevicePicture, refs_l0, refs_l1, d_cus: int, n_cu: int,
                         d_first: int, n_ctu: int, d_ext: int, n_ext: int, d_coef: int, n_coef: int, has_intra: int = 0,

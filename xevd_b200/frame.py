@@ -114,6 +114,17 @@ def ats_inter_tu(ats: int, log2w: int, log2h: int):
     return log2w - sh, log2h, ((1 << log2w) - (1 << (log2w - sh))) if pos else 0, 0
 
 
+def sparse_coef(coef: np.ndarray, chunk: int = 4096):
+    """the sparse form of a dense coefficient stream that xb200_recon_frame_sparse takes: (entries, chunk_first) with
+    entries[i] = position inside its chunk | level << 16 and chunk k owning entries[chunk_first[k] : chunk_first[k + 1]]"""
+    coef = np.ascontiguousarray(coef, np.int16)
+    idx = np.flatnonzero(coef)
+    entries = ((idx & (chunk - 1)).astype(np.uint32) | (coef[idx].view(np.uint16).astype(np.uint32) << 16)).astype(np.uint32)
+    n_chunks = (coef.size + chunk - 1) // chunk
+    chunk_first = np.searchsorted(idx >> 12 if chunk == 4096 else idx // chunk, np.arange(n_chunks + 1), side="left").astype(np.uint32)
+    return entries, chunk_first
+
+
 def cu_coef_count(cu) -> int:
     """number of int16 coefficients a CU contributes to the stream (planes with cbf == 0 are absent)"""
     lw, lh = ats_inter_tu(int(cu["ats"]), int(cu["log2w"]), int(cu["log2h"]))[:2] if int(cu["mode"]) != 0 else (int(cu["log2w"]), int(cu["log2h"]))
