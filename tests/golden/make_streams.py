@@ -38,6 +38,10 @@ STREAMS = {
     "main_ctu32_200x120_8b": ("main", {}, dict(w=200, h=120, bd=8, frames=5, seed=24, types="IBB", log2_ctu=5, lps_scale=350)),
     "main_noaddb_nohtdf_256x144_10b": ("main", dict(addb=0, htdf=0), dict(w=256, h=144, bd=10, frames=5, seed=25, types="IBB", lps_scale=350)),
     "main_intra_eipd_ats_192x128_10b": ("main", {}, dict(w=192, h=128, bd=10, frames=4, seed=26, types="I", lps_scale=400)),
+    # ALF: one random adaptation parameter set per picture (5x5 / 7x7 luma, 1..25 filters, fixed-filter patterns, chroma), CTB flags
+    "main_alf_256x128_10b": ("main", dict(alf=1), dict(w=256, h=128, bd=10, frames=6, seed=41, types="IPB", lps_scale=350)),
+    "main_alf_416x240_8b": ("main", dict(alf=1), dict(w=416, h=240, bd=8, frames=5, seed=42, types="IBB", lps_scale=350)),
+    "main_alf_ctu128_384x256_10b": ("main", dict(alf=1), dict(w=384, h=256, bd=10, frames=4, seed=43, types="IPP", log2_ctu=7, lps_scale=350)),
     "main_nodmvr_noaffine_256x128_8b_cip": ("main", dict(dmvr=0, affine=0), dict(w=256, h=128, bd=8, frames=5, seed=27, types="IPP", lps_scale=350, constrained_intra=1)),
 }
 

@@ -130,7 +130,84 @@ def write_pps(constrained_intra=0, cu_qp_delta=0):
     return b.bytes()
 
 
-def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_v_off=0, tid=0):
+GOLOMB_IDX = {5: [0, 0, 1, 0, 0, 1], 7: [0, 0, 1, 0, 0, 1, 2, 1, 0, 0, 1, 2]}      # golombIdx5 / golombIdx7 (src_main/xevdm_alf.h:165-178)
+
+
+def alf_golomb(b, v, k, signed):
+    """the code xevdm_alfGolombDecode reads (src_main/xevdm_eco.c:2154-2187): unary prefix of zeros, a one, prefix + k suffix bits, sign"""
+    a = abs(v)
+    n = 0
+    while a >= ((1 << (n + 1)) - 1) << k:
+        n += 1
+    b.u(0, n); b.u(1, 1)
+    if n + k > 0:
+        b.u(a - (((1 << n) - 1) << k), n + k)
+    if signed and a:
+        b.u(1 if v > 0 else 0, 1)
+
+
+def write_alf_filter(b, rng, chroma, n_filters, size):
+    """xevdm_eco_alf_filter (src_main/xevdm_eco.c:2224-2320)"""
+    delta_flag = 0
+    flags = [1] * n_filters
+    if not chroma:
+        delta_flag = int(rng.integers(0, 2))
+        b.u(delta_flag, 1)                                     # alf_coefficients_delta_flag
+        if not delta_flag and n_filters > 1:
+            b.u(int(rng.integers(0, 2)), 1)                    # coeff_delta_pred_mode_flag
+    kmin = int(rng.integers(0, 3))
+    b.ue(kmin)                                                 # alf_luma_min_eg_order_minus1
+    k, ktab = kmin + 1, []
+    for _ in range(2 if size == 5 else 3):
+        inc = int(rng.integers(0, 2))
+        b.u(inc, 1)                                            # alf_eg_order_increase_flag
+        k += inc
+        ktab.append(k)
+    if not chroma and delta_flag:
+        flags = [int(rng.integers(0, 2)) for _ in range(n_filters)]
+        for fl in flags:
+            b.u(fl, 1)                                         # filter_coefficient_flag
+    n_coef = size * size // 4                                  # numCoeff - 1
+    for i in range(1 if chroma else n_filters):
+        if not flags[i]:
+            continue
+        for c in range(n_coef):
+            alf_golomb(b, int(rng.integers(-24, 25)), ktab[GOLOMB_IDX[size][c]], True)
+
+
+def write_aps_alf(aps_id, rng, tid=0):
+    """an ALF adaptation parameter set with random content (xevdm_eco_aps_gen / xevdm_eco_alf_aps_param, src_main/xevdm_eco.c:2081-2477)"""
+    b = nal_header(X.NUT_APS, tid)
+    b.u(aps_id, 5); b.u(0, 3)                                  # aps id, aps_type_id 0 = ALF
+    luma, chroma = 1, int(rng.integers(0, 2))
+    b.u(luma, 1); b.u(chroma, 1)                               # alf_luma_filter_signal_flag, alf_chroma_filter_signal_flag
+    n_filters = int(rng.choice([1, 2, 3, 8, 25]))
+    b.ue(n_filters - 1)                                        # alf_luma_num_filters_signalled_minus1
+    size = int(rng.choice([5, 7]))
+    b.u(1 if size == 7 else 0, 1)                              # alf_luma_type_flag
+    if n_filters > 1:
+        bits = int(n_filters - 1).bit_length()                 # xevd_tbl_log2[n - 1] + 1
+        for _ in range(25):
+            b.u(int(rng.integers(0, n_filters)), bits)         # alf_luma_coeff_delta_idx
+    pattern = int(rng.integers(0, 3))
+    alf_golomb(b, pattern, 0, False)                           # alf_luma_fixed_filter_usage_pattern
+    use = [1] * 25 if pattern == 1 else [0] * 25
+    if pattern == 2:
+        use = [int(rng.integers(0, 2)) for _ in range(25)]
+        for u_ in use:
+            b.u(u_, 1)
+    if pattern > 0:
+        for u_ in use:
+            if u_:
+                b.u(int(rng.integers(0, 16)), 4)               # alf_luma_fixed_filter_set_idx
+    write_alf_filter(b, rng, False, n_filters, size)
+    if chroma:
+        write_alf_filter(b, rng, True, 1, 5)
+    b.u(0, 1)                                                  # aps_extension_flag
+    return b.bytes(), chroma
+
+
+def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_v_off=0, tid=0, alf=None):
     b = nal_header(nut, tid)
     b.ue(0)                                # slice_pic_parameter_set_id
     b.ue(slice_type)
@@ -139,7 +216,14 @@ def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_
     if t["mmvd"] and slice_type in (X.ST_B, X.ST_P):
         b.u(1, 1)                          # mmvd_group_enable_flag
     if t["alf"]:
-        b.u(0, 1)                          # alf_on (no APS in these streams)
+        b.u(1 if alf else 0, 1)            # alf_on
+        if alf:
+            aps_id, ctb_on, chroma_idc = alf
+            b.u(aps_id, 5)                 # aps_id_y
+            b.u(ctb_on, 1)                 # is_ctb_alf_on: per-CTB enable flags follow in the slice data (CABAC)
+            b.u(chroma_idc, 2)             # alf_chroma_idc: bit 0 Cb, bit 1 Cr
+            if chroma_idc:
+                b.u(aps_id, 5)             # aps_id_ch
     if slice_type != X.ST_I:
         b.u(0, 1)                          # num_ref_idx_active_override_flag
         if t["admvp"]:
@@ -181,13 +265,19 @@ class Generator:
         L = self.lib.lib
         tail = bytes(max(1 << 17, w * h * 8))
         params = [write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(**pps_kw)]
-        hdrs = []
+        hdrs, aps = [], []
         for f in range(frames):
             idr = f == 0 or (gop and f % gop == 0)
             st = X.ST_I if (idr or len(types) == 1) else {"I": X.ST_I, "P": X.ST_P, "B": X.ST_B}[types[1 + (f - 1) % (len(types) - 1)]]
+            alf = None
+            aps.append(None)
+            if tools["alf"] and rng.random() < 0.85:             # most pictures filtered, each with its own parameter set
+                nal, has_chroma = write_aps_alf(f % 32, rng)
+                aps[-1] = nal
+                alf = (f % 32, int(rng.integers(0, 2)), int(rng.integers(0, 4)) if has_chroma else 0)
             hdrs.append(write_sh(tools, X.NUT_IDR if idr else X.NUT_NONIDR, st, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), deblock=deblock,
                                  alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)), qp_u_off=int(rng.integers(-3, 4)),
-                                 qp_v_off=int(rng.integers(-3, 4))))
+                                 qp_v_off=int(rng.integers(-3, 4)), alf=alf))
         accepted = []                      # per picture: (slice data bytes, bins)
 
         def run(upto, attempt):
@@ -203,6 +293,9 @@ class Generator:
                     if replay:
                         bins = accepted[f][1]
                         L.gen_replay(bins.ctypes.data, bins.size)
+                    if aps[f] is not None:
+                        ret, _ = d.decode(aps[f])
+                        assert ret >= 0, ("adaptation parameter set rejected", f, ret)
                     ret, stat = d.decode(hdrs[f] + tail)
                     assert ret >= 0, ("generator decode failed", f, ret)
                     why = C.create_string_buffer(200)
@@ -241,7 +334,12 @@ class Generator:
             else:
                 raise NonConforming(f"picture {f}: no conforming slice in {tries} draws (last: {why})")
         pics, _ = run(frames, None)
-        return params + [hdrs[f] + accepted[f][0] for f in range(frames)], pics
+        out = list(params)
+        for f in range(frames):
+            if aps[f] is not None:
+                out.append(aps[f])
+            out.append(hdrs[f] + accepted[f][0])
+        return out, pics
 
 
 def same_pictures(a, b):
