@@ -100,16 +100,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def recorded_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture"""
-    best = None
+def recorded_counters(workload):
+    """what only a profiler can count, from the newest committed ncu capture of the dominant kernel on this workload (profiles/rN/traffic_*.json):
+    DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), warp instructions per launch, issue-slot utilisation"""
+    best = {}
     for p in sorted((ROOT / "profiles").glob("r*/traffic_*.json")):
         try:
             d = json.loads(p.read_text())
         except (OSError, ValueError):
             continue
         if d.get("workload") == workload:
-            best = float(d["traffic_bytes_per_launch"])
+            best = dict(d, file=str(p.relative_to(ROOT)))
     return best
 
 
@@ -215,8 +216,12 @@ def cpu_baseline_sample(workload, seconds_budget=20.0):
         dt = time.perf_counter() - t0
         if dt > seconds_budget or n >= 50:
             break
-    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": f"{n} pictures of {workload} (recon + pad), 1 thread, {dt:.1f} s"}
+    out = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": f"{n} pictures of {workload} (recon + pad), 1 thread, {dt:.1f} s"}
+    if kind == "reference":       # the 8-thread figure next to the single-thread one (8 single-threaded instances, GOP-parallel)
+        from tools import bench_extra
+        out["value_8_threads"] = bench_extra.cpu_rate("cpu_picture", (prm, cl, refs, refs[::-1], None), 8, 3)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -346,6 +351,7 @@ def run_ours(args):
     alg = float(np.mean([algorithmic_bytes(w, h, s["cl"]) for s in slots]))       # band mode: this rank's band
     peak, peak_src = measured_peak()
     achieved = alg / (kern_ms * 1e-3) / 1e9
+    counters = recorded_counters(args.workload)
 
     # ---- e2e: host buffers through the C ABI, H2D + D2H inside the timed region -------------------------------------------
     n_ctx = 1 if band else int(os.environ.get("XB200_BENCH_CONTEXTS", "3"))          # band mode: the exchange orders every picture on one stream
@@ -515,7 +521,15 @@ def run_ours(args):
                        "l2": f"{F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per rotation per GPU, {P} rotations per step; the slots share "
                              f"{len(frames)} distinct CU arrays / coefficient streams, every slot holds its own device copy"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(args.workload), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src},
+                         "traffic": counters.get("traffic_bytes_per_launch"), "kernel": "k_recon_inter_v2", "kernel_ms": kern_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
+                         # the kernel is integer-issue bound, so the instruction rate belongs next to the bandwidth fraction.  Instructions per
+                         # launch and issue utilisation come from the committed ncu capture (a profiler counter), the rate uses the time measured here
+                         "integer_issue": None if not counters.get("warp_instructions_per_launch") else {
+                             "warp_instructions_per_launch": counters["warp_instructions_per_launch"],
+                             "lane_instructions_per_sample": round(32.0 * counters["warp_instructions_per_launch"] / (w * h * 1.5), 1),
+                             "achieved_warp_inst_per_s": counters["warp_instructions_per_launch"] / (kern_ms * 1e-3),
+                             "peak_warp_inst_per_s": 148 * 4 * 1.965e9, "issue_util_ncu": counters.get("issue_active_pct", 0) / 100.0,
+                             "source": counters.get("file")}},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "contexts": n_ctx, "checksum": checksum,
                     "call": "xb200_recon_frame_sparse (coefficient stream as (position, level) entries, expanded on the device) + xb200_pad + xb200_pic_download",

@@ -12,6 +12,13 @@ import os
 from typing import Any, List, Sequence
 
 
+import contextlib
+
+
+def _null():
+    return contextlib.nullcontext()
+
+
 def env_rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -54,6 +61,9 @@ class BandExchange:
         self.buf = torch.empty(self.chunk * world, dtype=torch.uint8, device=device)
 
     def exchange(self, pic):
+        """pack -> all-gather -> unpack, all in the order of the CONTEXT's stream: the collective is issued with that stream as torch's
+        current stream, whatever the caller's current stream is (pack / unpack are launched on the context stream by the library)"""
+        import torch
         import torch.distributed as dist
         base = self.buf.data_ptr()
         y0, rows = self.rows[self.rank]
@@ -61,7 +71,9 @@ class BandExchange:
             self.ctx.band_pack(pic, y0, rows, base + self.rank * self.chunk)
         if self.world > 1:
             mine = self.buf[self.rank * self.chunk:(self.rank + 1) * self.chunk]
-            dist.all_gather_into_tensor(self.buf, mine)                 # in place: rank r's chunk is slot r of the output
+            st = self.ctx.stream
+            with torch.cuda.stream(torch.cuda.ExternalStream(st)) if (st and self.buf.is_cuda) else _null():
+                dist.all_gather_into_tensor(self.buf, mine)             # in place: rank r's chunk is slot r of the output
         for r, (yr, nr) in enumerate(self.rows):
             if r != self.rank and nr > 0:
                 self.ctx.band_unpack(pic, yr, nr, base + r * self.chunk)
