@@ -313,6 +313,21 @@ __device__ __forceinline__ void col_pass2(const int *__restrict__ src, const int
     for (int k = 0; k < N; k++) *(int *)(dst + k * rs) = pack_sat16(oa[k] >> sh2, ob[k] >> sh2);
 }
 
+// one past the last coefficient of a CU inside the stream (int16 units): its coded plane blocks, each padded to 8 entries; an ats_inter CU
+// carries only its sub-block transform unit (a full-CU figure here once made the CTU's bulk copy read past the end of the stream)
+__device__ __forceinline__ int cu_coef_end(const XbFrameArgs &a, const XB200_CU &cu)
+{
+    int tlw = cu.log2w, tlh = cu.log2h;
+    const int aidx = a.ats ? ats_inter_idx(cu) : 0;
+    if (aidx) { int xo, yo; ats_inter_tu(cu, aidx, tlw, tlh, xo, yo); }
+    const int n = 1 << (tlw + tlh);
+    int end = cu.coef_off;
+    if (cu.cbf & 0x00f) end += (n + 7) & ~7;
+    if (cu.cbf & 0x0f0) end += ((n >> 2) + 7) & ~7;
+    if (cu.cbf & 0xf00) end += ((n >> 2) + 7) & ~7;
+    return end;
+}
+
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
 // local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
 template <bool BI, bool PEER = false, bool IQT = false, bool DISP = false>
@@ -354,12 +369,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             XB200_CU c1;
             ((int4 *)&c1)[0] = l0; ((int4 *)&c1)[1] = l1;
             coef_base = f0.w;                                   // XB200_CU.coef_off is the last word of the record
-            const int n1 = 1 << (c1.log2w + c1.log2h);
-            int end = c1.coef_off;
-            if (c1.cbf & 0x00f) end += (n1 + 7) & ~7;
-            if (c1.cbf & 0x0f0) end += ((n1 >> 2) + 7) & ~7;
-            if (c1.cbf & 0xf00) end += ((n1 >> 2) + 7) & ~7;
-            coef_bytes = 2 * (end - coef_base);
+            coef_bytes = min(2 * (cu_coef_end(a, c1) - coef_base), kCoefStageBytes);     // (the clamp only matters for a malformed device-resident list)
             if (coef_bytes > 0) {
                 mbar_expect_tx(mbar_coef, (uint32_t)coef_bytes);
                 bulk_load(smem + L.coef, a.coef + coef_base, (uint32_t)coef_bytes, mbar_coef);
@@ -391,12 +401,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     if (ncu > 0) {
         const XB200_CU c0 = s_cu[0], c1 = s_cu[ncu - 1];
         coef_base = c0.coef_off;
-        const int n1 = 1 << (c1.log2w + c1.log2h);
-        int end = c1.coef_off;
-        if (c1.cbf & 0x00f) end += (n1 + 7) & ~7;
-        if (c1.cbf & 0x0f0) end += ((n1 >> 2) + 7) & ~7;
-        if (c1.cbf & 0xf00) end += ((n1 >> 2) + 7) & ~7;
-        coef_bytes = 2 * (end - coef_base);
+        coef_bytes = min(2 * (cu_coef_end(a, c1) - coef_base), kCoefStageBytes);
     }
 
     // ---- per-CU counts -> exclusive prefix sums: warp q scans quantity q -------------------------------------------------------
