@@ -42,6 +42,10 @@ STREAMS = {
     "main_alf_256x128_10b": ("main", dict(alf=1), dict(w=256, h=128, bd=10, frames=6, seed=41, types="IPB", lps_scale=350)),
     "main_alf_416x240_8b": ("main", dict(alf=1), dict(w=416, h=240, bd=8, frames=5, seed=42, types="IBB", lps_scale=350)),
     "main_alf_ctu128_384x256_10b": ("main", dict(alf=1), dict(w=384, h=256, bd=10, frames=4, seed=43, types="IPP", log2_ctu=7, lps_scale=350)),
+    # IBC: block vectors chosen by the generator among the decoded, in-picture positions at or left of / above the CU's CTU
+    "main_ibc_256x128_10b": ("main", dict(ibc=1), dict(w=256, h=128, bd=10, frames=5, seed=52, types="IPB", lps_scale=350)),
+    "main_ibc_alf_320x192_8b": ("main", dict(ibc=1, alf=1), dict(w=320, h=192, bd=8, frames=5, seed=53, types="IBB", lps_scale=350)),
+    "main_ibc_i_ctu128_256x256_10b": ("main", dict(ibc=1), dict(w=256, h=256, bd=10, frames=3, seed=54, types="I", log2_ctu=7, lps_scale=400)),
     "main_nodmvr_noaffine_256x128_8b_cip": ("main", dict(dmvr=0, affine=0), dict(w=256, h=128, bd=8, frames=5, seed=27, types="IPP", lps_scale=350, constrained_intra=1)),
 }
 

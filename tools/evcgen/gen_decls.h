@@ -9,3 +9,5 @@ int gen_force_next(int bin);
 u32 gen_merge_idx(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, u32 num_ctx, u32 max_num, u32 limit);
 u32 gen_unary_ep(XEVD_BSR *bs, XEVD_SBAC *sbac, u32 max_val, u32 max_symbol);
 int gen_last_bound(int pos, int width, int height);
+int gen_ibc_pick(XEVD_CTX *ctx, XEVD_CORE *core);
+int gen_ibc_mvd(XEVD_BSR *bs, XEVD_SBAC *sbac, s16 mvd[MV_D]);

@@ -143,6 +143,80 @@ u32 xevd_sbac_decode_bin(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model)
  * e.g. the split flag of a Baseline coding block that crosses the picture boundary, src_main/xevdm.c:1713) */
 int gen_force_next(int bin) { g_force = bin; return 0; }
 
+/* ---- intra block copy -------------------------------------------------------------------------------------------------------
+ * The block vector is coded like a motion vector difference (xevdm_eco.c:1796) and nothing in the syntax keeps it inside the part of the
+ * picture that is already decoded; the decoder copies from wherever it points (xevdm_IBC_mc).  An encoder only emits vectors whose source
+ * block is decoded, inside the picture, and not right of / below the current CTU.  The generator therefore CHOOSES the vector: before the
+ * ibc_flag bin it looks for such a vector (gen_ibc_pick; none found -> the flag is forced to 0), and the vector is then written through
+ * the decoder's own mvd syntax with every bin forced (gen_ibc_mvd). */
+u32 sbac_decode_bin_ep(XEVD_BSR *bs, XEVD_SBAC *sbac);
+static int g_ibc_bv[2];
+int gen_ibc_pick(XEVD_CTX *ctx, XEVD_CORE *core)
+{
+    const int x = core->x_scu << MIN_CU_LOG2, y = core->y_scu << MIN_CU_LOG2, w = 1 << core->log2_cuw, h = 1 << core->log2_cuh;
+    const int ctu = 1 << ctx->log2_max_cuwh, cx = x & ~(ctu - 1), cy = y & ~(ctu - 1);
+    for (int t = 0; t < 24; t++) {
+        const uint32_t r = rnd32();
+        int dx, dy;
+        switch (r & 3) {
+        case 0: dx = -(w + (int)((r >> 2) % 48)); dy = (int)((r >> 10) % 17) - 8; break;
+        case 1: dy = -(h + (int)((r >> 2) % 40)); dx = (int)((r >> 10) % 33) - 16; break;
+        case 2: dx = -(w + (int)((r >> 2) % 24)); dy = -(int)((r >> 10) % 24); break;
+        default: dx = -(int)((r >> 2) % 130); dy = -(h + (int)((r >> 12) % 8)); break;
+        }
+        const int rx = x + dx, ry = y + dy;
+        if (rx < 0 || ry < 0 || rx + w > ctx->w || ry + h > ctx->h || rx + w > cx + ctu || ry + h > cy + ctu) continue;
+        int ok = 1;
+        for (int sy = ry >> MIN_CU_LOG2; sy <= (ry + h - 1) >> MIN_CU_LOG2 && ok; sy++)
+            for (int sx = rx >> MIN_CU_LOG2; sx <= (rx + w - 1) >> MIN_CU_LOG2; sx++)
+                if (!ctx->cod_eco[sy * ctx->w_scu + sx]) { ok = 0; break; }
+        if (!ok) continue;
+        g_ibc_bv[0] = dx; g_ibc_bv[1] = dy;
+        return 1;
+    }
+    g_force = 0;                          /* nowhere to copy from: this CU is not an IBC CU */
+    return 0;
+}
+/* xevd_eco_abs_mvd (src_base/xevd_eco.c:520-555) with every bin forced so that it reads `a` */
+static u32 ibc_abs(XEVD_BSR *bs, XEVD_SBAC *sbac, SBAC_CTX_MODEL *model, int a)
+{
+    u32 val = 0, code, len;
+    int tl = 0;
+    while (((1 << (tl + 1)) - 1) <= a) tl++;
+    g_force = a == 0 ? 1 : 0;
+    code = xevd_sbac_decode_bin(bs, sbac, model);
+    if (code == 0) {
+        len = 0;
+        while (!(code & 1)) {
+            const int want = ((int)len + 1 == tl) ? 1 : 0;
+            if (len == 0) { g_force = want; code = xevd_sbac_decode_bin(bs, sbac, model); }
+            else { g_force_ep = want; code = sbac_decode_bin_ep(bs, sbac); }
+            len++;
+        }
+        val = (1u << len) - 1;
+        const int suffix = a - ((1 << tl) - 1);
+        while (len != 0) {
+            g_force_ep = (suffix >> (len - 1)) & 1;
+            code = sbac_decode_bin_ep(bs, sbac);
+            val += code << (--len);
+        }
+    }
+    return val;
+}
+int gen_ibc_mvd(XEVD_BSR *bs, XEVD_SBAC *sbac, s16 mvd[MV_D])
+{
+    for (int c = 0; c < 2; c++) {
+        const int t = g_ibc_bv[c];
+        const s16 v = (s16)ibc_abs(bs, sbac, sbac->ctx.mvd, t < 0 ? -t : t);
+        if (v == 0) mvd[c] = 0;
+        else {
+            g_force_ep = t < 0 ? 1 : 0;
+            mvd[c] = sbac_decode_bin_ep(bs, sbac) ? -v : v;
+        }
+    }
+    return XEVD_OK;
+}
+
 /* ADCC last-position prefixes in a block with a 64 dimension: stop at 7 (see tools/evcgen/Makefile, LAST_BOUND) */
 int gen_last_bound(int pos, int width, int height) { if ((width == 64 || height == 64) && pos >= 7) g_force = 0; return 0; }
 
