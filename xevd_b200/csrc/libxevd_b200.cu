@@ -62,6 +62,10 @@ struct xb200_ctx {
     pel *alf_copy;               // pre-ALF copy of the picture being filtered
     size_t alf_cap;
     uint8_t *alf_flags_pinned, *alf_flags_dev;
+    void *alf_tab_dev, *alf_tab_pinned;      // ALF: the 100 permuted luma filters of the current APS
+    cudaEvent_t alf_tab_done;
+    bool alf_tab_valid;
+    int16_t alf_tab_coef[25][13];            // the coefficients the device table was built from
     int alf_flags_cap;
     cudaEvent_t alf_flags_done;
     unsigned char *out_buf;      // output path: packed planes produced by k_output, then copied to the caller
@@ -213,6 +217,9 @@ void xb200_destroy(xb200_ctx *c)
     if (c->alf_copy) cudaFree(c->alf_copy);
     if (c->alf_flags_pinned) cudaFreeHost(c->alf_flags_pinned);
     if (c->alf_flags_dev) cudaFree(c->alf_flags_dev);
+    if (c->alf_tab_dev) cudaFree(c->alf_tab_dev);
+    if (c->alf_tab_pinned) cudaFreeHost(c->alf_tab_pinned);
+    if (c->alf_tab_done) cudaEventDestroy(c->alf_tab_done);
     if (c->alf_flags_done) cudaEventDestroy(c->alf_flags_done);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -805,23 +812,50 @@ int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_A
     if (prm->chroma_format_idc != 1) return XB200_ERR_UNSUPPORTED;
     if (!alf->enable[0] && !alf->enable[1] && !alf->enable[2]) return XB200_OK;   // alf_process :1172
     cudaSetDevice(c->device);
-    const size_t ny = (size_t)p->s_l * p->h, nc = (size_t)p->s_c * p->h_c;
-    if (c->alf_cap < ny + 2 * nc) {
+    // the pre-ALF copy has the layout of the picture's own buffer (padded planes back to back), so plane pointers translate by one offset
+    const size_t n_copy = p->luma_elems + 2 * p->chroma_elems;
+    if (c->alf_cap < n_copy) {
         CK(c, cudaStreamSynchronize(c->stream));
         if (c->alf_copy) cudaFree(c->alf_copy);
         c->alf_copy = nullptr; c->alf_cap = 0;
-        CK(c, cudaMalloc(&c->alf_copy, (ny + 2 * nc) * sizeof(pel)));
-        c->alf_cap = ny + 2 * nc;
+        CK(c, cudaMalloc(&c->alf_copy, n_copy * sizeof(pel)));
+        c->alf_cap = n_copy;
     }
     xb::AlfArgs a;
-    a.sy = c->alf_copy; a.su = c->alf_copy + ny; a.sv = c->alf_copy + ny + nc;
+    a.sy = c->alf_copy + (p->y - p->buf); a.su = c->alf_copy + (p->u - p->buf); a.sv = c->alf_copy + (p->v - p->buf);
     a.dy = p->y; a.du = p->u; a.dv = p->v;
     a.s_l = p->s_l; a.s_c = p->s_c; a.w = p->w; a.h = p->h; a.log2_ctu = prm->log2_ctu; a.bd = prm->bit_depth_luma;
     a.w_ctu = (p->w + (1 << prm->log2_ctu) - 1) >> prm->log2_ctu;
     a.ctb_flag = nullptr;
-    memcpy(a.coef_l, alf->coef_luma, sizeof(a.coef_l));
     memcpy(a.coef_c, alf->coef_chroma, sizeof(a.coef_c));
     memcpy(a.enable, alf->enable, 3);
+    if (alf->enable[0]) {
+        // the 100 luma filters a 4x4 block can select: 25 classes x 4 transposes, coefficients already permuted, 16 int16 each; the table
+        // lives on the device and is uploaded again only when the coefficients change (a new APS)
+        if (!c->alf_tab_dev) {
+            CK(c, cudaMalloc(&c->alf_tab_dev, xb::kAlfTabBytes));
+            CK(c, cudaMallocHost(&c->alf_tab_pinned, xb::kAlfTabBytes));
+            CK(c, cudaEventCreateWithFlags(&c->alf_tab_done, cudaEventDisableTiming));
+            c->alf_tab_valid = false;
+        }
+        if (!c->alf_tab_valid || memcmp(c->alf_tab_coef, alf->coef_luma, sizeof(c->alf_tab_coef)) != 0) {
+            static const uint8_t perm[4][13] = {{0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12}, {9, 4, 10, 8, 1, 5, 11, 7, 3, 0, 2, 6, 12},
+                                                {0, 3, 2, 1, 8, 7, 6, 5, 4, 9, 10, 11, 12}, {9, 8, 10, 4, 3, 7, 11, 5, 1, 0, 2, 6, 12}};
+            if (c->alf_tab_valid) CK(c, cudaEventSynchronize(c->alf_tab_done));      // the previous upload has left the pinned buffer
+            int16_t *tab = (int16_t *)c->alf_tab_pinned;
+            for (int cls = 0; cls < 25; cls++)
+                for (int tr = 0; tr < 4; tr++) {
+                    int16_t *f = tab + (cls * 4 + tr) * 16;
+                    for (int i = 0; i < 13; i++) f[i] = alf->coef_luma[cls][perm[tr][i]];
+                    f[13] = f[14] = f[15] = 0;
+                }
+            CK(c, cudaMemcpyAsync(c->alf_tab_dev, c->alf_tab_pinned, xb::kAlfTabBytes, cudaMemcpyHostToDevice, c->stream));
+            CK(c, cudaEventRecord(c->alf_tab_done, c->stream));
+            memcpy(c->alf_tab_coef, alf->coef_luma, sizeof(c->alf_tab_coef));
+            c->alf_tab_valid = true;
+        }
+        a.ftab = (const int4 *)c->alf_tab_dev;
+    }
     if (ctb_flag_luma && alf->enable[0]) {
         const int n = a.w_ctu * ((p->h + (1 << prm->log2_ctu) - 1) >> prm->log2_ctu);
         if (c->alf_flags_cap < n) {
@@ -841,9 +875,17 @@ int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_A
         CK(c, cudaEventRecord(c->alf_flags_done, c->stream));
         a.ctb_flag = c->alf_flags_dev;
     }
-    if (alf->enable[0]) CK(c, cudaMemcpy2DAsync((void *)a.sy, p->s_l * 2, p->y, p->s_l * 2, p->w * 2, p->h, cudaMemcpyDeviceToDevice, c->stream));
-    if (alf->enable[1]) CK(c, cudaMemcpy2DAsync((void *)a.su, p->s_c * 2, p->u, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToDevice, c->stream));
-    if (alf->enable[2]) CK(c, cudaMemcpy2DAsync((void *)a.sv, p->s_c * 2, p->v, p->s_c * 2, p->w_c * 2, p->h_c, cudaMemcpyDeviceToDevice, c->stream));
+    {   // sample rows of the enabled planes, whole rows (a row with its padding is a multiple of 16 bytes and the rows of a plane are contiguous)
+        xb::AlfCopyArgs ca;
+        const pel *rows[3] = {p->y - p->pad_l, p->u - p->pad_c, p->v - p->pad_c};
+        for (int pl = 0; pl < 3; pl++) {
+            ca.src[pl] = (const int4 *)rows[pl];
+            ca.dst[pl] = (int4 *)(c->alf_copy + (rows[pl] - p->buf));
+            ca.n[pl] = alf->enable[pl] ? (unsigned)((pl ? (size_t)p->s_c * p->h_c : (size_t)p->s_l * p->h) * sizeof(pel) / 16) : 0u;
+        }
+        xb::k_alf_copy<<<c->sm_count * 8, 256, 0, c->stream>>>(ca);
+        c->launches++;
+    }
     const dim3 grid((p->w + xb::kAlfT - 1) / xb::kAlfT, (p->h + xb::kAlfT - 1) / xb::kAlfT);
     xb::k_alf<<<grid, 256, 0, c->stream>>>(a);
     c->launches++;
