@@ -29,9 +29,9 @@
  *   - PICBUF_ALLOCATOR (ctx->pa.fn_alloc = xevdm_picbuf_alloc, :457): every XEVD_PIC gets a device twin (xb200_pic).
  *
  * There is no CPU fallback: xevd_create fails when no CUDA device is usable.
- * Limits (refused loudly with XEVD_ERR_UNSUPPORTED_COLORSPACE / XEVD_ERR_UNSUPPORTED): chroma formats other than 4:2:0; more than
- * one tile per picture (availability and CTU order are handled, but the device filters do not implement
- * loop_filter_across_tiles_enabled_flag == 0 margins).
+ * Limit (refused loudly with XEVD_ERR_UNSUPPORTED_COLORSPACE): chroma formats other than 4:2:0.
+ * Pictures of several tiles: the chunks of a slice are re-sorted into raster order and the tile grid goes to the loop filters
+ * (xb200_set_tiles).
  */
 #include <stddef.h>
 #include <stdio.h>
@@ -480,9 +480,15 @@ int glue_dec_slice(XEVD_CTX *ctx, XEVD_CORE *core)
     GLUE *g = glue_of(ctx);
     if (!g) return XEVD_ERR_UNEXPECTED;
     if (ctx->sps->chroma_format_idc != 1) return XEVD_ERR_UNSUPPORTED_COLORSPACE;
-    if (ctx->w_tile * ctx->h_tile > 1) {
-        fprintf(stderr, "[xevd-b200] %d tiles per picture: not supported by the device filters\n", ctx->w_tile * ctx->h_tile);
-        return XEVD_ERR_UNSUPPORTED;
+    {   /* the tile grid (set_tile_info, src_main/xevdm.c:2162): the loop filters need it, reconstruction does not */
+        uint16_t col_bd[XB200_MAX_TILE_COLS + 1] = {0}, row_bd[XB200_MAX_TILE_ROWS + 1] = {0};
+        if (ctx->w_tile > XB200_MAX_TILE_COLS || ctx->h_tile > XB200_MAX_TILE_ROWS) return XEVD_ERR_UNSUPPORTED;
+        for (int i = 0; i < ctx->w_tile; i++) col_bd[i + 1] = (uint16_t)(col_bd[i] + ctx->tile[i].w_ctb);
+        for (int j = 0; j < ctx->h_tile; j++) row_bd[j + 1] = (uint16_t)(row_bd[j] + ctx->tile[j * ctx->w_tile].h_ctb);
+        if (xb200_set_tiles(g->dev, ctx->w_tile, col_bd, ctx->h_tile, row_bd, ctx->pps.loop_filter_across_tiles_enabled_flag) < 0) {
+            dev_fail(g, XEVD_ERR, "xb200_set_tiles");
+            return g->err;
+        }
     }
     if (g->maps_pending) { xb200_sync(g->dev); g->maps_pending = 0; }     /* refined vectors of the previous picture are in place */
     g->n_cu = 0; g->n_ext = 0; g->n_coef = 0; g->n_chunk = 0; g->last_cu = -1;

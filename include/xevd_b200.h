@@ -283,6 +283,18 @@ int  xb200_deblock(xb200_ctx *ctx, const XB200_PARAMS *prm, xb200_pic *cur,
 /* chroma QP mapping used by deblocking: what xevd_qp_chroma_dynamic[0..1][0..57] holds for the sequence
  * (src_base/xevd_tbl.c:359-425); the context starts with the Baseline default table                         */
 int  xb200_set_chroma_qp_table(xb200_ctx *ctx, const int32_t *tbl /* [2][58] */);
+/* Tile grid of the pictures that follow (PPS; set_tile_info, src_main/xevdm.c:2162-2327): n_cols + 1 column and n_rows + 1 row
+ * boundaries in CTUs (first 0, last = the picture's size in CTUs) and pps.loop_filter_across_tiles_enabled_flag.  Reconstruction
+ * needs nothing of this (availability arrives per CU, CTUs in raster order); the loop filters do:
+ *   deblocking  - an edge between two tiles is filtered only with the flag set (xevdm_df.c:142,233,877,1088)
+ *   ALF         - the 7x7 / 5x5 windows never read another tile: without the flag they mirror at the tile border like at the
+ *                 picture border, with it they replicate the tile's border samples and mirror only at the picture's left and top
+ *                 (alf_process_tile, xevdm_alf.c:989-1046: tile_boundary_check against the tile or against the picture, windows
+ *                 taken from the per-tile extended copy)
+ * n_cols == n_rows == 1 (the state of a new context) = one tile; at most 20 columns and 22 rows (xevd_def.h MAX_NUM_TILES_*). */
+#define XB200_MAX_TILE_COLS 20
+#define XB200_MAX_TILE_ROWS 22
+int  xb200_set_tiles(xb200_ctx *ctx, int n_cols, const uint16_t *col_bd, int n_rows, const uint16_t *row_bd, int loop_filter_across_tiles);
 /* test support: overwrite the per-SCU maps of a device picture from host arrays (any pointer may be NULL)   */
 int  xb200_pic_upload_maps(xb200_ctx *ctx, xb200_pic *pic, const int16_t *map_mv, const int8_t *map_refi,
                            const uint32_t *map_scu, const uint8_t *map_edge);

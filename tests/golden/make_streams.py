@@ -46,6 +46,24 @@ STREAMS = {
     "main_ibc_256x128_10b": ("main", dict(ibc=1), dict(w=256, h=128, bd=10, frames=5, seed=52, types="IPB", lps_scale=350)),
     "main_ibc_alf_320x192_8b": ("main", dict(ibc=1, alf=1), dict(w=320, h=192, bd=8, frames=5, seed=53, types="IBB", lps_scale=350)),
     "main_ibc_i_ctu128_256x256_10b": ("main", dict(ibc=1), dict(w=256, h=256, bd=10, frames=3, seed=54, types="I", log2_ctu=7, lps_scale=400)),
+    # tiles: every tile is its own arithmetic code word, entry points in the slice header; one slice per picture.  across = the PPS's
+    # loop_filter_across_tiles_enabled_flag (deblocking of tile-boundary edges, ALF margins at tile borders)
+    "base_tiles2x2_320x192_8b": ("baseline", {}, dict(w=320, h=192, bd=8, frames=6, seed=61, types="IPB", tiles=dict(cols=2, rows=2, across=1))),
+    "base_tiles3x1_noacross_416x240_10b": ("baseline", {}, dict(w=416, h=240, bd=10, frames=6, seed=62, types="IPBB", tiles=dict(cols=3, rows=1, across=0))),
+    "main_tiles2x2_alf_noacross_384x256_10b": ("main", dict(alf=1), dict(w=384, h=256, bd=10, frames=5, seed=63, types="IPB", lps_scale=350,
+                                                                     tiles=dict(cols=2, rows=2, across=0))),
+    "main_tiles2x2_alf_across_320x192_8b": ("main", dict(alf=1), dict(w=320, h=192, bd=8, frames=5, seed=64, types="IBB", lps_scale=350,
+                                                                   tiles=dict(cols=2, rows=2, across=1))),
+    "main_tiles_explicit_ctu32_alf_256x160_10b": ("main", dict(alf=1), dict(w=256, h=160, bd=10, frames=5, seed=65, types="IPP", log2_ctu=5, lps_scale=350,
+                                                                         tiles=dict(cols=3, rows=2, col_w=[2, 5, 1], row_h=[4, 1], across=0))),
+    # several slices per picture, each a rectangle of tiles.  All pictures are IDR: without sps_pocs the reference derives a new POC for
+    # every non-IDR slice NAL (src_main/xevdm.c:3037-3041), so it cannot decode a multi-slice P / B picture of such a sequence itself
+    "base_slices2_tiles2x2_idr_320x192_8b": ("baseline", {}, dict(w=320, h=192, bd=8, frames=4, seed=66, types="I", gop=1,
+                                                                   tiles=dict(cols=2, rows=2, across=0), slices=[(0, 1), (2, 3)])),
+    "main_slices2_tiles3x2_alf_idr_384x256_10b": ("main", dict(alf=1), dict(w=384, h=256, bd=10, frames=4, seed=67, types="I", gop=1, lps_scale=350,
+                                                                         tiles=dict(cols=3, rows=2, across=1), slices=[(0, 3), (1, 5)])),
+    "main_slices3_tiles2x2_alf_idr_256x256_8b": ("main", dict(alf=1), dict(w=256, h=256, bd=8, frames=3, seed=68, types="I", gop=1, lps_scale=350,
+                                                                        tiles=dict(cols=2, rows=2, across=0), slices=[(0, 0), (1, 1), (2, 3)])),
     "main_nodmvr_noaffine_256x128_8b_cip": ("main", dict(dmvr=0, affine=0), dict(w=256, h=128, bd=8, frames=5, seed=27, types="IPP", lps_scale=350, constrained_intra=1)),
 }
 

@@ -145,6 +145,50 @@ def test_alf(ctx, oracle, w, h, bd, log2_ctu, enable):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
+@pytest.mark.parametrize("w,h,bd,log2_ctu,col_bd,row_bd", [(256, 128, 10, 6, [0, 2, 4], [0, 2]), (320, 192, 8, 5, [0, 3, 4, 10], [0, 2, 6]), (384, 256, 10, 7, [0, 1, 3], [0, 1, 2])])
+def test_alf_tiles_without_filtering_across(ctx, oracle, w, h, bd, log2_ctu, col_bd, row_bd):
+    """loop_filter_across_tiles_enabled_flag == 0: the ALF windows mirror at a tile border exactly as at the picture border
+    (alf_process_tile, xevdm_alf.c:989-1046), so every tile must come out as if it were a picture of its own (the oracle on the cut-out)"""
+    rng = np.random.default_rng(w + h + bd)
+    p = HostPicture.random(w, h, bd, rng)
+    prm = abi.make_params(w, h, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+    alf = synth.make_alf_params(rng, (1, 1, 1))
+    ctu = 1 << log2_ctu
+    w_ctu, h_ctu = (w + ctu - 1) >> log2_ctu, (h + ctu - 1) >> log2_ctu
+    flags = (rng.random(w_ctu * h_ctu) < 0.8).astype(np.uint8)
+    d = ctx.pic_alloc(w, h).upload(p, padded=False)
+    ctx.set_tiles(col_bd, row_bd, across=False)
+    try:
+        ctx.alf(prm, d, alf, flags)
+        got = d.download()
+    finally:
+        ctx.set_tiles()
+        d.free()
+    for tr in range(len(row_bd) - 1):
+        for tc in range(len(col_bd) - 1):
+            x0, x1, y0, y1 = col_bd[tc] * ctu, min(col_bd[tc + 1] * ctu, w), row_bd[tr] * ctu, min(row_bd[tr + 1] * ctu, h)
+            sub = HostPicture(x1 - x0, y1 - y0, 0)
+            sub.y[...] = p.y[y0:y1, x0:x1]; sub.u[...] = p.u[y0 // 2:y1 // 2, x0 // 2:x1 // 2]; sub.v[...] = p.v[y0 // 2:y1 // 2, x0 // 2:x1 // 2]
+            sprm = abi.make_params(x1 - x0, y1 - y0, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+            sflags = np.ascontiguousarray(flags.reshape(h_ctu, w_ctu)[row_bd[tr]:row_bd[tr + 1], col_bd[tc]:col_bd[tc + 1]]).ravel()
+            want = oracle.alf_frame(sprm, sub, alf, sflags)
+            for a, b, sh, name in ((got.y, want.y, 0, "y"), (got.u, want.u, 1, "u"), (got.v, want.v, 1, "v")):
+                cut = a[y0 >> sh:y1 >> sh, x0 >> sh:x1 >> sh]
+                assert np.array_equal(cut, b), (tr, tc, name, int((cut != b).sum()), np.argwhere(cut != b)[:4].tolist())
+
+
+def test_set_tiles_refuses_bad_grids(ctx):
+    L, H = ctx.lib, ctx.handle
+    ok = np.array([0, 2, 4], np.uint16)
+    assert L.xb200_set_tiles(H, 2, ok.ctypes.data, 1, np.array([0, 9], np.uint16).ctypes.data, 0) == 0
+    for cols in ([1, 2, 4], [0, 2, 2], [0, 3, 2]):
+        bad = np.array(cols, np.uint16)
+        assert L.xb200_set_tiles(H, 2, bad.ctypes.data, 1, np.array([0, 9], np.uint16).ctypes.data, 0) < 0
+    assert L.xb200_set_tiles(H, 21, ok.ctypes.data, 1, ok.ctypes.data, 0) < 0
+    assert L.xb200_set_tiles(H, 0, ok.ctypes.data, 1, ok.ctypes.data, 0) < 0
+    ctx.set_tiles()
+
+
 @pytest.mark.parametrize("kw,bd,addb", [({}, 10, 1), (dict(log2_ctu=7), 10, 1), (dict(log2_ctu=5), 8, 1), ({}, 10, 0), (dict(log2_ctu=7), 8, 0)])
 def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
     """both deblocking filters on Main-profile partitions (non-square CUs, ternary-split edges, 128-sample CUs, ats_inter CUs)"""

@@ -112,14 +112,30 @@ def write_sps(t, w, h, bd, max_refs=2, log2_ctu=6):
     return b.bytes()
 
 
-def write_pps(constrained_intra=0, cu_qp_delta=0):
+def write_pps(constrained_intra=0, cu_qp_delta=0, tiles=None):
+    """tiles: None (one tile) or dict(cols, rows, col_w=[...] / row_h=[...] in CTUs for explicit spacing, across=0/1)
+    (xevdm_eco_pps, src_main/xevdm_eco.c:2019-2052)"""
     b = nal_header(X.NUT_PPS)
     b.ue(0); b.ue(0)                       # pps id, sps id
     b.ue(0); b.ue(0)                       # num_ref_idx_default_active_minus1[0..1]
     b.ue(0)                                # additional_lt_poc_lsb_len
     b.u(0, 1)                              # rpl1_idx_present_flag
-    b.u(1, 1)                              # single_tile_in_pic_flag
-    b.ue(0)                                # tile_id_len_minus1
+    if tiles is None:
+        b.u(1, 1)                          # single_tile_in_pic_flag
+        b.ue(0)                            # tile_id_len_minus1
+    else:
+        b.u(0, 1)
+        b.ue(tiles["cols"] - 1); b.ue(tiles["rows"] - 1)
+        uniform = "col_w" not in tiles
+        b.u(1 if uniform else 0, 1)        # uniform_tile_spacing_flag
+        if not uniform:
+            for v in tiles["col_w"][:-1]:
+                b.ue(v - 1)                # tile_column_width_minus1
+            for v in tiles["row_h"][:-1]:
+                b.ue(v - 1)                # tile_row_height_minus1
+        b.u(tiles.get("across", 0), 1)     # loop_filter_across_tiles_enabled_flag
+        b.ue(TILE_OFFSET_BITS - 1)         # tile_offset_lens_minus1
+        b.ue(tile_id_bits(tiles) - 1)      # tile_id_len_minus1
     b.u(0, 1)                              # explicit_tile_id_flag
     b.u(0, 1)                              # pic_dra_enabled_flag
     b.u(0, 1)                              # arbitrary_slice_present_flag
@@ -128,6 +144,13 @@ def write_pps(constrained_intra=0, cu_qp_delta=0):
     if cu_qp_delta:
         b.ue(0)                            # cu_qp_delta_area - 6
     return b.bytes()
+
+
+TILE_OFFSET_BITS = 24                      # entry points are written with a fixed width, so they can be filled in after the tiles are generated
+
+
+def tile_id_bits(tiles):
+    return max(1, int(tiles["cols"] * tiles["rows"] - 1).bit_length())
 
 
 GOLOMB_IDX = {5: [0, 0, 1, 0, 0, 1], 7: [0, 0, 1, 0, 0, 1, 2, 1, 0, 0, 1, 2]}      # golombIdx5 / golombIdx7 (src_main/xevdm_alf.h:165-178)
@@ -207,9 +230,20 @@ def write_aps_alf(aps_id, rng, tid=0):
     return b.bytes(), chroma
 
 
-def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_v_off=0, tid=0, alf=None):
+def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_v_off=0, tid=0, alf=None, tiles=None, tile_range=None, entry=None):
+    """tiles: the PPS tile description; tile_range = (first_tile_id, last_tile_id) of this slice; entry: byte sizes of the slice's tiles
+    but the last (None while they are not known yet: the generator only needs a header of the right length)"""
     b = nal_header(nut, tid)
     b.ue(0)                                # slice_pic_parameter_set_id
+    n_tiles = 1
+    if tiles is not None:
+        first, last = tile_range
+        n_tiles = tiles_in_slice(tiles, first, last)
+        # single_tile_in_slice_flag: always 0 - with 1 the parser leaves last_tile_id at the previous slice's value (xevdm_eco.c:2530-2539)
+        # and the rectangle it derives (:2553-2590) is wrong for every single-tile slice but the first
+        b.u(0, 1)
+        b.u(first, tile_id_bits(tiles))    # first_tile_id
+        b.u(last, tile_id_bits(tiles))     # last_tile_id (arbitrary_slice_present_flag = 0)
     b.ue(slice_type)
     if nut == X.NUT_IDR:
         b.u(0, 1)                          # no_output_of_prior_pics_flag
@@ -233,7 +267,15 @@ def write_sh(t, nut, slice_type, qp, deblock=1, alpha=0, beta=0, qp_u_off=0, qp_
         b.se(alpha); b.se(beta)
     b.u(qp, 6)
     b.se(qp_u_off); b.se(qp_v_off)
+    for i in range(n_tiles - 1):           # entry_point_offset_minus1 (xevdm_eco.c:2789-2795)
+        b.u((entry[i] - 1) if entry else 255, TILE_OFFSET_BITS)
     return b.bytes()
+
+
+def tiles_in_slice(tiles, first, last):
+    """rectangle of tiles from first to last (xevdm_eco_sh, src_main/xevdm_eco.c:2553-2590)"""
+    wt = tiles["cols"]
+    return ((last % wt) - (first % wt) + 1) * ((last // wt) - (first // wt) + 1)
 
 
 class NonConforming(Exception):
@@ -256,48 +298,56 @@ class Generator:
         L.gen_replay.restype = None
         L.gen_log.argtypes = [C.c_void_p, C.c_size_t]
         L.gen_log.restype = C.c_size_t
+        L.gen_tile_sizes.argtypes = [C.c_void_p, C.c_int]
+        L.gen_tile_sizes.restype = C.c_int
 
-    def make(self, tools, w, h, bd, frames, seed, types="IPB", qp=30, lps_scale=256, ep_one=128, log2_ctu=6, deblock=1, gop=0, tries=40, **pps_kw):
+    def make(self, tools, w, h, bd, frames, seed, types="IPB", qp=30, lps_scale=256, ep_one=128, log2_ctu=6, deblock=1, gop=0, tries=40, tiles=None,
+             slices=None, **pps_kw):
         """returns (list of NAL units, pictures the generator's own decode produced in output order).
-        Picture by picture: draw a random slice; if the conformance watch of gen_engine.c objects, a FRESH decoder instance is brought to
-        the same state by replaying the recorded bins of the pictures accepted so far, and the picture is drawn again with another seed."""
+        Slice by slice: draw a random slice; if the conformance watch of gen_engine.c objects, a FRESH decoder instance is brought to
+        the same state by replaying the recorded bins of the slices accepted so far, and the slice is drawn again with another seed.
+        tiles: the PPS tile grid (write_pps); slices: the (first_tile_id, last_tile_id) rectangles a picture is cut into (default: one slice)"""
         rng = np.random.default_rng(seed)
         L = self.lib.lib
         tail = bytes(max(1 << 17, w * h * 8))
-        params = [write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(**pps_kw)]
-        hdrs, aps = [], []
+        params = [write_sps(tools, w, h, bd, log2_ctu=log2_ctu), write_pps(tiles=tiles, **pps_kw)]
+        n_tiles = tiles["cols"] * tiles["rows"] if tiles else 1
+        slices = slices or [(0, n_tiles - 1)]
+        units = []                         # one per slice NAL: dict(f, first (of its picture), aps, sh (write_sh arguments), hdr, n_tiles)
         for f in range(frames):
             idr = f == 0 or (gop and f % gop == 0)
             st = X.ST_I if (idr or len(types) == 1) else {"I": X.ST_I, "P": X.ST_P, "B": X.ST_B}[types[1 + (f - 1) % (len(types) - 1)]]
-            alf = None
-            aps.append(None)
+            alf, aps = None, None
             if tools["alf"] and rng.random() < 0.85:             # most pictures filtered, each with its own parameter set
-                nal, has_chroma = write_aps_alf(f % 32, rng)
-                aps[-1] = nal
+                aps, has_chroma = write_aps_alf(f % 32, rng)
                 alf = (f % 32, int(rng.integers(0, 2)), int(rng.integers(0, 4)) if has_chroma else 0)
-            hdrs.append(write_sh(tools, X.NUT_IDR if idr else X.NUT_NONIDR, st, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), deblock=deblock,
-                                 alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)), qp_u_off=int(rng.integers(-3, 4)),
-                                 qp_v_off=int(rng.integers(-3, 4)), alf=alf))
-        accepted = []                      # per picture: (slice data bytes, bins)
+            common = dict(nut=X.NUT_IDR if idr else X.NUT_NONIDR, slice_type=st, deblock=deblock, alpha=int(rng.integers(-3, 4)), beta=int(rng.integers(-3, 4)),
+                          qp_u_off=int(rng.integers(-3, 4)), qp_v_off=int(rng.integers(-3, 4)), alf=alf, tiles=tiles)
+            for k, tr in enumerate(slices):
+                sh = dict(common, qp=int(np.clip(qp + rng.integers(-4, 5), 0, 51)), tile_range=tr)
+                units.append(dict(f=f, first=k == 0, aps=aps if k == 0 else None, sh=sh, hdr=write_sh(tools, **sh),
+                                  n_tiles=tiles_in_slice(tiles, *tr) if tiles else 1))
+        accepted = []                      # per slice: (slice data bytes, bins, tile sizes)
 
         def run(upto, attempt):
-            """fresh decoder: replay pictures [0, upto), then draw picture `upto` (None: replay only).  Returns (pictures, result)"""
+            """fresh decoder: replay slices [0, upto), then draw slice `upto` (None: replay only).  Returns (pictures, result)"""
             pics, result = [], None
             with X.Decoder(self.lib) as d:
                 for n in params:
                     ret, _ = d.decode(n)
                     assert ret >= 0, ("parameter set rejected", ret)
-                for f in range(upto + (0 if attempt is None else 1)):
-                    replay = f < len(accepted) and (attempt is None or f < upto)
-                    L.gen_reset(int(seed) * 1000003 + f * 101 + (attempt or 0), lps_scale, ep_one)
+                for u in range(upto + (0 if attempt is None else 1)):
+                    unit = units[u]
+                    replay = u < len(accepted) and (attempt is None or u < upto)
+                    L.gen_reset(int(seed) * 1000003 + u * 101 + (attempt or 0), lps_scale, ep_one)
                     if replay:
-                        bins = accepted[f][1]
+                        bins = accepted[u][1]
                         L.gen_replay(bins.ctypes.data, bins.size)
-                    if aps[f] is not None:
-                        ret, _ = d.decode(aps[f])
-                        assert ret >= 0, ("adaptation parameter set rejected", f, ret)
-                    ret, stat = d.decode(hdrs[f] + tail)
-                    assert ret >= 0, ("generator decode failed", f, ret)
+                    if unit["aps"] is not None:
+                        ret, _ = d.decode(unit["aps"])
+                        assert ret >= 0, ("adaptation parameter set rejected", u, ret)
+                    ret, stat = d.decode(unit["hdr"] + tail)
+                    assert ret >= 0, ("generator decode failed", u, ret)
                     why = C.create_string_buffer(200)
                     invalid = L.gen_invalid(why, 200)
                     if replay:
@@ -307,12 +357,15 @@ class Generator:
                         n = L.gen_take(buf, len(tail))
                         assert n > 0, "slice data not terminated"
                         bad = L.gen_selfcheck()
-                        assert bad < 0, f"arithmetic encoder self-check: bin {bad} of picture {f} does not decode as chosen"
+                        assert bad < 0, f"arithmetic encoder self-check: bin {bad} of slice {u} does not decode as chosen"
                         lb = (C.c_int32 * (2 * 4000000))()
                         k = L.gen_log(lb, 2 * 4000000)
                         assert k <= 4000000
                         bins = np.frombuffer(lb, np.int32, 2 * k)[1::2].astype(np.uint8)
-                        result = (bytes(buf[:n]), bins, why.value.decode() if invalid else None)
+                        sizes = (C.c_int32 * 512)()
+                        nt = L.gen_tile_sizes(sizes, 512)
+                        assert nt == unit["n_tiles"] and sum(sizes[:nt]) == n, ("tiles generated", nt, list(sizes[:nt]), n)
+                        result = (bytes(buf[:n]), bins, why.value.decode() if invalid else None, list(sizes[:nt]))
                     while True:
                         p = d.pull()
                         if p is None:
@@ -325,20 +378,22 @@ class Generator:
                     pics.append(p)
             return pics, result
 
-        for f in range(frames):
+        for u in range(len(units)):
             for attempt in range(tries):
-                _, (data, bins, why) = run(f, attempt)
+                _, (data, bins, why, sizes) = run(u, attempt)
                 if why is None:
-                    accepted.append((data, bins))
+                    accepted.append((data, bins, sizes))
                     break
             else:
-                raise NonConforming(f"picture {f}: no conforming slice in {tries} draws (last: {why})")
-        pics, _ = run(frames, None)
+                raise NonConforming(f"slice {u} (picture {units[u]['f']}): no conforming slice in {tries} draws (last: {why})")
+        pics, _ = run(len(units), None)
         out = list(params)
-        for f in range(frames):
-            if aps[f] is not None:
-                out.append(aps[f])
-            out.append(hdrs[f] + accepted[f][0])
+        for u, unit in enumerate(units):
+            if unit["aps"] is not None:
+                out.append(unit["aps"])
+            hdr = write_sh(tools, entry=accepted[u][2], **unit["sh"]) if unit["n_tiles"] > 1 else unit["hdr"]     # the entry points are known now
+            assert len(hdr) == len(unit["hdr"])
+            out.append(hdr + accepted[u][0])
         return out, pics
 
 

@@ -11,3 +11,4 @@ u32 gen_unary_ep(XEVD_BSR *bs, XEVD_SBAC *sbac, u32 max_val, u32 max_symbol);
 int gen_last_bound(int pos, int width, int height);
 int gen_ibc_pick(XEVD_CTX *ctx, XEVD_CORE *core);
 int gen_ibc_mvd(XEVD_BSR *bs, XEVD_SBAC *sbac, s16 mvd[MV_D]);
+int gen_tile_start(void);

@@ -33,6 +33,12 @@ static struct {
     uint32_t *log; int32_t *log_off; size_t n_log, cap_log;     /* every bin: kind << 30 | model-before << 1 | bin, for the self-check */
 } E;
 
+/* tiles: every tile of a slice is its own arithmetic code word (xevd_tile_eco resets the decoder, src_main/xevdm.c:2396); the slice data is
+ * their concatenation and the slice header carries the byte sizes as entry points (xevdm_eco.c:2789-2795) */
+#define GEN_MAX_TILES 512
+static size_t g_tile_off[GEN_MAX_TILES + 1], g_tile_log[GEN_MAX_TILES + 1];
+static int g_n_tiles;
+
 static const uint8_t *g_replay; static size_t g_replay_n, g_replay_pos; static int g_replay_err;
 /* replay: the next slice takes its bins from a recorded sequence instead of drawing them (used to bring a fresh decoder instance to
  * the state after the pictures accepted so far, before another attempt at the next picture) */
@@ -95,6 +101,21 @@ void gen_reset(uint64_t seed, int lps_scale_q8, int ep_one_q8)
     E.ep_one_q8 = ep_one_q8 > 0 ? ep_one_q8 : 128;
     E.n_ctx = E.n_ep = E.n_trm = 0;
     E.n_log = 0;
+    g_n_tiles = 0;
+}
+/* called where xevd_tile_eco resets the arithmetic decoder (tools/evcgen/Makefile): the first tile continues the state gen_reset left,
+ * every further tile starts a new code word behind the bytes of the previous one */
+int gen_tile_start(void)
+{
+    if (g_n_tiles > 0) { E.low = 0; E.nb = 14; E.range = 16384; E.finished = 0; }
+    if (g_n_tiles < GEN_MAX_TILES) { g_tile_off[g_n_tiles] = E.n; g_tile_log[g_n_tiles] = E.n_log; g_n_tiles++; }
+    return 0;
+}
+/* byte sizes of the tiles of the slice generated last; returns their number */
+int gen_tile_sizes(int32_t *out, int cap)
+{
+    for (int i = 0; i < g_n_tiles && i < cap; i++) out[i] = (int32_t)((i + 1 < g_n_tiles ? g_tile_off[i + 1] : E.n) - g_tile_off[i]);
+    return g_n_tiles;
 }
 /* the slice data produced since gen_reset: whole bytes, the terminating bin included (0 when no slice was finished) */
 size_t gen_take(uint8_t *dst, size_t cap)
@@ -314,7 +335,12 @@ long long gen_selfcheck(void)
     uint32_t range = 16384, value = 0;
 #define NEXTBIT() ((pos >> 3) < E.n ? (uint32_t)((E.out[pos >> 3] >> (7 - (pos & 7))) & 1) : 0u); pos++
     for (int i = 0; i < 14; i++) { uint32_t b = NEXTBIT(); value = ((value << 1) | b) & 0xFFFF; }
+    int tile = 1;
     for (size_t k = 0; k < E.n_log; k++) {
+        if (tile < g_n_tiles && k == g_tile_log[tile]) {        /* the next tile's code word starts at its byte offset */
+            pos = g_tile_off[tile] * 8; range = 16384; value = 0; tile++;
+            for (int i = 0; i < 14; i++) { uint32_t b = NEXTBIT(); value = ((value << 1) | b) & 0xFFFF; }
+        }
         const uint32_t kind = E.log[k] >> 30, want = E.log[k] & 1;
         uint32_t bin;
         if (kind == 0) {

@@ -159,6 +159,7 @@ _SIGS = {
     ),
     "xb200_deblock": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "xb200_set_chroma_qp_table": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "xb200_set_tiles": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "xb200_pic_upload_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "xb200_pad": (C.c_int, [C.c_void_p, C.c_void_p]),
     "xb200_alf": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.POINTER(AlfParams), C.c_void_p]),

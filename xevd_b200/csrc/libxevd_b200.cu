@@ -62,6 +62,8 @@ struct xb200_ctx {
     pel *alf_copy;               // pre-ALF copy of the picture being filtered
     size_t alf_cap;
     uint8_t *alf_flags_pinned, *alf_flags_dev;
+    int tile_cols, tile_rows, tile_across;   // PPS tile grid (xb200_set_tiles); 1 x 1 = one tile
+    uint16_t tile_col_bd[XB200_MAX_TILE_COLS + 1], tile_row_bd[XB200_MAX_TILE_ROWS + 1];
     void *alf_tab_dev, *alf_tab_pinned;      // ALF: the 100 permuted luma filters of the current APS
     cudaEvent_t alf_tab_done;
     bool alf_tab_valid;
@@ -113,6 +115,8 @@ xb200_ctx *xb200_create(int device, int *err)
     c->d_sync = nullptr; c->sync_cap = 0; c->d_err = nullptr; c->wave_used = false;
     c->d_order = nullptr; c->order_w = c->order_n = 0;
     c->out_buf = nullptr; c->out_cap = 0; c->d_dra = nullptr;
+    c->tile_cols = c->tile_rows = 1; c->tile_across = 0;
+    c->tile_col_bd[0] = c->tile_row_bd[0] = 0; c->tile_col_bd[1] = c->tile_row_bd[1] = 0xffff;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         if (err) *err = XB200_ERR_CUDA;
@@ -827,6 +831,8 @@ int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_A
     a.s_l = p->s_l; a.s_c = p->s_c; a.w = p->w; a.h = p->h; a.log2_ctu = prm->log2_ctu; a.bd = prm->bit_depth_luma;
     a.w_ctu = (p->w + (1 << prm->log2_ctu) - 1) >> prm->log2_ctu;
     a.ctb_flag = nullptr;
+    a.n_tile_cols = c->tile_cols; a.n_tile_rows = c->tile_rows; a.tile_across = c->tile_across;
+    memcpy(a.tile_col_bd, c->tile_col_bd, sizeof(a.tile_col_bd)); memcpy(a.tile_row_bd, c->tile_row_bd, sizeof(a.tile_row_bd));
     memcpy(a.coef_c, alf->coef_chroma, sizeof(a.coef_c));
     memcpy(a.enable, alf->enable, 3);
     if (alf->enable[0]) {
@@ -893,6 +899,18 @@ int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_A
     return XB200_OK;
 }
 
+int xb200_set_tiles(xb200_ctx *c, int n_cols, const uint16_t *col_bd, int n_rows, const uint16_t *row_bd, int across)
+{
+    if (!c || n_cols < 1 || n_rows < 1 || n_cols > XB200_MAX_TILE_COLS || n_rows > XB200_MAX_TILE_ROWS || !col_bd || !row_bd) return XB200_ERR_INVALID_ARGUMENT;
+    if (col_bd[0] != 0 || row_bd[0] != 0) return XB200_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n_cols; i++) if (col_bd[i + 1] <= col_bd[i]) return XB200_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < n_rows; i++) if (row_bd[i + 1] <= row_bd[i]) return XB200_ERR_INVALID_ARGUMENT;
+    c->tile_cols = n_cols; c->tile_rows = n_rows; c->tile_across = across != 0;
+    memcpy(c->tile_col_bd, col_bd, sizeof(uint16_t) * (size_t)(n_cols + 1));
+    memcpy(c->tile_row_bd, row_bd, sizeof(uint16_t) * (size_t)(n_rows + 1));
+    return XB200_OK;
+}
+
 int xb200_set_chroma_qp_table(xb200_ctx *c, const int32_t *tbl)
 {
     if (!c || !tbl) return XB200_ERR_INVALID_ARGUMENT;
@@ -949,6 +967,15 @@ int xb200_deblock(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb200_p
                 if (id < 0) { all[n] = p; id = n++; }
                 a.ref_id[l][i] = (int8_t)id;
             }
+    }
+    if (c->tile_cols * c->tile_rows > 1 && !c->tile_across) {
+        // loop_filter_across_tiles_enabled_flag == 0: the edges that separate two tiles are not filtered
+        xb::TileEdgeArgs t;
+        t.map_edge = cur->map_edge; t.w_scu = cur->w_scu; t.h_scu = cur->h_scu; t.log2_ctu_scu = prm->log2_ctu - 2;
+        t.n_cols = c->tile_cols; t.n_rows = c->tile_rows;
+        memcpy(t.col_bd, c->tile_col_bd, sizeof(t.col_bd)); memcpy(t.row_bd, c->tile_row_bd, sizeof(t.row_bd));
+        if (c->tile_cols > 1) { xb::k_clear_tile_edges<true><<<dim3((cur->h_scu + 255) / 256, c->tile_cols - 1), 256, 0, c->stream>>>(t); c->launches++; }
+        if (c->tile_rows > 1) { xb::k_clear_tile_edges<false><<<dim3((cur->w_scu + 255) / 256, c->tile_rows - 1), 256, 0, c->stream>>>(t); c->launches++; }
     }
     xb::launch_deblock(a, prm->tool_addb != 0, c->stream);
     c->launches += 2;

@@ -22,6 +22,8 @@ struct AlfArgs {
     const uint8_t *ctb_flag;     // device, one byte per CTU, or nullptr
     int16_t coef_c[7];
     uint8_t enable[3];
+    int n_tile_cols, n_tile_rows, tile_across;      // xb200_set_tiles: boundaries in CTUs
+    uint16_t tile_col_bd[XB200_MAX_TILE_COLS + 1], tile_row_bd[XB200_MAX_TILE_ROWS + 1];
     const int4 *ftab;            // device: the 100 luma filters (class x 4 + transpose), 16 int16 each, coefficients in filtering order.  Kept
                                  // per context and uploaded only when the APS changes (as kernel parameters, the per-thread indexed copy
                                  // into shared memory was 11 % of the kernel's stall samples: divergent constant-bank reads)
@@ -32,17 +34,45 @@ constexpr int kAlfT = 32;        // luma tile edge; divides every CTU size the M
 __constant__ uint8_t c_alf_th[16] = {0, 1, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3, 4};
 __constant__ uint8_t c_alf_trans[8] = {0, 1, 0, 2, 2, 3, 1, 3};
 
-// Sample (gy, gx) of the window of the CTU whose rows are [cy0, cy1), gy in [-3, H+3), gx in [-3, W+3).
-// Rows outside the picture mirror (-1 -> 1, H -> H-2: alf_process_tile :1098-1110, :1133-1146); columns outside the picture mirror
-// on rows that belong to the CTU (:1060-1096) and replicate on rows taken from the CTU above / below, which come from the
-// replicated copy (:1112-1131, :1148-1160, alf_copy_and_extend_tile :805).
-__device__ __forceinline__ pel alf_sample(const pel *p, int s, int W, int H, int gy, int gx, int cy0, int cy1)
+// Where a window sample comes from.  The reference filters every CTU through a window cut from a copy of its TILE that was extended by
+// replication (alf_copy_and_extend_tile :805), and builds the 3-sample margins of the window per CTU side (alf_process_tile :1000-1046):
+// a side that is "available" takes the copy as it is - real neighbours inside the tile, the replicated border outside it; a side that is
+// not mirrors the CTU's own samples (rows: the assembled window rows, margins included).  Which sides are available is decided against
+// the tile (loop_filter_across_tiles_enabled_flag == 0, and always for a single tile) or against the picture (flag == 1;
+// tile_boundary_check :844 is then handed width - 1 / height - 1, so only the picture's left and top sides ever mirror).
+struct AlfGeom {
+    int cx0, cx1, cy0, cy1;      // the CTU (clipped to the picture), luma or chroma units
+    int tx0, tx1, ty0, ty1;      // its tile (clipped to the picture)
+    bool al, ar, at, ab;         // sides of the CTU whose margin comes from the copy
+};
+__device__ __forceinline__ AlfGeom alf_geom(const AlfArgs &a, int x0, int y0)
 {
+    AlfGeom g;
+    const int ctu = 1 << a.log2_ctu, cxi = x0 >> a.log2_ctu, cyi = y0 >> a.log2_ctu;
+    g.cx0 = cxi << a.log2_ctu; g.cy0 = cyi << a.log2_ctu;
+    g.cx1 = min(g.cx0 + ctu, a.w); g.cy1 = min(g.cy0 + ctu, a.h);
+    int tc = 0, tr = 0;
+    while (tc + 1 < a.n_tile_cols && cxi >= (int)a.tile_col_bd[tc + 1]) tc++;
+    while (tr + 1 < a.n_tile_rows && cyi >= (int)a.tile_row_bd[tr + 1]) tr++;
+    g.tx0 = (int)a.tile_col_bd[tc] << a.log2_ctu; g.ty0 = (int)a.tile_row_bd[tr] << a.log2_ctu;
+    g.tx1 = min((int)a.tile_col_bd[tc + 1] << a.log2_ctu, a.w); g.ty1 = min((int)a.tile_row_bd[tr + 1] << a.log2_ctu, a.h);
+    if (a.tile_across) { g.al = g.cx0 != 0; g.ar = true; g.at = g.cy0 != 0; g.ab = true; }
+    else { g.al = g.cx0 != g.tx0; g.ar = g.cx1 != g.tx1; g.at = g.cy0 != g.ty0; g.ab = g.cy1 != g.ty1; }
+    return g;
+}
+// Sample (gy, gx) of the window of that CTU; sh = 0 luma, 1 chroma (the geometry is in luma units and even)
+__device__ __forceinline__ pel alf_sample(const pel *p, int s, const AlfGeom &g, int sh, int gy, int gx)
+{
+    const int cx0 = g.cx0 >> sh, cx1 = g.cx1 >> sh, cy0 = g.cy0 >> sh, cy1 = g.cy1 >> sh;
     bool own_row = gy >= cy0 && gy < cy1;
-    if (gy < 0) { gy = -gy; own_row = true; }
-    else if (gy >= H) { gy = 2 * H - gy - 2; own_row = true; }
-    if (gx < 0) gx = own_row ? -gx : 0;
-    else if (gx >= W) gx = own_row ? 2 * W - gx - 2 : W - 1;
+    if (gy < cy0) { if (!g.at) { gy = 2 * cy0 - gy; own_row = true; } }
+    else if (gy >= cy1) { if (!g.ab) { gy = 2 * cy1 - gy - 2; own_row = true; } }
+    if (own_row) {
+        if (gx < cx0) { if (!g.al) gx = 2 * cx0 - gx; }
+        else if (gx >= cx1) { if (!g.ar) gx = 2 * cx1 - gx - 2; }
+    }
+    gx = min(max(gx, g.tx0 >> sh), (g.tx1 >> sh) - 1);
+    gy = min(max(gy, g.ty0 >> sh), (g.ty1 >> sh) - 1);
     return p[(size_t)gy * s + gx];
 }
 
@@ -84,14 +114,13 @@ __global__ void __launch_bounds__(256) k_alf(const __grid_constant__ AlfArgs a)
     const int t = threadIdx.x;
     const int x0 = blockIdx.x * kAlfT, y0 = blockIdx.y * kAlfT;
     const int tw = min(kAlfT, a.w - x0), th = min(kAlfT, a.h - y0);
-    const int ctu = 1 << a.log2_ctu;
-    const int cy0 = (y0 >> a.log2_ctu) << a.log2_ctu, cy1 = min(cy0 + ctu, a.h);
+    const AlfGeom g = alf_geom(a, x0, y0);
     const bool luma_on = a.enable[0] && (!a.ctb_flag || a.ctb_flag[(y0 >> a.log2_ctu) * a.w_ctu + (x0 >> a.log2_ctu)]);
     const int maxv = (1 << a.bd) - 1;
 
     // Tiles whose window lies inside the picture need none of the mirroring rules: 8-byte global loads of the aligned superset of every
     // window row (the planes start 16-byte aligned and x0 is a multiple of 32), one 16-byte shared-memory store each.
-    const bool interior = tw == kAlfT && th == kAlfT && x0 >= 4 && x0 + kAlfT + 4 <= a.w && y0 >= 3 && y0 + kAlfT + 3 <= a.h;
+    const bool interior = tw == kAlfT && th == kAlfT && x0 - 4 >= g.tx0 && x0 + kAlfT + 4 <= g.tx1 && y0 - 3 >= g.ty0 && y0 + kAlfT + 3 <= g.ty1;
     // the chroma windows of an interior tile (2 planes x 20 rows x 6 8-byte words = 240 loads, one per thread) are fetched now and parked in
     // registers: their latency hides behind the luma phases (the store that waited for them was 7 % of the stall samples)
     static_assert(2 * kAlfCH * (kAlfCW / 4) <= 256, "one chroma window word per thread");
@@ -110,7 +139,7 @@ __global__ void __launch_bounds__(256) k_alf(const __grid_constant__ AlfArgs a)
         } else
         for (int i = t; i < (kAlfT + 6) * (kAlfT + 6); i += 256) {
             const int r = i / (kAlfT + 6), c = i - r * (kAlfT + 6);
-            if (r < th + 6 && c < tw + 6) win[r * kAlfWinW + c + 1] = alf_sample(a.sy, a.s_l, a.w, a.h, y0 - 3 + r, x0 - 3 + c, cy0, cy1);
+            if (r < th + 6 && c < tw + 6) win[r * kAlfWinW + c + 1] = alf_sample(a.sy, a.s_l, g, 0, y0 - 3 + r, x0 - 3 + c);
         }
         __syncthreads();
         // Laplacians per 2x2 cell over rows/cols -2 .. +size+1 (alf_derive_classification_blk :60-106).  A thread takes two neighbouring
@@ -233,7 +262,7 @@ __global__ void __launch_bounds__(256) k_alf(const __grid_constant__ AlfArgs a)
     }
 
     // chroma: the 16x16 tiles of both planes in one phase, +-2 window, thread = 2 neighbouring samples of one plane
-    const int W_c = a.w >> 1, H_c = a.h >> 1, xc0 = x0 >> 1, yc0 = y0 >> 1, twc = tw >> 1, thc = th >> 1;
+    const int xc0 = x0 >> 1, yc0 = y0 >> 1, twc = tw >> 1, thc = th >> 1;
     if (!a.enable[1] && !a.enable[2]) return;
     __syncthreads();
     if (interior) {
@@ -243,7 +272,7 @@ __global__ void __launch_bounds__(256) k_alf(const __grid_constant__ AlfArgs a)
     for (int i = t; i < 2 * kAlfCH * kAlfCH; i += 256) {
         const int pl = i / (kAlfCH * kAlfCH), k = i - pl * (kAlfCH * kAlfCH), r = k / kAlfCH, c = k - r * kAlfCH;
         if (a.enable[1 + pl] && r < thc + 4 && c < twc + 4)
-            win[(pl * kAlfCH + r) * kAlfCW + c + 2] = alf_sample(pl ? a.sv : a.su, a.s_c, W_c, H_c, yc0 - 2 + r, xc0 - 2 + c, cy0 >> 1, cy1 >> 1);
+            win[(pl * kAlfCH + r) * kAlfCW + c + 2] = alf_sample(pl ? a.sv : a.su, a.s_c, g, 1, yc0 - 2 + r, xc0 - 2 + c);
     }
     __syncthreads();
     {

@@ -195,6 +195,27 @@ __device__ __forceinline__ int dbk_visit_time(const DbkArgs &a, int sx, int sy)
     return max(t0, t1);
 }
 
+// loop_filter_across_tiles_enabled_flag == 0: CU edges that coincide with a tile boundary lose their flags before the passes run
+// (the reference tests map_tidx on both sides of every edge, xevdm_df.c:142,233,877,1088).  blockIdx.y = one interior boundary; column
+// and row boundaries are two launches, because the SCU where they cross is one byte that both would read-modify-write.
+struct TileEdgeArgs {
+    uint8_t *map_edge;
+    int w_scu, h_scu, log2_ctu_scu, n_cols, n_rows;
+    uint16_t col_bd[XB200_MAX_TILE_COLS + 1], row_bd[XB200_MAX_TILE_ROWS + 1];
+};
+template <bool COLS>
+__global__ void __launch_bounds__(256) k_clear_tile_edges(const __grid_constant__ TileEdgeArgs a)
+{
+    const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+    if (COLS) {
+        const int sx = (int)a.col_bd[b + 1] << a.log2_ctu_scu;
+        if (sx < a.w_scu && i < a.h_scu) a.map_edge[i * a.w_scu + sx] &= (uint8_t)~(XB200_EDGE_LEFT | XB200_EDGE_LEFT_NOC);
+    } else {
+        const int sy = (int)a.row_bd[b + 1] << a.log2_ctu_scu;
+        if (sy < a.h_scu && i < a.w_scu) a.map_edge[sy * a.w_scu + i] &= (uint8_t)~(XB200_EDGE_TOP | XB200_EDGE_TOP_NOC);
+    }
+}
+
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs a)
 {

@@ -159,6 +159,12 @@ class Context:
             raise XevdB200Error(err.value, "xb200_pic_alloc", (self.lib.xb200_last_error(self.handle) or b"").decode())
         return DevicePicture(self, hnd, w, h)
 
+    def set_tiles(self, col_bd=None, row_bd=None, across: bool = False):
+        """tile grid for the loop filters: column / row boundaries in CTUs (None: one tile)"""
+        cb = np.ascontiguousarray(col_bd if col_bd is not None else [0, 0xffff], np.uint16)
+        rb = np.ascontiguousarray(row_bd if row_bd is not None else [0, 0xffff], np.uint16)
+        self._chk(self.lib.xb200_set_tiles(self.handle, len(cb) - 1, cb.ctypes.data, len(rb) - 1, rb.ctypes.data, int(across)), "xb200_set_tiles")
+
     def set_chroma_qp_table(self, tbl: np.ndarray):
         t = np.ascontiguousarray(tbl, np.int32)
         assert t.shape == (2, 58)
