@@ -75,6 +75,7 @@ struct xb200_ctx {
     int *d_dra;                  // DRA LUTs on the device (3 x 1024 ints)
     bool peer_maps;              // XB200_PEER_NOMAPS=1 (read once at creation) keeps the per-SCU maps local in band mode (debug)
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
+    int v2_variant;              // XB200_V2_VARIANT=rounds | slots: pin the prediction-stage variant of the throughput kernel (tests run both); else per picture
 };
 
 #define CK(ctx, call)                                                                              \
@@ -126,7 +127,8 @@ xb200_ctx *xb200_create(int device, int *err)
     // opt in to large dynamic shared memory for the CTU kernels (CTU 128 needs ~150 KB); a kernel that cannot get its shared memory would
     // fail at its first launch with a less readable error, so creation fails instead
     cudaError_t fe = cudaSuccess;
-#define XB_SMEM(fn, bytes) do { if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); } while (0)
+#define XB_SMEM(fn, bytes) do { if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+                                if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); } while (0)
     XB_SMEM((xb::k_recon_inter<false>), (int)xb::ReconSmem::bytes(7));
     XB_SMEM((xb::k_recon_inter<true>), (int)xb::ReconSmem::bytes(7));
     XB_SMEM((xb::k_recon_intra<false>), (int)xb::IntraSmem::bytes());
@@ -143,6 +145,14 @@ xb200_ctx *xb200_create(int device, int *err)
     XB_SMEM((xb::k_recon_inter_v2<true, false, true, true>), xb::R2Layout::make(2, 256).total);
     XB_SMEM((xb::k_recon_inter_v2<false, false, false, true>), xb::R2Layout::make(1, 256).total);
     XB_SMEM((xb::k_recon_inter_v2<true, false, false, true>), xb::R2Layout::make(2, 256).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, false, false, true>), xb::R2Layout::make(1, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, false, false, true>), xb::R2Layout::make(2, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, true, false, true>), xb::R2Layout::make(1, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, true, false, true>), xb::R2Layout::make(2, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, true, true, true>), xb::R2Layout::make(1, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, true, true, true>), xb::R2Layout::make(2, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<false, false, false, true, true>), xb::R2Layout::make(1, 256, false, true).total);
+    XB_SMEM((xb::k_recon_inter_v2<true, false, false, true, true>), xb::R2Layout::make(2, 256, false, true).total);
 #undef XB_SMEM
     if (fe != cudaSuccess) {
         fprintf(stderr, "[xb200] cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %s\n", cudaGetErrorString(fe));
@@ -157,6 +167,7 @@ xb200_ctx *xb200_create(int device, int *err)
         memcpy(c->chroma_qp[0], base, 58); memcpy(c->chroma_qp[1], base, 58);
     }
     { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
+    { const char *e = getenv("XB200_V2_VARIANT"); c->v2_variant = !e ? 0 : (!strcmp(e, "rounds") ? 1 : (!strcmp(e, "slots") ? 2 : 0)); }
     { const char *e = getenv("XB200_PEER_NOMAPS"); c->peer_maps = !(e && e[0] == '1'); }
     {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
         int16_t hl[2][16][8], hc[2][32][4];
@@ -193,10 +204,13 @@ xb200_ctx *xb200_create(int device, int *err)
         for (int nl = 1; nl <= 2; nl++)
             for (int mc = 16; mc <= 256; mc *= 4) {
                 int nb = 0;
-                const int sm = xb::R2Layout::make(nl, mc).total;
-                if (nl == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<false>, xb::kR2Threads, sm);
-                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<true>, xb::kR2Threads, sm);
-                fprintf(stderr, "[xb200] k_recon_inter_v2 lists=%d max_cu=%d: %d B dynamic smem, %d CTAs/SM\n", nl, mc, sm, nb);
+                const int sm = xb::R2Layout::make(nl, mc).total, smw = xb::R2Layout::make(nl, mc, false, true).total;
+                int nbw = 0;
+                if (nl == 1) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<false>, xb::kR2Threads, sm);
+                               cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbw, xb::k_recon_inter_v2<false, false, false, false, true>, xb::kR2Threads, smw); }
+                else { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, xb::k_recon_inter_v2<true>, xb::kR2Threads, sm);
+                       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbw, xb::k_recon_inter_v2<true, false, false, false, true>, xb::kR2Threads, smw); }
+                fprintf(stderr, "[xb200] k_recon_inter_v2 lists=%d max_cu=%d: rounds %d B dynamic smem, %d CTAs/SM; warp slots %d B, %d CTAs/SM\n", nl, mc, sm, nb, smw, nbw);
             }
     }
     if (err) *err = XB200_OK;
@@ -532,20 +546,21 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         max_cu = (max_cu + 15) & ~15;
         const bool bi = n1 > 0;
         const bool peer = a.n_peer > 0;
-        const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu, peer);
+        // warp-slot variant (three CTAs per SM, no block-wide step in the prediction stages) for pictures of large CUs; the round variant
+        // shares its per-tile passes between two tiles, which wins when most CUs are 8x8 and smaller (xb_recon2.cuh; A/B in profiles/r2)
+        const bool ws = !peer && (c->v2_variant == 2 || (c->v2_variant == 0 && (long long)n_cu <= 16LL * a.n_ctu));
+        const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu, peer, ws);
         const dim3 grid(a.w_ctu, a.n_ctu / a.w_ctu);
+#define XB_V2(BI_, IQT_, DISP_) do { if (ws) xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu); \
+                                     else xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu); } while (0)
         if (peer) {
             if (bi) xb::k_recon_inter_v2<true, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
             else    xb::k_recon_inter_v2<false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-        } else if (a.iqt || mixed) {
-            // Main variants: IQT transform and / or per-CU dispatch
-#define XB_V2(BI_, IQT_, DISP_) xb::k_recon_inter_v2<BI_, false, IQT_, DISP_><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu)
-            if (a.iqt && mixed) { if (bi) XB_V2(true, true, true); else XB_V2(false, true, true); }
-            else if (a.iqt)     { if (bi) XB_V2(true, true, false); else XB_V2(false, true, false); }
-            else                { if (bi) XB_V2(true, false, true); else XB_V2(false, false, true); }
+        } else if (a.iqt && mixed) { if (bi) XB_V2(true, true, true); else XB_V2(false, true, true); }
+        else if (a.iqt)            { if (bi) XB_V2(true, true, false); else XB_V2(false, true, false); }
+        else if (mixed)            { if (bi) XB_V2(true, false, true); else XB_V2(false, false, true); }
+        else                       { if (bi) XB_V2(true, false, false); else XB_V2(false, false, false); }
 #undef XB_V2
-        } else if (bi) xb::k_recon_inter_v2<true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
-        else           xb::k_recon_inter_v2<false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
         if (mixed) { c->launches++; CK(c, cudaGetLastError()); }
     }
     if (!fast || mixed) {

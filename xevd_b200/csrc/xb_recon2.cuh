@@ -31,11 +31,13 @@
 
 namespace xb {
 
-#ifndef XB_R2_MINB
-#define XB_R2_MINB 2
-#endif
 constexpr int kR2Threads = 256;
-constexpr int kTileCap = 16;                 // 16x16 luma tiles staged per round (a whole 64x64 CTU)
+// Two ways through the prediction stages (template parameter WS of the kernel):
+//   WS (warp slots)  8 tile slots, one per warp: a warp takes its tiles (warp, warp + 8, ...) through both stages and the reconstruction
+//                    alone, nothing block-wide after the residual; 72 KB and 80 registers -> three CTAs per SM.  Pictures of large CUs.
+//   !WS (rounds)     16 slots filled per round, two per warp in the horizontal stage, 16 threads per slot in the vertical stage:
+//                    half the per-tile passes when the tiles are small (8x8 CUs), two CTAs per SM.  Pictures of many small CUs.
+constexpr int kTileCapWS = 8, kTileCapRounds = 16;
 constexpr int kBoxLW = 40, kBoxLH = 23;      // luma TMA box: (offset <= 7) + 16 + 7 = 30 -> 40 samples keeps the row stride
 constexpr int kBoxCW = 24, kBoxCH = 11;      //   at 20 words (8 rows = 8 distinct bank quads); chroma: 7 + 8 + 3 = 18 -> 24
 constexpr int kWinLBytes = 1920;             // 40 x 23 x 2 = 1840, rounded to a multiple of 128
@@ -90,8 +92,9 @@ struct TilePred {                            // 16 bytes, per (tile, used list)
 // per-block line prefix sums (no per-line lists).
 struct R2Layout {
     int win_l, win_c, scratch, res_y, coef, cus, tus, pre1, pre2, batch, tiles, preds, offs, taps, out, total;
-    __host__ __device__ static R2Layout make(int nl, int max_cu, bool peer = false)
+    __host__ __device__ static R2Layout make(int nl, int max_cu, bool peer = false, bool ws = false)
     {
+        const int kTileCap = ws ? kTileCapWS : kTileCapRounds;
         R2Layout L;
         int o = 128;                                                       // [0,128): mbarrier + counters
         // windows and vertical-pair buffers hold ONE prediction list at a time: the lists of a bi-predicted picture go through them one
@@ -330,16 +333,17 @@ __device__ __forceinline__ int cu_coef_end(const XbFrameArgs &a, const XB200_CU 
 
 // PEER (band mode over NVLink): the reconstructed CTU is collected in shared memory and written out as whole 128-byte rows to the
 // local picture AND to its twins on the peer GPUs, so the exchange rides on the kernel's own stores at full NVLink request size.
-template <bool BI, bool PEER = false, bool IQT = false, bool DISP = false>
-__global__ void __launch_bounds__(kR2Threads, XB_R2_MINB)
+template <bool BI, bool PEER = false, bool IQT = false, bool DISP = false, bool WS = false>
+__global__ void __launch_bounds__(kR2Threads, WS ? 3 : 2)
 k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NL = BI ? 2 : 1;
-    const R2Layout L = R2Layout::make(NL, max_cu, PEER);
+    constexpr int kTileCap = WS ? kTileCapWS : kTileCapRounds;
+    const R2Layout L = R2Layout::make(NL, max_cu, PEER, WS);
     int16_t *s_out = (int16_t *)(smem + L.out);                 // [64][64] luma, then [2][32][32] chroma
-    uint64_t *mbar = (uint64_t *)smem, *mbar_coef = (uint64_t *)(smem + 8);
-    int *cnt = (int *)(smem + 16);           // totals: [0] luma blocks [1] chroma blocks [2,3] pass-1 lines y,c [4,5] pass-2 y,c [6] tiles
+    uint64_t *mbar = (uint64_t *)smem, *mbar_coef = (uint64_t *)(smem + 64);     // [0,64): WS: one mbarrier per tile slot (= per warp); !WS: the first one
+    int *cnt = (int *)(smem + 72);           // totals: [0] luma blocks [1] chroma blocks [2,3] pass-1 lines y,c [4,5] pass-2 y,c [6] tiles
     XB200_CU *s_cu = (XB200_CU *)(smem + L.cus);
     TuDesc *s_tu = (TuDesc *)(smem + L.tus);
     uint16_t *s_pre1 = (uint16_t *)(smem + L.pre1), *s_pre2 = (uint16_t *)(smem + L.pre2);
@@ -363,7 +367,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     //      before anything else happens (the wait for it was 10 % of all stall samples when it was issued after the staging barrier).
     int coef_base = 0, coef_bytes = 0;
     if (tid == 0) {
-        mbar_init(mbar, 1); mbar_init(mbar_coef, 1);
+        for (int k = 0; k < 8; k++) mbar_init((uint64_t *)smem + k, 1);
+        mbar_init(mbar_coef, 1);
         if (ncu > 0) {
             const int4 f0 = __ldg((const int4 *)(a.cus + cu0) + 1), l0 = __ldg((const int4 *)(a.cus + cu0 + ncu - 1)), l1 = __ldg((const int4 *)(a.cus + cu0 + ncu - 1) + 1);
             XB200_CU c1;
@@ -548,9 +553,25 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     }
     __syncthreads();
 
+    // ---- prediction windows: warp w owns tile slot w (window buffers, mbarrier, vertical-pair buffers) and takes the tiles w, w + 8, ... through
+    //      both interpolation stages and the reconstruction on its own - no block-wide barrier after the residual is complete.  Lane 0
+    //      issues the two boxes of a (tile, list) and announces their bytes on the slot's mbarrier; the first one flies during the residual
+    //      passes, every later one during the vertical stage of its predecessor.
+    uint64_t *mbar_w = (uint64_t *)smem + warp;
+    auto issue_w = [&](int tile, int l) {
+        if (lane == 0) {
+            const TilePred p = s_pred[tile * NL + l];
+            const CUtensorMap *tm = a.ref_tmap[p.ref];
+            mbar_expect_tx(mbar_w, 2u * (kBoxLW * kBoxLH + 2 * kBoxCW * kBoxCH));
+            tma_load_2d(smem + L.win_l + warp * kWinLBytes, tm + 0, p.wx & ~7, p.wy, mbar_w);
+            tma_load_3d(smem + L.win_c + warp * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, 0, mbar_w);        // Cb and Cr: one box over the plane dimension
+        }
+    };
+    if (WS && warp < n_tiles) issue_w(warp, 0);
+
     // ---- MC rounds (normally one: a CTU of >=16x16 CUs has at most 16 tiles) -----------------------------------------------
     const int n_rounds = (n_tiles + kTileCap - 1) / kTileCap;
-    auto issue = [&](int round, int l) {
+    auto issue_r = [&](int round, int l) {
         // the windows of list l of this round's tiles.  Every warp issues the boxes of its own two tile slots (lanes 0, 1): a single issuing
         // warp spent ~2000 cycles on 48 serialised TMA instructions and the other seven waited for it at the next barrier (13 % of
         // all stall samples).  Warp 0 announces the byte count of the whole batch.
@@ -568,7 +589,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             tma_load_3d(smem + L.win_c + slot * kWinCBytes, tm + 1, p.cwx & ~7, p.cwy, 0, mbar);        // Cb and Cr: one box over the plane dimension
         }
     };
-    issue(0, 0);
+    if (!WS) issue_r(0, 0);
 
     // Block lookup for line li of a pass: start at the block that holds the first line of the warp's 32-line batch (table written with the
     // descriptors) and step over the block starts up to li - one step per block boundary inside the batch, none for blocks of 32+ lines.
@@ -685,14 +706,171 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         }
     }
 
-    int *s_m2l = s_tmp;                                        // [16][kM2LWords]
-    int *s_m2c = s_tmp + kTileCap * kM2LWords;                 // [16][2][kM2CWords]
+    int *s_m2l = s_tmp;                                        // [slots][kM2LWords]
+    int *s_m2c = s_tmp + kTileCap * kM2LWords;                 // [slots][2][kM2CWords]
     const int maxv2 = ((1 << a.bd_l) - 1) * 0x00010001;        // the reference clips all planes with the luma depth
     const int maxc2 = ((1 << a.bd_c) - 1) * 0x00010001;
     const int s1l = min(4, a.bd_l - 8), s2l = max(8, 20 - a.bd_l);
     const int s1c = min(4, a.bd_c - 8), s2c = max(8, 20 - a.bd_c);
 
     int phase = 0;
+    if constexpr (WS) {
+#pragma unroll 1
+    for (int tile = warp; tile < n_tiles; tile += kTileCap) {
+        const TileDesc td = s_tile[tile];
+        const int slot = warp;
+        // the running prediction of this lane's samples: luma 2 columns x 4 rows, chroma 2 columns x 2 rows (packed pairs)
+        int outp[4], outc[2];
+#pragma unroll 1
+        for (int l = 0; l < NL; l++) {
+            if (l >= td.nl) break;                                  // (uniform: one tile per warp)
+            mbar_wait(mbar_w, phase & 1);
+            phase++;
+            const TilePred p = s_pred[tile * NL + l];
+            // ---- horizontal stage, output = vertical pairs.  luma: 24 tasks (2 column halves x 12 row-pairs), chroma: 12 (2 planes x 6 row-pairs)
+            if (lane < 24) {
+                const int half = lane >= 12 ? 1 : 0, rp = lane - 12 * half;
+                if (half * 8 < td.tw && 2 * rp < td.th + 7) {
+                    const int offx = p.offs & 7, par = offx & 1;
+                    const int *win = (const int *)(smem + L.win_l + slot * kWinLBytes) + (offx >> 1) + half * 4;
+                    const Taps5 te = ld_taps5(p.phx, par), to = ld_taps5(p.phx, par + 1);   // even outputs: A0 | B, odd outputs: B | A1
+                    const int sh = p.two_d ? s1l : 6;
+                    int hv[2][8];
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int *rowp = win + (2 * rp + rr) * kWinLStrideW;
+                        int q[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) q[j] = rowp[j];
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            hv[rr][2 * o] = fir5(te, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                            hv[rr][2 * o + 1] = fir5(to, q[o], q[o + 1], q[o + 2], q[o + 3], q[o + 4 < 8 ? o + 4 : 7], 0) >> sh;
+                        }
+                    }
+                    int4 *dst = (int4 *)(s_m2l + slot * kM2LWords + half * 8 + rp * kM2LStrideW);
+                    dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                    dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+                }
+            }
+            if (lane < 12) {
+                const int pl = lane >= 6 ? 1 : 0, rp = lane - 6 * pl;
+                if (2 * rp < (td.th >> 1) + 3) {
+                    const int offx = p.offs >> 4, par = offx & 1;
+                    const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1);
+                    const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
+                    const int sh = p.ctwo_d ? s1c : 6;
+                    int hv[2][8];
+#pragma unroll
+                    for (int rr = 0; rr < 2; rr++) {
+                        const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
+                        int q[6];
+#pragma unroll
+                        for (int j = 0; j < 6; j++) q[j] = rowp[j];
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                            hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                        }
+                    }
+                    int4 *dst = (int4 *)(s_m2c + (slot * 2 + pl) * kM2CWords + rp * kM2CStrideW);
+                    dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
+                    dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+                }
+            }
+            __syncwarp();
+            // the warp is done with its windows: the next boxes (other list of this tile, or the warp's next tile) load while the vertical
+            // stage of this one runs
+            if (l + 1 < td.nl) issue_w(tile, l + 1);
+            else if (tile + kTileCap < n_tiles) issue_w(tile + kTileCap, 0);
+
+            // ---- vertical stage: this list's prediction into the running registers (xevd_average_16b_no_clip for the second list) -----
+            // luma: one lane = 2 columns x 4 rows (8 column pairs x 4 row groups)
+            {
+                const int cp = lane & 7, rg = lane >> 3;
+                if (2 * cp < td.tw && 4 * rg < td.th) {
+                    const Taps5 te = ld_taps5(p.phy, 0), to = ld_taps5(p.phy, 1);
+                    const int sh = p.two_d ? s2l : 6, rnd = p.two_d ? (1 << (s2l - 1)) : 0;
+                    const int *m2 = s_m2l + slot * kM2LWords + (2 * rg) * kM2LStrideW + 2 * cp;
+                    int P[6][2];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) { const int2 v = *(const int2 *)(m2 + j * kM2LStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        int e0 = fir5(te, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], 0, rnd) >> sh;
+                        int e1 = fir5(te, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], 0, rnd) >> sh;
+                        int o0 = fir5(to, P[q][0], P[q + 1][0], P[q + 2][0], P[q + 3][0], P[q + 4][0], rnd) >> sh;
+                        int o1 = fir5(to, P[q][1], P[q + 1][1], P[q + 2][1], P[q + 3][1], P[q + 4][1], rnd) >> sh;
+                        int pe = __vimin_s16x2_relu(pack16(e0, e1), maxv2);
+                        int po = __vimin_s16x2_relu(pack16(o0, o1), maxv2);
+                        if (l == 0) { outp[2 * q] = pe; outp[2 * q + 1] = po; }
+                        else {      // two clipped, non-negative predictions
+                            outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                            outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                        }
+                    }
+                }
+            }
+            // chroma: one lane = 2 columns x 2 rows (2 planes x 4 column pairs x 4 row groups)
+            {
+                const int pl = lane >> 4, cp = lane & 3, rg = (lane >> 2) & 3;
+                const int cw = td.tw >> 1, ch = td.th >> 1;
+                if (2 * cp < cw && 2 * rg < ch) {
+                    const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
+                    const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
+                    const int *m2 = s_m2c + (slot * 2 + pl) * kM2CWords + rg * kM2CStrideW + 2 * cp;
+                    int P[3][2];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
+                    int e0 = fir3(te, P[0][0], P[1][0], 0, rnd) >> sh;
+                    int e1 = fir3(te, P[0][1], P[1][1], 0, rnd) >> sh;
+                    int o0 = fir3(to, P[0][0], P[1][0], P[2][0], rnd) >> sh;
+                    int o1 = fir3(to, P[0][1], P[1][1], P[2][1], rnd) >> sh;
+                    int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
+                    int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
+                    if (l == 0) { outc[0] = pe; outc[1] = po; }
+                    else {
+                        outc[0] = ((outc[0] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                        outc[1] = ((outc[1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                    }
+                }
+            }
+            __syncwarp();           // the pair buffers of this warp's slot are rewritten by the next list / tile
+        }
+
+        // ---- reconstruction: prediction + residual, clip, store -----------------------------------------------------------------------
+        {
+            const int cp = lane & 7, rg = lane >> 3;
+            if (2 * cp < td.tw && 4 * rg < td.th) {
+                const int x = td.px + 2 * cp, y = td.py + 4 * rg;
+                const int *res = (const int *)(s_res + y * kResStride + x);
+                pel *dst = a.cur.y + (size_t)(ctu_y + y) * a.s_l + ctu_x + x;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (4 * rg + r < td.th) {
+                        const int v = (int)__viaddmin_s16x2_relu(outp[r], res[r * (kResStride / 2)], maxv2);
+                        if (PEER) *(int *)(s_out + (y + r) * 64 + x) = v;
+                        else *(int *)(dst + (size_t)r * a.s_l) = v;
+                    }
+            }
+            const int pl = lane >> 4, ccp = lane & 3, crg = (lane >> 2) & 3;
+            const int cw = td.tw >> 1, ch = td.th >> 1;
+            if (2 * ccp < cw && 2 * crg < ch) {
+                const int x = (td.px >> 1) + 2 * ccp, y = (td.py >> 1) + 2 * crg;
+                const int *res = (const int *)(s_res + plane_origin(1 + pl, kResStride) + y * kResStride + x);
+                pel *dst = (pl ? a.cur.v : a.cur.u) + (size_t)((ctu_y >> 1) + y) * a.s_c + (ctu_x >> 1) + x;
+#pragma unroll
+                for (int r = 0; r < 2; r++)
+                    if (2 * crg + r < ch) {
+                        const int v = (int)__viaddmin_s16x2_relu(outc[r], res[r * (kResStride / 2)], maxv2);
+                        if (PEER) *(int *)(s_out + 64 * 64 + pl * 32 * 32 + (y + r) * 32 + x) = v;
+                        else *(int *)(dst + (size_t)r * a.s_c) = v;
+                    }
+            }
+        }
+    }
+
+    } else {
     for (int round = 0; round < n_rounds; round++) {
         const int t0 = round * kTileCap, nt = min(kTileCap, n_tiles - t0);
         // the running prediction of this thread's samples: luma 2 columns x 8 rows, chroma 2 columns x 4 rows (packed pairs)
@@ -767,7 +945,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             // every warp is done with the windows: the next batch (other list of this round, or the next round) loads while the vertical
             // stage of this one runs
             const bool more = l + 1 < NL || round + 1 < n_rounds;
-            if (more) { __syncthreads(); if (l + 1 < NL) issue(round, l + 1); else issue(round + 1, 0); }
+            if (more) { __syncthreads(); if (l + 1 < NL) issue_r(round, l + 1); else issue_r(round + 1, 0); }
             else __syncwarp();
 
             // ---- vertical stage: this list's prediction into the running registers (xevd_average_16b_no_clip for the second list) -----
@@ -871,6 +1049,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 }
             }
         }
+    }
+
     }
 
     if (PEER) {
