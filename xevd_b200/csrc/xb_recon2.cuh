@@ -47,8 +47,6 @@ constexpr int kWinLStrideW = kBoxLW / 2;     // window row stride in 32-bit word
 constexpr int kWinCStrideW = kBoxCW / 2;
 constexpr int kM2LStrideW = 20;              // vertical-pair buffer row stride (16 columns + 4 pad), words
 constexpr int kM2LWords = 12 * kM2LStrideW;  // 12 pair-rows
-constexpr int kM2CStrideW = 12;              // 8 columns + 4 pad
-constexpr int kM2CWords = 6 * kM2CStrideW;   // 6 pair-rows
 // pass-1 results and the residual: rows 0..63 hold luma, rows 64..95 hold Cb (columns 0..31) and Cr (columns 32..63) side by side, so one
 // compile-time row stride serves every plane (the strided accesses of the passes become immediate offsets)
 constexpr int kTmpStride = 68;               // pass-1 result row stride, words (64 + 4: int4 stores of 8 consecutive rows hit 8 distinct bank quads)
@@ -103,7 +101,7 @@ struct R2Layout {
         L.win_l = o; o += kTileCap * kWinLBytes;
         L.win_c = o; o += kTileCap * kWinCBytes;
         const int tmp_bytes = 4 * kPlaneRows * kTmpStride;
-        const int m2_bytes = 4 * kTileCap * (kM2LWords + 2 * kM2CWords);
+        const int m2_bytes = 4 * kTileCap * kM2LWords;
         L.scratch = o; o += tmp_bytes > m2_bytes ? tmp_bytes : m2_bytes;
         // residual planes; before the row pass the same bytes stage the CTU's slice of the coefficient stream, fetched by one bulk copy
         // while the descriptors are built (at most 2 int16 per luma sample: 4x4 CUs with their chroma blocks padded to 8)
@@ -706,8 +704,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
         }
     }
 
-    int *s_m2l = s_tmp;                                        // [slots][kM2LWords]
-    int *s_m2c = s_tmp + kTileCap * kM2LWords;                 // [slots][2][kM2CWords]
+    int *s_m2l = s_tmp;                                        // [slots][kM2LWords] (chroma needs no pair buffer: its two stages are one pass)
     const int maxv2 = ((1 << a.bd_l) - 1) * 0x00010001;        // the reference clips all planes with the luma depth
     const int maxc2 = ((1 << a.bd_c) - 1) * 0x00010001;
     const int s1l = min(4, a.bd_l - 8), s2l = max(8, 20 - a.bd_l);
@@ -727,7 +724,7 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
             mbar_wait(mbar_w, phase & 1);
             phase++;
             const TilePred p = s_pred[tile * NL + l];
-            // ---- horizontal stage, output = vertical pairs.  luma: 24 tasks (2 column halves x 12 row-pairs), chroma: 12 (2 planes x 6 row-pairs)
+            // ---- luma, horizontal stage, output = vertical pairs: 24 tasks (2 column halves x 12 row-pairs)
             if (lane < 24) {
                 const int half = lane >= 12 ? 1 : 0, rp = lane - 12 * half;
                 if (half * 8 < td.tw && 2 * rp < td.th + 7) {
@@ -753,29 +750,41 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                     dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
                 }
             }
-            if (lane < 12) {
-                const int pl = lane >= 6 ? 1 : 0, rp = lane - 6 * pl;
-                if (2 * rp < (td.th >> 1) + 3) {
+            // chroma, both stages in one pass of all 32 lanes (2 planes x 4 column pairs x 4 row groups, 2 columns x 2 rows each): a lane
+            // filters its 5 rows horizontally straight from the window and vertically from registers.  (As a separate horizontal pass the
+            // 12 row-pair tasks of the two planes kept 12 of 32 lanes busy and went through shared memory once more.)
+            {
+                const int pl = lane >> 4, cp = lane & 3, rg = (lane >> 2) & 3;
+                const int cw = td.tw >> 1, ch = td.th >> 1;
+                if (2 * cp < cw && 2 * rg < ch) {
                     const int offx = p.offs >> 4, par = offx & 1;
-                    const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1);
-                    const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
-                    const int sh = p.ctwo_d ? s1c : 6;
-                    int hv[2][8];
+                    const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1) + cp + (2 * rg) * kWinCStrideW;
+                    const Taps3 he = ld_taps3(p.cphx, par), ho = ld_taps3(p.cphx, par + 1);
+                    const int sh1 = p.ctwo_d ? s1c : 6;
+                    int h0[6], h1[6];
 #pragma unroll
-                    for (int rr = 0; rr < 2; rr++) {
-                        const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
-                        int q[6];
-#pragma unroll
-                        for (int j = 0; j < 6; j++) q[j] = rowp[j];
-#pragma unroll
-                        for (int o = 0; o < 4; o++) {
-                            hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
-                            hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
-                        }
+                    for (int r = 0; r < 5; r++) {
+                        const int q0 = win[r * kWinCStrideW], q1 = win[r * kWinCStrideW + 1], q2 = win[r * kWinCStrideW + 2];
+                        h0[r] = fir3(he, q0, q1, q2, 0) >> sh1;
+                        h1[r] = fir3(ho, q0, q1, q2, 0) >> sh1;
                     }
-                    int4 *dst = (int4 *)(s_m2c + (slot * 2 + pl) * kM2CWords + rp * kM2CStrideW);
-                    dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
-                    dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
+                    h0[5] = h1[5] = 0;              // weight 0 in the odd-row tap set
+                    int P[3][2];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) { P[j][0] = pack16(h0[2 * j], h0[2 * j + 1]); P[j][1] = pack16(h1[2 * j], h1[2 * j + 1]); }
+                    const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
+                    const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
+                    int e0 = fir3(te, P[0][0], P[1][0], 0, rnd) >> sh;
+                    int e1 = fir3(te, P[0][1], P[1][1], 0, rnd) >> sh;
+                    int o0 = fir3(to, P[0][0], P[1][0], P[2][0], rnd) >> sh;
+                    int o1 = fir3(to, P[0][1], P[1][1], P[2][1], rnd) >> sh;
+                    int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
+                    int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
+                    if (l == 0) { outc[0] = pe; outc[1] = po; }
+                    else {
+                        outc[0] = ((outc[0] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                        outc[1] = ((outc[1] + po + 0x00010001) >> 1) & 0x7fff7fff;
+                    }
                 }
             }
             __syncwarp();
@@ -808,30 +817,6 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                             outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
                             outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                         }
-                    }
-                }
-            }
-            // chroma: one lane = 2 columns x 2 rows (2 planes x 4 column pairs x 4 row groups)
-            {
-                const int pl = lane >> 4, cp = lane & 3, rg = (lane >> 2) & 3;
-                const int cw = td.tw >> 1, ch = td.th >> 1;
-                if (2 * cp < cw && 2 * rg < ch) {
-                    const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
-                    const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
-                    const int *m2 = s_m2c + (slot * 2 + pl) * kM2CWords + rg * kM2CStrideW + 2 * cp;
-                    int P[3][2];
-#pragma unroll
-                    for (int j = 0; j < 3; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
-                    int e0 = fir3(te, P[0][0], P[1][0], 0, rnd) >> sh;
-                    int e1 = fir3(te, P[0][1], P[1][1], 0, rnd) >> sh;
-                    int o0 = fir3(to, P[0][0], P[1][0], P[2][0], rnd) >> sh;
-                    int o1 = fir3(to, P[0][1], P[1][1], P[2][1], rnd) >> sh;
-                    int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
-                    int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
-                    if (l == 0) { outc[0] = pe; outc[1] = po; }
-                    else {
-                        outc[0] = ((outc[0] + pe + 0x00010001) >> 1) & 0x7fff7fff;
-                        outc[1] = ((outc[1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                     }
                 }
             }
@@ -912,33 +897,47 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                 dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
                 dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
             }
-            if (lane < 24) {
-                const int sidx = lane >= 12 ? 1 : 0, k = lane - 12 * sidx, pl = k >= 6 ? 1 : 0, rp = k - 6 * pl;
-                const int slot = 2 * warp + sidx;
+            // chroma, both stages in one pass (warp w's 32 threads are the vertical-stage threads of its own two slots): one thread =
+            // 2 columns x 4 rows of one plane; it filters its 7 rows horizontally straight from the window and vertically from registers
+            {
+                const int slot = tid >> 4, kk = tid & 15;
+                const int pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
                 if (slot < nt) {
                     const TileDesc td = s_tile[t0 + slot];
-                    if (l < td.nl && 2 * rp < (td.th >> 1) + 3) {
+                    const int cw = td.tw >> 1, ch = td.th >> 1;
+                    if (2 * cp < cw && 4 * rg < ch && l < td.nl) {
                         const TilePred p = s_pred[(t0 + slot) * NL + l];
                         const int offx = p.offs >> 4, par = offx & 1;
-                        const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1);
-                        const Taps3 te = ld_taps3(p.cphx, par), to = ld_taps3(p.cphx, par + 1);
-                        const int sh = p.ctwo_d ? s1c : 6;
-                        int hv[2][8];
+                        const int *win = (const int *)(smem + L.win_c + slot * kWinCBytes + pl * kWinCPlane) + (offx >> 1) + cp + (4 * rg) * kWinCStrideW;
+                        const Taps3 he = ld_taps3(p.cphx, par), ho = ld_taps3(p.cphx, par + 1);
+                        const int sh1 = p.ctwo_d ? s1c : 6;
+                        int h0[8], h1[8];
 #pragma unroll
-                        for (int rr = 0; rr < 2; rr++) {
-                            const int *rowp = win + (2 * rp + rr) * kWinCStrideW;
-                            int q[6];
+                        for (int r = 0; r < 7; r++) {
+                            const int q0 = win[r * kWinCStrideW], q1 = win[r * kWinCStrideW + 1], q2 = win[r * kWinCStrideW + 2];
+                            h0[r] = fir3(he, q0, q1, q2, 0) >> sh1;
+                            h1[r] = fir3(ho, q0, q1, q2, 0) >> sh1;
+                        }
+                        h0[7] = h1[7] = 0;              // weight 0 in the odd-row tap set
+                        int P[4][2];
 #pragma unroll
-                            for (int j = 0; j < 6; j++) q[j] = rowp[j];
+                        for (int j = 0; j < 4; j++) { P[j][0] = pack16(h0[2 * j], h0[2 * j + 1]); P[j][1] = pack16(h1[2 * j], h1[2 * j + 1]); }
+                        const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
+                        const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
 #pragma unroll
-                            for (int o = 0; o < 4; o++) {
-                                hv[rr][2 * o] = fir3(te, q[o], q[o + 1], q[o + 2], 0) >> sh;
-                                hv[rr][2 * o + 1] = fir3(to, q[o], q[o + 1], q[o + 2], 0) >> sh;
+                        for (int q = 0; q < 2; q++) {
+                            int e0 = fir3(te, P[q][0], P[q + 1][0], 0, rnd) >> sh;
+                            int e1 = fir3(te, P[q][1], P[q + 1][1], 0, rnd) >> sh;
+                            int o0 = fir3(to, P[q][0], P[q + 1][0], P[q + 2][0], rnd) >> sh;
+                            int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
+                            int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
+                            int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
+                            if (l == 0) { outc[2 * q] = pe; outc[2 * q + 1] = po; }
+                            else {
+                                outc[2 * q] = ((outc[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
+                                outc[2 * q + 1] = ((outc[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                             }
                         }
-                        int4 *dst = (int4 *)(s_m2c + (slot * 2 + pl) * kM2CWords + rp * kM2CStrideW);
-                        dst[0] = make_int4(pack16(hv[0][0], hv[1][0]), pack16(hv[0][1], hv[1][1]), pack16(hv[0][2], hv[1][2]), pack16(hv[0][3], hv[1][3]));
-                        dst[1] = make_int4(pack16(hv[0][4], hv[1][4]), pack16(hv[0][5], hv[1][5]), pack16(hv[0][6], hv[1][6]), pack16(hv[0][7], hv[1][7]));
                     }
                 }
             }
@@ -975,38 +974,6 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
                             else {      // two clipped, non-negative predictions
                                 outp[2 * q] = ((outp[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
                                 outp[2 * q + 1] = ((outp[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
-                            }
-                        }
-                    }
-                }
-            }
-            // chroma: one thread = 2 columns x 4 rows, 16 threads per slot (2 planes x 4 column pairs x 2 row groups)
-            {
-                const int slot = tid >> 4, kk = tid & 15;
-                const int pl = kk >> 3, cp = kk & 3, rg = (kk >> 2) & 1;
-                if (slot < nt) {
-                    const TileDesc td = s_tile[t0 + slot];
-                    const int cw = td.tw >> 1, ch = td.th >> 1;
-                    if (2 * cp < cw && 4 * rg < ch && l < td.nl) {
-                        const TilePred p = s_pred[(t0 + slot) * NL + l];
-                        const Taps3 te = ld_taps3(p.cphy, 0), to = ld_taps3(p.cphy, 1);
-                        const int sh = p.ctwo_d ? s2c : 6, rnd = p.ctwo_d ? (1 << (s2c - 1)) : 0;
-                        const int *m2 = s_m2c + (slot * 2 + pl) * kM2CWords + (2 * rg) * kM2CStrideW + 2 * cp;
-                        int P[4][2];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) { const int2 v = *(const int2 *)(m2 + j * kM2CStrideW); P[j][0] = v.x; P[j][1] = v.y; }
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            int e0 = fir3(te, P[q][0], P[q + 1][0], 0, rnd) >> sh;
-                            int e1 = fir3(te, P[q][1], P[q + 1][1], 0, rnd) >> sh;
-                            int o0 = fir3(to, P[q][0], P[q + 1][0], P[q + 2][0], rnd) >> sh;
-                            int o1 = fir3(to, P[q][1], P[q + 1][1], P[q + 2][1], rnd) >> sh;
-                            int pe = __vimin_s16x2_relu(pack16(e0, e1), maxc2);
-                            int po = __vimin_s16x2_relu(pack16(o0, o1), maxc2);
-                            if (l == 0) { outc[2 * q] = pe; outc[2 * q + 1] = po; }
-                            else {
-                                outc[2 * q] = ((outc[2 * q] + pe + 0x00010001) >> 1) & 0x7fff7fff;
-                                outc[2 * q + 1] = ((outc[2 * q + 1] + po + 0x00010001) >> 1) & 0x7fff7fff;
                             }
                         }
                     }
