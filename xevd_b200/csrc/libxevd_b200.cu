@@ -312,9 +312,9 @@ static int make_tensor_maps(xb200_ctx *c, xb200_pic *p)
         encode = (PFN_encodeTiled)fn;
     }
     // maps[0]: luma plane (2-D).  maps[1]: Cb and Cr as one 3-D tensor (x, y, plane) - the planes have the same geometry and lie
-    // chroma_elems apart, so one TMA instruction fetches a tile's two chroma windows.  maps[2]: Cr alone (2-D, kept for tools).
-    alignas(64) CUtensorMap maps[3];
-    for (int pl = 0; pl < 3; pl++) {
+    // chroma_elems apart, so one TMA instruction fetches a tile's two chroma windows.  maps[2], maps[3]: Cr / Cb alone (2-D; xb200_mc_blocks_dev).
+    alignas(64) CUtensorMap maps[4];
+    for (int pl = 0; pl < 4; pl++) {
         const bool luma = pl == 0, both = pl == 1;
         void *base = luma ? (void *)p->buf : (void *)(p->buf + p->luma_elems + (pl == 2 ? p->chroma_elems : 0));
         const cuuint64_t dims[3] = {(cuuint64_t)(luma ? p->s_l : p->s_c), (cuuint64_t)(luma ? p->h + 2 * p->pad_l : p->h_c + 2 * p->pad_c), 2};
@@ -350,7 +350,7 @@ xb200_pic *xb200_pic_alloc(xb200_ctx *c, int w, int h, int *err)
     const size_t nscu = (size_t)p->w_scu * p->h_scu;
     const size_t pix_bytes = (p->luma_elems + 2 * p->chroma_elems) * sizeof(pel);
     const size_t pix_al = (pix_bytes + 255) & ~(size_t)255;
-    const size_t total = pix_al + ((nscu * 26 + 255) & ~(size_t)255) + 3 * sizeof(CUtensorMap) + 256;
+    const size_t total = pix_al + ((nscu * 26 + 255) & ~(size_t)255) + 4 * sizeof(CUtensorMap) + 256;
     if (cudaMalloc((void **)&p->buf, total) != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu) failed", total);
         delete p;
@@ -1123,9 +1123,9 @@ int xb200_mc_blocks_dev(xb200_ctx *c, xb200_pic *ref, int plane, const void *d_m
 {
     if (!c || !ref || !d_mv || !d_out || n <= 0 || plane < 0 || plane > 2) return XB200_ERR_INVALID_ARGUMENT;
     cudaSetDevice(c->device);
-    const pel *base = plane == 0 ? ref->y : (plane == 1 ? ref->u : ref->v);
-    int r = xb::launch_mc_blocks(base, plane == 0 ? ref->s_l : ref->s_c, plane != 0, (const int *)d_mv, (pel *)d_out, n, w, h, bit_depth,
-                                 main_tables, c->stream);
+    if (bit_depth < 8 || bit_depth > 14 || ((uintptr_t)d_out & 3)) return XB200_ERR_INVALID_ARGUMENT;
+    int r = xb::launch_mc_blocks(ref->d_tmaps + (plane == 0 ? 0 : (plane == 1 ? 3 : 2)), plane ? ref->pad_c : ref->pad_l, plane, (const int *)d_mv, (pel *)d_out, n, w, h,
+                                 bit_depth, main_tables != 0, c->stream);
     if (r < 0) return r;
     c->launches += r;
     CK(c, cudaGetLastError());
