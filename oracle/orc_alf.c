@@ -1,8 +1,10 @@
 /*
  * Adaptive loop filter (Main profile).  TEST INFRASTRUCTURE ONLY (orc_common.h).
- * Restates, for a picture that is one tile:
+ * Restates:
  *   per-CTU window with 3-sample margins  alf_process_tile            src_main/xevdm_alf.c:901-1165 (T9: mirrored margins)
- *   picture copy with replicated border   alf_copy_and_extend_tile    :805-840
+ *   per-TILE copy with replicated border  alf_copy_and_extend_tile    :805-840 (a window never reads another tile)
+ *   which sides of a CTU take the copy    tile_boundary_check         :844-881, called with the tile (flag 0) or with
+ *                                                                     (0, width - 1, 0, height - 1) (flag 1), :989-999
  *   4x4 block classification              alf_derive_classification_blk :38-208
  *   7x7 diamond luma / 5x5 diamond chroma alf_filter_blk_7 / _5       :210-429
  * Every CTU filters from a copy of the pre-ALF picture, so CTUs are independent.
@@ -15,12 +17,13 @@ typedef struct {
     const pel *p;        /* pre-ALF plane copy, sample (0,0) */
     int s, W, H;         /* stride, plane size                */
     int x0, y0, w, h;    /* CTU rectangle in this plane        */
-    int aL, aR, aT, aB;  /* neighbour CTU exists               */
+    int aL, aR, aT, aB;  /* the side's margin comes from the (extended) tile copy; else it mirrors the CTU */
+    int tx0, tx1, ty0, ty1;   /* the CTU's tile in this plane */
 } Win;
 
-static pel ext(const Win *k, int y, int x)          /* the copy is extended by replication (alf_copy_and_extend_tile) */
+static pel ext(const Win *k, int y, int x)          /* the tile's copy is extended by replication (alf_copy_and_extend_tile) */
 {
-    y = orc_clip3(0, k->H - 1, y); x = orc_clip3(0, k->W - 1, x);
+    y = orc_clip3(k->ty0, k->ty1 - 1, y); x = orc_clip3(k->tx0, k->tx1 - 1, x);
     return k->p[y * k->s + x];
 }
 
@@ -106,7 +109,15 @@ int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, c
     for (int y0 = 0, n = 0; y0 < H; y0 += ctu)
         for (int x0 = 0; x0 < W; x0 += ctu, n++) {
             const int w = orc_min(ctu, W - x0), h = orc_min(ctu, H - y0);
-            Win k = {cy, W, W, H, x0, y0, w, h, x0 > 0, x0 + w < W, y0 > 0, y0 + h < H};
+            const ORC_TILES *tl = orc_tiles();
+            int tc = 0, tr = 0;
+            while (tc + 1 < tl->n_cols && (x0 >> prm->log2_ctu) >= tl->col_bd[tc + 1]) tc++;
+            while (tr + 1 < tl->n_rows && (y0 >> prm->log2_ctu) >= tl->row_bd[tr + 1]) tr++;
+            const int tx0 = tl->col_bd[tc] << prm->log2_ctu, ty0 = tl->row_bd[tr] << prm->log2_ctu;
+            const int tx1 = orc_min((int)tl->col_bd[tc + 1] << prm->log2_ctu, W), ty1 = orc_min((int)tl->row_bd[tr + 1] << prm->log2_ctu, H);
+            Win k = {cy, W, W, H, x0, y0, w, h, 0, 0, 0, 0, tx0, tx1, ty0, ty1};
+            if (tl->across) { k.aL = x0 != 0; k.aR = 1; k.aT = y0 != 0; k.aB = 1; }       /* x_pos + width is never width - 1 */
+            else { k.aL = x0 != tx0; k.aR = x0 + w != tx1; k.aT = y0 != ty0; k.aB = y0 + h != ty1; }
             (void)wc;
             if (alf->enable[0] && (!ctb_flag_luma || ctb_flag_luma[n]))
                 for (int by = 0; by < h; by += 4)
@@ -114,7 +125,7 @@ int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, c
                         filter_luma_blk(&k, by, bx, classify(&k, by, bx, prm->bit_depth_luma), alf->coef_luma, pic->y, pic->s_l, maxv);
             for (int c = 1; c < 3; c++) {
                 if (!alf->enable[c]) continue;
-                Win kc = {c == 1 ? cu : cv, W / 2, W / 2, H / 2, x0 / 2, y0 / 2, w / 2, h / 2, k.aL, k.aR, k.aT, k.aB};
+                Win kc = {c == 1 ? cu : cv, W / 2, W / 2, H / 2, x0 / 2, y0 / 2, w / 2, h / 2, k.aL, k.aR, k.aT, k.aB, tx0 / 2, tx1 / 2, ty0 / 2, ty1 / 2};
                 filter_chroma_ctu(&kc, alf->coef_chroma, c == 1 ? pic->u : pic->v, pic->s_c, maxv);
             }
         }

@@ -106,6 +106,13 @@ void orc_dra_apply(ORC_PIC *pic, const XB200_DRA *d);
 void orc_output(const ORC_PIC *pic, int out_bits, int crop_l, int crop_r, int crop_t, int crop_b, void *y, int sy, void *u, int su, void *v, int sv);
 
 /* orc_alf.c */
+/* PPS tile grid for the two loop filters that follow (xb200_set_tiles has the same arguments): column / row boundaries in CTUs and
+ * pps.loop_filter_across_tiles_enabled_flag; n_cols == n_rows == 1 = one tile (the initial state) */
+typedef struct { int n_cols, n_rows, across; uint16_t col_bd[XB200_MAX_TILE_COLS + 1], row_bd[XB200_MAX_TILE_ROWS + 1]; } ORC_TILES;
+void orc_set_tiles(int n_cols, const uint16_t *col_bd, int n_rows, const uint16_t *row_bd, int across);
+const ORC_TILES *orc_tiles(void);
+/* 1 when luma position `pos` (x for vertical edges, y for horizontal ones) lies on a boundary between two tiles */
+int orc_on_tile_boundary(const ORC_TILES *t, int log2_ctu, int pos, int vertical);
 int orc_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *alf, const uint8_t *ctb_flag_luma);
 
 /* orc_df.c */

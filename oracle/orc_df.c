@@ -120,17 +120,40 @@ static void edge_segment(DfCtx *c, int cur, int nb, int x, int y, int vertical)
     }
 }
 
+/* ---- PPS tile grid shared by the loop-filter restatements (orc_set_tiles) ------------------------------------------------------ */
+static ORC_TILES g_tiles = {1, 1, 0, {0, 0xffff}, {0, 0xffff}};
+void orc_set_tiles(int n_cols, const uint16_t *col_bd, int n_rows, const uint16_t *row_bd, int across)
+{
+    g_tiles.n_cols = n_cols; g_tiles.n_rows = n_rows; g_tiles.across = across != 0;
+    for (int i = 0; i <= n_cols; i++) g_tiles.col_bd[i] = col_bd[i];
+    for (int i = 0; i <= n_rows; i++) g_tiles.row_bd[i] = row_bd[i];
+}
+const ORC_TILES *orc_tiles(void) { return &g_tiles; }
+int orc_on_tile_boundary(const ORC_TILES *t, int log2_ctu, int pos, int vertical)
+{
+    if (pos & ((1 << log2_ctu) - 1)) return 0;
+    const int c = pos >> log2_ctu, n = vertical ? t->n_cols : t->n_rows;
+    const uint16_t *bd = vertical ? t->col_bd : t->row_bd;
+    for (int i = 1; i < n; i++) if (bd[i] == c) return 1;
+    return 0;
+}
+/* an edge between two tiles is filtered only with loop_filter_across_tiles_enabled_flag (no_boundary, xevdm_df.c:142,233,274,877,1088,1106) */
+static int tile_cut(const XB200_PARAMS *prm, int pos, int vertical)
+{
+    return !g_tiles.across && orc_on_tile_boundary(&g_tiles, prm->log2_ctu, pos, vertical);
+}
+
 static void visit(DfCtx *c, int x, int y, int w, int h, int pass)
 {
     ORC_PIC *p = c->pic;
     const int ws = p->w_scu, sx = x >> 2, sy = y >> 2, nw = w >> 2, nh = h >> 2;
     const int t = sy * ws + sx;
     if (pass == 0) {
-        if (x > 0 && c->cod[t - 1])
+        if (x > 0 && c->cod[t - 1] && !tile_cut(c->prm, x, 1))
             for (int i = 0; i < nh; i++) edge_segment(c, t + i * ws, t + i * ws - 1, x, y + 4 * i, 1);
-        if (x + w < p->w_l && c->cod[t + nw])
+        if (x + w < p->w_l && c->cod[t + nw] && !tile_cut(c->prm, x + w, 1))
             for (int i = 0; i < nh; i++) edge_segment(c, t + i * ws + nw, t + i * ws + nw - 1, x + w, y + 4 * i, 1);
-    } else if (y > 0) {
+    } else if (y > 0 && !tile_cut(c->prm, y, 0)) {
         for (int i = 0; i < nw; i++) edge_segment(c, t + i, t + i - ws, x + 4 * i, y, 0);
     }
     for (int j = 0; j < nh; j++) memset(c->cod + t + j * ws, 1, nw);
@@ -295,11 +318,11 @@ static void addb_visit(AddbCtx *c, int x, int y, int w, int h, int pass)
     const int ws = p->w_scu, sx = x >> 2, sy = y >> 2, nw = w >> 2, nh = h >> 2;
     const int t = sy * ws + sx;
     if (pass == 0) {
-        if ((x & 7) == 0 && x > 0 && c->cod[t - 1])
+        if ((x & 7) == 0 && x > 0 && c->cod[t - 1] && !tile_cut(c->prm, x, 1))
             for (int i = 0; i < nh; i++) addb_segment(c, t + i * ws, t + i * ws - 1, x, y + 4 * i, 1);
-        if (((x + w) & 7) == 0 && x + w < p->w_l && c->cod[t + nw])
+        if (((x + w) & 7) == 0 && x + w < p->w_l && c->cod[t + nw] && !tile_cut(c->prm, x + w, 1))
             for (int i = 0; i < nh; i++) addb_segment(c, t + i * ws + nw, t + i * ws + nw - 1, x + w, y + 4 * i, 1);
-    } else if ((y & 7) == 0 && y > 0) {
+    } else if ((y & 7) == 0 && y > 0 && !tile_cut(c->prm, y, 0)) {
         for (int i = 0; i < nw; i++) addb_segment(c, t + i, t + i - ws, x + 4 * i, y, 0);
     }
     for (int j = 0; j < nh; j++) memset(c->cod + t + j * ws, 1, nw);

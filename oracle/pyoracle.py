@@ -132,6 +132,15 @@ class _Backend:
             raise RuntimeError(f"{self.prefix}recon_frame failed: {r}")
         return cur
 
+    def set_tiles(self, col_bd=None, row_bd=None, across: bool = False):
+        """PPS tile grid for deblock_frame / alf_frame: column / row boundaries in CTUs (None: one tile)"""
+        cb = np.ascontiguousarray(col_bd if col_bd is not None else [0, 0xffff], np.uint16)
+        rb = np.ascontiguousarray(row_bd if row_bd is not None else [0, 0xffff], np.uint16)
+        fn = getattr(self.lib, self.prefix + "set_tiles")
+        fn.restype = None
+        fn.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        fn(len(cb) - 1, cb.ctypes.data, len(rb) - 1, rb.ctypes.data, int(across))
+
     def deblock_frame(self, prm: Params, pic: HostPicture, cl: CuList, chroma_qp_tbl: np.ndarray, tool_addb: bool = False,
                       ref_ids=((0, 1, 2, 3), (0, 1, 2, 3))):
         """both deblocking passes in place on `pic` (uses pic.map_scu / map_mv / map_refi).  ref_ids[l][i] identifies the

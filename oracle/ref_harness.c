@@ -444,6 +444,24 @@ void ref_pad(ORC_PIC *pic)
  * Mirrors xevdm_deblock + deblock_tree's leaves (src_main/xevdm.c:1935-2103) for one tile / one slice: COD bits cleared,
  * every CU visited in decoding order by xevdm_deblock_cu_ver (pass 1) then xevdm_deblock_cu_hor (pass 2), CUs larger than
  * MAX_TR_SIZE visited as two halves. */
+/* PPS tile grid for ref_deblock_frame / ref_alf_frame (same arguments as xb200_set_tiles / orc_set_tiles) */
+static struct { int n_cols, n_rows, across; uint16_t col_bd[XB200_MAX_TILE_COLS + 1], row_bd[XB200_MAX_TILE_ROWS + 1]; } g_ref_tiles = {1, 1, 0, {0, 0xffff}, {0, 0xffff}};
+void ref_set_tiles(int n_cols, const uint16_t *col_bd, int n_rows, const uint16_t *row_bd, int across)
+{
+    int i;
+    g_ref_tiles.n_cols = n_cols; g_ref_tiles.n_rows = n_rows; g_ref_tiles.across = across != 0;
+    for (i = 0; i <= n_cols; i++) g_ref_tiles.col_bd[i] = col_bd[i];
+    for (i = 0; i <= n_rows; i++) g_ref_tiles.row_bd[i] = row_bd[i];
+}
+/* tile index of the CTU at (cx, cy) in CTU units, as set_tile_info numbers them (src_main/xevdm.c:2275-2327) */
+static int ref_tile_of(int cx, int cy)
+{
+    int tc = 0, tr = 0;
+    while (tc + 1 < g_ref_tiles.n_cols && cx >= g_ref_tiles.col_bd[tc + 1]) tc++;
+    while (tr + 1 < g_ref_tiles.n_rows && cy >= g_ref_tiles.row_bd[tr + 1]) tr++;
+    return tr * g_ref_tiles.n_cols + tc;
+}
+
 int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus, int n_cu, const int *chroma_qp_tbl, int tool_addb,
                       const int *ref_id_l0, int n_l0, const int *ref_id_l1, int n_l1)
 {
@@ -478,6 +496,8 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
     ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu; ctx->w = pic->w_l; ctx->h = pic->h_l;
     ctx->log2_max_cuwh = prm->log2_ctu;
     ctx->map_tidx = (u8 *)calloc(f_scu, 1);
+    for (i = 0; i < f_scu; i++)        /* what set_tile_info writes (src_main/xevdm.c:2298-2320) */
+        ctx->map_tidx[i] = (u8)ref_tile_of(((i % pic->w_scu) << 2) >> prm->log2_ctu, ((i / pic->w_scu) << 2) >> prm->log2_ctu);
     ctx->map_cu_mode = (u32 *)calloc(f_scu, sizeof(u32));
     m->map_ats_inter = (u8 *)calloc(f_scu, 1);
     if (prm->tool_ats)          /* what xevdm_set_dec_info leaves in map_ats_inter (src_main/xevdm_util.c:4307-4311) */
@@ -511,13 +531,13 @@ int ref_deblock_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_CU *cus
                 const int parts = w > MAX_TR_SIZE ? 2 : 1;
                 for (i = 0; i < parts; i++)
                     xevdm_deblock_cu_ver(ctx, &xp, x + i * MAX_TR_SIZE, y, w / parts, h, ctx->map_scu, ctx->map_refi, m->map_unrefined_mv, ctx->w_scu,
-                                         ctx->log2_max_cuwh, ctx->map_cu_mode, ctx->refp, 0, tc, ctx->map_tidx, 0, tool_addb, m->map_ats_inter,
+                                         ctx->log2_max_cuwh, ctx->map_cu_mode, ctx->refp, 0, tc, ctx->map_tidx, g_ref_tiles.across, tool_addb, m->map_ats_inter,
                                          prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
             } else {
                 const int parts = h > MAX_TR_SIZE ? 2 : 1;
                 for (i = 0; i < parts; i++)
                     xevdm_deblock_cu_hor(ctx, &xp, x, y + i * MAX_TR_SIZE, w, h / parts, ctx->map_scu, ctx->map_refi, m->map_unrefined_mv, ctx->w_scu,
-                                         ctx->log2_max_cuwh, ctx->refp, 0, tc, ctx->map_tidx, 0, tool_addb, m->map_ats_inter,
+                                         ctx->log2_max_cuwh, ctx->refp, 0, tc, ctx->map_tidx, g_ref_tiles.across, tool_addb, m->map_ats_inter,
                                          prm->bit_depth_luma, prm->bit_depth_chroma, prm->chroma_format_idc);
             }
         }
@@ -571,10 +591,21 @@ int ref_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *ap, co
     ctx->w = pic->w_l; ctx->h = pic->h_l; ctx->w_scu = pic->w_scu; ctx->h_scu = pic->h_scu;
     ctx->log2_max_cuwh = prm->log2_ctu; ctx->max_cuwh = ctu;
     ctx->w_lcu = (pic->w_l + ctu - 1) / ctu; ctx->h_lcu = (pic->h_l + ctu - 1) / ctu; ctx->f_lcu = ctx->w_lcu * ctx->h_lcu;
-    ctx->w_tile = ctx->h_tile = 1;
-    ctx->tile = (XEVD_TILE *)calloc(1, sizeof(XEVD_TILE));
-    ctx->tile[0].ctba_rs_first = 0; ctx->tile[0].w_ctb = ctx->w_lcu; ctx->tile[0].h_ctb = ctx->h_lcu;
-    ctx->pps.loop_filter_across_tiles_enabled_flag = 0;
+    {   /* the tile array as set_tile_info builds it (src_main/xevdm.c:2275-2296); a grid that was never set is one tile */
+        const int nc = g_ref_tiles.n_cols, nr = g_ref_tiles.n_rows;
+        int tx, ty;
+        ctx->w_tile = nc; ctx->h_tile = nr;
+        ctx->tile = (XEVD_TILE *)calloc((size_t)nc * nr, sizeof(XEVD_TILE));
+        for (ty = 0; ty < nr; ty++)
+            for (tx = 0; tx < nc; tx++) {
+                XEVD_TILE *t = &ctx->tile[ty * nc + tx];
+                const int c0 = g_ref_tiles.col_bd[tx], c1 = tx + 1 == nc ? ctx->w_lcu : g_ref_tiles.col_bd[tx + 1];
+                const int r0 = g_ref_tiles.row_bd[ty], r1 = ty + 1 == nr ? ctx->h_lcu : g_ref_tiles.row_bd[ty + 1];
+                t->ctba_rs_first = r0 * ctx->w_lcu + c0; t->w_ctb = (u16)(c1 - c0); t->h_ctb = (u16)(r1 - r0); t->f_ctb = t->w_ctb * t->h_ctb;
+            }
+        ctx->pps.num_tile_columns_minus1 = nc - 1; ctx->pps.num_tile_rows_minus1 = nr - 1;
+        ctx->pps.loop_filter_across_tiles_enabled_flag = g_ref_tiles.across;
+    }
     wrap_pic(pic, &xp);
     cs.ctx = ctx; cs.pic = &xp;
     alf = new_alf(prm->bit_depth_luma);
@@ -589,8 +620,10 @@ int ref_alf_frame(const XB200_PARAMS *prm, ORC_PIC *pic, const XB200_ALF *ap, co
         sp->alf_ctb_flag[2 * ctx->f_lcu + i] = ap->enable[2];
     }
     for (c = 0; c < 3; c++) alf->ctu_enable_flag[c] = sp->alf_ctb_flag + ctx->f_lcu * c;
-    tmp.alf = alf; tmp.cs = &cs; tmp.alf_slice_param = sp; tmp.tile_idx = 0; tmp.tsk_num = 0;
-    alf_process_tile(&tmp);
+    for (i = 0; i < ctx->w_tile * ctx->h_tile; i++) {       /* alf_process (:1203-1247) runs the tiles one after the other */
+        tmp.alf = alf; tmp.cs = &cs; tmp.alf_slice_param = sp; tmp.tile_idx = i; tmp.tsk_num = 0;
+        alf_process_tile(&tmp);
+    }
     xevd_alf_destroy(alf); delete_alf(alf);
     free(sp->alf_ctb_flag); free(sp); free(ctx->tile); free(m);
     return XB200_OK;

@@ -207,6 +207,67 @@ def test_deblock_main_partitions(ctx, oracle, kw, bd, addb):
         assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
 
 
+@pytest.mark.parametrize("across", [0, 1])
+@pytest.mark.parametrize("kw,bd,addb,grid", [({}, 10, 1, (2, 2)), (dict(log2_ctu=5), 8, 1, (3, 2)), ({}, 10, 0, (2, 2)), (dict(log2_ctu=5), 10, 0, (4, 3)),
+                                             (dict(log2_ctu=7), 8, 0, (2, 1))])
+def test_deblock_tiles(ctx, oracle, kw, bd, addb, grid, across):
+    """pictures of several tiles (xb200_set_tiles): tile-boundary edges are filtered only with loop_filter_across_tiles_enabled_flag;
+    the oracle's rule is pinned to the reference's deblock functions in tests/test_oracle_vs_ref.py::test_deblock_tiles"""
+    from tests.test_oracle_vs_ref import deblock_main_inputs, tile_grid
+    w, h, prm, cl, base, tbl, ids = deblock_main_inputs(oracle, kw, bd, addb)
+    cb, rb = tile_grid(w, h, prm.log2_ctu, *grid)
+    oracle.set_tiles(cb, rb, bool(across))
+    try:
+        want = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    finally:
+        oracle.set_tiles()
+    pics = [ctx.pic_alloc(w, h) for _ in range(3)]
+    d = ctx.pic_alloc(w, h).upload(base, padded=False).upload_maps(base, cl.edge_flags())
+    ctx.set_chroma_qp_table(tbl)
+    ctx.set_tiles(cb, rb, across=bool(across))
+    try:
+        ctx.deblock(prm, d, [pics[0], pics[1], pics[0]], [pics[2], pics[1], pics[0]])
+        got = d.download()
+    finally:
+        ctx.set_tiles()
+        ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
+        for p in pics + [d]:
+            p.free()
+    for a, b, n in zip(got.planes(), want.planes(), "YUV"):
+        assert np.array_equal(a, b), f"plane {n}: {int((a != b).sum())} samples differ"
+
+
+@pytest.mark.parametrize("across", [0, 1])
+@pytest.mark.parametrize("w,h,bd,log2_ctu,grid", [(256, 136, 10, 6, (2, 2)), (200, 120, 8, 5, (3, 2)), (384, 256, 10, 7, (3, 1)), (320, 192, 10, 5, (4, 4)),
+                                                  (1920, 1080, 10, 6, (4, 3))])
+def test_alf_tiles(ctx, oracle, w, h, bd, log2_ctu, grid, across):
+    """ALF on pictures of several tiles, both values of the flag, against the oracle (pinned to alf_process_tile in
+    tests/test_oracle_vs_ref.py::test_alf_tiles)"""
+    from tests.test_oracle_vs_ref import tile_grid
+    rng = np.random.default_rng(w + h + bd + across)
+    p = HostPicture.random(w, h, bd, rng)
+    prm = abi.make_params(w, h, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+    alf = synth.make_alf_params(rng, (1, 1, 1))
+    n_ctu = ((w + (1 << log2_ctu) - 1) >> log2_ctu) * ((h + (1 << log2_ctu) - 1) >> log2_ctu)
+    flags = (rng.random(n_ctu) < 0.8).astype(np.uint8)
+    cb, rb = tile_grid(w, h, log2_ctu, *grid)
+    oracle.set_tiles(cb, rb, bool(across))
+    try:
+        want = oracle.alf_frame(prm, p.copy(), alf, flags)
+    finally:
+        oracle.set_tiles()
+    d = ctx.pic_alloc(w, h).upload(p, padded=False)
+    ctx.set_tiles(cb, rb, across=bool(across))
+    try:
+        ctx.alf(prm, d, alf, flags)
+        got = d.download()
+    finally:
+        ctx.set_tiles()
+        d.free()
+    for pa, pb, name in zip(got.planes(), want.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()), np.argwhere(pa != pb)[:5].tolist())
+
+
 @pytest.mark.parametrize("bd,addb,kw", [(10, 0, {}), (8, 0, dict(log2_ctu=5)), (10, 0, dict(log2_ctu=7)), (10, 1, {}), (10, 0, dict(suco=False))])
 def test_deblock_suco_order_4wide(ctx, oracle, bd, addb, kw):
     """recon -> deblock on binary/ternary partitions down to 4-wide CUs in SUCO order: neighbouring chroma edges are 2 samples apart, each

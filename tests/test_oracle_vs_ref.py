@@ -281,6 +281,61 @@ def test_deblock_main_partitions(oracle, reference, kw, bd, addb):
         assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
 
 
+def tile_grid(w, h, log2_ctu, n_cols, n_rows):
+    """uniform tile spacing as set_tile_info computes it (src_main/xevdm.c:2247-2258)"""
+    wc, hc = (w + (1 << log2_ctu) - 1) >> log2_ctu, (h + (1 << log2_ctu) - 1) >> log2_ctu
+    return [i * wc // n_cols for i in range(n_cols + 1)], [j * hc // n_rows for j in range(n_rows + 1)]
+
+
+@pytest.mark.parametrize("across", [0, 1])
+@pytest.mark.parametrize("kw,bd,addb,grid", [({}, 10, 1, (2, 2)), (dict(log2_ctu=5), 8, 1, (3, 2)), ({}, 10, 0, (2, 2)), (dict(log2_ctu=5, min_log2=2), 10, 0, (4, 3)),
+                                             (dict(log2_ctu=7), 8, 0, (2, 1))])
+def test_deblock_tiles(oracle, reference, kw, bd, addb, grid, across):
+    """pictures of several tiles: an edge between two tiles is filtered only with loop_filter_across_tiles_enabled_flag
+    (map_tidx tests of xevdm_df.c:142,233,274,877,1088,1106), both filters, SUCO partitions down to 4-wide CUs"""
+    w, h, prm, cl, base, tbl, ids = deblock_main_inputs(oracle, kw, bd, addb)
+    cb, rb = tile_grid(w, h, prm.log2_ctu, *grid)
+    one = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    for o in (oracle, reference):
+        o.set_tiles(cb, rb, bool(across))
+    try:
+        a = oracle.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+        b = reference.deblock_frame(prm, base.copy(), cl, tbl, bool(addb), ids)
+    finally:
+        for o in (oracle, reference):
+            o.set_tiles()
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()))
+    differs = sum(int((x != y).sum()) for x, y in zip(a.planes(), one.planes()))
+    assert (differs == 0) if across else (differs > 50), "the tile boundaries of the test picture carry no filtered edge"
+
+
+@pytest.mark.parametrize("across", [0, 1])
+@pytest.mark.parametrize("w,h,bd,log2_ctu,grid", [(256, 136, 10, 6, (2, 2)), (200, 120, 8, 5, (3, 2)), (384, 256, 10, 7, (3, 1)), (320, 192, 10, 5, (4, 4))])
+def test_alf_tiles(oracle, reference, w, h, bd, log2_ctu, grid, across):
+    """ALF on pictures of several tiles (alf_process_tile per tile): windows from the tile's own extended copy, margins mirrored at tile
+    borders without the flag, replicated with it (and then mirrored only at the picture's left and top)"""
+    rng = np.random.default_rng(w + h + bd + across)
+    p = HostPicture.random(w, h, bd, rng)
+    prm = __import__("xevd_b200.abi", fromlist=["make_params"]).make_params(w, h, bit_depth=bd, log2_ctu=log2_ctu, tool_alf=1)
+    alf = synth.make_alf_params(rng, (1, 1, 1))
+    n_ctu = ((w + (1 << log2_ctu) - 1) >> log2_ctu) * ((h + (1 << log2_ctu) - 1) >> log2_ctu)
+    flags = (rng.random(n_ctu) < 0.8).astype(np.uint8)
+    cb, rb = tile_grid(w, h, log2_ctu, *grid)
+    one = oracle.alf_frame(prm, p.copy(), alf, flags)
+    for o in (oracle, reference):
+        o.set_tiles(cb, rb, bool(across))
+    try:
+        a = oracle.alf_frame(prm, p.copy(), alf, flags)
+        b = reference.alf_frame(prm, p.copy(), alf, flags)
+    finally:
+        for o in (oracle, reference):
+            o.set_tiles()
+    for pa, pb, name in zip(a.planes(), b.planes(), "yuv"):
+        assert np.array_equal(pa, pb), (name, int((pa != pb).sum()), np.argwhere(pa != pb)[:4].tolist())
+    assert sum(int((x != y).sum()) for x, y in zip(a.planes(), one.planes())) > 100, "tile borders change nothing in this picture"
+
+
 def dual_tree_inputs(variant, kw, bd, eipd, htdf, intra_frac=1.0, ibc=0.0):
     w, h = 256, 136
     prm, cl = synth.make_inter_frame(w, h, bit_depth=bd, variant=variant, seed=81, n_refs=2, coded_frac=0.7, **kw)
