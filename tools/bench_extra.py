@@ -346,23 +346,28 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
                     whole, per_pic = [], []
                     for _ in range(3):
                         with X.Decoder(lib) as d:               # xevd_create / xevd_delete outside the timed region
-                            t_all, n = 0.0, 0
-                            for nal in nals:
-                                t0 = time.perf_counter()
-                                ret, stat = d.decode(nal)
-                                got = 0
-                                while d.pull() is not None:
-                                    got += 1
-                                dt = time.perf_counter() - t0
-                                t_all += dt
-                                n += got
-                                if got and n > 2:
-                                    per_pic.append(dt / got)
-                            whole.append(n / t_all)
+                            # the stream is fed three times to the same instance (it starts with an IDR picture): the first pass pays the
+                            # sequence set-up (picture buffers, page-locking, staging), passes two and three are the steady state
+                            for rep in range(3):
+                                t_all, n = 0.0, 0
+                                for nal in nals:
+                                    t0 = time.perf_counter()
+                                    ret, stat = d.decode(nal)
+                                    got = 0
+                                    while d.pull() is not None:
+                                        got += 1
+                                    dt = time.perf_counter() - t0
+                                    t_all += dt
+                                    n += got
+                                    if got and rep > 0:
+                                        per_pic.append(dt / got)
+                                if rep == 0:
+                                    whole.append(n / t_all)
                     res[tag] = {"whole_stream": round(float(np.median(whole)), 1), "steady_state": round(1.0 / float(np.median(per_pic)), 1)}
                 out.append({"workload": f"stream-{name}", "passes": "xevd_create / xevd_decode / xevd_pull on a generated elementary stream: entropy decoding and motion derivation on ONE host "
-                            "thread in both libraries (the reference's own code); libxevd_gpu.so reconstructs on the device and copies every picture back. whole_stream includes the "
-                            "sequence set-up of an 8-picture stream (picture buffers, page-locking), steady_state is 1 / median decode+pull time of the pictures after the second",
+                            "thread in both libraries (the reference's own code); libxevd_gpu.so reconstructs on the device and copies every picture back. whole_stream is the first pass over the 6..8-picture stream "
+                            "with its sequence set-up (picture buffers, page-locking, staging), steady_state is 1 / median decode+pull time per picture when the same instance "
+                            "decodes the stream a second and a third time",
                             "frames_per_sec": res})
                 log(f"extra: stream-{name}: {res}")
     except Exception as e:        # the drop-in library is optional at bench time
