@@ -194,7 +194,7 @@ def run_reference(args):
                          "sample": f"{cores} single-threaded decoder instances x {args.steps} pictures of {args.workload} each (recon + pad)"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def cpu_baseline_sample(workload, seconds_budget=20.0):
@@ -543,13 +543,28 @@ def run_ours(args):
             line["extra"] = extra
         if scatter_gather is not None:
             line["nccl_scatter_gather"] = scatter_gather
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def emit(text):
+    """the ONE result line goes to the process's real stdout; everything else that lands on file descriptor 1 - e.g. the "NCCL version ..."
+    banner NCCL prints from C when the communicator is created - was redirected to stderr at start-up (main)"""
+    out = _RESULT_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
