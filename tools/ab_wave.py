@@ -37,6 +37,8 @@ def cases():
     synth.add_intra_cus(cl, np.random.default_rng(7), 0.02, eipd=True)
     synth.derive_avail_cu(cl)
     yield ("Main P picture, HTDF on 60 % of the CUs", prm, cl, 2)
+    prm, cl, refs, _, _ = synth.make_main_frame(w, h, bit_depth=bd, seed=3)
+    yield ("config 3 picture (all Main tools: throughput + generic + wavefront kernel)", prm, cl, refs)
 
 
 for name, prm, cl, nl in cases():
@@ -45,7 +47,12 @@ for name, prm, cl, nl in cases():
               max_cu=int(np.diff(cl.ctu_first.astype(np.int64)).max()))
     res, sums = [], []
     for c, drefs, curs in ctxs:
-        def run(i):
+        own = None
+        if not isinstance(nl, int):         # the case brings its own reference pictures
+            own = [c.pic_alloc(w, h).upload(r) for r in nl]
+            drefs = own
+        nl_ = 2 if own else nl
+        def run(i, nl=nl_, drefs=drefs):
             c.recon_frame_dev(prm, curs[i], drefs[:nl] if nl == 1 else drefs, [] if nl == 1 else drefs[::-1], wk["cus"].data_ptr(), cl.n_cu, wk["first"].data_ptr(),
                               cl.n_ctu, wk["ext"].data_ptr(), len(cl.ext), wk["coef"].data_ptr(), cl.coef.size, has_intra=True, max_cu_per_ctu=wk["max_cu"])
         for i in range(NPIC):
@@ -61,4 +68,6 @@ for name, prm, cl, nl in cases():
         res.append(1e3 * float(np.median([a.elapsed_time(b) for a, b in ts])))
         got = curs[0].download()
         sums.append(int(got.y.astype(np.int64).sum() + 3 * got.u.astype(np.int64).sum() + 7 * got.v.astype(np.int64).sum()))
+        for p_ in own or []:
+            p_.free()
     print(f"{name}: " + "  ".join(f"{Path(p).name} {r:.0f} us" for p, r in zip(libs, res)) + f"  identical: {len(set(sums)) == 1}", flush=True)

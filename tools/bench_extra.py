@@ -263,8 +263,33 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
         payload = (prm_m, cl_m, refs_m, refs_m[::-1], (alf, flags, ids))
         cpu1 = cpu_rate("cpu_picture", payload, 1, 1)
         cpun = cpu_rate("cpu_picture", payload, cores, 1)
+    # the same pipeline with four independent pictures in flight (separate contexts / streams): the wavefront kernel keeps a fraction of the SMs
+    # busy, so pictures that do not reference each other overlap
+    conc = 4
+    cs, pics = [], []
+    for k in range(conc):
+        st = torch.cuda.Stream(device=dev)
+        c = Context(dev.index)
+        c.set_stream(st.cuda_stream)
+        c.set_chroma_qp_table(synth.chroma_qp_table(True))
+        cs.append((c, st)); pics.append([c.pic_alloc(w, h) for _ in range(2)])
+    def sweep_m(n):
+        for j in range(n):
+            for k, (c, _) in enumerate(cs):
+                cur = pics[k][j & 1]
+                recon(c, prm_m, cur, dm, dm[::-1], wk_m, has); c.deblock(prm_m, cur, dm, dm[::-1]); c.alf(prm_m, cur, alf, flags); c.pad(cur)
+        for c, _ in cs:
+            c.sync()
+    sweep_m(1)
+    t0 = time.perf_counter()
+    sweep_m(3)
+    fps_conc = 3 * conc / (time.perf_counter() - t0)
+    for k, (c, _) in enumerate(cs):
+        for p in pics[k]:
+            p.free()
+        c.close()
     entry("4k-main-full", us, alg, "xb200_recon_frame_dev (all Main tools) + xb200_deblock (ADDB) + xb200_alf + xb200_pad: BASELINE config 3", cpu1, cpun,
-          picture=f"{w}x{h} 4:2:0 {bd}-bit", us_by_call={k: round(v, 1) for k, v in parts.items()})
+          picture=f"{w}x{h} 4:2:0 {bd}-bit", us_by_call={k: round(v, 1) for k, v in parts.items()}, pictures_in_flight=conc, frames_per_sec_concurrent=round(fps_conc, 1))
     ctx.set_chroma_qp_table(synth.chroma_qp_table(False))
     for p in dm + drefs + curs:
         p.free()

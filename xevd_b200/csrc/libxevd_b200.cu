@@ -9,6 +9,7 @@
 #include <string.h>
 #include <math.h>
 #include <new>
+#include <atomic>
 
 #include "xb_common.cuh"
 #include "xb_itdq.cuh"
@@ -43,6 +44,11 @@ struct Staging {                 // one slot of the host->device staging ring
     bool busy = false;
 };
 
+// Only ONE context of the process runs its wavefront kernel beside the generic kernel (recon_frame_dev): wavefront CTAs spin on flags the
+// generic kernel raises, and the waiters of several contexts together could occupy every SM before the kernels they wait for get a CTA in.
+// The first context that needs it owns the right until it is destroyed; the others launch the two kernels one after the other.
+static std::atomic<xb200_ctx *> g_overlap_owner{nullptr};
+
 struct xb200_ctx {
     int device;
     cudaStream_t stream;
@@ -75,6 +81,9 @@ struct xb200_ctx {
     int *d_dra;                  // DRA LUTs on the device (3 x 1024 ints)
     bool peer_maps;              // XB200_PEER_NOMAPS=1 (read once at creation) keeps the per-SCU maps local in band mode (debug)
     bool force_generic;          // XB200_FORCE_GENERIC=1: route everything through the generic kernel (debug / A-B tests)
+    bool no_overlap;             // XB200_NO_OVERLAP=1: the wavefront kernel starts after the generic inter kernel instead of beside it (A/B, debugging)
+    cudaStream_t stream_w;       // second stream: the wavefront kernel when it runs beside the generic inter kernel
+    cudaEvent_t ev_fork, ev_join;
     int v2_variant;              // XB200_V2_VARIANT=rounds | slots: pin the prediction-stage variant of the throughput kernel (tests run both); else per picture
 };
 
@@ -113,6 +122,7 @@ xb200_ctx *xb200_create(int device, int *err)
     c->launches = 0;
     c->err[0] = 0;
     c->ring_pos = 0;
+    c->stream_w = nullptr; c->ev_fork = c->ev_join = nullptr;
     c->d_sync = nullptr; c->sync_cap = 0; c->d_err = nullptr; c->wave_used = false;
     c->d_order = nullptr; c->order_w = c->order_n = 0;
     c->out_buf = nullptr; c->out_cap = 0; c->d_dra = nullptr;
@@ -167,6 +177,7 @@ xb200_ctx *xb200_create(int device, int *err)
         memcpy(c->chroma_qp[0], base, 58); memcpy(c->chroma_qp[1], base, 58);
     }
     { const char *e = getenv("XB200_FORCE_GENERIC"); c->force_generic = e && e[0] == '1'; }
+    { const char *e = getenv("XB200_NO_OVERLAP"); c->no_overlap = e && e[0] == '1'; }
     { const char *e = getenv("XB200_V2_VARIANT"); c->v2_variant = !e ? 0 : (!strcmp(e, "rounds") ? 1 : (!strcmp(e, "slots") ? 2 : 0)); }
     { const char *e = getenv("XB200_PEER_NOMAPS"); c->peer_maps = !(e && e[0] == '1'); }
     {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
@@ -239,6 +250,10 @@ void xb200_destroy(xb200_ctx *c)
     if (c->alf_tab_pinned) cudaFreeHost(c->alf_tab_pinned);
     if (c->alf_tab_done) cudaEventDestroy(c->alf_tab_done);
     if (c->alf_flags_done) cudaEventDestroy(c->alf_flags_done);
+    { xb200_ctx *me = c; g_overlap_owner.compare_exchange_strong(me, nullptr); }
+    if (c->stream_w) cudaStreamDestroy(c->stream_w);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -471,6 +486,7 @@ static int fill_args(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur, xb20
     if (prm->log2_ctu < 5 || prm->log2_ctu > 7) return XB200_ERR_INVALID_ARGUMENT;
     if (n0 < 0 || n1 < 0 || n0 > XB_MAX_REFS || n1 > XB_MAX_REFS) return XB200_ERR_INVALID_ARGUMENT;
     if (prm->bit_depth_luma < 8 || prm->bit_depth_luma > 14) return XB200_ERR_UNSUPPORTED;
+    a.inter_done = a.inter_count = nullptr;
     memset(&a, 0, sizeof(a));
     a.cur.y = cur->y; a.cur.u = cur->u; a.cur.v = cur->v;
     for (int l = 0; l < 2; l++) {
@@ -541,6 +557,53 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     a.coef = (const int16_t *)d_coef;
     a.ext = (const XB200_CU_EXT *)d_ext;
     cudaSetDevice(c->device);
+    // With Main tools and wavefront work in one picture the wavefront kernel runs BESIDE the generic inter kernel on a second stream: it
+    // keeps a fraction of the SMs busy (a 126-step dependency chain), the generic kernel the rest.  The generic kernel raises one flag per
+    // CTU, the wavefront kernel waits for the flags of the CTUs it reads - its own, its four neighbours, the CTUs under an IBC source block
+    // (xb_intra.cuh).  Not with constrained intra prediction (reads map_scu of neighbours through the read-only path).
+    bool overlap = has_intra && mixed && !a.constrained && !c->no_overlap && a.n_peer == 0;
+    if (overlap) {
+        xb200_ctx *none = nullptr;
+        overlap = g_overlap_owner.compare_exchange_strong(none, c) || none == c;
+    }
+    if (has_intra) {
+        // synchronisation words of the wavefront kernel: ticket, one `done` flag per CTU, one `inter_done` flag per CTU
+        if (c->sync_cap < 2 * a.n_ctu + 2) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            if (c->d_sync) cudaFree(c->d_sync);
+            c->d_sync = nullptr; c->sync_cap = 0;
+            CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * (2 * a.n_ctu + 2)));
+            c->sync_cap = 2 * a.n_ctu + 2;
+        }
+        if (c->order_w != a.w_ctu || c->order_n != a.n_ctu) {
+            // wavefront order: sort CTU addresses by x + 2y (a stable counting pass per index)
+            const int wc = a.w_ctu, hc = a.n_ctu / a.w_ctu;
+            int *h = (int *)malloc(sizeof(int) * a.n_ctu);
+            if (!h) return XB200_ERR_OUT_OF_MEMORY;
+            int k = 0;
+            for (int d = 0; d <= (wc - 1) + 2 * (hc - 1); d++)
+                for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
+            cudaError_t e = cudaStreamSynchronize(c->stream);
+            if (c->d_order) cudaFree(c->d_order);
+            c->d_order = nullptr; c->order_w = c->order_n = 0;
+            if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu);
+            if (e == cudaSuccess) e = cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice);
+            free(h);
+            CK(c, e);
+            c->order_w = a.w_ctu; c->order_n = a.n_ctu;
+        }
+        CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (2 * a.n_ctu + 2), c->stream));
+        if (!c->d_err) { CK(c, cudaMalloc((void **)&c->d_err, sizeof(int))); CK(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream)); }
+        if (overlap && !c->stream_w) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CK(c, cudaStreamCreateWithPriority(&c->stream_w, cudaStreamNonBlocking, hi));
+            CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+    }
+    a.inter_done = overlap ? c->d_sync + 1 + a.n_ctu : nullptr;
+    a.inter_count = overlap ? c->d_sync + 1 + 2 * a.n_ctu : nullptr;
     if (fast) {
         int max_cu = max_cu_per_ctu > 0 ? (max_cu_per_ctu > 256 ? 256 : max_cu_per_ctu) : 256;
         max_cu = (max_cu + 15) & ~15;
@@ -563,6 +626,10 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
 #undef XB_V2
         if (mixed) { c->launches++; CK(c, cudaGetLastError()); }
     }
+    if (overlap) {              // the wavefront stream continues from here: the throughput kernel is complete, the generic kernel is not
+        CK(c, cudaEventRecord(c->ev_fork, c->stream));
+        CK(c, cudaStreamWaitEvent(c->stream_w, c->ev_fork, 0));
+    }
     if (!fast || mixed) {
         const size_t smem = xb::ReconSmem::bytes(a.log2_ctu);
         if (a.iqt) xb::k_recon_inter<true><<<a.n_ctu, xb::kReconThreads, smem, c->stream>>>(a);
@@ -571,41 +638,22 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     c->launches++;
     CK(c, cudaGetLastError());
     if (has_intra) {
-        // intra CUs: CTU wavefront over the picture the inter kernel just completed
-        if (c->sync_cap < a.n_ctu + 1) {
-            CK(c, cudaStreamSynchronize(c->stream));
-            if (c->d_sync) cudaFree(c->d_sync);
-            c->d_sync = nullptr; c->sync_cap = 0;
-            CK(c, cudaMalloc((void **)&c->d_sync, sizeof(int) * (a.n_ctu + 1)));
-            c->sync_cap = a.n_ctu + 1;
-        }
-        if (c->order_w != a.w_ctu || c->order_n != a.n_ctu) {
-            // wavefront order: sort CTU addresses by x + 2y (a stable counting pass per index)
-            const int wc = a.w_ctu, hc = a.n_ctu / a.w_ctu;
-            int *h = (int *)malloc(sizeof(int) * a.n_ctu);
-            if (!h) return XB200_ERR_OUT_OF_MEMORY;
-            int k = 0;
-            for (int d = 0; d <= (wc - 1) + 2 * (hc - 1); d++)
-                for (int y = 0; y < hc; y++) { const int x = d - 2 * y; if (x >= 0 && x < wc) h[k++] = y * wc + x; }
-            cudaError_t e = cudaStreamSynchronize(c->stream);
-            if (c->d_order) cudaFree(c->d_order);
-            c->d_order = nullptr; c->order_w = c->order_n = 0;
-            if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_order, sizeof(int) * a.n_ctu);
-            if (e == cudaSuccess) e = cudaMemcpy(c->d_order, h, sizeof(int) * a.n_ctu, cudaMemcpyHostToDevice);
-            free(h);
-            CK(c, e);
-            c->order_w = a.w_ctu; c->order_n = a.n_ctu;
-        }
-        CK(c, cudaMemsetAsync(c->d_sync, 0, sizeof(int) * (a.n_ctu + 1), c->stream));
-        if (!c->d_err) { CK(c, cudaMalloc((void **)&c->d_err, sizeof(int))); CK(c, cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream)); }
+        // intra CUs: CTU wavefront over the picture the inter kernels complete
         xb::IntraSync sy{c->d_sync, c->d_err, c->d_sync + 1, c->d_order};
         const size_t sm = xb::IntraSmem::bytes();
         // persistent CTAs (xb_intra.cuh): dense dependencies (I pictures) -> about as many CTAs as the x + 2y wavefront is wide
         const int h_ctu = a.n_ctu / a.w_ctu;
         int grid = a.n_ctu;
         if (has_intra & XB200_HAS_DENSE_WAVEFRONT) { const int wide = ((a.w_ctu + 1) / 2 < h_ctu ? (a.w_ctu + 1) / 2 : h_ctu) + 8; if (wide < grid) grid = wide; }
-        if (a.iqt) xb::k_recon_intra<true><<<grid, xb::kIntraThreads, sm, c->stream>>>(a, sy);
-        else       xb::k_recon_intra<false><<<grid, xb::kIntraThreads, sm, c->stream>>>(a, sy);
+        // beside the generic kernel: at most one wavefront CTA per two SMs, so that CTAs of the kernel it waits for always find a free SM
+        if (overlap && grid > c->sm_count / 2) grid = c->sm_count / 2;
+        cudaStream_t ws = overlap ? c->stream_w : c->stream;
+        if (a.iqt) xb::k_recon_intra<true><<<grid, xb::kIntraThreads, sm, ws>>>(a, sy);
+        else       xb::k_recon_intra<false><<<grid, xb::kIntraThreads, sm, ws>>>(a, sy);
+        if (overlap) {
+            CK(c, cudaEventRecord(c->ev_join, c->stream_w));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        }
         c->wave_used = true;
         c->launches++;
         CK(c, cudaGetLastError());

@@ -37,6 +37,9 @@ struct XbFrameArgs {
     int main_tables, iqt, eipd, ats, htdf, slice_qp, dmvr, poc, affine, ibc;
     int constrained;              // pps.constrained_intra_pred_flag (HTDF ring of intra CUs)
     int dispatch;                 // 1: the throughput kernel reconstructs the CUs it has code for, the generic kernel the ATS / DMVR / affine CUs
+    int *inter_count;             // (with inter_done) number of CTUs the generic kernel has finished: once it equals n_ctu no flag needs a look
+    int *inter_done;              // null, or one flag per CTU of this launch: the generic inter kernel sets it when the CTU's inter CUs are final, the
+                                  // wavefront kernel - running beside it on a second stream - waits for the flags of the CTUs it is about to read
     const XB200_CU *cus;
     const uint32_t *ctu_first;
     const int16_t *coef;

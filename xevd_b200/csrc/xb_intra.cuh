@@ -361,7 +361,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     int *s_tmp = (int *)(s_nb + 3 * IntraSmem::kNbElems);
     XB200_CU *s_cu = (XB200_CU *)(s_tmp + IntraSmem::kTmpElems);
     XB200_CU_EXT *s_ext = (XB200_CU_EXT *)(s_cu + IntraSmem::kCuStage);
-    __shared__ int s_ctu, s_scr12[12];
+    __shared__ int s_ctu, s_scr12[12], s_inter_all;
     __shared__ unsigned s_req[4], s_has[4];
     const int tid = threadIdx.x;
 
@@ -376,6 +376,17 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         unsigned spins = 0;
         while (*f == 0) { __nanosleep(64); if (++spins > (1u << 24)) { atomicExch(sy.err, 1); break; } }
     };
+    // Overlap with the generic inter kernel (a.inter_done): this kernel then runs beside it on a second stream and must not read a CTU's
+    // samples before that kernel is done with them - its own CTU before the preload, the four neighbours before their border row / column.
+    // Picture samples are read with ld.global.cg throughout, so a line cached before another kernel rewrote it cannot be served.
+    // Once the generic kernel has finished every CTU (a.inter_count) the CTA stops looking at flags (s_inter_all, written by thread 0 only).
+    auto wait_inter = [&](int nc) {
+        if (s_inter_all) return;
+        volatile int *f = a.inter_done + nc;
+        unsigned spins = 0;
+        while (*f == 0) { __nanosleep(64); if (++spins > (1u << 24)) { atomicExch(sy.err, 1); break; } }
+    };
+    if (tid == 0) s_inter_all = a.inter_done ? 0 : 1;
     for (;;) {
     __syncthreads();                // every thread is done with the previous CTU's shared state
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
@@ -419,12 +430,20 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         auto up = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4; };
         auto le = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + (2 * 128 + 8); };
         auto ri = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + 2 * (2 * 128 + 8); };
+        if (a.inter_done) {
+            if (tid == 0 && !s_inter_all) {
+                if (*(volatile int *)a.inter_count >= a.n_ctu) s_inter_all = 1;
+                else wait_inter(ctu);
+                __threadfence();
+            }
+            __syncthreads();
+        }
         // ---- before waiting: (1) the CTU's samples as the inter kernel left them (neighbours of intra CUs, HTDF input) -------------
         for (int pl = 0; pl < 3; pl++) {
             const int Sp = pc(pl).Sp, wv = min(Sp, ((a.w - ctu_x) >> (pl ? 1 : 0))), hv = min(Sp, ((a.h - ctu_y) >> (pl ? 1 : 0)));
             for (int i = tid; i < Sp * hv; i += kIntraThreads) {
                 const int y = i / Sp, x = i - y * Sp;
-                if (x < wv) pc(pl).rec[y * Sp + x] = pc(pl).res[y * Sp + x] = pc(pl).g[(size_t)y * pc(pl).gs + x];
+                if (x < wv) pc(pl).rec[y * Sp + x] = pc(pl).res[y * Sp + x] = __ldcg(pc(pl).g + (size_t)y * pc(pl).gs + x);
             }
         }
         //      intra / IBC areas hold the RESIDUAL there (parked by the inter kernel), which is why the preload fills both arrays
@@ -474,9 +493,12 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
             __syncthreads();
         }
         // ---- wait for them ----------------------------------------------------------------------------------------------------------
-        if (tid < 4 && (!prune || (s_req[tid] & s_has[tid]))) {
+        if (tid < 4) {
             const int nx = cx + (tid == 0 ? -1 : tid - 2), ny = cy - (tid == 0 ? 0 : 1);
-            if (nx >= 0 && nx < a.w_ctu && ny >= 0) wait_done(ny * a.w_ctu + nx);
+            if (nx >= 0 && nx < a.w_ctu && ny >= 0) {
+                if (a.inter_done) wait_inter(ny * a.w_ctu + nx);                  // its border samples are read below whether or not it has wavefront work
+                if (!prune || (s_req[tid] & s_has[tid])) wait_done(ny * a.w_ctu + nx);
+            }
             __threadfence();
         }
         __syncthreads();
@@ -512,6 +534,15 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
                 // picture (block vector mv[0], chroma vector = luma >> 1), then xevdm_recon.  Conforming vectors stay inside the
                 // current CTU row at or left of this CTU: samples of this CTU come from shared memory, older ones from the picture.
                 const int bx = cu.mv[0][0], by = cu.mv[0][1];
+                if (!s_inter_all) {         // (uniform) beside the generic kernel: the CTUs under the source block must have their inter CUs
+                    if (tid == 0) {
+                        const int X0 = max(cu.x + bx, 0), Y0 = max(cu.y + by, 0);
+                        for (int yy = Y0 >> a.log2_ctu; yy <= min(Y0 + h - 1, a.h - 1) >> a.log2_ctu; yy++)
+                            for (int xx = X0 >> a.log2_ctu; xx <= min(X0 + w - 1, a.w - 1) >> a.log2_ctu; xx++) wait_inter(yy * a.w_ctu + xx);
+                        __threadfence();
+                    }
+                    __syncthreads();
+                }
                 for (int pl = do_l ? 0 : 1; pl < (do_c ? 3 : 1); pl++) {
                     const int sh = pl ? 1 : 0, pw = w >> sh, ph = h >> sh, lwp = cu.log2w - sh, Sp = pc(pl).Sp;
                     const int ox = lx >> sh, oy = ly >> sh, vx = bx >> sh, vy = by >> sh;

@@ -667,7 +667,10 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
     const int cu0 = a.ctu_first[ctu], cu1 = a.ctu_first[ctu + 1];
     const XB200_CU *cus = a.cus + cu0;
     const int ncu = cu1 - cu0;
-    if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) return;      // no ATS / DMVR / affine CU here: the throughput kernel does it all
+    if (a.dispatch && !ctu_needs_generic(a, cus, ncu, tid, kReconThreads)) {            // no ATS / DMVR / affine CU here: the throughput kernel does it all
+        if (a.inter_done && tid == 0) { atomicExch(a.inter_done + ctu, 1); atomicAdd(a.inter_count, 1); }
+        return;
+    }
 
     // ---- SCU -> CU map, zero residual -------------------------------------------------------------------
     for (int i = tid; i < 2 * nscu * nscu; i += kReconThreads) sm.cu_of_scu[i] = 0xffff;          // both owner tables (contiguous)
@@ -911,6 +914,11 @@ k_recon_inter(const __grid_constant__ XbFrameArgs a)
             for (int y = 0; y < nh; y++) a.map_edge[(gy + y) * a.w_scu + gx] &= (uint8_t)~XB200_EDGE_LEFT_NOC;
             for (int x = 0; x < nw; x++) a.map_edge[gy * a.w_scu + gx + x] &= (uint8_t)~XB200_EDGE_TOP_NOC;
         }
+    }
+    if (a.inter_done) {         // samples and maps of this CTU are final as far as the inter kernels go: release the wavefront kernel's waiters
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) { atomicExch(a.inter_done + ctu, 1); atomicAdd(a.inter_count, 1); }
     }
 }
 
