@@ -249,6 +249,10 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
     ids = ((0, 1), (1, 0))
     ctx.set_chroma_qp_table(synth.chroma_qp_table(True))
     has = 3 if (cl_m.cus["flags"] & 3 != 3).any() else 1
+    # what xb200_recon_frame derives from the work list itself (libxevd_b200.cu): more than half of the CUs on the wavefront -> persistent grid
+    n_wave = int(((cl_m.cus["mode"] == 0) | (cl_m.cus["mode"] == 4) | ((cl_m.cus["cbf"] & 15) != 0)).sum())
+    if 2 * n_wave > cl_m.n_cu:
+        has |= 4
     parts = {}
     parts["recon"] = timed(lambda i: recon(ctx, prm_m, curs[i], dm, dm[::-1], wk_m, has))
     parts["deblock"] = timed(lambda i: ctx.deblock(prm_m, curs[i], dm, dm[::-1]))
