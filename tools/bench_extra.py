@@ -357,6 +357,62 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
     out.append({"workload": "config5-mc", "passes": "xb200_mc_blocks_dev: variant nn (both phases fractional) on 4 Mi samples per launch from a 4K reference plane", "rows": rows})
     log("extra: config5-mc: " + ", ".join(f"{r['plane'][:1]}{r['block']} {r['us']}us" for r in rows))
 
+    # ---- end to end with 8-bit output: the same public calls as bench.py's e2e leg on the headline workload, the decoded picture pulled as 8-bit
+    #      planes (what xevd_app --output-bit-depth 8 asks for; xb200_pic_pull narrows on the device, xevd_app_util.h:359-381): half the D2H
+    #      bytes of the headline's e2e, which sits on that copy
+    try:
+        import ctypes as C
+        from xevd_b200.frame import sparse_coef
+        w8, h8, bd8, F8, nctx = 3840, 2160, 10, 12, 3
+        work = []
+        for i in range(4):
+            prm8, cl8 = synth.make_inter_frame(w8, h8, bit_depth=bd8, variant="A", seed=100 + i, n_refs=1)
+            ent, cf = sparse_coef(cl8.coef)
+            work.append(dict(prm=prm8, cl=cl8, cus=torch.from_numpy(cl8.cus.view(np.uint8).copy()).pin_memory(),
+                             first=torch.from_numpy(cl8.ctu_first.view(np.int32).copy()).pin_memory(), ext=torch.from_numpy(cl8.ext.view(np.uint8).copy()).pin_memory(),
+                             ent=torch.from_numpy(ent.view(np.int32).copy()).pin_memory(), cf=torch.from_numpy(cf.view(np.int32).copy()).pin_memory()))
+        refs8 = synth.make_refs(w8, h8, bd8, 1, seed=8)
+        cs = []
+        for k in range(nctx):
+            st = torch.cuda.Stream(device=dev)
+            c = Context(dev.index)
+            c.set_stream(st.cuda_stream)
+            cs.append(dict(c=c, st=st, ref=c.pic_alloc(w8, h8).upload(refs8[0])))
+        slots8 = []
+        for i in range(F8):
+            c = cs[i % nctx]
+            slots8.append(dict(c=c, cur=c["c"].pic_alloc(w8, h8), wk=work[i % 4], y=torch.empty((h8, w8), dtype=torch.uint8).pin_memory(),
+                               u=torch.empty((h8 // 2, w8 // 2), dtype=torch.uint8).pin_memory(), v=torch.empty((h8 // 2, w8 // 2), dtype=torch.uint8).pin_memory()))
+        def step8():
+            for s8 in slots8:
+                c, wk = s8["c"]["c"], s8["wk"]
+                cl8 = wk["cl"]
+                rh = (C.c_void_p * 1)(s8["c"]["ref"].handle)
+                c._chk(c.lib.xb200_recon_frame_sparse(c.handle, C.byref(wk["prm"]), s8["cur"].handle, rh, 1, rh, 0, wk["cus"].data_ptr(), cl8.n_cu,
+                                                      wk["first"].data_ptr(), cl8.n_ctu, wk["ext"].data_ptr(), len(cl8.ext), wk["ent"].data_ptr(), wk["ent"].numel(),
+                                                      wk["cf"].data_ptr(), cl8.coef.size), "xb200_recon_frame_sparse")
+                c.pad(s8["cur"])
+                c._chk(c.lib.xb200_pic_pull(c.handle, s8["cur"].handle, None, 8, 0, 0, 0, 0, s8["y"].data_ptr(), w8, s8["u"].data_ptr(), w8 // 2,
+                                            s8["v"].data_ptr(), w8 // 2), "xb200_pic_pull")
+            for k in cs:
+                k["c"].sync()
+        step8()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            step8()
+        fps8 = 4 * F8 / (time.perf_counter() - t0)
+        h2d8 = int(np.mean([wk["cus"].numel() + wk["first"].numel() * 4 + wk["ext"].numel() + wk["ent"].numel() * 4 + wk["cf"].numel() * 4 for wk in work]))
+        out.append({"workload": "4k-2A-e2e-8bit-output", "passes": "xb200_recon_frame_sparse (host buffers) + xb200_pad + xb200_pic_pull to 8-bit planes, 3 contexts / streams: the e2e leg of "
+                    "bench.py with the decoded 10-bit picture delivered as 8-bit output", "frames_per_sec": round(fps8, 1), "h2d_bytes_per_picture": h2d8, "d2h_bytes_per_picture": w8 * h8 * 3 // 2,
+                    "checksum": int(slots8[0]["y"][::64, ::64].to(torch.int64).sum().item()), "picture": f"{w8}x{h8} 4:2:0 10-bit, 8-bit output"})
+        log(f"extra: 4k-2A-e2e-8bit-output: {fps8:.0f} pictures/s")
+        for s8 in slots8:
+            s8["cur"].free()
+        for k in cs:
+            k["ref"].free(); k["c"].close()
+    except Exception as e:
+        out.append({"workload": "4k-2A-e2e-8bit-output", "error": repr(e)})
+
     # ---- whole-decoder drop-in on real elementary streams --------------------------------------------------------------------
     try:
         from xevd_b200 import xevd_api as X
