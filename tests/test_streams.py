@@ -1,4 +1,5 @@
-"""Whole-decoder parity on real EVC elementary streams (tests/golden/streams/*.evc, made by tests/golden/make_streams.py).
+"""Whole-decoder parity on real EVC elementary streams (tests/golden/streams/*.evc, made by tests/golden/make_streams.py, and
+tests/golden/sweep/*.evc, made by tools/stream_sweep.py).
 
 CPU (`-m "not gpu"`): the unmodified reference (oracle/_ref/libxevd_ref.so, when built) decodes every stream to the recorded MD5s.
 GPU (`-m gpu`): glue/_build/libxevd_gpu.so - the reference decoder with entropy decoding + motion derivation on the host and ALL
@@ -14,6 +15,8 @@ import pytest
 from xevd_b200 import xevd_api as X
 
 STREAMS = sorted((Path(__file__).resolve().parent / "golden" / "streams").glob("*.evc"))
+# + a random-configuration sweep (tools/stream_sweep.py: profile, picture size, CTU size, tile grid, slices and Main tools drawn at random)
+STREAMS += sorted((Path(__file__).resolve().parent / "golden" / "sweep").glob("*.evc"))
 
 
 def pic_md5(p):
