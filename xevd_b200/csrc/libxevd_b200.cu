@@ -610,8 +610,9 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         const bool bi = n1 > 0;
         const bool peer = a.n_peer > 0;
         // warp-slot variant (three CTAs per SM, no block-wide step in the prediction stages) for pictures of large CUs; the round variant
-        // shares its per-tile passes between two tiles, which wins when most CUs are 8x8 and smaller (xb_recon2.cuh; A/B in profiles/r2)
-        const bool ws = !peer && (c->v2_variant == 2 || (c->v2_variant == 0 && (long long)n_cu <= 16LL * a.n_ctu));
+        // shares its per-tile passes between two tiles, which wins when most CUs are 8x8 and smaller: more than 32 CUs per CTU on average
+        // (xb_recon2.cuh; A/B in profiles/r2: quadtree pictures of ~20 CUs per CTU 160 vs 164 us for the slots, 8x8 pictures 160 vs 146 against them)
+        const bool ws = !peer && (c->v2_variant == 2 || (c->v2_variant == 0 && (long long)n_cu <= 32LL * a.n_ctu));
         const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu, peer, ws);
         const dim3 grid(a.w_ctu, a.n_ctu / a.w_ctu);
 #define XB_V2(BI_, IQT_, DISP_) do { if (ws) xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu); \
