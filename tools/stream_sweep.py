@@ -15,8 +15,13 @@ sys.path.insert(0, str(ROOT / "tools" / "evcgen"))
 from xevd_b200 import xevd_api as X  # noqa: E402
 
 
-def gen(out, n, seed0=1000):
+def gen(out, n, seed0=1000, skip=0, per_stream_s=240):
+    import signal
     import evcgen as G
+
+    def on_alarm(signum, frame):
+        raise TimeoutError()
+    signal.signal(signal.SIGALRM, on_alarm)
     out.mkdir(parents=True, exist_ok=True)
     g = G.Generator()
     ref = X.XevdLibrary(X.REF_SO)
@@ -43,11 +48,19 @@ def gen(out, n, seed0=1000):
                          affine=int(rng.integers(0, 2)), addb=int(rng.integers(0, 2)), htdf=int(rng.integers(0, 2)))
         kw = dict(w=w, h=h, bd=int(rng.choice([8, 10])), frames=int(rng.integers(2, 5)), seed=seed0 + 17 * k, types="I" if idr_only else str(rng.choice(["IPB", "IBB", "IPP"])),
                   qp=int(rng.integers(24, 40)), lps_scale=350 if main else 256, log2_ctu=log2_ctu, tiles=tiles, slices=slices, gop=1 if idr_only else 0)
+        if k < skip:
+            continue
+        signal.alarm(per_stream_s)
         try:
             nals, own = g.make(tools, **kw)
         except (G.NonConforming, AssertionError) as e:
             print(f"{k}: no stream ({str(e)[:80]})", flush=True)
             continue
+        except TimeoutError:
+            print(f"{k}: generation did not finish in {per_stream_s} s, skipped: tools {tools} {kw}", flush=True)
+            continue
+        finally:
+            signal.alarm(0)
         pics = X.decode_stream(ref, nals)
         if not G.same_pictures(own, pics):
             print(f"{k}: reference != generator, dropped", flush=True)
@@ -78,6 +91,7 @@ def check(d):
 
 if __name__ == "__main__":
     if sys.argv[1] == "gen":
-        gen(Path(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 16, int(sys.argv[4]) if len(sys.argv) > 4 else 1000)
+        gen(Path(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 16, int(sys.argv[4]) if len(sys.argv) > 4 else 1000,
+            int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     else:
         sys.exit(check(Path(sys.argv[2])))
