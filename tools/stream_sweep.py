@@ -16,15 +16,10 @@ from xevd_b200 import xevd_api as X  # noqa: E402
 
 
 def gen(out, n, seed0=1000, skip=0, per_stream_s=240):
-    import signal
+    import json
+    import subprocess
     import evcgen as G
-
-    def on_alarm(signum, frame):
-        raise TimeoutError()
-    signal.signal(signal.SIGALRM, on_alarm)
     out.mkdir(parents=True, exist_ok=True)
-    g = G.Generator()
-    ref = X.XevdLibrary(X.REF_SO)
     rng = np.random.default_rng(seed0)
     kept = 0
     for k in range(n):
@@ -50,26 +45,38 @@ def gen(out, n, seed0=1000, skip=0, per_stream_s=240):
                   qp=int(rng.integers(24, 40)), lps_scale=350 if main else 256, log2_ctu=log2_ctu, tiles=tiles, slices=slices, gop=1 if idr_only else 0)
         if k < skip:
             continue
-        signal.alarm(per_stream_s)
-        try:
-            nals, own = g.make(tools, **kw)
-        except (G.NonConforming, AssertionError) as e:
-            print(f"{k}: no stream ({str(e)[:80]})", flush=True)
-            continue
-        except TimeoutError:
-            print(f"{k}: generation did not finish in {per_stream_s} s, skipped: tools {tools} {kw}", flush=True)
-            continue
-        finally:
-            signal.alarm(0)
-        pics = X.decode_stream(ref, nals)
-        if not G.same_pictures(own, pics):
-            print(f"{k}: reference != generator, dropped", flush=True)
-            continue
         name = f"sweep_{k:03d}_{'main' if main else 'base'}_{w}x{h}_ctu{ctu}" + (f"_t{cols}x{rows}{'a' if tiles['across'] else 'n'}" if tiles else "") + ("_sl2" if slices else "")
-        X.write_stream(out / f"{name}.evc", nals)
-        kept += 1
-        print(f"{k}: {name}: {len(pics)} pictures, {sum(map(len, nals))} bytes, tools {dict((t, v) for t, v in tools.items() if t in ('alf', 'ibc', 'dmvr', 'affine', 'addb', 'htdf'))}", flush=True)
+        # one process per stream: a draw the generator cannot finish (it can loop inside the reference's parser) is cut off by the timeout
+        try:
+            r = subprocess.run([sys.executable, __file__, "one", str(out / f"{name}.evc"), json.dumps(dict(main=main, tools=tools, kw=kw))],
+                               timeout=per_stream_s, capture_output=True, text=True)
+            line = [l for l in r.stdout.splitlines() if l.startswith("one:")]
+            print(f"{k}: {name}: {line[-1][5:] if line else 'failed: ' + r.stderr.strip().splitlines()[-1][:120] if r.stderr.strip() else 'failed'}", flush=True)
+            kept += (out / f"{name}.evc").exists()
+        except subprocess.TimeoutExpired:
+            print(f"{k}: {name}: generation did not finish in {per_stream_s} s, skipped (tools {tools}, {kw})", flush=True)
     print(f"{kept} streams kept in {out}")
+
+
+def one(path, spec):
+    """generate one stream (own process); keep it only if the unmodified reference reproduces the generator's pictures"""
+    import json
+    import evcgen as G
+    spec = json.loads(spec)
+    kw = spec["kw"]
+    if kw.get("slices"):
+        kw["slices"] = [tuple(x) for x in kw["slices"]]
+    try:
+        nals, own = G.Generator().make(spec["tools"], **kw)
+    except (G.NonConforming, AssertionError) as e:
+        print(f"one: no stream ({str(e)[:80]})")
+        return
+    pics = X.decode_stream(X.XevdLibrary(X.REF_SO), nals)
+    if not G.same_pictures(own, pics):
+        print("one: reference != generator, dropped")
+        return
+    X.write_stream(path, nals)
+    print(f"one: {len(pics)} pictures, {sum(map(len, nals))} bytes")
 
 
 def check(d):
@@ -90,7 +97,9 @@ def check(d):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "gen":
+    if sys.argv[1] == "one":
+        one(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "gen":
         gen(Path(sys.argv[2]), int(sys.argv[3]) if len(sys.argv) > 3 else 16, int(sys.argv[4]) if len(sys.argv) > 4 else 1000,
             int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     else:
