@@ -392,6 +392,61 @@ void glue_htdf(s16 *rec, int qp, int w, int h, int s, BOOL intra_block_flag, pel
 }
 
 /* ---- picture buffers: every XEVD_PIC gets a device twin ------------------------------------------------------------------ */
+/* The plane buffers of a picture's XEVD_IMGB are the destination of one D2H copy per decoded picture, so they have to be page-locked.
+ * Registering the buffers xevd_imgb_create malloc'ed (cudaHostRegister) cost 13 ms per 6 MB plane on the test boxes - 20 ms per 1080p
+ * picture, most of the set-up time of a short stream.  The planes are therefore REPLACED by page-locked allocations (2-3 ms per picture):
+ * baddr / a of the imgb and buf_* / y,u,v of the picture are re-based, a 16-byte malloc block stands in for every original buffer, and a
+ * wrapper around imgb->release puts those stand-ins back (imgb_delete frees baddr with free(), src_base/xevd_util.c:102-118) and frees
+ * the page-locked planes when the last reference goes - which can be after the picture manager and the decoder are gone. */
+#include <pthread.h>
+typedef struct PIN_REC { XEVD_IMGB *imgb; void *pinned[3]; void *stub[3]; int (*release)(XEVD_IMGB *); struct PIN_REC *next; } PIN_REC;
+static PIN_REC *g_pins;
+static pthread_mutex_t g_pins_lock = PTHREAD_MUTEX_INITIALIZER;
+static int glue_imgb_release(XEVD_IMGB *imgb)
+{
+    PIN_REC *r = NULL, **pp;
+    pthread_mutex_lock(&g_pins_lock);
+    for (pp = &g_pins; *pp; pp = &(*pp)->next) if ((*pp)->imgb == imgb) { r = *pp; break; }
+    if (!r) { pthread_mutex_unlock(&g_pins_lock); return XEVD_ERR_UNEXPECTED; }
+    int (*release)(XEVD_IMGB *) = r->release;
+    if (imgb->getref(imgb) <= 1) {           /* the last reference: hand the imgb back the way xevd_imgb_create built it */
+        *pp = r->next;
+        pthread_mutex_unlock(&g_pins_lock);
+        for (int k = 0; k < 3; k++)
+            if (r->pinned[k]) { imgb->baddr[k] = r->stub[k]; imgb->a[k] = r->stub[k]; xb200_host_free(r->pinned[k]); }
+        free(r);
+    } else pthread_mutex_unlock(&g_pins_lock);
+    return release(imgb);
+}
+/* returns the number of planes now page-locked */
+static int pin_planes(XEVD_PIC *pic)
+{
+    XEVD_IMGB *imgb = pic->imgb;
+    if (!imgb || !imgb->release) return 0;
+    PIN_REC *r = (PIN_REC *)calloc(1, sizeof(PIN_REC));
+    if (!r) return 0;
+    int n = 0;
+    for (int k = 0; k < 3; k++) {
+        if (!imgb->baddr[k] || imgb->bsize[k] <= 0) continue;
+        void *stub = malloc(16), *pinned = stub ? xb200_host_alloc((size_t)imgb->bsize[k]) : NULL;
+        if (!pinned) { free(stub); continue; }
+        const ptrdiff_t off = (unsigned char *)imgb->a[k] - (unsigned char *)imgb->baddr[k];
+        free(imgb->baddr[k]);
+        imgb->baddr[k] = pinned; imgb->a[k] = (unsigned char *)pinned + off;
+        r->pinned[k] = pinned; r->stub[k] = stub;
+        n++;
+    }
+    if (!n) { free(r); return 0; }
+    pic->buf_y = imgb->baddr[0]; pic->buf_u = imgb->baddr[1]; pic->buf_v = imgb->baddr[2];
+    pic->y = imgb->a[0]; pic->u = imgb->a[1]; pic->v = imgb->a[2];
+    r->imgb = imgb; r->release = imgb->release;
+    imgb->release = glue_imgb_release;
+    pthread_mutex_lock(&g_pins_lock);
+    r->next = g_pins; g_pins = r;
+    pthread_mutex_unlock(&g_pins_lock);
+    return n;
+}
+
 XEVD_PIC *glue_picbuf_alloc(PICBUF_ALLOCATOR *pa, int *ret, int bitdepth)
 {
     XEVD_PIC *pic = xevdm_picbuf_alloc(pa, ret, bitdepth);
@@ -408,12 +463,17 @@ XEVD_PIC *glue_picbuf_alloc(PICBUF_ALLOCATOR *pa, int *ret, int bitdepth)
             slot->host = pic;
             /* every plane buffer of the XEVD_IMGB (xevd_imgb_generate allocates them one by one): page-locked, the copy in
              * glue_picbuf_expand is a true asynchronous DMA; a pageable plane would make that call wait for the device */
-            for (int k = 0; k < 3; k++) {
-                slot->registered[k] = NULL;
-                if (pic->imgb && pic->imgb->baddr[k] && pic->imgb->bsize[k] > 0 &&
-                    xb200_host_register(pic->imgb->baddr[k], (size_t)pic->imgb->bsize[k]) == XB200_OK)
-                    slot->registered[k] = pic->imgb->baddr[k];
-            }
+            for (int k = 0; k < 3; k++) slot->registered[k] = NULL;
+            if (pin_planes(pic) < 3)        /* (a plane that could not be replaced: register it in place; failing that the copy is a staged DMA) */
+                for (int k = 0; k < 3; k++) {
+                    int replaced = 0;
+                    pthread_mutex_lock(&g_pins_lock);
+                    for (PIN_REC *r = g_pins; r; r = r->next) if (r->imgb == pic->imgb && r->pinned[k]) replaced = 1;
+                    pthread_mutex_unlock(&g_pins_lock);
+                    if (!replaced && pic->imgb && pic->imgb->baddr[k] && pic->imgb->bsize[k] > 0 &&
+                        xb200_host_register(pic->imgb->baddr[k], (size_t)pic->imgb->bsize[k]) == XB200_OK)
+                        slot->registered[k] = pic->imgb->baddr[k];
+                }
             g->t_alloc += now_s() - t0;
             return pic;
         }
