@@ -84,16 +84,42 @@ __device__ __forceinline__ int dbk_st(int cls, int q)
     return (q < 0 || f >= 4 * 52) ? 0 : c_df_st[f];
 }
 
-// xevdm_get_tbl_qp_to_st (xevdm_df.c:38-104): 0 intra, 1 luma cbf, 2 motion differs (or IBC), 3 no filtering
-__device__ __forceinline__ int dbk_class(const DbkArgs &a, int cur, int nb)
+// Loads that are issued before the first test of a thread: a segment's work is a chain edge flag -> maps of both SCUs -> samples -> stores,
+// three dependent memory round trips (long_scoreboard 20.7 per issue, 19 % of the HBM peak in profiles/r1/deblock_ncu_summary.txt).  The
+// deblocking kernels fetch all of it at once, for every thread; `volatile` keeps the compiler from sinking a load below the test of its use.
+__device__ __forceinline__ int ld_now32(const void *p)
 {
-    const uint32_t m0 = a.map_scu[cur], m1 = a.map_scu[nb];
+    int v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ int2 ld_now64(const void *p)
+{
+    int2 v;
+    asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ int ld_now16(const void *p)
+{
+    unsigned short v;
+    asm volatile("ld.global.b16 %0, [%1];" : "=h"(v) : "l"(__cvta_generic_to_global(p)));
+    return (int16_t)v;
+}
+__device__ __forceinline__ unsigned ld_now8(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+
+// xevdm_get_tbl_qp_to_st (xevdm_df.c:38-104): 0 intra, 1 luma cbf, 2 motion differs (or IBC), 3 no filtering.  m = map_scu word, r = both
+// reference indices (s8 pair), v = both vectors of the current (0) and the neighbouring (1) SCU
+__device__ __forceinline__ int dbk_class_v(uint32_t m0, uint32_t m1, int r0, int r1, int2 v0, int2 v1)
+{
     if (((m0 | m1) >> 15) & 1) return 0;
     if (((m0 | m1) >> 24) & 1) return 1;
     if (((m0 | m1) >> 26) & 1) return 2;
-    const int16_t r0 = ((const int16_t *)a.map_refi)[cur], r1 = ((const int16_t *)a.map_refi)[nb];
     const int8_t r00 = (int8_t)(r0 & 0xff), r01 = (int8_t)(r0 >> 8), r10 = (int8_t)(r1 & 0xff), r11 = (int8_t)(r1 >> 8);
-    const int2 v0 = ((const int2 *)a.map_mv)[cur], v1 = ((const int2 *)a.map_mv)[nb];
     int a0x = (int16_t)(v0.x & 0xffff), a0y = v0.x >> 16, a1x = (int16_t)(v0.y & 0xffff), a1y = v0.y >> 16;
     int b0x = (int16_t)(v1.x & 0xffff), b0y = v1.x >> 16, b1x = (int16_t)(v1.y & 0xffff), b1y = v1.y >> 16;
     if (r00 < 0) a0x = a0y = 0;
@@ -105,6 +131,12 @@ __device__ __forceinline__ int dbk_class(const DbkArgs &a, int cur, int nb)
     if (r00 == r11 && r01 == r10)
         return (abs(a0x - b1x) >= 4 || abs(a0y - b1y) >= 4 || abs(a1x - b0x) >= 4 || abs(a1y - b0y) >= 4) ? 2 : 3;
     return 2;
+}
+__device__ __forceinline__ int dbk_class(const DbkArgs &a, int cur, int nb)
+{
+    const uint32_t m0 = a.map_scu[cur], m1 = a.map_scu[nb];
+    if ((((m0 | m1) >> 15) & 1) || (((m0 | m1) >> 24) & 1) || (((m0 | m1) >> 26) & 1)) return dbk_class_v(m0, m1, 0, 0, make_int2(0, 0), make_int2(0, 0));
+    return dbk_class_v(m0, m1, ((const int16_t *)a.map_refi)[cur], ((const int16_t *)a.map_refi)[nb], ((const int2 *)a.map_mv)[cur], ((const int2 *)a.map_mv)[nb]);
 }
 
 // deblock_scu_hor / _ver (xevd_df.c:96-134): all intermediates are s16 in the reference; `/` truncates toward zero (T6)
@@ -147,14 +179,16 @@ __device__ __forceinline__ bool dbk_has_edge_c(const DbkArgs &a, int sx, int sy,
 }
 
 // strengths of one segment: luma, Cb, Cr.  QP is the one of the CURRENT (right / lower) SCU only (xevd_df.c:347,446; T7)
-__device__ __forceinline__ void dbk_strengths(const DbkArgs &a, int cur, int nb, int &st, int &st_u, int &st_v)
+__device__ __forceinline__ void dbk_strengths_v(const DbkArgs &a, int cls, int qp, int &st, int &st_u, int &st_v)
 {
-    const int cls = dbk_class(a, cur, nb);
-    const int qp = (a.map_scu[cur] >> 16) & 0x7f;
     st = dbk_st(cls, qp) << (a.bd_l - 8);
     const int qu = xb_clip3(-6 * (a.bd_c - 8), 57, qp + a.qp_u_offset), qv = xb_clip3(-6 * (a.bd_c - 8), 57, qp + a.qp_v_offset);
     st_u = dbk_st(cls, qu < 0 ? qu : a.cq[0][qu]) << (a.bd_c - 8);
     st_v = dbk_st(cls, qv < 0 ? qv : a.cq[1][qv]) << (a.bd_c - 8);
+}
+__device__ __forceinline__ void dbk_strengths(const DbkArgs &a, int cur, int nb, int &st, int &st_u, int &st_v)
+{
+    dbk_strengths_v(a, dbk_class(a, cur, nb), (a.map_scu[cur] >> 16) & 0x7f, st, st_u, st_v);
 }
 
 // both chroma planes of the 4-sample (2 chroma samples) segment whose right / lower SCU is (cx, cy)
@@ -221,19 +255,40 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
 {
     const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (sx >= a.w_scu || sy >= a.h_scu) return;
-    if (!dbk_has_edge(a, sx, sy, VERTICAL)) return;
-    const int cur = sy * a.w_scu + sx, nb = VERTICAL ? cur - 1 : cur - a.w_scu;
+    constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
+    const bool inner = VERTICAL ? sx > 0 : sy > 0, has_next = VERTICAL ? sx + 1 < a.w_scu : sy + 1 < a.h_scu;
+    const int cur = sy * a.w_scu + sx, nb = inner ? (VERTICAL ? cur - 1 : cur - a.w_scu) : cur, nx = has_next ? (VERTICAL ? cur + 1 : cur + a.w_scu) : cur;
+    // ---- everything the common case reads, in one round trip (border padding makes the sample addresses of picture-edge SCUs valid) ----
+    const unsigned e = ld_now8(a.map_edge + cur), e_prev = ld_now8(a.map_edge + nb), e_next = ld_now8(a.map_edge + nx);
+    const uint32_t m0 = (uint32_t)ld_now32(a.map_scu + cur), m1 = (uint32_t)ld_now32(a.map_scu + nb);
+    const int r0 = ld_now16((const int16_t *)a.map_refi + cur), r1 = ld_now16((const int16_t *)a.map_refi + nb);
+    const int2 v0 = ld_now64((const int2 *)a.map_mv + cur), v1 = ld_now64((const int2 *)a.map_mv + nb);
+    pel *p = a.y + (size_t)(sy * 4) * a.s_l + sx * 4;
+    pel *pc[2] = {a.u + (size_t)(sy * 2) * a.s_c + sx * 2, a.v + (size_t)(sy * 2) * a.s_c + sx * 2};
+    int2 l[4];            // VERTICAL: row i, samples A B | C D around the edge; else row j - 2, the segment's four columns
+    int2 c[2][2];         // VERTICAL: plane k, row i, samples A B | C D; else plane k, rows (-2, -1) and (0, 1), the segment's two columns
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (VERTICAL) { l[i].x = ld_now32(p + (size_t)i * a.s_l - 2); l[i].y = ld_now32(p + (size_t)i * a.s_l); }
+        else l[i] = ld_now64(p + (ptrdiff_t)(i - 2) * a.s_l);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            if (VERTICAL) { c[k][i].x = ld_now32(pc[k] + (size_t)i * a.s_c - 2); c[k][i].y = ld_now32(pc[k] + (size_t)i * a.s_c); }
+            else { c[k][i].x = ld_now32(pc[k] + (ptrdiff_t)(2 * i - 2) * a.s_c); c[k][i].y = ld_now32(pc[k] + (ptrdiff_t)(2 * i - 1) * a.s_c); }
+        }
+    if (!(inner && (e & kEdge))) return;
     int st, st_u, st_v;
-    dbk_strengths(a, cur, nb, st, st_u, st_v);
+    dbk_strengths_v(a, dbk_class_v(m0, m1, r0, r1, v0, v1), (m0 >> 16) & 0x7f, st, st_u, st_v);
     const int maxl = (1 << a.bd_l) - 1, maxc = (1 << a.bd_c) - 1;
     if (st) {
-        pel *p = a.y + (size_t)(sy * 4) * a.s_l + sx * 4;
         if (VERTICAL) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 pel *q = p + (size_t)i * a.s_l;
-                const int lo = *(const int *)(q - 2), hi = *(const int *)q;           // A B | C D
-                int A = (int16_t)(lo & 0xffff), B = lo >> 16, C = (int16_t)(hi & 0xffff), D = hi >> 16;
+                int A = (int16_t)(l[i].x & 0xffff), B = l[i].x >> 16, C = (int16_t)(l[i].y & 0xffff), D = l[i].y >> 16;
                 dbk_luma(A, B, C, D, st, maxl);
                 *(int *)(q - 2) = (A & 0xffff) | (B << 16);
                 *(int *)q = (C & 0xffff) | (D << 16);
@@ -242,8 +297,7 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
             int r[4][4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int2 v = *(const int2 *)(p + (ptrdiff_t)(j - 2) * a.s_l);
-                r[j][0] = (int16_t)(v.x & 0xffff); r[j][1] = v.x >> 16; r[j][2] = (int16_t)(v.y & 0xffff); r[j][3] = v.y >> 16;
+                r[j][0] = (int16_t)(l[j].x & 0xffff); r[j][1] = l[j].x >> 16; r[j][2] = (int16_t)(l[j].y & 0xffff); r[j][3] = l[j].y >> 16;
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) dbk_luma(r[0][i], r[1][i], r[2][i], r[3][i], st, maxl);
@@ -253,9 +307,32 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
         }
     }
     // chroma: only the head of a run of consecutive segments works; it walks the run in the reference's order
-    if (!dbk_has_edge_c(a, sx, sy, VERTICAL)) return;
-    const int psx = VERTICAL ? sx - 1 : sx, psy = VERTICAL ? sy : sy - 1;
-    if (dbk_has_edge_c(a, psx, psy, VERTICAL)) return;
+    if ((e & (kEdge | kNoc)) != kEdge) return;
+    if ((VERTICAL ? sx - 1 > 0 : sy - 1 > 0) && (e_prev & (kEdge | kNoc)) == kEdge) return;
+    if (!(has_next && (e_next & (kEdge | kNoc)) == kEdge)) {
+        // a segment without neighbours in its row / column (any CU wider / higher than 4): nobody else touches its samples in this pass
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int s = k ? st_v : st_u;
+            if (!s) continue;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                if (VERTICAL) {
+                    pel *q = pc[k] + (size_t)i * a.s_c;
+                    int A = (int16_t)(c[k][i].x & 0xffff), B = c[k][i].x >> 16, C = (int16_t)(c[k][i].y & 0xffff), D = c[k][i].y >> 16;
+                    dbk_chroma(A, B, C, D, s, maxc);
+                    q[-1] = (pel)B; q[0] = (pel)C;
+                } else {
+                    pel *q = pc[k] + i;
+                    int A = i ? c[k][0].x >> 16 : (int16_t)(c[k][0].x & 0xffff), B = i ? c[k][0].y >> 16 : (int16_t)(c[k][0].y & 0xffff);
+                    int C = i ? c[k][1].x >> 16 : (int16_t)(c[k][1].x & 0xffff), D = i ? c[k][1].y >> 16 : (int16_t)(c[k][1].y & 0xffff);
+                    dbk_chroma(A, B, C, D, s, maxc);
+                    q[-a.s_c] = (pel)B; q[0] = (pel)C;
+                }
+            }
+        }
+        return;
+    }
     if (VERTICAL && a.map_order) {
         // SUCO: the reference filters an edge when the LATER of its two CUs is visited (its left edge, then its right edge; xevdm_df.c:272-300),
         // so inside a run the order is not left-to-right.  Only neighbouring edges interact: walk every maximal stretch of decreasing visit
@@ -298,19 +375,17 @@ __constant__ uint8_t c_addb_clip[52][5] = {
 __device__ __forceinline__ int addb_index(int qp, int offset) { return xb_clip3(0, 51, (qp & 0xff) + (offset & 0xff)); }   // u8 arguments in the reference
 __device__ __forceinline__ bool addb_near(int ax, int ay, int bx, int by) { return abs(ax - bx) < 4 && abs(ay - by) < 4; }
 
-__device__ __forceinline__ int addb_bs(const DbkArgs &a, int cur, int nb, int x0, int y0, int x1, int y1)
+// get_bs (xevdm_df.c:361-470).  m = map_scu words, ats = ats_present of either CU, r = reference index pairs, v = vector pairs (the caller picks
+// map_unrefined_mv where the DMVR flag of m is set), cross_ctu = the edge lies on a CTU boundary
+__device__ __forceinline__ int addb_bs_v(const DbkArgs &a, uint32_t m0, uint32_t m1, bool ats, int r0, int r1, int2 v0, int2 v1, bool cross_ctu)
 {
-    const uint32_t m0 = a.map_scu[cur], m1 = a.map_scu[nb];
     const bool intra = ((m0 | m1) >> 15) & 1;
-    if (intra) return ((x0 >> a.log2_ctu) != (x1 >> a.log2_ctu) || (y0 >> a.log2_ctu) != (y1 >> a.log2_ctu)) ? 4 : 3;
+    if (intra) return cross_ctu ? 4 : 3;
     if (((m0 | m1) >> 26) & 1) return 3;
-    if ((((m0 | m1) >> 24) & 1) || ((a.map_edge[cur] | a.map_edge[nb]) & XB200_EDGE_ATS)) return 2;     // luma cbf or ats_present (xevdm_df.c:415)
-    const int16_t r0 = ((const int16_t *)a.map_refi)[cur], r1 = ((const int16_t *)a.map_refi)[nb];
+    if ((((m0 | m1) >> 24) & 1) || ats) return 2;     // luma cbf or ats_present (xevdm_df.c:415)
     const int8_t r00 = (int8_t)(r0 & 0xff), r01 = (int8_t)(r0 >> 8), r10 = (int8_t)(r1 & 0xff), r11 = (int8_t)(r1 >> 8);
     const int pa0 = r00 >= 0 ? a.ref_id[0][r00] : -1, pa1 = r01 >= 0 ? a.ref_id[1][r01] : -1;
     const int pb0 = r10 >= 0 ? a.ref_id[0][r10] : -1, pb1 = r11 >= 0 ? a.ref_id[1][r11] : -1;
-    // xevdm_deblock copies map_mv over map_unrefined_mv wherever the DMVR flag is not set before it walks the tree (xevdm.c:2077-2090)
-    const int2 v0 = ((const int2 *)(((m0 >> 25) & 1) ? a.map_umv : a.map_mv))[cur], v1 = ((const int2 *)(((m1 >> 25) & 1) ? a.map_umv : a.map_mv))[nb];
     int a0x = (int16_t)(v0.x & 0xffff), a0y = v0.x >> 16, a1x = (int16_t)(v0.y & 0xffff), a1y = v0.y >> 16;
     int b0x = (int16_t)(v1.x & 0xffff), b0y = v1.x >> 16, b1x = (int16_t)(v1.y & 0xffff), b1y = v1.y >> 16;
     if (r00 < 0) a0x = a0y = 0;
@@ -372,45 +447,85 @@ __device__ __forceinline__ void addb_chroma(int (&p)[2], int (&q)[2], int bs, in
     p[1] = xb_clip3(0, maxv, p[1]); q[1] = xb_clip3(0, maxv, q[1]);
 }
 
+// One thread per segment of the 8x8 luma grid: lane <-> every second SCU column (vertical edges) / warp <-> every second SCU row (horizontal).
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ DbkArgs a)
 {
-    const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int gi = blockIdx.x * 32 + (threadIdx.x & 31), gj = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int sx = VERTICAL ? 2 * gi : gi, sy = VERTICAL ? gj : 2 * gj;
     if (sx >= a.w_scu || sy >= a.h_scu) return;
-    if (!dbk_has_edge(a, sx, sy, VERTICAL)) return;
-    if ((VERTICAL ? sx : sy) & 1) return;                                   // 8x8 luma grid only
-    const int cur = sy * a.w_scu + sx, nb = VERTICAL ? cur - 1 : cur - a.w_scu;
+    constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
+    const bool inner = VERTICAL ? sx > 0 : sy > 0;
+    const int cur = sy * a.w_scu + sx, nb = inner ? (VERTICAL ? cur - 1 : cur - a.w_scu) : cur;
     const int x = sx << 2, y = sy << 2;
-    const int bs = addb_bs(a, cur, nb, x, y, VERTICAL ? x - 1 : x, VERTICAL ? y : y - 1);
-    const int qp = (((a.map_scu[cur] >> 16) & 0x7f) + ((a.map_scu[nb] >> 16) & 0x7f) + 1) >> 1;
+    // ---- everything the segment reads, in one round trip (see ld_now32) ----
+    const unsigned e = ld_now8(a.map_edge + cur), e_nb = ld_now8(a.map_edge + nb);
+    const uint32_t m0 = (uint32_t)ld_now32(a.map_scu + cur), m1 = (uint32_t)ld_now32(a.map_scu + nb);
+    const int r0 = ld_now16((const int16_t *)a.map_refi + cur), r1 = ld_now16((const int16_t *)a.map_refi + nb);
+    int2 v0 = ld_now64((const int2 *)a.map_mv + cur), v1 = ld_now64((const int2 *)a.map_mv + nb);
+    pel *base = a.y + (size_t)y * a.s_l + x;
+    pel *cb[2] = {a.u + (size_t)(y >> 1) * a.s_c + (x >> 1), a.v + (size_t)(y >> 1) * a.s_c + (x >> 1)};
+    int2 l[8];            // VERTICAL: row i: samples p3 p2 p1 p0 (l[2i]) | q0 q1 q2 q3 (l[2i+1]); else rows -4..3, the segment's four columns
+    int c[2][4];          // VERTICAL: plane k, row i: p1 p0 (c[k][2i]) | q0 q1 (c[k][2i+1]); else plane k, rows -2..1, the segment's two columns
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (VERTICAL) { l[2 * i] = ld_now64(base + (size_t)i * a.s_l - 4); l[2 * i + 1] = ld_now64(base + (size_t)i * a.s_l); }
+        else { l[2 * i] = ld_now64(base + (ptrdiff_t)(2 * i - 4) * a.s_l); l[2 * i + 1] = ld_now64(base + (ptrdiff_t)(2 * i - 3) * a.s_l); }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            if (VERTICAL) { c[k][2 * i] = ld_now32(cb[k] + (size_t)i * a.s_c - 2); c[k][2 * i + 1] = ld_now32(cb[k] + (size_t)i * a.s_c); }
+            else { c[k][2 * i] = ld_now32(cb[k] + (ptrdiff_t)(2 * i - 2) * a.s_c); c[k][2 * i + 1] = ld_now32(cb[k] + (ptrdiff_t)(2 * i - 1) * a.s_c); }
+        }
+    if (!(inner && (e & kEdge))) return;
+    // xevdm_deblock copies map_mv over map_unrefined_mv wherever the DMVR flag is not set before it walks the tree (xevdm.c:2077-2090)
+    if ((m0 >> 25) & 1) v0 = ((const int2 *)a.map_umv)[cur];
+    if ((m1 >> 25) & 1) v1 = ((const int2 *)a.map_umv)[nb];
+    const int x1 = VERTICAL ? x - 1 : x, y1 = VERTICAL ? y : y - 1;
+    const int bs = addb_bs_v(a, m0, m1, ((e | e_nb) & XB200_EDGE_ATS) != 0, r0, r1, v0, v1,
+                             (x >> a.log2_ctu) != (x1 >> a.log2_ctu) || (y >> a.log2_ctu) != (y1 >> a.log2_ctu));
+    const int qp = (((m0 >> 16) & 0x7f) + ((m1 >> 16) & 0x7f) + 1) >> 1;
     const int scale = a.bd_l - 8;
     {
         const int ia = addb_index(qp, a.alpha_offset), ib = addb_index(qp, a.beta_offset);
         const int alpha = (c_addb_alpha[ia] << scale) & 0xffff, beta = (c_addb_beta[ib] << scale) & 0xff;
         const int c1 = (c_addb_clip[ia][bs] << max(0, a.bd_l - 9)) & 0xff;
-        pel *base = a.y + (size_t)y * a.s_l + x;
+        if (VERTICAL) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int p[4], q[4];
-            if (VERTICAL) {
+            for (int i = 0; i < 4; i++) {
+                int p[4], q[4];
                 pel *r = base + (size_t)i * a.s_l;
-                const int2 lo = *(const int2 *)(r - 4), hi = *(const int2 *)r;
+                const int2 lo = l[2 * i], hi = l[2 * i + 1];
                 p[3] = (int16_t)(lo.x & 0xffff); p[2] = lo.x >> 16; p[1] = (int16_t)(lo.y & 0xffff); p[0] = lo.y >> 16;
                 q[0] = (int16_t)(hi.x & 0xffff); q[1] = hi.x >> 16; q[2] = (int16_t)(hi.y & 0xffff); q[3] = hi.y >> 16;
                 addb_luma(p, q, bs, alpha, beta, c1, a.bd_l);
                 *(int2 *)(r - 4) = make_int2((p[3] & 0xffff) | (p[2] << 16), (p[1] & 0xffff) | (p[0] << 16));
                 *(int2 *)r = make_int2((q[0] & 0xffff) | (q[1] << 16), (q[2] & 0xffff) | (q[3] << 16));
-            } else {
-                pel *c = base + i;
+            }
+        } else {
+            int o[8][4];     // filtered rows -4..3
 #pragma unroll
-                for (int k = 0; k < 4; k++) { q[k] = c[(ptrdiff_t)k * a.s_l]; p[k] = c[-(ptrdiff_t)(k + 1) * a.s_l]; }
+            for (int i = 0; i < 4; i++) {
+                int p[4], q[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int2 rq = l[4 + k], rp = l[3 - k];
+                    const int wq = i < 2 ? rq.x : rq.y, wp = i < 2 ? rp.x : rp.y;
+                    q[k] = (i & 1) ? wq >> 16 : (int16_t)(wq & 0xffff);
+                    p[k] = (i & 1) ? wp >> 16 : (int16_t)(wp & 0xffff);
+                }
                 addb_luma(p, q, bs, alpha, beta, c1, a.bd_l);
 #pragma unroll
-                for (int k = 0; k < 4; k++) { c[(ptrdiff_t)k * a.s_l] = (pel)q[k]; c[-(ptrdiff_t)(k + 1) * a.s_l] = (pel)p[k]; }
+                for (int k = 0; k < 4; k++) { o[4 + k][i] = q[k]; o[3 - k][i] = p[k]; }
             }
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                *(int2 *)(base + (ptrdiff_t)(j - 4) * a.s_l) = make_int2((o[j][0] & 0xffff) | (o[j][1] << 16), (o[j][2] & 0xffff) | (o[j][3] << 16));
         }
     }
-    if (!dbk_has_edge_c(a, sx, sy, VERTICAL)) return;      // inner leaf boundary of a local dual tree node: a luma edge only (xevdm_df.c:916-920,986-997)
+    if ((e & (kEdge | kNoc)) != kEdge) return;      // inner leaf boundary of a local dual tree node: a luma edge only (xevdm_df.c:916-920,986-997)
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int qc = xb_clip3(-6 * (a.bd_c - 8), 57, qp + (k ? a.qp_v_offset : a.qp_u_offset));
@@ -418,15 +533,19 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
         const int ia = addb_index(qm, a.alpha_offset), ib = addb_index(qm, a.beta_offset);
         const int alpha = (c_addb_alpha[ia] << scale) & 0xffff, beta = (c_addb_beta[ib] << scale) & 0xff;
         const int c0 = ((c_addb_clip[ia][bs] + 1) << max(0, a.bd_c - 9)) & 0xff;
-        pel *base = (k ? a.v : a.u) + (size_t)(y >> 1) * a.s_c + (x >> 1);
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             int p[2], q[2];
-            const ptrdiff_t st = VERTICAL ? 1 : a.s_c;
-            pel *c = VERTICAL ? base + (size_t)i * a.s_c : base + i;
-            q[0] = c[0]; q[1] = c[st]; p[0] = c[-st]; p[1] = c[-2 * st];
+            if (VERTICAL) {
+                p[1] = (int16_t)(c[k][2 * i] & 0xffff); p[0] = c[k][2 * i] >> 16; q[0] = (int16_t)(c[k][2 * i + 1] & 0xffff); q[1] = c[k][2 * i + 1] >> 16;
+            } else {
+                p[1] = i ? c[k][0] >> 16 : (int16_t)(c[k][0] & 0xffff); p[0] = i ? c[k][1] >> 16 : (int16_t)(c[k][1] & 0xffff);
+                q[0] = i ? c[k][2] >> 16 : (int16_t)(c[k][2] & 0xffff); q[1] = i ? c[k][3] >> 16 : (int16_t)(c[k][3] & 0xffff);
+            }
             addb_chroma(p, q, bs, alpha, beta, c0, a.bd_c);
-            c[0] = (pel)q[0]; c[st] = (pel)q[1]; c[-st] = (pel)p[0]; c[-2 * st] = (pel)p[1];
+            const ptrdiff_t st = VERTICAL ? 1 : a.s_c;
+            pel *cc = VERTICAL ? cb[k] + (size_t)i * a.s_c : cb[k] + i;
+            cc[0] = (pel)q[0]; cc[st] = (pel)q[1]; cc[-st] = (pel)p[0]; cc[-2 * st] = (pel)p[1];
         }
     }
 }
@@ -435,8 +554,8 @@ inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
 {
     const dim3 grid((a.w_scu + 31) / 32, (a.h_scu + 7) / 8);
     if (addb) {
-        k_deblock_addb<true><<<grid, 256, 0, st>>>(a);
-        k_deblock_addb<false><<<grid, 256, 0, st>>>(a);
+        k_deblock_addb<true><<<dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + 7) / 8), 256, 0, st>>>(a);
+        k_deblock_addb<false><<<dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + 7) / 8), 256, 0, st>>>(a);
     } else {
         k_deblock<true><<<grid, 256, 0, st>>>(a);
         k_deblock<false><<<grid, 256, 0, st>>>(a);
