@@ -87,28 +87,29 @@ __device__ __forceinline__ int dbk_st(int cls, int q)
 // Loads that are issued before the first test of a thread: a segment's work is a chain edge flag -> maps of both SCUs -> samples -> stores,
 // three dependent memory round trips (long_scoreboard 20.7 per issue, 19 % of the HBM peak in profiles/r1/deblock_ncu_summary.txt).  The
 // deblocking kernels fetch all of it at once, for every thread; `volatile` keeps the compiler from sinking a load below the test of its use.
+// (Generic addresses of cudaMalloc'ed memory are global-window addresses: no cvta, which cost 5.7 % of the instructions of a pass.)
 __device__ __forceinline__ int ld_now32(const void *p)
 {
     int v;
-    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 __device__ __forceinline__ int2 ld_now64(const void *p)
 {
     int2 v;
-    asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(__cvta_generic_to_global(p)));
+    asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ int ld_now16(const void *p)
 {
     unsigned short v;
-    asm volatile("ld.global.b16 %0, [%1];" : "=h"(v) : "l"(__cvta_generic_to_global(p)));
+    asm volatile("ld.global.b16 %0, [%1];" : "=h"(v) : "l"(p));
     return (int16_t)v;
 }
 __device__ __forceinline__ unsigned ld_now8(const void *p)
 {
     unsigned v;
-    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
 
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256) k_clear_tile_edges(const __grid_constant_
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs a)
 {
-    const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (sx >= a.w_scu || sy >= a.h_scu) return;
     constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
     const bool inner = VERTICAL ? sx > 0 : sy > 0, has_next = VERTICAL ? sx + 1 < a.w_scu : sy + 1 < a.h_scu;
@@ -451,7 +452,7 @@ __device__ __forceinline__ void addb_chroma(int (&p)[2], int (&q)[2], int bs, in
 template <bool VERTICAL>
 __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ DbkArgs a)
 {
-    const int gi = blockIdx.x * 32 + (threadIdx.x & 31), gj = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int gi = blockIdx.x * 32 + (threadIdx.x & 31), gj = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int sx = VERTICAL ? 2 * gi : gi, sy = VERTICAL ? gj : 2 * gj;
     if (sx >= a.w_scu || sy >= a.h_scu) return;
     constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
@@ -552,13 +553,14 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
 
 inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
 {
-    const dim3 grid((a.w_scu + 31) / 32, (a.h_scu + 7) / 8);
+    // rows of SCUs (warps) per CTA: 1, 2, 4 and 8 measure the same (profiles/r2/ab_log.txt) - the passes are not bound by resident warps
+    constexpr int rv = 8, rh = 8;
     if (addb) {
-        k_deblock_addb<true><<<dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + 7) / 8), 256, 0, st>>>(a);
-        k_deblock_addb<false><<<dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + 7) / 8), 256, 0, st>>>(a);
+        k_deblock_addb<true><<<dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
+        k_deblock_addb<false><<<dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + rh - 1) / rh), 32 * rh, 0, st>>>(a);
     } else {
-        k_deblock<true><<<grid, 256, 0, st>>>(a);
-        k_deblock<false><<<grid, 256, 0, st>>>(a);
+        k_deblock<true><<<dim3((a.w_scu + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
+        k_deblock<false><<<dim3((a.w_scu + 31) / 32, (a.h_scu + rh - 1) / rh), 32 * rh, 0, st>>>(a);
     }
 }
 
