@@ -113,6 +113,15 @@ __device__ __forceinline__ unsigned ld_now8(const void *p)
     return v;
 }
 
+// The horizontal-edge pass is launched with programmatic stream serialisation (launch_deblock): its CTAs become resident while the vertical-edge
+// pass drains, fetch the maps - which the vertical pass does not write - and only then wait for the vertical pass to complete and become visible.
+template <bool VERTICAL>
+__device__ __forceinline__ void dbk_pass_order()
+{
+    if (VERTICAL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    else asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // xevdm_get_tbl_qp_to_st (xevdm_df.c:38-104): 0 intra, 1 luma cbf, 2 motion differs (or IBC), 3 no filtering.  m = map_scu word, r = both
 // reference indices (s8 pair), v = both vectors of the current (0) and the neighbouring (1) SCU
 __device__ __forceinline__ int dbk_class_v(uint32_t m0, uint32_t m1, int r0, int r1, int2 v0, int2 v1)
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
     const uint32_t m0 = (uint32_t)ld_now32(a.map_scu + cur), m1 = (uint32_t)ld_now32(a.map_scu + nb);
     const int r0 = ld_now16((const int16_t *)a.map_refi + cur), r1 = ld_now16((const int16_t *)a.map_refi + nb);
     const int2 v0 = ld_now64((const int2 *)a.map_mv + cur), v1 = ld_now64((const int2 *)a.map_mv + nb);
+    dbk_pass_order<VERTICAL>();
     pel *p = a.y + (size_t)(sy * 4) * a.s_l + sx * 4;
     pel *pc[2] = {a.u + (size_t)(sy * 2) * a.s_c + sx * 2, a.v + (size_t)(sy * 2) * a.s_c + sx * 2};
     int2 l[4];            // VERTICAL: row i, samples A B | C D around the edge; else row j - 2, the segment's four columns
@@ -464,6 +474,7 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
     const uint32_t m0 = (uint32_t)ld_now32(a.map_scu + cur), m1 = (uint32_t)ld_now32(a.map_scu + nb);
     const int r0 = ld_now16((const int16_t *)a.map_refi + cur), r1 = ld_now16((const int16_t *)a.map_refi + nb);
     int2 v0 = ld_now64((const int2 *)a.map_mv + cur), v1 = ld_now64((const int2 *)a.map_mv + nb);
+    dbk_pass_order<VERTICAL>();
     pel *base = a.y + (size_t)y * a.s_l + x;
     pel *cb[2] = {a.u + (size_t)(y >> 1) * a.s_c + (x >> 1), a.v + (size_t)(y >> 1) * a.s_c + (x >> 1)};
     int2 l[8];            // VERTICAL: row i: samples p3 p2 p1 p0 (l[2i]) | q0 q1 q2 q3 (l[2i+1]); else rows -4..3, the segment's four columns
@@ -551,16 +562,28 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
     }
 }
 
+template <typename K>
+inline void launch_after_start(K kernel, dim3 grid, int threads, cudaStream_t st, const DbkArgs &a)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
 {
     // rows of SCUs (warps) per CTA: 1, 2, 4 and 8 measure the same (profiles/r2/ab_log.txt) - the passes are not bound by resident warps
     constexpr int rv = 8, rh = 8;
     if (addb) {
         k_deblock_addb<true><<<dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
-        k_deblock_addb<false><<<dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + rh - 1) / rh), 32 * rh, 0, st>>>(a);
+        launch_after_start(k_deblock_addb<false>, dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + rh - 1) / rh), 32 * rh, st, a);
     } else {
         k_deblock<true><<<dim3((a.w_scu + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
-        k_deblock<false><<<dim3((a.w_scu + 31) / 32, (a.h_scu + rh - 1) / rh), 32 * rh, 0, st>>>(a);
+        launch_after_start(k_deblock<false>, dim3((a.w_scu + 31) / 32, (a.h_scu + rh - 1) / rh), 32 * rh, st, a);
     }
 }
 
