@@ -615,8 +615,9 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
         const bool ws = !peer && (c->v2_variant == 2 || (c->v2_variant == 0 && (long long)n_cu <= 32LL * a.n_ctu));
         const xb::R2Layout L = xb::R2Layout::make(bi ? 2 : 1, max_cu, peer, ws);
         const dim3 grid(a.w_ctu, a.n_ctu / a.w_ctu);
-#define XB_V2(BI_, IQT_, DISP_) do { if (ws) xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu); \
-                                     else xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, false><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu); } while (0)
+        // launched early: resident while the kernel before (the previous picture's padding, an expansion kernel) drains; waits before its first global access
+#define XB_V2(BI_, IQT_, DISP_) do { if (ws) xb_launch_early(xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, true>, grid, dim3(xb::kR2Threads), L.total, c->stream, a, max_cu); \
+                                     else xb_launch_early(xb::k_recon_inter_v2<BI_, false, IQT_, DISP_, false>, grid, dim3(xb::kR2Threads), L.total, c->stream, a, max_cu); } while (0)
         if (peer) {
             if (bi) xb::k_recon_inter_v2<true, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
             else    xb::k_recon_inter_v2<false, true><<<grid, xb::kR2Threads, L.total, c->stream>>>(a, max_cu);
@@ -953,11 +954,11 @@ int xb200_alf(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *p, const XB200_A
             ca.dst[pl] = (int4 *)(c->alf_copy + (rows[pl] - p->buf));
             ca.n[pl] = alf->enable[pl] ? (unsigned)((pl ? (size_t)p->s_c * p->h_c : (size_t)p->s_l * p->h) * sizeof(pel) / 16) : 0u;
         }
-        xb::k_alf_copy<<<c->sm_count * 8, 256, 0, c->stream>>>(ca);
+        xb_launch_early(xb::k_alf_copy, dim3(c->sm_count * 8), dim3(256), 0, c->stream, ca);
         c->launches++;
     }
     const dim3 grid((p->w + xb::kAlfT - 1) / xb::kAlfT, (p->h + xb::kAlfT - 1) / xb::kAlfT);
-    xb::k_alf<<<grid, 256, 0, c->stream>>>(a);
+    xb_launch_early(xb::k_alf, grid, dim3(256), 0, c->stream, a);
     c->launches++;
     CK(c, cudaGetLastError());
     return XB200_OK;

@@ -82,6 +82,8 @@ struct AlfCopyArgs { const int4 *src[3]; int4 *dst[3]; unsigned n[3]; };
 __global__ void __launch_bounds__(256) k_alf_copy(const __grid_constant__ AlfCopyArgs a)
 {
     const unsigned step = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    xb_grid_wait();
+    xb_grid_release();
 #pragma unroll 1
     for (int pl = 0; pl < 3; pl++) {
         const int4 *__restrict__ s = a.src[pl];
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256) k_alf(const __grid_constant__ AlfArgs a)
 
     const int t = threadIdx.x;
     const int x0 = blockIdx.x * kAlfT, y0 = blockIdx.y * kAlfT;
+    xb_grid_wait();
+    xb_grid_release();
     const int tw = min(kAlfT, a.w - x0), th = min(kAlfT, a.h - y0);
     const AlfGeom g = alf_geom(a, x0, y0);
     const bool luma_on = a.enable[0] && (!a.ctb_flag || a.ctb_flag[(y0 >> a.log2_ctu) * a.w_ctu + (x0 >> a.log2_ctu)]);

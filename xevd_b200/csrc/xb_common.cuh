@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 #include "../../include/xevd_b200.h"
 
 #define XB_MAX_REFS 17          // XEVD_MAX_NUM_REF_PICS (21) is never reached per list; 17 = 16 + 1
@@ -64,6 +65,24 @@ __device__ __forceinline__ void xb_store_all(const XbFrameArgs &a, T *dst, T v, 
     *dst = v;
     if (fan_out)
         for (int k = 0; k < a.n_peer; k++) *(T *)((char *)dst + a.peer_delta[k]) = v;
+}
+
+// Programmatic dependent launch (stream serialisation relaxed by the launch attribute below): the CTAs of a kernel launched through
+// xb_launch_early become resident while the kernel before it in the stream drains - once every CTA of that kernel has started - and do their
+// index arithmetic and shared-memory set-up; xb_grid_wait() returns when the kernel before has completed and its stores are visible, so it
+// stands before the first global access.  Both instructions are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void xb_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void xb_grid_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t xb_launch_early(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ int xb_clip3(int lo, int hi, int v) { return max(lo, min(hi, v)); }

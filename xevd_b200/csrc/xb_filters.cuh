@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(128) k_pad(const __grid_constant__ PadArgs a)
     const PadPlane P = a.pl[p];
     const int y = row - a.row_start[p] - P.pad;               // row relative to the picture
     const int ys = min(max(y, 0), P.h - 1);
+    xb_grid_wait();
+    xb_grid_release();
     const pel *src = P.org + (size_t)ys * P.stride;
     pel *dst = P.org + (size_t)y * P.stride;
     const int padv = P.pad >> 2, wv = P.w >> 2;
@@ -41,7 +43,7 @@ inline void launch_pad(pel *y, int s_l, int w, int h, int pad_l, pel *u, pel *v,
     a.row_start[1] = h + 2 * pad_l;
     a.row_start[2] = a.row_start[1] + h_c + 2 * pad_c;
     a.row_start[3] = a.row_start[2] + h_c + 2 * pad_c;
-    k_pad<<<a.row_start[3], 128, 0, st>>>(a);
+    xb_launch_early(k_pad, dim3(a.row_start[3]), dim3(128), 0, st, a);
 }
 
 }  // namespace xb
@@ -118,8 +120,8 @@ __device__ __forceinline__ unsigned ld_now8(const void *p)
 template <bool VERTICAL>
 __device__ __forceinline__ void dbk_pass_order()
 {
-    if (VERTICAL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    else asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (VERTICAL) xb_grid_release();
+    else xb_grid_wait();
 }
 
 // xevdm_get_tbl_qp_to_st (xevdm_df.c:38-104): 0 intra, 1 luma cbf, 2 motion differs (or IBC), 3 no filtering.  m = map_scu word, r = both
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(256) k_deblock(const __grid_constant__ DbkArgs
 {
     const int sx = blockIdx.x * 32 + (threadIdx.x & 31), sy = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (sx >= a.w_scu || sy >= a.h_scu) return;
+    if (VERTICAL) xb_grid_wait();          // the maps and samples come from the kernels before; the horizontal pass waits below, after its map loads
     constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
     const bool inner = VERTICAL ? sx > 0 : sy > 0, has_next = VERTICAL ? sx + 1 < a.w_scu : sy + 1 < a.h_scu;
     const int cur = sy * a.w_scu + sx, nb = inner ? (VERTICAL ? cur - 1 : cur - a.w_scu) : cur, nx = has_next ? (VERTICAL ? cur + 1 : cur + a.w_scu) : cur;
@@ -465,6 +468,7 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
     const int gi = blockIdx.x * 32 + (threadIdx.x & 31), gj = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int sx = VERTICAL ? 2 * gi : gi, sy = VERTICAL ? gj : 2 * gj;
     if (sx >= a.w_scu || sy >= a.h_scu) return;
+    if (VERTICAL) xb_grid_wait();          // the maps and samples come from the kernels before; the horizontal pass waits below, after its map loads
     constexpr unsigned kEdge = VERTICAL ? XB200_EDGE_LEFT : XB200_EDGE_TOP, kNoc = VERTICAL ? XB200_EDGE_LEFT_NOC : XB200_EDGE_TOP_NOC;
     const bool inner = VERTICAL ? sx > 0 : sy > 0;
     const int cur = sy * a.w_scu + sx, nb = inner ? (VERTICAL ? cur - 1 : cur - a.w_scu) : cur;
@@ -562,28 +566,16 @@ __global__ void __launch_bounds__(256) k_deblock_addb(const __grid_constant__ Db
     }
 }
 
-template <typename K>
-inline void launch_after_start(K kernel, dim3 grid, int threads, cudaStream_t st, const DbkArgs &a)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, a);
-}
-
 inline void launch_deblock(const DbkArgs &a, bool addb, cudaStream_t st)
 {
     // rows of SCUs (warps) per CTA: 1, 2, 4 and 8 measure the same (profiles/r2/ab_log.txt) - the passes are not bound by resident warps
     constexpr int rv = 8, rh = 8;
     if (addb) {
-        k_deblock_addb<true><<<dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
-        launch_after_start(k_deblock_addb<false>, dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + rh - 1) / rh), 32 * rh, st, a);
+        xb_launch_early(k_deblock_addb<true>, dim3(((a.w_scu + 1) / 2 + 31) / 32, (a.h_scu + rv - 1) / rv), dim3(32 * rv), 0, st, a);
+        xb_launch_early(k_deblock_addb<false>, dim3((a.w_scu + 31) / 32, ((a.h_scu + 1) / 2 + rh - 1) / rh), dim3(32 * rh), 0, st, a);
     } else {
-        k_deblock<true><<<dim3((a.w_scu + 31) / 32, (a.h_scu + rv - 1) / rv), 32 * rv, 0, st>>>(a);
-        launch_after_start(k_deblock<false>, dim3((a.w_scu + 31) / 32, (a.h_scu + rh - 1) / rh), 32 * rh, st, a);
+        xb_launch_early(k_deblock<true>, dim3((a.w_scu + 31) / 32, (a.h_scu + rv - 1) / rv), dim3(32 * rv), 0, st, a);
+        xb_launch_early(k_deblock<false>, dim3((a.w_scu + 31) / 32, (a.h_scu + rh - 1) / rh), dim3(32 * rh), 0, st, a);
     }
 }
 

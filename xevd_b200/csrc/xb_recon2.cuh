@@ -357,6 +357,8 @@ k_recon_inter_v2(const __grid_constant__ XbFrameArgs a, const int max_cu)
     const int ctu_x = blockIdx.x << 6, ctu_y = (blockIdx.y + a.ctu_row0) << 6;
     // the host entry points route pictures with more CUs per CTU than the lists hold to the generic kernel; the clamp keeps a wrong
     // max_cu_per_ctu handed to the _dev entry from overrunning shared memory
+    xb_grid_wait();            // launched early (xb_launch_early): the work lists, the reference pictures and this picture belong to the kernels before
+    xb_grid_release();
     const int cu0 = a.ctu_first[ctu], ncu = min((int)(a.ctu_first[ctu + 1] - cu0), max_cu);
 
     // ---- coefficient slice of this CTU: CUs are in decoding order, so their blocks are one contiguous range of the stream.  One bulk
