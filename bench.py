@@ -127,7 +127,9 @@ def common_config(args, world):
     return {"workload": args.workload, "picture": f"{w}x{h} 4:2:0 {bd}-bit",
             "cu_partition": "uniform 16x16 uni-pred all-coded" if variant == "A" else "quadtree 64..8, 50% bi-pred",
             "per_picture": "MC + dequant / inverse transform + reconstruction of every CU (xevd_ctu_row_rec_mt), then border padding (xevd_picbuf_expand)",
-            "sharding": args.sharding, "n_gpus": world, "l2": "every step streams more than the 126 MB L2 (distinct pictures in rotation)"}
+            "sharding": args.sharding, "n_gpus": world,
+            "per_device": "independent GOPs decoded side by side (GPU arm: three streams per GPU; reference arm: one decoder instance per host core)",
+            "l2": "every step streams more than the 126 MB L2 (distinct pictures in rotation)"}
 
 
 def make_workload(name, n_distinct, seed0=1):
@@ -259,6 +261,16 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local)
     ctx.set_stream(stream.cuda_stream)
+    # GOP sharding: pictures of different GOPs do not depend on each other, so one GPU decodes G GOPs side by side, one context / stream per
+    # GOP (the reference arm's host cores do the same: one decoder instance per core).  The kernels of one stream follow each other; the last
+    # wave of a picture's CTAs (2040 CTUs over 444 resident CTAs = 4.6 waves) shares the SMs with the first wave of the other GOP's picture.
+    n_gop = 1 if band else max(1, int(os.environ.get("XB200_BENCH_GOP_STREAMS", "3")))
+    gop_ctx, gop_stream = [ctx], [stream]
+    for _ in range(n_gop - 1):
+        st_ = torch.cuda.Stream(device=dev)
+        c_ = Context(local)
+        c_.set_stream(st_.cuda_stream)
+        gop_ctx.append(c_); gop_stream.append(st_)
 
     # ---- resident inputs: F slots, each with its own reference picture(s), CU array, coefficients, output picture
     host_refs = synth.make_refs(w, h, bd, 2, seed=1000 + (0 if band else rank))
@@ -266,15 +278,16 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         for i in range(F):
             prm, cl = frames[i % len(frames)]
-            refs = [ctx.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
+            sc = gop_ctx[i % n_gop]                      # a device picture belongs to the context / stream that fills it
+            refs = [sc.pic_alloc(w, h).upload(host_refs[(i + j) % 2]) for j in range(n_refs)]
             for j, r in enumerate(refs):
                 r.set_poc(host_refs[(i + j) % 2].poc if n_refs > 1 else 0)
-            cur = ctx.pic_alloc(w, h)
+            cur = sc.pic_alloc(w, h)
             d_cus = torch.from_numpy(cl.cus.view(np.uint8).copy()).to(dev)
             d_first = torch.from_numpy(cl.ctu_first.view(np.int32).copy()).to(dev)
             d_ext = torch.from_numpy(cl.ext.view(np.uint8).copy()).to(dev)
             d_coef = torch.from_numpy(cl.coef.copy()).to(dev)
-            slots.append(dict(prm=prm, cl=cl, refs=refs, refs_l1=(refs[::-1] if variant != "A" else []), cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef,
+            slots.append(dict(ctx=sc, prm=prm, cl=cl, refs=refs, refs_l1=(refs[::-1] if variant != "A" else []), cur=cur, d_cus=d_cus, d_first=d_first, d_ext=d_ext, d_coef=d_coef,
                               max_cu=int(np.diff(cl.ctu_first.astype(np.int64)).max())))
     torch.cuda.synchronize()
     exch = xdist.BandExchange(ctx, slots[0]["cur"], 6, rank, world, dev) if (band and not p2p) else None
@@ -295,15 +308,15 @@ def run_ours(args):
             for s in slots:
                 cl = s["cl"]
                 if cl.n_cu:
-                    ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
-                                        s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
-                                        max_cu_per_ctu=s["max_cu"])
+                    s["ctx"].recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
+                                             s["d_first"].data_ptr(), cl.n_ctu, s["d_ext"].data_ptr(), len(cl.ext), s["d_coef"].data_ptr(), cl.coef.size,
+                                             max_cu_per_ctu=s["max_cu"])
                 if exch is not None:
                     with torch.cuda.stream(stream):
                         exch.exchange(s["cur"])              # one in-place NCCL all-gather of the packed bands per picture
                 elif p2p:
                     stream_barrier()
-                ctx.pad(s["cur"])
+                s["ctx"].pad(s["cur"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -318,26 +331,33 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
+    l0 = sum(c_.launches for c_ in gop_ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record(stream)
+        for st_ in gop_stream[1:]:
+            st_.wait_event(e0)                            # the timed region opens on every GOP stream at e0 ...
         for _ in range(args.steps):
             step_resident()
+        for st_ in gop_stream[1:]:
+            done_ = torch.cuda.Event()
+            done_.record(st_)
+            stream.wait_event(done_)                      # ... and closes when the last of them has finished
         e1.record(stream)
     barrier()
-    launches = ctx.launches - l0
+    launches = sum(c_.launches for c_ in gop_ctx) - l0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     ms = xdist.max_over_ranks(ms, dev)
     fps = (1 if band else world) * P * F * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (k_recon_inter): per-launch CUDA-event timing on the launching stream --------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(F * min(args.steps, 4))]
+    own = [s for s in slots if s["ctx"] is ctx]           # the pictures of the first GOP stream, one kernel at a time (> L2 in rotation)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(len(own) * min(args.steps, 4) * n_gop)]
     k = 0
     with torch.cuda.stream(stream):
-        for _ in range(min(args.steps, 4)):
-            for s in slots:
+        for _ in range(min(args.steps, 4) * n_gop):
+            for s in own:
                 cl = s["cl"]
                 ev[k][0].record(stream)
                 ctx.recon_frame_dev(s["prm"], s["cur"], s["refs"], s["refs_l1"], s["d_cus"].data_ptr(), cl.n_cu,
@@ -515,7 +535,7 @@ def run_ours(args):
             "dtype": "s16", "data": "synthetic",
             "config": common_config(args, world),
             "detail": {"frames_per_step": P * F * (1 if band else world), "distinct_picture_slots": F,
-                       "calls_per_picture": ("xb200_recon_frame_dev (band, stores fanned out to the peer GPUs over NVLink) + stream barrier + xb200_pad" if p2p else
+                       "gop_streams_per_gpu": n_gop, "calls_per_picture": ("xb200_recon_frame_dev (band, stores fanned out to the peer GPUs over NVLink) + stream barrier + xb200_pad" if p2p else
                                              "xb200_recon_frame_dev (band) + NCCL all-gather of bands + xb200_pad") if band else "xb200_recon_frame_dev + xb200_pad",
                        "parallelism": (f"ctu-row bands x{world} (peer stores fused into the kernel)" if p2p else f"ctu-row bands x{world} (one all-gather per picture)") if band else f"gop-sharded x{world}",
                        "l2": f"{F} distinct picture slots x ~{(alg + 2 * w * h * 3) / 1e6:.0f} MB per rotation per GPU, {P} rotations per step; the slots share "
