@@ -164,7 +164,7 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
         log(f"extra: {name}: {us:.1f} us, {e['roofline']['frac']:.3f} of HBM peak" + (f", CPU 1 thread {cpu1:.1f}/s" if cpu1 else "") + (f", {cores} cores {cpun:.1f}/s" if cpun else ""))
 
     # ---- inter pictures --------------------------------------------------------------------------------------------------------
-    def inter_case(name, w, h, variant, all_cores=False, **kw):
+    def inter_case(name, w, h, variant, all_cores=False, concurrent=3, **kw):
         n_refs = 1 if variant == "A" else 2
         host_refs = synth.make_refs(w, h, bd, n_refs, seed=7)
         drefs = [ctx.pic_alloc(w, h).upload(r) for r in host_refs]
@@ -175,13 +175,52 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
             works.append((prm, cl, upload_work(cl)))
         r1 = [] if variant == "A" else drefs[::-1]
         us = timed(lambda i: (recon(ctx, works[i % 2][0], curs[i], drefs, r1, works[i % 2][2], 0), ctx.pad(curs[i])))
+        more = {}
+        if concurrent:
+            # independent GOPs side by side, one context / stream each (what bench.py's headline leg does): the tail wave of one picture's grid
+            # overlaps the head of another's - a 1080p picture is 510 CTUs, 1.15 waves of the 444 resident CTAs.  Device time between one event
+            # all streams wait for and the last stream's end; enough picture slots to exceed the L2.
+            pic_mb = (w + 288) * (h + 288) * 3 / 1e6
+            per = max(2, int(np.ceil(160.0 / pic_mb / concurrent)))
+            cs, sts, pics = [], [], []
+            for k in range(concurrent):
+                st = torch.cuda.Stream(device=dev)
+                c = Context(dev.index)
+                c.set_stream(st.cuda_stream)
+                cs.append(c); sts.append(st); pics.append([c.pic_alloc(w, h) for _ in range(per)])
+
+            def sweep(n):
+                for j in range(n):
+                    for k, c in enumerate(cs):
+                        wk_ = works[(j + k) % 2]
+                        recon(c, wk_[0], pics[k][j % per], drefs, r1, wk_[2], 0)
+                        c.pad(pics[k][j % per])
+            sweep(per)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(sts[0])
+            for st in sts[1:]:
+                st.wait_event(e0)
+            n_sweep = 4 * per
+            sweep(n_sweep)
+            for st in sts[1:]:
+                d_ = torch.cuda.Event()
+                d_.record(st)
+                sts[0].wait_event(d_)
+            e1.record(sts[0])
+            torch.cuda.synchronize()
+            more = {"gop_streams": concurrent, "frames_per_sec_concurrent": round(n_sweep * concurrent / (e0.elapsed_time(e1) * 1e-3), 1)}
+            for k, c in enumerate(cs):
+                for p_ in pics[k]:
+                    p_.free()
+                c.close()
         cpu1 = cpun = None
         if have_ref:
             payload = (works[0][0], works[0][1], host_refs, [] if variant == "A" else host_refs[::-1], None)
             cpu1 = cpu_rate("cpu_picture", payload, 1, 2)
             if all_cores:
                 cpun = cpu_rate("cpu_picture", payload, cores, 2)
-        entry(name, us, alg_recon(works[0][1]), "xb200_recon_frame_dev + xb200_pad", cpu1, cpun, picture=f"{w}x{h} 4:2:0 {bd}-bit")
+        entry(name, us, alg_recon(works[0][1]), "xb200_recon_frame_dev + xb200_pad", cpu1, cpun, picture=f"{w}x{h} 4:2:0 {bd}-bit", **more)
         for p in drefs + curs:
             p.free()
 

@@ -390,6 +390,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
     for (;;) {
     __syncthreads();                // every thread is done with the previous CTU's shared state
     if (tid == 0) s_ctu = atomicAdd(sy.ticket, 1);
+    const int inter_all_seen = s_inter_all;      // read between barriers: thread 0 sets the word further down (a stale 0 only costs one more look at a.inter_count)
     __syncthreads();
     if (s_ctu >= a.n_ctu) return;
     const int ctu = sy.order[s_ctu];
@@ -431,7 +432,7 @@ k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
         auto le = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + (2 * 128 + 8); };
         auto ri = [&](int pl) -> int16_t * { return s_nb + pl * IntraSmem::kNbElems + 4 + 2 * (2 * 128 + 8); };
         if (a.inter_done) {
-            if (tid == 0 && !s_inter_all) {
+            if (tid == 0 && !inter_all_seen) {       // (the register copy: a shared-memory read here is hoisted above the test of tid and races with the store below)
                 if (*(volatile int *)a.inter_count >= a.n_ctu) s_inter_all = 1;
                 else wait_inter(ctu);
                 __threadfence();
