@@ -272,7 +272,7 @@ def run(torch, ctx, stream, dev, peak, log=lambda s: None, npic=6, reps=4, cores
     prm_x, cl_x = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=21, n_refs=2, coded_frac=0.7)
     synth.add_intra_cus(cl_x, np.random.default_rng(6), 0.1)
     synth.derive_avail_cu(cl_x)
-    wavefront_case("4k-P-intra10", prm_x, cl_x, drefs, drefs[::-1], host_refs, host_refs[::-1])
+    wavefront_case("4k-P-intra10", prm_x, cl_x, drefs, drefs[::-1], host_refs, host_refs[::-1], concurrent=4)
     for eipd in (0, 1):
         prm_i, cl_i = synth.make_inter_frame(w, h, bit_depth=bd, variant="B", seed=9, n_refs=1, coded_frac=0.7, iqt=bool(eipd))
         prm_i.tool_eipd = prm_i.tool_htdf = eipd
