@@ -53,6 +53,7 @@ struct xb200_ctx {
     int device;
     cudaStream_t stream;
     bool own_stream;
+    bool wavefront_alone;        // XB200_WAVEFRONT_ALONE=1: one wavefront CTA per SM
     long long launches;
     char err[256];
     Staging ring[3];
@@ -141,8 +142,8 @@ xb200_ctx *xb200_create(int device, int *err)
                                 if (fe == cudaSuccess) fe = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); } while (0)
     XB_SMEM((xb::k_recon_inter<false>), (int)xb::ReconSmem::bytes(7));
     XB_SMEM((xb::k_recon_inter<true>), (int)xb::ReconSmem::bytes(7));
-    XB_SMEM((xb::k_recon_intra<false>), (int)xb::IntraSmem::bytes());
-    XB_SMEM((xb::k_recon_intra<true>), (int)xb::IntraSmem::bytes());
+    XB_SMEM((xb::k_recon_intra<false>), (int)xb::IntraSmem::bytes(7));
+    XB_SMEM((xb::k_recon_intra<true>), (int)xb::IntraSmem::bytes(7));
     XB_SMEM((xb::k_itdq_blocks<false>), xb::itdq_blocks_smem(1, 6, 32));          // the widest case: 2-wide blocks (row stride w + 4)
     XB_SMEM((xb::k_itdq_blocks<true>), xb::itdq_blocks_smem(1, 6, 32));
     XB_SMEM((xb::k_recon_inter_v2<false>), xb::R2Layout::make(1, 256).total);
@@ -180,6 +181,7 @@ xb200_ctx *xb200_create(int device, int *err)
     { const char *e = getenv("XB200_NO_OVERLAP"); c->no_overlap = e && e[0] == '1'; }
     { const char *e = getenv("XB200_V2_VARIANT"); c->v2_variant = !e ? 0 : (!strcmp(e, "rounds") ? 1 : (!strcmp(e, "slots") ? 2 : 0)); }
     { const char *e = getenv("XB200_PEER_NOMAPS"); c->peer_maps = !(e && e[0] == '1'); }
+    { const char *e = getenv("XB200_WAVEFRONT_ALONE"); c->wavefront_alone = e && e[0] == '1'; }
     {   // packed IDP.2A tap tables for the throughput kernel, derived from the interpolation tables
         int16_t hl[2][16][8], hc[2][32][4];
         cudaMemcpyFromSymbol(hl, c_mc_l, sizeof(hl));
@@ -642,7 +644,11 @@ int xb200_recon_frame_dev(xb200_ctx *c, const XB200_PARAMS *prm, xb200_pic *cur,
     if (has_intra) {
         // intra CUs: CTU wavefront over the picture the inter kernels complete
         xb::IntraSync sy{c->d_sync, c->d_err, c->d_sync + 1, c->d_order};
-        const size_t sm = xb::IntraSmem::bytes();
+        // Two wavefront CTAs share an SM with CTUs of 64 samples and less (91 KB each): +30..50 % pictures/s with several pictures in flight and
+        // -22 % on a P picture's wavefront pass, but a lone I picture's ~40 chained CTAs then also pair up on SMs and its critical path gets
+        // 3..9 % longer.  XB200_WAVEFRONT_ALONE=1 asks for more than half an SM's shared memory, i.e. one CTA per SM (the latency setting).
+        size_t sm = xb::IntraSmem::bytes(a.log2_ctu);
+        if (c->wavefront_alone && sm < (size_t)116 * 1024) sm = (size_t)116 * 1024;
         // persistent CTAs (xb_intra.cuh): dense dependencies (I pictures) -> about as many CTAs as the x + 2y wavefront is wide
         const int h_ctu = a.n_ctu / a.w_ctu;
         int grid = a.n_ctu;

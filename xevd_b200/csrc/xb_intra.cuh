@@ -28,15 +28,18 @@ constexpr int kIntraThreads = 256;
 // not depend on them), the CTU's reconstructed samples (inter CUs preloaded from the picture, wavefront CUs written as they
 // finish, mirrored to global memory), and the row above / column left of the CTU fetched once after the wait.
 struct IntraSmem {
-    static constexpr int kPlaneElems = 128 * 128 + 2 * 64 * 64;     // CTU-raster, luma then Cb, Cr (plane stride = plane CTU size)
+    // CTU-raster samples, luma then Cb, Cr (plane stride = plane CTU size).  Sized by the picture's CTU: with 64x64 CTUs the two arrays take
+    // 24 KB instead of the 96 KB of 128x128 CTUs, the CTA 91 KB instead of 163 KB, and two CTAs share an SM (118 registers allow it) - the
+    // kernel's phases are chains of global-memory round trips that one CTA of eight warps cannot hide.
+    static constexpr int plane_elems(int log2_ctu) { return (1 << (2 * log2_ctu)) * 3 / 2; }
     static constexpr int kTopElems = 2 * 128 + 8;                   // per plane: x = -1 .. 2 * S - 1 of the row above
     static constexpr int kLeftElems = 128;                          // per plane: the column left of the CTU
     static constexpr int kTmpElems = 66 * 66 / 2 + 65 * 65 * 2 + 16; // HTDF: ring-extended copy of the CU (int16) + four outputs per 2x2 window (4 x int16)
     static constexpr int kNbElems = 3 * (2 * 128 + 8);              // up[-1..w+h), left[-1..w+h), right[-1..w+h)
     static constexpr int kCuStage = 256;                            // CU descriptors + extension records staged on chip (the rest stay in L2)
-    static size_t bytes()
+    static size_t bytes(int log2_ctu)
     {
-        return sizeof(int16_t) * (2 * kPlaneElems + 3 * kTopElems + 3 * kLeftElems + 3 * kNbElems) + sizeof(int) * kTmpElems +
+        return sizeof(int16_t) * (2 * plane_elems(log2_ctu) + 3 * kTopElems + 3 * kLeftElems + 3 * kNbElems) + sizeof(int) * kTmpElems +
                kCuStage * (sizeof(XB200_CU) + sizeof(XB200_CU_EXT)) + 64;
     }
 };
@@ -353,14 +356,16 @@ __global__ void __launch_bounds__(kIntraThreads, 1)
 k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int16_t *s_rec = (int16_t *)smem_raw;
-    int16_t *s_res = s_rec + IntraSmem::kPlaneElems;
-    int16_t *s_top = s_res + IntraSmem::kPlaneElems;
-    int16_t *s_left = s_top + 3 * IntraSmem::kTopElems;
-    int16_t *s_nb = s_left + 3 * IntraSmem::kLeftElems;
-    int *s_tmp = (int *)(s_nb + 3 * IntraSmem::kNbElems);
+    // the arrays of fixed size first, at compile-time offsets (the CU chain is bound by its instruction count: run-time offsets for all of them
+    // cost 9 % on an I picture); only the residual array behind the CTU-sized sample array sits at an offset computed from log2_ctu
+    int *s_tmp = (int *)smem_raw;
     XB200_CU *s_cu = (XB200_CU *)(s_tmp + IntraSmem::kTmpElems);
     XB200_CU_EXT *s_ext = (XB200_CU_EXT *)(s_cu + IntraSmem::kCuStage);
+    int16_t *s_top = (int16_t *)(s_ext + IntraSmem::kCuStage);
+    int16_t *s_left = s_top + 3 * IntraSmem::kTopElems;
+    int16_t *s_nb = s_left + 3 * IntraSmem::kLeftElems;
+    int16_t *s_rec = s_nb + 3 * IntraSmem::kNbElems;
+    int16_t *s_res = s_rec + IntraSmem::plane_elems(a.log2_ctu);
     __shared__ int s_ctu, s_scr12[12], s_inter_all;
     __shared__ unsigned s_req[4], s_has[4];
     const int tid = threadIdx.x;
