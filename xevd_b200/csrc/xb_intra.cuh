@@ -352,7 +352,7 @@ struct IntraSync {
 };
 
 template <bool IQT>
-__global__ void __launch_bounds__(kIntraThreads, 1)
+__global__ void __launch_bounds__(kIntraThreads, 2)      // two CTAs per SM with CTUs of 64 samples and less (IntraSmem): at most 128 registers
 k_recon_intra(const __grid_constant__ XbFrameArgs a, const IntraSync sy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
